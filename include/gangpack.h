@@ -1,0 +1,180 @@
+/*
+ * gangpack.h -- C ABI of libgangpack.so, the B200-native gang-scheduling bin-packer.
+ *
+ * This is the drop-in boundary for ONE hot path of palantir/k8s-spark-scheduler: what a cgo shim
+ * registered in internal/binpacker.binpackFunctions (internal/binpacker/binpack.go:43-49) binds in
+ * place of binpack.TightlyPack / binpack.DistributeEvenly
+ * (vendor/github.com/palantir/k8s-spark-scheduler-lib/pkg/binpack/pack_tightly.go:25-32,
+ *  distribute_evenly.go:25-32; contract binpack.SparkBinPackFunction, binpack.go:43-48) and what a
+ * batched fitEarlierDrivers (internal/extender/resource.go:224-262) calls once per Predicate.
+ * The reference-side binding is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no exceptions cross the boundary; every call returns a
+ *    gp_status (0 = ok) and gp_last_error() describes the last failure on that context.
+ *  - Quantities are exact int64: CPU in millicores (Quantity.MilliValue), memory in bytes, GPU in
+ *    units -- the int64 model of resource.Quantity.  Inputs that are not
+ *    representable that way must be routed by the caller to the original Go packer.
+ *  - Nodes are addressed by index into the caller's node table; names never cross the boundary.
+ *  - A gp_ctx is NOT thread-safe (one per calling goroutine role, or a mutex), owns one CUDA
+ *    stream, and there is NO CPU fallback: if no CUDA device is usable gp_create fails.
+ */
+#ifndef GANGPACK_H
+#define GANGPACK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_ABI_VERSION 1
+
+typedef struct gp_ctx gp_ctx;
+
+typedef enum {
+    GP_OK = 0,
+    GP_ERR_INVALID = 1,       /* bad argument / precondition (negative request, index out of range, duplicate in an order ...) */
+    GP_ERR_CUDA = 2,          /* CUDA runtime error; message in gp_last_error */
+    GP_ERR_NO_DEVICE = 3,     /* no usable sm_100 device: the library has no CPU path */
+    GP_ERR_NO_SNAPSHOT = 4,   /* gp_pack_* before gp_set_snapshot */
+    GP_ERR_CAPACITY = 5,      /* result buffer too small */
+    GP_ERR_UNREPRESENTABLE = 6 /* quantity outside the exact-int64 domain (|v| >= 2^61) */
+} gp_status;
+
+/* binpack algorithm: the `binpack:` config values of internal/binpacker/binpack.go:21-24 */
+typedef enum {
+    GP_TIGHTLY_PACK = 0,      /* "tightly-pack"      -> pack_tightly.go:34-63, ExecutorNodes node-major  */
+    GP_DISTRIBUTE_EVENLY = 1  /* "distribute-evenly" -> distribute_evenly.go:34-73, round-major (also the
+                                 fallback for unknown names, binpack.go:52-57) */
+} gp_algo;
+
+typedef enum {
+    /* every app is packed against the same unmodified snapshot: the shape of
+       internal/extender/unschedulablepods.go:132-166 and of each Predicate's own pack (resource.go:321) */
+    GP_MODE_INDEPENDENT = 0,
+    /* fitEarlierDrivers (resource.go:224-262): apps in queue order per instance group against a
+       MUTATING snapshot, usage charged like sparkResourceUsage (sparkpods.go:139-146: each distinct
+       executor node one executor; a driver node that hosts an executor is charged the executor only) */
+    GP_MODE_FIFO_REFERENCE = 1,
+    /* same loop with exact accounting (driver + every executor charged), i.e. what separate
+       Predicate calls converge to through UsageForNodes (resources.go:31-43) */
+    GP_MODE_FIFO_EXACT = 2
+} gp_mode;
+
+typedef struct {
+    int32_t device;          /* CUDA device ordinal; -1 = current device */
+    int32_t reserved[7];
+} gp_config;
+
+/* The node snapshot (NodeGroupSchedulingMetadata.AvailableResources, resources.go:61-100) plus the
+ * two priority orders of NodeSorter.PotentialNodes (internal/sort/nodesorting.go:41-64), per
+ * instance group.  Group g owns exec_order[exec_off[g]..exec_off[g+1]) and
+ * drv_order[drv_off[g]..drv_off[g+1]); entries are indices into the node table, without
+ * duplicates inside a group.  A driver candidate need not be an executor candidate.
+ * Names absent from the metadata map are simply omitted by the caller (binpack.go:68-69,
+ * pack_tightly.go:51-52: they can neither host a driver nor an executor). */
+typedef struct {
+    int32_t n_nodes;
+    const int64_t* avail_cpu_milli;  /* [n_nodes] may be negative (over-committed node) */
+    const int64_t* avail_mem_bytes;  /* [n_nodes] */
+    const int64_t* avail_gpu;        /* [n_nodes] or NULL (= all zero) */
+    int32_t n_groups;                /* >= 1 */
+    const int32_t* exec_off;         /* [n_groups+1] */
+    const int32_t* exec_order;       /* [exec_off[n_groups]] */
+    const int32_t* drv_off;          /* [n_groups+1] */
+    const int32_t* drv_order;        /* [drv_off[n_groups]] */
+} gp_nodes;
+
+/* The pending-application queue (types.SparkApplicationResources, internal/types/types.go:22-27, as
+ * produced by sparkResources, internal/extender/sparkpods.go:73-137): SoA, queue order = index
+ * order (creation-time ascending, sparkpods.go:67-69).  All requests must be >= 0. */
+typedef struct {
+    int32_t n_apps;
+    const int64_t* drv_cpu_milli;    /* [n_apps] driver resources */
+    const int64_t* drv_mem_bytes;
+    const int64_t* drv_gpu;          /* or NULL (= 0) */
+    const int64_t* exe_cpu_milli;    /* [n_apps] per-executor resources */
+    const int64_t* exe_mem_bytes;
+    const int64_t* exe_gpu;          /* or NULL (= 0) */
+    const int32_t* exe_count;        /* [n_apps] MinExecutorCount (resource.go:242,325); >= 0 */
+    const int32_t* group;            /* [n_apps] instance group, or NULL (= 0) */
+    const uint8_t* skip_if_no_fit;   /* [n_apps] FIFO only: shouldSkipDriverFifo (resource.go:264-270), or NULL */
+    const int64_t* exec_out_off;     /* [n_apps+1] exclusive prefix sum of exe_count, or NULL (computed) */
+} gp_apps;
+
+/* binpack.PackingResult (binpack.go:25-30) for a batch.
+ *   driver_node[i] >= 0 : HasCapacity, DriverNode = that node index
+ *                  == -1: HasCapacity=false (EmptyPackingResult)
+ *                  == -2: not evaluated -- an earlier app of its group blocked the FIFO queue
+ *   executor_nodes[exec_out_off[i] .. +exe_count[i]) : ExecutorNodes, in the reference's order
+ *     (reservation names executor-1..k follow it, resourcereservations.go:501-510); untouched
+ *     unless driver_node[i] >= 0.
+ * PackingEfficiencies are not produced on the device (metrics by-product). */
+typedef struct {
+    int32_t* driver_node;            /* [n_apps] */
+    int32_t* executor_nodes;         /* [executor_nodes_cap] */
+    int64_t executor_nodes_cap;      /* entries available; must be >= sum(exe_count) */
+} gp_results;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int gp_abi_version(void);
+gp_status gp_create(gp_ctx** out, const gp_config* cfg /* may be NULL */);
+void gp_destroy(gp_ctx* ctx);
+const char* gp_last_error(const gp_ctx* ctx /* NULL = creation errors */);
+/* 1 = CUDA (the only backend).  Present so a shim can assert it is not on a silent fallback. */
+int gp_backend(const gp_ctx* ctx);
+
+/* Pinned host memory for the SoA buffers that cross the boundary (cudaHostAlloc); a Go caller
+ * wraps it with unsafe.Slice.  Pageable memory is accepted everywhere, just slower. */
+gp_status gp_alloc_pinned(gp_ctx* ctx, size_t bytes, void** out);
+gp_status gp_free_pinned(gp_ctx* ctx, void* p);
+
+/* ---- snapshot ------------------------------------------------------------------------------ */
+/* Validates, copies to the device and lays the snapshot out in executor-priority order. */
+gp_status gp_set_snapshot(gp_ctx* ctx, const gp_nodes* nodes);
+/* Current device snapshot back in node-table order (after FIFO modes: with the usage subtracted,
+ * i.e. metadata after SubtractUsageIfExists, resources.go:129-135).  Any pointer may be NULL. */
+gp_status gp_get_snapshot(gp_ctx* ctx, int64_t* avail_cpu_milli, int64_t* avail_mem_bytes, int64_t* avail_gpu);
+
+/* ---- packing ------------------------------------------------------------------------------- */
+/* One batch through the hot path with HOST buffers: H2D of the app SoA, kernels, D2H of the
+ * results; returns when the results are in host memory.  FIFO modes mutate the device snapshot. */
+gp_status gp_pack_batch(gp_ctx* ctx, const gp_apps* apps, gp_algo algo, gp_mode mode, gp_results* out);
+
+/* binpack.SparkBinPackFunction for one application (group 0 of the snapshot).
+ * Returns GP_OK and *has_capacity; executor_nodes must hold exe_count entries. */
+gp_status gp_pack_one(gp_ctx* ctx, gp_algo algo,
+                      int64_t drv_cpu_milli, int64_t drv_mem_bytes, int64_t drv_gpu,
+                      int64_t exe_cpu_milli, int64_t exe_mem_bytes, int64_t exe_gpu,
+                      int32_t exe_count, int32_t* has_capacity, int32_t* driver_node, int32_t* executor_nodes);
+
+/* ---- device-resident entry points (multi-GPU plumbing, kernel-only timing) ----------------- */
+/* Same as gp_set_snapshot / gp_pack_batch but every array pointer inside gp_nodes / gp_apps /
+ * gp_results is a DEVICE pointer on ctx's device (exec_out_off is then mandatory; group and
+ * skip_if_no_fit may still be NULL) and nothing is copied or validated on the host.  Work is
+ * enqueued on `stream` (a cudaStream_t; NULL = the context's stream) and NOT synchronised.
+ * gp_set_snapshot_device keeps no reference to the caller's arrays after it returns. */
+gp_status gp_set_snapshot_device(gp_ctx* ctx, const gp_nodes* dev_nodes, void* stream);
+gp_status gp_pack_batch_device(gp_ctx* ctx, const gp_apps* dev_apps, gp_algo algo, gp_mode mode,
+                               gp_results* dev_out, void* stream);
+/* the context's own stream (cudaStream_t) so callers can order their work / record events on it */
+void* gp_stream(gp_ctx* ctx);
+gp_status gp_synchronize(gp_ctx* ctx);
+
+/* Statistics of the last gp_pack_batch* on this context (host call, synchronises the stream):
+ * nodes_scanned = executor-order entries visited, drivers_tried = driver-order entries visited,
+ * summed over apps -- the N_e / N_d of the algorithmic-bytes formula. */
+typedef struct {
+    int64_t nodes_scanned;
+    int64_t drivers_tried;
+    int64_t kernel_launches;   /* launches of this library's kernels in that call */
+    int64_t reserved[5];
+} gp_stats;
+gp_status gp_last_stats(gp_ctx* ctx, gp_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANGPACK_H */

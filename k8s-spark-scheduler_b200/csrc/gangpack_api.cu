@@ -1,0 +1,694 @@
+// gangpack_api.cu -- global kernels + the C ABI of include/gangpack.h.
+// There is no CPU code path in this library: without a usable CUDA device gp_create fails.
+#include "gangpack.h"
+#include "gangpack_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace gp;
+
+// =============================================================================================
+// kernels
+// =============================================================================================
+
+// Thread per application: validate, derive the division magics and the driver-displacement bound.
+// Source tuple: types.SparkApplicationResources (internal/types/types.go:22-27).
+__global__ void gp_prep_apps(int32_t n_apps,
+                             const int64_t* __restrict__ d_cpu, const int64_t* __restrict__ d_mem, const int64_t* __restrict__ d_gpu,
+                             const int64_t* __restrict__ e_cpu, const int64_t* __restrict__ e_mem, const int64_t* __restrict__ e_gpu,
+                             const int32_t* __restrict__ count, const int32_t* __restrict__ group,
+                             const uint8_t* __restrict__ skip, const int64_t* __restrict__ out_off,
+                             int32_t n_groups, int64_t out_cap,
+                             PrepApp* __restrict__ prep, int* __restrict__ err) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_apps) return;
+    int64_t d[3] = {d_cpu[i], d_mem[i], d_gpu ? d_gpu[i] : 0};
+    int64_t e[3] = {e_cpu[i], e_mem[i], e_gpu ? e_gpu[i] : 0};
+    int32_t k = count[i];
+    int32_t g = group ? group[i] : 0;
+    int bad = 0;
+    if (k < 0) bad |= kErrNegativeRequest;
+    if (k > kMaxCount) bad |= kErrUnrepresentable;
+    if (g < 0 || g >= n_groups) bad |= kErrBadGroup;
+    int64_t off = out_off[i];
+    if (off < 0 || out_off[i + 1] - off != (int64_t)k || out_off[i + 1] > out_cap) bad |= kErrBadOffsets;
+    PrepApp p;
+    uint64_t lmax = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        if (d[t] < 0 || e[t] < 0) bad |= kErrNegativeRequest;
+        if (d[t] >= kMaxQuantity || e[t] >= kMaxQuantity) bad |= kErrUnrepresentable;
+        p.drv[t] = d[t];
+        DimDiv dv;
+        dv.e = e[t]; dv.magic = 0; dv.sh = 0; dv.kind = kDivInf;
+        if (e[t] > 0) {
+            uint32_t sh = (uint32_t)(__ffsll((long long)e[t]) - 1);
+            uint64_t odd = (uint64_t)e[t] >> sh;
+            dv.sh = sh;
+            if (odd == 1) dv.kind = kDivShift;
+            else if ((odd >> 32) == 0) { dv.kind = kDivMagic; dv.magic = 0xFFFFFFFFFFFFFFFFull / odd + 1; }
+            else { dv.kind = kDivSlow; dv.sh = 0; }
+            // a driver of d displaces at most ceil(d/e) executors in this dimension
+            if (d[t] > 0) {
+                uint64_t l = ((uint64_t)d[t] + (uint64_t)e[t] - 1) / (uint64_t)e[t];
+                if (l > lmax) lmax = l;
+            }
+        }
+        p.div[t] = dv;
+    }
+    if (bad) { atomicOr(err, bad); k = 0; g = 0; }
+    p.out_off = off;
+    p.count = k;
+    p.group = g;
+    p.lmax = (int32_t)(lmax < (uint64_t)k ? lmax : (uint64_t)k);
+    p.flags = ((d[2] != 0 || e[2] != 0) ? 1u : 0u) | ((skip && skip[i]) ? 2u : 0u) | (bad ? 4u : 0u);
+    prep[i] = p;
+}
+
+// Independent mode (GP_MODE_INDEPENDENT): one warp per application, grid-stride over the batch.
+template <int ALGO>
+__global__ void __launch_bounds__(256) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+                                                           int32_t* __restrict__ driver_node,
+                                                           int32_t* __restrict__ executor_nodes,
+                                                           int2* __restrict__ scratch,
+                                                           unsigned long long* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    WarpStats st{0, 0};
+    for (int32_t i = warp; i < n_apps; i += n_warps) {
+        const PrepApp* pa = prep + i;
+        int32_t d = -1;
+        if (!(pa->flags & 4u)) d = pack_app<ALGO, 0>(s, pa, executor_nodes, scratch, st, lane);
+        if (lane == 0) driver_node[i] = d;
+    }
+    if (lane == 0) {
+        atomicAdd(stats + 0, st.nodes);
+        atomicAdd(stats + 1, st.drivers);
+    }
+}
+
+// FIFO modes: one warp per instance group walks ITS applications in queue order against the
+// mutating snapshot (fitEarlierDrivers, internal/extender/resource.go:224-262).
+template <int ALGO, int FIFO_MODE>
+__global__ void __launch_bounds__(32) gp_pack_fifo(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+                                                   int32_t* __restrict__ driver_node,
+                                                   int32_t* __restrict__ executor_nodes,
+                                                   int2* __restrict__ scratch,
+                                                   unsigned long long* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int32_t grp = blockIdx.x;
+    WarpStats st{0, 0};
+    bool blocked = false;
+    for (int32_t i0 = 0; i0 < n_apps; i0 += kWarp) {
+        int32_t i = i0 + lane;
+        bool mine = (i < n_apps) && (prep[i].group == grp);
+        unsigned m = __ballot_sync(kFull, mine);
+        while (m) {
+            int src = __ffs(m) - 1;
+            m &= m - 1;
+            int32_t app = i0 + src;
+            const PrepApp* pa = prep + app;
+            int32_t d;
+            if (blocked) d = -2;                                   // never evaluated (resource.go:252)
+            else {
+                d = -1;
+                if (!(pa->flags & 4u)) d = pack_app<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, st, lane);
+                if (d < 0 && !(pa->flags & 2u)) blocked = true;   // resource.go:244-253
+            }
+            if (lane == 0) driver_node[app] = d;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(stats + 0, st.nodes);
+        atomicAdd(stats + 1, st.drivers);
+    }
+}
+
+// ---- snapshot construction -------------------------------------------------------------------
+__device__ __forceinline__ int32_t find_group(const int32_t* off, int32_t n_groups, int32_t idx) {
+    int32_t lo = 0, hi = n_groups - 1;
+    while (lo < hi) {
+        int32_t mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= idx) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void gp_build_groups(int32_t n_groups, const int32_t* __restrict__ exec_off, const int32_t* __restrict__ drv_off,
+                                GroupDesc* __restrict__ groups) {
+    int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    GroupDesc d;
+    d.sbase = exec_off[g] + drv_off[g];
+    d.ne = exec_off[g + 1] - exec_off[g];
+    d.dbase = drv_off[g];
+    d.nd = drv_off[g + 1] - drv_off[g];
+    groups[g] = d;
+}
+
+// executor-order entries -> slots [sbase, sbase+ne)
+__global__ void gp_build_exec_slots(int32_t n_exec, int32_t n_groups,
+                                    const int32_t* __restrict__ exec_off, const int32_t* __restrict__ drv_off,
+                                    const int32_t* __restrict__ exec_order,
+                                    const int64_t* __restrict__ cpu, const int64_t* __restrict__ mem, const int64_t* __restrict__ gpu,
+                                    longlong2* __restrict__ pair, int64_t* __restrict__ sgpu, int32_t* __restrict__ slot_node,
+                                    int32_t* __restrict__ node_slot, int* __restrict__ flags) {
+    int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_exec) return;
+    int32_t g = find_group(exec_off, n_groups, e);
+    int32_t slot = exec_off[g] + drv_off[g] + (e - exec_off[g]);
+    int32_t node = exec_order[e];
+    pair[slot] = make_longlong2(cpu[node], mem[node]);
+    int64_t gv = gpu ? gpu[node] : 0;
+    sgpu[slot] = gv;
+    if (gv < 0) atomicOr(flags, kSnapGpuNegative);
+    slot_node[slot] = node;
+    node_slot[node] = slot;
+}
+
+// driver-order entries -> group-local slot (an executor slot, or the spare slot ne + j)
+__global__ void gp_build_driver_slots(int32_t n_drv, int32_t n_groups,
+                                      const int32_t* __restrict__ exec_off, const int32_t* __restrict__ drv_off,
+                                      const int32_t* __restrict__ drv_order,
+                                      const int64_t* __restrict__ cpu, const int64_t* __restrict__ mem, const int64_t* __restrict__ gpu,
+                                      longlong2* __restrict__ pair, int64_t* __restrict__ sgpu, int32_t* __restrict__ slot_node,
+                                      const int32_t* __restrict__ node_slot, int32_t* __restrict__ drv_slot, int* __restrict__ flags) {
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_drv) return;
+    int32_t g = find_group(drv_off, n_groups, j);
+    int32_t sbase = exec_off[g] + drv_off[g];
+    int32_t ne = exec_off[g + 1] - exec_off[g];
+    int32_t node = drv_order[j];
+    int32_t ns = node_slot[node];
+    if (ns >= sbase && ns < sbase + ne) {
+        drv_slot[j] = ns - sbase;
+    } else {
+        int32_t local = ne + (j - drv_off[g]);
+        int32_t slot = sbase + local;
+        pair[slot] = make_longlong2(cpu[node], mem[node]);
+        int64_t gv = gpu ? gpu[node] : 0;
+        sgpu[slot] = gv;
+        if (gv < 0) atomicOr(flags, kSnapGpuNegative);
+        slot_node[slot] = node;
+        drv_slot[j] = local;
+    }
+}
+
+// slots -> node-table order (gp_get_snapshot)
+__global__ void gp_scatter_slots(int32_t n_slots, const longlong2* __restrict__ pair, const int64_t* __restrict__ sgpu,
+                                 const int32_t* __restrict__ slot_node,
+                                 int64_t* __restrict__ cpu, int64_t* __restrict__ mem, int64_t* __restrict__ gpu) {
+    int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    int32_t node = slot_node[s];
+    if (node < 0) return;
+    longlong2 v = pair[s];
+    cpu[node] = v.x; mem[node] = v.y; gpu[node] = sgpu[s];
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct gp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // snapshot
+    bool have_snapshot = false;
+    int32_t n_nodes = 0, n_groups = 0, n_exec = 0, n_drv = 0, n_slots = 0;
+    DevBuf node_cpu, node_mem, node_gpu;        // node-table order (as given)
+    DevBuf exec_off, drv_off, exec_order, drv_order;
+    DevBuf pair, sgpu, slot_node, node_slot, drv_slot, groups, snap_flags;
+
+    // batch staging
+    DevBuf a_dcpu, a_dmem, a_dgpu, a_ecpu, a_emem, a_egpu, a_count, a_group, a_skip, a_off;
+    DevBuf prep, r_driver, r_exec, scratch, dev_misc;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
+    void* pinned_misc = nullptr;                         // 32 B pinned mirror of dev_misc
+    std::vector<int64_t> host_off;
+
+    gp_stats last{};
+};
+
+static thread_local std::string g_create_error;
+
+#define GP_CUDA(ctx, expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                   \
+            return GP_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+static gp_status fail(gp_ctx* ctx, gp_status st, const std::string& msg) {
+    ctx->err = msg;
+    return st;
+}
+
+static Snapshot make_snapshot(const gp_ctx* c) {
+    Snapshot s;
+    s.pair = c->pair.as<longlong2>();
+    s.gpu = c->sgpu.as<int64_t>();
+    s.slot_node = c->slot_node.as<int32_t>();
+    s.drv_slot = c->drv_slot.as<int32_t>();
+    s.groups = c->groups.as<GroupDesc>();
+    s.flags = c->snap_flags.as<int>();
+    s.n_groups = c->n_groups;
+    s.n_slots = c->n_slots;
+    return s;
+}
+
+extern "C" {
+
+int gp_abi_version(void) { return GP_ABI_VERSION; }
+
+const char* gp_last_error(const gp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gp_backend(const gp_ctx* ctx) { return ctx ? 1 : 0; }
+
+gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
+    if (!out) { g_create_error = "gp_create: out is NULL"; return GP_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("gp_create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); libgangpack has no CPU path";
+        return GP_ERR_NO_DEVICE;
+    }
+    int dev = (cfg && cfg->device >= 0) ? cfg->device : -1;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= n) { g_create_error = "gp_create: device ordinal out of range"; return GP_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) {
+        g_create_error = std::string("gp_create: cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return GP_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "gp_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                         "; this library ships sm_100a code only";
+        return GP_ERR_NO_DEVICE;
+    }
+    gp_ctx* c = new (std::nothrow) gp_ctx();
+    if (!c) { g_create_error = "gp_create: out of memory"; return GP_ERR_INVALID; }
+    c->device = dev;
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(dev)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaHostAlloc(&c->pinned_misc, 64, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = c->dev_misc.reserve(64)) != cudaSuccess || (e = c->snap_flags.reserve(16)) != cudaSuccess) {
+        g_create_error = std::string("gp_create: ") + cudaGetErrorString(e);
+        delete c;
+        return GP_ERR_CUDA;
+    }
+    *out = c;
+    return GP_OK;
+}
+
+void gp_destroy(gp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->node_cpu, &c->node_mem, &c->node_gpu, &c->exec_off, &c->drv_off, &c->exec_order, &c->drv_order,
+                      &c->pair, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
+                      &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
+                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc};
+    for (DevBuf* b : bufs) b->release();
+    if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+gp_status gp_alloc_pinned(gp_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return GP_ERR_INVALID;
+    GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    GP_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return GP_OK;
+}
+
+gp_status gp_free_pinned(gp_ctx* ctx, void* p) {
+    if (!ctx) return GP_ERR_INVALID;
+    if (p) GP_CUDA(ctx, cudaFreeHost(p));
+    return GP_OK;
+}
+
+void* gp_stream(gp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+gp_status gp_synchronize(gp_ctx* ctx) {
+    if (!ctx) return GP_ERR_INVALID;
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GP_OK;
+}
+
+}  // extern "C"
+
+// ---- snapshot ---------------------------------------------------------------------------------
+
+// Build the slot layout from DEVICE-resident gp_nodes arrays on `st`.
+static gp_status build_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_exec, int32_t n_drv, cudaStream_t st) {
+    const int32_t n_slots = n_exec + n_drv;
+    GP_CUDA(c, c->pair.reserve(sizeof(longlong2) * (size_t)(n_slots + 1)));
+    GP_CUDA(c, c->sgpu.reserve(sizeof(int64_t) * (size_t)(n_slots + 1)));
+    GP_CUDA(c, c->slot_node.reserve(sizeof(int32_t) * (size_t)(n_slots + 1)));
+    GP_CUDA(c, c->node_slot.reserve(sizeof(int32_t) * (size_t)(dn->n_nodes + 1)));
+    GP_CUDA(c, c->drv_slot.reserve(sizeof(int32_t) * (size_t)(n_drv + 1)));
+    GP_CUDA(c, c->groups.reserve(sizeof(GroupDesc) * (size_t)dn->n_groups));
+    GP_CUDA(c, cudaMemsetAsync(c->slot_node.p, 0xFF, sizeof(int32_t) * (size_t)(n_slots + 1), st));
+    GP_CUDA(c, cudaMemsetAsync(c->node_slot.p, 0xFF, sizeof(int32_t) * (size_t)(dn->n_nodes + 1), st));
+    GP_CUDA(c, cudaMemsetAsync(c->snap_flags.p, 0, sizeof(int), st));
+    const int T = 256;
+    gp_build_groups<<<(dn->n_groups + T - 1) / T, T, 0, st>>>(dn->n_groups, dn->exec_off, dn->drv_off, c->groups.as<GroupDesc>());
+    if (n_exec > 0)
+        gp_build_exec_slots<<<(n_exec + T - 1) / T, T, 0, st>>>(
+            n_exec, dn->n_groups, dn->exec_off, dn->drv_off, dn->exec_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
+            dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
+            c->node_slot.as<int32_t>(), c->snap_flags.as<int>());
+    if (n_drv > 0)
+        gp_build_driver_slots<<<(n_drv + T - 1) / T, T, 0, st>>>(
+            n_drv, dn->n_groups, dn->exec_off, dn->drv_off, dn->drv_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
+            dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
+            c->node_slot.as<int32_t>(), c->drv_slot.as<int32_t>(), c->snap_flags.as<int>());
+    GP_CUDA(c, cudaGetLastError());
+    c->n_nodes = dn->n_nodes; c->n_groups = dn->n_groups; c->n_exec = n_exec; c->n_drv = n_drv; c->n_slots = n_slots;
+    c->have_snapshot = true;
+    return GP_OK;
+}
+
+extern "C" {
+
+gp_status gp_set_snapshot(gp_ctx* c, const gp_nodes* n) {
+    if (!c) return GP_ERR_INVALID;
+    if (!n || n->n_nodes < 0 || n->n_groups < 1 || !n->exec_off || !n->drv_off ||
+        (n->n_nodes > 0 && (!n->avail_cpu_milli || !n->avail_mem_bytes)))
+        return fail(c, GP_ERR_INVALID, "gp_set_snapshot: missing arrays or bad sizes");
+    // ---- host validation (O(N)): offsets monotone, indices in range, one group per node, domain
+    const int32_t G = n->n_groups;
+    if (n->exec_off[0] != 0 || n->drv_off[0] != 0) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: offsets must start at 0");
+    for (int32_t g = 0; g < G; ++g)
+        if (n->exec_off[g + 1] < n->exec_off[g] || n->drv_off[g + 1] < n->drv_off[g])
+            return fail(c, GP_ERR_INVALID, "gp_set_snapshot: offsets not monotone");
+    const int32_t n_exec = n->exec_off[G], n_drv = n->drv_off[G];
+    if ((n_exec > 0 && !n->exec_order) || (n_drv > 0 && !n->drv_order))
+        return fail(c, GP_ERR_INVALID, "gp_set_snapshot: order arrays missing");
+    {
+        std::vector<int32_t> owner((size_t)n->n_nodes, -1);
+        std::vector<uint8_t> seen_e((size_t)n->n_nodes, 0), seen_d((size_t)n->n_nodes, 0);
+        for (int32_t g = 0; g < G; ++g) {
+            for (int32_t e = n->exec_off[g]; e < n->exec_off[g + 1]; ++e) {
+                int32_t v = n->exec_order[e];
+                if (v < 0 || v >= n->n_nodes) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: exec_order index out of range");
+                if (seen_e[v]) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node listed twice in executor orders");
+                seen_e[v] = 1; owner[v] = g;
+            }
+            for (int32_t d = n->drv_off[g]; d < n->drv_off[g + 1]; ++d) {
+                int32_t v = n->drv_order[d];
+                if (v < 0 || v >= n->n_nodes) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: drv_order index out of range");
+                if (seen_d[v]) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node listed twice in driver orders");
+                if (owner[v] >= 0 && owner[v] != g)
+                    return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node belongs to two instance groups");
+                seen_d[v] = 1; owner[v] = g;
+            }
+        }
+        for (int32_t i = 0; i < n->n_nodes; ++i) {
+            int64_t a = n->avail_cpu_milli[i], b = n->avail_mem_bytes[i], g = n->avail_gpu ? n->avail_gpu[i] : 0;
+            if (a >= kMaxQuantity || a <= -kMaxQuantity || b >= kMaxQuantity || b <= -kMaxQuantity ||
+                g >= kMaxQuantity || g <= -kMaxQuantity)
+                return fail(c, GP_ERR_UNREPRESENTABLE, "gp_set_snapshot: |quantity| >= 2^61");
+        }
+    }
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t nb = sizeof(int64_t) * (size_t)(n->n_nodes + 1);
+    GP_CUDA(c, c->node_cpu.reserve(nb)); GP_CUDA(c, c->node_mem.reserve(nb)); GP_CUDA(c, c->node_gpu.reserve(nb));
+    GP_CUDA(c, c->exec_off.reserve(sizeof(int32_t) * (size_t)(G + 1)));
+    GP_CUDA(c, c->drv_off.reserve(sizeof(int32_t) * (size_t)(G + 1)));
+    GP_CUDA(c, c->exec_order.reserve(sizeof(int32_t) * (size_t)(n_exec + 1)));
+    GP_CUDA(c, c->drv_order.reserve(sizeof(int32_t) * (size_t)(n_drv + 1)));
+    const size_t vb = sizeof(int64_t) * (size_t)n->n_nodes;
+    if (vb) {
+        GP_CUDA(c, cudaMemcpyAsync(c->node_cpu.p, n->avail_cpu_milli, vb, cudaMemcpyHostToDevice, st));
+        GP_CUDA(c, cudaMemcpyAsync(c->node_mem.p, n->avail_mem_bytes, vb, cudaMemcpyHostToDevice, st));
+        if (n->avail_gpu) GP_CUDA(c, cudaMemcpyAsync(c->node_gpu.p, n->avail_gpu, vb, cudaMemcpyHostToDevice, st));
+        else GP_CUDA(c, cudaMemsetAsync(c->node_gpu.p, 0, vb, st));
+    }
+    GP_CUDA(c, cudaMemcpyAsync(c->exec_off.p, n->exec_off, sizeof(int32_t) * (size_t)(G + 1), cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(c->drv_off.p, n->drv_off, sizeof(int32_t) * (size_t)(G + 1), cudaMemcpyHostToDevice, st));
+    if (n_exec) GP_CUDA(c, cudaMemcpyAsync(c->exec_order.p, n->exec_order, sizeof(int32_t) * (size_t)n_exec, cudaMemcpyHostToDevice, st));
+    if (n_drv) GP_CUDA(c, cudaMemcpyAsync(c->drv_order.p, n->drv_order, sizeof(int32_t) * (size_t)n_drv, cudaMemcpyHostToDevice, st));
+    gp_nodes dn = *n;
+    dn.avail_cpu_milli = c->node_cpu.as<int64_t>(); dn.avail_mem_bytes = c->node_mem.as<int64_t>();
+    dn.avail_gpu = c->node_gpu.as<int64_t>();
+    dn.exec_off = c->exec_off.as<int32_t>(); dn.drv_off = c->drv_off.as<int32_t>();
+    dn.exec_order = c->exec_order.as<int32_t>(); dn.drv_order = c->drv_order.as<int32_t>();
+    gp_status s = build_snapshot_device(c, &dn, n_exec, n_drv, st);
+    if (s != GP_OK) return s;
+    GP_CUDA(c, cudaStreamSynchronize(st));   // the caller may reuse its host buffers
+    return GP_OK;
+}
+
+gp_status gp_set_snapshot_device(gp_ctx* c, const gp_nodes* dn, void* stream) {
+    if (!c) return GP_ERR_INVALID;
+    if (!dn || dn->n_nodes < 0 || dn->n_groups < 1 || !dn->exec_off || !dn->drv_off)
+        return fail(c, GP_ERR_INVALID, "gp_set_snapshot_device: missing arrays or bad sizes");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    // sizes live on the device: fetch the two totals (8 bytes) -- the only host round trip
+    int32_t n_exec = 0, n_drv = 0;
+    GP_CUDA(c, cudaMemcpyAsync(&n_exec, dn->exec_off + dn->n_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(&n_drv, dn->drv_off + dn->n_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    if (n_exec < 0 || n_drv < 0) return fail(c, GP_ERR_INVALID, "gp_set_snapshot_device: negative order length");
+    // keep a node-table copy so gp_get_snapshot can answer for nodes outside every group
+    const size_t nb = sizeof(int64_t) * (size_t)(dn->n_nodes + 1), vb = sizeof(int64_t) * (size_t)dn->n_nodes;
+    GP_CUDA(c, c->node_cpu.reserve(nb)); GP_CUDA(c, c->node_mem.reserve(nb)); GP_CUDA(c, c->node_gpu.reserve(nb));
+    if (vb) {
+        GP_CUDA(c, cudaMemcpyAsync(c->node_cpu.p, dn->avail_cpu_milli, vb, cudaMemcpyDeviceToDevice, st));
+        GP_CUDA(c, cudaMemcpyAsync(c->node_mem.p, dn->avail_mem_bytes, vb, cudaMemcpyDeviceToDevice, st));
+        if (dn->avail_gpu) GP_CUDA(c, cudaMemcpyAsync(c->node_gpu.p, dn->avail_gpu, vb, cudaMemcpyDeviceToDevice, st));
+        else GP_CUDA(c, cudaMemsetAsync(c->node_gpu.p, 0, vb, st));
+    }
+    return build_snapshot_device(c, dn, n_exec, n_drv, st);
+}
+
+gp_status gp_get_snapshot(gp_ctx* c, int64_t* cpu, int64_t* mem, int64_t* gpu) {
+    if (!c) return GP_ERR_INVALID;
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, "gp_get_snapshot: no snapshot");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int T = 256;
+    if (c->n_slots > 0)
+        gp_scatter_slots<<<(c->n_slots + T - 1) / T, T, 0, st>>>(c->n_slots, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(),
+                                                                c->slot_node.as<int32_t>(), c->node_cpu.as<int64_t>(),
+                                                                c->node_mem.as<int64_t>(), c->node_gpu.as<int64_t>());
+    GP_CUDA(c, cudaGetLastError());
+    const size_t vb = sizeof(int64_t) * (size_t)c->n_nodes;
+    if (vb) {
+        if (cpu) GP_CUDA(c, cudaMemcpyAsync(cpu, c->node_cpu.p, vb, cudaMemcpyDeviceToHost, st));
+        if (mem) GP_CUDA(c, cudaMemcpyAsync(mem, c->node_mem.p, vb, cudaMemcpyDeviceToHost, st));
+        if (gpu) GP_CUDA(c, cudaMemcpyAsync(gpu, c->node_gpu.p, vb, cudaMemcpyDeviceToHost, st));
+    }
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    return GP_OK;
+}
+
+}  // extern "C"
+
+// ---- packing ------------------------------------------------------------------------------------
+
+template <int ALGO>
+static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepApp* prep, int32_t n_apps,
+                        int32_t* driver_node, int32_t* executor_nodes, int2* scratch, unsigned long long* stats,
+                        cudaStream_t st) {
+    if (mode == GP_MODE_INDEPENDENT) {
+        const int T = 256;
+        int64_t warps_needed = n_apps;
+        int blocks = (int)((warps_needed * 32 + T - 1) / T);
+        int max_blocks = c->sm_count * 8;
+        if (blocks > max_blocks) blocks = max_blocks;
+        if (blocks < 1) blocks = 1;
+        gp_pack_independent<ALGO><<<blocks, T, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats);
+    } else if (mode == GP_MODE_FIFO_REFERENCE) {
+        gp_pack_fifo<ALGO, 1><<<s.n_groups, 32, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats);
+    } else {
+        gp_pack_fifo<ALGO, 2><<<s.n_groups, 32, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats);
+    }
+}
+
+// everything device-resident; enqueues prep + pack on `st`
+static gp_status pack_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode mode, gp_results* dout, cudaStream_t st) {
+    const int32_t q = da->n_apps;
+    int* d_err = c->dev_misc.as<int>();
+    unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(c->dev_misc.as<char>() + 8);
+    GP_CUDA(c, cudaMemsetAsync(c->dev_misc.p, 0, 32, st));
+    c->last = gp_stats{};
+    if (q == 0) return GP_OK;
+    GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));
+    int2* scratch = nullptr;
+    if (algo == GP_DISTRIBUTE_EVENLY) {
+        GP_CUDA(c, c->scratch.reserve(sizeof(int2) * (size_t)(dout->executor_nodes_cap + 1)));
+        scratch = c->scratch.as<int2>();
+    }
+    const int T = 256;
+    gp_prep_apps<<<(q + T - 1) / T, T, 0, st>>>(q, da->drv_cpu_milli, da->drv_mem_bytes, da->drv_gpu, da->exe_cpu_milli,
+                                                da->exe_mem_bytes, da->exe_gpu, da->exe_count, da->group,
+                                                da->skip_if_no_fit, da->exec_out_off, c->n_groups,
+                                                dout->executor_nodes_cap, c->prep.as<PrepApp>(), d_err);
+    Snapshot s = make_snapshot(c);
+    if (algo == GP_TIGHTLY_PACK)
+        launch_pack<0>(c, mode, s, c->prep.as<PrepApp>(), q, dout->driver_node, dout->executor_nodes, scratch, d_stats, st);
+    else
+        launch_pack<1>(c, mode, s, c->prep.as<PrepApp>(), q, dout->driver_node, dout->executor_nodes, scratch, d_stats, st);
+    GP_CUDA(c, cudaGetLastError());
+    c->last.kernel_launches = 2;
+    return GP_OK;
+}
+
+static gp_status check_args(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, const gp_results* out, const char* who) {
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, std::string(who) + ": gp_set_snapshot first");
+    if (!a || !out || a->n_apps < 0) return fail(c, GP_ERR_INVALID, std::string(who) + ": NULL apps/results");
+    if (algo != GP_TIGHTLY_PACK && algo != GP_DISTRIBUTE_EVENLY) return fail(c, GP_ERR_INVALID, std::string(who) + ": unknown algo");
+    if (mode != GP_MODE_INDEPENDENT && mode != GP_MODE_FIFO_REFERENCE && mode != GP_MODE_FIFO_EXACT)
+        return fail(c, GP_ERR_INVALID, std::string(who) + ": unknown mode");
+    if (a->n_apps > 0 && (!a->drv_cpu_milli || !a->drv_mem_bytes || !a->exe_cpu_milli || !a->exe_mem_bytes || !a->exe_count ||
+                          !out->driver_node))
+        return fail(c, GP_ERR_INVALID, std::string(who) + ": missing app/result arrays");
+    return GP_OK;
+}
+
+static gp_status decode_device_error(gp_ctx* c, int err) {
+    if (err == 0) return GP_OK;
+    if (err & kErrUnrepresentable) return fail(c, GP_ERR_UNREPRESENTABLE, "pack: quantity >= 2^61 or exe_count > 2^24");
+    if (err & kErrNegativeRequest) return fail(c, GP_ERR_INVALID, "pack: negative resource request or executor count");
+    if (err & kErrBadGroup) return fail(c, GP_ERR_INVALID, "pack: app group out of range");
+    return fail(c, GP_ERR_CAPACITY, "pack: exec_out_off inconsistent with exe_count or executor_nodes_cap too small");
+}
+
+extern "C" {
+
+gp_status gp_pack_batch_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode mode, gp_results* dout, void* stream) {
+    if (!c) return GP_ERR_INVALID;
+    gp_status s = check_args(c, da, algo, mode, dout, "gp_pack_batch_device");
+    if (s != GP_OK) return s;
+    if (da->n_apps > 0 && !da->exec_out_off) return fail(c, GP_ERR_INVALID, "gp_pack_batch_device: exec_out_off is mandatory");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    return pack_device(c, da, algo, mode, dout, stream ? (cudaStream_t)stream : c->stream);
+}
+
+gp_status gp_last_stats(gp_ctx* c, gp_stats* out) {
+    if (!c || !out) return GP_ERR_INVALID;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, cudaMemcpyAsync(c->pinned_misc, c->dev_misc.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>((const char*)c->pinned_misc + 8);
+    c->last.nodes_scanned = (int64_t)s[0];
+    c->last.drivers_tried = (int64_t)s[1];
+    *out = c->last;
+    int err = *reinterpret_cast<const int*>(c->pinned_misc);
+    return decode_device_error(c, err);
+}
+
+gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out) {
+    if (!c) return GP_ERR_INVALID;
+    gp_status s = check_args(c, a, algo, mode, out, "gp_pack_batch");
+    if (s != GP_OK) return s;
+    const int32_t q = a->n_apps;
+    if (q == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // ExecutorNodes offsets: the caller's CSR offsets, or computed here
+    const int64_t* off = a->exec_out_off;
+    if (!off) {
+        c->host_off.resize((size_t)q + 1);
+        int64_t acc = 0;
+        for (int32_t i = 0; i < q; ++i) { c->host_off[i] = acc; acc += a->exe_count[i] > 0 ? a->exe_count[i] : 0; }
+        c->host_off[q] = acc;
+        off = c->host_off.data();
+    }
+    const int64_t total = off[q];
+    if (total < 0 || total > out->executor_nodes_cap) return fail(c, GP_ERR_CAPACITY, "gp_pack_batch: executor_nodes_cap too small");
+    if (total > 0 && !out->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_batch: executor_nodes is NULL");
+
+    const size_t b64 = sizeof(int64_t) * (size_t)q, b32 = sizeof(int32_t) * (size_t)q;
+    GP_CUDA(c, c->a_dcpu.reserve(b64)); GP_CUDA(c, c->a_dmem.reserve(b64)); GP_CUDA(c, c->a_ecpu.reserve(b64));
+    GP_CUDA(c, c->a_emem.reserve(b64)); GP_CUDA(c, c->a_count.reserve(b32));
+    GP_CUDA(c, c->a_off.reserve(sizeof(int64_t) * (size_t)(q + 1)));
+    GP_CUDA(c, c->r_driver.reserve(b32));
+    GP_CUDA(c, c->r_exec.reserve(sizeof(int32_t) * (size_t)(total + 1)));
+    gp_apps da = *a;
+    GP_CUDA(c, cudaMemcpyAsync(c->a_dcpu.p, a->drv_cpu_milli, b64, cudaMemcpyHostToDevice, st)); da.drv_cpu_milli = c->a_dcpu.as<int64_t>();
+    GP_CUDA(c, cudaMemcpyAsync(c->a_dmem.p, a->drv_mem_bytes, b64, cudaMemcpyHostToDevice, st)); da.drv_mem_bytes = c->a_dmem.as<int64_t>();
+    GP_CUDA(c, cudaMemcpyAsync(c->a_ecpu.p, a->exe_cpu_milli, b64, cudaMemcpyHostToDevice, st)); da.exe_cpu_milli = c->a_ecpu.as<int64_t>();
+    GP_CUDA(c, cudaMemcpyAsync(c->a_emem.p, a->exe_mem_bytes, b64, cudaMemcpyHostToDevice, st)); da.exe_mem_bytes = c->a_emem.as<int64_t>();
+    GP_CUDA(c, cudaMemcpyAsync(c->a_count.p, a->exe_count, b32, cudaMemcpyHostToDevice, st)); da.exe_count = c->a_count.as<int32_t>();
+    GP_CUDA(c, cudaMemcpyAsync(c->a_off.p, off, sizeof(int64_t) * (size_t)(q + 1), cudaMemcpyHostToDevice, st)); da.exec_out_off = c->a_off.as<int64_t>();
+    if (a->drv_gpu) { GP_CUDA(c, c->a_dgpu.reserve(b64)); GP_CUDA(c, cudaMemcpyAsync(c->a_dgpu.p, a->drv_gpu, b64, cudaMemcpyHostToDevice, st)); da.drv_gpu = c->a_dgpu.as<int64_t>(); }
+    if (a->exe_gpu) { GP_CUDA(c, c->a_egpu.reserve(b64)); GP_CUDA(c, cudaMemcpyAsync(c->a_egpu.p, a->exe_gpu, b64, cudaMemcpyHostToDevice, st)); da.exe_gpu = c->a_egpu.as<int64_t>(); }
+    if (a->group) { GP_CUDA(c, c->a_group.reserve(b32)); GP_CUDA(c, cudaMemcpyAsync(c->a_group.p, a->group, b32, cudaMemcpyHostToDevice, st)); da.group = c->a_group.as<int32_t>(); }
+    if (a->skip_if_no_fit) { GP_CUDA(c, c->a_skip.reserve((size_t)q)); GP_CUDA(c, cudaMemcpyAsync(c->a_skip.p, a->skip_if_no_fit, (size_t)q, cudaMemcpyHostToDevice, st)); da.skip_if_no_fit = c->a_skip.as<uint8_t>(); }
+
+    gp_results dr;
+    dr.driver_node = c->r_driver.as<int32_t>();
+    dr.executor_nodes = c->r_exec.as<int32_t>();
+    dr.executor_nodes_cap = total;
+    s = pack_device(c, &da, algo, mode, &dr, st);
+    if (s != GP_OK) return s;
+    GP_CUDA(c, cudaMemcpyAsync(out->driver_node, dr.driver_node, b32, cudaMemcpyDeviceToHost, st));
+    if (total > 0) GP_CUDA(c, cudaMemcpyAsync(out->executor_nodes, dr.executor_nodes, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(c->pinned_misc, c->dev_misc.p, 32, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    const unsigned long long* sv = reinterpret_cast<const unsigned long long*>((const char*)c->pinned_misc + 8);
+    c->last.nodes_scanned = (int64_t)sv[0];
+    c->last.drivers_tried = (int64_t)sv[1];
+    return decode_device_error(c, *reinterpret_cast<const int*>(c->pinned_misc));
+}
+
+gp_status gp_pack_one(gp_ctx* c, gp_algo algo, int64_t drv_cpu, int64_t drv_mem, int64_t drv_gpu, int64_t exe_cpu,
+                      int64_t exe_mem, int64_t exe_gpu, int32_t exe_count, int32_t* has_capacity, int32_t* driver_node,
+                      int32_t* executor_nodes) {
+    if (!c) return GP_ERR_INVALID;
+    if (!has_capacity || !driver_node) return fail(c, GP_ERR_INVALID, "gp_pack_one: NULL outputs");
+    int64_t off[2] = {0, exe_count > 0 ? exe_count : 0};
+    gp_apps a{};
+    a.n_apps = 1;
+    a.drv_cpu_milli = &drv_cpu; a.drv_mem_bytes = &drv_mem; a.drv_gpu = &drv_gpu;
+    a.exe_cpu_milli = &exe_cpu; a.exe_mem_bytes = &exe_mem; a.exe_gpu = &exe_gpu;
+    a.exe_count = &exe_count;
+    a.exec_out_off = off;
+    gp_results r{};
+    int32_t d = -1;
+    r.driver_node = &d;
+    r.executor_nodes = executor_nodes;
+    r.executor_nodes_cap = off[1];
+    gp_status s = gp_pack_batch(c, &a, algo, GP_MODE_INDEPENDENT, &r);
+    if (s != GP_OK) return s;
+    *has_capacity = d >= 0 ? 1 : 0;
+    *driver_node = d >= 0 ? d : -1;
+    return GP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+"""ctypes binding of libgangpack.so (include/gangpack.h) -- the only compute path of this package.
+
+There is deliberately no CPU fallback here: if the shared library is missing or no sm_100 device is
+usable, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libgangpack.so")
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("gangpack_api.cu", "gangpack_kernels.cuh")] + [
+    os.path.join(_ROOT, "include", "gangpack.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+TIGHTLY_PACK = 0
+DISTRIBUTE_EVENLY = 1
+MODE_INDEPENDENT = 0
+MODE_FIFO_REFERENCE = 1
+MODE_FIFO_EXACT = 2
+
+STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO_DEVICE", 4: "GP_ERR_NO_SNAPSHOT",
+                5: "GP_ERR_CAPACITY", 6: "GP_ERR_UNREPRESENTABLE"}
+
+# every symbol include/gangpack.h declares (tests assert the .so exports exactly these)
+EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
+           "gp_free_pinned", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_one",
+           "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats"]
+
+
+class GangpackError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libgangpack.so")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into k8s-spark-scheduler_b200/libgangpack.so (in-tree)."""
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in _SOURCES)
+    if stale:
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, _SOURCES[0]]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class gp_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class gp_nodes(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("avail_cpu_milli", C.c_void_p), ("avail_mem_bytes", C.c_void_p),
+                ("avail_gpu", C.c_void_p), ("n_groups", C.c_int32), ("exec_off", C.c_void_p),
+                ("exec_order", C.c_void_p), ("drv_off", C.c_void_p), ("drv_order", C.c_void_p)]
+
+
+class gp_apps(C.Structure):
+    _fields_ = [("n_apps", C.c_int32), ("drv_cpu_milli", C.c_void_p), ("drv_mem_bytes", C.c_void_p),
+                ("drv_gpu", C.c_void_p), ("exe_cpu_milli", C.c_void_p), ("exe_mem_bytes", C.c_void_p),
+                ("exe_gpu", C.c_void_p), ("exe_count", C.c_void_p), ("group", C.c_void_p),
+                ("skip_if_no_fit", C.c_void_p), ("exec_out_off", C.c_void_p)]
+
+
+class gp_results(C.Structure):
+    _fields_ = [("driver_node", C.c_void_p), ("executor_nodes", C.c_void_p), ("executor_nodes_cap", C.c_int64)]
+
+
+class gp_stats(C.Structure):
+    _fields_ = [("nodes_scanned", C.c_int64), ("drivers_tried", C.c_int64), ("kernel_launches", C.c_int64),
+                ("reserved", C.c_int64 * 5)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libgangpack.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(this package has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.gp_abi_version.restype = C.c_int
+    L.gp_create.restype = C.c_int
+    L.gp_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(gp_config)]
+    L.gp_destroy.restype = None
+    L.gp_destroy.argtypes = [C.c_void_p]
+    L.gp_last_error.restype = C.c_char_p
+    L.gp_last_error.argtypes = [C.c_void_p]
+    L.gp_backend.restype = C.c_int
+    L.gp_backend.argtypes = [C.c_void_p]
+    L.gp_alloc_pinned.restype = C.c_int
+    L.gp_alloc_pinned.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.gp_free_pinned.restype = C.c_int
+    L.gp_free_pinned.argtypes = [C.c_void_p, C.c_void_p]
+    L.gp_set_snapshot.restype = C.c_int
+    L.gp_set_snapshot.argtypes = [C.c_void_p, C.POINTER(gp_nodes)]
+    L.gp_get_snapshot.restype = C.c_int
+    L.gp_get_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gp_pack_batch.restype = C.c_int
+    L.gp_pack_batch.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.c_int, C.POINTER(gp_results)]
+    L.gp_pack_one.restype = C.c_int
+    L.gp_pack_one.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 6 + [C.c_int32, C.POINTER(C.c_int32),
+                                                                          C.POINTER(C.c_int32), C.c_void_p]
+    L.gp_set_snapshot_device.restype = C.c_int
+    L.gp_set_snapshot_device.argtypes = [C.c_void_p, C.POINTER(gp_nodes), C.c_void_p]
+    L.gp_pack_batch_device.restype = C.c_int
+    L.gp_pack_batch_device.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.c_int, C.POINTER(gp_results), C.c_void_p]
+    L.gp_stream.restype = C.c_void_p
+    L.gp_stream.argtypes = [C.c_void_p]
+    L.gp_synchronize.restype = C.c_int
+    L.gp_synchronize.argtypes = [C.c_void_p]
+    L.gp_last_stats.restype = C.c_int
+    L.gp_last_stats.argtypes = [C.c_void_p, C.POINTER(gp_stats)]
+    _lib = L
+    return L
+
+
+def _np(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class PinnedArray:
+    """numpy view over gp_alloc_pinned memory."""
+
+    def __init__(self, packer: "GangPacker", shape, dtype):
+        self._packer = packer
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        self.nbytes = max(n * self.dtype.itemsize, 1)
+        ptr = C.c_void_p()
+        packer._check(load().gp_alloc_pinned(packer._h, self.nbytes, C.byref(ptr)))
+        self._ptr = ptr
+        buf = (C.c_char * self.nbytes).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=n).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None and self._packer._h:
+            self.array = None
+            load().gp_free_pinned(self._packer._h, self._ptr)
+            self._ptr = None
+
+
+class GangPacker:
+    """One gp_ctx.  Not thread-safe (like the C ABI)."""
+
+    def __init__(self, device: int = -1):
+        L = load()
+        self._h = C.c_void_p()
+        cfg = gp_config(device=device)
+        st = L.gp_create(C.byref(self._h), C.byref(cfg))
+        if st != 0:
+            raise GangpackError(st, (L.gp_last_error(None) or b"").decode())
+        self._keep = None
+        self._pinned = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for p in self._pinned:
+                p.free()
+            self._pinned = []
+            load().gp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != 0:
+            raise GangpackError(st, (load().gp_last_error(self._h) or b"").decode())
+
+    def pinned(self, shape, dtype) -> np.ndarray:
+        p = PinnedArray(self, shape, dtype)
+        self._pinned.append(p)
+        return p.array
+
+    # ---- snapshot ----------------------------------------------------------------------------
+    def set_snapshot(self, avail_cpu, avail_mem, avail_gpu, exec_order, drv_order, exec_off=None, drv_off=None):
+        cpu, mem = _np(avail_cpu, np.int64), _np(avail_mem, np.int64)
+        gpu = _np(avail_gpu, np.int64)
+        eo, do = _np(exec_order, np.int32), _np(drv_order, np.int32)
+        eoff = _np(exec_off if exec_off is not None else [0, len(eo)], np.int32)
+        doff = _np(drv_off if drv_off is not None else [0, len(do)], np.int32)
+        n = gp_nodes(n_nodes=len(cpu), avail_cpu_milli=_p(cpu), avail_mem_bytes=_p(mem), avail_gpu=_p(gpu),
+                     n_groups=len(eoff) - 1, exec_off=_p(eoff), exec_order=_p(eo), drv_off=_p(doff), drv_order=_p(do))
+        self._check(load().gp_set_snapshot(self._h, C.byref(n)))
+        self.n_nodes = len(cpu)
+
+    def get_snapshot(self):
+        cpu = np.empty(self.n_nodes, np.int64); mem = np.empty(self.n_nodes, np.int64); gpu = np.empty(self.n_nodes, np.int64)
+        self._check(load().gp_get_snapshot(self._h, _p(cpu), _p(mem), _p(gpu)))
+        return cpu, mem, gpu
+
+    # ---- packing -----------------------------------------------------------------------------
+    def pack_batch(self, apps: dict, algo: int, mode: int = MODE_INDEPENDENT, out=None):
+        """apps: dict with drv_cpu, drv_mem, [drv_gpu], exe_cpu, exe_mem, [exe_gpu], count, [group], [young],
+        [off].  Returns (driver_node[q], executor_nodes[sum count], off[q+1])."""
+        q = len(apps["count"])
+        count = _np(apps["count"], np.int32)
+        off = _np(apps.get("off"), np.int64)
+        if off is None:
+            off = np.zeros(q + 1, np.int64)
+            np.cumsum(np.maximum(count, 0), out=off[1:])
+        arrs = dict(
+            drv_cpu=_np(apps["drv_cpu"], np.int64), drv_mem=_np(apps["drv_mem"], np.int64),
+            drv_gpu=_np(apps.get("drv_gpu"), np.int64),
+            exe_cpu=_np(apps["exe_cpu"], np.int64), exe_mem=_np(apps["exe_mem"], np.int64),
+            exe_gpu=_np(apps.get("exe_gpu"), np.int64),
+            group=_np(apps.get("group"), np.int32), young=_np(apps.get("young"), np.uint8))
+        total = int(off[-1]) if q else 0
+        if out is None:
+            driver_node = np.full(q, -9, np.int32)
+            executor_nodes = np.full(max(total, 1), -9, np.int32)
+        else:
+            driver_node, executor_nodes = out
+        a = gp_apps(n_apps=q, drv_cpu_milli=_p(arrs["drv_cpu"]), drv_mem_bytes=_p(arrs["drv_mem"]),
+                    drv_gpu=_p(arrs["drv_gpu"]), exe_cpu_milli=_p(arrs["exe_cpu"]), exe_mem_bytes=_p(arrs["exe_mem"]),
+                    exe_gpu=_p(arrs["exe_gpu"]), exe_count=_p(count), group=_p(arrs["group"]),
+                    skip_if_no_fit=_p(arrs["young"]), exec_out_off=_p(off))
+        r = gp_results(driver_node=_p(driver_node), executor_nodes=_p(executor_nodes),
+                       executor_nodes_cap=len(executor_nodes))
+        self._check(load().gp_pack_batch(self._h, C.byref(a), algo, mode, C.byref(r)))
+        return driver_node, executor_nodes[:total], off
+
+    def pack_one(self, algo, drv, exe, count):
+        """binpack.SparkBinPackFunction for one app -> (has_capacity, driver_node, executor_nodes)."""
+        has = C.c_int32(0); d = C.c_int32(-1)
+        en = np.full(max(count, 1), -9, np.int32)
+        self._check(load().gp_pack_one(self._h, algo, int(drv[0]), int(drv[1]), int(drv[2]), int(exe[0]), int(exe[1]),
+                                       int(exe[2]), int(count), C.byref(has), C.byref(d), _p(en)))
+        return bool(has.value), d.value, en[:count] if has.value else en[:0]
+
+    def stats(self) -> dict:
+        s = gp_stats()
+        self._check(load().gp_last_stats(self._h, C.byref(s)))
+        return {"nodes_scanned": s.nodes_scanned, "drivers_tried": s.drivers_tried, "kernel_launches": s.kernel_launches}
+
+    # ---- device-resident (torch tensors on this context's device) ----------------------------
+    def stream_handle(self) -> int:
+        return load().gp_stream(self._h) or 0
+
+    def synchronize(self):
+        self._check(load().gp_synchronize(self._h))
+
+    def set_snapshot_device(self, cpu, mem, gpu, exec_off, exec_order, drv_off, drv_order, stream: int = 0):
+        """All arguments are torch CUDA tensors (int64 / int32); kept alive by the caller."""
+        n = gp_nodes(n_nodes=cpu.numel(), avail_cpu_milli=cpu.data_ptr(), avail_mem_bytes=mem.data_ptr(),
+                     avail_gpu=gpu.data_ptr() if gpu is not None else None, n_groups=exec_off.numel() - 1,
+                     exec_off=exec_off.data_ptr(), exec_order=exec_order.data_ptr(), drv_off=drv_off.data_ptr(),
+                     drv_order=drv_order.data_ptr())
+        self._check(load().gp_set_snapshot_device(self._h, C.byref(n), stream or None))
+        self.n_nodes = cpu.numel()
+
+    def pack_batch_device(self, t: dict, algo: int, mode: int, driver_node, executor_nodes, stream: int = 0):
+        """t: dict of torch CUDA tensors (drv_cpu, drv_mem, [drv_gpu], exe_cpu, exe_mem, [exe_gpu], count, [group],
+        [young], off).  Asynchronous on `stream` (0 = the context's stream)."""
+        def dp(name):
+            v = t.get(name)
+            return v.data_ptr() if v is not None else None
+        a = gp_apps(n_apps=t["count"].numel(), drv_cpu_milli=dp("drv_cpu"), drv_mem_bytes=dp("drv_mem"),
+                    drv_gpu=dp("drv_gpu"), exe_cpu_milli=dp("exe_cpu"), exe_mem_bytes=dp("exe_mem"),
+                    exe_gpu=dp("exe_gpu"), exe_count=dp("count"), group=dp("group"), skip_if_no_fit=dp("young"),
+                    exec_out_off=dp("off"))
+        r = gp_results(driver_node=driver_node.data_ptr(), executor_nodes=executor_nodes.data_ptr(),
+                       executor_nodes_cap=executor_nodes.numel())
+        self._check(load().gp_pack_batch_device(self._h, C.byref(a), algo, mode, C.byref(r), stream or None))

@@ -1,0 +1,181 @@
+/*
+ * oracle/gangpack_closed.c -- CLOSED-FORM CPU restatement (int64 SoA, index orders).
+ * TEST INFRASTRUCTURE ONLY (see gangpack_oracle.h).  Parity status: partially pinned, see header.
+ *
+ * Same results as the literal restatement (tests/ cross-check them on randomized inputs), computed
+ * from the per-node executor capacity -- the reference's own statement of which is
+ * LIB/capacity/capacity.go:36-75 (GetNodeCapacity):
+ *
+ *   cap_dim(n | r) = 0                      if r_dim > avail_dim      (resources.go:239 on `reserved`)
+ *                  = +INF                   if exe_dim == 0
+ *                  = floor((avail-r)/exe)   otherwise
+ *   cap(n | r)     = min over cpu, mem, gpu;   0 for a node that is not in the metadata
+ *
+ * tightly-pack  (LIB/binpack/pack_tightly.go:34-63): node n receives min(cap, remaining), node-major.
+ * distribute-evenly (LIB/binpack/distribute_evenly.go:34-73): round r hands one executor to every
+ *   node with cap >= r, in order, until `count` are placed.
+ * driver loop (LIB/binpack/binpack.go:60-87): first d in driverOrder with !gt(drv, avail[d]) whose
+ *   executor total  S0 - min(cap(d|0),k) + min(cap(d|drv),k)  reaches k.
+ *
+ * Precondition (checked by the product API too): exec_order / driver_order hold no duplicates.
+ */
+#include "gangpack_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define CAP_INF INT64_MAX
+
+static inline int64_t cap_dim(int64_t avail, int64_t r, int64_t e) {
+    if (r > avail) return 0;
+    if (e == 0) return CAP_INF;
+    return (avail - r) / e;
+}
+static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+typedef struct {
+    int32_t n_nodes;
+    int64_t *cpu, *mem, *gpu;
+    const int32_t* driver_order; int32_t n_driver;
+    const int32_t* exec_order; int32_t n_exec;
+    const uint8_t* in_exec; /* [n_nodes] */
+} snap;
+
+static inline int valid(const snap* s, int32_t n) { return n >= 0 && n < s->n_nodes; }
+
+static inline int64_t node_cap(const snap* s, int32_t n, const orc_res* r, const orc_res* e) {
+    if (!valid(s, n)) return 0;
+    int64_t c = cap_dim(s->cpu[n], r->cpu, e->cpu);
+    c = min64(c, cap_dim(s->mem[n], r->mem, e->mem));
+    c = min64(c, cap_dim(s->gpu[n], r->gpu, e->gpu));
+    return c;
+}
+
+/* returns driver node or -1; writes executor nodes (count entries) on success */
+static int32_t pack_one(const snap* s, int algo, const orc_res* drv, const orc_res* exe, int32_t k,
+                        int32_t* executor_nodes) {
+    static const orc_res zero = {0, 0, 0};
+    int64_t S0 = 0;
+    for (int32_t i = 0; i < s->n_exec; ++i) {
+        S0 += min64(node_cap(s, s->exec_order[i], &zero, exe), k);
+    }
+    int32_t d = -1;
+    int64_t cd = 0;
+    for (int32_t i = 0; i < s->n_driver; ++i) {
+        int32_t c = s->driver_order[i];
+        if (!valid(s, c)) continue;                                                       /* binpack.go:68-69 */
+        if (drv->cpu > s->cpu[c] || drv->mem > s->mem[c] || drv->gpu > s->gpu[c]) continue; /* :69 */
+        int64_t Sd = S0;
+        int64_t capd = 0;
+        if (s->in_exec[c]) {
+            capd = node_cap(s, c, drv, exe);
+            Sd = S0 - min64(node_cap(s, c, &zero, exe), k) + min64(capd, k);
+        }
+        if (Sd >= k) { d = c; cd = capd; break; }
+    }
+    if (d < 0) return -1;
+    int32_t placed = 0;
+    if (k == 0) return d;
+    if (algo == ORC_TIGHTLY_PACK) {
+        for (int32_t i = 0; i < s->n_exec && placed < k; ++i) {
+            int32_t n = s->exec_order[i];
+            int64_t c = (n == d) ? cd : node_cap(s, n, &zero, exe);
+            int64_t take = min64(c, (int64_t)(k - placed));
+            for (int64_t t = 0; t < take; ++t) executor_nodes[placed++] = n;
+        }
+    } else {
+        for (int64_t r = 1; placed < k; ++r) {
+            for (int32_t i = 0; i < s->n_exec && placed < k; ++i) {
+                int32_t n = s->exec_order[i];
+                int64_t c = (n == d) ? cd : node_cap(s, n, &zero, exe);
+                if (c >= r) executor_nodes[placed++] = n;
+            }
+        }
+    }
+    return d;
+}
+
+typedef struct {
+    const snap* s; int algo; int32_t lo, hi;
+    const orc_res *drv, *exe; const int32_t* count;
+    const int64_t* exec_off; int32_t* driver_node; int32_t* executor_nodes;
+} job;
+
+static void* worker(void* p) {
+    job* j = (job*)p;
+    for (int32_t i = j->lo; i < j->hi; ++i)
+        j->driver_node[i] = pack_one(j->s, j->algo, &j->drv[i], &j->exe[i], j->count[i],
+                                     j->executor_nodes + j->exec_off[i]);
+    return NULL;
+}
+
+int32_t orc_closed_batch(int algo, int mode, int32_t n_nodes,
+                         int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu,
+                         const int32_t* driver_order, int32_t n_driver,
+                         const int32_t* exec_order, int32_t n_exec,
+                         int32_t n_apps, const orc_res* drv, const orc_res* exe,
+                         const int32_t* count, const uint8_t* young, int n_threads,
+                         const int64_t* exec_off, int32_t* driver_node, int32_t* executor_nodes) {
+    uint8_t* in_exec = (uint8_t*)calloc((size_t)(n_nodes > 0 ? n_nodes : 1), 1);
+    for (int32_t i = 0; i < n_exec; ++i)
+        if (exec_order[i] >= 0 && exec_order[i] < n_nodes) in_exec[exec_order[i]] = 1;
+    snap s = {n_nodes, avail_cpu, avail_mem, avail_gpu, driver_order, n_driver, exec_order, n_exec, in_exec};
+    int32_t blocked = -1;
+
+    if (mode == 0) {
+        if (n_threads < 1) n_threads = 1;
+        if (n_threads > n_apps) n_threads = n_apps > 0 ? n_apps : 1;
+        job* jobs = (job*)malloc(sizeof(job) * (size_t)n_threads);
+        pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+        for (int t = 0; t < n_threads; ++t) {
+            job j = {&s, algo, (int32_t)((int64_t)n_apps * t / n_threads), (int32_t)((int64_t)n_apps * (t + 1) / n_threads),
+                     drv, exe, count, exec_off, driver_node, executor_nodes};
+            jobs[t] = j;
+            if (n_threads == 1) worker(&jobs[t]); else pthread_create(&th[t], NULL, worker, &jobs[t]);
+        }
+        if (n_threads > 1) for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+        free(jobs); free(th);
+    } else {
+        /* fitEarlierDrivers, EXT/resource.go:224-262 */
+        uint8_t* seen = (uint8_t*)calloc((size_t)(n_nodes > 0 ? n_nodes : 1), 1);
+        int32_t i = 0;
+        for (; i < n_apps; ++i) {
+            int32_t* en = executor_nodes + exec_off[i];
+            int32_t d = pack_one(&s, algo, &drv[i], &exe[i], count[i], en);
+            driver_node[i] = d;
+            if (d < 0) {
+                if (young && young[i]) continue;      /* :245-249 */
+                blocked = i; ++i; break;              /* :250-252 */
+            }
+            if (mode == ORC_FIFO_REFERENCE) {
+                /* EXT/sparkpods.go:139-146: usage[driver]=drv, then usage[n]=exe for each executor
+                 * node (assignment) -> each distinct executor node charged once; a driver node that
+                 * also hosts an executor is charged the executor only. */
+                int driver_hosts_executor = 0;
+                for (int32_t k = 0; k < count[i]; ++k) {
+                    int32_t n = en[k];
+                    if (n == d) driver_hosts_executor = 1;
+                    if (!seen[n]) {
+                        seen[n] = 1;
+                        avail_cpu[n] -= exe[i].cpu; avail_mem[n] -= exe[i].mem; avail_gpu[n] -= exe[i].gpu;
+                    }
+                }
+                for (int32_t k = 0; k < count[i]; ++k) seen[en[k]] = 0;
+                if (!driver_hosts_executor) {
+                    avail_cpu[d] -= drv[i].cpu; avail_mem[d] -= drv[i].mem; avail_gpu[d] -= drv[i].gpu;
+                }
+            } else {
+                avail_cpu[d] -= drv[i].cpu; avail_mem[d] -= drv[i].mem; avail_gpu[d] -= drv[i].gpu;
+                for (int32_t k = 0; k < count[i]; ++k) {
+                    int32_t n = en[k];
+                    avail_cpu[n] -= exe[i].cpu; avail_mem[n] -= exe[i].mem; avail_gpu[n] -= exe[i].gpu;
+                }
+            }
+        }
+        for (; i < n_apps; ++i) driver_node[i] = -2;
+        free(seen);
+    }
+    free(in_exec);
+    return blocked;
+}

@@ -1,0 +1,558 @@
+/*
+ * oracle/gangpack_oracle.c -- LITERAL CPU restatement of the reference placement hot path.
+ * TEST INFRASTRUCTURE ONLY (see gangpack_oracle.h).  Parity status: partially pinned, see header.
+ *
+ * Written loop-for-loop from the cited reference lines, keeping the reference's data structures
+ * (string-keyed hash maps, a fresh `reserved` map per driver candidate, an N-entry
+ * `availableNodes` set per distribute-evenly call) so that it can also stand in for the cost
+ * profile of the Go path when timed as the CPU baseline ("restated, not Go").
+ */
+#include "gangpack_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ Resources ---- */
+/* LIB/resources/resources.go:202-206 */
+static inline void res_add(orc_res* r, const orc_res* o) { r->cpu += o->cpu; r->mem += o->mem; r->gpu += o->gpu; }
+/* LIB/resources/resources.go:209-213 */
+static inline void res_sub(orc_res* r, const orc_res* o) { r->cpu -= o->cpu; r->mem -= o->mem; r->gpu -= o->gpu; }
+/* LIB/resources/resources.go:239-241: any dimension strictly greater */
+static inline int res_greater_than(const orc_res* r, const orc_res* o) {
+    return r->cpu > o->cpu || r->mem > o->mem || r->gpu > o->gpu;
+}
+/* LIB/resources/resources.go:244-246 */
+static inline int res_eq(const orc_res* r, const orc_res* o) {
+    return r->cpu == o->cpu && r->mem == o->mem && r->gpu == o->gpu;
+}
+
+/* ------------------------------------------------------------------ string-keyed map ---- */
+/* Stand-in for Go's map[string]T: open addressing, FNV-1a, tombstones, value = int32 slot. */
+typedef struct {
+    const char** keys; /* NULL = empty, TOMB = deleted */
+    int32_t* vals;
+    uint32_t cap;      /* power of two */
+    uint32_t len;
+    uint32_t used;     /* len + tombstones */
+} strmap;
+
+static const char TOMB_OBJ = 0;
+#define TOMB (&TOMB_OBJ)
+
+static uint64_t fnv1a(const char* s) {
+    uint64_t h = 1469598103934665603ull;
+    for (; *s; ++s) { h ^= (unsigned char)*s; h *= 1099511628211ull; }
+    return h;
+}
+static uint32_t pow2_at_least(uint32_t x) { uint32_t c = 8; while (c < x) c <<= 1; return c; }
+
+static void strmap_init(strmap* m, uint32_t expected) {
+    m->cap = pow2_at_least(expected * 2 + 2);
+    m->keys = (const char**)calloc(m->cap, sizeof(char*));
+    m->vals = (int32_t*)malloc(m->cap * sizeof(int32_t));
+    m->len = 0; m->used = 0;
+}
+static void strmap_free(strmap* m) { free(m->keys); free(m->vals); m->keys = NULL; m->vals = NULL; }
+
+static int32_t* strmap_find(const strmap* m, const char* k) {
+    uint32_t i = (uint32_t)fnv1a(k) & (m->cap - 1);
+    for (;;) {
+        const char* e = m->keys[i];
+        if (e == NULL) return NULL;
+        if (e != TOMB && strcmp(e, k) == 0) return &m->vals[i];
+        i = (i + 1) & (m->cap - 1);
+    }
+}
+static void strmap_grow(strmap* m);
+static int32_t* strmap_insert(strmap* m, const char* k, int32_t v) { /* k assumed absent */
+    if ((m->used + 1) * 4 > m->cap * 3) strmap_grow(m);
+    uint32_t i = (uint32_t)fnv1a(k) & (m->cap - 1);
+    while (m->keys[i] != NULL && m->keys[i] != TOMB) i = (i + 1) & (m->cap - 1);
+    if (m->keys[i] == NULL) m->used++;
+    m->keys[i] = k; m->vals[i] = v; m->len++;
+    return &m->vals[i];
+}
+static void strmap_grow(strmap* m) {
+    strmap n;
+    n.cap = m->cap * 2;
+    n.keys = (const char**)calloc(n.cap, sizeof(char*));
+    n.vals = (int32_t*)malloc(n.cap * sizeof(int32_t));
+    n.len = 0; n.used = 0;
+    for (uint32_t i = 0; i < m->cap; ++i)
+        if (m->keys[i] != NULL && m->keys[i] != TOMB) strmap_insert(&n, m->keys[i], m->vals[i]);
+    strmap_free(m);
+    *m = n;
+}
+static void strmap_delete(strmap* m, const char* k) {
+    uint32_t i = (uint32_t)fnv1a(k) & (m->cap - 1);
+    for (;;) {
+        const char* e = m->keys[i];
+        if (e == NULL) return;
+        if (e != TOMB && strcmp(e, k) == 0) { m->keys[i] = TOMB; m->len--; return; }
+        i = (i + 1) & (m->cap - 1);
+    }
+}
+
+/* ------------------------------------------------------------------ cluster ---- */
+typedef struct {
+    orc_res available;    /* AvailableResources   */
+    orc_res schedulable;  /* SchedulableResources */
+    const char* zone;     /* ZoneLabel            */
+    uint8_t unschedulable, ready;
+} node_meta;
+
+struct orc_cluster {
+    int32_t n;
+    char** names;     /* owned copies, insertion order */
+    char** zones;     /* owned copies */
+    node_meta* meta;
+    strmap index;     /* name -> slot */
+};
+
+static char* dupstr(const char* s) {
+    size_t l = strlen(s) + 1; char* d = (char*)malloc(l); memcpy(d, s, l); return d;
+}
+
+orc_cluster* orc_cluster_new(int32_t n, const char* const* names,
+                             const int64_t* avail_cpu, const int64_t* avail_mem, const int64_t* avail_gpu,
+                             const int64_t* sched_cpu, const int64_t* sched_mem, const int64_t* sched_gpu,
+                             const char* const* zone, const uint8_t* unschedulable, const uint8_t* ready) {
+    orc_cluster* c = (orc_cluster*)calloc(1, sizeof(*c));
+    c->n = n;
+    c->names = (char**)malloc(sizeof(char*) * (size_t)(n > 0 ? n : 1));
+    c->zones = (char**)malloc(sizeof(char*) * (size_t)(n > 0 ? n : 1));
+    c->meta = (node_meta*)calloc((size_t)(n > 0 ? n : 1), sizeof(node_meta));
+    strmap_init(&c->index, (uint32_t)n);
+    for (int32_t i = 0; i < n; ++i) {
+        c->names[i] = dupstr(names[i]);
+        /* LIB/resources/resources.go:78-81: missing zone label -> "default" */
+        c->zones[i] = dupstr(zone ? zone[i] : "default");
+        node_meta* m = &c->meta[i];
+        m->available.cpu = avail_cpu[i]; m->available.mem = avail_mem[i]; m->available.gpu = avail_gpu ? avail_gpu[i] : 0;
+        m->schedulable.cpu = sched_cpu ? sched_cpu[i] : m->available.cpu;
+        m->schedulable.mem = sched_mem ? sched_mem[i] : m->available.mem;
+        m->schedulable.gpu = sched_gpu ? sched_gpu[i] : m->available.gpu;
+        m->zone = c->zones[i];
+        m->unschedulable = unschedulable ? unschedulable[i] : 0;
+        m->ready = ready ? ready[i] : 1;
+        strmap_insert(&c->index, c->names[i], i);
+    }
+    return c;
+}
+void orc_cluster_free(orc_cluster* c) {
+    if (!c) return;
+    for (int32_t i = 0; i < c->n; ++i) { free(c->names[i]); free(c->zones[i]); }
+    free(c->names); free(c->zones); free(c->meta); strmap_free(&c->index); free(c);
+}
+int32_t orc_cluster_size(const orc_cluster* c) { return c->n; }
+int32_t orc_cluster_index(const orc_cluster* c, const char* name) {
+    int32_t* s = strmap_find(&c->index, name); return s ? *s : -1;
+}
+void orc_cluster_get_available(const orc_cluster* c, int64_t* cpu, int64_t* mem, int64_t* gpu) {
+    for (int32_t i = 0; i < c->n; ++i) {
+        cpu[i] = c->meta[i].available.cpu; mem[i] = c->meta[i].available.mem; gpu[i] = c->meta[i].available.gpu;
+    }
+}
+/* nodesSchedulingMetadata[name] with the ", ok" form */
+static inline node_meta* meta_lookup(const orc_cluster* c, const char* name) {
+    int32_t* s = strmap_find(&c->index, name); return s ? &c->meta[*s] : NULL;
+}
+
+/* ------------------------------------------------------------------ reserved map ---- */
+/* resources.NodeGroupResources: map[string]*Resources (LIB/resources/resources.go:103) */
+typedef struct { strmap idx; orc_res* vals; int32_t n, cap; } resmap;
+
+static void resmap_init(resmap* r, int32_t expected) {
+    strmap_init(&r->idx, (uint32_t)expected);
+    r->cap = expected > 4 ? expected : 4;
+    r->vals = (orc_res*)malloc(sizeof(orc_res) * (size_t)r->cap);
+    r->n = 0;
+}
+static void resmap_free(resmap* r) { strmap_free(&r->idx); free(r->vals); }
+static orc_res* resmap_get(resmap* r, const char* k) {
+    int32_t* s = strmap_find(&r->idx, k); return s ? &r->vals[*s] : NULL;
+}
+static orc_res* resmap_put(resmap* r, const char* k, const orc_res* v) {
+    orc_res* e = resmap_get(r, k);
+    if (e) { *e = *v; return e; }
+    if (r->n == r->cap) { r->cap *= 2; r->vals = (orc_res*)realloc(r->vals, sizeof(orc_res) * (size_t)r->cap); }
+    r->vals[r->n] = *v;
+    strmap_insert(&r->idx, k, r->n);
+    return &r->vals[r->n++];
+}
+
+/* ------------------------------------------------------------------ executor distributors ---- */
+typedef int (*distribute_fn)(const orc_cluster*, const orc_res*, int32_t, const char* const*, int32_t,
+                             resmap*, const char**);
+
+/* tightlyPackExecutors, LIB/binpack/pack_tightly.go:34-63 */
+static int tightly_pack_executors(const orc_cluster* c, const orc_res* exe, int32_t count,
+                                  const char* const* order, int32_t n_order,
+                                  resmap* reserved, const char** executor_nodes) {
+    static const orc_res zero = {0, 0, 0};
+    int32_t placed = 0;
+    if (count == 0) return 1;                                       /* :42-44 */
+    for (int32_t i = 0; i < n_order; ++i) {                         /* :45 */
+        const char* n = order[i];
+        orc_res* r = resmap_get(reserved, n);                       /* :46-48 */
+        if (r == NULL) r = resmap_put(reserved, n, &zero);
+        for (;;) {                                                  /* :49 */
+            res_add(r, exe);                                        /* :50 */
+            const node_meta* m = meta_lookup(c, n);                 /* :51 */
+            if (m == NULL || res_greater_than(r, &m->available)) {  /* :52 */
+                res_sub(r, exe);                                    /* :53 */
+                break;                                              /* :54 */
+            }
+            executor_nodes[placed++] = n;                           /* :56 */
+            if (placed == count) return 1;                          /* :57-59 */
+        }
+    }
+    return 0;                                                       /* :62 */
+}
+
+/* distributeExecutorsEvenly, LIB/binpack/distribute_evenly.go:34-73 */
+static int distribute_executors_evenly(const orc_cluster* c, const orc_res* exe, int32_t count,
+                                       const char* const* order, int32_t n_order,
+                                       resmap* reserved, const char** executor_nodes) {
+    static const orc_res zero = {0, 0, 0};
+    strmap available;                                               /* :41-44 */
+    strmap_init(&available, (uint32_t)n_order);
+    for (int32_t i = 0; i < n_order; ++i)
+        if (strmap_find(&available, order[i]) == NULL) strmap_insert(&available, order[i], 1);
+    int32_t placed = 0;
+    if (count == 0) { strmap_free(&available); return 1; }          /* :46-48 */
+    while (available.len > 0) {                                     /* :49 */
+        for (int32_t i = 0; i < n_order; ++i) {                     /* :50 */
+            const char* n = order[i];
+            if (strmap_find(&available, n) == NULL) continue;       /* :51-53 */
+            orc_res* r = resmap_get(reserved, n);                   /* :55-57 */
+            if (r == NULL) r = resmap_put(reserved, n, &zero);
+            res_add(r, exe);                                        /* :58 */
+            const node_meta* m = meta_lookup(c, n);                 /* :59 */
+            if (m == NULL || res_greater_than(r, &m->available)) {  /* :60 */
+                strmap_delete(&available, n);                       /* :62 */
+                res_sub(r, exe);                                    /* :63 */
+            } else {
+                executor_nodes[placed++] = n;                       /* :65 */
+                if (placed == count) { strmap_free(&available); return 1; } /* :66-68 */
+            }
+        }
+    }
+    strmap_free(&available);
+    return 0;                                                       /* :72 */
+}
+
+/* ------------------------------------------------------------------ efficiencies ---- */
+/* Quantity.Value() for a milli-scaled CPU (quantity.go:732-734 -> int64Amount.AsScaledInt64 ->
+ * negativeScaleInt64, math.go:166-199): whole cores, inexact values rounded AWAY from zero.
+ * Memory / GPU are scale 0. */
+static inline int64_t cpu_value(int64_t milli) {
+    int64_t q = milli / 1000, rem = milli % 1000;
+    if (rem > 0) return q + 1;
+    if (rem < 0) return q - 1;
+    return q;
+}
+static inline int64_t normalize_resource(int64_t v) { return v == 0 ? 1 : v; } /* efficiency.go:104-109 */
+
+typedef struct { double cpu, mem, gpu; } pack_eff;
+
+/* computePackingEfficiency, LIB/binpack/efficiency.go:79-102 */
+static pack_eff compute_packing_efficiency(const node_meta* m, const orc_res* reserved /* may be NULL */) {
+    orc_res r = m->schedulable;               /* :84 */
+    res_sub(&r, &m->available);               /* :85 */
+    if (reserved) res_add(&r, reserved);      /* :86-88 */
+    pack_eff e;
+    e.gpu = 0.0;                              /* :92-95 */
+    if (m->schedulable.gpu != 0) e.gpu = (double)r.gpu / (double)normalize_resource(m->schedulable.gpu);
+    e.cpu = (double)cpu_value(r.cpu) / (double)normalize_resource(cpu_value(m->schedulable.cpu));
+    e.mem = (double)r.mem / (double)normalize_resource(m->schedulable.mem);
+    return e;
+}
+
+/* ComputePackingEfficiencies (efficiency.go:66-77) followed by
+ * computeAvgPackingEfficiencyForResult (EXT/resource.go:372-381) -> ComputeAvgPackingEfficiency
+ * (efficiency.go:114-156).  Iteration: cluster insertion order (Go: map order). */
+static void avg_packing_efficiency(const orc_cluster* c, resmap* reserved, double* out4) {
+    pack_eff* effs = (pack_eff*)malloc(sizeof(pack_eff) * (size_t)(c->n > 0 ? c->n : 1)); /* one per node, :72-74 */
+    for (int32_t i = 0; i < c->n; ++i)
+        effs[i] = compute_packing_efficiency(&c->meta[i], resmap_get(reserved, c->names[i]));
+    double cpu = 0, mem = 0, gpu = 0, mx = 0; int32_t with_gpu = 0;
+    for (int32_t i = 0; i < c->n; ++i) {
+        cpu += effs[i].cpu; mem += effs[i].mem;
+        if (c->meta[i].schedulable.gpu != 0) { gpu += effs[i].gpu; with_gpu++; }
+        double m2 = effs[i].cpu > effs[i].mem ? effs[i].cpu : effs[i].mem;
+        mx += effs[i].gpu > m2 ? effs[i].gpu : m2;
+    }
+    if (out4) {
+        if (c->n == 0) { out4[0] = out4[1] = out4[2] = out4[3] = 0.0; }  /* WorstAvgPackingEfficiency */
+        else {
+            double len = (double)c->n;
+            out4[0] = cpu / len; out4[1] = mem / len;
+            out4[2] = with_gpu == 0 ? 1.0 : gpu / (double)with_gpu;
+            out4[3] = mx / len;
+        }
+    }
+    free(effs);
+}
+
+/* ------------------------------------------------------------------ SparkBinPack ---- */
+/* LIB/binpack/binpack.go:60-87.  executor_names: scratch of >= count entries. */
+static int spark_bin_pack(const orc_cluster* c, const orc_res* drv, const orc_res* exe, int32_t count,
+                          const char* const* driver_order, int32_t n_driver,
+                          const char* const* exec_order, int32_t n_exec,
+                          distribute_fn distribute, int with_efficiencies,
+                          const char** driver_name, const char** executor_names, double* avg_eff) {
+    for (int32_t i = 0; i < n_driver; ++i) {                                   /* :67 */
+        const char* d = driver_order[i];
+        const node_meta* m = meta_lookup(c, d);                                /* :68 */
+        if (m == NULL || res_greater_than(drv, &m->available)) continue;       /* :69-71 */
+        resmap reserved;                                                       /* :72 make(map, len(metadata)) */
+        resmap_init(&reserved, c->n);
+        resmap_put(&reserved, d, drv);                                         /* :73 */
+        int ok = distribute(c, exe, count, exec_order, n_exec, &reserved, executor_names); /* :74-75 */
+        if (ok) {                                                              /* :76 */
+            if (with_efficiencies) avg_packing_efficiency(c, &reserved, avg_eff); /* :77 */
+            resmap_free(&reserved);
+            *driver_name = d;                                                  /* :78-83 */
+            return 1;
+        }
+        resmap_free(&reserved);
+    }
+    *driver_name = NULL;                                                       /* :86 EmptyPackingResult */
+    if (avg_eff) { avg_eff[0] = avg_eff[1] = avg_eff[2] = avg_eff[3] = 0.0; }
+    return 0;
+}
+
+/* internal/binpacker/binpack.go:43-58: name -> function; here by algo id. */
+static distribute_fn select_distributor(int algo) {
+    return algo == ORC_TIGHTLY_PACK ? tightly_pack_executors : distribute_executors_evenly;
+}
+
+int orc_binpack(const orc_cluster* c, int algo, const orc_res* drv, const orc_res* exe, int32_t count,
+                const char* const* driver_order, int32_t n_driver,
+                const char* const* exec_order, int32_t n_exec,
+                int with_efficiencies,
+                int32_t* driver_node, int32_t* executor_nodes, double* avg_eff) {
+    const char** names = (const char**)malloc(sizeof(char*) * (size_t)(count > 0 ? count : 1));
+    const char* dname = NULL;
+    int ok = spark_bin_pack(c, drv, exe, count, driver_order, n_driver, exec_order, n_exec,
+                            select_distributor(algo), with_efficiencies, &dname, names, avg_eff);
+    *driver_node = ok ? orc_cluster_index(c, dname) : -1;
+    if (ok) for (int32_t i = 0; i < count; ++i) executor_nodes[i] = orc_cluster_index(c, names[i]);
+    free(names);
+    return ok;
+}
+
+/* ------------------------------------------------------------------ independent batch ---- */
+typedef struct {
+    const orc_cluster* c; int algo; int32_t lo, hi;
+    const orc_res *drv, *exe; const int32_t* count;
+    const char* const* driver_order; int32_t n_driver;
+    const char* const* exec_order; int32_t n_exec;
+    int with_eff; const int64_t* exec_off; int32_t* driver_node; int32_t* executor_nodes;
+} batch_job;
+
+static void* batch_worker(void* p) {
+    batch_job* j = (batch_job*)p;
+    for (int32_t i = j->lo; i < j->hi; ++i) {
+        double eff[4];
+        orc_binpack(j->c, j->algo, &j->drv[i], &j->exe[i], j->count[i], j->driver_order, j->n_driver,
+                    j->exec_order, j->n_exec, j->with_eff, &j->driver_node[i],
+                    j->executor_nodes + j->exec_off[i], eff);
+    }
+    return NULL;
+}
+
+void orc_binpack_batch(const orc_cluster* c, int algo, int32_t n_apps,
+                       const orc_res* drv, const orc_res* exe, const int32_t* count,
+                       const char* const* driver_order, int32_t n_driver,
+                       const char* const* exec_order, int32_t n_exec,
+                       int with_efficiencies, int n_threads,
+                       const int64_t* exec_off, int32_t* driver_node, int32_t* executor_nodes) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_apps) n_threads = n_apps > 0 ? n_apps : 1;
+    batch_job* jobs = (batch_job*)malloc(sizeof(batch_job) * (size_t)n_threads);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; ++t) {
+        batch_job j = {c, algo, (int32_t)((int64_t)n_apps * t / n_threads), (int32_t)((int64_t)n_apps * (t + 1) / n_threads),
+                       drv, exe, count, driver_order, n_driver, exec_order, n_exec,
+                       with_efficiencies, exec_off, driver_node, executor_nodes};
+        jobs[t] = j;
+        if (n_threads == 1) batch_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+    }
+    if (n_threads > 1) for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    free(jobs); free(th);
+}
+
+/* ------------------------------------------------------------------ FIFO loop ---- */
+/* fitEarlierDrivers, EXT/resource.go:224-262 (+ the caller's own pack at :321 as the last app). */
+int32_t orc_fifo(orc_cluster* c, int algo, int mode, int32_t n_apps,
+                 const orc_res* drv, const orc_res* exe, const int32_t* count, const uint8_t* young,
+                 const char* const* driver_order, int32_t n_driver,
+                 const char* const* exec_order, int32_t n_exec,
+                 int with_efficiencies,
+                 const int64_t* exec_off, int32_t* driver_node, int32_t* executor_nodes) {
+    int32_t blocked = -1;
+    int32_t maxc = 1;
+    for (int32_t i = 0; i < n_apps; ++i) if (count[i] > maxc) maxc = count[i];
+    const char** names = (const char**)malloc(sizeof(char*) * (size_t)maxc);
+    int32_t i = 0;
+    for (; i < n_apps; ++i) {                                                    /* :230 */
+        const char* dname = NULL; double eff[4];
+        int ok = spark_bin_pack(c, &drv[i], &exe[i], count[i], driver_order, n_driver, exec_order, n_exec,
+                                select_distributor(algo), with_efficiencies, &dname, names, eff); /* :238-243 */
+        if (!ok) {                                                               /* :244 */
+            driver_node[i] = -1;
+            if (young && young[i]) continue;                                     /* :245-249 shouldSkipDriverFifo */
+            blocked = i;                                                         /* :250-252 */
+            ++i;
+            break;
+        }
+        driver_node[i] = orc_cluster_index(c, dname);
+        for (int32_t k = 0; k < count[i]; ++k) executor_nodes[exec_off[i] + k] = orc_cluster_index(c, names[k]);
+
+        if (mode == ORC_FIFO_REFERENCE) {
+            /* sparkResourceUsage, EXT/sparkpods.go:139-146: map ASSIGNMENT, not accumulation */
+            resmap usage; resmap_init(&usage, count[i] + 1);
+            resmap_put(&usage, dname, &drv[i]);                                  /* :141 */
+            for (int32_t k = 0; k < count[i]; ++k) resmap_put(&usage, names[k], &exe[i]); /* :142-144 */
+            /* SubtractUsageIfExists, LIB/resources/resources.go:129-135 */
+            for (uint32_t s = 0; s < usage.idx.cap; ++s) {
+                const char* k = usage.idx.keys[s];
+                if (k == NULL || k == TOMB) continue;
+                node_meta* m = meta_lookup(c, k);
+                if (m) res_sub(&m->available, &usage.vals[usage.idx.vals[s]]);
+            }
+            resmap_free(&usage);
+        } else {
+            /* exact accounting: every placed pod is charged */
+            node_meta* m = meta_lookup(c, dname);
+            if (m) res_sub(&m->available, &drv[i]);
+            for (int32_t k = 0; k < count[i]; ++k) {
+                node_meta* e = meta_lookup(c, names[k]);
+                if (e) res_sub(&e->available, &exe[i]);
+            }
+        }
+    }
+    for (; i < n_apps; ++i) driver_node[i] = -2;  /* never evaluated: fitEarlierDrivers returned false */
+    free(names);
+    return blocked;
+}
+
+/* ------------------------------------------------------------------ node sorting ---- */
+/* resourcesLessThan, internal/sort/nodesorting.go:74-80 */
+static int resources_less_than(const orc_res* l, const orc_res* r) {
+    if (l->mem != r->mem) return l->mem < r->mem;
+    return l->cpu < r->cpu;
+}
+typedef struct { int32_t az_priority; const orc_res* res; const char* name; int32_t idx; } sched_ctx;
+/* scheduleContextLessThan, internal/sort/nodesorting.go:83-93 */
+static int schedule_context_less_than(const sched_ctx* l, const sched_ctx* r) {
+    if (l->az_priority != r->az_priority) return l->az_priority < r->az_priority;
+    if (!res_eq(l->res, r->res)) return resources_less_than(l->res, r->res);
+    return strcmp(l->name, r->name) < 0;
+}
+
+/* stable merge sort on sched_ctx / generic index arrays */
+static void msort_ctx(sched_ctx* a, sched_ctx* tmp, int32_t n) {
+    if (n < 2) return;
+    int32_t h = n / 2;
+    msort_ctx(a, tmp, h); msort_ctx(a + h, tmp, n - h);
+    int32_t i = 0, j = h, k = 0;
+    while (i < h && j < n) tmp[k++] = schedule_context_less_than(&a[j], &a[i]) ? a[j++] : a[i++];
+    while (i < h) tmp[k++] = a[i++];
+    while (j < n) tmp[k++] = a[j++];
+    memcpy(a, tmp, sizeof(sched_ctx) * (size_t)n);
+}
+
+/* createLabelLessThanFunction, internal/sort/nodesorting.go:161-180, on precomputed ranks:
+ * rank1 unknown -> false; rank2 unknown -> true; else rank1 < rank2. */
+static int label_less_than(int32_t r1, int32_t r2) {
+    if (r1 < 0) return 0;
+    if (r2 < 0) return 1;
+    return r1 < r2;
+}
+/* sort.SliceStable(nodeNames, lessThan)  (:191-200) */
+static void stable_sort_by_label(int32_t* a, int32_t* tmp, int32_t n, const int32_t* rank) {
+    if (n < 2) return;
+    int32_t h = n / 2;
+    stable_sort_by_label(a, tmp, h, rank); stable_sort_by_label(a + h, tmp, n - h, rank);
+    int32_t i = 0, j = h, k = 0;
+    while (i < h && j < n) tmp[k++] = label_less_than(rank[a[j]], rank[a[i]]) ? a[j++] : a[i++];
+    while (i < h) tmp[k++] = a[i++];
+    while (j < n) tmp[k++] = a[j++];
+    memcpy(a, tmp, sizeof(int32_t) * (size_t)n);
+}
+
+void orc_potential_nodes(const orc_cluster* c, const char* const* candidate_names, int32_t n_candidates,
+                         const int32_t* driver_label_rank, const int32_t* exec_label_rank,
+                         int32_t* driver_out, int32_t* n_driver_out,
+                         int32_t* exec_out, int32_t* n_exec_out) {
+    int32_t n = c->n;
+    /* getNodeNamesInPriorityOrder, :95-122 */
+    /* groupNodeNamesByAZ :136-143 + getAvailableResourcesByAZ :124-134 */
+    strmap az_index; strmap_init(&az_index, 16);
+    int32_t n_az = 0, az_cap = 16;
+    const char** az_label = (const char**)malloc(sizeof(char*) * (size_t)az_cap);
+    orc_res* az_res = (orc_res*)malloc(sizeof(orc_res) * (size_t)az_cap);
+    int32_t* node_az = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t* s = strmap_find(&az_index, c->meta[i].zone);
+        int32_t a;
+        if (s) a = *s;
+        else {
+            if (n_az == az_cap) {
+                az_cap *= 2;
+                az_label = (const char**)realloc(az_label, sizeof(char*) * (size_t)az_cap);
+                az_res = (orc_res*)realloc(az_res, sizeof(orc_res) * (size_t)az_cap);
+            }
+            a = n_az++;
+            az_label[a] = c->meta[i].zone;
+            az_res[a].cpu = az_res[a].mem = az_res[a].gpu = 0;
+            strmap_insert(&az_index, c->meta[i].zone, a);
+        }
+        node_az[i] = a;
+        res_add(&az_res[a], &c->meta[i].available);
+    }
+    /* sort AZ labels by resourcesLessThan (:102-104).  Unstable in the reference; here: insertion
+     * sort (stable) over first-seen order. */
+    int32_t* az_order = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_az > 0 ? n_az : 1));
+    for (int32_t a = 0; a < n_az; ++a) az_order[a] = a;
+    for (int32_t a = 1; a < n_az; ++a) {
+        int32_t v = az_order[a], b = a - 1;
+        while (b >= 0 && resources_less_than(&az_res[v], &az_res[az_order[b]])) { az_order[b + 1] = az_order[b]; --b; }
+        az_order[b + 1] = v;
+    }
+    int32_t* az_priority = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_az > 0 ? n_az : 1));
+    for (int32_t p = 0; p < n_az; ++p) az_priority[az_order[p]] = p;   /* :106-115 */
+
+    sched_ctx* ctx = (sched_ctx*)malloc(sizeof(sched_ctx) * (size_t)(n > 0 ? n : 1));
+    sched_ctx* tmp = (sched_ctx*)malloc(sizeof(sched_ctx) * (size_t)(n > 0 ? n : 1));
+    for (int32_t i = 0; i < n; ++i) {
+        ctx[i].az_priority = az_priority[node_az[i]];
+        ctx[i].res = &c->meta[i].available;
+        ctx[i].name = c->names[i];
+        ctx[i].idx = i;
+    }
+    msort_ctx(ctx, tmp, n);                                              /* :117-119 */
+
+    /* PotentialNodes, :41-64 */
+    strmap cand; strmap_init(&cand, (uint32_t)n_candidates);             /* :46-49 */
+    for (int32_t i = 0; i < n_candidates; ++i)
+        if (strmap_find(&cand, candidate_names[i]) == NULL) strmap_insert(&cand, candidate_names[i], 1);
+    int32_t nd = 0, ne = 0;
+    for (int32_t i = 0; i < n; ++i) {                                    /* :51 */
+        int32_t node = ctx[i].idx;
+        if (strmap_find(&cand, c->names[node]) != NULL) driver_out[nd++] = node;         /* :52-54 */
+        if (!c->meta[node].unschedulable && c->meta[node].ready) exec_out[ne++] = node;  /* :55-57 */
+    }
+    int32_t* itmp = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    if (driver_label_rank) stable_sort_by_label(driver_out, itmp, nd, driver_label_rank); /* :61 */
+    if (exec_label_rank) stable_sort_by_label(exec_out, itmp, ne, exec_label_rank);       /* :62 */
+    *n_driver_out = nd; *n_exec_out = ne;
+
+    free(itmp); strmap_free(&cand); free(ctx); free(tmp); free(az_priority); free(az_order);
+    free(node_az); free(az_res); free(az_label); strmap_free(&az_index);
+}

@@ -1,0 +1,202 @@
+"""Pure-Python literal restatement of the reference hot path (dicts keyed by node name).
+
+TEST INFRASTRUCTURE ONLY; small cases only (pure-Python loops).  It exists as an independent third
+statement of the algorithm: tests/gen_golden.py uses it to derive tests/golden/*.json and the tests
+check the two C oracles against it.  Parity status: partially pinned (see gangpack_oracle.h).
+
+LIB = /root/reference/vendor/github.com/palantir/k8s-spark-scheduler-lib/pkg, EXT = internal/extender.
+Resources are (cpu_milli, mem_bytes, gpu) tuples.
+"""
+from __future__ import annotations
+
+import functools
+
+
+def gt(a, b):
+    """Resources.GreaterThan, LIB/resources/resources.go:239-241."""
+    return a[0] > b[0] or a[1] > b[1] or a[2] > b[2]
+
+
+def add(a, b):
+    return (a[0] + b[0], a[1] + b[1], a[2] + b[2])
+
+
+def sub(a, b):
+    return (a[0] - b[0], a[1] - b[1], a[2] - b[2])
+
+
+ZERO = (0, 0, 0)
+
+
+def tightly_pack_executors(exe, count, order, meta, reserved):
+    """LIB/binpack/pack_tightly.go:34-63.  meta: name -> available Resources."""
+    out = []
+    if count == 0:
+        return out, True
+    for n in order:
+        if n not in reserved:
+            reserved[n] = ZERO
+        while True:
+            reserved[n] = add(reserved[n], exe)
+            if n not in meta or gt(reserved[n], meta[n]):
+                reserved[n] = sub(reserved[n], exe)
+                break
+            out.append(n)
+            if len(out) == count:
+                return out, True
+    return None, False
+
+
+def distribute_executors_evenly(exe, count, order, meta, reserved):
+    """LIB/binpack/distribute_evenly.go:34-73."""
+    available = {n: True for n in order}
+    out = []
+    if count == 0:
+        return out, True
+    while len(available) > 0:
+        for n in order:
+            if n not in available:
+                continue
+            if n not in reserved:
+                reserved[n] = ZERO
+            reserved[n] = add(reserved[n], exe)
+            if n not in meta or gt(reserved[n], meta[n]):
+                del available[n]
+                reserved[n] = sub(reserved[n], exe)
+            else:
+                out.append(n)
+                if len(out) == count:
+                    return out, True
+    return None, False
+
+
+DISTRIBUTORS = {"tightly-pack": tightly_pack_executors, "distribute-evenly": distribute_executors_evenly}
+
+
+def spark_bin_pack(drv, exe, count, driver_order, exec_order, meta, distribute):
+    """LIB/binpack/binpack.go:60-87 -> (driver|None, executor_nodes, has_capacity)."""
+    for d in driver_order:
+        if d not in meta or gt(drv, meta[d]):
+            continue
+        reserved = {d: drv}
+        nodes, ok = distribute(exe, count, exec_order, meta, reserved)
+        if ok:
+            return d, nodes, True
+    return None, [], False
+
+
+def spark_resource_usage(drv, exe, driver_node, executor_nodes):
+    """EXT/sparkpods.go:139-146 (assignment, not accumulation)."""
+    res = {driver_node: drv}
+    for n in executor_nodes:
+        res[n] = exe
+    return res
+
+
+def fit_earlier_drivers(apps, driver_order, exec_order, meta, algo, mode="reference"):
+    """EXT/resource.go:224-262.  apps: dicts {drv, exe, count, young}.  Mutates meta.
+    Returns (blocked_index|-1, [(driver|None|'unevaluated', nodes)])."""
+    distribute = DISTRIBUTORS[algo]
+    results = []
+    blocked = -1
+    for i, a in enumerate(apps):
+        if blocked >= 0:
+            results.append(("unevaluated", []))
+            continue
+        d, nodes, ok = spark_bin_pack(a["drv"], a["exe"], a["count"], driver_order, exec_order, meta, distribute)
+        if not ok:
+            results.append((None, []))
+            if a.get("young"):
+                continue
+            blocked = i
+            continue
+        results.append((d, nodes))
+        if mode == "reference":
+            usage = spark_resource_usage(a["drv"], a["exe"], d, nodes)
+            for n, u in usage.items():  # SubtractUsageIfExists, LIB/resources/resources.go:129-135
+                if n in meta:
+                    meta[n] = sub(meta[n], u)
+        else:
+            meta[d] = sub(meta[d], a["drv"])
+            for n in nodes:
+                meta[n] = sub(meta[n], a["exe"])
+    return blocked, results
+
+
+def resources_less_than(l, r):
+    """internal/sort/nodesorting.go:74-80."""
+    if l[1] != r[1]:
+        return l[1] < r[1]
+    return l[0] < r[0]
+
+
+def node_names_in_priority_order(meta, zones):
+    """getNodeNamesInPriorityOrder, internal/sort/nodesorting.go:95-122.  meta: name -> avail,
+    zones: name -> zone label.  Python's sort is stable; the reference's is not."""
+    by_az = {}
+    for n in meta:
+        by_az.setdefault(zones.get(n, "default"), []).append(n)
+    az_res = {}
+    for az, ns in by_az.items():
+        tot = ZERO
+        for n in ns:
+            tot = add(tot, meta[n])
+        az_res[az] = tot
+
+    def az_cmp(a, b):
+        if resources_less_than(az_res[a], az_res[b]):
+            return -1
+        if resources_less_than(az_res[b], az_res[a]):
+            return 1
+        return 0
+
+    azs = sorted(by_az.keys(), key=functools.cmp_to_key(az_cmp))
+    prio = {az: i for i, az in enumerate(azs)}
+
+    def less(a, b):  # scheduleContextLessThan :83-93
+        pa, pb = prio[zones.get(a, "default")], prio[zones.get(b, "default")]
+        if pa != pb:
+            return pa < pb
+        if meta[a] != meta[b]:
+            return resources_less_than(meta[a], meta[b])
+        return a < b
+
+    def cmp(a, b):
+        if less(a, b):
+            return -1
+        if less(b, a):
+            return 1
+        return 0
+
+    return sorted(meta.keys(), key=functools.cmp_to_key(cmp))
+
+
+def potential_nodes(meta, zones, candidate_names, unschedulable=(), not_ready=(),
+                    driver_label_rank=None, exec_label_rank=None):
+    """PotentialNodes, internal/sort/nodesorting.go:41-64.  *_label_rank: name -> rank (absent = unknown)."""
+    order = node_names_in_priority_order(meta, zones)
+    cand = set(candidate_names)
+    drivers = [n for n in order if n in cand]
+    execs = [n for n in order if n not in unschedulable and n not in not_ready]
+
+    def label_sort(names, rank):
+        if rank is None:
+            return names
+
+        def less(a, b):  # createLabelLessThanFunction :161-180
+            if a not in rank:
+                return False
+            if b not in rank:
+                return True
+            return rank[a] < rank[b]
+
+        def cmp(a, b):
+            if less(a, b):
+                return -1
+            if less(b, a):
+                return 1
+            return 0
+
+        return sorted(names, key=functools.cmp_to_key(cmp))
+
+    return label_sort(drivers, driver_label_rank), label_sort(execs, exec_label_rank)

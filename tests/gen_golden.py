@@ -1,0 +1,212 @@
+#!/usr/bin/env python
+"""Generates tests/golden/hotpath_vectors.json.
+
+Go cannot run in this environment and the reference is not importable, so the golden vectors are:
+  (a) what the reference's OWN tests pin for this path (fit / no-fit, min-executor semantics, node
+      priority orders) -- each case cites the reference test file:line; and
+  (b) hand-derived vectors whose full outputs are re-derived here by the
+      independent pure-Python literal restatement oracle/pyref.py; generation FAILS if pyref
+      disagrees with the hand-derived expectation embedded below.
+Fields marked "pinned": "reference-test" are asserted by a reference test; "derived" are not
+(parity unpinned for those outputs -- authority is the cited source lines).
+
+Run:  python tests/gen_golden.py      (rewrites the JSON in place; committed with the fixture)
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyref  # noqa: E402
+
+Gi = 1 << 30
+ALGOS = ("tightly-pack", "distribute-evenly")
+
+
+def nodes(*specs):
+    return [{"name": n, "cpu": c, "mem": m, "gpu": g} for (n, c, m, g) in specs]
+
+
+def pack_case(cid, source, node_list, app, driver_order=None, exec_order=None, expect_hand=None, pinned_fit=None):
+    names = [n["name"] for n in node_list]
+    driver_order = driver_order if driver_order is not None else names
+    exec_order = exec_order if exec_order is not None else names
+    meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in node_list}
+    expect = {}
+    for algo in ALGOS:
+        d, ex, ok = pyref.spark_bin_pack(tuple(app["drv"]), tuple(app["exe"]), app["count"],
+                                         driver_order, exec_order, dict(meta), pyref.DISTRIBUTORS[algo])
+        expect[algo] = {"fit": ok, "driver": d, "executors": ex}
+        if expect_hand and algo in expect_hand:
+            hd, hex_ = expect_hand[algo]
+            assert ok and d == hd and ex == hex_, (cid, algo, (d, ex), (hd, hex_))
+        if pinned_fit is not None:
+            assert ok == pinned_fit, (cid, algo, ok, pinned_fit)
+    return {"id": cid, "source": source, "nodes": node_list, "driver_order": driver_order,
+            "exec_order": exec_order, "app": app, "expect": expect,
+            "pinned": {"fit": "reference-test" if pinned_fit is not None else "derived",
+                       "driver": "derived", "executors": "derived"}}
+
+
+def main():
+    app_readme = {"drv": [1000, 1 * Gi, 0], "exe": [2000, 4 * Gi, 0], "count": 8}  # README.md:37-41
+    cases = []
+    # ---- SURVEY App. A.5 hand-derived vectors -------------------------------------------------
+    v1_nodes = nodes(*[(f"n{i}", 8000, 16 * Gi, 0) for i in range(4)])
+    cases.append(pack_case(
+        "V1", "BASELINE.json configs[0]; README.md:37-41 app on 4 free nodes (hand-derived)",
+        v1_nodes, app_readme,
+        expect_hand={"tightly-pack": ("n0", ["n0"] * 3 + ["n1"] * 4 + ["n2"]),
+                     "distribute-evenly": ("n0", ["n0", "n1", "n2", "n3"] * 2)}))
+    cases.append(pack_case(
+        "V3", "hand-derived: driver skips n0 (cpu), executors skip n0/n1",
+        nodes(("n0", 500, 16 * Gi, 0), ("n1", 8000, 2 * Gi, 0), ("n2", 8000, 16 * Gi, 0), ("n3", 4000, 8 * Gi, 0)),
+        {**app_readme, "count": 5},
+        expect_hand={"tightly-pack": ("n1", ["n2"] * 4 + ["n3"]),
+                     "distribute-evenly": ("n1", ["n2", "n3", "n2", "n3", "n2"])}))
+    cases.append(pack_case(
+        "V4", "hand-derived: driver shares n0 with one executor",
+        nodes(("n0", 3000, 5 * Gi, 0), ("n1", 4000, 8 * Gi, 0), ("n2", 2000, 4 * Gi, 0)),
+        {**app_readme, "count": 4},
+        expect_hand={"tightly-pack": ("n0", ["n0", "n1", "n1", "n2"]),
+                     "distribute-evenly": ("n0", ["n0", "n1", "n2", "n1"])}))
+    cases.append(pack_case(
+        "V6", "hand-derived: first driver candidate rejected by the executor fit (binpack.go:74-83)",
+        nodes(("n0", 2000, 4 * Gi, 0), ("n1", 3000, 5 * Gi, 0)),
+        {**app_readme, "count": 2},
+        expect_hand={"tightly-pack": ("n1", ["n0", "n1"]),
+                     "distribute-evenly": ("n1", ["n0", "n1"])}))
+    # ---- pinned by the reference's own tests ---------------------------------------------------
+    harness_nodes = nodes(("node1", 8000, 8 * Gi, 1), ("node2", 8000, 8 * Gi, 1))  # extender_test_utils.go:239-271
+    static_app = {"drv": [1000, 1, 1], "exe": [1000, 1, 0]}  # StaticAllocationSparkPods "1","1","1","1" + driver gpu 1
+    cases.append(pack_case(
+        "T0", "internal/extender/resource_test.go:27-51 TestScheduler: 2-executor app fits 2 nodes",
+        harness_nodes, {**static_app, "count": 2}, pinned_fit=True))
+    cases.append(pack_case(
+        "T1a", "internal/extender/unschedulablepods_test.go:24-43: 2-executor app does not exceed capacity",
+        harness_nodes, {**static_app, "count": 2}, pinned_fit=True))
+    cases.append(pack_case(
+        "T1b", "internal/extender/unschedulablepods_test.go:45-53: 100-executor app exceeds capacity",
+        harness_nodes, {**static_app, "count": 100}, pinned_fit=False))
+    cases.append(pack_case(
+        "T2", "internal/extender/unschedulablepods_test.go:55-80 TestSchedulerFailsToScheduleWhenNotEnoughNvidiaGPUs",
+        harness_nodes, {"drv": [1000, 1, 1], "exe": [1000, 1, 1], "count": 2}, pinned_fit=False))
+    cases.append(pack_case(
+        "T3", "internal/extender/resource_test.go:172-196 dynamic allocation min=1/max=3: only MIN is gang-packed "
+              "(EXT/resource.go:242,325) -> exactly one executor slot",
+        harness_nodes, {**static_app, "count": 1}, pinned_fit=True))
+    # ---- edge cases the semantics imply (derived) ------------------------------------------------
+    cases.append(pack_case(
+        "E0", "count==0 succeeds on the first driver-feasible node (pack_tightly.go:42-44, distribute_evenly.go:46-48)",
+        nodes(("n0", 500, 1 * Gi, 0), ("n1", 4000, 8 * Gi, 0)), {**app_readme, "count": 0}))
+    cases.append(pack_case(
+        "E1", "negative availability: over-committed node never hosts, even for zero-request dims (resources.go:239)",
+        nodes(("n0", 8000, 16 * Gi, -1), ("n1", -500, 64 * Gi, 0), ("n2", 8000, 16 * Gi, 0)),
+        {**app_readme, "count": 3}))
+    cases.append(pack_case(
+        "E2", "driver node not in executor order; executor order names a node missing from metadata",
+        nodes(("n0", 1000, 1 * Gi, 0), ("n1", 8000, 16 * Gi, 0), ("n2", 8000, 16 * Gi, 0)),
+        {**app_readme, "count": 4}, driver_order=["ghost", "n0", "n1"], exec_order=["ghost", "n1", "n2"]))
+    cases.append(pack_case(
+        "E3", "no driver fits anywhere", nodes(("n0", 500, 16 * Gi, 0), ("n1", 900, 16 * Gi, 0)),
+        {**app_readme, "count": 1}))
+    cases.append(pack_case(
+        "E4", "zero-resource executors: unlimited capacity on the first admissible node",
+        nodes(("n0", 1000, 1 * Gi, 0), ("n1", 8000, 16 * Gi, 0)),
+        {"drv": [1000, 1 * Gi, 0], "exe": [0, 0, 0], "count": 5}))
+    cases.append(pack_case(
+        "E5", "distribute-evenly needs 3 rounds with uneven capacities",
+        nodes(("n0", 7000, 64 * Gi, 0), ("n1", 2000, 64 * Gi, 0), ("n2", 4500, 64 * Gi, 0)),
+        {**app_readme, "count": 6}))
+    cases.append(pack_case(
+        "E6", "empty executor order with count>0 never fits; empty driver order never fits",
+        nodes(("n0", 8000, 16 * Gi, 0)), {**app_readme, "count": 1}, exec_order=[]))
+
+    # ---- FIFO loop (fitEarlierDrivers) ----------------------------------------------------------
+    fifo_cases = []
+
+    def fifo_case(cid, source, node_list, apps, algo, mode, expect_hand=None):
+        names = [n["name"] for n in node_list]
+        meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in node_list}
+        py_apps = [{"drv": tuple(a["drv"]), "exe": tuple(a["exe"]), "count": a["count"], "young": a.get("young", False)}
+                   for a in apps]
+        blocked, res = pyref.fit_earlier_drivers(py_apps, names, names, meta, algo, mode)
+        out = [{"driver": d, "executors": ex} for d, ex in res]
+        final = [{"name": n, "cpu": meta[n][0], "mem": meta[n][1], "gpu": meta[n][2]} for n in names]
+        if expect_hand:
+            expect_hand(blocked, out, final)
+        return {"id": cid, "source": source, "nodes": node_list, "apps": apps, "algo": algo, "mode": mode,
+                "expect": {"blocked": blocked, "results": out, "final_available": final},
+                "pinned": "derived"}
+
+    def v5_ref(blocked, out, final):
+        assert blocked == -1
+        assert out[0] == {"driver": "n0", "executors": ["n0"] * 3 + ["n1"] * 4 + ["n2"]}
+        assert out[1] == {"driver": "n0", "executors": ["n0"] * 2 + ["n1"] * 3 + ["n2"] * 3}
+        assert out[2] == {"driver": "n0", "executors": ["n0"] + ["n1"] * 2 + ["n2"] * 2 + ["n3"] * 3}
+        assert [(f["cpu"], f["mem"]) for f in final] == [(2000, 4 * Gi)] * 3 + [(6000, 12 * Gi)]
+
+    def v5_exact(blocked, out, final):
+        assert blocked == 1 and out[0]["driver"] == "n0" and out[1]["driver"] is None and out[2]["driver"] == "unevaluated"
+
+    three = [dict(app_readme) for _ in range(3)]
+    fifo_cases.append(fifo_case("V5-reference", "SURVEY App. A.5 V5: sparkResourceUsage overwrite quirk (EXT/sparkpods.go:139-146)",
+                                v1_nodes, three, "tightly-pack", "reference", v5_ref))
+    fifo_cases.append(fifo_case("V5-exact", "SURVEY App. A.5 V5 with exact accounting: second app blocks the queue",
+                                v1_nodes, three, "tightly-pack", "exact", v5_exact))
+    young = [dict(app_readme), {**app_readme, "count": 40, "young": True}, dict(app_readme),
+             {**app_readme, "count": 40}, dict(app_readme)]
+    fifo_cases.append(fifo_case("F1-young-skip", "EXT/resource.go:244-253: non-fitting young driver is skipped, old one blocks",
+                                v1_nodes, young, "tightly-pack", "reference"))
+    fifo_cases.append(fifo_case("F2-evenly", "FIFO with distribute-evenly, reference accounting",
+                                v1_nodes, three, "distribute-evenly", "reference"))
+    fifo_cases.append(fifo_case("F3-evenly-exact", "FIFO with distribute-evenly, exact accounting",
+                                v1_nodes, three, "distribute-evenly", "exact"))
+
+    # ---- node priority order (internal/sort) ------------------------------------------------------
+    sort_cases = []
+
+    def sort_case(cid, source, node_list, zones, expect, candidates=None, **kw):
+        meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in node_list}
+        names = [n["name"] for n in node_list]
+        got = pyref.node_names_in_priority_order(meta, zones)
+        assert got == expect, (cid, got, expect)
+        d, e = pyref.potential_nodes(meta, zones, candidates if candidates is not None else names, **kw)
+        return {"id": cid, "source": source, "nodes": node_list, "zones": zones,
+                "candidates": candidates if candidates is not None else names,
+                "expect_priority_order": expect, "expect_driver": d, "expect_executor": e,
+                "pinned": {"priority_order": "reference-test"}}
+
+    sort_cases.append(sort_case(
+        "S1", "internal/sort/nodesorting_test.go:98-141 TestAZAwareNodeSorting",
+        nodes(("zone1Node1", 1, 1, 0), ("zone1Node2", 1, 2, 0), ("zone1Node3", 2, 1, 0), ("zone2Node1", 1, 1, 0)),
+        {"zone1Node1": "zone1", "zone1Node2": "zone1", "zone1Node3": "zone1", "zone2Node1": "zone2"},
+        ["zone2Node1", "zone1Node1", "zone1Node3", "zone1Node2"]))
+    sort_cases.append(sort_case(
+        "S2", "internal/sort/nodesorting_test.go:143-182 TestAZAwareNodeSortingWorksIfZoneLabelIsMissing",
+        nodes(("node1", 2, 1, 0), ("node2", 2, 2, 0), ("node3", 1, 1, 0)), {},
+        ["node3", "node1", "node2"]))
+    # label priority (nodesorting_test.go:195-252): input order + label ranks -> expected order
+    label_cases = [
+        {"id": "L1", "source": "internal/sort/nodesorting_test.go:203-216 sorts when extra label values",
+         "input": ["node1", "node3", "node2"], "rank": {"node2": 1, "node3": 0}, "expect": ["node3", "node2", "node1"]},
+        {"id": "L2", "source": "internal/sort/nodesorting_test.go:217-230 extra nodes with no labels set",
+         "input": ["node2", "node3", "node1"], "rank": {"node2": 1, "node3": 0}, "expect": ["node3", "node2", "node1"]},
+        {"id": "L3", "source": "internal/sort/nodesorting_test.go:231-244 all nodes have ranked values",
+         "input": ["node1", "node2", "node3"], "rank": {"node1": 1, "node2": 2, "node3": 0}, "expect": ["node3", "node1", "node2"]},
+    ]
+
+    out = {"_comment": "generated by tests/gen_golden.py -- do not edit by hand",
+           "units": {"cpu": "millicores", "mem": "bytes", "gpu": "units"},
+           "pack_cases": cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
+    path = os.path.join(ROOT, "tests", "golden", "hotpath_vectors.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1, sort_keys=False)
+        f.write("\n")
+    print("wrote", path, len(cases), "pack,", len(fifo_cases), "fifo,", len(sort_cases), "sort cases")
+
+
+if __name__ == "__main__":
+    main()

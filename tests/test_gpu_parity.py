@@ -1,0 +1,236 @@
+"""Parity of the CUDA path (through the C ABI, libgangpack.so) against the CPU oracle: bit-exact
+driver nodes and ExecutorNodes (contents AND order) on golden vectors, randomized edge-case
+clusters, the synthetic bench workload, and all FIFO modes including the final snapshot."""
+import numpy as np
+import pytest
+
+from helpers import (ALGO_ID, MODE_ID, assert_same_results, case_arrays, order_indices, random_apps,
+                     random_cluster, res_aos)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def packer(gangpack):
+    p = gangpack.GangPacker()
+    yield p
+    p.close()
+
+
+def _oracle_batch(oracle, algo, mode, cpu, mem, gpu, drv_idx, exec_idx, apps, young=None):
+    drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"])
+    exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+    blocked, dn, en, off, final = oracle.closed_batch(algo, mode, cpu, mem, gpu, drv_idx, exec_idx, drv, exe,
+                                                      apps["count"], young, n_threads=8 if mode == 0 else 1)
+    return blocked, (dn, en, off), final
+
+
+def test_golden_pack_cases(golden, packer):
+    for case in golden["pack_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        packer.set_snapshot(cpu, mem, gpu, order_indices(case["exec_order"], names),
+                            order_indices(case["driver_order"], names))
+        app = case["app"]
+        for algo, aid in ALGO_ID.items():
+            ok, d, ex = packer.pack_one(aid, app["drv"], app["exe"], app["count"])
+            exp = case["expect"][algo]
+            assert ok == exp["fit"], (case["id"], algo)
+            if ok:
+                assert names[d] == exp["driver"], (case["id"], algo)
+                assert [names[i] for i in ex] == exp["executors"], (case["id"], algo)
+        c2, m2, g2 = packer.get_snapshot()   # independent packs never mutate the snapshot
+        assert np.array_equal(c2, cpu) and np.array_equal(m2, mem) and np.array_equal(g2, gpu)
+
+
+def test_golden_fifo_cases(golden, packer):
+    for case in golden["fifo_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        idx = np.arange(len(names), dtype=np.int32)
+        packer.set_snapshot(cpu, mem, gpu, idx, idx)
+        apps = case["apps"]
+        a = {"drv_cpu": [x["drv"][0] for x in apps], "drv_mem": [x["drv"][1] for x in apps],
+             "drv_gpu": [x["drv"][2] for x in apps], "exe_cpu": [x["exe"][0] for x in apps],
+             "exe_mem": [x["exe"][1] for x in apps], "exe_gpu": [x["exe"][2] for x in apps],
+             "count": [x["count"] for x in apps], "young": [1 if x.get("young") else 0 for x in apps]}
+        dn, en, off = packer.pack_batch(a, ALGO_ID[case["algo"]], MODE_ID[case["mode"]])
+        exp = case["expect"]
+        for i, r in enumerate(exp["results"]):
+            if r["driver"] == "unevaluated":
+                assert dn[i] == -2, case["id"]
+            elif r["driver"] is None:
+                assert dn[i] == -1, case["id"]
+            else:
+                assert names[dn[i]] == r["driver"], case["id"]
+                assert [names[j] for j in en[off[i]:off[i + 1]]] == r["executors"], case["id"]
+        fc, fm, fg = packer.get_snapshot()
+        for j, f in enumerate(exp["final_available"]):
+            assert (fc[j], fm[j], fg[j]) == (f["cpu"], f["mem"], f["gpu"]), case["id"]
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_independent(oracle, packer, seed):
+    rng = np.random.default_rng(3000 + seed)
+    for trial in range(5):
+        n = int(rng.integers(1, 200))
+        cpu, mem, gpu = random_cluster(rng, n, tight=bool(trial % 2), gpus=bool(seed % 2), negative=bool(seed % 3 == 0))
+        perm = rng.permutation(n)
+        exec_idx = perm[rng.random(n) < 0.85].astype(np.int32)
+        drv_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.3, 1.0)))].astype(np.int32)
+        apps = random_apps(rng, 200, gpus=bool(seed % 2), zero_dims=bool(seed % 4 == 1), big_counts=bool(seed % 4 == 2))
+        packer.set_snapshot(cpu, mem, gpu, exec_idx, drv_idx)
+        for algo in (0, 1):
+            _, want, _ = _oracle_batch(oracle, algo, 0, cpu, mem, gpu, drv_idx, exec_idx, apps)
+            got = packer.pack_batch(apps, algo, 0)
+            assert_same_results(got, want, f"seed {seed} trial {trial} algo {algo}")
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("mode", [1, 2])
+def test_random_fifo(oracle, packer, seed, mode):
+    rng = np.random.default_rng(4000 + seed)
+    for trial in range(4):
+        n = int(rng.integers(2, 300))
+        cpu, mem, gpu = random_cluster(rng, n, gpus=bool(seed % 2))
+        perm = rng.permutation(n)
+        exec_idx = perm[rng.random(n) < 0.9].astype(np.int32)
+        drv_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.3, 1.0)))].astype(np.int32)
+        q = 300
+        apps = random_apps(rng, q, gpus=bool(seed % 2), zero_dims=bool(seed % 3 == 1), big_counts=bool(trial == 3))
+        young = (rng.random(q) < (0.9 if trial % 2 else 0.2)).astype(np.uint8)
+        apps["young"] = young
+        for algo in (0, 1):
+            packer.set_snapshot(cpu, mem, gpu, exec_idx, drv_idx)
+            blocked, want, final = _oracle_batch(oracle, algo, mode, cpu, mem, gpu, drv_idx, exec_idx, apps, young)
+            got = packer.pack_batch(apps, algo, mode)
+            assert_same_results(got, want, f"seed {seed} trial {trial} algo {algo} mode {mode}")
+            fc, fm, fg = packer.get_snapshot()
+            assert np.array_equal(fc, final[0]) and np.array_equal(fm, final[1]) and np.array_equal(fg, final[2])
+
+
+def test_awkward_divisors(oracle, packer):
+    """Exercise every division path of cap_dim: power-of-two, magic (odd < 2^32), slow (odd >= 2^32),
+    shifted numerators above 2^32, 1-byte requests (reference tests use mem '1')."""
+    rng = np.random.default_rng(77)
+    n = 64
+    cpu = rng.integers(0, 1 << 40, n).astype(np.int64)
+    mem = rng.integers(0, 1 << 45, n).astype(np.int64)
+    gpu = np.zeros(n, np.int64)
+    idx = np.arange(n, dtype=np.int32)
+    exe_mem = np.array([1, 3, 1 << 20, (1 << 20) * 3, (1 << 33) + 1, (1 << 34) + 2, 7 << 31, 12345678901, 1 << 44, 5], np.int64)
+    q = len(exe_mem) * 4
+    apps = {
+        "drv_cpu": np.zeros(q, np.int64), "drv_mem": rng.integers(0, 1 << 30, q).astype(np.int64), "drv_gpu": np.zeros(q, np.int64),
+        "exe_cpu": np.tile(np.array([1, 1000, 4097, (1 << 35) + 7], np.int64), len(exe_mem)),
+        "exe_mem": np.repeat(exe_mem, 4), "exe_gpu": np.zeros(q, np.int64),
+        "count": rng.integers(1, 3000, q).astype(np.int32),
+    }
+    packer.set_snapshot(cpu, mem, gpu, idx, idx)
+    for algo in (0, 1):
+        _, want, _ = _oracle_batch(oracle, algo, 0, cpu, mem, gpu, idx, idx, apps)
+        got = packer.pack_batch(apps, algo, 0)
+        assert_same_results(got, want, f"awkward algo {algo}")
+
+
+def test_multi_group(oracle, packer):
+    """Instance groups: disjoint node sets with their own orders; FIFO queues are per group
+    (sparkpods.go:61, resource.go:292-295) and must equal the oracle run per group."""
+    import k8s_spark_scheduler_b200.synth as synth
+    G = 5
+    nodes = synth.make_nodes(700, groups=G)
+    apps = synth.make_apps(900, groups=G, young_frac=0.1)
+    eoff, eorder = synth.group_orders(nodes)
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], eorder, eorder, eoff, eoff)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count", "group", "young")}
+    for algo in (0, 1):
+        for mode in (0, 1, 2):
+            packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], eorder, eorder, eoff, eoff)
+            dn, en, off = packer.pack_batch(a, algo, mode)
+            for g in range(G):
+                sel = np.nonzero(apps["group"] == g)[0]
+                sub = {k: np.asarray(v)[sel] for k, v in a.items()}
+                order = eorder[eoff[g]:eoff[g + 1]]
+                _, want, _ = _oracle_batch(oracle, algo, mode, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"],
+                                           order, order, sub, sub["young"] if mode else None)
+                wd, we, woff = want
+                assert np.array_equal(dn[sel], wd), (algo, mode, g)
+                for j, i in enumerate(sel):
+                    if wd[j] >= 0:
+                        assert np.array_equal(en[off[i]:off[i + 1]], we[woff[j]:woff[j + 1]]), (algo, mode, g, i)
+
+
+def test_synthetic_bench_workload_sample(oracle, packer):
+    """BASELINE configs[1]/[2] shape (10k nodes) on a 4k-app sample: bit-exact vs the oracle."""
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(10000)
+    apps = synth.make_apps(4000)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    for algo in (0, 1):
+        _, want, _ = _oracle_batch(oracle, algo, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order, a)
+        got = packer.pack_batch(a, algo, 0)
+        assert_same_results(got, want, f"synthetic algo {algo}")
+        assert (got[0] >= 0).all()
+
+
+def test_full_size_properties(packer):
+    """BASELINE full size (10k nodes x 100k apps): size-independent properties instead of the oracle:
+    every placement respects capacity, ExecutorNodes has the algorithm's shape, and the batch equals
+    the concatenation of two half batches (independence)."""
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(10000)
+    apps = synth.make_apps(100000)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    rank = np.empty(10000, np.int64); rank[order] = np.arange(10000)
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    for algo in (0, 1):
+        dn, en, off = packer.pack_batch(a, algo, 0)
+        assert (dn >= 0).all()
+        h = 50000
+        first = packer.pack_batch({k: v[:h] for k, v in a.items()}, algo, 0)
+        second = packer.pack_batch({k: v[h:] for k, v in a.items()}, algo, 0)
+        assert np.array_equal(dn, np.concatenate([first[0], second[0]]))
+        assert np.array_equal(en, np.concatenate([first[1], second[1]]))
+        # capacity: per app, driver + executors on each node fit the node
+        app_of = np.repeat(np.arange(100000), apps["count"])
+        key = app_of * 10000 + en
+        uniq, cnt = np.unique(key, return_counts=True)
+        ua, un = uniq // 10000, uniq % 10000
+        on_driver = (dn[ua] == un)
+        need_cpu = cnt * apps["exe_cpu"][ua] + on_driver * apps["drv_cpu"][ua]
+        need_mem = cnt * apps["exe_mem"][ua] + on_driver * apps["drv_mem"][ua]
+        assert (need_cpu <= nodes["avail_cpu"][un]).all() and (need_mem <= nodes["avail_mem"][un]).all()
+        assert (apps["drv_cpu"] <= nodes["avail_cpu"][dn]).all() and (apps["drv_mem"] <= nodes["avail_mem"][dn]).all()
+        r = rank[en]
+        same_app = app_of[1:] == app_of[:-1]
+        if algo == 0:   # node-major: priority rank is non-decreasing inside an app
+            assert (r[1:][same_app] >= r[:-1][same_app]).all()
+        else:           # round-major with one round here: strictly increasing ranks unless a new round starts
+            assert ((r[1:][same_app] > r[:-1][same_app]) | (cnt.max() > 1)).all()
+
+
+def test_error_paths(packer):
+    Gi = 1 << 30
+    idx = np.arange(2, dtype=np.int32)
+    packer.set_snapshot([8000, 8000], [8 * Gi, 8 * Gi], [0, 0], idx, idx)
+    base = {"drv_cpu": [1000], "drv_mem": [Gi], "drv_gpu": [0], "exe_cpu": [1000], "exe_mem": [Gi], "exe_gpu": [0], "count": [1]}
+    from k8s_spark_scheduler_b200 import GangpackError
+    with pytest.raises(GangpackError) as e:
+        packer.pack_batch({**base, "exe_cpu": [-1]}, 0, 0)
+    assert e.value.status == 1
+    with pytest.raises(GangpackError) as e:
+        packer.pack_batch({**base, "exe_mem": [1 << 62]}, 0, 0)
+    assert e.value.status == 6
+    with pytest.raises(GangpackError) as e:
+        packer.pack_batch({**base, "group": [3]}, 0, 0)
+    assert e.value.status == 1
+    with pytest.raises(GangpackError) as e:
+        packer.set_snapshot([1, 2], [1, 2], [0, 0], np.array([0, 0], np.int32), idx)   # duplicate node in an order
+    assert e.value.status == 1
+    # the context is still usable after errors
+    dn, en, off = packer.pack_batch(base, 0, 0)
+    assert dn[0] == 0 and en[0] == 0
+    # empty batch
+    dn, en, off = packer.pack_batch({k: [] for k in base}, 0, 0)
+    assert len(dn) == 0

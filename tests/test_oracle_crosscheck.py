@@ -1,0 +1,113 @@
+"""Three independent statements of the algorithm must agree on randomized inputs:
+pure-Python literal (oracle/pyref.py) == literal C (string maps) == closed-form C (int64 SoA).
+Inputs include negative availability, zero-request dimensions, GPU dimension, driver candidates that
+are not executor candidates, orders naming nodes missing from the metadata, count == 0."""
+import numpy as np
+import pytest
+
+from helpers import random_apps, random_cluster, res_aos
+from oracle import pyref
+
+ALGOS = [(0, "tightly-pack"), (1, "distribute-evenly")]
+
+
+def _orders(rng, n, names):
+    perm = rng.permutation(n)
+    exec_idx = perm[rng.random(n) < 0.85]
+    drv_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.3, 1.0)))]
+    return exec_idx.astype(np.int32), drv_idx.astype(np.int32)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_pack_three_way(oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    for trial in range(6):
+        n = int(rng.integers(1, 40))
+        cpu, mem, gpu = random_cluster(rng, n, tight=bool(trial % 2), gpus=bool(seed % 2), negative=bool(seed % 3 == 0))
+        names = ["node-%03d" % i for i in range(n)]
+        exec_idx, drv_idx = _orders(rng, n, names)
+        apps = random_apps(rng, 24, gpus=bool(seed % 2), zero_dims=bool(seed % 4 == 1), big_counts=bool(seed % 4 == 2))
+        # the literal oracles also see names that are NOT in the metadata
+        exec_names = [names[i] for i in exec_idx] + ["ghost-e"]
+        drv_names = ["ghost-d"] + [names[i] for i in drv_idx]
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"])
+        exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+        meta = {names[i]: (int(cpu[i]), int(mem[i]), int(gpu[i])) for i in range(n)}
+        for algo_id, algo in ALGOS:
+            ld, le, off = cl.binpack_batch(algo_id, drv, exe, apps["count"], drv_names, exec_names, n_threads=2)
+            _, cd, ce, coff, _ = oracle.closed_batch(algo_id, 0, cpu, mem, gpu, drv_idx, exec_idx, drv, exe, apps["count"])
+            assert np.array_equal(off, coff)
+            assert np.array_equal(ld, cd), (seed, trial, algo)
+            for q in range(len(apps["count"])):
+                d, ex, ok = pyref.spark_bin_pack(tuple(int(x) for x in drv[q]), tuple(int(x) for x in exe[q]),
+                                                 int(apps["count"][q]), drv_names, exec_names, dict(meta),
+                                                 pyref.DISTRIBUTORS[algo])
+                assert ok == (ld[q] >= 0), (seed, trial, algo, q)
+                if ok:
+                    assert names[ld[q]] == d
+                    assert [names[i] for i in le[off[q]:off[q + 1]]] == ex, (seed, trial, algo, q)
+                    assert np.array_equal(le[off[q]:off[q + 1]], ce[off[q]:off[q + 1]]), (seed, trial, algo, q)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("mode", ["reference", "exact"])
+def test_fifo_three_way(oracle, seed, mode):
+    rng = np.random.default_rng(2000 + seed)
+    mode_id = {"reference": 1, "exact": 2}[mode]
+    for trial in range(4):
+        n = int(rng.integers(2, 30))
+        cpu, mem, gpu = random_cluster(rng, n, gpus=bool(seed % 2))
+        names = ["node-%03d" % i for i in range(n)]
+        exec_idx, drv_idx = _orders(rng, n, names)
+        q = 30
+        apps = random_apps(rng, q, gpus=bool(seed % 2), zero_dims=bool(seed % 3 == 1))
+        young = (rng.random(q) < 0.3).astype(np.uint8)
+        drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"])
+        exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+        exec_names = [names[i] for i in exec_idx]
+        drv_names = [names[i] for i in drv_idx]
+        for algo_id, algo in ALGOS:
+            cl = oracle.Cluster(names, cpu, mem, gpu)
+            lb, ld, le, off = cl.fifo(algo_id, mode_id, drv, exe, apps["count"], young, drv_names, exec_names)
+            cb, cd, ce, coff, cfinal = oracle.closed_batch(algo_id, mode_id, cpu, mem, gpu, drv_idx, exec_idx, drv, exe,
+                                                           apps["count"], young)
+            assert lb == cb and np.array_equal(ld, cd), (seed, trial, algo)
+            lfinal = cl.available()
+            for a, b in zip(lfinal, cfinal):
+                assert np.array_equal(a, b), (seed, trial, algo)
+            meta = {names[i]: (int(cpu[i]), int(mem[i]), int(gpu[i])) for i in range(n)}
+            py_apps = [{"drv": tuple(int(x) for x in drv[i]), "exe": tuple(int(x) for x in exe[i]),
+                        "count": int(apps["count"][i]), "young": bool(young[i])} for i in range(q)]
+            pb, pres = pyref.fit_earlier_drivers(py_apps, drv_names, exec_names, meta, algo, mode)
+            assert pb == lb
+            for i, (d, ex) in enumerate(pres):
+                if d == "unevaluated":
+                    assert ld[i] == -2
+                elif d is None:
+                    assert ld[i] == -1
+                else:
+                    assert names[ld[i]] == d
+                    assert [names[j] for j in le[off[i]:off[i + 1]]] == ex
+                    assert np.array_equal(le[off[i]:off[i + 1]], ce[off[i]:off[i + 1]])
+            for i in range(n):
+                assert meta[names[i]] == (lfinal[0][i], lfinal[1][i], lfinal[2][i])
+
+
+def test_synthetic_workload_oracles_agree(oracle):
+    """The bench workload shape at reduced size: literal (threaded) == closed form."""
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(600)
+    apps = synth.make_apps(300)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    names = synth.node_names(600)
+    cl = oracle.Cluster(names, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"])
+    onames = [names[i] for i in order]
+    drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"])
+    exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+    for algo in (0, 1):
+        ld, le, off = cl.binpack_batch(algo, drv, exe, apps["count"], onames, onames, n_threads=4)
+        _, cd, ce, coff, _ = oracle.closed_batch(algo, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"],
+                                                 order, order, drv, exe, apps["count"], n_threads=4)
+        assert np.array_equal(ld, cd) and np.array_equal(le, ce)
+        assert (ld >= 0).mean() > 0.5

@@ -1,0 +1,149 @@
+"""The CPU oracles against every golden vector: what the reference's own tests pin for this path
+(fit/no-fit, min-executor semantics, node priority orders -- cited per case in the fixture) and the
+hand-derived vectors of SURVEY App. A.5."""
+import numpy as np
+import pytest
+
+from helpers import ALGO_ID, MODE_ID, case_arrays, order_indices, res_aos
+
+
+def test_fixture_is_current(golden):
+    """tests/gen_golden.py (pyref, hand-derived expectations asserted inside) reproduces the fixture."""
+    import json, os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "tests", "gen_golden.py")).read()
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "tests", "golden"))
+        # run the generator against a scratch ROOT that sees the real oracle package
+        code = src.replace('ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))', f'ROOT = {td!r}')
+        code = code.replace("sys.path.insert(0, ROOT)", f"sys.path.insert(0, {root!r})")
+        subprocess.check_call([sys.executable, "-c", code], stdout=subprocess.DEVNULL)
+        regenerated = json.load(open(os.path.join(td, "tests", "golden", "hotpath_vectors.json")))
+    assert regenerated == golden
+
+
+@pytest.mark.parametrize("algo", ["tightly-pack", "distribute-evenly"])
+def test_literal_oracle_pack_cases(golden, oracle, algo):
+    for case in golden["pack_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        app = case["app"]
+        ok, d, ex, _ = cl.binpack(ALGO_ID[algo], app["drv"], app["exe"], app["count"],
+                                  case["driver_order"], case["exec_order"])
+        exp = case["expect"][algo]
+        assert ok == exp["fit"], case["id"]
+        if ok:
+            assert d == exp["driver"], case["id"]
+            assert ex == exp["executors"], case["id"]
+        # SparkBinPackFunction must not mutate the metadata (binpack.go:60-87)
+        assert np.array_equal(cl.available()[0], cpu) and np.array_equal(cl.available()[1], mem)
+
+
+@pytest.mark.parametrize("algo", ["tightly-pack", "distribute-evenly"])
+def test_closed_oracle_pack_cases(golden, oracle, algo):
+    for case in golden["pack_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        app = case["app"]
+        drv = res_aos([app["drv"][0]], [app["drv"][1]], [app["drv"][2]])
+        exe = res_aos([app["exe"][0]], [app["exe"][1]], [app["exe"][2]])
+        _, dn, en, off, _ = oracle.closed_batch(
+            ALGO_ID[algo], 0, cpu, mem, gpu, order_indices(case["driver_order"], names),
+            order_indices(case["exec_order"], names), drv, exe, [app["count"]])
+        exp = case["expect"][algo]
+        assert (dn[0] >= 0) == exp["fit"], case["id"]
+        if exp["fit"]:
+            assert names[dn[0]] == exp["driver"], case["id"]
+            assert [names[i] for i in en[:app["count"]]] == exp["executors"], case["id"]
+
+
+def _fifo_inputs(case):
+    names, cpu, mem, gpu = case_arrays(case["nodes"])
+    apps = case["apps"]
+    drv = res_aos([a["drv"][0] for a in apps], [a["drv"][1] for a in apps], [a["drv"][2] for a in apps])
+    exe = res_aos([a["exe"][0] for a in apps], [a["exe"][1] for a in apps], [a["exe"][2] for a in apps])
+    count = np.array([a["count"] for a in apps], np.int32)
+    young = np.array([1 if a.get("young") else 0 for a in apps], np.uint8)
+    return names, cpu, mem, gpu, drv, exe, count, young
+
+
+def _check_fifo(case, names, blocked, dn, en, off, final):
+    exp = case["expect"]
+    assert blocked == exp["blocked"], case["id"]
+    for i, r in enumerate(exp["results"]):
+        if r["driver"] == "unevaluated":
+            assert dn[i] == -2, case["id"]
+        elif r["driver"] is None:
+            assert dn[i] == -1, case["id"]
+        else:
+            assert names[dn[i]] == r["driver"], case["id"]
+            assert [names[j] for j in en[off[i]:off[i + 1]]] == r["executors"], case["id"]
+    for j, f in enumerate(exp["final_available"]):
+        assert (final[0][j], final[1][j], final[2][j]) == (f["cpu"], f["mem"], f["gpu"]), case["id"]
+
+
+def test_literal_oracle_fifo_cases(golden, oracle):
+    for case in golden["fifo_cases"]:
+        names, cpu, mem, gpu, drv, exe, count, young = _fifo_inputs(case)
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        blocked, dn, en, off = cl.fifo(ALGO_ID[case["algo"]], MODE_ID[case["mode"]], drv, exe, count, young, names, names)
+        _check_fifo(case, names, blocked, dn, en, off, cl.available())
+
+
+def test_closed_oracle_fifo_cases(golden, oracle):
+    for case in golden["fifo_cases"]:
+        names, cpu, mem, gpu, drv, exe, count, young = _fifo_inputs(case)
+        idx = np.arange(len(names), dtype=np.int32)
+        blocked, dn, en, off, final = oracle.closed_batch(ALGO_ID[case["algo"]], MODE_ID[case["mode"]], cpu, mem, gpu,
+                                                          idx, idx, drv, exe, count, young)
+        _check_fifo(case, names, blocked, dn, en, off, final)
+
+
+def test_node_priority_order_goldens(golden, oracle):
+    """internal/sort/nodesorting_test.go:98-182 through PotentialNodes (all nodes are candidates)."""
+    for case in golden["sort_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        zone = [case["zones"].get(n, "default") for n in names]
+        cl = oracle.Cluster(names, cpu, mem, gpu, zone=zone)
+        d, e = cl.potential_nodes(case["candidates"])
+        assert d == case["expect_priority_order"], case["id"]
+        assert e == case["expect_priority_order"], case["id"]
+        assert d == case["expect_driver"] and e == case["expect_executor"]
+
+
+def test_label_priority_goldens(golden, oracle):
+    """internal/sort/nodesorting_test.go:195-252: stable re-sort by configured label rank.  The input
+    order is reproduced by giving the nodes memory in that order (priority = memory ascending)."""
+    for case in golden["label_cases"]:
+        names = case["input"]
+        n = len(names)
+        cl = oracle.Cluster(names, np.ones(n, np.int64), np.arange(1, n + 1, dtype=np.int64), np.zeros(n, np.int64))
+        rank = [case["rank"].get(nm, -1) for nm in names]
+        d, e = cl.potential_nodes(names, driver_label_rank=rank, exec_label_rank=rank)
+        assert d == case["expect"], case["id"]
+        assert e == case["expect"], case["id"]
+
+
+def test_potential_nodes_filters(oracle):
+    """PotentialNodes: drivers = priority order ∩ candidates; executors = schedulable ∧ ready
+    (internal/sort/nodesorting.go:51-58)."""
+    names = ["a", "b", "c", "d"]
+    cl = oracle.Cluster(names, [4, 3, 2, 1], [4, 3, 2, 1], None, unschedulable=[0, 1, 0, 0], ready=[1, 1, 0, 1])
+    d, e = cl.potential_nodes(["a", "c", "zzz"])
+    assert d == ["c", "a"]
+    assert e == ["d", "a"]
+
+
+def test_packing_efficiency_by_product(oracle):
+    """LIB/binpack/efficiency.go:66-156 on V1 (schedulable == initial available): after tightly-pack
+    n0 carries driver + 3 executors = 7 of 8 cores, 13 of 16 GiB."""
+    Gi = 1 << 30
+    names = ["n0", "n1", "n2", "n3"]
+    cpu = np.full(4, 8000, np.int64); mem = np.full(4, 16 * Gi, np.int64); gpu = np.zeros(4, np.int64)
+    cl = oracle.Cluster(names, cpu, mem, gpu, sched=(cpu, mem, gpu))
+    ok, d, ex, eff = cl.binpack(0, (1000, Gi, 0), (2000, 4 * Gi, 0), 8, names, names, with_efficiencies=True)
+    assert ok and d == "n0"
+    # per node cpu: 7/8, 8/8, 2/8, 0 ; mem: 13/16, 16/16, 4/16, 0
+    assert eff[0] == pytest.approx((7 / 8 + 1 + 2 / 8 + 0) / 4, rel=0, abs=1e-15)
+    assert eff[1] == pytest.approx((13 / 16 + 1 + 4 / 16 + 0) / 4, rel=0, abs=1e-15)
+    assert eff[2] == 1.0          # no node has GPUs -> 1 (efficiency.go:141-145)
+    assert eff[3] == pytest.approx((7 / 8 + 1 + 2 / 8 + 0) / 4, rel=0, abs=1e-15)
