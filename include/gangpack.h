@@ -154,9 +154,12 @@ gp_status gp_pack_one(gp_ctx* ctx, gp_algo algo,
 /* Same as gp_set_snapshot / gp_pack_batch but every array pointer inside gp_nodes / gp_apps /
  * gp_results is a DEVICE pointer on ctx's device (exec_out_off is then mandatory; group and
  * skip_if_no_fit may still be NULL) and nothing is copied or validated on the host.  Work is
- * enqueued on `stream` (a cudaStream_t; NULL = the context's stream) and NOT synchronised.
+ * enqueued on `stream` (a cudaStream_t; NULL = the context's stream) and NOT synchronised (the two
+ * order lengths are passed by value so that no device->host read is needed).
  * gp_set_snapshot_device keeps no reference to the caller's arrays after it returns. */
-gp_status gp_set_snapshot_device(gp_ctx* ctx, const gp_nodes* dev_nodes, void* stream);
+gp_status gp_set_snapshot_device(gp_ctx* ctx, const gp_nodes* dev_nodes,
+                                 int32_t n_exec_total /* = exec_off[n_groups] */,
+                                 int32_t n_drv_total /* = drv_off[n_groups] */, void* stream);
 gp_status gp_pack_batch_device(gp_ctx* ctx, const gp_apps* dev_apps, gp_algo algo, gp_mode mode,
                                gp_results* dev_out, void* stream);
 /* the context's own stream (cudaStream_t) so callers can order their work / record events on it */
@@ -170,7 +173,9 @@ typedef struct {
     int64_t nodes_scanned;
     int64_t drivers_tried;
     int64_t kernel_launches;   /* launches of this library's kernels in that call */
-    int64_t reserved[5];
+    int64_t pack_kernel_ns;    /* device time of the pack kernel (CUDA events on the launch stream) */
+    int64_t prep_kernel_ns;    /* device time of the app-preparation kernel */
+    int64_t reserved[3];
 } gp_stats;
 gp_status gp_last_stats(gp_ctx* ctx, gp_stats* out);
 

@@ -236,6 +236,8 @@ struct gp_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // prep start, pack start, pack end
+    bool ev_valid = false;
     std::string err;
 
     // snapshot
@@ -320,6 +322,8 @@ gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
     c->sm_count = prop.multiProcessorCount;
     if ((e = cudaSetDevice(dev)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev[0])) != cudaSuccess || (e = cudaEventCreate(&c->ev[1])) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev[2])) != cudaSuccess ||
         (e = cudaHostAlloc(&c->pinned_misc, 64, cudaHostAllocDefault)) != cudaSuccess ||
         (e = c->dev_misc.reserve(64)) != cudaSuccess || (e = c->snap_flags.reserve(16)) != cudaSuccess) {
         g_create_error = std::string("gp_create: ") + cudaGetErrorString(e);
@@ -340,6 +344,7 @@ void gp_destroy(gp_ctx* c) {
                       &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
+    for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -471,18 +476,13 @@ gp_status gp_set_snapshot(gp_ctx* c, const gp_nodes* n) {
     return GP_OK;
 }
 
-gp_status gp_set_snapshot_device(gp_ctx* c, const gp_nodes* dn, void* stream) {
+gp_status gp_set_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_exec, int32_t n_drv, void* stream) {
     if (!c) return GP_ERR_INVALID;
-    if (!dn || dn->n_nodes < 0 || dn->n_groups < 1 || !dn->exec_off || !dn->drv_off)
+    if (!dn || dn->n_nodes < 0 || dn->n_groups < 1 || !dn->exec_off || !dn->drv_off || n_exec < 0 || n_drv < 0 ||
+        (n_exec > 0 && !dn->exec_order) || (n_drv > 0 && !dn->drv_order))
         return fail(c, GP_ERR_INVALID, "gp_set_snapshot_device: missing arrays or bad sizes");
     GP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    // sizes live on the device: fetch the two totals (8 bytes) -- the only host round trip
-    int32_t n_exec = 0, n_drv = 0;
-    GP_CUDA(c, cudaMemcpyAsync(&n_exec, dn->exec_off + dn->n_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    GP_CUDA(c, cudaMemcpyAsync(&n_drv, dn->drv_off + dn->n_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    GP_CUDA(c, cudaStreamSynchronize(st));
-    if (n_exec < 0 || n_drv < 0) return fail(c, GP_ERR_INVALID, "gp_set_snapshot_device: negative order length");
     // keep a node-table copy so gp_get_snapshot can answer for nodes outside every group
     const size_t nb = sizeof(int64_t) * (size_t)(dn->n_nodes + 1), vb = sizeof(int64_t) * (size_t)dn->n_nodes;
     GP_CUDA(c, c->node_cpu.reserve(nb)); GP_CUDA(c, c->node_mem.reserve(nb)); GP_CUDA(c, c->node_gpu.reserve(nb));
@@ -546,6 +546,7 @@ static gp_status pack_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(c->dev_misc.as<char>() + 8);
     GP_CUDA(c, cudaMemsetAsync(c->dev_misc.p, 0, 32, st));
     c->last = gp_stats{};
+    c->ev_valid = false;
     if (q == 0) return GP_OK;
     GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));
     int2* scratch = nullptr;
@@ -554,16 +555,20 @@ static gp_status pack_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode
         scratch = c->scratch.as<int2>();
     }
     const int T = 256;
+    GP_CUDA(c, cudaEventRecord(c->ev[0], st));
     gp_prep_apps<<<(q + T - 1) / T, T, 0, st>>>(q, da->drv_cpu_milli, da->drv_mem_bytes, da->drv_gpu, da->exe_cpu_milli,
                                                 da->exe_mem_bytes, da->exe_gpu, da->exe_count, da->group,
                                                 da->skip_if_no_fit, da->exec_out_off, c->n_groups,
                                                 dout->executor_nodes_cap, c->prep.as<PrepApp>(), d_err);
     Snapshot s = make_snapshot(c);
+    GP_CUDA(c, cudaEventRecord(c->ev[1], st));
     if (algo == GP_TIGHTLY_PACK)
         launch_pack<0>(c, mode, s, c->prep.as<PrepApp>(), q, dout->driver_node, dout->executor_nodes, scratch, d_stats, st);
     else
         launch_pack<1>(c, mode, s, c->prep.as<PrepApp>(), q, dout->driver_node, dout->executor_nodes, scratch, d_stats, st);
     GP_CUDA(c, cudaGetLastError());
+    GP_CUDA(c, cudaEventRecord(c->ev[2], st));
+    c->ev_valid = true;
     c->last.kernel_launches = 2;
     return GP_OK;
 }
@@ -578,6 +583,14 @@ static gp_status check_args(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode m
                           !out->driver_node))
         return fail(c, GP_ERR_INVALID, std::string(who) + ": missing app/result arrays");
     return GP_OK;
+}
+
+// after the stream has been synchronised: event times of the last pack
+static void fill_kernel_times(gp_ctx* c) {
+    if (!c->ev_valid) return;
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, c->ev[0], c->ev[1]) == cudaSuccess) c->last.prep_kernel_ns = (int64_t)(a * 1.0e6);
+    if (cudaEventElapsedTime(&b, c->ev[1], c->ev[2]) == cudaSuccess) c->last.pack_kernel_ns = (int64_t)(b * 1.0e6);
 }
 
 static gp_status decode_device_error(gp_ctx* c, int err) {
@@ -607,6 +620,7 @@ gp_status gp_last_stats(gp_ctx* c, gp_stats* out) {
     const unsigned long long* s = reinterpret_cast<const unsigned long long*>((const char*)c->pinned_misc + 8);
     c->last.nodes_scanned = (int64_t)s[0];
     c->last.drivers_tried = (int64_t)s[1];
+    fill_kernel_times(c);
     *out = c->last;
     int err = *reinterpret_cast<const int*>(c->pinned_misc);
     return decode_device_error(c, err);
@@ -664,6 +678,7 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
     const unsigned long long* sv = reinterpret_cast<const unsigned long long*>((const char*)c->pinned_misc + 8);
     c->last.nodes_scanned = (int64_t)sv[0];
     c->last.drivers_tried = (int64_t)sv[1];
+    fill_kernel_times(c);
     return decode_device_error(c, *reinterpret_cast<const int*>(c->pinned_misc));
 }
 

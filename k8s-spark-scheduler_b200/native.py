@@ -84,7 +84,7 @@ class gp_results(C.Structure):
 
 class gp_stats(C.Structure):
     _fields_ = [("nodes_scanned", C.c_int64), ("drivers_tried", C.c_int64), ("kernel_launches", C.c_int64),
-                ("reserved", C.c_int64 * 5)]
+                ("pack_kernel_ns", C.c_int64), ("prep_kernel_ns", C.c_int64), ("reserved", C.c_int64 * 3)]
 
 
 _lib = None
@@ -122,7 +122,7 @@ def load():
     L.gp_pack_one.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 6 + [C.c_int32, C.POINTER(C.c_int32),
                                                                           C.POINTER(C.c_int32), C.c_void_p]
     L.gp_set_snapshot_device.restype = C.c_int
-    L.gp_set_snapshot_device.argtypes = [C.c_void_p, C.POINTER(gp_nodes), C.c_void_p]
+    L.gp_set_snapshot_device.argtypes = [C.c_void_p, C.POINTER(gp_nodes), C.c_int32, C.c_int32, C.c_void_p]
     L.gp_pack_batch_device.restype = C.c_int
     L.gp_pack_batch_device.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.c_int, C.POINTER(gp_results), C.c_void_p]
     L.gp_stream.restype = C.c_void_p
@@ -259,7 +259,8 @@ class GangPacker:
     def stats(self) -> dict:
         s = gp_stats()
         self._check(load().gp_last_stats(self._h, C.byref(s)))
-        return {"nodes_scanned": s.nodes_scanned, "drivers_tried": s.drivers_tried, "kernel_launches": s.kernel_launches}
+        return {"nodes_scanned": s.nodes_scanned, "drivers_tried": s.drivers_tried, "kernel_launches": s.kernel_launches,
+                "pack_kernel_ns": s.pack_kernel_ns, "prep_kernel_ns": s.prep_kernel_ns}
 
     # ---- device-resident (torch tensors on this context's device) ----------------------------
     def stream_handle(self) -> int:
@@ -274,7 +275,8 @@ class GangPacker:
                      avail_gpu=gpu.data_ptr() if gpu is not None else None, n_groups=exec_off.numel() - 1,
                      exec_off=exec_off.data_ptr(), exec_order=exec_order.data_ptr(), drv_off=drv_off.data_ptr(),
                      drv_order=drv_order.data_ptr())
-        self._check(load().gp_set_snapshot_device(self._h, C.byref(n), stream or None))
+        self._check(load().gp_set_snapshot_device(self._h, C.byref(n), exec_order.numel(), drv_order.numel(),
+                                                  stream or None))
         self.n_nodes = cpu.numel()
 
     def pack_batch_device(self, t: dict, algo: int, mode: int, driver_node, executor_nodes, stream: int = 0):

@@ -13,6 +13,36 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Allocation model.  The Go code allocates a fresh map per driver candidate / per call from the GC
+ * heap (zeroed spans, no syscalls on the hot path).  glibc would serve these several-hundred-KB
+ * blocks with mmap/munmap or trim the thread arenas after every free, so worker threads serialise
+ * on the kernel's mm lock and the multi-threaded CPU baseline would look far worse than a Go
+ * runtime.  Stand-in: a small thread-local cache of freed blocks; every "allocation" still pays
+ * the zeroing a fresh Go map pays. */
+#define POOL_SLOTS 24
+typedef struct { void* p; size_t size; } pool_slot;
+static __thread pool_slot g_pool[POOL_SLOTS];
+
+static void* pool_alloc(size_t size, int zero) {
+    for (int i = 0; i < POOL_SLOTS; ++i) {
+        if (g_pool[i].p && g_pool[i].size == size) {
+            void* p = g_pool[i].p;
+            g_pool[i].p = NULL;
+            if (zero) memset(p, 0, size);
+            return p;
+        }
+    }
+    return zero ? calloc(1, size) : malloc(size);
+}
+static void pool_free(void* p, size_t size) {
+    if (!p) return;
+    for (int i = 0; i < POOL_SLOTS; ++i) {
+        if (!g_pool[i].p) { g_pool[i].p = p; g_pool[i].size = size; return; }
+    }
+    free(p);
+}
+static void tune_allocator(void) {}
+
 /* ------------------------------------------------------------------ Resources ---- */
 /* LIB/resources/resources.go:202-206 */
 static inline void res_add(orc_res* r, const orc_res* o) { r->cpu += o->cpu; r->mem += o->mem; r->gpu += o->gpu; }
@@ -49,11 +79,14 @@ static uint32_t pow2_at_least(uint32_t x) { uint32_t c = 8; while (c < x) c <<= 
 
 static void strmap_init(strmap* m, uint32_t expected) {
     m->cap = pow2_at_least(expected * 2 + 2);
-    m->keys = (const char**)calloc(m->cap, sizeof(char*));
-    m->vals = (int32_t*)malloc(m->cap * sizeof(int32_t));
+    m->keys = (const char**)pool_alloc(m->cap * sizeof(char*), 1);
+    m->vals = (int32_t*)pool_alloc(m->cap * sizeof(int32_t), 0);
     m->len = 0; m->used = 0;
 }
-static void strmap_free(strmap* m) { free(m->keys); free(m->vals); m->keys = NULL; m->vals = NULL; }
+static void strmap_free(strmap* m) {
+    pool_free((void*)m->keys, m->cap * sizeof(char*)); pool_free(m->vals, m->cap * sizeof(int32_t));
+    m->keys = NULL; m->vals = NULL;
+}
 
 static int32_t* strmap_find(const strmap* m, const char* k) {
     uint32_t i = (uint32_t)fnv1a(k) & (m->cap - 1);
@@ -76,8 +109,8 @@ static int32_t* strmap_insert(strmap* m, const char* k, int32_t v) { /* k assume
 static void strmap_grow(strmap* m) {
     strmap n;
     n.cap = m->cap * 2;
-    n.keys = (const char**)calloc(n.cap, sizeof(char*));
-    n.vals = (int32_t*)malloc(n.cap * sizeof(int32_t));
+    n.keys = (const char**)pool_alloc(n.cap * sizeof(char*), 1);
+    n.vals = (int32_t*)pool_alloc(n.cap * sizeof(int32_t), 0);
     n.len = 0; n.used = 0;
     for (uint32_t i = 0; i < m->cap; ++i)
         if (m->keys[i] != NULL && m->keys[i] != TOMB) strmap_insert(&n, m->keys[i], m->vals[i]);
@@ -166,17 +199,22 @@ typedef struct { strmap idx; orc_res* vals; int32_t n, cap; } resmap;
 static void resmap_init(resmap* r, int32_t expected) {
     strmap_init(&r->idx, (uint32_t)expected);
     r->cap = expected > 4 ? expected : 4;
-    r->vals = (orc_res*)malloc(sizeof(orc_res) * (size_t)r->cap);
+    r->vals = (orc_res*)pool_alloc(sizeof(orc_res) * (size_t)r->cap, 0);
     r->n = 0;
 }
-static void resmap_free(resmap* r) { strmap_free(&r->idx); free(r->vals); }
+static void resmap_free(resmap* r) { strmap_free(&r->idx); pool_free(r->vals, sizeof(orc_res) * (size_t)r->cap); }
 static orc_res* resmap_get(resmap* r, const char* k) {
     int32_t* s = strmap_find(&r->idx, k); return s ? &r->vals[*s] : NULL;
 }
 static orc_res* resmap_put(resmap* r, const char* k, const orc_res* v) {
     orc_res* e = resmap_get(r, k);
     if (e) { *e = *v; return e; }
-    if (r->n == r->cap) { r->cap *= 2; r->vals = (orc_res*)realloc(r->vals, sizeof(orc_res) * (size_t)r->cap); }
+    if (r->n == r->cap) {
+        orc_res* nv = (orc_res*)pool_alloc(sizeof(orc_res) * (size_t)r->cap * 2, 0);
+        memcpy(nv, r->vals, sizeof(orc_res) * (size_t)r->n);
+        pool_free(r->vals, sizeof(orc_res) * (size_t)r->cap);
+        r->vals = nv; r->cap *= 2;
+    }
     r->vals[r->n] = *v;
     strmap_insert(&r->idx, k, r->n);
     return &r->vals[r->n++];
@@ -274,7 +312,8 @@ static pack_eff compute_packing_efficiency(const node_meta* m, const orc_res* re
  * computeAvgPackingEfficiencyForResult (EXT/resource.go:372-381) -> ComputeAvgPackingEfficiency
  * (efficiency.go:114-156).  Iteration: cluster insertion order (Go: map order). */
 static void avg_packing_efficiency(const orc_cluster* c, resmap* reserved, double* out4) {
-    pack_eff* effs = (pack_eff*)malloc(sizeof(pack_eff) * (size_t)(c->n > 0 ? c->n : 1)); /* one per node, :72-74 */
+    size_t effs_bytes = sizeof(pack_eff) * (size_t)(c->n > 0 ? c->n : 1);
+    pack_eff* effs = (pack_eff*)pool_alloc(effs_bytes, 0); /* one per node, :72-74 */
     for (int32_t i = 0; i < c->n; ++i)
         effs[i] = compute_packing_efficiency(&c->meta[i], resmap_get(reserved, c->names[i]));
     double cpu = 0, mem = 0, gpu = 0, mx = 0; int32_t with_gpu = 0;
@@ -293,7 +332,7 @@ static void avg_packing_efficiency(const orc_cluster* c, resmap* reserved, doubl
             out4[3] = mx / len;
         }
     }
-    free(effs);
+    pool_free(effs, effs_bytes);
 }
 
 /* ------------------------------------------------------------------ SparkBinPack ---- */
@@ -370,6 +409,7 @@ void orc_binpack_batch(const orc_cluster* c, int algo, int32_t n_apps,
                        const char* const* exec_order, int32_t n_exec,
                        int with_efficiencies, int n_threads,
                        const int64_t* exec_off, int32_t* driver_node, int32_t* executor_nodes) {
+    tune_allocator();
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n_apps) n_threads = n_apps > 0 ? n_apps : 1;
     batch_job* jobs = (batch_job*)malloc(sizeof(batch_job) * (size_t)n_threads);
