@@ -329,6 +329,7 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         e2e_t = []
+        e2e_launches = 0
         for s in range(args.steps):
             with torch.cuda.stream(stream):
                 flush.fill_(s & 0xff)
@@ -336,9 +337,9 @@ def main():
             t0 = time.perf_counter()
             e2e_step()
             e2e_t.append(time.perf_counter() - t0)
+            e2e_launches += 3 + packer.stats()["kernel_launches"]   # snapshot layout + (prep + pack) per pipelined chunk
         e2e_ms = float(np.mean(e2e_t)) * 1e3
         e2e_value = q / (e2e_ms * 1e-3)
-        e2e_launches = launches_per_step * args.steps
     else:
         # N>1: rank 0 uploads the snapshot and broadcasts it; every rank packs its host-resident shard
         # through the C ABI; placements are all-gathered on the device and rank 0 reads all of them.

@@ -23,7 +23,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
                              const int64_t* __restrict__ e_cpu, const int64_t* __restrict__ e_mem, const int64_t* __restrict__ e_gpu,
                              const int32_t* __restrict__ count, const int32_t* __restrict__ group,
                              const uint8_t* __restrict__ skip, const int64_t* __restrict__ out_off,
-                             int32_t n_groups, int64_t out_cap,
+                             int32_t n_groups, int64_t out_cap, const SnapMeta* __restrict__ meta,
                              PrepApp* __restrict__ prep, int* __restrict__ err) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_apps) return;
@@ -39,6 +39,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
     if (off < 0 || out_off[i + 1] - off != (int64_t)k || out_off[i + 1] > out_cap) bad |= kErrBadOffsets;
     PrepApp p;
     uint64_t lmax = 0;
+    bool fast = true;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
         if (d[t] < 0 || e[t] < 0) bad |= kErrNegativeRequest;
@@ -60,32 +61,48 @@ __global__ void gp_prep_apps(int32_t n_apps,
             }
         }
         p.div[t] = dv;
+        // fast class: the shifted numerator of every node fits 32 bits (SnapMeta::max_avail bounds it)
+        if (dv.kind == kDivSlow) fast = false;
+        else if (dv.kind != kDivInf) {
+            long long mx = meta->max_avail[t];
+            if (mx > 0 && (((unsigned long long)mx >> dv.sh) >> 32) != 0) fast = false;
+        }
     }
     if (bad) { atomicOr(err, bad); k = 0; g = 0; }
     p.out_off = off;
     p.count = k;
     p.group = g;
     p.lmax = (int32_t)(lmax < (uint64_t)k ? lmax : (uint64_t)k);
-    p.flags = ((d[2] != 0 || e[2] != 0) ? 1u : 0u) | ((skip && skip[i]) ? 2u : 0u) | (bad ? 4u : 0u);
+    p.flags = ((d[2] != 0 || e[2] != 0) ? kAppUsesGpu : 0u) | ((skip && skip[i]) ? kAppSkipIfNoFit : 0u) |
+              (bad ? kAppInvalid : 0u) | (fast ? kAppFast : 0u);
     prep[i] = p;
 }
 
-// Independent mode (GP_MODE_INDEPENDENT): one warp per application, grid-stride over the batch.
+// Independent mode (GP_MODE_INDEPENDENT): one warp per application; warps claim applications from a
+// global counter (claim-then-broadcast, next index prefetched) so long scans do not leave a tail.
+constexpr int kPackThreads = 256;
 template <int ALGO>
-__global__ void __launch_bounds__(256) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
-                                                           int32_t* __restrict__ driver_node,
-                                                           int32_t* __restrict__ executor_nodes,
-                                                           int2* __restrict__ scratch,
-                                                           unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(kPackThreads) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+                                                                    int32_t* __restrict__ driver_node,
+                                                                    int32_t* __restrict__ executor_nodes,
+                                                                    int2* __restrict__ scratch,
+                                                                    unsigned long long* __restrict__ stats,
+                                                                    unsigned int* __restrict__ next_app) {
+    __shared__ uint16_t cap_cache[kPackThreads / 32][kCapCache];
     const int lane = threadIdx.x & 31;
-    const int32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint16_t* wcache = cap_cache[threadIdx.x >> 5];
     WarpStats st{0, 0};
-    for (int32_t i = warp; i < n_apps; i += n_warps) {
+    unsigned int i = 0;
+    if (lane == 0) i = atomicAdd(next_app, 1u);
+    i = __shfl_sync(kFull, i, 0);
+    while (i < (unsigned int)n_apps) {
+        unsigned int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(next_app, 1u);     // in flight while this application is packed
         const PrepApp* pa = prep + i;
         int32_t d = -1;
-        if (!(pa->flags & 4u)) d = pack_app<ALGO, 0>(s, pa, executor_nodes, scratch, st, lane);
+        if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO, 0>(s, pa, executor_nodes, scratch, wcache, st, lane);
         if (lane == 0) driver_node[i] = d;
+        i = __shfl_sync(kFull, nxt, 0);
     }
     if (lane == 0) {
         atomicAdd(stats + 0, st.nodes);
@@ -101,6 +118,7 @@ __global__ void __launch_bounds__(32) gp_pack_fifo(Snapshot s, const PrepApp* __
                                                    int32_t* __restrict__ executor_nodes,
                                                    int2* __restrict__ scratch,
                                                    unsigned long long* __restrict__ stats) {
+    __shared__ uint16_t wcache[kCapCache];
     const int lane = threadIdx.x & 31;
     const int32_t grp = blockIdx.x;
     WarpStats st{0, 0};
@@ -118,8 +136,8 @@ __global__ void __launch_bounds__(32) gp_pack_fifo(Snapshot s, const PrepApp* __
             if (blocked) d = -2;                                   // never evaluated (resource.go:252)
             else {
                 d = -1;
-                if (!(pa->flags & 4u)) d = pack_app<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, st, lane);
-                if (d < 0 && !(pa->flags & 2u)) blocked = true;   // resource.go:244-253
+                if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, wcache, st, lane);
+                if (d < 0 && !(pa->flags & kAppSkipIfNoFit)) blocked = true;   // resource.go:244-253
             }
             if (lane == 0) driver_node[app] = d;
         }
@@ -152,22 +170,30 @@ __global__ void gp_build_groups(int32_t n_groups, const int32_t* __restrict__ ex
     groups[g] = d;
 }
 
+// snapshot-wide facts: negative gpu availability, per-dimension maxima (bounds for the fast class)
+__device__ __forceinline__ void note_node(SnapMeta* meta, int64_t cv, int64_t mv, int64_t gv) {
+    if (gv < 0) atomicOr(&meta->flags, kSnapGpuNegative);
+    if (cv > 0 && cv > meta->max_avail[0]) atomicMax(&meta->max_avail[0], (long long)cv);
+    if (mv > 0 && mv > meta->max_avail[1]) atomicMax(&meta->max_avail[1], (long long)mv);
+    if (gv > 0 && gv > meta->max_avail[2]) atomicMax(&meta->max_avail[2], (long long)gv);
+}
+
 // executor-order entries -> slots [sbase, sbase+ne)
 __global__ void gp_build_exec_slots(int32_t n_exec, int32_t n_groups,
                                     const int32_t* __restrict__ exec_off, const int32_t* __restrict__ drv_off,
                                     const int32_t* __restrict__ exec_order,
                                     const int64_t* __restrict__ cpu, const int64_t* __restrict__ mem, const int64_t* __restrict__ gpu,
                                     longlong2* __restrict__ pair, int64_t* __restrict__ sgpu, int32_t* __restrict__ slot_node,
-                                    int32_t* __restrict__ node_slot, int* __restrict__ flags) {
+                                    int32_t* __restrict__ node_slot, SnapMeta* __restrict__ meta) {
     int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_exec) return;
     int32_t g = find_group(exec_off, n_groups, e);
     int32_t slot = exec_off[g] + drv_off[g] + (e - exec_off[g]);
     int32_t node = exec_order[e];
-    pair[slot] = make_longlong2(cpu[node], mem[node]);
-    int64_t gv = gpu ? gpu[node] : 0;
+    const int64_t cv = cpu[node], mv = mem[node], gv = gpu ? gpu[node] : 0;
+    pair[slot] = make_longlong2(cv, mv);
     sgpu[slot] = gv;
-    if (gv < 0) atomicOr(flags, kSnapGpuNegative);
+    note_node(meta, cv, mv, gv);
     slot_node[slot] = node;
     node_slot[node] = slot;
 }
@@ -178,7 +204,7 @@ __global__ void gp_build_driver_slots(int32_t n_drv, int32_t n_groups,
                                       const int32_t* __restrict__ drv_order,
                                       const int64_t* __restrict__ cpu, const int64_t* __restrict__ mem, const int64_t* __restrict__ gpu,
                                       longlong2* __restrict__ pair, int64_t* __restrict__ sgpu, int32_t* __restrict__ slot_node,
-                                      const int32_t* __restrict__ node_slot, int32_t* __restrict__ drv_slot, int* __restrict__ flags) {
+                                      const int32_t* __restrict__ node_slot, int32_t* __restrict__ drv_slot, SnapMeta* __restrict__ meta) {
     int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_drv) return;
     int32_t g = find_group(drv_off, n_groups, j);
@@ -191,10 +217,10 @@ __global__ void gp_build_driver_slots(int32_t n_drv, int32_t n_groups,
     } else {
         int32_t local = ne + (j - drv_off[g]);
         int32_t slot = sbase + local;
-        pair[slot] = make_longlong2(cpu[node], mem[node]);
-        int64_t gv = gpu ? gpu[node] : 0;
+        const int64_t cv = cpu[node], mv = mem[node], gv = gpu ? gpu[node] : 0;
+        pair[slot] = make_longlong2(cv, mv);
         sgpu[slot] = gv;
-        if (gv < 0) atomicOr(flags, kSnapGpuNegative);
+        note_node(meta, cv, mv, gv);
         slot_node[slot] = node;
         drv_slot[j] = local;
     }
@@ -236,8 +262,12 @@ struct gp_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // prep start, pack start, pack end
-    bool ev_valid = false;
+    static constexpr int kLanes = 3;       // H2D / kernels / D2H of consecutive chunks overlap across lanes
+    static constexpr int kMaxChunks = 16;
+    cudaStream_t lane[kLanes] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kMaxChunks][3] = {};    // per chunk: prep start, pack start, pack end
+    cudaEvent_t ev_ready = nullptr, ev_done[kLanes] = {nullptr, nullptr, nullptr};
+    int ev_chunks = 0;
     std::string err;
 
     // snapshot
@@ -257,6 +287,18 @@ struct gp_ctx {
 };
 
 static thread_local std::string g_create_error;
+// dev_misc layout: [0] error bits (int), [8..24) stats (2 x u64), [32..32+4*kMaxChunks) per-chunk work counters
+static constexpr size_t kMiscCounters = 32, kMiscBytes = 32 + 4 * 16;
+static constexpr int32_t kChunkApps = 24576;   // apps per pipelined chunk of gp_pack_batch (~1.5 MB H2D, ~70 us of kernel)
+
+static cudaError_t create_aux(gp_ctx* c) {
+    cudaError_t e;
+    for (auto& l : c->lane) if ((e = cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (auto& row : c->ev) for (auto& ev : row) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (auto& ev : c->ev_done) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
 
 #define GP_CUDA(ctx, expr)                                                                     \
     do {                                                                                       \
@@ -279,7 +321,7 @@ static Snapshot make_snapshot(const gp_ctx* c) {
     s.slot_node = c->slot_node.as<int32_t>();
     s.drv_slot = c->drv_slot.as<int32_t>();
     s.groups = c->groups.as<GroupDesc>();
-    s.flags = c->snap_flags.as<int>();
+    s.meta = c->snap_flags.as<SnapMeta>();
     s.n_groups = c->n_groups;
     s.n_slots = c->n_slots;
     return s;
@@ -322,10 +364,9 @@ gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
     c->sm_count = prop.multiProcessorCount;
     if ((e = cudaSetDevice(dev)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreate(&c->ev[0])) != cudaSuccess || (e = cudaEventCreate(&c->ev[1])) != cudaSuccess ||
-        (e = cudaEventCreate(&c->ev[2])) != cudaSuccess ||
+        (e = create_aux(c)) != cudaSuccess ||
         (e = cudaHostAlloc(&c->pinned_misc, 64, cudaHostAllocDefault)) != cudaSuccess ||
-        (e = c->dev_misc.reserve(64)) != cudaSuccess || (e = c->snap_flags.reserve(16)) != cudaSuccess) {
+        (e = c->dev_misc.reserve(kMiscBytes)) != cudaSuccess || (e = c->snap_flags.reserve(sizeof(SnapMeta))) != cudaSuccess) {
         g_create_error = std::string("gp_create: ") + cudaGetErrorString(e);
         delete c;
         return GP_ERR_CUDA;
@@ -344,7 +385,10 @@ void gp_destroy(gp_ctx* c) {
                       &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
-    for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& row : c->ev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    for (cudaEvent_t e : c->ev_done) if (e) cudaEventDestroy(e);
+    for (cudaStream_t l : c->lane) if (l) cudaStreamDestroy(l);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -385,19 +429,19 @@ static gp_status build_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_
     GP_CUDA(c, c->groups.reserve(sizeof(GroupDesc) * (size_t)dn->n_groups));
     GP_CUDA(c, cudaMemsetAsync(c->slot_node.p, 0xFF, sizeof(int32_t) * (size_t)(n_slots + 1), st));
     GP_CUDA(c, cudaMemsetAsync(c->node_slot.p, 0xFF, sizeof(int32_t) * (size_t)(dn->n_nodes + 1), st));
-    GP_CUDA(c, cudaMemsetAsync(c->snap_flags.p, 0, sizeof(int), st));
+    GP_CUDA(c, cudaMemsetAsync(c->snap_flags.p, 0, sizeof(SnapMeta), st));
     const int T = 256;
     gp_build_groups<<<(dn->n_groups + T - 1) / T, T, 0, st>>>(dn->n_groups, dn->exec_off, dn->drv_off, c->groups.as<GroupDesc>());
     if (n_exec > 0)
         gp_build_exec_slots<<<(n_exec + T - 1) / T, T, 0, st>>>(
             n_exec, dn->n_groups, dn->exec_off, dn->drv_off, dn->exec_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
             dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
-            c->node_slot.as<int32_t>(), c->snap_flags.as<int>());
+            c->node_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
     if (n_drv > 0)
         gp_build_driver_slots<<<(n_drv + T - 1) / T, T, 0, st>>>(
             n_drv, dn->n_groups, dn->exec_off, dn->drv_off, dn->drv_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
             dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
-            c->node_slot.as<int32_t>(), c->drv_slot.as<int32_t>(), c->snap_flags.as<int>());
+            c->node_slot.as<int32_t>(), c->drv_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
     GP_CUDA(c, cudaGetLastError());
     c->n_nodes = dn->n_nodes; c->n_groups = dn->n_groups; c->n_exec = n_exec; c->n_drv = n_drv; c->n_slots = n_slots;
     c->have_snapshot = true;
@@ -523,15 +567,20 @@ gp_status gp_get_snapshot(gp_ctx* c, int64_t* cpu, int64_t* mem, int64_t* gpu) {
 template <int ALGO>
 static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepApp* prep, int32_t n_apps,
                         int32_t* driver_node, int32_t* executor_nodes, int2* scratch, unsigned long long* stats,
-                        cudaStream_t st) {
+                        unsigned int* next_app, cudaStream_t st) {
     if (mode == GP_MODE_INDEPENDENT) {
-        const int T = 256;
-        int64_t warps_needed = n_apps;
-        int blocks = (int)((warps_needed * 32 + T - 1) / T);
-        int max_blocks = c->sm_count * 8;
+        // persistent grid: as many CTAs as fit on the device (or fewer for small batches)
+        static int per_sm = 0;
+        if (per_sm == 0) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gp_pack_independent<ALGO>, kPackThreads, 0);
+            if (per_sm < 1) per_sm = 1;
+        }
+        int64_t blocks = ((int64_t)n_apps * 32 + kPackThreads - 1) / kPackThreads;
+        int64_t max_blocks = (int64_t)c->sm_count * per_sm;
         if (blocks > max_blocks) blocks = max_blocks;
         if (blocks < 1) blocks = 1;
-        gp_pack_independent<ALGO><<<blocks, T, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats);
+        gp_pack_independent<ALGO><<<(int)blocks, kPackThreads, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch,
+                                                                       stats, next_app);
     } else if (mode == GP_MODE_FIFO_REFERENCE) {
         gp_pack_fifo<ALGO, 1><<<s.n_groups, 32, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats);
     } else {
@@ -539,38 +588,57 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
     }
 }
 
-// everything device-resident; enqueues prep + pack on `st`
-static gp_status pack_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode mode, gp_results* dout, cudaStream_t st) {
-    const int32_t q = da->n_apps;
+// Device-resident apps [lo, hi): enqueue prep + pack on `st`; chunk index selects the timing events.
+static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int32_t hi, gp_algo algo, gp_mode mode,
+                                   gp_results* dout, int2* scratch, cudaStream_t st, int chunk) {
+    const int32_t q = hi - lo;
+    if (q <= 0) return GP_OK;
     int* d_err = c->dev_misc.as<int>();
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(c->dev_misc.as<char>() + 8);
-    GP_CUDA(c, cudaMemsetAsync(c->dev_misc.p, 0, 32, st));
+    PrepApp* prep = c->prep.as<PrepApp>() + lo;
+    unsigned int* next_app = reinterpret_cast<unsigned int*>(c->dev_misc.as<char>() + kMiscCounters) + chunk;
+    const int T = 256;
+    GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
+    gp_prep_apps<<<(q + T - 1) / T, T, 0, st>>>(
+        q, da->drv_cpu_milli + lo, da->drv_mem_bytes + lo, da->drv_gpu ? da->drv_gpu + lo : nullptr, da->exe_cpu_milli + lo,
+        da->exe_mem_bytes + lo, da->exe_gpu ? da->exe_gpu + lo : nullptr, da->exe_count + lo, da->group ? da->group + lo : nullptr,
+        da->skip_if_no_fit ? da->skip_if_no_fit + lo : nullptr, da->exec_out_off + lo, c->n_groups, dout->executor_nodes_cap,
+        c->snap_flags.as<SnapMeta>(), prep, d_err);
+    Snapshot s = make_snapshot(c);
+    GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
+    if (algo == GP_TIGHTLY_PACK)
+        launch_pack<0>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
+    else
+        launch_pack<1>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
+    GP_CUDA(c, cudaGetLastError());
+    GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
+    c->last.kernel_launches += 2;
+    return GP_OK;
+}
+
+// common prologue: buffers, counters
+static gp_status pack_begin(gp_ctx* c, int32_t q, gp_algo algo, const gp_results* dout, int2** scratch, cudaStream_t st) {
+    GP_CUDA(c, cudaMemsetAsync(c->dev_misc.p, 0, kMiscBytes, st));
     c->last = gp_stats{};
-    c->ev_valid = false;
+    c->ev_chunks = 0;
+    *scratch = nullptr;
     if (q == 0) return GP_OK;
     GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));
-    int2* scratch = nullptr;
     if (algo == GP_DISTRIBUTE_EVENLY) {
         GP_CUDA(c, c->scratch.reserve(sizeof(int2) * (size_t)(dout->executor_nodes_cap + 1)));
-        scratch = c->scratch.as<int2>();
+        *scratch = c->scratch.as<int2>();
     }
-    const int T = 256;
-    GP_CUDA(c, cudaEventRecord(c->ev[0], st));
-    gp_prep_apps<<<(q + T - 1) / T, T, 0, st>>>(q, da->drv_cpu_milli, da->drv_mem_bytes, da->drv_gpu, da->exe_cpu_milli,
-                                                da->exe_mem_bytes, da->exe_gpu, da->exe_count, da->group,
-                                                da->skip_if_no_fit, da->exec_out_off, c->n_groups,
-                                                dout->executor_nodes_cap, c->prep.as<PrepApp>(), d_err);
-    Snapshot s = make_snapshot(c);
-    GP_CUDA(c, cudaEventRecord(c->ev[1], st));
-    if (algo == GP_TIGHTLY_PACK)
-        launch_pack<0>(c, mode, s, c->prep.as<PrepApp>(), q, dout->driver_node, dout->executor_nodes, scratch, d_stats, st);
-    else
-        launch_pack<1>(c, mode, s, c->prep.as<PrepApp>(), q, dout->driver_node, dout->executor_nodes, scratch, d_stats, st);
-    GP_CUDA(c, cudaGetLastError());
-    GP_CUDA(c, cudaEventRecord(c->ev[2], st));
-    c->ev_valid = true;
-    c->last.kernel_launches = 2;
     return GP_OK;
+}
+
+// everything device-resident; enqueues prep + pack on `st`
+static gp_status pack_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode mode, gp_results* dout, cudaStream_t st) {
+    int2* scratch = nullptr;
+    gp_status s = pack_begin(c, da->n_apps, algo, dout, &scratch, st);
+    if (s != GP_OK || da->n_apps == 0) return s;
+    s = pack_device_range(c, da, 0, da->n_apps, algo, mode, dout, scratch, st, 0);
+    if (s == GP_OK) c->ev_chunks = 1;
+    return s;
 }
 
 static gp_status check_args(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, const gp_results* out, const char* who) {
@@ -585,12 +653,14 @@ static gp_status check_args(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode m
     return GP_OK;
 }
 
-// after the stream has been synchronised: event times of the last pack
+// after the streams have been synchronised: event times of the last pack, summed over its chunks
 static void fill_kernel_times(gp_ctx* c) {
-    if (!c->ev_valid) return;
-    float a = 0.f, b = 0.f;
-    if (cudaEventElapsedTime(&a, c->ev[0], c->ev[1]) == cudaSuccess) c->last.prep_kernel_ns = (int64_t)(a * 1.0e6);
-    if (cudaEventElapsedTime(&b, c->ev[1], c->ev[2]) == cudaSuccess) c->last.pack_kernel_ns = (int64_t)(b * 1.0e6);
+    c->last.prep_kernel_ns = 0; c->last.pack_kernel_ns = 0;
+    for (int i = 0; i < c->ev_chunks; ++i) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, c->ev[i][0], c->ev[i][1]) == cudaSuccess) c->last.prep_kernel_ns += (int64_t)(a * 1.0e6);
+        if (cudaEventElapsedTime(&b, c->ev[i][1], c->ev[i][2]) == cudaSuccess) c->last.pack_kernel_ns += (int64_t)(b * 1.0e6);
+    }
 }
 
 static gp_status decode_device_error(gp_ctx* c, int err) {
@@ -653,26 +723,66 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
     GP_CUDA(c, c->a_off.reserve(sizeof(int64_t) * (size_t)(q + 1)));
     GP_CUDA(c, c->r_driver.reserve(b32));
     GP_CUDA(c, c->r_exec.reserve(sizeof(int32_t) * (size_t)(total + 1)));
+    if (a->drv_gpu) GP_CUDA(c, c->a_dgpu.reserve(b64));
+    if (a->exe_gpu) GP_CUDA(c, c->a_egpu.reserve(b64));
+    if (a->group) GP_CUDA(c, c->a_group.reserve(b32));
+    if (a->skip_if_no_fit) GP_CUDA(c, c->a_skip.reserve((size_t)q));
     gp_apps da = *a;
-    GP_CUDA(c, cudaMemcpyAsync(c->a_dcpu.p, a->drv_cpu_milli, b64, cudaMemcpyHostToDevice, st)); da.drv_cpu_milli = c->a_dcpu.as<int64_t>();
-    GP_CUDA(c, cudaMemcpyAsync(c->a_dmem.p, a->drv_mem_bytes, b64, cudaMemcpyHostToDevice, st)); da.drv_mem_bytes = c->a_dmem.as<int64_t>();
-    GP_CUDA(c, cudaMemcpyAsync(c->a_ecpu.p, a->exe_cpu_milli, b64, cudaMemcpyHostToDevice, st)); da.exe_cpu_milli = c->a_ecpu.as<int64_t>();
-    GP_CUDA(c, cudaMemcpyAsync(c->a_emem.p, a->exe_mem_bytes, b64, cudaMemcpyHostToDevice, st)); da.exe_mem_bytes = c->a_emem.as<int64_t>();
-    GP_CUDA(c, cudaMemcpyAsync(c->a_count.p, a->exe_count, b32, cudaMemcpyHostToDevice, st)); da.exe_count = c->a_count.as<int32_t>();
-    GP_CUDA(c, cudaMemcpyAsync(c->a_off.p, off, sizeof(int64_t) * (size_t)(q + 1), cudaMemcpyHostToDevice, st)); da.exec_out_off = c->a_off.as<int64_t>();
-    if (a->drv_gpu) { GP_CUDA(c, c->a_dgpu.reserve(b64)); GP_CUDA(c, cudaMemcpyAsync(c->a_dgpu.p, a->drv_gpu, b64, cudaMemcpyHostToDevice, st)); da.drv_gpu = c->a_dgpu.as<int64_t>(); }
-    if (a->exe_gpu) { GP_CUDA(c, c->a_egpu.reserve(b64)); GP_CUDA(c, cudaMemcpyAsync(c->a_egpu.p, a->exe_gpu, b64, cudaMemcpyHostToDevice, st)); da.exe_gpu = c->a_egpu.as<int64_t>(); }
-    if (a->group) { GP_CUDA(c, c->a_group.reserve(b32)); GP_CUDA(c, cudaMemcpyAsync(c->a_group.p, a->group, b32, cudaMemcpyHostToDevice, st)); da.group = c->a_group.as<int32_t>(); }
-    if (a->skip_if_no_fit) { GP_CUDA(c, c->a_skip.reserve((size_t)q)); GP_CUDA(c, cudaMemcpyAsync(c->a_skip.p, a->skip_if_no_fit, (size_t)q, cudaMemcpyHostToDevice, st)); da.skip_if_no_fit = c->a_skip.as<uint8_t>(); }
-
+    da.drv_cpu_milli = c->a_dcpu.as<int64_t>(); da.drv_mem_bytes = c->a_dmem.as<int64_t>();
+    da.exe_cpu_milli = c->a_ecpu.as<int64_t>(); da.exe_mem_bytes = c->a_emem.as<int64_t>();
+    da.exe_count = c->a_count.as<int32_t>(); da.exec_out_off = c->a_off.as<int64_t>();
+    da.drv_gpu = a->drv_gpu ? c->a_dgpu.as<int64_t>() : nullptr;
+    da.exe_gpu = a->exe_gpu ? c->a_egpu.as<int64_t>() : nullptr;
+    da.group = a->group ? c->a_group.as<int32_t>() : nullptr;
+    da.skip_if_no_fit = a->skip_if_no_fit ? c->a_skip.as<uint8_t>() : nullptr;
     gp_results dr;
     dr.driver_node = c->r_driver.as<int32_t>();
     dr.executor_nodes = c->r_exec.as<int32_t>();
     dr.executor_nodes_cap = total;
-    s = pack_device(c, &da, algo, mode, &dr, st);
+
+    // Independent decisions are chunked and the chunks rotate over kLanes streams, so the H2D of
+    // chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap (PCIe is full duplex).
+    // FIFO modes are one sequential pass: a single chunk.
+    int n_chunks = 1;
+    if (mode == GP_MODE_INDEPENDENT && q >= 2 * kChunkApps) {
+        n_chunks = (q + kChunkApps - 1) / kChunkApps;
+        if (n_chunks > gp_ctx::kMaxChunks) n_chunks = gp_ctx::kMaxChunks;
+    }
+    int2* scratch = nullptr;
+    s = pack_begin(c, q, algo, &dr, &scratch, st);
     if (s != GP_OK) return s;
-    GP_CUDA(c, cudaMemcpyAsync(out->driver_node, dr.driver_node, b32, cudaMemcpyDeviceToHost, st));
-    if (total > 0) GP_CUDA(c, cudaMemcpyAsync(out->executor_nodes, dr.executor_nodes, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaEventRecord(c->ev_ready, st));      // snapshot + zeroed counters are ready
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int32_t lo = (int32_t)((int64_t)q * ch / n_chunks), hi = (int32_t)((int64_t)q * (ch + 1) / n_chunks);
+        const size_t n = (size_t)(hi - lo);
+        cudaStream_t ls = n_chunks == 1 ? st : c->lane[ch % gp_ctx::kLanes];
+        if (n_chunks > 1) GP_CUDA(c, cudaStreamWaitEvent(ls, c->ev_ready, 0));
+#define GP_H2D(dst, src, type, extra)                                                                           \
+        GP_CUDA(c, cudaMemcpyAsync((type*)(dst) + lo, (src) + lo, sizeof(type) * (n + (extra)), cudaMemcpyHostToDevice, ls))
+        GP_H2D(c->a_dcpu.p, a->drv_cpu_milli, int64_t, 0); GP_H2D(c->a_dmem.p, a->drv_mem_bytes, int64_t, 0);
+        GP_H2D(c->a_ecpu.p, a->exe_cpu_milli, int64_t, 0); GP_H2D(c->a_emem.p, a->exe_mem_bytes, int64_t, 0);
+        GP_H2D(c->a_count.p, a->exe_count, int32_t, 0);
+        GP_H2D(c->a_off.p, off, int64_t, 1);
+        if (a->drv_gpu) GP_H2D(c->a_dgpu.p, a->drv_gpu, int64_t, 0);
+        if (a->exe_gpu) GP_H2D(c->a_egpu.p, a->exe_gpu, int64_t, 0);
+        if (a->group) GP_H2D(c->a_group.p, a->group, int32_t, 0);
+        if (a->skip_if_no_fit) GP_H2D(c->a_skip.p, a->skip_if_no_fit, uint8_t, 0);
+#undef GP_H2D
+        s = pack_device_range(c, &da, lo, hi, algo, mode, &dr, scratch, ls, ch);
+        if (s != GP_OK) return s;
+        GP_CUDA(c, cudaMemcpyAsync(out->driver_node + lo, dr.driver_node + lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ls));
+        const int64_t e0 = off[lo], e1 = off[hi];
+        if (e1 > e0)
+            GP_CUDA(c, cudaMemcpyAsync(out->executor_nodes + e0, dr.executor_nodes + e0, sizeof(int32_t) * (size_t)(e1 - e0),
+                                       cudaMemcpyDeviceToHost, ls));
+    }
+    c->ev_chunks = n_chunks;
+    if (n_chunks > 1) {
+        for (int l = 0; l < gp_ctx::kLanes && l < n_chunks; ++l) {
+            GP_CUDA(c, cudaEventRecord(c->ev_done[l], c->lane[l]));
+            GP_CUDA(c, cudaStreamWaitEvent(st, c->ev_done[l], 0));
+        }
+    }
     GP_CUDA(c, cudaMemcpyAsync(c->pinned_misc, c->dev_misc.p, 32, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaStreamSynchronize(st));
     const unsigned long long* sv = reinterpret_cast<const unsigned long long*>((const char*)c->pinned_misc + 8);

@@ -42,8 +42,16 @@ enum : int {
     kErrBadOffsets = 8,        // exec_out_off inconsistent with exe_count / capacity
 };
 
-// snapshot flags (device int)
+// snapshot flags (device int) -- SnapMeta::flags
 enum : int { kSnapGpuNegative = 1 };
+
+// Per-snapshot facts the kernels need: flags + the largest availability per dimension (a node's
+// availability only ever decreases afterwards, so the maxima stay upper bounds in FIFO modes).
+struct SnapMeta {
+    int flags;
+    int pad;
+    long long max_avail[3];   // cpu milli, mem bytes, gpu
+};
 
 // How to divide by one executor-request dimension.
 enum : uint32_t { kDivInf = 0, kDivMagic = 1, kDivShift = 2, kDivSlow = 3 };
@@ -63,8 +71,9 @@ struct __align__(16) PrepApp {
     int32_t count;       // MinExecutorCount
     int32_t group;
     int32_t lmax;        // max executors the driver can displace on its own node (<= count)
-    uint32_t flags;      // bit0: uses gpu dim, bit1: skip_if_no_fit, bit2: invalid
+    uint32_t flags;      // bit0: uses gpu dim, bit1: skip_if_no_fit, bit2: invalid, bit3: fast class
 };
+enum : uint32_t { kAppUsesGpu = 1u, kAppSkipIfNoFit = 2u, kAppInvalid = 4u, kAppFast = 8u };
 static_assert(sizeof(PrepApp) == 128, "PrepApp layout");
 
 struct GroupDesc {
@@ -82,7 +91,7 @@ struct Snapshot {
     int32_t* slot_node;    // [n_slots] caller's node index, -1 = unused spare
     const int32_t* drv_slot; // [n_drv] group-local slot of each driver candidate
     const GroupDesc* groups;
-    const int* flags;      // kSnap*
+    const SnapMeta* meta;
     int32_t n_groups;
     int32_t n_slots;
 };
@@ -90,28 +99,46 @@ struct Snapshot {
 // ---------------------------------------------------------------------------------------------
 // capacity arithmetic
 // ---------------------------------------------------------------------------------------------
+// Executors of request e that fit into `a` free units:  a < 0 -> 0 (reserved > avail in this
+// dimension, resources.go:239); e == 0 -> unlimited; else floor(a / e).
+// Exact division by the warp-uniform request: e = e' << sh, a >= 0  =>  floor(a/e) = floor((a >> sh)/e');
+// for xs = a >> sh < 2^32 and e' < 2^32, floor(xs/e') = mulhi64(magic, xs) with
+// magic = floor((2^64-1)/e') + 1 (Lemire, Kaser, Kurz 2019, N = 32).
 
-// Executors of request `p.e` that fit into `a` free units, clamped to k.
-// Exactness: a >= 0, e = e' << sh  =>  floor(a/e) = floor((a >> sh)/e').  For xs = a >> sh < 2^32
-// and e' < 2^32, floor(xs/e') = mulhi64(magic, xs) with magic = floor((2^64-1)/e') + 1
-// (Lemire/Kaser/Kurz 2019, N = 32).  Anything else takes the 64-bit divide.
+__device__ __noinline__ uint64_t udiv64(uint64_t a, uint64_t b) { return a / b; }
+
+// ---- general class: any int64 request ----------------------------------------------------------
 __device__ __forceinline__ uint32_t cap_dim(int64_t a, const DimDiv& p, uint32_t k) {
-    if (a < 0) return 0;                       // reserved(=0) > avail in this dim (resources.go:239)
-    if (p.kind == kDivInf) return k;           // zero request never limits
+    if (a < 0) return 0;
+    if (p.kind == kDivInf) return k;
     uint64_t xs = (uint64_t)a >> p.sh;
     uint64_t q;
     if (p.kind == kDivShift) q = xs;
     else if (p.kind == kDivMagic && (xs >> 32) == 0) q = __umul64hi(p.magic, xs);
-    else q = (uint64_t)a / (uint64_t)p.e;
+    else q = udiv64((uint64_t)a, (uint64_t)p.e);
     return q < (uint64_t)k ? (uint32_t)q : k;
 }
 
-// cap(n | reserved = r) for a single node with an arbitrary reservation (the driver's node).
-__device__ __forceinline__ uint32_t cap_dim_reserved(int64_t a, int64_t r, int64_t e, uint32_t k) {
-    if (r > a) return 0;
-    if (e == 0) return k;
-    uint64_t q = (uint64_t)(a - r) / (uint64_t)e;
-    return q < (uint64_t)k ? (uint32_t)q : k;
+// ---- fast class: every dimension has (max_avail >> sh) < 2^32 and e' < 2^32 (decided per app by
+// gp_prep_apps from SnapMeta::max_avail) -> branch-free 32-bit arithmetic ---------------------------
+struct FastDim {
+    uint32_t m_lo, m_hi;   // magic
+    uint32_t sh;           // 0..63
+    uint32_t mode;         // kDivMagic / kDivShift / kDivInf
+};
+__device__ __forceinline__ FastDim fast_dim(const DimDiv& d) {
+    FastDim f;
+    f.m_lo = (uint32_t)d.magic; f.m_hi = (uint32_t)(d.magic >> 32); f.sh = d.sh; f.mode = d.kind;
+    return f;
+}
+__device__ __forceinline__ uint32_t fast_q(int64_t a, const FastDim& p) {
+    const uint32_t lo = (uint32_t)a, hi = (uint32_t)((uint64_t)a >> 32);
+    const bool big = p.sh >= 32;
+    const uint32_t xs = __funnelshift_r(big ? hi : lo, big ? 0u : hi, p.sh & 31);   // (a >> sh), known < 2^32
+    uint32_t q = (uint32_t)(((uint64_t)p.m_hi * xs + __umulhi(p.m_lo, xs)) >> 32);  // mulhi64(magic, xs)
+    q = p.mode == kDivShift ? xs : q;
+    q = p.mode == kDivInf ? 0xFFFFFFFFu : q;
+    return (int32_t)hi < 0 ? 0u : q;
 }
 
 template <bool MUTABLE>
@@ -145,80 +172,108 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     }
     return v;
 }
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
 
 // ---------------------------------------------------------------------------------------------
-// per-application state shared by the phases
+// per-application capacity calculators (registers of one warp)
 // ---------------------------------------------------------------------------------------------
-struct AppRegs {
+template <bool FAST> struct Caps;
+
+template <> struct Caps<true> {
+    FastDim cpu, mem, gpu;
     int64_t d_cpu, d_mem, d_gpu;
-    DimDiv cpu, mem, gpu;
-    int64_t out_off;
+    int64_t e_cpu, e_mem, e_gpu;
     uint32_t k;
-    uint32_t lmax;
     bool use_gpu;
+    __device__ __forceinline__ void init(const PrepApp* pa, bool ug) {
+        d_cpu = pa->drv[0]; d_mem = pa->drv[1]; d_gpu = pa->drv[2];
+        cpu = fast_dim(pa->div[0]); mem = fast_dim(pa->div[1]); gpu = fast_dim(pa->div[2]);
+        e_cpu = pa->div[0].e; e_mem = pa->div[1].e; e_gpu = pa->div[2].e;
+        k = (uint32_t)pa->count; use_gpu = ug;
+    }
+    // cap(n | reserved = r) clamped to k
+    template <bool MUT>
+    __device__ __forceinline__ uint32_t cap(const Snapshot& s, int32_t slot, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
+        longlong2 v = load_pair<MUT>(s.pair + slot);
+        uint32_t c = umin3(fast_q(v.x - r_cpu, cpu), fast_q(v.y - r_mem, mem), k);
+        if (use_gpu) c = min(c, fast_q(load_gpu<MUT>(s.gpu + slot) - r_gpu, gpu));
+        return c;
+    }
+    template <bool MUT>
+    __device__ __forceinline__ uint32_t cap0(const Snapshot& s, int32_t slot) const {
+        longlong2 v = load_pair<MUT>(s.pair + slot);
+        uint32_t c = umin3(fast_q(v.x, cpu), fast_q(v.y, mem), k);
+        if (use_gpu) c = min(c, fast_q(load_gpu<MUT>(s.gpu + slot), gpu));
+        return c;
+    }
 };
 
-template <bool MUTABLE>
-__device__ __forceinline__ uint32_t cap0_at(const Snapshot& s, int32_t slot, const AppRegs& a) {
-    longlong2 v = load_pair<MUTABLE>(s.pair + slot);
-    uint32_t c = cap_dim(v.x, a.cpu, a.k);
-    uint32_t m = cap_dim(v.y, a.mem, a.k);
-    c = c < m ? c : m;
-    if (a.use_gpu) {
-        uint32_t g = cap_dim(load_gpu<MUTABLE>(s.gpu + slot), a.gpu, a.k);
-        c = c < g ? c : g;
+template <> struct Caps<false> {
+    DimDiv cpu, mem, gpu;
+    int64_t d_cpu, d_mem, d_gpu;
+    int64_t e_cpu, e_mem, e_gpu;
+    uint32_t k;
+    bool use_gpu;
+    __device__ __forceinline__ void init(const PrepApp* pa, bool ug) {
+        d_cpu = pa->drv[0]; d_mem = pa->drv[1]; d_gpu = pa->drv[2];
+        cpu = pa->div[0]; mem = pa->div[1]; gpu = pa->div[2];
+        e_cpu = cpu.e; e_mem = mem.e; e_gpu = gpu.e;
+        k = (uint32_t)pa->count; use_gpu = ug;
     }
-    return c;
-}
-
-// cap(d | drv) for the chosen driver's slot
-template <bool MUTABLE>
-__device__ __forceinline__ uint32_t capd_at(const Snapshot& s, int32_t slot, const AppRegs& a) {
-    longlong2 v = load_pair<MUTABLE>(s.pair + slot);
-    uint32_t c = cap_dim_reserved(v.x, a.d_cpu, a.cpu.e, a.k);
-    uint32_t m = cap_dim_reserved(v.y, a.d_mem, a.mem.e, a.k);
-    c = c < m ? c : m;
-    // the gpu dim must be honoured whenever it can bind; with !use_gpu it cannot (request 0, avail >= 0)
-    if (a.use_gpu) {
-        uint32_t g = cap_dim_reserved(load_gpu<MUTABLE>(s.gpu + slot), a.d_gpu, a.gpu.e, a.k);
-        c = c < g ? c : g;
+    template <bool MUT>
+    __device__ __forceinline__ uint32_t cap(const Snapshot& s, int32_t slot, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
+        longlong2 v = load_pair<MUT>(s.pair + slot);
+        uint32_t c = min(cap_dim(v.x - r_cpu, cpu, k), cap_dim(v.y - r_mem, mem, k));
+        if (use_gpu) c = min(c, cap_dim(load_gpu<MUT>(s.gpu + slot) - r_gpu, gpu, k));
+        return c;
     }
-    return c;
-}
+    template <bool MUT>
+    __device__ __forceinline__ uint32_t cap0(const Snapshot& s, int32_t slot) const { return cap<MUT>(s, slot, 0, 0, 0); }
+};
 
 // driverResources.GreaterThan(available) == false  (binpack.go:69)
-template <bool MUTABLE>
-__device__ __forceinline__ bool driver_fits(const Snapshot& s, int32_t slot, const AppRegs& a) {
-    longlong2 v = load_pair<MUTABLE>(s.pair + slot);
+template <bool MUT, class C>
+__device__ __forceinline__ bool driver_fits(const Snapshot& s, int32_t slot, const C& a) {
+    longlong2 v = load_pair<MUT>(s.pair + slot);
     bool ok = !(a.d_cpu > v.x) && !(a.d_mem > v.y);
-    if (a.use_gpu) ok = ok && !(a.d_gpu > load_gpu<MUTABLE>(s.gpu + slot));
+    if (a.use_gpu) ok = ok && !(a.d_gpu > load_gpu<MUT>(s.gpu + slot));
     return ok;
 }
 
+// SubtractUsageIfExists for one slot (resources.go:129-135): avail -= mult * (cpu, mem, gpu)
+__device__ __forceinline__ void charge(const Snapshot& s, int32_t slot, long long mult, int64_t cpu, int64_t mem, int64_t gpu) {
+    longlong2* pp = s.pair + slot;
+    longlong2 v = *pp;
+    v.x -= mult * cpu; v.y -= mult * mem;
+    *pp = v;
+    if (gpu != 0) s.gpu[slot] -= mult * gpu;
+}
+
 struct WarpStats { unsigned long long nodes; unsigned long long drivers; };
+
+constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 capacities (uint16)
 
 // ---------------------------------------------------------------------------------------------
 // One application, one warp.  Returns the driver's node index (>= 0) or -1.
 // ALGO: 0 tightly-pack, 1 distribute-evenly.  FIFO_MODE: 0 none, 1 reference usage, 2 exact usage
 // (then the snapshot is read with plain loads and the placement is subtracted from it).
+// wcache: this warp's kCapCache x uint16 scratch in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, int FIFO_MODE>
-__device__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, int32_t* __restrict__ executor_nodes,
-                            int2* __restrict__ scratch, WarpStats& st, int lane) {
+template <int ALGO, int FIFO_MODE, bool FAST>
+__device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepApp* __restrict__ pa,
+                                                 int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
+                                                 uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
     constexpr bool MUT = FIFO_MODE != 0;
-    AppRegs a;
-    a.d_cpu = pa->drv[0]; a.d_mem = pa->drv[1]; a.d_gpu = pa->drv[2];
-    a.cpu = pa->div[0]; a.mem = pa->div[1]; a.gpu = pa->div[2];
-    a.out_off = pa->out_off;
-    a.k = (uint32_t)pa->count;
-    a.lmax = (uint32_t)pa->lmax;
-    const uint32_t flags = pa->flags;
-    a.use_gpu = (flags & 1u) || ((*s.flags) & kSnapGpuNegative);
+    Caps<FAST> a;
+    a.init(pa, (pa->flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
     const GroupDesc g = s.groups[pa->group];
     const uint32_t k = a.k;
+    const uint32_t lmax = (uint32_t)pa->lmax;
     const int32_t ne = g.ne;
-    int32_t* out = executor_nodes + a.out_off;
-    int2* list = scratch ? scratch + a.out_off : nullptr;   // distribute-evenly candidate list
+    const int64_t out_off = pa->out_off;
+    int32_t* out = executor_nodes + out_off;
+    int2* list = scratch ? scratch + out_off : nullptr;   // distribute-evenly candidate list
+    const bool cache_ok = k <= 0xFFFFu;
 
     // ---- phase 1: how many executors fit, walking the executor priority order --------------------
     // P = sum min(cap(n|0), k) over the scanned prefix; m1 = #nodes with cap >= 1.
@@ -229,10 +284,11 @@ __device__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, i
     uint32_t m1 = 0;
     int32_t pos = 0;
     bool early = (k == 0);
-    const unsigned long long need = (unsigned long long)k + a.lmax;
+    const unsigned long long need = (unsigned long long)k + lmax;
     while (!early && pos < ne) {
         int32_t i = pos + lane;
-        uint32_t c = (i < ne) ? cap0_at<MUT>(s, g.sbase + i, a) : 0u;
+        uint32_t c = (i < ne) ? a.template cap0<MUT>(s, g.sbase + i) : 0u;
+        if (cache_ok && i < kCapCache) wcache[i] = (uint16_t)c;
         unsigned has = __ballot_sync(kFull, c != 0);
         if (ALGO == 1) {
             // remember the first k nodes that can host at all: (position, cap)
@@ -246,38 +302,34 @@ __device__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, i
         else early = (m1 >= k + 1);
     }
     st.nodes += (unsigned long long)(pos < ne ? pos : ne);
+    const int32_t cached_end = cache_ok ? (pos < kCapCache ? pos : kCapCache) : 0;
     const bool exact_total = !early;          // scanned everything: P == S0
     if (exact_total && P < k) return -1;      // not even without a driver
 
     // ---- phase 2: first feasible driver candidate (binpack.go:67-85) ----------------------------
     int32_t dslot = -1;
-    uint32_t cd = 0;      // cap(d | drv), clamped
     for (int32_t j0 = 0; j0 < g.nd && dslot < 0; j0 += kWarp) {
         int32_t j = j0 + lane;
         bool feasible = false;
         int32_t ls = -1;
-        uint32_t lcd = 0;
         if (j < g.nd) {
             ls = s.drv_slot[g.dbase + j];
             feasible = driver_fits<MUT>(s, g.sbase + ls, a);
-            if (feasible && ls < ne) {
-                lcd = capd_at<MUT>(s, g.sbase + ls, a);
-                if (exact_total) {
-                    uint32_t c0 = cap0_at<MUT>(s, g.sbase + ls, a);
-                    feasible = (P - c0 + lcd >= k);
-                }
+            if (feasible && exact_total && ls < ne) {
+                // the executor total with the driver on this node must still reach k
+                uint32_t c0 = a.template cap0<MUT>(s, g.sbase + ls);
+                uint32_t cdl = a.template cap<MUT>(s, g.sbase + ls, a.d_cpu, a.d_mem, a.d_gpu);
+                feasible = (P - c0 + cdl >= k);
             }
         }
         unsigned vote = __ballot_sync(kFull, feasible);
         st.drivers += (unsigned long long)((g.nd - j0) < kWarp ? (g.nd - j0) : kWarp);
-        if (vote) {
-            int src = __ffs(vote) - 1;
-            dslot = __shfl_sync(kFull, ls, src);
-            cd = __shfl_sync(kFull, lcd, src);
-        }
+        if (vote) dslot = __shfl_sync(kFull, ls, __ffs(vote) - 1);
     }
     if (dslot < 0) return -1;
     const int32_t driver_node = s.slot_node[g.sbase + dslot];
+    // cap(d | drv): only matters when the driver's node is an executor candidate
+    const uint32_t cd = (dslot < ne && k != 0) ? a.template cap<MUT>(s, g.sbase + dslot, a.d_cpu, a.d_mem, a.d_gpu) : 0u;
 
     // ---- phase 3: emit ExecutorNodes -------------------------------------------------------------
     bool driver_hosts_executor = false;
@@ -286,36 +338,35 @@ __device__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, i
             // node-major: node n receives min(cap_d(n), remaining)  (pack_tightly.go:45-61)
             uint32_t placed = 0;
             for (int32_t p0 = 0; placed < k && p0 < ne; p0 += kWarp) {
-                st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 int32_t i = p0 + lane;
                 uint32_t c = 0;
-                if (i < ne) c = (i == dslot) ? cd : cap0_at<MUT>(s, g.sbase + i, a);
+                if (i == dslot) c = cd;
+                else if (i < cached_end) c = wcache[i];
+                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i);
+                if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 uint32_t incl = warp_incl_scan(c, lane);
                 uint32_t total = __shfl_sync(kFull, incl, kWarp - 1);
                 uint32_t room = k - placed;
                 uint32_t T = total < room ? total : room;
-                uint32_t excl = incl - c;
-                uint32_t take = excl >= T ? 0u : ((c < T - excl) ? c : (T - excl));
-                int32_t node = (i < ne) ? s.slot_node[g.sbase + i] : -1;
-                // cooperative expansion: output j belongs to the first lane with incl > j
-                for (uint32_t j = lane; j < ((T + kWarp - 1) & ~(uint32_t)(kWarp - 1)); j += kWarp) {
-                    int lo = 0;
+                if (T != 0) {
+                    uint32_t excl = incl - c;
+                    uint32_t take = excl >= T ? 0u : ((c < T - excl) ? c : (T - excl));
+                    int32_t node = (take != 0) ? s.slot_node[g.sbase + i] : -1;
+                    // cooperative expansion: output j belongs to the first lane with incl > j
+                    for (uint32_t j = lane; j < ((T + kWarp - 1) & ~(uint32_t)(kWarp - 1)); j += kWarp) {
+                        int lo = 0;
 #pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) {
-                        uint32_t v = __shfl_sync(kFull, incl, lo + step - 1);
-                        if (v <= j) lo += step;
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            uint32_t v = __shfl_sync(kFull, incl, lo + step - 1);
+                            if (v <= j) lo += step;
+                        }
+                        int32_t nd = __shfl_sync(kFull, node, lo & 31);
+                        if (j < T) out[placed + j] = nd;
                     }
-                    int32_t nd = __shfl_sync(kFull, node, lo & 31);
-                    if (j < T) out[placed + j] = nd;
-                }
-                if (FIFO_MODE != 0 && take != 0) {
-                    if (i == dslot) driver_hosts_executor = true;
-                    long long mult = (FIFO_MODE == 1) ? 1 : (long long)take;
-                    longlong2* pp = s.pair + g.sbase + i;
-                    longlong2 v = *pp;
-                    v.x -= mult * a.cpu.e; v.y -= mult * a.mem.e;
-                    *pp = v;
-                    s.gpu[g.sbase + i] -= mult * a.gpu.e;
+                    if (FIFO_MODE != 0 && take != 0) {
+                        if (i == dslot) driver_hosts_executor = true;
+                        charge(s, g.sbase + i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
+                    }
                 }
                 placed += T;
             }
@@ -323,33 +374,30 @@ __device__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, i
             // one round: the first k nodes with cap_d >= 1, in order  (distribute_evenly.go:49-70)
             uint32_t placed = 0;
             for (int32_t p0 = 0; placed < k && p0 < ne; p0 += kWarp) {
-                st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 int32_t i = p0 + lane;
                 uint32_t c = 0;
-                if (i < ne) c = (i == dslot) ? cd : cap0_at<MUT>(s, g.sbase + i, a);
+                if (i == dslot) c = cd;
+                else if (i < cached_end) c = wcache[i];
+                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i);
+                if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 unsigned has = __ballot_sync(kFull, c != 0);
                 uint32_t r = placed + __popc(has & ((1u << lane) - 1u));
                 if (c != 0 && r < k) {
                     out[r] = s.slot_node[g.sbase + i];
                     if (FIFO_MODE != 0) {
                         if (i == dslot) driver_hosts_executor = true;
-                        longlong2* pp = s.pair + g.sbase + i;
-                        longlong2 v = *pp;
-                        v.x -= a.cpu.e; v.y -= a.mem.e;
-                        *pp = v;
-                        s.gpu[g.sbase + i] -= a.gpu.e;
+                        charge(s, g.sbase + i, 1, a.e_cpu, a.e_mem, a.e_gpu);
                     }
                 }
                 placed += __popc(has);
             }
         } else {
             // general rounds over the complete candidate list (m1 <= k entries, in order):
-            // R* = min r with sum min(c, r) >= k; node gets min(c, R*-1) (+1 for the first
-            // k - sum min(c, R*-1) nodes with c >= R*); ExecutorNodes is round-major.
+            // R* = min r with sum min(c, r) >= k; round r hands one executor to every node with
+            // c >= r until k are placed; ExecutorNodes is round-major.
             __syncwarp();
             const uint32_t m = m1;
-            // patch the driver's own entry with cap(d|drv)
-            for (uint32_t t = lane; t < m; t += kWarp) {
+            for (uint32_t t = lane; t < m; t += kWarp) {   // patch the driver's own entry with cap(d|drv)
                 int2 e = list[t];
                 if (e.x == dslot) { e.y = (int)cd; list[t] = e; }
             }
@@ -376,13 +424,7 @@ __device__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, i
                     uint32_t idx = base + __popc(has & ((1u << lane) - 1u));
                     if (in && idx < k) {
                         out[idx] = s.slot_node[g.sbase + e.x];
-                        if (FIFO_MODE == 2 || (FIFO_MODE == 1 && r == 1)) {
-                            longlong2* pp = s.pair + g.sbase + e.x;
-                            longlong2 v = *pp;
-                            v.x -= a.cpu.e; v.y -= a.mem.e;
-                            *pp = v;
-                            s.gpu[g.sbase + e.x] -= a.gpu.e;
-                        }
+                        if (FIFO_MODE == 2 || (FIFO_MODE == 1 && r == 1)) charge(s, g.sbase + e.x, 1, a.e_cpu, a.e_mem, a.e_gpu);
                         if (FIFO_MODE != 0 && e.x == dslot) driver_hosts_executor = true;
                     }
                     base += __popc(has);
@@ -395,16 +437,25 @@ __device__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, i
     if (FIFO_MODE != 0) {
         bool hosted = __any_sync(kFull, driver_hosts_executor);
         __syncwarp();   // executor charges (other lanes) are ordered before the driver charge
-        if (lane == 0 && (FIFO_MODE == 2 || !hosted)) {
-            longlong2* pp = s.pair + g.sbase + dslot;
-            longlong2 v = *pp;
-            v.x -= a.d_cpu; v.y -= a.d_mem;
-            *pp = v;
-            s.gpu[g.sbase + dslot] -= a.d_gpu;
-        }
+        if (lane == 0 && (FIFO_MODE == 2 || !hosted)) charge(s, g.sbase + dslot, 1, a.d_cpu, a.d_mem, a.d_gpu);
         __syncwarp();   // the next application of this queue sees the charged snapshot
     }
     return driver_node;
+}
+
+template <int ALGO, int FIFO_MODE>
+__device__ __noinline__ int32_t pack_app_general(const Snapshot& s, const PrepApp* __restrict__ pa,
+                                                 int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
+                                                 uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
+    return pack_app_impl<ALGO, FIFO_MODE, false>(s, pa, executor_nodes, scratch, wcache, st, lane);
+}
+
+// class dispatch (warp-uniform): fast = 32-bit magic arithmetic, general = any int64 request
+template <int ALGO, int FIFO_MODE>
+__device__ __forceinline__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, int32_t* __restrict__ executor_nodes,
+                                            int2* __restrict__ scratch, uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
+    if (pa->flags & kAppFast) return pack_app_impl<ALGO, FIFO_MODE, true>(s, pa, executor_nodes, scratch, wcache, st, lane);
+    return pack_app_general<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, wcache, st, lane);
 }
 
 }  // namespace gp
