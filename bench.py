@@ -319,8 +319,14 @@ def main():
     h2d = sum(v.nbytes for v in pin.values()) + 3 * 8 * w["nodes"] + 2 * 4 * len(eorder) + 2 * 4 * len(eoff)
     d2h = out_driver.nbytes + 4 * total_exec
 
+    # the snapshot SoA also lives in pinned host memory (what the shim fills per Predicate)
+    pn = {}
+    for k, v in (("cpu", nodes["avail_cpu"]), ("mem", nodes["avail_mem"]), ("gpu", nodes["avail_gpu"]),
+                 ("eorder", eorder), ("eoff", eoff)):
+        pn[k] = packer.pinned(len(v), v.dtype); pn[k][:] = v
+
     def e2e_step():
-        packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], eorder, eorder, eoff, eoff)
+        packer.set_snapshot(pn["cpu"], pn["mem"], pn["gpu"], pn["eorder"], pn["eorder"], pn["eoff"], pn["eoff"])
         packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
         return int(out_driver[0])          # the host reads the result
 

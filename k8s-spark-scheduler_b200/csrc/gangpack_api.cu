@@ -2,6 +2,7 @@
 // There is no CPU code path in this library: without a usable CUDA device gp_create fails.
 #include "gangpack.h"
 #include "gangpack_kernels.cuh"
+#include "gangpack_fifo.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -24,7 +25,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
                              const int32_t* __restrict__ count, const int32_t* __restrict__ group,
                              const uint8_t* __restrict__ skip, const int64_t* __restrict__ out_off,
                              int32_t n_groups, int64_t out_cap, const SnapMeta* __restrict__ meta,
-                             PrepApp* __restrict__ prep, int* __restrict__ err) {
+                             GroupMin* __restrict__ gmins, PrepApp* __restrict__ prep, int* __restrict__ err) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_apps) return;
     int64_t d[3] = {d_cpu[i], d_mem[i], d_gpu ? d_gpu[i] : 0};
@@ -69,6 +70,15 @@ __global__ void gp_prep_apps(int32_t n_apps,
         }
     }
     if (bad) { atomicOr(err, bad); k = 0; g = 0; }
+    else if (gmins) {
+        // batch-wide minima per instance group (FIFO dead-node skipping)
+        GroupMin* gm = gmins + g;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (e[t] < gm->exe[t]) atomicMin(&gm->exe[t], (long long)e[t]);
+            if (d[t] < gm->drv[t]) atomicMin(&gm->drv[t], (long long)d[t]);
+        }
+    }
     p.out_off = off;
     p.count = k;
     p.group = g;
@@ -103,44 +113,6 @@ __global__ void __launch_bounds__(kPackThreads) gp_pack_independent(Snapshot s, 
         if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO, 0>(s, pa, executor_nodes, scratch, wcache, st, lane);
         if (lane == 0) driver_node[i] = d;
         i = __shfl_sync(kFull, nxt, 0);
-    }
-    if (lane == 0) {
-        atomicAdd(stats + 0, st.nodes);
-        atomicAdd(stats + 1, st.drivers);
-    }
-}
-
-// FIFO modes: one warp per instance group walks ITS applications in queue order against the
-// mutating snapshot (fitEarlierDrivers, internal/extender/resource.go:224-262).
-template <int ALGO, int FIFO_MODE>
-__global__ void __launch_bounds__(32) gp_pack_fifo(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
-                                                   int32_t* __restrict__ driver_node,
-                                                   int32_t* __restrict__ executor_nodes,
-                                                   int2* __restrict__ scratch,
-                                                   unsigned long long* __restrict__ stats) {
-    __shared__ uint16_t wcache[kCapCache];
-    const int lane = threadIdx.x & 31;
-    const int32_t grp = blockIdx.x;
-    WarpStats st{0, 0};
-    bool blocked = false;
-    for (int32_t i0 = 0; i0 < n_apps; i0 += kWarp) {
-        int32_t i = i0 + lane;
-        bool mine = (i < n_apps) && (prep[i].group == grp);
-        unsigned m = __ballot_sync(kFull, mine);
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            int32_t app = i0 + src;
-            const PrepApp* pa = prep + app;
-            int32_t d;
-            if (blocked) d = -2;                                   // never evaluated (resource.go:252)
-            else {
-                d = -1;
-                if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, wcache, st, lane);
-                if (d < 0 && !(pa->flags & kAppSkipIfNoFit)) blocked = true;   // resource.go:244-253
-            }
-            if (lane == 0) driver_node[app] = d;
-        }
     }
     if (lane == 0) {
         atomicAdd(stats + 0, st.nodes);
@@ -226,6 +198,21 @@ __global__ void gp_build_driver_slots(int32_t n_drv, int32_t n_groups,
     }
 }
 
+// Several small host->device copies in ONE launch: sources are mapped pinned host buffers read
+// straight over PCIe (a chain of tiny DMA copies costs ~8-10 us each in stream order).
+struct CopyJob { const void* src; void* dst; unsigned long long bytes; };
+struct CopyJobs { CopyJob j[8]; int n; };
+__global__ void gp_multi_copy(CopyJobs jobs) {
+    for (int k = 0; k < jobs.n; ++k) {
+        const unsigned long long words = jobs.j[k].bytes >> 2;     // every array here is a multiple of 4 bytes
+        const unsigned int* src = static_cast<const unsigned int*>(jobs.j[k].src);
+        unsigned int* dst = static_cast<unsigned int*>(jobs.j[k].dst);
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < words;
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
+}
+
 // slots -> node-table order (gp_get_snapshot)
 __global__ void gp_scatter_slots(int32_t n_slots, const longlong2* __restrict__ pair, const int64_t* __restrict__ sgpu,
                                  const int32_t* __restrict__ slot_node,
@@ -279,9 +266,15 @@ struct gp_ctx {
 
     // batch staging
     DevBuf a_dcpu, a_dmem, a_dgpu, a_ecpu, a_emem, a_egpu, a_count, a_group, a_skip, a_off;
-    DevBuf prep, r_driver, r_exec, scratch, dev_misc;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
+    DevBuf prep, r_driver, r_exec, scratch, dev_misc, gmin;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
     void* pinned_misc = nullptr;                         // 32 B pinned mirror of dev_misc
     std::vector<int64_t> host_off;
+    std::vector<int32_t> v_owner;                 // gp_set_snapshot validation scratch (no per-call allocation)
+    std::vector<uint8_t> v_seen_e, v_seen_d;
+    std::vector<std::pair<const char*, size_t>> pinned_blocks;   // gp_alloc_pinned allocations (device-mapped under UVA)
+    void* one_block = nullptr;                    // gp_pack_one staging (mapped pinned)
+    size_t one_bytes = 0;
+    int zero_copy = 1;                            // GANGPACK_ZERO_COPY=0 disables reading/writing mapped host buffers in kernels
 
     gp_stats last{};
 };
@@ -289,7 +282,8 @@ struct gp_ctx {
 static thread_local std::string g_create_error;
 // dev_misc layout: [0] error bits (int), [8..24) stats (2 x u64), [32..32+4*kMaxChunks) per-chunk work counters
 static constexpr size_t kMiscCounters = 32, kMiscBytes = 32 + 4 * 16;
-static constexpr int32_t kChunkApps = 24576;   // apps per pipelined chunk of gp_pack_batch (~1.5 MB H2D, ~70 us of kernel)
+static constexpr int32_t kChunkApps = 24576;
+static constexpr int32_t kZeroCopyOutApps = 8192;  // batches up to this size write results straight into mapped host memory   // apps per pipelined chunk of gp_pack_batch (~1.5 MB H2D, ~70 us of kernel)
 
 static cudaError_t create_aux(gp_ctx* c) {
     cudaError_t e;
@@ -309,6 +303,19 @@ static cudaError_t create_aux(gp_ctx* c) {
         }                                                                                      \
     } while (0)
 
+// Device-visible alias of a host buffer, or nullptr.  Buffers from gp_alloc_pinned are known; anything
+// else is asked of the driver (cudaHostRegister / cudaHostAlloc memory of the caller qualifies).
+static const void* mapped_ptr(gp_ctx* c, const void* p, size_t bytes) {
+    if (!p || !c->zero_copy) return nullptr;
+    const char* q = static_cast<const char*>(p);
+    for (const auto& b : c->pinned_blocks)
+        if (q >= b.first && q + bytes <= b.first + b.second) return p;     // UVA: same address on the device
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type == cudaMemoryTypeHost && a.devicePointer) return a.devicePointer;
+    return nullptr;
+}
+
 static gp_status fail(gp_ctx* ctx, gp_status st, const std::string& msg) {
     ctx->err = msg;
     return st;
@@ -322,6 +329,7 @@ static Snapshot make_snapshot(const gp_ctx* c) {
     s.drv_slot = c->drv_slot.as<int32_t>();
     s.groups = c->groups.as<GroupDesc>();
     s.meta = c->snap_flags.as<SnapMeta>();
+    s.gmins = nullptr;
     s.n_groups = c->n_groups;
     s.n_slots = c->n_slots;
     return s;
@@ -362,6 +370,7 @@ gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
     if (!c) { g_create_error = "gp_create: out of memory"; return GP_ERR_INVALID; }
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* z = std::getenv("GANGPACK_ZERO_COPY")) c->zero_copy = std::atoi(z);
     if ((e = cudaSetDevice(dev)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = create_aux(c)) != cudaSuccess ||
@@ -382,9 +391,10 @@ void gp_destroy(gp_ctx* c) {
     DevBuf* bufs[] = {&c->node_cpu, &c->node_mem, &c->node_gpu, &c->exec_off, &c->drv_off, &c->exec_order, &c->drv_order,
                       &c->pair, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
-                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc};
+                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
+    if (c->one_block) cudaFreeHost(c->one_block);
     for (auto& row : c->ev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     for (cudaEvent_t e : c->ev_done) if (e) cudaEventDestroy(e);
@@ -397,12 +407,17 @@ gp_status gp_alloc_pinned(gp_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return GP_ERR_INVALID;
     GP_CUDA(ctx, cudaSetDevice(ctx->device));
     GP_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    ctx->pinned_blocks.emplace_back(static_cast<const char*>(*out), bytes ? bytes : 1);
     return GP_OK;
 }
 
 gp_status gp_free_pinned(gp_ctx* ctx, void* p) {
     if (!ctx) return GP_ERR_INVALID;
-    if (p) GP_CUDA(ctx, cudaFreeHost(p));
+    if (p) {
+        for (size_t i = 0; i < ctx->pinned_blocks.size(); ++i)
+            if (ctx->pinned_blocks[i].first == static_cast<const char*>(p)) { ctx->pinned_blocks.erase(ctx->pinned_blocks.begin() + (long)i); break; }
+        GP_CUDA(ctx, cudaFreeHost(p));
+    }
     return GP_OK;
 }
 
@@ -465,8 +480,11 @@ gp_status gp_set_snapshot(gp_ctx* c, const gp_nodes* n) {
     if ((n_exec > 0 && !n->exec_order) || (n_drv > 0 && !n->drv_order))
         return fail(c, GP_ERR_INVALID, "gp_set_snapshot: order arrays missing");
     {
-        std::vector<int32_t> owner((size_t)n->n_nodes, -1);
-        std::vector<uint8_t> seen_e((size_t)n->n_nodes, 0), seen_d((size_t)n->n_nodes, 0);
+        std::vector<int32_t>& owner = c->v_owner;
+        std::vector<uint8_t>&seen_e = c->v_seen_e, &seen_d = c->v_seen_d;
+        owner.assign((size_t)n->n_nodes, -1);
+        seen_e.assign((size_t)n->n_nodes, 0);
+        seen_d.assign((size_t)n->n_nodes, 0);
         for (int32_t g = 0; g < G; ++g) {
             for (int32_t e = n->exec_off[g]; e < n->exec_off[g + 1]; ++e) {
                 int32_t v = n->exec_order[e];
@@ -499,16 +517,39 @@ gp_status gp_set_snapshot(gp_ctx* c, const gp_nodes* n) {
     GP_CUDA(c, c->exec_order.reserve(sizeof(int32_t) * (size_t)(n_exec + 1)));
     GP_CUDA(c, c->drv_order.reserve(sizeof(int32_t) * (size_t)(n_drv + 1)));
     const size_t vb = sizeof(int64_t) * (size_t)n->n_nodes;
-    if (vb) {
-        GP_CUDA(c, cudaMemcpyAsync(c->node_cpu.p, n->avail_cpu_milli, vb, cudaMemcpyHostToDevice, st));
-        GP_CUDA(c, cudaMemcpyAsync(c->node_mem.p, n->avail_mem_bytes, vb, cudaMemcpyHostToDevice, st));
-        if (n->avail_gpu) GP_CUDA(c, cudaMemcpyAsync(c->node_gpu.p, n->avail_gpu, vb, cudaMemcpyHostToDevice, st));
-        else GP_CUDA(c, cudaMemsetAsync(c->node_gpu.p, 0, vb, st));
+    const size_t ob = sizeof(int32_t) * (size_t)(G + 1);
+    // mapped pinned inputs: one gather-copy kernel reads them over PCIe instead of 7 chained DMA copies
+    const void* m_cpu = mapped_ptr(c, n->avail_cpu_milli, vb);
+    const void* m_mem = mapped_ptr(c, n->avail_mem_bytes, vb);
+    const void* m_gpu = n->avail_gpu ? mapped_ptr(c, n->avail_gpu, vb) : nullptr;
+    const void* m_eoff = mapped_ptr(c, n->exec_off, ob);
+    const void* m_doff = mapped_ptr(c, n->drv_off, ob);
+    const void* m_eord = n_exec ? mapped_ptr(c, n->exec_order, sizeof(int32_t) * (size_t)n_exec) : n->exec_order;
+    const void* m_dord = n_drv ? mapped_ptr(c, n->drv_order, sizeof(int32_t) * (size_t)n_drv) : n->drv_order;
+    const bool all_mapped = vb && m_cpu && m_mem && (!n->avail_gpu || m_gpu) && m_eoff && m_doff && (!n_exec || m_eord) && (!n_drv || m_dord);
+    if (all_mapped) {
+        CopyJobs jobs{};
+        auto add = [&](const void* src, void* dst, size_t bytes) { if (bytes) jobs.j[jobs.n++] = CopyJob{src, dst, bytes}; };
+        add(m_cpu, c->node_cpu.p, vb); add(m_mem, c->node_mem.p, vb);
+        if (n->avail_gpu) add(m_gpu, c->node_gpu.p, vb);
+        add(m_eoff, c->exec_off.p, ob); add(m_doff, c->drv_off.p, ob);
+        add(m_eord, c->exec_order.p, sizeof(int32_t) * (size_t)n_exec);
+        add(m_dord, c->drv_order.p, sizeof(int32_t) * (size_t)n_drv);
+        if (!n->avail_gpu) GP_CUDA(c, cudaMemsetAsync(c->node_gpu.p, 0, vb, st));
+        gp_multi_copy<<<c->sm_count, 512, 0, st>>>(jobs);
+        GP_CUDA(c, cudaGetLastError());
+    } else {
+        if (vb) {
+            GP_CUDA(c, cudaMemcpyAsync(c->node_cpu.p, n->avail_cpu_milli, vb, cudaMemcpyHostToDevice, st));
+            GP_CUDA(c, cudaMemcpyAsync(c->node_mem.p, n->avail_mem_bytes, vb, cudaMemcpyHostToDevice, st));
+            if (n->avail_gpu) GP_CUDA(c, cudaMemcpyAsync(c->node_gpu.p, n->avail_gpu, vb, cudaMemcpyHostToDevice, st));
+            else GP_CUDA(c, cudaMemsetAsync(c->node_gpu.p, 0, vb, st));
+        }
+        GP_CUDA(c, cudaMemcpyAsync(c->exec_off.p, n->exec_off, ob, cudaMemcpyHostToDevice, st));
+        GP_CUDA(c, cudaMemcpyAsync(c->drv_off.p, n->drv_off, ob, cudaMemcpyHostToDevice, st));
+        if (n_exec) GP_CUDA(c, cudaMemcpyAsync(c->exec_order.p, n->exec_order, sizeof(int32_t) * (size_t)n_exec, cudaMemcpyHostToDevice, st));
+        if (n_drv) GP_CUDA(c, cudaMemcpyAsync(c->drv_order.p, n->drv_order, sizeof(int32_t) * (size_t)n_drv, cudaMemcpyHostToDevice, st));
     }
-    GP_CUDA(c, cudaMemcpyAsync(c->exec_off.p, n->exec_off, sizeof(int32_t) * (size_t)(G + 1), cudaMemcpyHostToDevice, st));
-    GP_CUDA(c, cudaMemcpyAsync(c->drv_off.p, n->drv_off, sizeof(int32_t) * (size_t)(G + 1), cudaMemcpyHostToDevice, st));
-    if (n_exec) GP_CUDA(c, cudaMemcpyAsync(c->exec_order.p, n->exec_order, sizeof(int32_t) * (size_t)n_exec, cudaMemcpyHostToDevice, st));
-    if (n_drv) GP_CUDA(c, cudaMemcpyAsync(c->drv_order.p, n->drv_order, sizeof(int32_t) * (size_t)n_drv, cudaMemcpyHostToDevice, st));
     gp_nodes dn = *n;
     dn.avail_cpu_milli = c->node_cpu.as<int64_t>(); dn.avail_mem_bytes = c->node_mem.as<int64_t>();
     dn.avail_gpu = c->node_gpu.as<int64_t>();
@@ -581,10 +622,21 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
         if (blocks < 1) blocks = 1;
         gp_pack_independent<ALGO><<<(int)blocks, kPackThreads, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch,
                                                                        stats, next_app);
-    } else if (mode == GP_MODE_FIFO_REFERENCE) {
-        gp_pack_fifo<ALGO, 1><<<s.n_groups, 32, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats);
     } else {
-        gp_pack_fifo<ALGO, 2><<<s.n_groups, 32, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats);
+        // FIFO: one persistent 1024-thread CTA per instance group, its slots staged in shared memory
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(gp_pack_fifo_cta<ALGO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFifoSmemBytes);
+            cudaFuncSetAttribute(gp_pack_fifo_cta<ALGO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFifoSmemBytes);
+            attr_set = true;
+        }
+        // small groups: fewer threads per CTA (the per-application fixed cost scales with the CTA size)
+        const int avg_ne = c->n_groups > 0 ? c->n_exec / c->n_groups : 0;
+        const int kFifoThreadsRt = avg_ne <= 1536 ? 256 : (avg_ne <= 4096 ? 512 : kFifoThreads);
+        if (mode == GP_MODE_FIFO_REFERENCE)
+            gp_pack_fifo_cta<ALGO, 1><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins);
+        else
+            gp_pack_fifo_cta<ALGO, 2><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins);
     }
 }
 
@@ -598,13 +650,18 @@ static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int
     PrepApp* prep = c->prep.as<PrepApp>() + lo;
     unsigned int* next_app = reinterpret_cast<unsigned int*>(c->dev_misc.as<char>() + kMiscCounters) + chunk;
     const int T = 256;
+    if (mode != GP_MODE_INDEPENDENT) {
+        GP_CUDA(c, c->gmin.reserve(sizeof(GroupMin) * (size_t)c->n_groups));
+        GP_CUDA(c, cudaMemsetAsync(c->gmin.p, 0x7f, sizeof(GroupMin) * (size_t)c->n_groups, st));   // +inf-ish
+    }
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
     gp_prep_apps<<<(q + T - 1) / T, T, 0, st>>>(
         q, da->drv_cpu_milli + lo, da->drv_mem_bytes + lo, da->drv_gpu ? da->drv_gpu + lo : nullptr, da->exe_cpu_milli + lo,
         da->exe_mem_bytes + lo, da->exe_gpu ? da->exe_gpu + lo : nullptr, da->exe_count + lo, da->group ? da->group + lo : nullptr,
         da->skip_if_no_fit ? da->skip_if_no_fit + lo : nullptr, da->exec_out_off + lo, c->n_groups, dout->executor_nodes_cap,
-        c->snap_flags.as<SnapMeta>(), prep, d_err);
+        c->snap_flags.as<SnapMeta>(), mode == GP_MODE_INDEPENDENT ? nullptr : c->gmin.as<GroupMin>(), prep, d_err);
     Snapshot s = make_snapshot(c);
+    s.gmins = c->gmin.as<GroupMin>();
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
     if (algo == GP_TIGHTLY_PACK)
         launch_pack<0>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
@@ -727,17 +784,40 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
     if (a->exe_gpu) GP_CUDA(c, c->a_egpu.reserve(b64));
     if (a->group) GP_CUDA(c, c->a_group.reserve(b32));
     if (a->skip_if_no_fit) GP_CUDA(c, c->a_skip.reserve((size_t)q));
+    // Mapped pinned inputs are read by gp_prep_apps straight from host memory (each value is read exactly
+    // once, so staging them in HBM first would only add a copy); otherwise they are staged by DMA.
+    const void* mi[10] = {mapped_ptr(c, a->drv_cpu_milli, b64), mapped_ptr(c, a->drv_mem_bytes, b64),
+                          mapped_ptr(c, a->exe_cpu_milli, b64), mapped_ptr(c, a->exe_mem_bytes, b64),
+                          mapped_ptr(c, a->exe_count, b32), mapped_ptr(c, off, sizeof(int64_t) * (size_t)(q + 1)),
+                          a->drv_gpu ? mapped_ptr(c, a->drv_gpu, b64) : nullptr, a->exe_gpu ? mapped_ptr(c, a->exe_gpu, b64) : nullptr,
+                          a->group ? mapped_ptr(c, a->group, b32) : nullptr,
+                          a->skip_if_no_fit ? mapped_ptr(c, a->skip_if_no_fit, (size_t)q) : nullptr};
+    const bool in_mapped = mi[0] && mi[1] && mi[2] && mi[3] && mi[4] && mi[5] && (!a->drv_gpu || mi[6]) && (!a->exe_gpu || mi[7]) &&
+                           (!a->group || mi[8]) && (!a->skip_if_no_fit || mi[9]);
+    // Small batches are latency-bound: results are written straight into mapped host buffers.
+    // Large ones are bandwidth-bound: one big DMA per chunk uses PCIe better than 64-byte stores.
+    void* mo_driver = const_cast<void*>(mapped_ptr(c, out->driver_node, b32));
+    void* mo_exec = total > 0 ? const_cast<void*>(mapped_ptr(c, out->executor_nodes, sizeof(int32_t) * (size_t)total)) : nullptr;
+    const bool out_mapped = q <= kZeroCopyOutApps && mo_driver && (total == 0 || mo_exec);
     gp_apps da = *a;
-    da.drv_cpu_milli = c->a_dcpu.as<int64_t>(); da.drv_mem_bytes = c->a_dmem.as<int64_t>();
-    da.exe_cpu_milli = c->a_ecpu.as<int64_t>(); da.exe_mem_bytes = c->a_emem.as<int64_t>();
-    da.exe_count = c->a_count.as<int32_t>(); da.exec_out_off = c->a_off.as<int64_t>();
-    da.drv_gpu = a->drv_gpu ? c->a_dgpu.as<int64_t>() : nullptr;
-    da.exe_gpu = a->exe_gpu ? c->a_egpu.as<int64_t>() : nullptr;
-    da.group = a->group ? c->a_group.as<int32_t>() : nullptr;
-    da.skip_if_no_fit = a->skip_if_no_fit ? c->a_skip.as<uint8_t>() : nullptr;
+    if (in_mapped) {
+        da.drv_cpu_milli = (const int64_t*)mi[0]; da.drv_mem_bytes = (const int64_t*)mi[1];
+        da.exe_cpu_milli = (const int64_t*)mi[2]; da.exe_mem_bytes = (const int64_t*)mi[3];
+        da.exe_count = (const int32_t*)mi[4]; da.exec_out_off = (const int64_t*)mi[5];
+        da.drv_gpu = (const int64_t*)mi[6]; da.exe_gpu = (const int64_t*)mi[7];
+        da.group = (const int32_t*)mi[8]; da.skip_if_no_fit = (const uint8_t*)mi[9];
+    } else {
+        da.drv_cpu_milli = c->a_dcpu.as<int64_t>(); da.drv_mem_bytes = c->a_dmem.as<int64_t>();
+        da.exe_cpu_milli = c->a_ecpu.as<int64_t>(); da.exe_mem_bytes = c->a_emem.as<int64_t>();
+        da.exe_count = c->a_count.as<int32_t>(); da.exec_out_off = c->a_off.as<int64_t>();
+        da.drv_gpu = a->drv_gpu ? c->a_dgpu.as<int64_t>() : nullptr;
+        da.exe_gpu = a->exe_gpu ? c->a_egpu.as<int64_t>() : nullptr;
+        da.group = a->group ? c->a_group.as<int32_t>() : nullptr;
+        da.skip_if_no_fit = a->skip_if_no_fit ? c->a_skip.as<uint8_t>() : nullptr;
+    }
     gp_results dr;
-    dr.driver_node = c->r_driver.as<int32_t>();
-    dr.executor_nodes = c->r_exec.as<int32_t>();
+    dr.driver_node = out_mapped ? (int32_t*)mo_driver : c->r_driver.as<int32_t>();
+    dr.executor_nodes = out_mapped ? (int32_t*)mo_exec : c->r_exec.as<int32_t>();
     dr.executor_nodes_cap = total;
 
     // Independent decisions are chunked and the chunks rotate over kLanes streams, so the H2D of
@@ -757,6 +837,7 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
         const size_t n = (size_t)(hi - lo);
         cudaStream_t ls = n_chunks == 1 ? st : c->lane[ch % gp_ctx::kLanes];
         if (n_chunks > 1) GP_CUDA(c, cudaStreamWaitEvent(ls, c->ev_ready, 0));
+        if (!in_mapped) {
 #define GP_H2D(dst, src, type, extra)                                                                           \
         GP_CUDA(c, cudaMemcpyAsync((type*)(dst) + lo, (src) + lo, sizeof(type) * (n + (extra)), cudaMemcpyHostToDevice, ls))
         GP_H2D(c->a_dcpu.p, a->drv_cpu_milli, int64_t, 0); GP_H2D(c->a_dmem.p, a->drv_mem_bytes, int64_t, 0);
@@ -768,8 +849,10 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
         if (a->group) GP_H2D(c->a_group.p, a->group, int32_t, 0);
         if (a->skip_if_no_fit) GP_H2D(c->a_skip.p, a->skip_if_no_fit, uint8_t, 0);
 #undef GP_H2D
+        }
         s = pack_device_range(c, &da, lo, hi, algo, mode, &dr, scratch, ls, ch);
         if (s != GP_OK) return s;
+        if (out_mapped) continue;
         GP_CUDA(c, cudaMemcpyAsync(out->driver_node + lo, dr.driver_node + lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ls));
         const int64_t e0 = off[lo], e1 = off[hi];
         if (e1 > e0)
@@ -797,22 +880,41 @@ gp_status gp_pack_one(gp_ctx* c, gp_algo algo, int64_t drv_cpu, int64_t drv_mem,
                       int32_t* executor_nodes) {
     if (!c) return GP_ERR_INVALID;
     if (!has_capacity || !driver_node) return fail(c, GP_ERR_INVALID, "gp_pack_one: NULL outputs");
-    int64_t off[2] = {0, exe_count > 0 ? exe_count : 0};
+    if (exe_count > 0 && !executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_one: executor_nodes is NULL");
+    // The tuple and the result travel through a context-owned mapped pinned block: no DMA copies at all
+    // on this latency-critical path (one app = one SparkBinPackFunction call).
+    const size_t n_exec = exe_count > 0 ? (size_t)exe_count : 0;
+    const size_t need = 128 + sizeof(int32_t) * (n_exec + 1);
+    if (need > c->one_bytes) {
+        GP_CUDA(c, cudaSetDevice(c->device));
+        if (c->one_block) { gp_free_pinned(c, c->one_block); c->one_block = nullptr; c->one_bytes = 0; }
+        void* blk = nullptr;
+        gp_status st = gp_alloc_pinned(c, need * 2, &blk);
+        if (st != GP_OK) return st;
+        c->one_block = blk; c->one_bytes = need * 2;
+    }
+    int64_t* q = static_cast<int64_t*>(c->one_block);         // [0..5] tuple, [6..7] offsets
+    q[0] = drv_cpu; q[1] = drv_mem; q[2] = drv_gpu; q[3] = exe_cpu; q[4] = exe_mem; q[5] = exe_gpu;
+    q[6] = 0; q[7] = (int64_t)n_exec;
+    int32_t* i32 = reinterpret_cast<int32_t*>(q + 8);          // [0] count, [1] driver result
+    i32[0] = exe_count; i32[1] = -1;
+    int32_t* exec_out = reinterpret_cast<int32_t*>(static_cast<char*>(c->one_block) + 128);
     gp_apps a{};
     a.n_apps = 1;
-    a.drv_cpu_milli = &drv_cpu; a.drv_mem_bytes = &drv_mem; a.drv_gpu = &drv_gpu;
-    a.exe_cpu_milli = &exe_cpu; a.exe_mem_bytes = &exe_mem; a.exe_gpu = &exe_gpu;
-    a.exe_count = &exe_count;
-    a.exec_out_off = off;
+    a.drv_cpu_milli = q + 0; a.drv_mem_bytes = q + 1; a.drv_gpu = q + 2;
+    a.exe_cpu_milli = q + 3; a.exe_mem_bytes = q + 4; a.exe_gpu = q + 5;
+    a.exe_count = i32;
+    a.exec_out_off = q + 6;
     gp_results r{};
-    int32_t d = -1;
-    r.driver_node = &d;
-    r.executor_nodes = executor_nodes;
-    r.executor_nodes_cap = off[1];
+    r.driver_node = i32 + 1;
+    r.executor_nodes = exec_out;
+    r.executor_nodes_cap = (int64_t)n_exec;
     gp_status s = gp_pack_batch(c, &a, algo, GP_MODE_INDEPENDENT, &r);
     if (s != GP_OK) return s;
+    const int32_t d = i32[1];
     *has_capacity = d >= 0 ? 1 : 0;
     *driver_node = d >= 0 ? d : -1;
+    if (d >= 0 && n_exec) std::memcpy(executor_nodes, exec_out, sizeof(int32_t) * n_exec);
     return GP_OK;
 }
 

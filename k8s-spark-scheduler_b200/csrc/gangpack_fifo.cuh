@@ -1,0 +1,379 @@
+// gangpack_fifo.cuh -- FIFO modes: fitEarlierDrivers (internal/extender/resource.go:224-262) on the device.
+//
+// The loop is a true sequential dependency inside one instance group (application i+1 sees the
+// usage application i subtracted), so parallelism comes from WITHIN an application and ACROSS
+// instance groups: one persistent CTA (1024 threads) owns one group's queue.
+//   * the group's executor-order slots (16 B (cpu,mem) records) are staged into shared memory with
+//     TMA bulk copies (cp.async.bulk + mbarrier) and written back with a bulk store at the end, so the
+//     block-serial commit of reservations never leaves the SM;
+//   * every thread owns one node per step: block-wide reduction / prefix scan / first-feasible vote
+//     replace the warp primitives of the independent kernel;
+//   * slots that do not fit shared memory (very large groups, driver-only spare slots, the gpu
+//     dimension) are served from global memory by the same accessors.
+#pragma once
+
+#include "gangpack_kernels.cuh"
+
+namespace gp {
+
+constexpr int kFifoThreads = 1024;
+constexpr int kFifoWarps = kFifoThreads / 32;
+constexpr int kFifoSmemSlots = 11776;          // 184 KB of (cpu,mem) records
+constexpr int kFifoCache = 12288;              // uint16 capacity cache entries (24 KB)
+
+struct FifoScratch {
+    unsigned long long bar;                    // mbarrier for the TMA staging
+    uint32_t part_a[2][kFifoWarps];
+    uint32_t part_b[2][kFifoWarps];
+    int32_t found[2][kFifoWarps];
+    unsigned mask[kFifoWarps];
+    int32_t first_live_e;                      // executor-order positions before this are dead for the whole batch
+    int32_t first_live_d;                      // same for driver-order entries
+};
+
+// dead for every application of the batch (see GroupMin)
+__device__ __forceinline__ bool dead_for(const long long* mn, longlong2 v, int64_t gpu_avail, bool use_gpu) {
+    bool dead = v.x < mn[0] || v.y < mn[1] || v.x < 0 || v.y < 0;
+    if (use_gpu) dead = dead || gpu_avail < mn[2] || gpu_avail < 0;
+    return dead;
+}
+
+// ---- TMA 1-D bulk copies -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+
+// ---- the group's mutable view: slots [0, n_smem) live in shared memory, the rest in global ------------
+struct FifoView {
+    longlong2* sp;          // shared-memory copy of slots [0, n_smem)
+    longlong2* gp;          // global slots of this group (s.pair + sbase)
+    int64_t* gg;            // global gpu values of this group
+    int32_t n_smem;
+    __device__ __forceinline__ longlong2* pair_ptr(int32_t local) const { return local < n_smem ? sp + local : gp + local; }
+    __device__ __forceinline__ longlong2 pair(int32_t local) const {
+        if (local < n_smem) return sp[local];
+        longlong2 v;
+        asm volatile("ld.global.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(gp + local) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ int64_t gpu(int32_t local) const {
+        int64_t v;
+        asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(gg + local) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void charge(int32_t local, long long mult, int64_t cpu, int64_t mem, int64_t gpu_req) const {
+        longlong2* pp = pair_ptr(local);
+        longlong2 v = *pp;
+        v.x -= mult * cpu; v.y -= mult * mem;
+        *pp = v;
+        if (gpu_req != 0) gg[local] -= mult * gpu_req;
+    }
+};
+
+// capacity of one slot for one application (fast or general class), clamped to k
+template <bool FAST> struct FifoCaps;
+template <> struct FifoCaps<true> : Caps<true> {
+    __device__ __forceinline__ uint32_t capr(const FifoView& v, int32_t local, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
+        longlong2 p = v.pair(local);
+        uint32_t c = umin3(fast_q(p.x - r_cpu, cpu), fast_q(p.y - r_mem, mem), k);
+        if (use_gpu) c = min(c, fast_q(v.gpu(local) - r_gpu, gpu));
+        return c;
+    }
+};
+template <> struct FifoCaps<false> : Caps<false> {
+    __device__ __forceinline__ uint32_t capr(const FifoView& v, int32_t local, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
+        longlong2 p = v.pair(local);
+        uint32_t c = min(cap_dim(p.x - r_cpu, cpu, k), cap_dim(p.y - r_mem, mem, k));
+        if (use_gpu) c = min(c, cap_dim(v.gpu(local) - r_gpu, gpu, k));
+        return c;
+    }
+};
+
+// ---- block primitives (all 1024 threads call them; `buf` alternates so one barrier per call suffices)
+__device__ __forceinline__ void block_reduce2(FifoScratch& sh, int& buf, uint32_t a, uint32_t b, uint32_t& ra, uint32_t& rb) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t wa = warp_sum(a), wb = warp_sum(b);
+    if (lane == 0) { sh.part_a[buf][w] = wa; sh.part_b[buf][w] = wb; }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    ra = warp_sum(lane < nw ? sh.part_a[buf][lane] : 0u);
+    rb = warp_sum(lane < nw ? sh.part_b[buf][lane] : 0u);
+    buf ^= 1;
+}
+__device__ __forceinline__ void block_excl_scan(FifoScratch& sh, int& buf, uint32_t v, uint32_t& excl, uint32_t& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) sh.part_a[buf][w] = incl;
+    __syncthreads();
+    uint32_t t = lane < (int)(blockDim.x >> 5) ? sh.part_a[buf][lane] : 0u;
+    uint32_t ti = warp_incl_scan(t, lane);
+    uint32_t before = __shfl_sync(kFull, ti - t, w);     // sum of the totals of the warps before mine
+    total = __shfl_sync(kFull, ti, 31);
+    excl = before + incl - v;
+    buf ^= 1;
+}
+// value of the first thread (in thread order) whose predicate holds, or -1
+__device__ __forceinline__ int32_t block_first(FifoScratch& sh, int& buf, bool pred, int32_t value) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned vote = __ballot_sync(kFull, pred);
+    int32_t first = vote ? __shfl_sync(kFull, value, __ffs(vote) - 1) : -1;
+    if (lane == 0) sh.found[buf][w] = first;
+    __syncthreads();
+    int32_t f = lane < (int)(blockDim.x >> 5) ? sh.found[buf][lane] : -1;
+    unsigned v2 = __ballot_sync(kFull, f >= 0);
+    int32_t r = v2 ? __shfl_sync(kFull, f, __ffs(v2) - 1) : -1;
+    buf ^= 1;
+    return r;
+}
+
+// ---- one application, the whole CTA ----------------------------------------------------------------
+template <int ALGO, int FIFO_MODE, bool FAST>
+__device__ __forceinline__ int32_t fifo_app(const Snapshot& s, const GroupDesc& g, const FifoView& view, const PrepApp* __restrict__ pa,
+                                            int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
+                                            uint16_t* __restrict__ cache, FifoScratch& sh, int& buf, WarpStats& st,
+                                            const GroupMin& gm) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int32_t nt = (int32_t)blockDim.x;
+    FifoCaps<FAST> a;
+    a.init(pa, (pa->flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
+    const uint32_t k = a.k;
+    const uint32_t lmax = (uint32_t)pa->lmax;
+    const int32_t ne = g.ne;
+    const int64_t out_off = pa->out_off;
+    int32_t* out = executor_nodes + out_off;
+    int2* list = scratch ? scratch + out_off : nullptr;
+    const int32_t* slot_node = s.slot_node + g.sbase;
+    const bool cache_ok = k <= 0xFFFFu;
+
+    // ---- phase 1 (see pack_app_impl): P, m1 over a prefix of the executor order, 1024 nodes per step
+    unsigned long long P = 0;
+    uint32_t m1 = 0;
+    const int32_t start_e = sh.first_live_e;      // block-uniform (written before the last barrier)
+    const int32_t start_d = sh.first_live_d;
+    int32_t pos = start_e;
+    bool early = (k == 0);
+    const unsigned long long need = (unsigned long long)k + lmax;
+    while (!early && pos < ne) {
+        int32_t i = pos + tid;
+        uint32_t c = (i < ne) ? a.capr(view, i, 0, 0, 0) : 0u;
+        if (cache_ok && i - start_e < kFifoCache) cache[i - start_e] = (uint16_t)c;
+        if (pos == start_e) {
+            // advance the dead prefix: first position of this step that can still host something
+            bool alive = (i < ne) && !dead_for(gm.exe, view.pair(i), a.use_gpu ? view.gpu(i) : 0, a.use_gpu);
+            int32_t f = block_first(sh, buf, alive, i);
+            if (tid == 0) sh.first_live_e = f >= 0 ? f : (pos + nt < ne ? pos + nt : ne);
+        }
+        uint32_t sum, cnt;
+        if (ALGO == 1) {
+            uint32_t excl, total;
+            block_excl_scan(sh, buf, c != 0 ? 1u : 0u, excl, total);
+            uint32_t r = m1 + excl;
+            if (c != 0 && r < k) list[r] = make_int2(i, (int)c);
+            cnt = total;
+            uint32_t dummy;
+            block_reduce2(sh, buf, c, 0u, sum, dummy);
+        } else {
+            block_reduce2(sh, buf, c, c != 0 ? 1u : 0u, sum, cnt);
+        }
+        P += sum;
+        m1 += cnt;
+        pos += nt;
+        if (ALGO == 0) early = (P >= need) || (m1 >= k + 1);
+        else early = (m1 >= k + 1);
+    }
+    if (tid == 0) st.nodes += (unsigned long long)((pos < ne ? pos : ne) - start_e);
+    const int32_t cached_end = cache_ok ? ((pos - start_e) < kFifoCache ? pos : start_e + kFifoCache) : start_e;
+    const bool exact_total = !early;
+    if (exact_total && P < k) return -1;
+
+    // ---- phase 2: first feasible driver candidate -------------------------------------------------------
+    int32_t dslot = -1;
+    for (int32_t j0 = start_d; j0 < g.nd && dslot < 0; j0 += nt) {
+        int32_t j = j0 + tid;
+        bool feasible = false;
+        int32_t ls = -1;
+        bool alive = false;
+        if (j < g.nd) {
+            ls = s.drv_slot[g.dbase + j];
+            longlong2 v = view.pair(ls);
+            const int64_t gv = a.use_gpu ? view.gpu(ls) : 0;
+            alive = !dead_for(gm.drv, v, gv, a.use_gpu);
+            feasible = !(a.d_cpu > v.x) && !(a.d_mem > v.y);
+            if (a.use_gpu) feasible = feasible && !(a.d_gpu > gv);
+            if (feasible && exact_total && ls < ne) {
+                uint32_t c0 = a.capr(view, ls, 0, 0, 0);
+                uint32_t cdl = a.capr(view, ls, a.d_cpu, a.d_mem, a.d_gpu);
+                feasible = (P - c0 + cdl >= k);
+            }
+        }
+        if (j0 == start_d) {
+            int32_t f = block_first(sh, buf, alive, j);
+            if (tid == 0) sh.first_live_d = f >= 0 ? f : (j0 + nt < g.nd ? j0 + nt : g.nd);
+        }
+        dslot = block_first(sh, buf, feasible, ls);
+        if (tid == 0) st.drivers += (unsigned long long)((g.nd - j0) < nt ? (g.nd - j0) : nt);
+    }
+    if (dslot < 0) return -1;
+    const int32_t driver_node = slot_node[dslot];
+    const uint32_t cd = (dslot < ne && k != 0) ? a.capr(view, dslot, a.d_cpu, a.d_mem, a.d_gpu) : 0u;
+
+    // ---- phase 3: emit ExecutorNodes + charge the snapshot -----------------------------------------------
+    bool driver_hosts_executor = false;   // per thread; combined below
+    if (k != 0) {
+        if (ALGO == 0 || early) {
+            uint32_t placed = 0;
+            for (int32_t p0 = start_e; placed < k && p0 < ne; p0 += nt) {
+                int32_t i = p0 + tid;
+                uint32_t c = 0;
+                if (i == dslot) c = cd;
+                else if (i < cached_end) c = cache[i - start_e];
+                else if (i < ne) c = a.capr(view, i, 0, 0, 0);
+                if (tid == 0 && p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < nt ? (ne - p0) : nt);
+                const uint32_t unit = (ALGO == 0) ? c : (c != 0 ? 1u : 0u);   // tightly: all it can take; evenly round 1: one
+                uint32_t excl, total;
+                block_excl_scan(sh, buf, unit, excl, total);
+                uint32_t room = k - placed;
+                uint32_t T = total < room ? total : room;
+                uint32_t take = excl >= T ? 0u : ((unit < T - excl) ? unit : (T - excl));
+                if (take != 0) {
+                    int32_t node = slot_node[i];
+                    for (uint32_t t = 0; t < take; ++t) out[placed + excl + t] = node;
+                    if (i == dslot) driver_hosts_executor = true;
+                    view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
+                }
+                placed += T;
+            }
+        } else {
+            // general rounds: warp 0 works on the complete candidate list
+            __syncthreads();
+            if (tid < 32) {
+                bool h = evenly_rounds<FIFO_MODE>(list, m1, k, dslot, cd, out, slot_node, lane,
+                                                  [&](int32_t local) { view.charge(local, 1, a.e_cpu, a.e_mem, a.e_gpu); });
+                driver_hosts_executor = h;
+            }
+        }
+    }
+    // ---- charge the driver (sparkpods.go:139-146 / exact) ----------------------------------------------------
+    uint32_t hosted, dummy;
+    block_reduce2(sh, buf, driver_hosts_executor ? 1u : 0u, 0u, hosted, dummy);   // also orders the executor charges
+    if (tid == 0 && (FIFO_MODE == 2 || hosted == 0)) view.charge(dslot, 1, a.d_cpu, a.d_mem, a.d_gpu);
+    __syncthreads();   // the next application sees the charged snapshot
+    return driver_node;
+}
+
+template <int ALGO, int FIFO_MODE>
+__global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+                                                                    int32_t* __restrict__ driver_node,
+                                                                    int32_t* __restrict__ executor_nodes,
+                                                                    int2* __restrict__ scratch,
+                                                                    unsigned long long* __restrict__ stats,
+                                                                    const GroupMin* __restrict__ gmins) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FifoScratch& sh = *reinterpret_cast<FifoScratch*>(smem_raw);
+    uint16_t* cache = reinterpret_cast<uint16_t*>(smem_raw + 2048);
+    longlong2* spair = reinterpret_cast<longlong2*>(smem_raw + 2048 + kFifoCache * sizeof(uint16_t));
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int32_t grp = blockIdx.x;
+    const GroupDesc g = s.groups[grp];
+
+    // ---- stage the group's executor slots into shared memory (TMA bulk copy) --------------------------
+    FifoView view;
+    view.sp = spair;
+    view.gp = s.pair + g.sbase;
+    view.gg = s.gpu + g.sbase;
+    view.n_smem = g.ne < kFifoSmemSlots ? g.ne : kFifoSmemSlots;
+    const uint32_t stage_bytes = (uint32_t)view.n_smem * (uint32_t)sizeof(longlong2);
+    if (tid == 0) { mbar_init(&sh.bar, 1); sh.first_live_e = 0; sh.first_live_d = 0; }
+    const GroupMin gm = gmins[grp];
+    __syncthreads();
+    if (tid == 0 && stage_bytes != 0) {
+        mbar_expect_tx(&sh.bar, stage_bytes);
+        for (uint32_t off = 0; off < stage_bytes; off += 32768u) {
+            uint32_t n = stage_bytes - off < 32768u ? stage_bytes - off : 32768u;
+            tma_load_1d(reinterpret_cast<unsigned char*>(spair) + off, reinterpret_cast<const unsigned char*>(view.gp) + off, n, &sh.bar);
+        }
+    }
+    if (stage_bytes != 0) mbar_wait(&sh.bar, 0);
+    __syncthreads();
+
+    WarpStats st{0, 0};
+    int buf = 0;
+    bool blocked = false;
+    const int32_t nt = (int32_t)blockDim.x, nw = nt >> 5;
+    for (int32_t i0 = 0; i0 < n_apps; i0 += nt) {
+        int32_t i = i0 + tid;
+        bool mine = (i < n_apps) && (prep[i].group == grp);
+        unsigned m = __ballot_sync(kFull, mine);
+        __syncthreads();                 // previous round's masks fully consumed
+        if (lane == 0) sh.mask[w] = m;
+        __syncthreads();
+        for (int ww = 0; ww < nw; ++ww) {
+            unsigned mm = sh.mask[ww];
+            while (mm) {
+                int src = __ffs(mm) - 1;
+                mm &= mm - 1;
+                int32_t app = i0 + ww * 32 + src;
+                const PrepApp* pa = prep + app;
+                int32_t d;
+                if (blocked) d = -2;                                   // never evaluated (resource.go:252)
+                else {
+                    d = -1;
+                    const uint32_t fl = pa->flags;
+                    if (!(fl & kAppInvalid)) {
+                        if (fl & kAppFast) d = fifo_app<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm);
+                        else d = fifo_app<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm);
+                    }
+                    if (d < 0 && !(fl & kAppSkipIfNoFit)) blocked = true;   // resource.go:244-253
+                }
+                if (tid == 0) driver_node[app] = d;
+            }
+        }
+    }
+
+    // ---- write the charged slots back (TMA bulk store) ---------------------------------------------------
+    __syncthreads();
+    if (tid == 0 && stage_bytes != 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (uint32_t off = 0; off < stage_bytes; off += 32768u) {
+            uint32_t n = stage_bytes - off < 32768u ? stage_bytes - off : 32768u;
+            tma_store_1d(reinterpret_cast<unsigned char*>(view.gp) + off, reinterpret_cast<unsigned char*>(spair) + off, n);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (tid == 0) {
+        atomicAdd(stats + 0, st.nodes);
+        atomicAdd(stats + 1, st.drivers);
+    }
+}
+
+constexpr size_t kFifoSmemBytes = 2048 + kFifoCache * sizeof(uint16_t) + (size_t)kFifoSmemSlots * sizeof(longlong2);
+
+}  // namespace gp

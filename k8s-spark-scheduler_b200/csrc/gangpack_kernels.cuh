@@ -76,6 +76,14 @@ struct __align__(16) PrepApp {
 enum : uint32_t { kAppUsesGpu = 1u, kAppSkipIfNoFit = 2u, kAppInvalid = 4u, kAppFast = 8u };
 static_assert(sizeof(PrepApp) == 128, "PrepApp layout");
 
+// Smallest requests over the batch's applications of one instance group (gp_prep_apps, atomicMin).
+// A node with avail < min request in some dimension can host nothing for ANY application of the batch,
+// and availability only decreases in the FIFO loop -> such nodes can be skipped for good.
+struct GroupMin {
+    long long exe[3];   // min executor cpu, mem, gpu (0 = some app asks nothing in that dimension)
+    long long drv[3];   // min driver   cpu, mem, gpu
+};
+
 struct GroupDesc {
     int32_t sbase;   // first slot of the group
     int32_t ne;      // executor-order length: slots [sbase, sbase+ne) in priority order
@@ -92,6 +100,7 @@ struct Snapshot {
     const int32_t* drv_slot; // [n_drv] group-local slot of each driver candidate
     const GroupDesc* groups;
     const SnapMeta* meta;
+    const GroupMin* gmins;   // FIFO modes only
     int32_t n_groups;
     int32_t n_slots;
 };
@@ -249,6 +258,52 @@ __device__ __forceinline__ void charge(const Snapshot& s, int32_t slot, long lon
     if (gpu != 0) s.gpu[slot] -= mult * gpu;
 }
 
+// distribute-evenly, general rounds (distribute_evenly.go:49-70) over the complete candidate list
+// (m <= k entries (position, cap) in priority order), executed by ONE warp:
+// R* = min r with sum min(c, r) >= k; round r hands one executor to every node with c >= r until k are
+// placed; ExecutorNodes is round-major.  charge1(local_slot) subtracts one executor (FIFO modes).
+// Returns whether the driver's node received an executor.
+template <int FIFO_MODE, class ChargeFn>
+__device__ __forceinline__ bool evenly_rounds(int2* __restrict__ list, uint32_t m, uint32_t k, int32_t dslot, uint32_t cd,
+                                              int32_t* __restrict__ out, const int32_t* __restrict__ slot_node, int lane,
+                                              ChargeFn charge1) {
+    bool driver_hosts_executor = false;
+    for (uint32_t t = lane; t < m; t += kWarp) {   // patch the driver's own entry with cap(d|drv)
+        int2 e = list[t];
+        if (e.x == dslot) { e.y = (int)cd; list[t] = e; }
+    }
+    __syncwarp();
+    uint32_t lo = 1, hi = k;   // f(k) >= k is known (feasible)
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        unsigned long long f = 0;
+        for (uint32_t t0 = 0; t0 < m; t0 += kWarp) {
+            uint32_t t = t0 + lane;
+            uint32_t c = (t < m) ? (uint32_t)list[t].y : 0u;
+            f += warp_sum(c < mid ? c : mid);
+        }
+        if (f >= k) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t R = lo;
+    uint32_t base = 0;
+    for (uint32_t r = 1; r <= R && base < k; ++r) {
+        for (uint32_t t0 = 0; t0 < m && base < k; t0 += kWarp) {
+            uint32_t t = t0 + lane;
+            int2 e = (t < m) ? list[t] : make_int2(0, 0);
+            bool in = (t < m) && ((uint32_t)e.y >= r);
+            unsigned has = __ballot_sync(kFull, in);
+            uint32_t idx = base + __popc(has & ((1u << lane) - 1u));
+            if (in && idx < k) {
+                out[idx] = slot_node[e.x];
+                if (FIFO_MODE == 2 || (FIFO_MODE == 1 && r == 1)) charge1(e.x);
+                if (FIFO_MODE != 0 && e.x == dslot) driver_hosts_executor = true;
+            }
+            base += __popc(has);
+        }
+    }
+    return driver_hosts_executor;
+}
+
 struct WarpStats { unsigned long long nodes; unsigned long long drivers; };
 
 constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 capacities (uint16)
@@ -392,44 +447,9 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
                 placed += __popc(has);
             }
         } else {
-            // general rounds over the complete candidate list (m1 <= k entries, in order):
-            // R* = min r with sum min(c, r) >= k; round r hands one executor to every node with
-            // c >= r until k are placed; ExecutorNodes is round-major.
             __syncwarp();
-            const uint32_t m = m1;
-            for (uint32_t t = lane; t < m; t += kWarp) {   // patch the driver's own entry with cap(d|drv)
-                int2 e = list[t];
-                if (e.x == dslot) { e.y = (int)cd; list[t] = e; }
-            }
-            __syncwarp();
-            uint32_t lo = 1, hi = k;   // f(k) >= k is known (feasible)
-            while (lo < hi) {
-                uint32_t mid = lo + (hi - lo) / 2;
-                unsigned long long f = 0;
-                for (uint32_t t0 = 0; t0 < m; t0 += kWarp) {
-                    uint32_t t = t0 + lane;
-                    uint32_t c = (t < m) ? (uint32_t)list[t].y : 0u;
-                    f += warp_sum(c < mid ? c : mid);
-                }
-                if (f >= k) hi = mid; else lo = mid + 1;
-            }
-            const uint32_t R = lo;
-            uint32_t base = 0;
-            for (uint32_t r = 1; r <= R && base < k; ++r) {
-                for (uint32_t t0 = 0; t0 < m && base < k; t0 += kWarp) {
-                    uint32_t t = t0 + lane;
-                    int2 e = (t < m) ? list[t] : make_int2(0, 0);
-                    bool in = (t < m) && ((uint32_t)e.y >= r);
-                    unsigned has = __ballot_sync(kFull, in);
-                    uint32_t idx = base + __popc(has & ((1u << lane) - 1u));
-                    if (in && idx < k) {
-                        out[idx] = s.slot_node[g.sbase + e.x];
-                        if (FIFO_MODE == 2 || (FIFO_MODE == 1 && r == 1)) charge(s, g.sbase + e.x, 1, a.e_cpu, a.e_mem, a.e_gpu);
-                        if (FIFO_MODE != 0 && e.x == dslot) driver_hosts_executor = true;
-                    }
-                    base += __popc(has);
-                }
-            }
+            driver_hosts_executor = evenly_rounds<FIFO_MODE>(list, m1, k, dslot, cd, out, s.slot_node + g.sbase, lane,
+                [&](int32_t local) { charge(s, g.sbase + local, 1, a.e_cpu, a.e_mem, a.e_gpu); });
         }
     }
 
