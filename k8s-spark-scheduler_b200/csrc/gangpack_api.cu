@@ -4,6 +4,8 @@
 #include "gangpack_kernels.cuh"
 #include "gangpack_fifo.cuh"
 
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,7 +27,8 @@ __global__ void gp_prep_apps(int32_t n_apps,
                              const int32_t* __restrict__ count, const int32_t* __restrict__ group,
                              const uint8_t* __restrict__ skip, const int64_t* __restrict__ out_off,
                              int32_t n_groups, int64_t out_cap, const SnapMeta* __restrict__ meta,
-                             GroupMin* __restrict__ gmins, PrepApp* __restrict__ prep, int* __restrict__ err) {
+                             GroupMin* __restrict__ gmins, PrepApp* __restrict__ prep, int* __restrict__ err,
+                             volatile int* __restrict__ err_host) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_apps) return;
     int64_t d[3] = {d_cpu[i], d_mem[i], d_gpu ? d_gpu[i] : 0};
@@ -69,7 +72,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
             if (mx > 0 && (((unsigned long long)mx >> dv.sh) >> 32) != 0) fast = false;
         }
     }
-    if (bad) { atomicOr(err, bad); k = 0; g = 0; }
+    if (bad) { atomicOr(err, bad); *err_host = bad; k = 0; g = 0; }   // err_host: mapped pinned word, no D2H copy needed
     else if (gmins) {
         // batch-wide minima per instance group (FIFO dead-node skipping)
         GroupMin* gm = gmins + g;
@@ -245,6 +248,11 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// dev_misc layout: [0] error bits (int), [8..24) stats (2 x u64), [32..32+4*kMaxChunks) per-chunk work counters
+static constexpr size_t kMiscCounters = 32, kMiscBytes = 32 + 4 * 16;
+static constexpr int32_t kChunkApps = 32768;
+static constexpr int32_t kZeroCopyOutApps = 8192;  // batches up to this size write results straight into mapped host memory   // apps per pipelined chunk of gp_pack_batch (~1.5 MB H2D, ~70 us of kernel)
+
 struct gp_ctx {
     int device = 0;
     int sm_count = 0;
@@ -275,15 +283,14 @@ struct gp_ctx {
     void* one_block = nullptr;                    // gp_pack_one staging (mapped pinned)
     size_t one_bytes = 0;
     int zero_copy = 1;                            // GANGPACK_ZERO_COPY=0 disables reading/writing mapped host buffers in kernels
+    int zero_copy_in_max = 1 << 30;               // batches up to this size read their inputs in place (GANGPACK_ZC_IN_MAX)
+    int chunk_apps = kChunkApps;                  // GANGPACK_CHUNK_APPS
+    int trace = 0;                                // GANGPACK_TRACE=1: host-side phase timing on stderr
 
     gp_stats last{};
 };
 
 static thread_local std::string g_create_error;
-// dev_misc layout: [0] error bits (int), [8..24) stats (2 x u64), [32..32+4*kMaxChunks) per-chunk work counters
-static constexpr size_t kMiscCounters = 32, kMiscBytes = 32 + 4 * 16;
-static constexpr int32_t kChunkApps = 24576;
-static constexpr int32_t kZeroCopyOutApps = 8192;  // batches up to this size write results straight into mapped host memory   // apps per pipelined chunk of gp_pack_batch (~1.5 MB H2D, ~70 us of kernel)
 
 static cudaError_t create_aux(gp_ctx* c) {
     cudaError_t e;
@@ -371,6 +378,9 @@ gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
     if (const char* z = std::getenv("GANGPACK_ZERO_COPY")) c->zero_copy = std::atoi(z);
+    if (const char* z = std::getenv("GANGPACK_ZC_IN_MAX")) c->zero_copy_in_max = std::atoi(z);
+    if (const char* z = std::getenv("GANGPACK_CHUNK_APPS")) c->chunk_apps = std::max(1024, std::atoi(z));
+    if (const char* z = std::getenv("GANGPACK_TRACE")) c->trace = std::atoi(z);
     if ((e = cudaSetDevice(dev)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = create_aux(c)) != cudaSuccess ||
@@ -659,7 +669,8 @@ static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int
         q, da->drv_cpu_milli + lo, da->drv_mem_bytes + lo, da->drv_gpu ? da->drv_gpu + lo : nullptr, da->exe_cpu_milli + lo,
         da->exe_mem_bytes + lo, da->exe_gpu ? da->exe_gpu + lo : nullptr, da->exe_count + lo, da->group ? da->group + lo : nullptr,
         da->skip_if_no_fit ? da->skip_if_no_fit + lo : nullptr, da->exec_out_off + lo, c->n_groups, dout->executor_nodes_cap,
-        c->snap_flags.as<SnapMeta>(), mode == GP_MODE_INDEPENDENT ? nullptr : c->gmin.as<GroupMin>(), prep, d_err);
+        c->snap_flags.as<SnapMeta>(), mode == GP_MODE_INDEPENDENT ? nullptr : c->gmin.as<GroupMin>(), prep, d_err,
+        reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48));
     Snapshot s = make_snapshot(c);
     s.gmins = c->gmin.as<GroupMin>();
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
@@ -676,6 +687,7 @@ static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int
 // common prologue: buffers, counters
 static gp_status pack_begin(gp_ctx* c, int32_t q, gp_algo algo, const gp_results* dout, int2** scratch, cudaStream_t st) {
     GP_CUDA(c, cudaMemsetAsync(c->dev_misc.p, 0, kMiscBytes, st));
+    *reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48) = 0;   // host-visible error word
     c->last = gp_stats{};
     c->ev_chunks = 0;
     *scratch = nullptr;
@@ -759,6 +771,7 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
     if (s != GP_OK) return s;
     const int32_t q = a->n_apps;
     if (q == 0) return GP_OK;
+    const auto t_begin = std::chrono::steady_clock::now();
     GP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     // ExecutorNodes offsets: the caller's CSR offsets, or computed here
@@ -792,7 +805,7 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
                           a->drv_gpu ? mapped_ptr(c, a->drv_gpu, b64) : nullptr, a->exe_gpu ? mapped_ptr(c, a->exe_gpu, b64) : nullptr,
                           a->group ? mapped_ptr(c, a->group, b32) : nullptr,
                           a->skip_if_no_fit ? mapped_ptr(c, a->skip_if_no_fit, (size_t)q) : nullptr};
-    const bool in_mapped = mi[0] && mi[1] && mi[2] && mi[3] && mi[4] && mi[5] && (!a->drv_gpu || mi[6]) && (!a->exe_gpu || mi[7]) &&
+    const bool in_mapped = q <= c->zero_copy_in_max && mi[0] && mi[1] && mi[2] && mi[3] && mi[4] && mi[5] && (!a->drv_gpu || mi[6]) && (!a->exe_gpu || mi[7]) &&
                            (!a->group || mi[8]) && (!a->skip_if_no_fit || mi[9]);
     // Small batches are latency-bound: results are written straight into mapped host buffers.
     // Large ones are bandwidth-bound: one big DMA per chunk uses PCIe better than 64-byte stores.
@@ -824,8 +837,8 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
     // chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap (PCIe is full duplex).
     // FIFO modes are one sequential pass: a single chunk.
     int n_chunks = 1;
-    if (mode == GP_MODE_INDEPENDENT && q >= 2 * kChunkApps) {
-        n_chunks = (q + kChunkApps - 1) / kChunkApps;
+    if (mode == GP_MODE_INDEPENDENT && q >= 2 * c->chunk_apps) {
+        n_chunks = (q + c->chunk_apps - 1) / c->chunk_apps;
         if (n_chunks > gp_ctx::kMaxChunks) n_chunks = gp_ctx::kMaxChunks;
     }
     int2* scratch = nullptr;
@@ -860,19 +873,23 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
                                        cudaMemcpyDeviceToHost, ls));
     }
     c->ev_chunks = n_chunks;
+    const auto t_issued = std::chrono::steady_clock::now();
     if (n_chunks > 1) {
         for (int l = 0; l < gp_ctx::kLanes && l < n_chunks; ++l) {
             GP_CUDA(c, cudaEventRecord(c->ev_done[l], c->lane[l]));
             GP_CUDA(c, cudaStreamWaitEvent(st, c->ev_done[l], 0));
         }
     }
-    GP_CUDA(c, cudaMemcpyAsync(c->pinned_misc, c->dev_misc.p, 32, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaStreamSynchronize(st));
-    const unsigned long long* sv = reinterpret_cast<const unsigned long long*>((const char*)c->pinned_misc + 8);
-    c->last.nodes_scanned = (int64_t)sv[0];
-    c->last.drivers_tried = (int64_t)sv[1];
-    fill_kernel_times(c);
-    return decode_device_error(c, *reinterpret_cast<const int*>(c->pinned_misc));
+    if (c->trace) {
+        const auto t_done = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[gangpack] pack_batch q=%d chunks=%d in_mapped=%d out_mapped=%d issue=%.1fus wait=%.1fus\n", q, n_chunks,
+                     (int)in_mapped, (int)out_mapped, std::chrono::duration<double, std::micro>(t_issued - t_begin).count(),
+                     std::chrono::duration<double, std::micro>(t_done - t_issued).count());
+    }
+    // validation errors arrive through the mapped error word; scan statistics stay on the device until
+    // gp_last_stats asks for them
+    return decode_device_error(c, *reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48));
 }
 
 gp_status gp_pack_one(gp_ctx* c, gp_algo algo, int64_t drv_cpu, int64_t drv_mem, int64_t drv_gpu, int64_t exe_cpu,
