@@ -406,11 +406,18 @@ def main():
     alg_bytes = (stats["nodes_scanned"] * 8 * R + stats["drivers_tried"] * 4 + q * (64 + 8) + 8 * 0 + 4 * k_total)
     nominal_bytes = q * (w["nodes"] * 8 * R + w["nodes"] * 4 + 64 + 8) + 4 * k_total
     pack_s = float(np.mean(pack_ns)) * 1e-9
+    kernel_name = f"gp_pack_{'independent' if mode == 0 else 'fifo_cta'}<{ALGO_NAME[algo]}>"
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(kernel_name)
+        if t and t.get("workload") == args.workload and world == 1:
+            traffic = t["dram_bytes_per_launch"]
     roofline = {
-        "bound": "hbm", "kernel": f"gp_pack_{'independent' if mode == 0 else 'fifo'}<{ALGO_NAME[algo]}>",
+        "bound": "hbm", "kernel": kernel_name,
         "achieved": alg_bytes / pack_s / 1e9, "peak": peak, "unit": "GB/s",
         "frac": alg_bytes / pack_s / 1e9 / peak, "peak_source": peak_src,
-        "traffic": None,
+        "traffic": traffic,
         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": pack_s * 1e3,
         "nodes_scanned_per_decision": stats["nodes_scanned"] / q, "drivers_tried_per_decision": stats["drivers_tried"] / q,
         "full_table_equivalent_GBps": nominal_bytes / pack_s / 1e9,
