@@ -191,6 +191,17 @@ def run_reference_arm(args, w):
 
 
 # ------------------------------------------------------------------------------------------------
+def _watchdog(seconds: float):
+    """A hung collective must not hang the caller: hard-exit with an error after `seconds`."""
+    def fire():
+        print(f"[bench] watchdog: no result after {seconds:.0f} s, aborting", file=sys.stderr, flush=True)
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,7 +211,9 @@ def main():
     ap.add_argument("--workload", default="tightly-100k", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="apps per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: abort if the run takes longer")
     args = ap.parse_args()
+    _watchdog(args.max_seconds)
     w = WORKLOADS[args.workload]
     if args.cpu_sample == 0:
         # ~10-30 s of CPU work: ~0.2-0.5 ms per decision per thread for the literal port
@@ -237,12 +250,15 @@ def main():
     def dev_t(x, dtype):
         return torch.from_numpy(np.ascontiguousarray(x)).to(dtype).to(dev)
     with torch.cuda.stream(stream):
-        tn = {"cpu": dev_t(nodes["avail_cpu"], torch.int64), "mem": dev_t(nodes["avail_mem"], torch.int64),
-              "gpu": dev_t(nodes["avail_gpu"], torch.int64), "eoff": dev_t(eoff, torch.int32),
-              "eorder": dev_t(eorder, torch.int32)}
-        if rank != 0:   # only rank 0 knows the snapshot; the others receive it by NCCL broadcast every step
-            for k in ("cpu", "mem", "gpu", "eorder"):
-                tn[k].zero_()
+        # the snapshot lives in ONE flat buffer so that a single NCCL broadcast moves it:
+        # [cpu int64 x N | mem int64 x N | gpu int64 x N | executor/driver order int32 x len(eorder)]
+        n_nodes, n_ord = w["nodes"], len(eorder)
+        snapbuf = torch.zeros(3 * n_nodes + (n_ord + 1) // 2, dtype=torch.int64, device=dev)
+        tn = {"cpu": snapbuf[0:n_nodes], "mem": snapbuf[n_nodes:2 * n_nodes], "gpu": snapbuf[2 * n_nodes:3 * n_nodes],
+              "eorder": snapbuf[3 * n_nodes:].view(torch.int32)[:n_ord], "eoff": dev_t(eoff, torch.int32)}
+        if rank == 0:   # only rank 0 knows the snapshot; the others receive it by NCCL broadcast every step
+            tn["cpu"].copy_(dev_t(nodes["avail_cpu"], torch.int64)); tn["mem"].copy_(dev_t(nodes["avail_mem"], torch.int64))
+            tn["gpu"].copy_(dev_t(nodes["avail_gpu"], torch.int64)); tn["eorder"].copy_(dev_t(eorder, torch.int32))
         ta = {k: dev_t(a[k], torch.int64 if a[k].dtype == np.int64 else (torch.uint8 if a[k].dtype == np.uint8 else torch.int32))
               for k in APP_KEYS}
         ta["off"] = dev_t(a["off"], torch.int64)
@@ -251,38 +267,76 @@ def main():
         if mode == 0:
             ta.pop("young")
         d_driver = torch.empty(q, dtype=torch.int32, device=dev)
-        # all ranks use the same (max) ExecutorNodes length so the all-gather is regular
+        d_exec = torch.empty(max(total_exec, 1), dtype=torch.int32, device=dev)
         max_exec = total_exec
+        chunks = []
         if world > 1:
+            # N>1: the batch is packed in chunks and every chunk's placements ([driver | ExecutorNodes], padded to the
+            # largest rank so the collective is regular) are all-gathered asynchronously while the next chunk is
+            # packed: the exchange overlaps the compute tile by tile.
+            n_ch = 4 if mode == 0 else 1
+            for c in range(n_ch):
+                lo, hi = (q * c) // n_ch, (q * (c + 1)) // n_ch
+                e0, e1 = int(a["off"][lo]), int(a["off"][hi])
+                t = torch.tensor([e1 - e0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); pad = max(int(t.item()), 1)
+                res = torch.empty((hi - lo) + pad, dtype=torch.int32, device=dev)
+                tc = {k: v[lo:hi] for k, v in ta.items() if k != "off"}
+                tc["off"] = (ta["off"][lo:hi + 1] - e0).contiguous()
+                chunks.append({"apps": tc, "res": res, "driver": res[:hi - lo], "exec": res[hi - lo:],
+                               "gathered": torch.empty(res.numel() * world, dtype=torch.int32, device=dev)})
             t = torch.tensor([total_exec], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); max_exec = int(t.item())
-        d_exec = torch.empty(max(max_exec, 1), dtype=torch.int32, device=dev)
-        g_driver = torch.empty(q * world, dtype=torch.int32, device=dev) if world > 1 else None
-        g_exec = torch.empty(max(max_exec, 1) * world, dtype=torch.int32, device=dev) if world > 1 else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream.synchronize()
 
     def device_step():
         """broadcast snapshot (N>1) -> lay it out -> prep + pack -> all-gather placements (N>1)."""
-        if world > 1:
-            for k in ("cpu", "mem", "gpu", "eorder"):
-                dist.broadcast(tn[k], src=0)
+        if world == 1:
+            packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
+            packer.pack_batch_device(ta, algo, mode, d_driver, d_exec)
+            return 5
+        dist.broadcast(snapbuf, src=0)
         packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
-        packer.pack_batch_device(ta, algo, mode, d_driver, d_exec)
-        if world > 1:
-            dist.all_gather_into_tensor(g_driver, d_driver)
-            dist.all_gather_into_tensor(g_exec, d_exec)
+        works = []
+        for ch in chunks:
+            packer.pack_batch_device(ch["apps"], algo, mode, ch["driver"], ch["exec"])
+            works.append(dist.all_gather_into_tensor(ch["gathered"], ch["res"], async_op=True))
+        for wk in works:
+            wk.wait()
+        return 3 + 2 * len(chunks)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches_per_step = 3 + 2   # build_groups, build_exec_slots, build_driver_slots, prep_apps, pack
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             flush.fill_(1)
-            device_step()
+            launches_per_step = device_step()   # build_groups, build_exec_slots, build_driver_slots + (prep, pack) per chunk
         barrier()
+        # N>1: the step is a chain of ~12 small launches (NCCL broadcast, layout kernels, 4 x (prep, pack,
+        # all-gather)); issued from Python it is launch-bound, so it is captured ONCE into a CUDA graph
+        # and replayed (same work, one launch).  N=1 stays eager so the library's per-kernel event timer
+        # (roofline) keeps working.
+        graph = None
+        eager_stats = packer.stats()
+        if world > 1 and os.environ.get("BENCH_GRAPH", "1") != "0":
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    device_step()
+                for _ in range(2):
+                    graph.replay()
+                torch.cuda.synchronize()
+            except Exception as e:   # capture not possible: run eagerly
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                graph = None
+                torch.cuda.synchronize()
+        flags = torch.tensor([1 if graph is not None else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)      # all ranks must agree (collectives inside the graph)
+            if int(flags.item()) == 0:
+                graph = None
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -293,14 +347,20 @@ def main():
         for s in range(args.steps):
             flush.fill_(s & 0xff)              # L2 flush, outside the event pair
             evs[s][0].record(stream)
-            device_step()
+            if graph is not None:
+                graph.replay()
+            else:
+                device_step()
             evs[s][1].record(stream)
-            st = packer.stats()                # synchronises the stream; reads the pack kernel's own event time
-            pack_ns.append(st["pack_kernel_ns"]); prep_ns.append(st["prep_kernel_ns"])
+            if graph is None:
+                st = packer.stats()            # synchronises the stream; reads the pack kernel's own event time
+                pack_ns.append(st["pack_kernel_ns"]); prep_ns.append(st["prep_kernel_ns"])
         barrier()
         wall1 = time.perf_counter()
         step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    stats = packer.stats()
+    if graph is not None:
+        pack_ns, prep_ns = [eager_stats["pack_kernel_ns"]], [eager_stats["prep_kernel_ns"]]
+    stats = packer.stats() if graph is None else eager_stats
     ms = float(np.mean(step_ms))
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
@@ -351,27 +411,27 @@ def main():
     else:
         # N>1: rank 0 uploads the snapshot and broadcasts it; every rank packs its host-resident shard
         # through the C ABI; placements are all-gathered on the device and rank 0 reads all of them.
+        g_driver = torch.empty(q * world, dtype=torch.int32, device=dev)
+        d_exec_pad = torch.empty(max(max_exec, 1), dtype=torch.int32, device=dev)
+        g_exec = torch.empty(max(max_exec, 1) * world, dtype=torch.int32, device=dev)
+        h_snap = torch.empty(snapbuf.numel(), dtype=torch.int64).pin_memory()
+        if rank == 0:
+            h_snap.copy_(snapbuf.cpu())
         h_all_driver = torch.empty(q * world, dtype=torch.int32).pin_memory() if rank == 0 else None
         h_all_exec = torch.empty(max(max_exec, 1) * world, dtype=torch.int32).pin_memory() if rank == 0 else None
-        hn = {k: torch.from_numpy(np.ascontiguousarray(nodes[s])).pin_memory() for k, s in
-              (("cpu", "avail_cpu"), ("mem", "avail_mem"), ("gpu", "avail_gpu"))}
-        h_eorder = torch.from_numpy(np.ascontiguousarray(eorder)).pin_memory()
 
         def e2e_step_multi():
             with torch.cuda.stream(stream):
                 if rank == 0:
-                    for k in ("cpu", "mem", "gpu"):
-                        tn[k].copy_(hn[k], non_blocking=True)
-                    tn["eorder"].copy_(h_eorder, non_blocking=True)
-                for k in ("cpu", "mem", "gpu", "eorder"):
-                    dist.broadcast(tn[k], src=0)
+                    snapbuf.copy_(h_snap, non_blocking=True)
+                dist.broadcast(snapbuf, src=0)
                 packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
                 stream.synchronize()
                 packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
                 d_driver.copy_(torch.from_numpy(out_driver), non_blocking=True)   # placements back for the gather
-                d_exec[:total_exec].copy_(torch.from_numpy(out_exec[:total_exec]), non_blocking=True)
+                d_exec_pad[:total_exec].copy_(torch.from_numpy(out_exec[:total_exec]), non_blocking=True)
                 dist.all_gather_into_tensor(g_driver, d_driver)
-                dist.all_gather_into_tensor(g_exec, d_exec)
+                dist.all_gather_into_tensor(g_exec, d_exec_pad)
                 if rank == 0:
                     h_all_driver.copy_(g_driver, non_blocking=True)
                     h_all_exec.copy_(g_exec, non_blocking=True)
@@ -444,7 +504,10 @@ def main():
                        "algo": ALGO_NAME[algo], "mode": MODE_NAME[mode], "instance_groups": w["groups"],
                        "executors_total_per_gpu": total_exec,
                        "l2": "256 MiB write between steps, outside the per-step CUDA-event pair",
-                       "step": "snapshot layout + prep + pack" + (" + NCCL snapshot broadcast + placement all-gather" if world > 1 else ""),
+                       "step": "snapshot layout + prep + pack" + (" + NCCL snapshot broadcast + placement all-gather (4 chunks, "
+                                                                   "all-gather of chunk i overlaps the pack of chunk i+1; "
+                                                                   + ("replayed from one CUDA graph)" if graph is not None else "eager launches)")
+                                                                   if world > 1 else ""),
                        "fits": None},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "decisions/s", "ms_per_step": e2e_ms,
@@ -456,9 +519,14 @@ def main():
             "wall_s_value_region": wall1 - wall0,
         }
         print(json.dumps(line), flush=True)
-    packer.close()
-    if world > 1:
-        dist.destroy_process_group()
+    # Leave without tearing anything down: tensors allocated on the library's stream must not outlive that
+    # stream (the caching allocator records events on it when they are freed), and destroying a process group
+    # whose communicator is referenced by a captured CUDA graph can block.  Every rank has finished its last
+    # collective (the all-reduce of the e2e time) at this point.
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
