@@ -55,7 +55,8 @@ __global__ void gp_prep_apps(int32_t n_apps,
             uint32_t sh = (uint32_t)(__ffsll((long long)e[t]) - 1);
             uint64_t odd = (uint64_t)e[t] >> sh;
             dv.sh = sh;
-            if (odd == 1) dv.kind = kDivShift;
+            if (odd == 1 && sh >= 1) { dv.kind = kDivMagic; dv.magic = 1ull << 63; dv.sh = sh - 1; }   // a / 2^sh = (a >> (sh-1)) / 2
+            else if (odd == 1) dv.kind = kDivShift;                                                     // e == 1
             else if ((odd >> 32) == 0) { dv.kind = kDivMagic; dv.magic = 0xFFFFFFFFFFFFFFFFull / odd + 1; }
             else { dv.kind = kDivSlow; dv.sh = 0; }
             // a driver of d displaces at most ceil(d/e) executors in this dimension
@@ -67,6 +68,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
         p.div[t] = dv;
         // fast class: the shifted numerator of every node fits 32 bits (SnapMeta::max_avail bounds it)
         if (dv.kind == kDivSlow) fast = false;
+        else if (t < 2 && dv.kind != kDivMagic) fast = false;       // cpu / mem of the fast class are magic divisions only
         else if (dv.kind != kDivInf) {
             long long mx = meta->max_avail[t];
             if (mx > 0 && (((unsigned long long)mx >> dv.sh) >> 32) != 0) fast = false;
@@ -95,7 +97,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
 // global counter (claim-then-broadcast, next index prefetched) so long scans do not leave a tail.
 constexpr int kPackThreads = 256;
 template <int ALGO>
-__global__ void __launch_bounds__(kPackThreads) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+__global__ void __launch_bounds__(kPackThreads, 4) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
                                                                     int32_t* __restrict__ driver_node,
                                                                     int32_t* __restrict__ executor_nodes,
                                                                     int2* __restrict__ scratch,

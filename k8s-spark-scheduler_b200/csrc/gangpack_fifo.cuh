@@ -102,7 +102,7 @@ template <bool FAST> struct FifoCaps;
 template <> struct FifoCaps<true> : Caps<true> {
     __device__ __forceinline__ uint32_t capr(const FifoView& v, int32_t local, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
         longlong2 p = v.pair(local);
-        uint32_t c = umin3(fast_q(p.x - r_cpu, cpu), fast_q(p.y - r_mem, mem), k);
+        uint32_t c = cap_pair(p, r_cpu, r_mem);
         if (use_gpu) c = min(c, fast_q(v.gpu(local) - r_gpu, gpu));
         return c;
     }

@@ -150,6 +150,16 @@ __device__ __forceinline__ uint32_t fast_q(int64_t a, const FastDim& p) {
     return (int32_t)hi < 0 ? 0u : q;
 }
 
+// cpu / mem dimensions of the fast class are always kDivMagic (a power-of-two request 2^sh is prepared as
+// "divide (a >> (sh-1)) by 2", magic 2^63): no mode selects in the hot loop.
+__device__ __forceinline__ uint32_t fast_q_magic(int64_t a, const FastDim& p) {
+    const uint32_t lo = (uint32_t)a, hi = (uint32_t)((uint64_t)a >> 32);
+    const bool big = p.sh >= 32;
+    const uint32_t xs = __funnelshift_r(big ? hi : lo, big ? 0u : hi, p.sh & 31);
+    const uint32_t q = (uint32_t)(((uint64_t)p.m_hi * xs + __umulhi(p.m_lo, xs)) >> 32);
+    return (int32_t)hi < 0 ? 0u : q;
+}
+
 template <bool MUTABLE>
 __device__ __forceinline__ longlong2 load_pair(const longlong2* p) {
     if (MUTABLE) {
@@ -200,21 +210,18 @@ template <> struct Caps<true> {
         e_cpu = pa->div[0].e; e_mem = pa->div[1].e; e_gpu = pa->div[2].e;
         k = (uint32_t)pa->count; use_gpu = ug;
     }
-    // cap(n | reserved = r) clamped to k
+    // capacity from already-loaded availability, reservation r, clamped to k
+    __device__ __forceinline__ uint32_t cap_pair(longlong2 v, int64_t r_cpu, int64_t r_mem) const {
+        return umin3(fast_q_magic(v.x - r_cpu, cpu), fast_q_magic(v.y - r_mem, mem), k);
+    }
     template <bool MUT>
-    __device__ __forceinline__ uint32_t cap(const Snapshot& s, int32_t slot, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
-        longlong2 v = load_pair<MUT>(s.pair + slot);
-        uint32_t c = umin3(fast_q(v.x - r_cpu, cpu), fast_q(v.y - r_mem, mem), k);
-        if (use_gpu) c = min(c, fast_q(load_gpu<MUT>(s.gpu + slot) - r_gpu, gpu));
+    __device__ __forceinline__ uint32_t cap(const Snapshot& s, int32_t slot, int64_t r_cpu, int64_t r_mem, int64_t r_gpu, bool ug) const {
+        uint32_t c = cap_pair(load_pair<MUT>(s.pair + slot), r_cpu, r_mem);
+        if (ug) c = min(c, fast_q(load_gpu<MUT>(s.gpu + slot) - r_gpu, gpu));
         return c;
     }
     template <bool MUT>
-    __device__ __forceinline__ uint32_t cap0(const Snapshot& s, int32_t slot) const {
-        longlong2 v = load_pair<MUT>(s.pair + slot);
-        uint32_t c = umin3(fast_q(v.x, cpu), fast_q(v.y, mem), k);
-        if (use_gpu) c = min(c, fast_q(load_gpu<MUT>(s.gpu + slot), gpu));
-        return c;
-    }
+    __device__ __forceinline__ uint32_t cap0(const Snapshot& s, int32_t slot, bool ug) const { return cap<MUT>(s, slot, 0, 0, 0, ug); }
 };
 
 template <> struct Caps<false> {
@@ -230,22 +237,22 @@ template <> struct Caps<false> {
         k = (uint32_t)pa->count; use_gpu = ug;
     }
     template <bool MUT>
-    __device__ __forceinline__ uint32_t cap(const Snapshot& s, int32_t slot, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
+    __device__ __forceinline__ uint32_t cap(const Snapshot& s, int32_t slot, int64_t r_cpu, int64_t r_mem, int64_t r_gpu, bool ug) const {
         longlong2 v = load_pair<MUT>(s.pair + slot);
         uint32_t c = min(cap_dim(v.x - r_cpu, cpu, k), cap_dim(v.y - r_mem, mem, k));
-        if (use_gpu) c = min(c, cap_dim(load_gpu<MUT>(s.gpu + slot) - r_gpu, gpu, k));
+        if (ug) c = min(c, cap_dim(load_gpu<MUT>(s.gpu + slot) - r_gpu, gpu, k));
         return c;
     }
     template <bool MUT>
-    __device__ __forceinline__ uint32_t cap0(const Snapshot& s, int32_t slot) const { return cap<MUT>(s, slot, 0, 0, 0); }
+    __device__ __forceinline__ uint32_t cap0(const Snapshot& s, int32_t slot, bool ug) const { return cap<MUT>(s, slot, 0, 0, 0, ug); }
 };
 
 // driverResources.GreaterThan(available) == false  (binpack.go:69)
 template <bool MUT, class C>
-__device__ __forceinline__ bool driver_fits(const Snapshot& s, int32_t slot, const C& a) {
+__device__ __forceinline__ bool driver_fits(const Snapshot& s, int32_t slot, const C& a, bool ug) {
     longlong2 v = load_pair<MUT>(s.pair + slot);
     bool ok = !(a.d_cpu > v.x) && !(a.d_mem > v.y);
-    if (a.use_gpu) ok = ok && !(a.d_gpu > load_gpu<MUT>(s.gpu + slot));
+    if (ug) ok = ok && !(a.d_gpu > load_gpu<MUT>(s.gpu + slot));
     return ok;
 }
 
@@ -314,13 +321,14 @@ constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 cap
 // (then the snapshot is read with plain loads and the placement is subtracted from it).
 // wcache: this warp's kCapCache x uint16 scratch in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, int FIFO_MODE, bool FAST>
+template <int ALGO, int FIFO_MODE, bool FAST, bool NOGPU>
 __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
     constexpr bool MUT = FIFO_MODE != 0;
     Caps<FAST> a;
     a.init(pa, (pa->flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
+    const bool ug = NOGPU ? false : a.use_gpu;      // compile-time false on the hot instantiation
     const GroupDesc g = s.groups[pa->group];
     const uint32_t k = a.k;
     const uint32_t lmax = (uint32_t)pa->lmax;
@@ -335,24 +343,32 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     // Early exit is exact: once P >= k + lmax (or m1 >= k+1) every driver candidate that fits
     // leaves >= k executor slots inside the prefix (the driver displaces <= lmax of them, all on one
     // node).  distribute-evenly may only stop on m1 >= k+1 (then one round places everything).
+    // Each lane evaluates two nodes per step (64 per warp): two independent 128-bit loads in flight and the
+    // vote / reduction / loop control amortised over twice the nodes.
     unsigned long long P = 0;
     uint32_t m1 = 0;
     int32_t pos = 0;
+    int32_t first_nz = -1;                    // first step that saw any capacity: emission starts there
     bool early = (k == 0);
     const unsigned long long need = (unsigned long long)k + lmax;
     while (!early && pos < ne) {
-        int32_t i = pos + lane;
-        uint32_t c = (i < ne) ? a.template cap0<MUT>(s, g.sbase + i) : 0u;
-        if (cache_ok && i < kCapCache) wcache[i] = (uint16_t)c;
-        unsigned has = __ballot_sync(kFull, c != 0);
+        const int32_t i0 = pos + lane, i1 = i0 + kWarp;
+        const uint32_t c0 = (i0 < ne) ? a.template cap0<MUT>(s, g.sbase + i0, ug) : 0u;
+        const uint32_t c1 = (i1 < ne) ? a.template cap0<MUT>(s, g.sbase + i1, ug) : 0u;
+        if (cache_ok && i1 < kCapCache) { wcache[i0] = (uint16_t)c0; wcache[i1] = (uint16_t)c1; }
+        const unsigned has0 = __ballot_sync(kFull, c0 != 0), has1 = __ballot_sync(kFull, c1 != 0);
         if (ALGO == 1) {
             // remember the first k nodes that can host at all: (position, cap)
-            uint32_t r = m1 + __popc(has & ((1u << lane) - 1u));
-            if (c != 0 && r < k) list[r] = make_int2(i, (int)c);
+            const unsigned below = (1u << lane) - 1u;
+            uint32_t r0 = m1 + __popc(has0 & below);
+            uint32_t r1 = m1 + __popc(has0) + __popc(has1 & below);
+            if (c0 != 0 && r0 < k) list[r0] = make_int2(i0, (int)c0);
+            if (c1 != 0 && r1 < k) list[r1] = make_int2(i1, (int)c1);
         }
-        P += warp_sum(c);
-        m1 += __popc(has);
-        pos += kWarp;
+        if (first_nz < 0 && (has0 | has1)) first_nz = has0 ? pos : pos + kWarp;
+        P += warp_sum(c0 + c1);
+        m1 += __popc(has0) + __popc(has1);
+        pos += 2 * kWarp;
         if (ALGO == 0) early = (P >= need) || (m1 >= k + 1);
         else early = (m1 >= k + 1);
     }
@@ -360,6 +376,7 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     const int32_t cached_end = cache_ok ? (pos < kCapCache ? pos : kCapCache) : 0;
     const bool exact_total = !early;          // scanned everything: P == S0
     if (exact_total && P < k) return -1;      // not even without a driver
+    if (first_nz < 0) first_nz = 0;
 
     // ---- phase 2: first feasible driver candidate (binpack.go:67-85) ----------------------------
     int32_t dslot = -1;
@@ -369,11 +386,11 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
         int32_t ls = -1;
         if (j < g.nd) {
             ls = s.drv_slot[g.dbase + j];
-            feasible = driver_fits<MUT>(s, g.sbase + ls, a);
+            feasible = driver_fits<MUT>(s, g.sbase + ls, a, ug);
             if (feasible && exact_total && ls < ne) {
                 // the executor total with the driver on this node must still reach k
-                uint32_t c0 = a.template cap0<MUT>(s, g.sbase + ls);
-                uint32_t cdl = a.template cap<MUT>(s, g.sbase + ls, a.d_cpu, a.d_mem, a.d_gpu);
+                uint32_t c0 = a.template cap0<MUT>(s, g.sbase + ls, ug);
+                uint32_t cdl = a.template cap<MUT>(s, g.sbase + ls, a.d_cpu, a.d_mem, a.d_gpu, ug);
                 feasible = (P - c0 + cdl >= k);
             }
         }
@@ -384,7 +401,7 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     if (dslot < 0) return -1;
     const int32_t driver_node = s.slot_node[g.sbase + dslot];
     // cap(d | drv): only matters when the driver's node is an executor candidate
-    const uint32_t cd = (dslot < ne && k != 0) ? a.template cap<MUT>(s, g.sbase + dslot, a.d_cpu, a.d_mem, a.d_gpu) : 0u;
+    const uint32_t cd = (dslot < ne && k != 0) ? a.template cap<MUT>(s, g.sbase + dslot, a.d_cpu, a.d_mem, a.d_gpu, ug) : 0u;
 
     // ---- phase 3: emit ExecutorNodes -------------------------------------------------------------
     bool driver_hosts_executor = false;
@@ -392,12 +409,12 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
         if (ALGO == 0) {
             // node-major: node n receives min(cap_d(n), remaining)  (pack_tightly.go:45-61)
             uint32_t placed = 0;
-            for (int32_t p0 = 0; placed < k && p0 < ne; p0 += kWarp) {
+            for (int32_t p0 = first_nz; placed < k && p0 < ne; p0 += kWarp) {   // nodes before first_nz host nothing
                 int32_t i = p0 + lane;
                 uint32_t c = 0;
                 if (i == dslot) c = cd;
                 else if (i < cached_end) c = wcache[i];
-                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i);
+                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i, ug);
                 if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 uint32_t incl = warp_incl_scan(c, lane);
                 uint32_t total = __shfl_sync(kFull, incl, kWarp - 1);
@@ -428,12 +445,12 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
         } else if (early) {
             // one round: the first k nodes with cap_d >= 1, in order  (distribute_evenly.go:49-70)
             uint32_t placed = 0;
-            for (int32_t p0 = 0; placed < k && p0 < ne; p0 += kWarp) {
+            for (int32_t p0 = first_nz; placed < k && p0 < ne; p0 += kWarp) {
                 int32_t i = p0 + lane;
                 uint32_t c = 0;
                 if (i == dslot) c = cd;
                 else if (i < cached_end) c = wcache[i];
-                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i);
+                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i, ug);
                 if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 unsigned has = __ballot_sync(kFull, c != 0);
                 uint32_t r = placed + __popc(has & ((1u << lane) - 1u));
@@ -463,18 +480,21 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     return driver_node;
 }
 
+// everything that is not (fast class, gpu dimension idle): any int64 request / binding gpu dimension
 template <int ALGO, int FIFO_MODE>
 __device__ __noinline__ int32_t pack_app_general(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
-    return pack_app_impl<ALGO, FIFO_MODE, false>(s, pa, executor_nodes, scratch, wcache, st, lane);
+    return pack_app_impl<ALGO, FIFO_MODE, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane);
 }
 
-// class dispatch (warp-uniform): fast = 32-bit magic arithmetic, general = any int64 request
+// class dispatch (warp-uniform): hot path = fast class with the gpu dimension idle
 template <int ALGO, int FIFO_MODE>
 __device__ __forceinline__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, int32_t* __restrict__ executor_nodes,
                                             int2* __restrict__ scratch, uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
-    if (pa->flags & kAppFast) return pack_app_impl<ALGO, FIFO_MODE, true>(s, pa, executor_nodes, scratch, wcache, st, lane);
+    const bool gpu_idle = !(pa->flags & kAppUsesGpu) && !(s.meta->flags & kSnapGpuNegative);
+    if ((pa->flags & kAppFast) && gpu_idle)
+        return pack_app_impl<ALGO, FIFO_MODE, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane);
     return pack_app_general<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, wcache, st, lane);
 }
 
