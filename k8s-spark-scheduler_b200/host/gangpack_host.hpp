@@ -145,6 +145,40 @@ public:
         n.drv_off = doff; n.drv_order = drv_.data();
         check(gp_set_snapshot(ctx_, &n), "gp_set_snapshot");
     }
+    // One instance group per entry of `groups` (driver order, executor order): used by the single-AZ packers,
+    // where a "group" is a zone.  Nodes are interned once; a node may appear in one group only.
+    void SetSnapshotGroups(const resources::NodeGroupSchedulingMetadata& md,
+                           const std::vector<std::pair<std::vector<std::string>, std::vector<std::string>>>& groups) {
+        names_.clear(); index_.clear();
+        cpu_.clear(); mem_.clear(); gpu_.clear(); exec_.clear(); drv_.clear();
+        std::vector<int32_t> eoff{0}, doff{0};
+        auto intern = [&](const std::string& n) -> int32_t {
+            auto it = index_.find(n);
+            if (it != index_.end()) return it->second;
+            auto m = md.find(n);
+            if (m == md.end()) return -1;
+            int32_t i = (int32_t)names_.size();
+            names_.push_back(n);
+            index_.emplace(n, i);
+            cpu_.push_back(m->second.AvailableResources.CPU);
+            mem_.push_back(m->second.AvailableResources.Memory);
+            gpu_.push_back(m->second.AvailableResources.NvidiaGPU);
+            return i;
+        };
+        for (const auto& g : groups) {
+            for (const auto& n : g.second) { int32_t i = intern(n); if (i >= 0) exec_.push_back(i); }
+            for (const auto& n : g.first) { int32_t i = intern(n); if (i >= 0) drv_.push_back(i); }
+            eoff.push_back((int32_t)exec_.size());
+            doff.push_back((int32_t)drv_.size());
+        }
+        gp_nodes n{};
+        n.n_nodes = (int32_t)names_.size();
+        n.avail_cpu_milli = cpu_.data(); n.avail_mem_bytes = mem_.data(); n.avail_gpu = gpu_.data();
+        n.n_groups = (int32_t)groups.size();
+        n.exec_off = eoff.data(); n.exec_order = exec_.data();
+        n.drv_off = doff.data(); n.drv_order = drv_.data();
+        check(gp_set_snapshot(ctx_, &n), "gp_set_snapshot");
+    }
     const std::string& name(int32_t i) const { return names_.at((size_t)i); }
     size_t n_nodes() const { return names_.size(); }
     void check(int st, const char* what) {
@@ -211,6 +245,165 @@ inline const SparkBinPackFunction DistributeEvenly = [](const resources::Resourc
 }  // namespace binpack
 
 // ------------------------------------------------------------------------------------------------
+// Packing efficiencies (LIB/binpack/efficiency.go) and the zone-aware tightly-pack variants
+// (SURVEY §8f row f3).  Host-side float64, same operation order as the Go code; the placements
+// themselves come from the device: one instance group per zone, one independent decision per zone.
+namespace binpack {
+
+struct PackingEfficiency {                 // efficiency.go:51-56
+    std::string NodeName;
+    double CPU = 0, Memory = 0, GPU = 0;
+    double Max() const { return std::max(GPU, std::max(CPU, Memory)); }           // :59-61
+};
+struct AvgPackingEfficiency {              // efficiency.go:24-29
+    double CPU = 0, Memory = 0, GPU = 0, Max = 0;
+    bool LessThan(const AvgPackingEfficiency& o) const { return Max < o.Max; }    // :33-35
+};
+inline AvgPackingEfficiency WorstAvgPackingEfficiency() { return AvgPackingEfficiency{}; }   // :38-45
+
+// Quantity.Value() of a milli-scaled CPU: whole cores, inexact values rounded away from zero
+// (k8s apimachinery quantity.go:732-734 -> math.go:166-199)
+inline int64_t cpuValue(int64_t milli) {
+    int64_t q = milli / 1000, rem = milli % 1000;
+    return rem > 0 ? q + 1 : (rem < 0 ? q - 1 : q);
+}
+inline int64_t normalizeResource(int64_t v) { return v == 0 ? 1 : v; }            // :104-109
+
+// computePackingEfficiency, efficiency.go:79-102
+inline PackingEfficiency computePackingEfficiency(const std::string& nodeName, const resources::NodeSchedulingMetadata& m,
+                                                  const resources::NodeGroupResources& reserved) {
+    resources::Resources r = m.SchedulableResources;
+    r.Sub(m.AvailableResources);
+    auto it = reserved.find(nodeName);
+    if (it != reserved.end()) r.Add(it->second);
+    PackingEfficiency e;
+    e.NodeName = nodeName;
+    if (m.SchedulableResources.NvidiaGPU != 0)
+        e.GPU = (double)r.NvidiaGPU / (double)normalizeResource(m.SchedulableResources.NvidiaGPU);
+    e.CPU = (double)cpuValue(r.CPU) / (double)normalizeResource(cpuValue(m.SchedulableResources.CPU));
+    e.Memory = (double)r.Memory / (double)normalizeResource(m.SchedulableResources.Memory);
+    return e;
+}
+
+// ComputeAvgPackingEfficiency, efficiency.go:114-156
+inline AvgPackingEfficiency ComputeAvgPackingEfficiency(const resources::NodeGroupSchedulingMetadata& md,
+                                                        const std::vector<PackingEfficiency>& effs) {
+    if (effs.empty()) return WorstAvgPackingEfficiency();
+    double cpuSum = 0, gpuSum = 0, memorySum = 0, maxSum = 0;
+    int nodesWithGPU = 0;
+    for (const auto& e : effs) {
+        cpuSum += e.CPU;
+        memorySum += e.Memory;
+        if (md.at(e.NodeName).SchedulableResources.NvidiaGPU != 0) { gpuSum += e.GPU; nodesWithGPU++; }
+        maxSum += e.Max();
+    }
+    double length = std::max((double)effs.size(), 1.0);
+    AvgPackingEfficiency a;
+    a.CPU = cpuSum / length; a.Memory = memorySum / length;
+    a.GPU = nodesWithGPU == 0 ? 1.0 : gpuSum / (double)nodesWithGPU;
+    a.Max = maxSum / length;
+    return a;
+}
+
+// reserved map of SparkBinPack (binpack.go:72-75) rebuilt from a placement
+inline resources::NodeGroupResources ReservedOf(const resources::Resources& drv, const resources::Resources& exe,
+                                                const PackingResult& r) {
+    resources::NodeGroupResources reserved;
+    reserved[r.DriverNode] = drv;
+    for (const auto& n : r.ExecutorNodes) reserved[n].Add(exe);
+    return reserved;
+}
+
+// groupNodesByZone, single_az.go:57-73
+inline void groupNodesByZone(const std::vector<std::string>& nodeNames, const resources::NodeGroupSchedulingMetadata& md,
+                             std::vector<std::string>* zonesInOrder, std::unordered_map<std::string, std::vector<std::string>>* byZone) {
+    for (const auto& n : nodeNames) {
+        auto m = md.find(n);
+        if (m == md.end()) continue;
+        auto it = byZone->find(m->second.ZoneLabel);
+        if (it == byZone->end()) { zonesInOrder->push_back(m->second.ZoneLabel); it = byZone->emplace(m->second.ZoneLabel, std::vector<std::string>{}).first; }
+        it->second.push_back(n);
+    }
+}
+
+// getSingleAZSparkBinFunction(tightlyPackExecutors) + chooseBestResult, single_az.go:23-55,75-97:
+// every candidate zone is packed in ONE device batch (zone = instance group), the best result is chosen on
+// the host by average packing efficiency over [driver] + ExecutorNodes.
+inline PackingResult SingleAZTightlyPackImpl(const resources::Resources& drv, const resources::Resources& exe, int count,
+                                             const std::vector<std::string>& driverOrder, const std::vector<std::string>& executorOrder,
+                                             const resources::NodeGroupSchedulingMetadata& md) {
+    std::vector<std::string> dzOrder, ezOrder;
+    std::unordered_map<std::string, std::vector<std::string>> dz, ez;
+    groupNodesByZone(driverOrder, md, &dzOrder, &dz);
+    groupNodesByZone(executorOrder, md, &ezOrder, &ez);
+    std::vector<std::pair<std::vector<std::string>, std::vector<std::string>>> groups;
+    for (const auto& z : dzOrder)
+        if (ez.count(z)) groups.emplace_back(dz[z], ez[z]);                         // :36-41
+    if (groups.empty()) return EmptyPackingResult();
+    gangpack::Device& d = gangpack::Device::Get();
+    d.SetSnapshotGroups(md, groups);
+    const size_t Z = groups.size();
+    const int64_t k = count > 0 ? count : 0;
+    std::vector<int64_t> dc(Z, drv.CPU), dm(Z, drv.Memory), dg(Z, drv.NvidiaGPU), ec(Z, exe.CPU), em(Z, exe.Memory), eg(Z, exe.NvidiaGPU), off(Z + 1);
+    std::vector<int32_t> cnt(Z, count), grp(Z), driver(Z, -1), exec((size_t)std::max<int64_t>(k * (int64_t)Z, 1));
+    for (size_t z = 0; z < Z; ++z) { grp[z] = (int32_t)z; off[z] = k * (int64_t)z; }
+    off[Z] = k * (int64_t)Z;
+    gp_apps a{};
+    a.n_apps = (int32_t)Z;
+    a.drv_cpu_milli = dc.data(); a.drv_mem_bytes = dm.data(); a.drv_gpu = dg.data();
+    a.exe_cpu_milli = ec.data(); a.exe_mem_bytes = em.data(); a.exe_gpu = eg.data();
+    a.exe_count = cnt.data(); a.group = grp.data(); a.exec_out_off = off.data();
+    gp_results r{};
+    r.driver_node = driver.data(); r.executor_nodes = exec.data(); r.executor_nodes_cap = (int64_t)exec.size();
+    d.check(gp_pack_batch(d.ctx(), &a, GP_TIGHTLY_PACK, GP_MODE_INDEPENDENT, &r), "gp_pack_batch");
+    PackingResult best = EmptyPackingResult();                                      // :79
+    AvgPackingEfficiency bestAvg = WorstAvgPackingEfficiency();                     // :80
+    for (size_t z = 0; z < Z; ++z) {
+        if (driver[z] < 0) continue;                                                // :44-46
+        PackingResult res;
+        res.HasCapacity = true;
+        res.DriverNode = d.name(driver[z]);
+        for (int64_t t = off[z]; t < off[z + 1]; ++t) res.ExecutorNodes.push_back(d.name(exec[(size_t)t]));
+        auto reserved = ReservedOf(drv, exe, res);
+        std::vector<PackingEfficiency> effs;                                        // :83-89: [driver] + executors, duplicates kept
+        effs.push_back(computePackingEfficiency(res.DriverNode, md.at(res.DriverNode), reserved));
+        for (const auto& n : res.ExecutorNodes) effs.push_back(computePackingEfficiency(n, md.at(n), reserved));
+        AvgPackingEfficiency avg = ComputeAvgPackingEfficiency(md, effs);
+        if (bestAvg.LessThan(avg)) { best = res; bestAvg = avg; }                   // :91-94
+    }
+    return best;
+}
+
+inline PackingResult GuardedSingleAZ(bool azAware, const resources::Resources& d, const resources::Resources& e, int c,
+                                     const std::vector<std::string>& dord, const std::vector<std::string>& eord,
+                                     const resources::NodeGroupSchedulingMetadata& md) {
+    const int key = azAware ? 101 : 100;
+    try {
+        PackingResult r = SingleAZTightlyPackImpl(d, e, c, dord, eord, md);
+        if (r.HasCapacity || !azAware) return r;
+        return gangpack::PackOne(GP_TIGHTLY_PACK, d, e, c, dord, eord, md);          // az_aware_pack_tightly.go:33-37
+    } catch (const gangpack::Error&) {
+        auto f = gangpack::Fallbacks().find(key);
+        if (f != gangpack::Fallbacks().end() && f->second) return f->second(d, e, c, dord, eord, md);
+        throw;
+    }
+}
+
+// binpack.SingleAZTightlyPack (single_az_pack_tightly.go) / binpack.AzAwareTightlyPack (az_aware_pack_tightly.go:27-38)
+inline const SparkBinPackFunction SingleAZTightlyPack = [](const resources::Resources& d, const resources::Resources& e, int c,
+                                                           const std::vector<std::string>& dord, const std::vector<std::string>& eord,
+                                                           const resources::NodeGroupSchedulingMetadata& md) {
+    return GuardedSingleAZ(false, d, e, c, dord, eord, md);
+};
+inline const SparkBinPackFunction AzAwareTightlyPack = [](const resources::Resources& d, const resources::Resources& e, int c,
+                                                          const std::vector<std::string>& dord, const std::vector<std::string>& eord,
+                                                          const resources::NodeGroupSchedulingMetadata& md) {
+    return GuardedSingleAZ(true, d, e, c, dord, eord, md);
+};
+
+}  // namespace binpack
+
+// ------------------------------------------------------------------------------------------------
 namespace binpacker {
 
 struct Binpacker {                        // internal/binpacker/binpack.go:37-41
@@ -222,20 +415,24 @@ struct Binpacker {                        // internal/binpacker/binpack.go:37-41
 
 inline const char* const tightlyPack = "tightly-pack";            // :23
 inline const char* const distributeEvenly = "distribute-evenly";  // :22
+inline const char* const azAwareTightlyPack = "az-aware-tightly-pack";      // :24
+inline const char* const SingleAzTightlyPack = "single-az-tightly-pack";    // :29
 
-// binpackFunctions (:43-49) restricted to the two packers on the hot path.  The reference's other three
-// names (az-aware-tightly-pack, single-az-tightly-pack, single-az-minimal-fragmentation) are NOT
-// provided here: SelectBinpacker returns nullptr for them so the embedding keeps the Go function.
+// binpackFunctions (:43-49): the two packers of the hot path plus the zone-aware tightly-pack variants built
+// on them.  single-az-minimal-fragmentation is NOT provided: SelectBinpacker returns nullptr for it so the
+// embedding keeps the Go function.
 inline const std::map<std::string, Binpacker>& binpackFunctions() {
     static const std::map<std::string, Binpacker> m = {
         {tightlyPack, {tightlyPack, binpack::TightlyPack, false, GP_TIGHTLY_PACK}},
         {distributeEvenly, {distributeEvenly, binpack::DistributeEvenly, false, GP_DISTRIBUTE_EVENLY}},
+        {azAwareTightlyPack, {azAwareTightlyPack, binpack::AzAwareTightlyPack, false, GP_TIGHTLY_PACK}},
+        {SingleAzTightlyPack, {SingleAzTightlyPack, binpack::SingleAZTightlyPack, true, GP_TIGHTLY_PACK}},
     };
     return m;
 }
 
 inline bool IsReferenceOnlyPacker(const std::string& name) {
-    return name == "az-aware-tightly-pack" || name == "single-az-tightly-pack" || name == "single-az-minimal-fragmentation";
+    return name == "single-az-minimal-fragmentation";
 }
 
 // SelectBinpacker (:52-58): unknown names select distribute-evenly, exactly like the reference.

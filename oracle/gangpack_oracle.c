@@ -335,13 +335,34 @@ static void avg_packing_efficiency(const orc_cluster* c, resmap* reserved, doubl
     pool_free(effs, effs_bytes);
 }
 
+/* ComputeAvgPackingEfficiency (efficiency.go:114-156) over the node list [driver] + ExecutorNodes of one
+ * result, exactly as chooseBestResult builds it (single_az.go:83-89; duplicates included, slice order). */
+static void result_nodes_avg_efficiency(const orc_cluster* c, resmap* reserved, const char* driver,
+                                        const char* const* execs, int32_t count, double* out4) {
+    double cpu = 0, mem = 0, gpu = 0, mx = 0; int32_t with_gpu = 0;
+    for (int32_t i = -1; i < count; ++i) {
+        const char* n = i < 0 ? driver : execs[i];
+        const node_meta* m = meta_lookup(c, n);
+        pack_eff e = compute_packing_efficiency(m, resmap_get(reserved, n));
+        cpu += e.cpu; mem += e.mem;
+        if (m->schedulable.gpu != 0) { gpu += e.gpu; with_gpu++; }
+        double m2 = e.cpu > e.mem ? e.cpu : e.mem;
+        mx += e.gpu > m2 ? e.gpu : m2;
+    }
+    double len = (double)(count + 1);
+    out4[0] = cpu / len; out4[1] = mem / len;
+    out4[2] = with_gpu == 0 ? 1.0 : gpu / (double)with_gpu;
+    out4[3] = mx / len;
+}
+
 /* ------------------------------------------------------------------ SparkBinPack ---- */
 /* LIB/binpack/binpack.go:60-87.  executor_names: scratch of >= count entries. */
 static int spark_bin_pack(const orc_cluster* c, const orc_res* drv, const orc_res* exe, int32_t count,
                           const char* const* driver_order, int32_t n_driver,
                           const char* const* exec_order, int32_t n_exec,
                           distribute_fn distribute, int with_efficiencies,
-                          const char** driver_name, const char** executor_names, double* avg_eff) {
+                          const char** driver_name, const char** executor_names, double* avg_eff,
+                          double* choose_eff /* may be NULL: chooseBestResult's average */) {
     for (int32_t i = 0; i < n_driver; ++i) {                                   /* :67 */
         const char* d = driver_order[i];
         const node_meta* m = meta_lookup(c, d);                                /* :68 */
@@ -352,6 +373,7 @@ static int spark_bin_pack(const orc_cluster* c, const orc_res* drv, const orc_re
         int ok = distribute(c, exe, count, exec_order, n_exec, &reserved, executor_names); /* :74-75 */
         if (ok) {                                                              /* :76 */
             if (with_efficiencies) avg_packing_efficiency(c, &reserved, avg_eff); /* :77 */
+            if (choose_eff) result_nodes_avg_efficiency(c, &reserved, d, executor_names, count, choose_eff);
             resmap_free(&reserved);
             *driver_name = d;                                                  /* :78-83 */
             return 1;
@@ -365,7 +387,92 @@ static int spark_bin_pack(const orc_cluster* c, const orc_res* drv, const orc_re
 
 /* internal/binpacker/binpack.go:43-58: name -> function; here by algo id. */
 static distribute_fn select_distributor(int algo) {
-    return algo == ORC_TIGHTLY_PACK ? tightly_pack_executors : distribute_executors_evenly;
+    return algo == ORC_DISTRIBUTE_EVENLY ? distribute_executors_evenly : tightly_pack_executors;
+}
+
+/* groupNodesByZone, LIB/binpack/single_az.go:57-73: zones in order of first appearance, names per zone in
+ * order; names missing from the metadata are dropped. */
+typedef struct { int32_t n_zones; const char** zone; const char*** names; int32_t* count; } zone_groups;
+
+static void group_nodes_by_zone(const orc_cluster* c, const char* const* order, int32_t n, zone_groups* g) {
+    g->n_zones = 0;
+    g->zone = (const char**)malloc(sizeof(char*) * (size_t)(n > 0 ? n : 1));
+    g->names = (const char***)malloc(sizeof(char**) * (size_t)(n > 0 ? n : 1));
+    g->count = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    for (int32_t i = 0; i < n; ++i) {
+        const node_meta* m = meta_lookup(c, order[i]);
+        if (m == NULL) continue;                                              /* :62-65 */
+        int32_t z = -1;
+        for (int32_t k = 0; k < g->n_zones; ++k) if (strcmp(g->zone[k], m->zone) == 0) { z = k; break; }
+        if (z < 0) {                                                          /* :67-69 */
+            z = g->n_zones++;
+            g->zone[z] = m->zone;
+            g->names[z] = (const char**)malloc(sizeof(char*) * (size_t)n);
+            g->count[z] = 0;
+        }
+        g->names[z][g->count[z]++] = order[i];                                /* :70 */
+    }
+}
+static void zone_groups_free(zone_groups* g) {
+    for (int32_t k = 0; k < g->n_zones; ++k) free((void*)g->names[k]);
+    free((void*)g->zone); free((void*)g->names); free(g->count);
+}
+
+/* getSingleAZSparkBinFunction + chooseBestResult, LIB/binpack/single_az.go:23-55,75-97 */
+static int single_az_pack(const orc_cluster* c, const orc_res* drv, const orc_res* exe, int32_t count,
+                          const char* const* driver_order, int32_t n_driver,
+                          const char* const* exec_order, int32_t n_exec,
+                          distribute_fn distribute, int with_efficiencies,
+                          const char** driver_name, const char** executor_names, double* avg_eff) {
+    zone_groups dz, ez;
+    group_nodes_by_zone(c, driver_order, n_driver, &dz);                      /* :31 */
+    group_nodes_by_zone(c, exec_order, n_exec, &ez);                          /* :32 */
+    const char** trial = (const char**)malloc(sizeof(char*) * (size_t)(count > 0 ? count : 1));
+    int have_best = 0;
+    double best_max = 0.0;                                                    /* WorstAvgPackingEfficiency, :80 */
+    double best_avg[4] = {0, 0, 0, 0};
+    for (int32_t z = 0; z < dz.n_zones; ++z) {                                /* :36 */
+        int32_t e = -1;
+        for (int32_t k = 0; k < ez.n_zones; ++k) if (strcmp(ez.zone[k], dz.zone[z]) == 0) { e = k; break; }
+        if (e < 0) continue;                                                  /* :38-41 */
+        const char* dname = NULL; double all_eff[4], choose[4];
+        int ok = spark_bin_pack(c, drv, exe, count, dz.names[z], dz.count[z], ez.names[e], ez.count[e], distribute,
+                                with_efficiencies, &dname, trial, all_eff, choose);      /* :42 */
+        if (!ok) continue;                                                    /* :44-46 */
+        if (best_max < choose[3]) {                                           /* :91 LessThan compares Max only */
+            have_best = 1; best_max = choose[3];
+            *driver_name = dname;
+            memcpy((void*)executor_names, trial, sizeof(char*) * (size_t)count);
+            memcpy(best_avg, all_eff, sizeof(best_avg));
+        }
+    }
+    free((void*)trial); zone_groups_free(&dz); zone_groups_free(&ez);
+    if (!have_best) {                                                         /* :49-51 and the EmptyPackingResult start value of :79 */
+        *driver_name = NULL;
+        if (avg_eff) avg_eff[0] = avg_eff[1] = avg_eff[2] = avg_eff[3] = 0.0;
+        return 0;
+    }
+    if (avg_eff && with_efficiencies) memcpy(avg_eff, best_avg, sizeof(best_avg));
+    return 1;
+}
+
+/* the `binpack:` registry of internal/binpacker/binpack.go:43-49 restricted to the packers restated here */
+static int pack_by_algo(const orc_cluster* c, int algo, const orc_res* drv, const orc_res* exe, int32_t count,
+                        const char* const* driver_order, int32_t n_driver,
+                        const char* const* exec_order, int32_t n_exec, int with_efficiencies,
+                        const char** driver_name, const char** executor_names, double* avg_eff) {
+    if (algo == ORC_SINGLE_AZ_TIGHTLY_PACK)                                   /* single_az_pack_tightly.go */
+        return single_az_pack(c, drv, exe, count, driver_order, n_driver, exec_order, n_exec, tightly_pack_executors,
+                              with_efficiencies, driver_name, executor_names, avg_eff);
+    if (algo == ORC_AZ_AWARE_TIGHTLY_PACK) {                                  /* az_aware_pack_tightly.go:27-38 */
+        if (single_az_pack(c, drv, exe, count, driver_order, n_driver, exec_order, n_exec, tightly_pack_executors,
+                           with_efficiencies, driver_name, executor_names, avg_eff))
+            return 1;
+        return spark_bin_pack(c, drv, exe, count, driver_order, n_driver, exec_order, n_exec, tightly_pack_executors,
+                              with_efficiencies, driver_name, executor_names, avg_eff, NULL);
+    }
+    return spark_bin_pack(c, drv, exe, count, driver_order, n_driver, exec_order, n_exec, select_distributor(algo),
+                          with_efficiencies, driver_name, executor_names, avg_eff, NULL);
 }
 
 int orc_binpack(const orc_cluster* c, int algo, const orc_res* drv, const orc_res* exe, int32_t count,
@@ -375,8 +482,8 @@ int orc_binpack(const orc_cluster* c, int algo, const orc_res* drv, const orc_re
                 int32_t* driver_node, int32_t* executor_nodes, double* avg_eff) {
     const char** names = (const char**)malloc(sizeof(char*) * (size_t)(count > 0 ? count : 1));
     const char* dname = NULL;
-    int ok = spark_bin_pack(c, drv, exe, count, driver_order, n_driver, exec_order, n_exec,
-                            select_distributor(algo), with_efficiencies, &dname, names, avg_eff);
+    int ok = pack_by_algo(c, algo, drv, exe, count, driver_order, n_driver, exec_order, n_exec,
+                          with_efficiencies, &dname, names, avg_eff);
     *driver_node = ok ? orc_cluster_index(c, dname) : -1;
     if (ok) for (int32_t i = 0; i < count; ++i) executor_nodes[i] = orc_cluster_index(c, names[i]);
     free(names);
@@ -441,8 +548,8 @@ int32_t orc_fifo(orc_cluster* c, int algo, int mode, int32_t n_apps,
     int32_t i = 0;
     for (; i < n_apps; ++i) {                                                    /* :230 */
         const char* dname = NULL; double eff[4];
-        int ok = spark_bin_pack(c, &drv[i], &exe[i], count[i], driver_order, n_driver, exec_order, n_exec,
-                                select_distributor(algo), with_efficiencies, &dname, names, eff); /* :238-243 */
+        int ok = pack_by_algo(c, algo, &drv[i], &exe[i], count[i], driver_order, n_driver, exec_order, n_exec,
+                              with_efficiencies, &dname, names, eff); /* :238-243 */
         if (!ok) {                                                               /* :244 */
             driver_node[i] = -1;
             if (young && young[i]) continue;                                     /* :245-249 shouldSkipDriverFifo */

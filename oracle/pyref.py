@@ -200,3 +200,91 @@ def potential_nodes(meta, zones, candidate_names, unschedulable=(), not_ready=()
         return sorted(names, key=functools.cmp_to_key(cmp))
 
     return label_sort(drivers, driver_label_rank), label_sort(execs, exec_label_rank)
+
+
+# ---------------------------------------------------------------------------------------------
+# single-AZ / AZ-aware tightly-pack with the float64 packing efficiencies
+# ---------------------------------------------------------------------------------------------
+def cpu_value(milli):
+    """Quantity.Value() of a milli-scaled CPU: whole cores, inexact values rounded away from zero
+    (quantity.go:732-734 -> math.go:166-199)."""
+    q, rem = abs(milli) // 1000, abs(milli) % 1000
+    v = q + (1 if rem else 0)
+    return v if milli >= 0 else -v
+
+
+def compute_packing_efficiency(avail, sched, reserved):
+    """computePackingEfficiency, LIB/binpack/efficiency.go:79-102 -> (cpu, mem, gpu)."""
+    r = sub(sched, avail)
+    if reserved is not None:
+        r = add(r, reserved)
+    norm = lambda v: 1 if v == 0 else v
+    gpu = 0.0
+    if sched[2] != 0:
+        gpu = float(r[2]) / float(norm(sched[2]))
+    return (float(cpu_value(r[0])) / float(norm(cpu_value(sched[0]))), float(r[1]) / float(norm(sched[1])), gpu)
+
+
+def avg_packing_efficiency(effs_with_sched_gpu):
+    """ComputeAvgPackingEfficiency, efficiency.go:114-156 over [(cpu, mem, gpu, sched_gpu)] -> (cpu, mem, gpu, max)."""
+    if not effs_with_sched_gpu:
+        return (0.0, 0.0, 0.0, 0.0)
+    cpu = mem = gpu = mx = 0.0
+    with_gpu = 0
+    for c, m, g, sg in effs_with_sched_gpu:
+        cpu += c
+        mem += m
+        if sg != 0:
+            gpu += g
+            with_gpu += 1
+        mx += max(g, max(c, m))
+    n = max(float(len(effs_with_sched_gpu)), 1.0)
+    return (cpu / n, mem / n, 1.0 if with_gpu == 0 else gpu / float(with_gpu), mx / n)
+
+
+def _reserved_of(drv, exe, driver, nodes):
+    reserved = {driver: drv}
+    for n in nodes:
+        reserved[n] = add(reserved.get(n, ZERO), exe)
+    return reserved
+
+
+def group_nodes_by_zone(order, meta, zones):
+    """groupNodesByZone, LIB/binpack/single_az.go:57-73."""
+    in_order, by_zone = [], {}
+    for n in order:
+        if n not in meta:
+            continue
+        z = zones.get(n, "default")
+        if z not in by_zone:
+            in_order.append(z)
+            by_zone[z] = []
+        by_zone[z].append(n)
+    return in_order, by_zone
+
+
+def single_az_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched, zones):
+    """getSingleAZSparkBinFunction(tightlyPackExecutors) + chooseBestResult, single_az.go:23-55,75-97."""
+    dz_order, dz = group_nodes_by_zone(driver_order, meta, zones)
+    _, ez = group_nodes_by_zone(exec_order, meta, zones)
+    best, best_max = (None, [], False), 0.0
+    for z in dz_order:
+        if z not in ez:
+            continue
+        d, nodes, ok = spark_bin_pack(drv, exe, count, dz[z], ez[z], meta, tightly_pack_executors)
+        if not ok:
+            continue
+        reserved = _reserved_of(drv, exe, d, nodes)
+        effs = [compute_packing_efficiency(meta[n], sched[n], reserved.get(n)) + (sched[n][2],) for n in [d] + nodes]
+        avg = avg_packing_efficiency(effs)
+        if best_max < avg[3]:
+            best, best_max = (d, nodes, True), avg[3]
+    return best
+
+
+def az_aware_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched, zones):
+    """AzAwareTightlyPack, LIB/binpack/az_aware_pack_tightly.go:27-38."""
+    r = single_az_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched, zones)
+    if r[2]:
+        return r
+    return spark_bin_pack(drv, exe, count, driver_order, exec_order, meta, tightly_pack_executors)

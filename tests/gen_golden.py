@@ -123,6 +123,43 @@ def main():
         "E6", "empty executor order with count>0 never fits; empty driver order never fits",
         nodes(("n0", 8000, 16 * Gi, 0)), {**app_readme, "count": 1}, exec_order=[]))
 
+    # ---- single-AZ / AZ-aware tightly-pack ----------------------------------------
+    zone_cases = []
+
+    def zone_case(cid, source, node_list, zones, app, pinned_fit=None, sched=None):
+        names = [n["name"] for n in node_list]
+        meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in node_list}
+        sch = sched if sched is not None else dict(meta)
+        expect = {}
+        for algo, fn in (("single-az-tightly-pack", pyref.single_az_tightly_pack), ("az-aware-tightly-pack", pyref.az_aware_tightly_pack)):
+            d, ex, ok = fn(tuple(app["drv"]), tuple(app["exe"]), app["count"], names, names, dict(meta), sch, zones)
+            expect[algo] = {"fit": ok, "driver": d, "executors": ex}
+            if pinned_fit is not None:
+                assert ok == pinned_fit, (cid, algo)
+        return {"id": cid, "source": source, "nodes": node_list, "zones": zones,
+                "schedulable": [{"name": n, "cpu": sch[n][0], "mem": sch[n][1], "gpu": sch[n][2]} for n in names],
+                "app": app, "expect": expect,
+                "pinned": {"fit": "reference-test" if pinned_fit is not None else "derived", "driver": "derived", "executors": "derived"}}
+
+    hz = {"node1": "zone1", "node2": "zone1"}
+    zone_cases.append(zone_case("Z-T0", "internal/extender/resource_test.go:27-51 TestScheduler through single-az-tightly-pack (the harness packer)",
+                                harness_nodes, hz, {**static_app, "count": 2}, pinned_fit=True))
+    zone_cases.append(zone_case("Z-T1b", "internal/extender/unschedulablepods_test.go:45-53: 100 executors exceed capacity",
+                                harness_nodes, hz, {**static_app, "count": 100}, pinned_fit=False))
+    zone_cases.append(zone_case("Z-T2", "internal/extender/unschedulablepods_test.go:55-80: not enough GPUs",
+                                harness_nodes, hz, {"drv": [1000, 1, 1], "exe": [1000, 1, 1], "count": 2}, pinned_fit=False))
+    three_zone = nodes(("a1", 8000, 16 * Gi, 0), ("a2", 2000, 4 * Gi, 0), ("b1", 16000, 64 * Gi, 0), ("b2", 4000, 8 * Gi, 0),
+                       ("c1", 3000, 6 * Gi, 0))
+    tz = {"a1": "za", "a2": "za", "b1": "zb", "b2": "zb", "c1": "zc"}
+    tsched = {"a1": (8000, 16 * Gi, 0), "a2": (8000, 16 * Gi, 0), "b1": (16000, 64 * Gi, 0), "b2": (8000, 16 * Gi, 0), "c1": (4000, 8 * Gi, 0)}
+    zone_cases.append(zone_case("Z1", "derived: both za and zb fit; chooseBestResult takes the higher average Max efficiency (single_az.go:75-97)",
+                                three_zone, tz, {**app_readme, "count": 3}, sched=tsched))
+    zone_cases.append(zone_case("Z2", "derived: no single zone fits 9 executors; az-aware falls back to plain tightly-pack (az_aware_pack_tightly.go:33-37)",
+                                three_zone, tz, {**app_readme, "count": 9}, sched=tsched))
+    zone_cases.append(zone_case("Z3", "derived: zero-resource app: every zone 'fits' with efficiency... chooseBestResult needs Max > 0",
+                                nodes(("a1", 0, 0, 0), ("b1", 0, 0, 0)), {"a1": "za", "b1": "zb"},
+                                {"drv": [0, 0, 0], "exe": [0, 0, 0], "count": 2}, sched={"a1": (0, 0, 0), "b1": (0, 0, 0)}))
+
     # ---- FIFO loop (fitEarlierDrivers) ----------------------------------------------------------
     fifo_cases = []
 
@@ -199,7 +236,7 @@ def main():
 
     out = {"_comment": "generated by tests/gen_golden.py -- do not edit by hand",
            "units": {"cpu": "millicores", "mem": "bytes", "gpu": "units"},
-           "pack_cases": cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
+           "pack_cases": cases, "zone_cases": zone_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
     path = os.path.join(ROOT, "tests", "golden", "hotpath_vectors.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:

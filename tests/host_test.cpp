@@ -8,6 +8,8 @@
 #include <vector>
 
 #include "gangpack_host.hpp"
+#include "gangpack_oracle.h"   // the CPU oracle is the checker here (tests/ may link it; the product never does)
+#include <random>
 
 static int failures = 0;
 #define EXPECT(cond, msg)                                                            \
@@ -68,7 +70,9 @@ static void TestSelectBinpacker() {   // internal/binpacker/binpack.go:52-58
     EXPECT(binpacker::SelectBinpacker("tightly-pack")->Name == "tightly-pack", "tightly-pack");
     EXPECT(binpacker::SelectBinpacker("no-such-packer")->Name == "distribute-evenly", "unknown name selects distribute-evenly");
     EXPECT(!binpacker::SelectBinpacker("tightly-pack")->IsSingleAz, "IsSingleAz false");
-    EXPECT(binpacker::SelectBinpacker("single-az-tightly-pack") == nullptr, "reference-only packers stay with the Go function");
+    EXPECT(binpacker::SelectBinpacker("single-az-tightly-pack")->IsSingleAz, "single-az-tightly-pack is a single-AZ packer (demands.go:169 reads this)");
+    EXPECT(!binpacker::SelectBinpacker("az-aware-tightly-pack")->IsSingleAz, "az-aware-tightly-pack is not");
+    EXPECT(binpacker::SelectBinpacker("single-az-minimal-fragmentation") == nullptr, "packers not provided stay with the Go function");
 }
 
 static void TestExecutorNodeOrder() {   // SURVEY App. A.5 V1 / V3 (tests/golden/hotpath_vectors.json)
@@ -176,8 +180,108 @@ static void TestFallbackPolicy() {
     gangpack::Fallbacks().clear();
 }
 
+// The reference's harness tests run through single-az-tightly-pack (resource_test.go:34, unschedulablepods_test.go:29,62)
+static void TestHarnessThroughSingleAz() {
+    NodeGroupSchedulingMetadata md;
+    md["node1"] = NewNode("zone1"); md["node2"] = NewNode("zone1");
+    Names n = {"node1", "node2"};
+    for (const char* name : {"single-az-tightly-pack", "az-aware-tightly-pack"}) {
+        const binpacker::Binpacker* bp = binpacker::SelectBinpacker(name);
+        EXPECT(bp->BinpackFunc(CreateResources(1000, 1, 1), CreateResources(1000, 1, 0), 2, n, n, md).HasCapacity,
+               "TestScheduler: there should be enough capacity to schedule the full application");
+        EXPECT(!bp->BinpackFunc(CreateResources(1000, 1, 1), CreateResources(1000, 1, 0), 100, n, n, md).HasCapacity,
+               "TestUnschedulablePodMarker: the hundred executor application should not fit");
+        EXPECT(!bp->BinpackFunc(CreateResources(1000, 1, 1), CreateResources(1000, 1, 1), 2, n, n, md).HasCapacity,
+               "TestSchedulerFailsToScheduleWhenNotEnoughNvidiaGPUs");
+    }
+}
+
+static NodeSchedulingMetadata Node(int64_t cpu, int64_t mem, int64_t gpu, int64_t scpu, int64_t smem, int64_t sgpu, const std::string& zone) {
+    NodeSchedulingMetadata m;
+    m.AvailableResources = CreateResources(cpu, mem, gpu);
+    m.SchedulableResources = CreateResources(scpu, smem, sgpu);
+    m.ZoneLabel = zone;
+    return m;
+}
+
+static void TestZoneGoldens() {   // tests/golden/hotpath_vectors.json zone_cases Z1..Z3
+    NodeGroupSchedulingMetadata md;
+    md["a1"] = Node(8000, 16 * Gi, 0, 8000, 16 * Gi, 0, "za"); md["a2"] = Node(2000, 4 * Gi, 0, 8000, 16 * Gi, 0, "za");
+    md["b1"] = Node(16000, 64 * Gi, 0, 16000, 64 * Gi, 0, "zb"); md["b2"] = Node(4000, 8 * Gi, 0, 8000, 16 * Gi, 0, "zb");
+    md["c1"] = Node(3000, 6 * Gi, 0, 4000, 8 * Gi, 0, "zc");
+    Names n = {"a1", "a2", "b1", "b2", "c1"};
+    auto drv = CreateResources(1000, Gi, 0), exe = CreateResources(2000, 4 * Gi, 0);
+    auto z1 = binpack::SingleAZTightlyPack(drv, exe, 3, n, n, md);
+    EXPECT(z1.HasCapacity && z1.DriverNode == "a1" && z1.ExecutorNodes == Names({"a1", "a1", "a1"}), "Z1: chooseBestResult prefers the fuller zone");
+    auto z2s = binpack::SingleAZTightlyPack(drv, exe, 9, n, n, md);
+    EXPECT(z2s.HasCapacity && z2s.DriverNode == "b1" && z2s.ExecutorNodes.size() == 9 && z2s.ExecutorNodes[8] == "b2", "Z2 single-az");
+    auto z2 = binpack::AzAwareTightlyPack(drv, exe, 9, n, n, md);
+    EXPECT(z2.HasCapacity && z2.DriverNode == z2s.DriverNode && z2.ExecutorNodes == z2s.ExecutorNodes, "Z2 az-aware == single-az when a zone fits");
+    NodeGroupSchedulingMetadata zero;
+    zero["a1"] = Node(0, 0, 0, 0, 0, 0, "za"); zero["b1"] = Node(0, 0, 0, 0, 0, 0, "zb");
+    Names zn = {"a1", "b1"};
+    auto z3 = binpack::SingleAZTightlyPack(CreateResources(0, 0, 0), CreateResources(0, 0, 0), 2, zn, zn, zero);
+    EXPECT(!z3.HasCapacity, "Z3: zero efficiency never beats WorstAvgPackingEfficiency (single_az.go:79-94)");
+    auto z3a = binpack::AzAwareTightlyPack(CreateResources(0, 0, 0), CreateResources(0, 0, 0), 2, zn, zn, zero);
+    EXPECT(z3a.HasCapacity && z3a.DriverNode == "a1" && z3a.ExecutorNodes == Names({"a1", "a1"}), "Z3: az-aware falls back to tightly-pack");
+}
+
+// random multi-zone clusters: the device-backed host layer vs the literal CPU oracle, all four packers
+static void TestRandomAgainstOracle() {
+    std::mt19937_64 rng(20260922);
+    auto U = [&](int64_t lo, int64_t hi) { return (int64_t)(lo + (int64_t)(rng() % (uint64_t)(hi - lo + 1))); };
+    int compared = 0;
+    for (int trial = 0; trial < 60; ++trial) {
+        int n = (int)U(2, 40);
+        NodeGroupSchedulingMetadata md;
+        std::vector<std::string> names, zones;
+        std::vector<int64_t> cpu, mem, gpu, scpu, smem, sgpu;
+        for (int i = 0; i < n; ++i) {
+            char buf[16]; std::snprintf(buf, sizeof buf, "n%02d", i);
+            int64_t sc = U(1, 16) * 1000, sm = U(1, 32) * Gi, sg = U(0, 2);
+            int64_t c = U(0, sc / 250) * 250, m = U(0, sm / (Gi / 4)) * (Gi / 4), g = std::min<int64_t>(sg, U(0, 2));
+            std::string z = "z" + std::to_string(U(0, 2));
+            md[buf] = Node(c, m, g, sc, sm, sg, z);
+            names.push_back(buf); zones.push_back(z);
+            cpu.push_back(c); mem.push_back(m); gpu.push_back(g); scpu.push_back(sc); smem.push_back(sm); sgpu.push_back(sg);
+        }
+        Names order = names;
+        std::shuffle(order.begin(), order.end(), rng);
+        std::vector<const char*> cn, cz, co;
+        for (auto& s2 : names) cn.push_back(s2.c_str());
+        for (auto& s2 : zones) cz.push_back(s2.c_str());
+        for (auto& s2 : order) co.push_back(s2.c_str());
+        orc_cluster* cl = orc_cluster_new(n, cn.data(), cpu.data(), mem.data(), gpu.data(), scpu.data(), smem.data(), sgpu.data(),
+                                          cz.data(), nullptr, nullptr);
+        for (int rep = 0; rep < 4; ++rep) {
+            orc_res drv = {U(0, 2) * 500, U(0, 2) * (Gi / 2), U(0, 1)}, exe = {U(1, 4) * 500, U(1, 8) * (Gi / 4), U(0, 1)};
+            int k = (int)U(0, 9);
+            const char* algos[4] = {"tightly-pack", "distribute-evenly", "single-az-tightly-pack", "az-aware-tightly-pack"};
+            for (int algo = 0; algo < 4; ++algo) {
+                int32_t od = -1; std::vector<int32_t> oe((size_t)std::max(k, 1)); double eff[4];
+                int ok = orc_binpack(cl, algo, &drv, &exe, k, co.data(), n, co.data(), n, 1, &od, oe.data(), eff);
+                auto r = binpacker::SelectBinpacker(algos[algo])->BinpackFunc(CreateResources(drv.cpu, drv.mem, drv.gpu),
+                                                                             CreateResources(exe.cpu, exe.mem, exe.gpu), k, order, order, md);
+                bool same = (r.HasCapacity == (ok != 0));
+                if (same && ok) {
+                    same = r.DriverNode == names[(size_t)od] && (int)r.ExecutorNodes.size() == k;
+                    for (int t = 0; same && t < k; ++t) same = r.ExecutorNodes[(size_t)t] == names[(size_t)oe[(size_t)t]];
+                }
+                if (!same) std::printf("mismatch trial %d rep %d algo %s\n", trial, rep, algos[algo]);
+                EXPECT(same, "host layer (device) == literal oracle");
+                ++compared;
+            }
+        }
+        orc_cluster_free(cl);
+    }
+    std::printf("compared %d placements against the oracle\n", compared);
+}
+
 int main() {
     TestScheduler();
+    TestHarnessThroughSingleAz();
+    TestZoneGoldens();
+    TestRandomAgainstOracle();
     TestUnschedulablePodMarker();
     TestSchedulerFailsToScheduleWhenNotEnoughNvidiaGPUs();
     TestSelectBinpacker();

@@ -147,3 +147,52 @@ def test_packing_efficiency_by_product(oracle):
     assert eff[1] == pytest.approx((13 / 16 + 1 + 4 / 16 + 0) / 4, rel=0, abs=1e-15)
     assert eff[2] == 1.0          # no node has GPUs -> 1 (efficiency.go:141-145)
     assert eff[3] == pytest.approx((7 / 8 + 1 + 2 / 8 + 0) / 4, rel=0, abs=1e-15)
+
+
+ZONE_ALGO = {"single-az-tightly-pack": 2, "az-aware-tightly-pack": 3}
+
+
+def test_literal_oracle_zone_cases(golden, oracle):
+    """single-az / az-aware tightly-pack: the harness shapes the reference's own tests run
+    through `single-az-tightly-pack` (fit / no-fit pinned) and derived multi-zone cases incl. the
+    chooseBestResult efficiency comparison and its Max > 0 quirk."""
+    for case in golden["zone_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        _, sc, sm, sg = case_arrays(case["schedulable"])
+        zone = [case["zones"].get(n, "default") for n in names]
+        cl = oracle.Cluster(names, cpu, mem, gpu, sched=(sc, sm, sg), zone=zone)
+        app = case["app"]
+        for algo, aid in ZONE_ALGO.items():
+            ok, d, ex, _ = cl.binpack(aid, app["drv"], app["exe"], app["count"], names, names, with_efficiencies=True)
+            exp = case["expect"][algo]
+            assert ok == exp["fit"], (case["id"], algo)
+            if ok:
+                assert d == exp["driver"] and ex == exp["executors"], (case["id"], algo)
+
+
+def test_zone_packers_random_three_way(oracle):
+    """literal C == pure Python on random multi-zone clusters (efficiency-driven choice included)."""
+    from oracle import pyref
+    rng = np.random.default_rng(99)
+    for trial in range(40):
+        n = int(rng.integers(2, 24))
+        names = ["n%02d" % i for i in range(n)]
+        sched_cpu = rng.integers(1, 17, n) * 1000; sched_mem = rng.integers(1, 33, n) * (1 << 30); sched_gpu = rng.integers(0, 3, n)
+        cpu = (sched_cpu * rng.uniform(0, 1, n)).astype(np.int64) // 250 * 250
+        mem = (sched_mem * rng.uniform(0, 1, n)).astype(np.int64) // (1 << 28) * (1 << 28)
+        gpu = np.minimum(sched_gpu, rng.integers(0, 3, n))
+        zones = {nm: "z%d" % rng.integers(0, 3) for nm in names}
+        order = list(rng.permutation(names))
+        cl = oracle.Cluster(names, cpu, mem, gpu, sched=(sched_cpu, sched_mem, sched_gpu), zone=[zones[nm] for nm in names])
+        meta = {names[i]: (int(cpu[i]), int(mem[i]), int(gpu[i])) for i in range(n)}
+        sched = {names[i]: (int(sched_cpu[i]), int(sched_mem[i]), int(sched_gpu[i])) for i in range(n)}
+        for _ in range(6):
+            drv = (int(rng.integers(0, 3)) * 500, int(rng.integers(0, 3)) << 29, int(rng.integers(0, 2)))
+            exe = (int(rng.integers(1, 5)) * 500, int(rng.integers(1, 9)) << 28, int(rng.integers(0, 2)))
+            k = int(rng.integers(0, 10))
+            for fn, aid in ((pyref.single_az_tightly_pack, 2), (pyref.az_aware_tightly_pack, 3)):
+                d, ex, ok = fn(drv, exe, k, order, order, dict(meta), sched, zones)
+                lok, ld, lex, _ = cl.binpack(aid, drv, exe, k, order, order, with_efficiencies=True)
+                assert ok == lok, (trial, aid)
+                if ok:
+                    assert d == ld and ex == lex, (trial, aid)
