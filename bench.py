@@ -369,8 +369,11 @@ def main():
     # ---- end-to-end through the C ABI with host buffers -------------------------------------------
     # all-zero GPU request columns are passed as NULL (= 0), as the ABI allows; the shim knows while marshalling
     host_keys = [k for k in a if not (k in ("drv_gpu", "exe_gpu") and not a[k].any())]
-    pin = {k: packer.pinned(len(a[k]), a[k].dtype) for k in host_keys}
+    i64_cols = [k for k in ("drv_cpu", "drv_mem", "exe_cpu", "exe_mem", "drv_gpu", "exe_gpu") if k in host_keys]
+    pin = packer.pinned_columns(q, i64_cols)          # one pinned block, column after column (as the shim allocates it)
     for k in host_keys:
+        if k not in pin:
+            pin[k] = packer.pinned(len(a[k]), a[k].dtype)
         pin[k][:] = a[k]
     if w["groups"] == 1:
         pin.pop("group", None)

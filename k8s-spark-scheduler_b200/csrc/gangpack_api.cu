@@ -285,7 +285,9 @@ struct gp_ctx {
     void* one_block = nullptr;                    // gp_pack_one staging (mapped pinned)
     size_t one_bytes = 0;
     int zero_copy = 1;                            // GANGPACK_ZERO_COPY=0 disables reading/writing mapped host buffers in kernels
-    int zero_copy_in_max = 1 << 30;               // batches up to this size read their inputs in place (GANGPACK_ZC_IN_MAX)
+    int zero_copy_in_max = 1 << 30;               // batches up to this size read their inputs in place (GANGPACK_ZC_IN_MAX).
+                                                  // Measured on this pool: SM reads of mapped memory sustain ~21 GB/s, H2D DMA
+                                                  // 15-33 GB/s depending on the host -> in-place reads are the steadier default
     int chunk_apps = kChunkApps;                  // GANGPACK_CHUNK_APPS
     int trace = 0;                                // GANGPACK_TRACE=1: host-side phase timing on stderr
 
@@ -790,13 +792,14 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
     if (total > 0 && !out->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_batch: executor_nodes is NULL");
 
     const size_t b64 = sizeof(int64_t) * (size_t)q, b32 = sizeof(int32_t) * (size_t)q;
-    GP_CUDA(c, c->a_dcpu.reserve(b64)); GP_CUDA(c, c->a_dmem.reserve(b64)); GP_CUDA(c, c->a_ecpu.reserve(b64));
-    GP_CUDA(c, c->a_emem.reserve(b64)); GP_CUDA(c, c->a_count.reserve(b32));
+    // the int64 columns are staged in ONE pitched device block (rows: drv cpu, drv mem, exe cpu, exe mem, drv gpu,
+    // exe gpu) so that equally spaced host columns can be moved by a single 2-D DMA per chunk
+    const size_t dpitch = (b64 + 255) & ~(size_t)255;
+    GP_CUDA(c, c->a_dcpu.reserve(dpitch * 6));
+    GP_CUDA(c, c->a_count.reserve(b32));
     GP_CUDA(c, c->a_off.reserve(sizeof(int64_t) * (size_t)(q + 1)));
     GP_CUDA(c, c->r_driver.reserve(b32));
     GP_CUDA(c, c->r_exec.reserve(sizeof(int32_t) * (size_t)(total + 1)));
-    if (a->drv_gpu) GP_CUDA(c, c->a_dgpu.reserve(b64));
-    if (a->exe_gpu) GP_CUDA(c, c->a_egpu.reserve(b64));
     if (a->group) GP_CUDA(c, c->a_group.reserve(b32));
     if (a->skip_if_no_fit) GP_CUDA(c, c->a_skip.reserve((size_t)q));
     // Mapped pinned inputs are read by gp_prep_apps straight from host memory (each value is read exactly
@@ -822,11 +825,12 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
         da.drv_gpu = (const int64_t*)mi[6]; da.exe_gpu = (const int64_t*)mi[7];
         da.group = (const int32_t*)mi[8]; da.skip_if_no_fit = (const uint8_t*)mi[9];
     } else {
-        da.drv_cpu_milli = c->a_dcpu.as<int64_t>(); da.drv_mem_bytes = c->a_dmem.as<int64_t>();
-        da.exe_cpu_milli = c->a_ecpu.as<int64_t>(); da.exe_mem_bytes = c->a_emem.as<int64_t>();
+        char* blk = c->a_dcpu.as<char>();
+        da.drv_cpu_milli = (const int64_t*)(blk + 0 * dpitch); da.drv_mem_bytes = (const int64_t*)(blk + 1 * dpitch);
+        da.exe_cpu_milli = (const int64_t*)(blk + 2 * dpitch); da.exe_mem_bytes = (const int64_t*)(blk + 3 * dpitch);
         da.exe_count = c->a_count.as<int32_t>(); da.exec_out_off = c->a_off.as<int64_t>();
-        da.drv_gpu = a->drv_gpu ? c->a_dgpu.as<int64_t>() : nullptr;
-        da.exe_gpu = a->exe_gpu ? c->a_egpu.as<int64_t>() : nullptr;
+        da.drv_gpu = a->drv_gpu ? (const int64_t*)(blk + 4 * dpitch) : nullptr;
+        da.exe_gpu = a->exe_gpu ? (const int64_t*)(blk + 5 * dpitch) : nullptr;
         da.group = a->group ? c->a_group.as<int32_t>() : nullptr;
         da.skip_if_no_fit = a->skip_if_no_fit ? c->a_skip.as<uint8_t>() : nullptr;
     }
@@ -853,17 +857,31 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
         cudaStream_t ls = n_chunks == 1 ? st : c->lane[ch % gp_ctx::kLanes];
         if (n_chunks > 1) GP_CUDA(c, cudaStreamWaitEvent(ls, c->ev_ready, 0));
         if (!in_mapped) {
-#define GP_H2D(dst, src, type, extra)                                                                           \
-        GP_CUDA(c, cudaMemcpyAsync((type*)(dst) + lo, (src) + lo, sizeof(type) * (n + (extra)), cudaMemcpyHostToDevice, ls))
-        GP_H2D(c->a_dcpu.p, a->drv_cpu_milli, int64_t, 0); GP_H2D(c->a_dmem.p, a->drv_mem_bytes, int64_t, 0);
-        GP_H2D(c->a_ecpu.p, a->exe_cpu_milli, int64_t, 0); GP_H2D(c->a_emem.p, a->exe_mem_bytes, int64_t, 0);
-        GP_H2D(c->a_count.p, a->exe_count, int32_t, 0);
-        GP_H2D(c->a_off.p, off, int64_t, 1);
-        if (a->drv_gpu) GP_H2D(c->a_dgpu.p, a->drv_gpu, int64_t, 0);
-        if (a->exe_gpu) GP_H2D(c->a_egpu.p, a->exe_gpu, int64_t, 0);
-        if (a->group) GP_H2D(c->a_group.p, a->group, int32_t, 0);
-        if (a->skip_if_no_fit) GP_H2D(c->a_skip.p, a->skip_if_no_fit, uint8_t, 0);
-#undef GP_H2D
+            // int64 columns: one 2-D DMA when the host columns are equally spaced (one pinned block laid out
+            // column after column, as the shim allocates it), else one DMA per column
+            const int64_t* cols[6] = {a->drv_cpu_milli, a->drv_mem_bytes, a->exe_cpu_milli, a->exe_mem_bytes, a->drv_gpu, a->exe_gpu};
+            int ncols = 4;
+            if (a->drv_gpu && a->exe_gpu) ncols = 6;
+            const ptrdiff_t spitch = (const char*)cols[1] - (const char*)cols[0];
+            bool spaced = spitch >= (ptrdiff_t)b64;
+            for (int k = 2; spaced && k < ncols; ++k) spaced = ((const char*)cols[k] - (const char*)cols[k - 1]) == spitch;
+            char* blk = c->a_dcpu.as<char>();
+            if (spaced) {
+                GP_CUDA(c, cudaMemcpy2DAsync(blk + sizeof(int64_t) * (size_t)lo, dpitch, cols[0] + lo, (size_t)spitch,
+                                             sizeof(int64_t) * n, (size_t)ncols, cudaMemcpyHostToDevice, ls));
+            } else {
+                for (int k = 0; k < ncols; ++k)
+                    GP_CUDA(c, cudaMemcpyAsync(blk + k * dpitch + sizeof(int64_t) * (size_t)lo, cols[k] + lo, sizeof(int64_t) * n,
+                                               cudaMemcpyHostToDevice, ls));
+            }
+            if (ncols == 4) {   // gpu columns given one at a time
+                if (a->drv_gpu) GP_CUDA(c, cudaMemcpyAsync(blk + 4 * dpitch + sizeof(int64_t) * (size_t)lo, a->drv_gpu + lo, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ls));
+                if (a->exe_gpu) GP_CUDA(c, cudaMemcpyAsync(blk + 5 * dpitch + sizeof(int64_t) * (size_t)lo, a->exe_gpu + lo, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ls));
+            }
+            GP_CUDA(c, cudaMemcpyAsync(c->a_count.as<int32_t>() + lo, a->exe_count + lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ls));
+            GP_CUDA(c, cudaMemcpyAsync(c->a_off.as<int64_t>() + lo, off + lo, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ls));
+            if (a->group) GP_CUDA(c, cudaMemcpyAsync(c->a_group.as<int32_t>() + lo, a->group + lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ls));
+            if (a->skip_if_no_fit) GP_CUDA(c, cudaMemcpyAsync(c->a_skip.as<uint8_t>() + lo, a->skip_if_no_fit + lo, n, cudaMemcpyHostToDevice, ls));
         }
         s = pack_device_range(c, &da, lo, hi, algo, mode, &dr, scratch, ls, ch);
         if (s != GP_OK) return s;

@@ -200,6 +200,12 @@ class GangPacker:
         self._pinned.append(p)
         return p.array
 
+    def pinned_columns(self, n: int, names, dtype=np.int64) -> dict:
+        """`names` equally spaced columns of n elements inside ONE pinned block (column after column): the layout
+        that lets gp_pack_batch move all int64 columns of a chunk with a single 2-D DMA."""
+        block = self.pinned((len(names), n), dtype)
+        return {name: block[i] for i, name in enumerate(names)}
+
     # ---- snapshot ----------------------------------------------------------------------------
     def set_snapshot(self, avail_cpu, avail_mem, avail_gpu, exec_order, drv_order, exec_off=None, drv_off=None):
         cpu, mem = _np(avail_cpu, np.int64), _np(avail_mem, np.int64)

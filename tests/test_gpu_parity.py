@@ -234,3 +234,43 @@ def test_error_paths(packer):
     # empty batch
     dn, en, off = packer.pack_batch({k: [] for k in base}, 0, 0)
     assert len(dn) == 0
+
+
+def test_pinned_host_paths(oracle, packer):
+    """Every host-buffer route of gp_pack_batch gives the same bits: pageable (DMA staging), mapped pinned small
+    batch (inputs read in place, results written in place), pinned equally spaced columns (one 2-D DMA per
+    chunk, pipelined chunks) and pinned scattered columns."""
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(3000)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order)
+    keys = ("drv_cpu", "drv_mem", "exe_cpu", "exe_mem", "drv_gpu", "exe_gpu")
+    for q in (1500, 70000):
+        apps = synth.make_apps(q, gpu_variant=True)
+        a = {k: apps[k] for k in keys + ("count",)}
+        ref = packer.pack_batch(a, 0, 0)                                   # pageable numpy arrays
+        if q == 1500:
+            _, want, _ = _oracle_batch(oracle, 0, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order, a)
+            assert_same_results(ref, want, "pageable")
+        total = int(ref[2][-1])
+        cols = packer.pinned_columns(q, keys)                              # one block, equally spaced
+        for k in keys:
+            cols[k][:] = a[k]
+        cols["count"] = packer.pinned(q, np.int32); cols["count"][:] = a["count"]
+        cols["off"] = packer.pinned(q + 1, np.int64); cols["off"][:] = ref[2]
+        od = packer.pinned(q, np.int32); oe = packer.pinned(max(total, 1), np.int32)
+        od[:] = -7; oe[:] = -7
+        got = packer.pack_batch(cols, 0, 0, out=(od, oe))
+        assert_same_results(got, ref, f"pinned columns q={q}")
+        scattered = {k: packer.pinned(q, np.int64) for k in keys}          # separate allocations
+        for k in keys:
+            scattered[k][:] = a[k]
+        scattered["count"] = cols["count"]; scattered["off"] = cols["off"]
+        od[:] = -7; oe[:] = -7
+        got = packer.pack_batch(scattered, 1, 0, out=(od, oe))
+        ref1 = packer.pack_batch(a, 1, 0)
+        assert_same_results(got, ref1, f"pinned scattered q={q}")
+        # drop the all-or-nothing gpu columns one at a time (NULL = 0 semantics)
+        no_gpu = {k: v for k, v in cols.items() if k not in ("drv_gpu", "exe_gpu")}
+        a0 = dict(a); a0["drv_gpu"] = np.zeros(q, np.int64); a0["exe_gpu"] = np.zeros(q, np.int64)
+        assert_same_results(packer.pack_batch(no_gpu, 0, 0, out=(od, oe)), packer.pack_batch(a0, 0, 0), f"NULL gpu columns q={q}")
