@@ -863,13 +863,15 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
             int ncols = 4;
             if (a->drv_gpu && a->exe_gpu) ncols = 6;
             const ptrdiff_t spitch = (const char*)cols[1] - (const char*)cols[0];
-            bool spaced = spitch >= (ptrdiff_t)b64;
+            bool spaced = spitch >= (ptrdiff_t)b64 && spitch <= ((ptrdiff_t)1 << 30);   // cudaMemcpy2D pitch limit (maxPitch ~2 GiB)
             for (int k = 2; spaced && k < ncols; ++k) spaced = ((const char*)cols[k] - (const char*)cols[k - 1]) == spitch;
             char* blk = c->a_dcpu.as<char>();
-            if (spaced) {
-                GP_CUDA(c, cudaMemcpy2DAsync(blk + sizeof(int64_t) * (size_t)lo, dpitch, cols[0] + lo, (size_t)spitch,
-                                             sizeof(int64_t) * n, (size_t)ncols, cudaMemcpyHostToDevice, ls));
-            } else {
+            if (spaced && cudaMemcpy2DAsync(blk + sizeof(int64_t) * (size_t)lo, dpitch, cols[0] + lo, (size_t)spitch,
+                                            sizeof(int64_t) * n, (size_t)ncols, cudaMemcpyHostToDevice, ls) != cudaSuccess) {
+                cudaGetLastError();      // not accepted as a 2-D copy after all: column by column
+                spaced = false;
+            }
+            if (!spaced) {
                 for (int k = 0; k < ncols; ++k)
                     GP_CUDA(c, cudaMemcpyAsync(blk + k * dpitch + sizeof(int64_t) * (size_t)lo, cols[k] + lo, sizeof(int64_t) * n,
                                                cudaMemcpyHostToDevice, ls));

@@ -158,7 +158,7 @@ template <int ALGO, int FIFO_MODE, bool FAST>
 __device__ __forceinline__ int32_t fifo_app(const Snapshot& s, const GroupDesc& g, const FifoView& view, const PrepApp* __restrict__ pa,
                                             int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                             uint16_t* __restrict__ cache, FifoScratch& sh, int& buf, WarpStats& st,
-                                            const GroupMin& gm) {
+                                            const GroupMin& gm, uint32_t app_seq) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int32_t nt = (int32_t)blockDim.x;
     FifoCaps<FAST> a;
@@ -172,11 +172,82 @@ __device__ __forceinline__ int32_t fifo_app(const Snapshot& s, const GroupDesc& 
     const int32_t* slot_node = s.slot_node + g.sbase;
     const bool cache_ok = k <= 0xFFFFu;
 
+    const int32_t start_e = sh.first_live_e;      // block-uniform (written before the last barrier)
+    const int32_t start_d = sh.first_live_d;
+
+    // ---- optimistic single pass (tightly-pack): the first driver candidate that FITS is the reference's
+    // answer whenever the executors fit with it (binpack.go:67-85), which is the common case.  Capacities are
+    // evaluated once, ExecutorNodes is emitted on the fly, the charges are deferred until the placement is
+    // known to be complete (the takes wait in the shared-memory cache).  If the executors do not fit with
+    // that candidate nothing has been charged and the general three-phase path below decides exactly.
+    if (ALGO == 0 && k != 0 && cache_ok) {
+        const bool refresh = (app_seq & 3u) == 0;          // dead-prefix bookkeeping every 4th application
+        int32_t j1 = -1;
+        for (int32_t j0 = start_d; j0 < g.nd && j1 < 0; j0 += nt) {
+            int32_t j = j0 + tid;
+            bool fits = false, alive = false;
+            if (j < g.nd) {
+                const int32_t ls = s.drv_slot[g.dbase + j];
+                longlong2 v = view.pair(ls);
+                const int64_t gv = a.use_gpu ? view.gpu(ls) : 0;
+                fits = !(a.d_cpu > v.x) && !(a.d_mem > v.y) && !(a.use_gpu && a.d_gpu > gv);
+                alive = !dead_for(gm.drv, v, gv, a.use_gpu);
+            }
+            if (refresh && j0 == start_d) {
+                int32_t f = block_first(sh, buf, alive, j);
+                if (tid == 0) sh.first_live_d = f >= 0 ? f : (j0 + nt < g.nd ? j0 + nt : g.nd);
+            }
+            j1 = block_first(sh, buf, fits, j);
+            if (tid == 0) st.drivers += (unsigned long long)((g.nd - j0) < nt ? (g.nd - j0) : nt);
+        }
+        if (j1 < 0) return -1;                               // no node can host the driver at all
+        const int32_t d1 = s.drv_slot[g.dbase + j1];
+        const uint32_t cd1 = d1 < ne ? a.capr(view, d1, a.d_cpu, a.d_mem, a.d_gpu) : 0u;
+        uint32_t placed = 0;
+        int32_t pos = start_e;
+        for (; placed < k && pos < ne && pos - start_e < kFifoCache; pos += nt) {
+            const int32_t i = pos + tid;
+            uint32_t c = 0;
+            if (i < ne) c = (i == d1) ? cd1 : a.capr(view, i, 0, 0, 0);
+            if (refresh && pos == start_e) {
+                bool alive = (i < ne) && !dead_for(gm.exe, view.pair(i), a.use_gpu ? view.gpu(i) : 0, a.use_gpu);
+                int32_t f = block_first(sh, buf, alive, i);
+                if (tid == 0) sh.first_live_e = f >= 0 ? f : (pos + nt < ne ? pos + nt : ne);
+            }
+            uint32_t excl, total;
+            block_excl_scan(sh, buf, c, excl, total);
+            const uint32_t room = k - placed;
+            const uint32_t T = total < room ? total : room;
+            const uint32_t take = excl >= T ? 0u : ((c < T - excl) ? c : (T - excl));
+            if (i - start_e < kFifoCache) cache[i - start_e] = (uint16_t)take;
+            if (take != 0) {
+                const int32_t node = slot_node[i];
+                for (uint32_t t = 0; t < take; ++t) out[placed + excl + t] = node;
+            }
+            placed += T;
+        }
+        if (tid == 0) st.nodes += (unsigned long long)((pos < ne ? pos : ne) - start_e);
+        if (placed == k) {
+            // commit: charge the executors' nodes and the driver's node (sparkpods.go:139-146 / exact)
+            bool driver_done = false;
+            for (int32_t p0 = start_e; p0 < pos; p0 += nt) {
+                const int32_t i = p0 + tid;
+                if (i >= ne) continue;
+                const uint32_t take = cache[i - start_e];
+                if (take != 0) view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
+                if (i == d1 && (FIFO_MODE == 2 || take == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+            }
+            driver_done = (d1 >= start_e && d1 < pos && d1 < ne);      // its owner thread handled it above
+            if (!driver_done && tid == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+            __syncthreads();   // the next application sees the charged snapshot
+            return slot_node[d1];
+        }
+        // executors do not fit with the first fitting driver (or the scan outgrew the cache): decide exactly below
+    }
+
     // ---- phase 1 (see pack_app_impl): P, m1 over a prefix of the executor order, 1024 nodes per step
     unsigned long long P = 0;
     uint32_t m1 = 0;
-    const int32_t start_e = sh.first_live_e;      // block-uniform (written before the last barrier)
-    const int32_t start_d = sh.first_live_d;
     int32_t pos = start_e;
     bool early = (k == 0);
     const unsigned long long need = (unsigned long long)k + lmax;
@@ -326,6 +397,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
     WarpStats st{0, 0};
     int buf = 0;
     bool blocked = false;
+    uint32_t app_seq = 0;
     const int32_t nt = (int32_t)blockDim.x, nw = nt >> 5;
     for (int32_t i0 = 0; i0 < n_apps; i0 += nt) {
         int32_t i = i0 + tid;
@@ -347,8 +419,8 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
                     d = -1;
                     const uint32_t fl = pa->flags;
                     if (!(fl & kAppInvalid)) {
-                        if (fl & kAppFast) d = fifo_app<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm);
-                        else d = fifo_app<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm);
+                        if (fl & kAppFast) d = fifo_app<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, app_seq++);
+                        else d = fifo_app<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, app_seq++);
                     }
                     if (d < 0 && !(fl & kAppSkipIfNoFit)) blocked = true;   // resource.go:244-253
                 }

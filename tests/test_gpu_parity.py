@@ -274,3 +274,94 @@ def test_pinned_host_paths(oracle, packer):
         no_gpu = {k: v for k, v in cols.items() if k not in ("drv_gpu", "exe_gpu")}
         a0 = dict(a); a0["drv_gpu"] = np.zeros(q, np.int64); a0["exe_gpu"] = np.zeros(q, np.int64)
         assert_same_results(packer.pack_batch(no_gpu, 0, 0, out=(od, oe)), packer.pack_batch(a0, 0, 0), f"NULL gpu columns q={q}")
+
+
+def test_pinned_host_paths_dma_route():
+    """Same test with in-place reads disabled, so the pinned buffers take the (2-D) DMA staging route."""
+    import os, subprocess, sys
+    env = dict(os.environ, GANGPACK_ZC_IN_MAX="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "test_pinned_host_paths and not dma_route"], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_large_cluster_and_big_fifo_group(oracle, packer):
+    """BASELINE configs[4] shape (50k nodes) on a sample, and a FIFO group larger than the shared-memory
+    staging area (slots beyond it are served from global memory by the same kernel)."""
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(50000)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    apps = synth.make_apps(3000)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order)
+    for algo in (0, 1):
+        _, want, _ = _oracle_batch(oracle, algo, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order, a)
+        assert_same_results(packer.pack_batch(a, algo, 0), want, f"50k nodes algo {algo}")
+    # FIFO over 14 000 nodes (> 11 776 staged slots), queue long enough to reach deep into the order
+    n = 14000
+    sub = {k: v[:n] for k, v in nodes.items() if hasattr(v, "__len__")}
+    order = synth.priority_order(sub["avail_cpu"], sub["avail_mem"])
+    big = synth.make_apps(6000, seed=77)
+    a = {k: big[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    a["exe_cpu"] = a["exe_cpu"] * 4; a["count"] = np.minimum(a["count"] * 4, 100).astype(np.int32)   # hungry apps: fill the cluster
+    young = (np.arange(6000) % 3 == 0).astype(np.uint8)
+    a["young"] = young
+    for algo in (0, 1):
+        for mode in (1, 2):
+            packer.set_snapshot(sub["avail_cpu"], sub["avail_mem"], sub["avail_gpu"], order, order)
+            blocked, want, final = _oracle_batch(oracle, algo, mode, sub["avail_cpu"], sub["avail_mem"], sub["avail_gpu"], order, order, a, young)
+            got = packer.pack_batch(a, algo, mode)
+            assert_same_results(got, want, f"big fifo algo {algo} mode {mode}")
+            fc, fm, fg = packer.get_snapshot()
+            assert np.array_equal(fc, final[0]) and np.array_equal(fm, final[1])
+
+
+def test_degenerate_groups(oracle, packer):
+    """Groups with no executor candidates / no driver candidates, and apps pointing at them."""
+    Gi = 1 << 30
+    cpu = np.array([8000, 8000, 8000, 8000], np.int64); mem = np.full(4, 16 * Gi, np.int64); gpu = np.zeros(4, np.int64)
+    # group 0: nodes 0,1 both orders; group 1: drivers only (node 2); group 2: executors only (node 3); group 3: empty
+    eoff = np.array([0, 2, 2, 3, 3], np.int32); eorder = np.array([0, 1, 3], np.int32)
+    doff = np.array([0, 2, 3, 3, 3], np.int32); dorder = np.array([0, 1, 2], np.int32)
+    packer.set_snapshot(cpu, mem, gpu, eorder, dorder, eoff, doff)
+    apps = {"drv_cpu": [1000] * 8, "drv_mem": [Gi] * 8, "drv_gpu": [0] * 8, "exe_cpu": [2000] * 8, "exe_mem": [4 * Gi] * 8,
+            "exe_gpu": [0] * 8, "count": [2, 0, 2, 0, 2, 0, 2, 0], "group": [0, 0, 1, 1, 2, 2, 3, 3]}
+    for algo in (0, 1):
+        for mode in (0, 1, 2):
+            packer.set_snapshot(cpu, mem, gpu, eorder, dorder, eoff, doff)
+            young = np.ones(8, np.uint8)
+            dn, en, off = packer.pack_batch({**apps, "young": young}, algo, mode)
+            assert dn[0] == 0 and dn[1] >= 0          # group 0 works; count 0 needs only a driver
+            assert dn[2] == -1 and dn[3] == 2         # group 1: no executor candidates: count 2 fails, count 0 fits on node 2
+            assert dn[4] == -1 and dn[5] == -1        # group 2: no driver candidates
+            assert dn[6] == -1 and dn[7] == -1        # group 3: empty
+
+
+def test_device_resident_api(oracle, packer):
+    """gp_set_snapshot_device / gp_pack_batch_device (what bench.py's `value` path and the NCCL path use)."""
+    import torch
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(2000, groups=3)
+    apps = synth.make_apps(5000, groups=3)
+    eoff, eorder = synth.group_orders(nodes)
+    dev = torch.device("cuda", 0)
+    t = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x)).to(dt).to(dev)
+    tn = [t(nodes["avail_cpu"], torch.int64), t(nodes["avail_mem"], torch.int64), t(nodes["avail_gpu"], torch.int64),
+          t(eoff, torch.int32), t(eorder, torch.int32)]
+    off = synth.exec_offsets(apps["count"])
+    ta = {k: t(apps[k], torch.int64) for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}
+    ta["count"] = t(apps["count"], torch.int32); ta["group"] = t(apps["group"], torch.int32); ta["off"] = t(off, torch.int64)
+    d_driver = torch.full((5000,), -9, dtype=torch.int32, device=dev)
+    d_exec = torch.full((int(off[-1]),), -9, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count", "group")}
+    for algo in (0, 1):
+        packer.set_snapshot_device(tn[0], tn[1], tn[2], tn[3], tn[4], tn[3], tn[4])
+        packer.pack_batch_device(ta, algo, 0, d_driver, d_exec)
+        packer.synchronize()
+        st = packer.stats()
+        assert st["nodes_scanned"] > 0 and st["pack_kernel_ns"] > 0
+        packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], eorder, eorder, eoff, eoff)
+        want = packer.pack_batch(a, algo, 0)
+        assert_same_results((d_driver.cpu().numpy(), d_exec.cpu().numpy(), off), want, f"device api algo {algo}")
