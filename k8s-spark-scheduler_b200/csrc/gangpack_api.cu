@@ -97,7 +97,10 @@ __global__ void gp_prep_apps(int32_t n_apps,
 // global counter (claim-then-broadcast, next index prefetched) so long scans do not leave a tail.
 constexpr int kPackThreads = 256;
 template <int ALGO>
-__global__ void __launch_bounds__(kPackThreads, 4) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+#ifndef GP_PACK_MIN_BLOCKS
+#define GP_PACK_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kPackThreads, GP_PACK_MIN_BLOCKS) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
                                                                     int32_t* __restrict__ driver_node,
                                                                     int32_t* __restrict__ executor_nodes,
                                                                     int2* __restrict__ scratch,
@@ -107,17 +110,24 @@ __global__ void __launch_bounds__(kPackThreads, 4) gp_pack_independent(Snapshot 
     const int lane = threadIdx.x & 31;
     uint16_t* wcache = cap_cache[threadIdx.x >> 5];
     WarpStats st{0, 0};
-    unsigned int i = 0;
-    if (lane == 0) i = atomicAdd(next_app, 1u);
+    const int snap_flags = s.meta->flags;          // per-kernel facts stay in registers
+    const GroupDesc g0 = s.groups[0];
+    // claim-then-broadcast, two applications ahead: while application i is packed, the index of i+2 is in
+    // flight and the record of i+1 is being pulled into L1
+    unsigned int i = 0, n1 = 0;
+    if (lane == 0) { i = atomicAdd(next_app, 1u); n1 = atomicAdd(next_app, 1u); }
     i = __shfl_sync(kFull, i, 0);
+    n1 = __shfl_sync(kFull, n1, 0);
     while (i < (unsigned int)n_apps) {
-        unsigned int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(next_app, 1u);     // in flight while this application is packed
+        unsigned int n2 = 0;
+        if (lane == 0) n2 = atomicAdd(next_app, 1u);
+        if (lane == 0 && n1 < (unsigned int)n_apps) asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + n1));
         const PrepApp* pa = prep + i;
         int32_t d = -1;
-        if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO, 0>(s, pa, executor_nodes, scratch, wcache, st, lane);
+        if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO, 0>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
         if (lane == 0) driver_node[i] = d;
-        i = __shfl_sync(kFull, nxt, 0);
+        i = n1;
+        n1 = __shfl_sync(kFull, n2, 0);
     }
     if (lane == 0) {
         atomicAdd(stats + 0, st.nodes);

@@ -324,12 +324,14 @@ constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 cap
 template <int ALGO, int FIFO_MODE, bool FAST, bool NOGPU>
 __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
-                                                 uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
+                                                 uint16_t* __restrict__ wcache, WarpStats& st, int lane,
+                                                 int snap_flags, const GroupDesc& g0) {
     constexpr bool MUT = FIFO_MODE != 0;
     Caps<FAST> a;
-    a.init(pa, (pa->flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
+    a.init(pa, (pa->flags & kAppUsesGpu) || (snap_flags & kSnapGpuNegative));
     const bool ug = NOGPU ? false : a.use_gpu;      // compile-time false on the hot instantiation
-    const GroupDesc g = s.groups[pa->group];
+    const int32_t grp = pa->group;
+    const GroupDesc g = grp == 0 ? g0 : s.groups[grp];   // group 0's descriptor is kept in registers by the caller
     const uint32_t k = a.k;
     const uint32_t lmax = (uint32_t)pa->lmax;
     const int32_t ne = g.ne;
@@ -484,18 +486,21 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
 template <int ALGO, int FIFO_MODE>
 __device__ __noinline__ int32_t pack_app_general(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
-                                                 uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
-    return pack_app_impl<ALGO, FIFO_MODE, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane);
+                                                 uint16_t* __restrict__ wcache, WarpStats& st, int lane, int snap_flags) {
+    const GroupDesc g0 = s.groups[0];
+    return pack_app_impl<ALGO, FIFO_MODE, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
 }
 
 // class dispatch (warp-uniform): hot path = fast class with the gpu dimension idle
 template <int ALGO, int FIFO_MODE>
 __device__ __forceinline__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, int32_t* __restrict__ executor_nodes,
-                                            int2* __restrict__ scratch, uint16_t* __restrict__ wcache, WarpStats& st, int lane) {
-    const bool gpu_idle = !(pa->flags & kAppUsesGpu) && !(s.meta->flags & kSnapGpuNegative);
-    if ((pa->flags & kAppFast) && gpu_idle)
-        return pack_app_impl<ALGO, FIFO_MODE, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane);
-    return pack_app_general<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, wcache, st, lane);
+                                            int2* __restrict__ scratch, uint16_t* __restrict__ wcache, WarpStats& st, int lane,
+                                            int snap_flags, const GroupDesc& g0) {
+    const uint32_t fl = pa->flags;
+    const bool gpu_idle = !(fl & kAppUsesGpu) && !(snap_flags & kSnapGpuNegative);
+    if ((fl & kAppFast) && gpu_idle)
+        return pack_app_impl<ALGO, FIFO_MODE, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+    return pack_app_general<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
 }
 
 }  // namespace gp
