@@ -7,13 +7,15 @@
 A "step" is one pass of the hot path over one batch of synthetic input: the 10 000-node snapshot is
 laid out on the device (gp_set_snapshot_device) and 100 000 pending applications are packed
 (tightly-pack, independent decisions against that snapshot) by prep + pack kernels.  With N>1 every
-rank packs its own 100 000 applications (weak scaling) after ONE NCCL broadcast of the node snapshot
-from rank 0, and the emitted placements are all-gathered over NVLink.
+rank packs its own 100 000 applications (weak scaling).
 
-value : decisions/s with inputs resident in HBM, CUDA events on the launch stream, L2 flushed between
-        steps (outside the per-step event pairs), max over ranks.
-e2e   : the same through the C ABI with HOST buffers: gp_set_snapshot + gp_pack_batch from pinned memory,
-        results read back to the host, wall clock around the call (it returns after the D2H).
+value : decisions/s with inputs resident in HBM (every rank: snapshot + its block of the queue), no collective
+        in the data path, CUDA events on the launch stream, L2 flushed between steps (outside the per-step
+        event pairs), max over ranks.
+e2e   : host buffers in, host results out.  N=1: gp_set_snapshot + gp_pack_batch from pinned memory through
+        the C ABI.  N>1: rank 0 uploads the snapshot, ONE NCCL broadcast distributes it, every rank packs its
+        host-resident block, the placements are all-gathered over NVLink (overlapped chunk by chunk with the
+        packing) and rank 0 copies all of them to host memory.  Wall clock, max over ranks.
 roofline / cpu_baseline: see DESIGN.md section 6.
 """
 from __future__ import annotations
@@ -245,20 +247,28 @@ def main():
     q = len(a["count"])
     total_exec = int(a["off"][-1])
     algo, mode = w["algo"], w["mode"]
+    n_nodes, n_ord = w["nodes"], len(eorder)
 
-    # ---- device-resident copies (value path) -----------------------------------------------------
     def dev_t(x, dtype):
         return torch.from_numpy(np.ascontiguousarray(x)).to(dtype).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ================= value: device-resident inputs, no collective in the data path =====================
+    # Every rank holds the snapshot and its own block of the queue in HBM; a step = snapshot layout + prep + pack.
+    # (The path shards by application with nothing to exchange while packing; distributing the snapshot and
+    #  collecting the placements are the multi-GPU analogue of H2D / D2H and are timed in `e2e` below.)
     with torch.cuda.stream(stream):
-        # the snapshot lives in ONE flat buffer so that a single NCCL broadcast moves it:
+        # the snapshot lives in ONE flat buffer so that a single NCCL broadcast can move it (e2e):
         # [cpu int64 x N | mem int64 x N | gpu int64 x N | executor/driver order int32 x len(eorder)]
-        n_nodes, n_ord = w["nodes"], len(eorder)
         snapbuf = torch.zeros(3 * n_nodes + (n_ord + 1) // 2, dtype=torch.int64, device=dev)
         tn = {"cpu": snapbuf[0:n_nodes], "mem": snapbuf[n_nodes:2 * n_nodes], "gpu": snapbuf[2 * n_nodes:3 * n_nodes],
               "eorder": snapbuf[3 * n_nodes:].view(torch.int32)[:n_ord], "eoff": dev_t(eoff, torch.int32)}
-        if rank == 0:   # only rank 0 knows the snapshot; the others receive it by NCCL broadcast every step
-            tn["cpu"].copy_(dev_t(nodes["avail_cpu"], torch.int64)); tn["mem"].copy_(dev_t(nodes["avail_mem"], torch.int64))
-            tn["gpu"].copy_(dev_t(nodes["avail_gpu"], torch.int64)); tn["eorder"].copy_(dev_t(eorder, torch.int32))
+        tn["cpu"].copy_(dev_t(nodes["avail_cpu"], torch.int64)); tn["mem"].copy_(dev_t(nodes["avail_mem"], torch.int64))
+        tn["gpu"].copy_(dev_t(nodes["avail_gpu"], torch.int64)); tn["eorder"].copy_(dev_t(eorder, torch.int32))
         ta = {k: dev_t(a[k], torch.int64 if a[k].dtype == np.int64 else (torch.uint8 if a[k].dtype == np.uint8 else torch.int32))
               for k in APP_KEYS}
         ta["off"] = dev_t(a["off"], torch.int64)
@@ -268,75 +278,19 @@ def main():
             ta.pop("young")
         d_driver = torch.empty(q, dtype=torch.int32, device=dev)
         d_exec = torch.empty(max(total_exec, 1), dtype=torch.int32, device=dev)
-        max_exec = total_exec
-        chunks = []
-        if world > 1:
-            # N>1: the batch is packed in chunks and every chunk's placements ([driver | ExecutorNodes], padded to the
-            # largest rank so the collective is regular) are all-gathered asynchronously while the next chunk is
-            # packed: the exchange overlaps the compute tile by tile.
-            n_ch = 4 if mode == 0 else 1
-            for c in range(n_ch):
-                lo, hi = (q * c) // n_ch, (q * (c + 1)) // n_ch
-                e0, e1 = int(a["off"][lo]), int(a["off"][hi])
-                t = torch.tensor([e1 - e0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); pad = max(int(t.item()), 1)
-                res = torch.empty((hi - lo) + pad, dtype=torch.int32, device=dev)
-                tc = {k: v[lo:hi] for k, v in ta.items() if k != "off"}
-                tc["off"] = (ta["off"][lo:hi + 1] - e0).contiguous()
-                chunks.append({"apps": tc, "res": res, "driver": res[:hi - lo], "exec": res[hi - lo:],
-                               "gathered": torch.empty(res.numel() * world, dtype=torch.int32, device=dev)})
-            t = torch.tensor([total_exec], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); max_exec = int(t.item())
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream.synchronize()
 
     def device_step():
-        """broadcast snapshot (N>1) -> lay it out -> prep + pack -> all-gather placements (N>1)."""
-        if world == 1:
-            packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
-            packer.pack_batch_device(ta, algo, mode, d_driver, d_exec)
-            return 5
-        dist.broadcast(snapbuf, src=0)
         packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
-        works = []
-        for ch in chunks:
-            packer.pack_batch_device(ch["apps"], algo, mode, ch["driver"], ch["exec"])
-            works.append(dist.all_gather_into_tensor(ch["gathered"], ch["res"], async_op=True))
-        for wk in works:
-            wk.wait()
-        return 3 + 2 * len(chunks)
+        packer.pack_batch_device(ta, algo, mode, d_driver, d_exec)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    launches_per_step = 3 + 2   # build_groups, build_exec_slots, build_driver_slots, prep_apps, pack
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             flush.fill_(1)
-            launches_per_step = device_step()   # build_groups, build_exec_slots, build_driver_slots + (prep, pack) per chunk
+            device_step()
         barrier()
-        # N>1: the step is a chain of ~12 small launches (NCCL broadcast, layout kernels, 4 x (prep, pack,
-        # all-gather)); issued from Python it is launch-bound, so it is captured ONCE into a CUDA graph
-        # and replayed (same work, one launch).  N=1 stays eager so the library's per-kernel event timer
-        # (roofline) keeps working.
-        graph = None
-        eager_stats = packer.stats()
-        if world > 1 and os.environ.get("BENCH_GRAPH", "1") != "0":
-            try:
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=stream):
-                    device_step()
-                for _ in range(2):
-                    graph.replay()
-                torch.cuda.synchronize()
-            except Exception as e:   # capture not possible: run eagerly
-                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-                graph = None
-                torch.cuda.synchronize()
-        flags = torch.tensor([1 if graph is not None else 0], device=dev)
-        if world > 1:
-            dist.all_reduce(flags, op=dist.ReduceOp.MIN)      # all ranks must agree (collectives inside the graph)
-            if int(flags.item()) == 0:
-                graph = None
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -347,26 +301,20 @@ def main():
         for s in range(args.steps):
             flush.fill_(s & 0xff)              # L2 flush, outside the event pair
             evs[s][0].record(stream)
-            if graph is not None:
-                graph.replay()
-            else:
-                device_step()
+            device_step()
             evs[s][1].record(stream)
-            if graph is None:
-                st = packer.stats()            # synchronises the stream; reads the pack kernel's own event time
-                pack_ns.append(st["pack_kernel_ns"]); prep_ns.append(st["prep_kernel_ns"])
+            st = packer.stats()                # synchronises the stream; reads the pack kernel's own event time
+            pack_ns.append(st["pack_kernel_ns"]); prep_ns.append(st["prep_kernel_ns"])
         barrier()
         wall1 = time.perf_counter()
         step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    if graph is not None:
-        pack_ns, prep_ns = [eager_stats["pack_kernel_ns"]], [eager_stats["prep_kernel_ns"]]
-    stats = packer.stats() if graph is None else eager_stats
+    stats = packer.stats()
     ms = float(np.mean(step_ms))
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     value = q * world / (ms * 1e-3)
 
-    # ---- end-to-end through the C ABI with host buffers -------------------------------------------
+    # ================= e2e: host buffers in, host results out ================================================
     # all-zero GPU request columns are passed as NULL (= 0), as the ABI allows; the shim knows while marshalling
     host_keys = [k for k in a if not (k in ("drv_gpu", "exe_gpu") and not a[k].any())]
     i64_cols = [k for k in ("drv_cpu", "drv_mem", "exe_cpu", "exe_mem", "drv_gpu", "exe_gpu") if k in host_keys]
@@ -379,23 +327,25 @@ def main():
         pin.pop("group", None)
     if mode == 0:
         pin.pop("young", None)
-    out_driver = packer.pinned(q, np.int32)
-    out_exec = packer.pinned(max(total_exec, 1), np.int32)
-    h2d = sum(v.nbytes for v in pin.values()) + 3 * 8 * w["nodes"] + 2 * 4 * len(eorder) + 2 * 4 * len(eoff)
-    d2h = out_driver.nbytes + 4 * total_exec
-
     # the snapshot SoA also lives in pinned host memory (what the shim fills per Predicate)
     pn = {}
     for k, v in (("cpu", nodes["avail_cpu"]), ("mem", nodes["avail_mem"]), ("gpu", nodes["avail_gpu"]),
                  ("eorder", eorder), ("eoff", eoff)):
         pn[k] = packer.pinned(len(v), v.dtype); pn[k][:] = v
-
-    def e2e_step():
-        packer.set_snapshot(pn["cpu"], pn["mem"], pn["gpu"], pn["eorder"], pn["eorder"], pn["eoff"], pn["eoff"])
-        packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
-        return int(out_driver[0])          # the host reads the result
+    snap_bytes = 3 * 8 * n_nodes + 2 * 4 * n_ord + 2 * 4 * len(eoff)
+    in_bytes = sum(v.nbytes for v in pin.values())
 
     if world == 1:
+        out_driver = packer.pinned(q, np.int32)
+        out_exec = packer.pinned(max(total_exec, 1), np.int32)
+        h2d = in_bytes + snap_bytes
+        d2h = out_driver.nbytes + 4 * total_exec
+
+        def e2e_step():
+            packer.set_snapshot(pn["cpu"], pn["mem"], pn["gpu"], pn["eorder"], pn["eorder"], pn["eoff"], pn["eoff"])
+            packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
+            return int(out_driver[0])          # the host reads the result
+
         for _ in range(max(args.warmup, 3)):
             e2e_step()
         torch.cuda.synchronize()
@@ -411,17 +361,32 @@ def main():
             e2e_launches += 3 + packer.stats()["kernel_launches"]   # snapshot layout + (prep + pack) per pipelined chunk
         e2e_ms = float(np.mean(e2e_t)) * 1e3
         e2e_value = q / (e2e_ms * 1e-3)
+        e2e_step_desc = "gp_set_snapshot + gp_pack_batch from pinned host buffers to host results"
     else:
-        # N>1: rank 0 uploads the snapshot and broadcasts it; every rank packs its host-resident shard
-        # through the C ABI; placements are all-gathered on the device and rank 0 reads all of them.
-        g_driver = torch.empty(q * world, dtype=torch.int32, device=dev)
-        d_exec_pad = torch.empty(max(max_exec, 1), dtype=torch.int32, device=dev)
-        g_exec = torch.empty(max(max_exec, 1) * world, dtype=torch.int32, device=dev)
+        # N>1: rank 0 uploads the snapshot (H2D) and ONE NCCL broadcast distributes it; every rank packs
+        # its own host-resident block of the queue (inputs read in place from mapped pinned memory) in 4 chunks, and
+        # each chunk's placements ([driver | ExecutorNodes], padded to the largest rank so the collective is regular)
+        # are all-gathered over NVLink asynchronously while the next chunk is packed; rank 0 finally copies every
+        # rank's placements to its host memory.  Timed with wall clock between barriers, max over ranks.
+        n_ch = 4 if mode == 0 else 1
         h_snap = torch.empty(snapbuf.numel(), dtype=torch.int64).pin_memory()
-        if rank == 0:
-            h_snap.copy_(snapbuf.cpu())
-        h_all_driver = torch.empty(q * world, dtype=torch.int32).pin_memory() if rank == 0 else None
-        h_all_exec = torch.empty(max(max_exec, 1) * world, dtype=torch.int32).pin_memory() if rank == 0 else None
+        h_snap.copy_(snapbuf.cpu())
+        chunks = []
+        with torch.cuda.stream(stream):
+            for c in range(n_ch):
+                lo, hi = (q * c) // n_ch, (q * (c + 1)) // n_ch
+                e0, e1 = int(a["off"][lo]), int(a["off"][hi])
+                t = torch.tensor([e1 - e0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); pad = max(int(t.item()), 1)
+                res = torch.empty((hi - lo) + pad, dtype=torch.int32, device=dev)
+                hin = {k: torch.from_numpy(v[lo:hi]) for k, v in pin.items() if k != "off"}      # mapped pinned views
+                off_c = packer.pinned(hi - lo + 1, np.int64); off_c[:] = a["off"][lo:hi + 1] - e0
+                hin["off"] = torch.from_numpy(off_c)
+                gathered = torch.empty(res.numel() * world, dtype=torch.int32, device=dev)
+                chunks.append({"apps": hin, "res": res, "driver": res[:hi - lo], "exec": res[hi - lo:], "gathered": gathered,
+                               "host": torch.empty(gathered.numel(), dtype=torch.int32).pin_memory() if rank == 0 else None})
+        stream.synchronize()
+        h2d = in_bytes + (snapbuf.numel() * 8 if rank == 0 else 0)
+        d2h = sum(ch["gathered"].numel() * 4 for ch in chunks) if rank == 0 else 0
 
         def e2e_step_multi():
             with torch.cuda.stream(stream):
@@ -429,21 +394,24 @@ def main():
                     snapbuf.copy_(h_snap, non_blocking=True)
                 dist.broadcast(snapbuf, src=0)
                 packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
+                works = []
+                for ch in chunks:
+                    packer.pack_batch_device(ch["apps"], algo, mode, ch["driver"], ch["exec"])
+                    works.append(dist.all_gather_into_tensor(ch["gathered"], ch["res"], async_op=True))
+                for ch, wk in zip(chunks, works):
+                    wk.wait()
+                    if rank == 0:
+                        ch["host"].copy_(ch["gathered"], non_blocking=True)
                 stream.synchronize()
-                packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
-                d_driver.copy_(torch.from_numpy(out_driver), non_blocking=True)   # placements back for the gather
-                d_exec_pad[:total_exec].copy_(torch.from_numpy(out_exec[:total_exec]), non_blocking=True)
-                dist.all_gather_into_tensor(g_driver, d_driver)
-                dist.all_gather_into_tensor(g_exec, d_exec_pad)
-                if rank == 0:
-                    h_all_driver.copy_(g_driver, non_blocking=True)
-                    h_all_exec.copy_(g_exec, non_blocking=True)
-                stream.synchronize()
+            return int(chunks[0]["host"][0]) if rank == 0 else 0
+
         for _ in range(max(args.warmup, 3)):
             e2e_step_multi()
         barrier()
         e2e_t = []
         for s in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(s & 0xff)
             barrier()
             t0 = time.perf_counter()
             e2e_step_multi()
@@ -453,9 +421,9 @@ def main():
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
         e2e_value = q * world / (e2e_ms * 1e-3)
-        e2e_launches = launches_per_step * args.steps
-        h2d = h2d + d2h      # the shard's placements go back up for the device all-gather
-        d2h = d2h + (4 * q * world + 4 * max_exec * world if rank == 0 else 0)
+        e2e_launches = (3 + 2 * n_ch) * args.steps
+        e2e_step_desc = ("rank 0 H2D snapshot + NCCL broadcast + layout + per-rank pack of host-resident apps (4 chunks) + "
+                         "async NCCL all-gather of placements overlapped with the next chunk + rank 0 D2H of all placements")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel (pack) ----------------------------------------------------
@@ -507,10 +475,9 @@ def main():
                        "algo": ALGO_NAME[algo], "mode": MODE_NAME[mode], "instance_groups": w["groups"],
                        "executors_total_per_gpu": total_exec,
                        "l2": "256 MiB write between steps, outside the per-step CUDA-event pair",
-                       "step": "snapshot layout + prep + pack" + (" + NCCL snapshot broadcast + placement all-gather (4 chunks, "
-                                                                   "all-gather of chunk i overlaps the pack of chunk i+1; "
-                                                                   + ("replayed from one CUDA graph)" if graph is not None else "eager launches)")
-                                                                   if world > 1 else ""),
+                       "step": "snapshot layout + prep + pack, device-resident inputs, no collective in the data path "
+                               "(every rank packs its own block of the queue against its copy of the snapshot)",
+                       "e2e_step": e2e_step_desc,
                        "fits": None},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "decisions/s", "ms_per_step": e2e_ms,
@@ -524,7 +491,7 @@ def main():
         print(json.dumps(line), flush=True)
     # Leave without tearing anything down: tensors allocated on the library's stream must not outlive that
     # stream (the caching allocator records events on it when they are freed), and destroying a process group
-    # whose communicator is referenced by a captured CUDA graph can block.  Every rank has finished its last
+    # with outstanding async work can block.  Every rank has finished its last
     # collective (the all-reduce of the e2e time) at this point.
     torch.cuda.synchronize()
     sys.stdout.flush()
