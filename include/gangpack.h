@@ -138,6 +138,31 @@ gp_status gp_set_snapshot(gp_ctx* ctx, const gp_nodes* nodes);
  * i.e. metadata after SubtractUsageIfExists, resources.go:129-135).  Any pointer may be NULL. */
 gp_status gp_get_snapshot(gp_ctx* ctx, int64_t* avail_cpu_milli, int64_t* avail_mem_bytes, int64_t* avail_gpu);
 
+/* ---- node priority order (the step before the hot path) ------------------- */
+/* NodeSorter.PotentialNodes (internal/sort/nodesorting.go:41-64) on the device: nodes in ascending
+ * (AZ priority, available memory, available CPU, name) order (:83-122), split into the driver candidates
+ * (restricted to kube-scheduler's NodeNames, :52-54) and the executor candidates (schedulable && ready,
+ * :55-57), each optionally re-sorted stably by the rank of a configured label value (:61-62,161-200).
+ * The outputs are node indices and can be passed straight to gp_nodes.drv_order / exec_order.
+ * Where the reference's comparators leave the order undefined (equal zone totals; equal (memory, cpu) with
+ * different gpu) zones are ordered by id and nodes by name. */
+typedef struct {
+    int32_t n_nodes;
+    const int64_t* avail_cpu_milli;      /* [n_nodes] */
+    const int64_t* avail_mem_bytes;      /* [n_nodes] */
+    int32_t n_zones;                     /* >= 1 */
+    const int32_t* zone_id;              /* [n_nodes] dense ids 0..n_zones-1 (ZoneLabel interned in first-seen order), or NULL (one zone) */
+    const int32_t* name_rank;            /* [n_nodes] rank of the node name in ascending byte order (unique), or NULL (= index order) */
+    const uint8_t* is_driver_candidate;  /* [n_nodes] member of ExtenderArgs.NodeNames, or NULL (= all) */
+    const uint8_t* unschedulable;        /* [n_nodes] node.Spec.Unschedulable, or NULL (= none) */
+    const uint8_t* ready;                /* [n_nodes] NodeReady == True, or NULL (= all) */
+    const int32_t* driver_label_rank;    /* [n_nodes] rank of the node's value of driver-prioritized-node-label, -1 unknown; NULL = not configured */
+    const int32_t* executor_label_rank;  /* same for executor-prioritized-node-label */
+} gp_sort_input;
+gp_status gp_potential_nodes(gp_ctx* ctx, const gp_sort_input* in,
+                             int32_t* driver_order /* [n_nodes] */, int32_t* n_driver,
+                             int32_t* executor_order /* [n_nodes] */, int32_t* n_executor);
+
 /* ---- packing ------------------------------------------------------------------------------- */
 /* One batch through the hot path with HOST buffers: H2D of the app SoA, kernels, D2H of the
  * results; returns when the results are in host memory.  FIFO modes mutate the device snapshot. */

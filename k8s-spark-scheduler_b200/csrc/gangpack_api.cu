@@ -3,6 +3,7 @@
 #include "gangpack.h"
 #include "gangpack_kernels.cuh"
 #include "gangpack_fifo.cuh"
+#include "gangpack_sort.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -286,7 +287,7 @@ struct gp_ctx {
 
     // batch staging
     DevBuf a_dcpu, a_dmem, a_dgpu, a_ecpu, a_emem, a_egpu, a_count, a_group, a_skip, a_off;
-    DevBuf prep, r_driver, r_exec, scratch, dev_misc, gmin;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
+    DevBuf prep, r_driver, r_exec, scratch, dev_misc, gmin, sortbuf;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
     void* pinned_misc = nullptr;                         // 32 B pinned mirror of dev_misc
     std::vector<int64_t> host_off;
     std::vector<int32_t> v_owner;                 // gp_set_snapshot validation scratch (no per-call allocation)
@@ -300,6 +301,8 @@ struct gp_ctx {
                                                   // 15-33 GB/s depending on the host -> in-place reads are the steadier default
     int chunk_apps = kChunkApps;                  // GANGPACK_CHUNK_APPS
     int trace = 0;                                // GANGPACK_TRACE=1: host-side phase timing on stderr
+    int pack_ctas_per_sm[2] = {0, 0};             // occupancy of gp_pack_independent<ALGO> on this device
+    bool fifo_attr_set[2] = {false, false};       // dynamic shared-memory opt-in of gp_pack_fifo_cta<ALGO,*> done on this device
 
     gp_stats last{};
 };
@@ -415,7 +418,7 @@ void gp_destroy(gp_ctx* c) {
     DevBuf* bufs[] = {&c->node_cpu, &c->node_mem, &c->node_gpu, &c->exec_off, &c->drv_off, &c->exec_order, &c->drv_order,
                       &c->pair, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
-                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin};
+                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
     if (c->one_block) cudaFreeHost(c->one_block);
@@ -635,7 +638,7 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
                         unsigned int* next_app, cudaStream_t st) {
     if (mode == GP_MODE_INDEPENDENT) {
         // persistent grid: as many CTAs as fit on the device (or fewer for small batches)
-        static int per_sm = 0;
+        int& per_sm = c->pack_ctas_per_sm[ALGO];
         if (per_sm == 0) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gp_pack_independent<ALGO>, kPackThreads, 0);
             if (per_sm < 1) per_sm = 1;
@@ -648,7 +651,7 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
                                                                        stats, next_app);
     } else {
         // FIFO: one persistent 1024-thread CTA per instance group, its slots staged in shared memory
-        static bool attr_set = false;
+        bool& attr_set = c->fifo_attr_set[ALGO];     // per device: function attributes live in the device's context
         if (!attr_set) {
             cudaFuncSetAttribute(gp_pack_fifo_cta<ALGO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFifoSmemBytes);
             cudaFuncSetAttribute(gp_pack_fifo_cta<ALGO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFifoSmemBytes);
@@ -779,8 +782,25 @@ gp_status gp_last_stats(gp_ctx* c, gp_stats* out) {
     return decode_device_error(c, err);
 }
 
+static gp_status pack_batch_impl(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out);
+
 gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out) {
     if (!c) return GP_ERR_INVALID;
+    gp_status s = pack_batch_impl(c, a, algo, mode, out);
+    if (s != GP_OK) {
+        // Whatever was enqueued before the failure may still read the caller's buffers or write its results:
+        // drain every stream of this context before handing control (and buffer ownership) back.
+        const std::string keep = c->err;
+        cudaSetDevice(c->device);
+        for (cudaStream_t l : c->lane) if (l) cudaStreamSynchronize(l);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        cudaGetLastError();
+        c->err = keep;
+    }
+    return s;
+}
+
+static gp_status pack_batch_impl(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out) {
     gp_status s = check_args(c, a, algo, mode, out, "gp_pack_batch");
     if (s != GP_OK) return s;
     const int32_t q = a->n_apps;
@@ -964,6 +984,79 @@ gp_status gp_pack_one(gp_ctx* c, gp_algo algo, int64_t drv_cpu, int64_t drv_mem,
     *has_capacity = d >= 0 ? 1 : 0;
     *driver_node = d >= 0 ? d : -1;
     if (d >= 0 && n_exec) std::memcpy(executor_nodes, exec_out, sizeof(int32_t) * n_exec);
+    return GP_OK;
+}
+
+// ---- node priority order (f1) -------------------------------------------------------------------------
+gp_status gp_potential_nodes(gp_ctx* c, const gp_sort_input* in, int32_t* driver_order, int32_t* n_driver,
+                             int32_t* executor_order, int32_t* n_executor) {
+    if (!c) return GP_ERR_INVALID;
+    if (!in || in->n_nodes < 0 || in->n_zones < 1 || !n_driver || !n_executor ||
+        (in->n_nodes > 0 && (!in->avail_cpu_milli || !in->avail_mem_bytes || !driver_order || !executor_order)))
+        return fail(c, GP_ERR_INVALID, "gp_potential_nodes: missing arrays or bad sizes");
+    const int32_t n = in->n_nodes;
+    *n_driver = 0; *n_executor = 0;
+    if (n == 0) return GP_OK;
+    // cheap host validation of the two id arrays the kernels index with
+    if (in->zone_id) for (int32_t i = 0; i < n; ++i)
+        if (in->zone_id[i] < 0 || in->zone_id[i] >= in->n_zones) return fail(c, GP_ERR_INVALID, "gp_potential_nodes: zone_id out of range");
+    if (in->name_rank) for (int32_t i = 0; i < n; ++i)
+        if (in->name_rank[i] < 0 || in->name_rank[i] >= n) return fail(c, GP_ERR_INVALID, "gp_potential_nodes: name_rank out of range");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // one scratch block: [cpu i64][mem i64][keys][tot u64 x 2Z][zone][nrank][prio Z][pos][order][drv][exe][drv2][exe2][lr_d][lr_e][counts 2][flags 3n]
+    const size_t N = (size_t)n, Z = (size_t)in->n_zones;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_cpu = take(8 * N), o_mem = take(8 * N), o_keys = take(sizeof(SortKey) * N), o_tot = take(16 * Z),
+                 o_zone = take(4 * N), o_nr = take(4 * N), o_prio = take(4 * Z), o_pos = take(4 * N), o_order = take(4 * N),
+                 o_drv = take(4 * N), o_exe = take(4 * N), o_drv2 = take(4 * N), o_exe2 = take(4 * N), o_lrd = take(4 * N),
+                 o_lre = take(4 * N), o_cnt = take(8), o_fc = take(N), o_fu = take(N), o_fr = take(N);
+    GP_CUDA(c, c->sortbuf.reserve(off));
+    char* b = c->sortbuf.as<char>();
+    auto up = [&](size_t o, const void* src, size_t bytes) { return cudaMemcpyAsync(b + o, src, bytes, cudaMemcpyHostToDevice, st); };
+    GP_CUDA(c, up(o_cpu, in->avail_cpu_milli, 8 * N));
+    GP_CUDA(c, up(o_mem, in->avail_mem_bytes, 8 * N));
+    if (in->zone_id) GP_CUDA(c, up(o_zone, in->zone_id, 4 * N)); else GP_CUDA(c, cudaMemsetAsync(b + o_zone, 0, 4 * N, st));
+    std::vector<int32_t> iota;
+    if (in->name_rank) GP_CUDA(c, up(o_nr, in->name_rank, 4 * N));
+    else { iota.resize(N); for (int32_t i = 0; i < n; ++i) iota[(size_t)i] = i; GP_CUDA(c, up(o_nr, iota.data(), 4 * N)); }
+    if (in->is_driver_candidate) GP_CUDA(c, up(o_fc, in->is_driver_candidate, N));
+    if (in->unschedulable) GP_CUDA(c, up(o_fu, in->unschedulable, N));
+    if (in->ready) GP_CUDA(c, up(o_fr, in->ready, N));
+    if (in->driver_label_rank) GP_CUDA(c, up(o_lrd, in->driver_label_rank, 4 * N));
+    if (in->executor_label_rank) GP_CUDA(c, up(o_lre, in->executor_label_rank, 4 * N));
+    GP_CUDA(c, cudaMemsetAsync(b + o_tot, 0, 16 * Z, st));
+    const int T = 256;
+    const int nb = (n + T - 1) / T;
+    gp_zone_totals<<<nb, T, 0, st>>>(n, (const long long*)(b + o_cpu), (const long long*)(b + o_mem), (const int32_t*)(b + o_zone),
+                                     (unsigned long long*)(b + o_tot));
+    gp_zone_priority<<<(in->n_zones + T - 1) / T, T, 0, st>>>(in->n_zones, (const unsigned long long*)(b + o_tot), (int32_t*)(b + o_prio));
+    gp_make_keys<<<nb, T, 0, st>>>(n, (const long long*)(b + o_cpu), (const long long*)(b + o_mem), (const int32_t*)(b + o_zone),
+                                   (const int32_t*)(b + o_prio), (const int32_t*)(b + o_nr), (SortKey*)(b + o_keys), (int32_t*)(b + o_pos));
+    gp_rank_nodes<<<dim3((unsigned)nb, (unsigned)((n + kTileJ - 1) / kTileJ)), T, 0, st>>>(n, (const SortKey*)(b + o_keys), (int32_t*)(b + o_pos));
+    gp_scatter_order<<<nb, T, 0, st>>>(n, (const int32_t*)(b + o_pos), (int32_t*)(b + o_order));
+    gp_split_candidates<<<1, 1024, 0, st>>>(n, (const int32_t*)(b + o_order), in->is_driver_candidate ? (const uint8_t*)(b + o_fc) : nullptr,
+                                           in->unschedulable ? (const uint8_t*)(b + o_fu) : nullptr, in->ready ? (const uint8_t*)(b + o_fr) : nullptr,
+                                           (int32_t*)(b + o_drv), (int32_t*)(b + o_exe), (int32_t*)(b + o_cnt));
+    const int32_t* d_drv = (const int32_t*)(b + o_drv);
+    const int32_t* d_exe = (const int32_t*)(b + o_exe);
+    if (in->driver_label_rank) {
+        gp_label_sort<<<nb, T, 0, st>>>((const int32_t*)(b + o_cnt), d_drv, (const int32_t*)(b + o_lrd), (int32_t*)(b + o_drv2));
+        d_drv = (const int32_t*)(b + o_drv2);
+    }
+    if (in->executor_label_rank) {
+        gp_label_sort<<<nb, T, 0, st>>>((const int32_t*)(b + o_cnt) + 1, d_exe, (const int32_t*)(b + o_lre), (int32_t*)(b + o_exe2));
+        d_exe = (const int32_t*)(b + o_exe2);
+    }
+    GP_CUDA(c, cudaGetLastError());
+    int32_t counts[2] = {0, 0};
+    GP_CUDA(c, cudaMemcpyAsync(counts, b + o_cnt, 8, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(driver_order, d_drv, 4 * N, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(executor_order, d_exe, 4 * N, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    *n_driver = counts[0];
+    *n_executor = counts[1];
     return GP_OK;
 }
 

@@ -15,7 +15,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("GANGPACK_LIB") or os.path.join(_PKG, "libgangpack.so")   # GANGPACK_LIB: experimental builds
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("gangpack_api.cu", "gangpack_kernels.cuh", "gangpack_fifo.cuh")] + [
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("gangpack_api.cu", "gangpack_kernels.cuh", "gangpack_fifo.cuh", "gangpack_sort.cuh")] + [
     os.path.join(_ROOT, "include", "gangpack.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -33,7 +33,8 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 # every symbol include/gangpack.h declares (tests assert the .so exports exactly these)
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
            "gp_free_pinned", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_one",
-           "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats"]
+           "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
+           "gp_potential_nodes"]
 
 
 class GangpackError(RuntimeError):
@@ -80,6 +81,13 @@ class gp_apps(C.Structure):
 
 class gp_results(C.Structure):
     _fields_ = [("driver_node", C.c_void_p), ("executor_nodes", C.c_void_p), ("executor_nodes_cap", C.c_int64)]
+
+
+class gp_sort_input(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("avail_cpu_milli", C.c_void_p), ("avail_mem_bytes", C.c_void_p),
+                ("n_zones", C.c_int32), ("zone_id", C.c_void_p), ("name_rank", C.c_void_p),
+                ("is_driver_candidate", C.c_void_p), ("unschedulable", C.c_void_p), ("ready", C.c_void_p),
+                ("driver_label_rank", C.c_void_p), ("executor_label_rank", C.c_void_p)]
 
 
 class gp_stats(C.Structure):
@@ -131,6 +139,9 @@ def load():
     L.gp_synchronize.argtypes = [C.c_void_p]
     L.gp_last_stats.restype = C.c_int
     L.gp_last_stats.argtypes = [C.c_void_p, C.POINTER(gp_stats)]
+    L.gp_potential_nodes.restype = C.c_int
+    L.gp_potential_nodes.argtypes = [C.c_void_p, C.POINTER(gp_sort_input), C.c_void_p, C.POINTER(C.c_int32),
+                                     C.c_void_p, C.POINTER(C.c_int32)]
     _lib = L
     return L
 
@@ -222,6 +233,22 @@ class GangPacker:
         cpu = np.empty(self.n_nodes, np.int64); mem = np.empty(self.n_nodes, np.int64); gpu = np.empty(self.n_nodes, np.int64)
         self._check(load().gp_get_snapshot(self._h, _p(cpu), _p(mem), _p(gpu)))
         return cpu, mem, gpu
+
+    # ---- node priority order (NodeSorter.PotentialNodes) ---------------------------------------
+    def potential_nodes(self, avail_cpu, avail_mem, zone_id=None, n_zones=1, name_rank=None, is_driver_candidate=None,
+                        unschedulable=None, ready=None, driver_label_rank=None, executor_label_rank=None):
+        """-> (driver_order, executor_order) as int32 node-index arrays."""
+        cpu, mem = _np(avail_cpu, np.int64), _np(avail_mem, np.int64)
+        n = len(cpu)
+        arrs = [_np(zone_id, np.int32), _np(name_rank, np.int32), _np(is_driver_candidate, np.uint8), _np(unschedulable, np.uint8),
+                _np(ready, np.uint8), _np(driver_label_rank, np.int32), _np(executor_label_rank, np.int32)]
+        si = gp_sort_input(n_nodes=n, avail_cpu_milli=_p(cpu), avail_mem_bytes=_p(mem), n_zones=n_zones, zone_id=_p(arrs[0]),
+                           name_rank=_p(arrs[1]), is_driver_candidate=_p(arrs[2]), unschedulable=_p(arrs[3]), ready=_p(arrs[4]),
+                           driver_label_rank=_p(arrs[5]), executor_label_rank=_p(arrs[6]))
+        d = np.empty(max(n, 1), np.int32); e = np.empty(max(n, 1), np.int32)
+        nd, ne = C.c_int32(0), C.c_int32(0)
+        self._check(load().gp_potential_nodes(self._h, C.byref(si), _p(d), C.byref(nd), _p(e), C.byref(ne)))
+        return d[:nd.value].copy(), e[:ne.value].copy()
 
     # ---- packing -----------------------------------------------------------------------------
     def pack_batch(self, apps: dict, algo: int, mode: int = MODE_INDEPENDENT, out=None):

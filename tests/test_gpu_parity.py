@@ -365,3 +365,119 @@ def test_device_resident_api(oracle, packer):
         packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], eorder, eorder, eoff, eoff)
         want = packer.pack_batch(a, algo, 0)
         assert_same_results((d_driver.cpu().numpy(), d_exec.cpu().numpy(), off), want, f"device api algo {algo}")
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fifo_full_size_conservation(packer, mode):
+    """BASELINE configs[1] in FIFO mode at full size (10k nodes x 10k apps): size-independent properties.
+    (i) conservation: initial - final availability equals the usage recomputed from the emitted placements under
+    the mode's accounting (reference: each distinct executor node one executor, driver node charged the driver
+    only if it hosts no executor -- EXT/sparkpods.go:139-146; exact: every pod); (ii) after the first blocking
+    application nothing is evaluated; (iii) every placement respected the availability at its turn (no node
+    ever goes below its running balance by more than the accounting allows)."""
+    import k8s_spark_scheduler_b200.synth as synth
+    N, Q = 10000, 10000
+    nodes = synth.make_nodes(N)
+    apps = synth.make_apps(Q)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    young = (np.arange(Q) % 7 == 0).astype(np.uint8)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    a["young"] = young
+    for algo in (0, 1):
+        packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order)
+        dn, en, off = packer.pack_batch(a, algo, mode)
+        fc, fm, _ = packer.get_snapshot()
+        fits = dn >= 0
+        # (ii) block semantics
+        nofit_old = np.nonzero((dn == -1) & (young == 0))[0]
+        if nofit_old.size:
+            b = nofit_old[0]
+            assert (dn[b + 1:] == -2).all() and (dn[:b] != -2).all()
+        else:
+            assert (dn != -2).all()
+        # (i) conservation
+        app_of = np.repeat(np.arange(Q), apps["count"])
+        keep = fits[app_of]
+        ea, eno = app_of[keep], en[:len(app_of)][keep]
+        use_cpu = np.zeros(N, np.int64); use_mem = np.zeros(N, np.int64)
+        if mode == 2:
+            np.add.at(use_cpu, eno, apps["exe_cpu"][ea]); np.add.at(use_mem, eno, apps["exe_mem"][ea])
+            np.add.at(use_cpu, dn[fits], apps["drv_cpu"][fits]); np.add.at(use_mem, dn[fits], apps["drv_mem"][fits])
+        else:
+            key = np.unique(ea.astype(np.int64) * N + eno)
+            ua, un = key // N, key % N
+            np.add.at(use_cpu, un, apps["exe_cpu"][ua]); np.add.at(use_mem, un, apps["exe_mem"][ua])
+            hosted = np.zeros(Q, bool)
+            hosted[ua[dn[ua] == un]] = True
+            drv_only = fits & ~hosted
+            np.add.at(use_cpu, dn[drv_only], apps["drv_cpu"][drv_only]); np.add.at(use_mem, dn[drv_only], apps["drv_mem"][drv_only])
+        assert np.array_equal(nodes["avail_cpu"] - use_cpu, fc), (algo, mode)
+        assert np.array_equal(nodes["avail_mem"] - use_mem, fm), (algo, mode)
+        assert fits.sum() > 1000
+
+
+def _potential_nodes_inputs(names, zones):
+    zid, seen = [], {}
+    for n in names:
+        z = zones.get(n, "default")
+        zid.append(seen.setdefault(z, len(seen)))           # dense ids in first-seen order
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    rank = np.empty(len(names), np.int32); rank[order] = np.arange(len(names))
+    return np.array(zid, np.int32), max(len(seen), 1), rank
+
+
+def test_potential_nodes_goldens(golden, packer):
+    """internal/sort/nodesorting_test.go:98-252 through the device implementation of PotentialNodes."""
+    for case in golden["sort_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        zid, nz, rank = _potential_nodes_inputs(names, case["zones"])
+        d, e = packer.potential_nodes(cpu, mem, zid, nz, rank)
+        assert [names[i] for i in d] == case["expect_priority_order"], case["id"]
+        assert [names[i] for i in e] == case["expect_priority_order"], case["id"]
+    for case in golden["label_cases"]:
+        names = case["input"]
+        n = len(names)
+        zid, nz, rank = _potential_nodes_inputs(names, {})
+        lr = np.array([case["rank"].get(nm, -1) for nm in names], np.int32)
+        d, e = packer.potential_nodes(np.ones(n, np.int64), np.arange(1, n + 1, dtype=np.int64), zid, nz, rank,
+                                      driver_label_rank=lr, executor_label_rank=lr)
+        assert [names[i] for i in d] == case["expect"] and [names[i] for i in e] == case["expect"], case["id"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_potential_nodes_random(oracle, packer, seed):
+    """Device PotentialNodes == the literal oracle on random multi-zone clusters with heavy (memory, cpu) ties,
+    candidate subsets, unschedulable / not-ready nodes and label priorities (inputs avoid the ties the reference
+    itself leaves undefined: gpu is constant)."""
+    rng = np.random.default_rng(5000 + seed)
+    for n in (1, 2, 37, 700, 5000):
+        names = ["node-%05d" % int(x) for x in rng.permutation(n * 3)[:n]]
+        cpu = rng.integers(0, 6, n) * 1000
+        mem = rng.integers(0, 5, n) * (1 << 30)
+        zones = {nm: "zone-%d" % rng.integers(0, 4) for nm in names} if seed % 2 else {}
+        unsched = (rng.random(n) < 0.1).astype(np.uint8)
+        ready = (rng.random(n) < 0.9).astype(np.uint8)
+        cand_mask = (rng.random(n) < 0.6).astype(np.uint8)
+        lr_d = rng.integers(-1, 3, n).astype(np.int32) if seed % 3 == 0 else None
+        lr_e = rng.integers(-1, 2, n).astype(np.int32) if seed % 3 != 1 else None
+        cl = oracle.Cluster(names, cpu, mem, np.zeros(n, np.int64), zone=[zones.get(nm, "default") for nm in names],
+                            unschedulable=unsched, ready=ready)
+        wd, we = cl.potential_nodes([nm for nm, m in zip(names, cand_mask) if m], lr_d, lr_e)
+        zid, nz, rank = _potential_nodes_inputs(names, zones)
+        d, e = packer.potential_nodes(cpu, mem, zid, nz, rank, cand_mask, unsched, ready, lr_d, lr_e)
+        assert [names[i] for i in d] == wd, (seed, n)
+        assert [names[i] for i in e] == we, (seed, n)
+
+
+def test_potential_nodes_feeds_the_packer(oracle, packer):
+    """sort on the device -> snapshot -> pack == the host-sorted reference flow (synthetic 10k-node cluster)."""
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(10000)
+    host_order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    d, e = packer.potential_nodes(nodes["avail_cpu"], nodes["avail_mem"])
+    assert np.array_equal(d, host_order) and np.array_equal(e, host_order)
+    apps = synth.make_apps(2000)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], e, d)
+    _, want, _ = _oracle_batch(oracle, 0, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], host_order, host_order, a)
+    assert_same_results(packer.pack_batch(a, 0, 0), want, "device-sorted orders")

@@ -34,6 +34,11 @@ snap = lambda: p.set_snapshot(pn["cpu"], pn["mem"], pn["gpu"], pn["eorder"], pn[
 print("set_snapshot pageable %8.1f us" % t(snap_pageable))
 print("pack_one            %8.1f us" % t(lambda: p.pack_one(0, (1000, 1 << 30, 0), (2000, 4 << 30, 0), 8)))
 pack = lambda: p.pack_batch(pin, w["algo"], w["mode"], out=(od, oe))
+print("potential_nodes (device sort, 10k nodes) %8.1f us" % t(lambda: p.potential_nodes(pn["cpu"], pn["mem"])))
+import k8s_spark_scheduler_b200.synth as _synth
+_n50 = _synth.make_nodes(50000)
+print("potential_nodes (device sort, 50k nodes) %8.1f us" % t(lambda: p.potential_nodes(_n50["avail_cpu"], _n50["avail_mem"]), 5))
+_t0 = time.perf_counter(); _synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"]); print("numpy lexsort 10k nodes %8.1f us" % ((time.perf_counter() - _t0) * 1e6))
 print("set_snapshot        %8.1f us" % t(snap))
 print("pack_batch (pinned) %8.1f us" % t(pack), p.stats())
 pageable = {k: np.array(v) for k, v in pin.items()}
