@@ -138,6 +138,33 @@ gp_status gp_set_snapshot(gp_ctx* ctx, const gp_nodes* nodes);
  * i.e. metadata after SubtractUsageIfExists, resources.go:129-135).  Any pointer may be NULL. */
 gp_status gp_get_snapshot(gp_ctx* ctx, int64_t* avail_cpu_milli, int64_t* avail_mem_bytes, int64_t* avail_gpu);
 
+/* ---- availability snapshot from reservations ------------------------------ */
+/* GetReservedResources (internal/extender/resourcereservations.go:258-263: UsageForNodes over the hard
+ * reservations, LIB/resources/resources.go:31-43, plus the soft reservations, internal/cache/
+ * softreservations.go:155-170) followed by NodeSchedulingMetadataForNodes (resources.go:61-100):
+ *   available[n]   = allocatable[n] - (sum of reservations on n + overhead[n])
+ *   schedulable[n] = allocatable[n] - overhead[n]
+ * One entry of res_* per reservation (hard and soft alike); res_node = index into the node table, or -1 for a
+ * reservation whose node is not in the table (ignored, like the map lookup at resources.go:72-75). */
+typedef struct {
+    int32_t n_nodes;
+    const int64_t* alloc_cpu_milli;      /* [n_nodes] node.Status.Allocatable */
+    const int64_t* alloc_mem_bytes;
+    const int64_t* alloc_gpu;            /* or NULL (= 0) */
+    const int64_t* overhead_cpu_milli;   /* [n_nodes] OverheadComputer.GetOverhead, or NULL (= 0) */
+    const int64_t* overhead_mem_bytes;   /* or NULL */
+    const int64_t* overhead_gpu;         /* or NULL */
+    int64_t n_reservations;
+    const int32_t* res_node;             /* [n_reservations] */
+    const int64_t* res_cpu_milli;
+    const int64_t* res_mem_bytes;
+    const int64_t* res_gpu;              /* or NULL (= 0) */
+} gp_usage_input;
+/* Outputs are [n_nodes] each; any of them may be NULL. */
+gp_status gp_build_availability(gp_ctx* ctx, const gp_usage_input* in,
+                                int64_t* avail_cpu_milli, int64_t* avail_mem_bytes, int64_t* avail_gpu,
+                                int64_t* sched_cpu_milli, int64_t* sched_mem_bytes, int64_t* sched_gpu);
+
 /* ---- node priority order (the step before the hot path) ------------------- */
 /* NodeSorter.PotentialNodes (internal/sort/nodesorting.go:41-64) on the device: nodes in ascending
  * (AZ priority, available memory, available CPU, name) order (:83-122), split into the driver candidates
@@ -162,6 +189,15 @@ typedef struct {
 gp_status gp_potential_nodes(gp_ctx* ctx, const gp_sort_input* in,
                              int32_t* driver_order /* [n_nodes] */, int32_t* n_driver,
                              int32_t* executor_order /* [n_nodes] */, int32_t* n_executor);
+
+/* ---- everything before the hot path in one call ---------------------------------------------- */
+/* gp_build_availability -> gp_potential_nodes -> gp_set_snapshot chained on the device: the availability computed
+ * from the reservations never returns to the host, the two priority orders are consumed where they are produced
+ * and the context ends up with a one-group snapshot ready for gp_pack_batch (what selectDriverNode does at
+ * internal/extender/resource.go:300-304 before the FIFO loop).  sort->avail_* are ignored.  Node indices in later
+ * results refer to this node table. */
+gp_status gp_prepare_cluster(gp_ctx* ctx, const gp_usage_input* usage, const gp_sort_input* sort,
+                             int32_t* n_driver /* may be NULL */, int32_t* n_executor /* may be NULL */);
 
 /* ---- packing ------------------------------------------------------------------------------- */
 /* One batch through the hot path with HOST buffers: H2D of the app SoA, kernels, D2H of the

@@ -174,7 +174,7 @@ __global__ void gp_build_exec_slots(int32_t n_exec, int32_t n_groups,
                                     longlong2* __restrict__ pair, int64_t* __restrict__ sgpu, int32_t* __restrict__ slot_node,
                                     int32_t* __restrict__ node_slot, SnapMeta* __restrict__ meta) {
     int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_exec) return;
+    if (e >= n_exec || e >= exec_off[n_groups]) return;     // n_exec may be an upper bound (device-built orders)
     int32_t g = find_group(exec_off, n_groups, e);
     int32_t slot = exec_off[g] + drv_off[g] + (e - exec_off[g]);
     int32_t node = exec_order[e];
@@ -194,7 +194,7 @@ __global__ void gp_build_driver_slots(int32_t n_drv, int32_t n_groups,
                                       longlong2* __restrict__ pair, int64_t* __restrict__ sgpu, int32_t* __restrict__ slot_node,
                                       const int32_t* __restrict__ node_slot, int32_t* __restrict__ drv_slot, SnapMeta* __restrict__ meta) {
     int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_drv) return;
+    if (j >= n_drv || j >= drv_off[n_groups]) return;       // n_drv may be an upper bound
     int32_t g = find_group(drv_off, n_groups, j);
     int32_t sbase = exec_off[g] + drv_off[g];
     int32_t ne = exec_off[g + 1] - exec_off[g];
@@ -287,7 +287,8 @@ struct gp_ctx {
 
     // batch staging
     DevBuf a_dcpu, a_dmem, a_dgpu, a_ecpu, a_emem, a_egpu, a_count, a_group, a_skip, a_off;
-    DevBuf prep, r_driver, r_exec, scratch, dev_misc, gmin, sortbuf;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
+    DevBuf prep, r_driver, r_exec, scratch, dev_misc, gmin, sortbuf, usagebuf;
+    std::vector<int32_t> iota;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
     void* pinned_misc = nullptr;                         // 32 B pinned mirror of dev_misc
     std::vector<int64_t> host_off;
     std::vector<int32_t> v_owner;                 // gp_set_snapshot validation scratch (no per-call allocation)
@@ -418,7 +419,7 @@ void gp_destroy(gp_ctx* c) {
     DevBuf* bufs[] = {&c->node_cpu, &c->node_mem, &c->node_gpu, &c->exec_off, &c->drv_off, &c->exec_order, &c->drv_order,
                       &c->pair, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
-                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf};
+                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
     if (c->one_block) cudaFreeHost(c->one_block);
@@ -987,23 +988,59 @@ gp_status gp_pack_one(gp_ctx* c, gp_algo algo, int64_t drv_cpu, int64_t drv_mem,
     return GP_OK;
 }
 
-// ---- node priority order (f1) -------------------------------------------------------------------------
-gp_status gp_potential_nodes(gp_ctx* c, const gp_sort_input* in, int32_t* driver_order, int32_t* n_driver,
-                             int32_t* executor_order, int32_t* n_executor) {
-    if (!c) return GP_ERR_INVALID;
-    if (!in || in->n_nodes < 0 || in->n_zones < 1 || !n_driver || !n_executor ||
-        (in->n_nodes > 0 && (!in->avail_cpu_milli || !in->avail_mem_bytes || !driver_order || !executor_order)))
-        return fail(c, GP_ERR_INVALID, "gp_potential_nodes: missing arrays or bad sizes");
+// ---- node priority order (f1) and availability snapshot (f2): device stages + the entries built on them ----
+}  // extern "C"
+
+// f2 stage: uploads the inputs, leaves avail[3][N] / sched[3][N] on the device (usagebuf).
+static gp_status stage_availability(gp_ctx* c, const gp_usage_input* in, cudaStream_t st, long long** d_avail, long long** d_sched) {
     const int32_t n = in->n_nodes;
-    *n_driver = 0; *n_executor = 0;
-    if (n == 0) return GP_OK;
+    const size_t N = (size_t)n, R = (size_t)in->n_reservations;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_alloc = take(24 * N), o_over = take(24 * N), o_usage = take(24 * N), o_avail = take(24 * N), o_sched = take(24 * N),
+                 o_rn = take(4 * R), o_rc = take(8 * R), o_rm = take(8 * R), o_rg = take(8 * R);
+    GP_CUDA(c, c->usagebuf.reserve(off));
+    char* b = c->usagebuf.as<char>();
+    auto up = [&](size_t o, const void* src, size_t bytes) { return cudaMemcpyAsync(b + o, src, bytes, cudaMemcpyHostToDevice, st); };
+    GP_CUDA(c, up(o_alloc, in->alloc_cpu_milli, 8 * N));
+    GP_CUDA(c, up(o_alloc + 8 * N, in->alloc_mem_bytes, 8 * N));
+    if (in->alloc_gpu) GP_CUDA(c, up(o_alloc + 16 * N, in->alloc_gpu, 8 * N));
+    if (in->overhead_cpu_milli) GP_CUDA(c, up(o_over, in->overhead_cpu_milli, 8 * N));
+    if (in->overhead_mem_bytes) GP_CUDA(c, up(o_over + 8 * N, in->overhead_mem_bytes, 8 * N));
+    if (in->overhead_gpu) GP_CUDA(c, up(o_over + 16 * N, in->overhead_gpu, 8 * N));
+    GP_CUDA(c, cudaMemsetAsync(b + o_usage, 0, 24 * N, st));
+    const int T = 256;
+    if (R) {
+        GP_CUDA(c, up(o_rn, in->res_node, 4 * R));
+        GP_CUDA(c, up(o_rc, in->res_cpu_milli, 8 * R));
+        GP_CUDA(c, up(o_rm, in->res_mem_bytes, 8 * R));
+        if (in->res_gpu) GP_CUDA(c, up(o_rg, in->res_gpu, 8 * R));
+        gp_usage_scatter<<<(unsigned)((R + T - 1) / T), T, 0, st>>>((long long)R, (const int32_t*)(b + o_rn), (const long long*)(b + o_rc),
+                                                                   (const long long*)(b + o_rm), in->res_gpu ? (const long long*)(b + o_rg) : nullptr,
+                                                                   n, (unsigned long long*)(b + o_usage));
+    }
+    const long long* al = (const long long*)(b + o_alloc);
+    const long long* ov = (const long long*)(b + o_over);
+    gp_availability<<<(n + T - 1) / T, T, 0, st>>>(n, al, al + N, in->alloc_gpu ? al + 2 * N : nullptr, in->overhead_cpu_milli ? ov : nullptr,
+                                                   in->overhead_mem_bytes ? ov + N : nullptr, in->overhead_gpu ? ov + 2 * N : nullptr,
+                                                   (const unsigned long long*)(b + o_usage), (long long*)(b + o_avail), (long long*)(b + o_sched));
+    GP_CUDA(c, cudaGetLastError());
+    *d_avail = (long long*)(b + o_avail);
+    *d_sched = (long long*)(b + o_sched);
+    return GP_OK;
+}
+
+struct SortStage { const int32_t* drv; const int32_t* exe; const int32_t* counts; };
+
+// f1 stage: d_cpu / d_mem are device arrays (NULL: uploaded from `in`); leaves the two orders and their lengths on the device.
+static gp_status stage_sort(gp_ctx* c, const gp_sort_input* in, const long long* d_cpu, const long long* d_mem, cudaStream_t st,
+                            SortStage* out) {
+    const int32_t n = in->n_nodes;
     // cheap host validation of the two id arrays the kernels index with
     if (in->zone_id) for (int32_t i = 0; i < n; ++i)
         if (in->zone_id[i] < 0 || in->zone_id[i] >= in->n_zones) return fail(c, GP_ERR_INVALID, "gp_potential_nodes: zone_id out of range");
     if (in->name_rank) for (int32_t i = 0; i < n; ++i)
         if (in->name_rank[i] < 0 || in->name_rank[i] >= n) return fail(c, GP_ERR_INVALID, "gp_potential_nodes: name_rank out of range");
-    GP_CUDA(c, cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
     // one scratch block: [cpu i64][mem i64][keys][tot u64 x 2Z][zone][nrank][prio Z][pos][order][drv][exe][drv2][exe2][lr_d][lr_e][counts 2][flags 3n]
     const size_t N = (size_t)n, Z = (size_t)in->n_zones;
     size_t off = 0;
@@ -1015,12 +1052,11 @@ gp_status gp_potential_nodes(gp_ctx* c, const gp_sort_input* in, int32_t* driver
     GP_CUDA(c, c->sortbuf.reserve(off));
     char* b = c->sortbuf.as<char>();
     auto up = [&](size_t o, const void* src, size_t bytes) { return cudaMemcpyAsync(b + o, src, bytes, cudaMemcpyHostToDevice, st); };
-    GP_CUDA(c, up(o_cpu, in->avail_cpu_milli, 8 * N));
-    GP_CUDA(c, up(o_mem, in->avail_mem_bytes, 8 * N));
+    if (!d_cpu) { GP_CUDA(c, up(o_cpu, in->avail_cpu_milli, 8 * N)); d_cpu = (const long long*)(b + o_cpu); }
+    if (!d_mem) { GP_CUDA(c, up(o_mem, in->avail_mem_bytes, 8 * N)); d_mem = (const long long*)(b + o_mem); }
     if (in->zone_id) GP_CUDA(c, up(o_zone, in->zone_id, 4 * N)); else GP_CUDA(c, cudaMemsetAsync(b + o_zone, 0, 4 * N, st));
-    std::vector<int32_t> iota;
     if (in->name_rank) GP_CUDA(c, up(o_nr, in->name_rank, 4 * N));
-    else { iota.resize(N); for (int32_t i = 0; i < n; ++i) iota[(size_t)i] = i; GP_CUDA(c, up(o_nr, iota.data(), 4 * N)); }
+    else { c->iota.resize(N); for (int32_t i = 0; i < n; ++i) c->iota[(size_t)i] = i; GP_CUDA(c, up(o_nr, c->iota.data(), 4 * N)); }
     if (in->is_driver_candidate) GP_CUDA(c, up(o_fc, in->is_driver_candidate, N));
     if (in->unschedulable) GP_CUDA(c, up(o_fu, in->unschedulable, N));
     if (in->ready) GP_CUDA(c, up(o_fr, in->ready, N));
@@ -1029,34 +1065,124 @@ gp_status gp_potential_nodes(gp_ctx* c, const gp_sort_input* in, int32_t* driver
     GP_CUDA(c, cudaMemsetAsync(b + o_tot, 0, 16 * Z, st));
     const int T = 256;
     const int nb = (n + T - 1) / T;
-    gp_zone_totals<<<nb, T, 0, st>>>(n, (const long long*)(b + o_cpu), (const long long*)(b + o_mem), (const int32_t*)(b + o_zone),
-                                     (unsigned long long*)(b + o_tot));
+    gp_zone_totals<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (unsigned long long*)(b + o_tot));
     gp_zone_priority<<<(in->n_zones + T - 1) / T, T, 0, st>>>(in->n_zones, (const unsigned long long*)(b + o_tot), (int32_t*)(b + o_prio));
-    gp_make_keys<<<nb, T, 0, st>>>(n, (const long long*)(b + o_cpu), (const long long*)(b + o_mem), (const int32_t*)(b + o_zone),
-                                   (const int32_t*)(b + o_prio), (const int32_t*)(b + o_nr), (SortKey*)(b + o_keys), (int32_t*)(b + o_pos));
+    gp_make_keys<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (const int32_t*)(b + o_prio), (const int32_t*)(b + o_nr),
+                                   (SortKey*)(b + o_keys), (int32_t*)(b + o_pos));
     gp_rank_nodes<<<dim3((unsigned)nb, (unsigned)((n + kTileJ - 1) / kTileJ)), T, 0, st>>>(n, (const SortKey*)(b + o_keys), (int32_t*)(b + o_pos));
     gp_scatter_order<<<nb, T, 0, st>>>(n, (const int32_t*)(b + o_pos), (int32_t*)(b + o_order));
     gp_split_candidates<<<1, 1024, 0, st>>>(n, (const int32_t*)(b + o_order), in->is_driver_candidate ? (const uint8_t*)(b + o_fc) : nullptr,
                                            in->unschedulable ? (const uint8_t*)(b + o_fu) : nullptr, in->ready ? (const uint8_t*)(b + o_fr) : nullptr,
                                            (int32_t*)(b + o_drv), (int32_t*)(b + o_exe), (int32_t*)(b + o_cnt));
-    const int32_t* d_drv = (const int32_t*)(b + o_drv);
-    const int32_t* d_exe = (const int32_t*)(b + o_exe);
+    out->drv = (const int32_t*)(b + o_drv);
+    out->exe = (const int32_t*)(b + o_exe);
+    out->counts = (const int32_t*)(b + o_cnt);
     if (in->driver_label_rank) {
-        gp_label_sort<<<nb, T, 0, st>>>((const int32_t*)(b + o_cnt), d_drv, (const int32_t*)(b + o_lrd), (int32_t*)(b + o_drv2));
-        d_drv = (const int32_t*)(b + o_drv2);
+        gp_label_sort<<<nb, T, 0, st>>>(out->counts, out->drv, (const int32_t*)(b + o_lrd), (int32_t*)(b + o_drv2));
+        out->drv = (const int32_t*)(b + o_drv2);
     }
     if (in->executor_label_rank) {
-        gp_label_sort<<<nb, T, 0, st>>>((const int32_t*)(b + o_cnt) + 1, d_exe, (const int32_t*)(b + o_lre), (int32_t*)(b + o_exe2));
-        d_exe = (const int32_t*)(b + o_exe2);
+        gp_label_sort<<<nb, T, 0, st>>>(out->counts + 1, out->exe, (const int32_t*)(b + o_lre), (int32_t*)(b + o_exe2));
+        out->exe = (const int32_t*)(b + o_exe2);
     }
     GP_CUDA(c, cudaGetLastError());
+    return GP_OK;
+}
+
+// offsets of the single instance group from the device-resident candidate counts
+__global__ void gp_offsets_from_counts(const int32_t* __restrict__ counts, int32_t* __restrict__ exec_off, int32_t* __restrict__ drv_off) {
+    if (threadIdx.x == 0) { drv_off[0] = 0; drv_off[1] = counts[0]; exec_off[0] = 0; exec_off[1] = counts[1]; }
+}
+
+extern "C" {
+
+gp_status gp_potential_nodes(gp_ctx* c, const gp_sort_input* in, int32_t* driver_order, int32_t* n_driver,
+                             int32_t* executor_order, int32_t* n_executor) {
+    if (!c) return GP_ERR_INVALID;
+    if (!in || in->n_nodes < 0 || in->n_zones < 1 || !n_driver || !n_executor ||
+        (in->n_nodes > 0 && (!in->avail_cpu_milli || !in->avail_mem_bytes || !driver_order || !executor_order)))
+        return fail(c, GP_ERR_INVALID, "gp_potential_nodes: missing arrays or bad sizes");
+    const int32_t n = in->n_nodes;
+    *n_driver = 0; *n_executor = 0;
+    if (n == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    SortStage so{};
+    gp_status s = stage_sort(c, in, nullptr, nullptr, st, &so);
+    if (s != GP_OK) return s;
     int32_t counts[2] = {0, 0};
-    GP_CUDA(c, cudaMemcpyAsync(counts, b + o_cnt, 8, cudaMemcpyDeviceToHost, st));
-    GP_CUDA(c, cudaMemcpyAsync(driver_order, d_drv, 4 * N, cudaMemcpyDeviceToHost, st));
-    GP_CUDA(c, cudaMemcpyAsync(executor_order, d_exe, 4 * N, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(counts, so.counts, 8, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(driver_order, so.drv, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(executor_order, so.exe, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaStreamSynchronize(st));
     *n_driver = counts[0];
     *n_executor = counts[1];
+    return GP_OK;
+}
+
+gp_status gp_build_availability(gp_ctx* c, const gp_usage_input* in, int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu,
+                                int64_t* sched_cpu, int64_t* sched_mem, int64_t* sched_gpu) {
+    if (!c) return GP_ERR_INVALID;
+    if (!in || in->n_nodes < 0 || in->n_reservations < 0 || (in->n_nodes > 0 && (!in->alloc_cpu_milli || !in->alloc_mem_bytes)) ||
+        (in->n_reservations > 0 && (!in->res_node || !in->res_cpu_milli || !in->res_mem_bytes)))
+        return fail(c, GP_ERR_INVALID, "gp_build_availability: missing arrays or bad sizes");
+    const int32_t n = in->n_nodes;
+    if (n == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    long long *d_avail = nullptr, *d_sched = nullptr;
+    gp_status s = stage_availability(c, in, st, &d_avail, &d_sched);
+    if (s != GP_OK) return s;
+    const size_t N = (size_t)n;
+    int64_t* outs[6] = {avail_cpu, avail_mem, avail_gpu, sched_cpu, sched_mem, sched_gpu};
+    for (int k = 0; k < 6; ++k)
+        if (outs[k]) GP_CUDA(c, cudaMemcpyAsync(outs[k], (k < 3 ? d_avail : d_sched) + N * (size_t)(k % 3), 8 * N, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    return GP_OK;
+}
+
+// reservations -> availability -> priority orders -> slot layout, without leaving the device
+gp_status gp_prepare_cluster(gp_ctx* c, const gp_usage_input* usage, const gp_sort_input* sort, int32_t* n_driver, int32_t* n_executor) {
+    if (!c) return GP_ERR_INVALID;
+    if (!usage || !sort || usage->n_nodes != sort->n_nodes || usage->n_nodes < 0 || sort->n_zones < 1 || usage->n_reservations < 0 ||
+        (usage->n_nodes > 0 && (!usage->alloc_cpu_milli || !usage->alloc_mem_bytes)) ||
+        (usage->n_reservations > 0 && (!usage->res_node || !usage->res_cpu_milli || !usage->res_mem_bytes)))
+        return fail(c, GP_ERR_INVALID, "gp_prepare_cluster: missing arrays or mismatched sizes");
+    const int32_t n = usage->n_nodes;
+    if (n_driver) *n_driver = 0;
+    if (n_executor) *n_executor = 0;
+    if (n == 0) return fail(c, GP_ERR_INVALID, "gp_prepare_cluster: empty node table");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    long long *d_avail = nullptr, *d_sched = nullptr;
+    gp_status s = stage_availability(c, usage, st, &d_avail, &d_sched);
+    if (s != GP_OK) return s;
+    const size_t N = (size_t)n;
+    SortStage so{};
+    s = stage_sort(c, sort, d_avail, d_avail + N, st, &so);
+    if (s != GP_OK) return s;
+    // node-table copy (gp_get_snapshot) and the one-group offsets, then the usual slot layout with N as the upper bound
+    const size_t nb = sizeof(int64_t) * (N + 1);
+    GP_CUDA(c, c->node_cpu.reserve(nb)); GP_CUDA(c, c->node_mem.reserve(nb)); GP_CUDA(c, c->node_gpu.reserve(nb));
+    GP_CUDA(c, cudaMemcpyAsync(c->node_cpu.p, d_avail, 8 * N, cudaMemcpyDeviceToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(c->node_mem.p, d_avail + N, 8 * N, cudaMemcpyDeviceToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(c->node_gpu.p, d_avail + 2 * N, 8 * N, cudaMemcpyDeviceToDevice, st));
+    GP_CUDA(c, c->exec_off.reserve(8)); GP_CUDA(c, c->drv_off.reserve(8));
+    gp_offsets_from_counts<<<1, 32, 0, st>>>(so.counts, c->exec_off.as<int32_t>(), c->drv_off.as<int32_t>());
+    gp_nodes dn{};
+    dn.n_nodes = n;
+    dn.avail_cpu_milli = c->node_cpu.as<int64_t>(); dn.avail_mem_bytes = c->node_mem.as<int64_t>(); dn.avail_gpu = c->node_gpu.as<int64_t>();
+    dn.n_groups = 1;
+    dn.exec_off = c->exec_off.as<int32_t>(); dn.exec_order = so.exe;
+    dn.drv_off = c->drv_off.as<int32_t>(); dn.drv_order = so.drv;
+    s = build_snapshot_device(c, &dn, n, n, st);      // n is the upper bound of both order lengths
+    if (s != GP_OK) return s;
+    int32_t counts[2] = {0, 0};
+    GP_CUDA(c, cudaMemcpyAsync(counts, so.counts, 8, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    c->n_drv = counts[0]; c->n_exec = counts[1];
+    if (n_driver) *n_driver = counts[0];
+    if (n_executor) *n_executor = counts[1];
     return GP_OK;
 }
 

@@ -152,4 +152,40 @@ __global__ void __launch_bounds__(256) gp_label_sort(const int32_t* __restrict__
     out[cnt] = node;
 }
 
+// ---- the availability snapshot from reservations -------------------------------------------
+// usage[node] = sum of the resources of every (hard or soft) reservation on that node: UsageForNodes
+// (LIB/resources/resources.go:31-43) + UsedSoftReservationResources (internal/cache/softreservations.go:155-170),
+// summed as in GetReservedResources (EXT/resourcereservations.go:258-263).  A segmented reduction over
+// (reservation -> node) pairs: thread per reservation, 64-bit atomics (integer adds commute: exact).
+__global__ void gp_usage_scatter(long long n_res, const int32_t* __restrict__ res_node, const long long* __restrict__ res_cpu,
+                                 const long long* __restrict__ res_mem, const long long* __restrict__ res_gpu, int32_t n_nodes,
+                                 unsigned long long* __restrict__ usage /* [3][n_nodes] */) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= n_res) return;
+    const int32_t node = res_node[r];
+    if (node < 0 || node >= n_nodes) return;            // reservation on a node that is not in the list: ignored (:67-75)
+    atomicAdd(usage + node, (unsigned long long)res_cpu[r]);
+    atomicAdd(usage + n_nodes + node, (unsigned long long)res_mem[r]);
+    if (res_gpu) atomicAdd(usage + 2 * (size_t)n_nodes + node, (unsigned long long)res_gpu[r]);
+}
+
+// NodeSchedulingMetadataForNodes (resources.go:61-100): available = allocatable - (usage + overhead),
+// schedulable = allocatable - overhead.
+__global__ void gp_availability(int32_t n, const long long* __restrict__ alloc_cpu, const long long* __restrict__ alloc_mem,
+                                const long long* __restrict__ alloc_gpu, const long long* __restrict__ over_cpu,
+                                const long long* __restrict__ over_mem, const long long* __restrict__ over_gpu,
+                                const unsigned long long* __restrict__ usage, long long* __restrict__ avail /* [3][n] */,
+                                long long* __restrict__ sched /* [3][n] */) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long a[3] = {alloc_cpu[i], alloc_mem[i], alloc_gpu ? alloc_gpu[i] : 0};
+    const long long o[3] = {over_cpu ? over_cpu[i] : 0, over_mem ? over_mem[i] : 0, over_gpu ? over_gpu[i] : 0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const long long u = (long long)usage[(size_t)d * n + i];
+        avail[(size_t)d * n + i] = a[d] - (u + o[d]);
+        sched[(size_t)d * n + i] = a[d] - o[d];
+    }
+}
+
 }  // namespace gp

@@ -34,7 +34,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
            "gp_free_pinned", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_one",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
-           "gp_potential_nodes"]
+           "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster"]
 
 
 class GangpackError(RuntimeError):
@@ -90,6 +90,13 @@ class gp_sort_input(C.Structure):
                 ("driver_label_rank", C.c_void_p), ("executor_label_rank", C.c_void_p)]
 
 
+class gp_usage_input(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("alloc_cpu_milli", C.c_void_p), ("alloc_mem_bytes", C.c_void_p), ("alloc_gpu", C.c_void_p),
+                ("overhead_cpu_milli", C.c_void_p), ("overhead_mem_bytes", C.c_void_p), ("overhead_gpu", C.c_void_p),
+                ("n_reservations", C.c_int64), ("res_node", C.c_void_p), ("res_cpu_milli", C.c_void_p),
+                ("res_mem_bytes", C.c_void_p), ("res_gpu", C.c_void_p)]
+
+
 class gp_stats(C.Structure):
     _fields_ = [("nodes_scanned", C.c_int64), ("drivers_tried", C.c_int64), ("kernel_launches", C.c_int64),
                 ("pack_kernel_ns", C.c_int64), ("prep_kernel_ns", C.c_int64), ("reserved", C.c_int64 * 3)]
@@ -139,6 +146,11 @@ def load():
     L.gp_synchronize.argtypes = [C.c_void_p]
     L.gp_last_stats.restype = C.c_int
     L.gp_last_stats.argtypes = [C.c_void_p, C.POINTER(gp_stats)]
+    L.gp_build_availability.restype = C.c_int
+    L.gp_build_availability.argtypes = [C.c_void_p, C.POINTER(gp_usage_input)] + [C.c_void_p] * 6
+    L.gp_prepare_cluster.restype = C.c_int
+    L.gp_prepare_cluster.argtypes = [C.c_void_p, C.POINTER(gp_usage_input), C.POINTER(gp_sort_input), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32)]
     L.gp_potential_nodes.restype = C.c_int
     L.gp_potential_nodes.argtypes = [C.c_void_p, C.POINTER(gp_sort_input), C.c_void_p, C.POINTER(C.c_int32),
                                      C.c_void_p, C.POINTER(C.c_int32)]
@@ -233,6 +245,42 @@ class GangPacker:
         cpu = np.empty(self.n_nodes, np.int64); mem = np.empty(self.n_nodes, np.int64); gpu = np.empty(self.n_nodes, np.int64)
         self._check(load().gp_get_snapshot(self._h, _p(cpu), _p(mem), _p(gpu)))
         return cpu, mem, gpu
+
+    # ---- availability snapshot from reservations (NodeSchedulingMetadataForNodes) ----------------
+    def build_availability(self, alloc, overhead, res_node, res):
+        """alloc / overhead / res: (cpu, mem, gpu) triples (overhead may be None) -> (avail triple, sched triple)."""
+        al = [_np(x, np.int64) for x in alloc]
+        ov = [_np(x, np.int64) for x in overhead] if overhead is not None else [None] * 3
+        rn = _np(res_node, np.int32)
+        rs = [_np(x, np.int64) for x in res]
+        n = len(al[0])
+        ui = gp_usage_input(n_nodes=n, alloc_cpu_milli=_p(al[0]), alloc_mem_bytes=_p(al[1]), alloc_gpu=_p(al[2]),
+                            overhead_cpu_milli=_p(ov[0]), overhead_mem_bytes=_p(ov[1]), overhead_gpu=_p(ov[2]),
+                            n_reservations=len(rn), res_node=_p(rn), res_cpu_milli=_p(rs[0]), res_mem_bytes=_p(rs[1]), res_gpu=_p(rs[2]))
+        outs = [np.empty(max(n, 1), np.int64) for _ in range(6)]
+        self._check(load().gp_build_availability(self._h, C.byref(ui), *[_p(o) for o in outs]))
+        return [o[:n] for o in outs[:3]], [o[:n] for o in outs[3:]]
+
+    def prepare_cluster(self, alloc, overhead, res_node, res, zone_id=None, n_zones=1, name_rank=None, is_driver_candidate=None,
+                        unschedulable=None, ready=None, driver_label_rank=None, executor_label_rank=None):
+        """reservations -> availability -> priority orders -> snapshot, chained on the device.  -> (n_driver, n_executor)."""
+        al = [_np(x, np.int64) for x in alloc]
+        ov = [_np(x, np.int64) for x in overhead] if overhead is not None else [None] * 3
+        rn = _np(res_node, np.int32)
+        rs = [_np(x, np.int64) for x in res]
+        n = len(al[0])
+        ui = gp_usage_input(n_nodes=n, alloc_cpu_milli=_p(al[0]), alloc_mem_bytes=_p(al[1]), alloc_gpu=_p(al[2]),
+                            overhead_cpu_milli=_p(ov[0]), overhead_mem_bytes=_p(ov[1]), overhead_gpu=_p(ov[2]),
+                            n_reservations=len(rn), res_node=_p(rn), res_cpu_milli=_p(rs[0]), res_mem_bytes=_p(rs[1]), res_gpu=_p(rs[2]))
+        arrs = [_np(zone_id, np.int32), _np(name_rank, np.int32), _np(is_driver_candidate, np.uint8), _np(unschedulable, np.uint8),
+                _np(ready, np.uint8), _np(driver_label_rank, np.int32), _np(executor_label_rank, np.int32)]
+        si = gp_sort_input(n_nodes=n, avail_cpu_milli=None, avail_mem_bytes=None, n_zones=n_zones, zone_id=_p(arrs[0]),
+                           name_rank=_p(arrs[1]), is_driver_candidate=_p(arrs[2]), unschedulable=_p(arrs[3]), ready=_p(arrs[4]),
+                           driver_label_rank=_p(arrs[5]), executor_label_rank=_p(arrs[6]))
+        nd, ne = C.c_int32(0), C.c_int32(0)
+        self._check(load().gp_prepare_cluster(self._h, C.byref(ui), C.byref(si), C.byref(nd), C.byref(ne)))
+        self.n_nodes = n
+        return nd.value, ne.value
 
     # ---- node priority order (NodeSorter.PotentialNodes) ---------------------------------------
     def potential_nodes(self, avail_cpu, avail_mem, zone_id=None, n_zones=1, name_rank=None, is_driver_candidate=None,

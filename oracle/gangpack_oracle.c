@@ -588,6 +588,42 @@ int32_t orc_fifo(orc_cluster* c, int algo, int mode, int32_t n_apps,
     return blocked;
 }
 
+/* ------------------------------------------------------------------ snapshot build ---- */
+/* UsageForNodes (LIB/resources/resources.go:31-43) over hard reservations + UsedSoftReservationResources
+ * (internal/cache/softreservations.go:155-170), summed like GetReservedResources
+ * (EXT/resourcereservations.go:258-263); then NodeSchedulingMetadataForNodes (resources.go:61-100):
+ * available = allocatable - (usage + overhead), schedulable = allocatable - overhead, per listed node. */
+void orc_node_scheduling_metadata(int32_t n_nodes, const char* const* names,
+                                  const int64_t* alloc_cpu, const int64_t* alloc_mem, const int64_t* alloc_gpu,
+                                  const int64_t* over_cpu, const int64_t* over_mem, const int64_t* over_gpu,
+                                  int64_t n_res, const char* const* res_node_name,
+                                  const int64_t* res_cpu, const int64_t* res_mem, const int64_t* res_gpu,
+                                  int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu,
+                                  int64_t* sched_cpu, int64_t* sched_mem, int64_t* sched_gpu) {
+    static const orc_res zero = {0, 0, 0};
+    resmap usage;                                              /* resources.go:32 */
+    resmap_init(&usage, n_nodes);
+    for (int64_t r = 0; r < n_res; ++r) {                      /* :33-41 (and softreservations.go:160-168) */
+        orc_res* u = resmap_get(&usage, res_node_name[r]);
+        if (u == NULL) u = resmap_put(&usage, res_node_name[r], &zero);
+        orc_res add = {res_cpu[r], res_mem[r], res_gpu ? res_gpu[r] : 0};
+        res_add(u, &add);                                      /* AddFromReservation, :186-190 */
+    }
+    for (int32_t i = 0; i < n_nodes; ++i) {                    /* resources.go:67 */
+        orc_res overhead = {over_cpu ? over_cpu[i] : 0, over_mem ? over_mem[i] : 0, over_gpu ? over_gpu[i] : 0};   /* :68-71 */
+        orc_res* u = resmap_get(&usage, names[i]);             /* :72-75 */
+        orc_res cur = u ? *u : zero;
+        res_add(&cur, &overhead);                              /* :76 */
+        orc_res alloc = {alloc_cpu[i], alloc_mem[i], alloc_gpu ? alloc_gpu[i] : 0};
+        orc_res a = alloc, sc = alloc;
+        res_sub(&a, &cur);                                     /* :89 subtractFromResourceList(allocatable, usage+overhead) */
+        res_sub(&sc, &overhead);                               /* :90 */
+        avail_cpu[i] = a.cpu; avail_mem[i] = a.mem; avail_gpu[i] = a.gpu;
+        if (sched_cpu) { sched_cpu[i] = sc.cpu; sched_mem[i] = sc.mem; sched_gpu[i] = sc.gpu; }
+    }
+    resmap_free(&usage);
+}
+
 /* ------------------------------------------------------------------ node sorting ---- */
 /* resourcesLessThan, internal/sort/nodesorting.go:74-80 */
 static int resources_less_than(const orc_res* l, const orc_res* r) {

@@ -106,6 +106,18 @@ void orc_potential_nodes(const orc_cluster*, const char* const* candidate_names,
                          int32_t* driver_out, int32_t* n_driver_out,
                          int32_t* exec_out, int32_t* n_exec_out);
 
+/* Snapshot build: GetReservedResources (EXT/resourcereservations.go:258-263: UsageForNodes over
+ * the hard reservations, LIB/resources/resources.go:31-43, plus the soft reservations,
+ * internal/cache/softreservations.go:155-170) and NodeSchedulingMetadataForNodes (resources.go:61-100).
+ * Reservations name their node; names outside the node list are ignored.  sched_* may be NULL. */
+void orc_node_scheduling_metadata(int32_t n_nodes, const char* const* names,
+                                  const int64_t* alloc_cpu, const int64_t* alloc_mem, const int64_t* alloc_gpu,
+                                  const int64_t* over_cpu, const int64_t* over_mem, const int64_t* over_gpu,
+                                  int64_t n_res, const char* const* res_node_name,
+                                  const int64_t* res_cpu, const int64_t* res_mem, const int64_t* res_gpu,
+                                  int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu,
+                                  int64_t* sched_cpu, int64_t* sched_mem, int64_t* sched_gpu);
+
 /* ------------------------------------------------------------------ closed form ---- */
 
 /* Same semantics on index arrays: node table [n_nodes] (int64 SoA), exec_order / driver_order are

@@ -61,6 +61,9 @@ def lib():
         L.orc_potential_nodes.restype = None
         L.orc_potential_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]
+        L.orc_node_scheduling_metadata.restype = None
+        L.orc_node_scheduling_metadata.argtypes = [C.c_int32, C.POINTER(C.c_char_p)] + [C.c_void_p] * 6 + [
+            C.c_int64, C.POINTER(C.c_char_p)] + [C.c_void_p] * 9
         L.orc_closed_batch.restype = C.c_int32
         L.orc_closed_batch.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
@@ -171,6 +174,20 @@ class Cluster:
         lib().orc_potential_nodes(self._h, _names(candidate_names), len(candidate_names), _ptr(dr), _ptr(er),
                                   _ptr(d), C.byref(nd), _ptr(e), C.byref(ne))
         return ([self.names[i] for i in d[:nd.value]], [self.names[i] for i in e[:ne.value]])
+
+
+def node_scheduling_metadata(names, alloc, overhead, res_node_names, res):
+    """(alloc, overhead, res) = triples of int64 arrays (cpu, mem, gpu); -> (avail triple, sched triple)."""
+    n = len(names)
+    al = [_i64(x) for x in alloc]
+    ov = [_i64(x) for x in overhead] if overhead is not None else [None] * 3
+    rs = [_i64(x) for x in res]
+    av = [np.empty(n, np.int64) for _ in range(3)]
+    sc = [np.empty(n, np.int64) for _ in range(3)]
+    lib().orc_node_scheduling_metadata(n, _names(names), _ptr(al[0]), _ptr(al[1]), _ptr(al[2]), _ptr(ov[0]), _ptr(ov[1]), _ptr(ov[2]),
+                                       len(res_node_names), _names(res_node_names), _ptr(rs[0]), _ptr(rs[1]), _ptr(rs[2]),
+                                       _ptr(av[0]), _ptr(av[1]), _ptr(av[2]), _ptr(sc[0]), _ptr(sc[1]), _ptr(sc[2]))
+    return av, sc
 
 
 def closed_batch(algo, mode, avail_cpu, avail_mem, avail_gpu, driver_order, exec_order,

@@ -288,3 +288,22 @@ def az_aware_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched
     if r[2]:
         return r
     return spark_bin_pack(drv, exe, count, driver_order, exec_order, meta, tightly_pack_executors)
+
+
+# ---------------------------------------------------------------------------------------------
+# snapshot build
+# ---------------------------------------------------------------------------------------------
+def node_scheduling_metadata(alloc, overhead, reservations):
+    """GetReservedResources (EXT/resourcereservations.go:258-263) + NodeSchedulingMetadataForNodes
+    (LIB/resources/resources.go:61-100).  alloc / overhead: name -> Resources; reservations: [(node, Resources)]
+    (hard and soft alike).  -> (available, schedulable) dicts over the nodes of `alloc`."""
+    usage = {}
+    for node, r in reservations:                      # UsageForNodes :31-43, softreservations.go:155-170
+        usage[node] = add(usage.get(node, ZERO), r)
+    available, schedulable = {}, {}
+    for n, a in alloc.items():
+        o = overhead.get(n, ZERO)
+        u = add(usage.get(n, ZERO), o)                # :76
+        available[n] = sub(a, u)                      # :89
+        schedulable[n] = sub(a, o)                    # :90
+    return available, schedulable

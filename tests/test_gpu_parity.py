@@ -481,3 +481,62 @@ def test_potential_nodes_feeds_the_packer(oracle, packer):
     packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], e, d)
     _, want, _ = _oracle_batch(oracle, 0, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], host_order, host_order, a)
     assert_same_results(packer.pack_batch(a, 0, 0), want, "device-sorted orders")
+
+
+def test_build_availability(oracle, packer):
+    """f2: reservations (hard + soft) and overhead -> available / schedulable on the device == literal oracle."""
+    rng = np.random.default_rng(11)
+    for n, R in ((1, 0), (50, 400), (10000, 250000)):
+        names = ["node-%05d" % i for i in range(n)]
+        alloc = [rng.integers(1, 97, n) * 1000, rng.integers(1, 385, n) * (1 << 30), rng.integers(0, 9, n)]
+        over = [rng.integers(0, 3, n) * 250, rng.integers(0, 4, n) * (1 << 28), np.zeros(n, np.int64)]
+        rnode = rng.integers(-1, n, R).astype(np.int32)          # -1: reservation on a node that left the cluster
+        res = [rng.integers(0, 8, R) * 500, rng.integers(0, 16, R) * (1 << 29), rng.integers(0, 2, R)]
+        av, sc = packer.build_availability(alloc, over, rnode, res)
+        rn = [names[i] if i >= 0 else "gone" for i in rnode]
+        wav, wsc = oracle.node_scheduling_metadata(names, alloc, over, rn, res)
+        for d in range(3):
+            assert np.array_equal(av[d], wav[d]) and np.array_equal(sc[d], wsc[d]), (n, R, d)
+        av2, _ = packer.build_availability(alloc, None, rnode, res)      # no overhead arrays
+        assert np.array_equal(av2[0], av[0] + over[0])
+
+
+def test_prepare_cluster_chain(oracle, packer):
+    """gp_prepare_cluster (reservations -> availability -> orders -> snapshot, all on the device) followed by a
+    FIFO batch == the same steps through the separate entries == the CPU oracle end to end."""
+    rng = np.random.default_rng(21)
+    n, R, q = 3000, 40000, 800
+    names = ["node-%05d" % int(x) for x in rng.permutation(n * 2)[:n]]
+    alloc = [rng.integers(8, 97, n) * 1000, rng.integers(32, 385, n) * (1 << 30), np.zeros(n, np.int64)]
+    over = [rng.integers(0, 3, n) * 250, rng.integers(0, 4, n) * (1 << 28), np.zeros(n, np.int64)]
+    rnode = rng.integers(-1, n, R).astype(np.int32)
+    res = [rng.integers(0, 6, R) * 500, rng.integers(0, 12, R) * (1 << 29), np.zeros(R, np.int64)]
+    zones = {nm: "zone-%d" % rng.integers(0, 3) for nm in names}
+    zid, nz, rank = _potential_nodes_inputs(names, zones)
+    unsched = (rng.random(n) < 0.05).astype(np.uint8); ready = (rng.random(n) < 0.95).astype(np.uint8)
+    cand = (rng.random(n) < 0.8).astype(np.uint8)
+    import k8s_spark_scheduler_b200.synth as synth
+    apps = synth.make_apps(q, seed=5)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    a["young"] = (np.arange(q) % 5 == 0).astype(np.uint8)
+    # chained on the device
+    nd, ne = packer.prepare_cluster(alloc, over, rnode, res, zid, nz, rank, cand, unsched, ready)
+    got = packer.pack_batch(a, 0, 1)
+    snap = packer.get_snapshot()
+    # the same through the separate entries
+    av, _ = packer.build_availability(alloc, over, rnode, res)
+    d, e = packer.potential_nodes(av[0], av[1], zid, nz, rank, cand, unsched, ready)
+    assert (nd, ne) == (len(d), len(e))
+    packer.set_snapshot(av[0], av[1], av[2], e, d)
+    want = packer.pack_batch(a, 0, 1)
+    assert_same_results(got, want, "chained vs separate")
+    for x, y in zip(snap, packer.get_snapshot()):
+        assert np.array_equal(x, y)
+    # and the CPU oracle end to end (string-keyed)
+    rn = [names[i] if i >= 0 else "gone" for i in rnode]
+    wav, _ = oracle.node_scheduling_metadata(names, alloc, over, rn, res)
+    cl = oracle.Cluster(names, wav[0], wav[1], wav[2], zone=[zones[nm] for nm in names], unschedulable=unsched, ready=ready)
+    wd, we = cl.potential_nodes([nm for nm, m in zip(names, cand) if m])
+    drv = res_aos(a["drv_cpu"], a["drv_mem"], a["drv_gpu"]); exe = res_aos(a["exe_cpu"], a["exe_mem"], a["exe_gpu"])
+    _, od, oe, ooff = cl.fifo(0, 1, drv, exe, a["count"], a["young"], wd, we)
+    assert_same_results(got, (od, oe, ooff), "device pipeline vs literal oracle pipeline")

@@ -196,3 +196,24 @@ def test_zone_packers_random_three_way(oracle):
                 assert ok == lok, (trial, aid)
                 if ok:
                     assert d == ld and ex == lex, (trial, aid)
+
+
+def test_snapshot_build_oracles_agree(oracle):
+    """f2: usage from hard + soft reservations and overhead -> available / schedulable (literal C == Python)."""
+    from oracle import pyref
+    rng = np.random.default_rng(7)
+    n = 50
+    names = ["n%02d" % i for i in range(n)]
+    alloc = [rng.integers(1, 64, n) * 1000, rng.integers(1, 256, n) * (1 << 30), rng.integers(0, 9, n)]
+    over = [rng.integers(0, 3, n) * 250, rng.integers(0, 4, n) * (1 << 28), np.zeros(n, np.int64)]
+    R = 400
+    rn = [names[i] if i < n else "gone-%d" % i for i in rng.integers(0, n + 5, R)]     # some reservations on nodes that left
+    res = [rng.integers(0, 8, R) * 500, rng.integers(0, 16, R) * (1 << 29), rng.integers(0, 2, R)]
+    av, sc = oracle.node_scheduling_metadata(names, alloc, over, rn, res)
+    pa, ps = pyref.node_scheduling_metadata({names[i]: tuple(int(x[i]) for x in alloc) for i in range(n)},
+                                            {names[i]: tuple(int(x[i]) for x in over) for i in range(n)},
+                                            [(rn[r], tuple(int(x[r]) for x in res)) for r in range(R)])
+    for i, nm in enumerate(names):
+        assert (av[0][i], av[1][i], av[2][i]) == pa[nm]
+        assert (sc[0][i], sc[1][i], sc[2][i]) == ps[nm]
+    assert (av[0] < 0).any()      # over-committed nodes exist: availability may be negative

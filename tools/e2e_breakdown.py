@@ -39,6 +39,13 @@ import k8s_spark_scheduler_b200.synth as _synth
 _n50 = _synth.make_nodes(50000)
 print("potential_nodes (device sort, 50k nodes) %8.1f us" % t(lambda: p.potential_nodes(_n50["avail_cpu"], _n50["avail_mem"]), 5))
 _t0 = time.perf_counter(); _synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"]); print("numpy lexsort 10k nodes %8.1f us" % ((time.perf_counter() - _t0) * 1e6))
+_R = 200000
+_rng = np.random.default_rng(1)
+_rnode = _rng.integers(0, len(nodes["avail_cpu"]), _R).astype(np.int32)
+_res = [(_rng.integers(0, 4, _R) * 500).astype(np.int64), (_rng.integers(0, 8, _R) << 29).astype(np.int64), np.zeros(_R, np.int64)]
+_alloc = [nodes["alloc_cpu"], nodes["alloc_mem"], nodes["alloc_gpu"]]
+print("build_availability (10k nodes, 200k reservations) %8.1f us" % t(lambda: p.build_availability(_alloc, None, _rnode, _res)))
+print("prepare_cluster (availability + sort + layout, chained) %8.1f us" % t(lambda: p.prepare_cluster(_alloc, None, _rnode, _res)))
 print("set_snapshot        %8.1f us" % t(snap))
 print("pack_batch (pinned) %8.1f us" % t(pack), p.stats())
 pageable = {k: np.array(v) for k, v in pin.items()}
