@@ -228,6 +228,8 @@ def main():
     import torch
     import torch.distributed as dist
     import k8s_spark_scheduler_b200 as g
+    if not os.path.exists(g.native.LIB_PATH):      # normally prebuilt in-tree by __graft_entry__.build()
+        g.native.build()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
