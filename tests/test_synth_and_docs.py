@@ -1,0 +1,60 @@
+"""The synthetic workloads are part of the measurement contract (seeds 0xB200 / 0x5CED): pin them by
+checksum so that numbers from different rounds refer to the same inputs.  Also: the integration document must
+mention every entry point the header declares."""
+import os
+import re
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _crc(*arrs):
+    c = 0
+    for x in arrs:
+        c = zlib.crc32(np.ascontiguousarray(x).tobytes(), c)
+    return c
+
+
+def test_synthetic_workloads_are_pinned():
+    import k8s_spark_scheduler_b200.synth as synth
+    n = synth.make_nodes(10000)
+    a = synth.make_apps(100000)
+    o = synth.priority_order(n["avail_cpu"], n["avail_mem"])
+    assert _crc(n["avail_cpu"], n["avail_mem"], n["avail_gpu"]) == 3133782155
+    assert _crc(o) == 2210498708
+    assert _crc(a["drv_cpu"], a["drv_mem"], a["exe_cpu"], a["exe_mem"], a["count"]) == 1814995498
+    assert int(a["count"].sum()) == 1647812
+    n2 = synth.make_nodes(10000, groups=16)
+    a2 = synth.make_apps(50000, groups=16, da_sweep=True)
+    assert _crc(n2["group"]) == 4013496626 and _crc(a2["count"], a2["max_count"], a2["group"]) == 2888400462
+    # shape facts the docs quote
+    assert n["avail_cpu"].min() > 0 and (n["avail_mem"] % (256 << 20) == 0).all() and (n["avail_cpu"] % 250 == 0).all()
+    assert a["count"].min() == 1 and a["count"].max() == 32
+    assert (a2["max_count"] >= a2["count"]).all() and set(np.unique(a2["count"])) <= {0, 1, 2, 4, 8, 16}
+
+
+def test_priority_order_matches_the_node_sorter_semantics():
+    """synth.priority_order is the single-zone PotentialNodes order: memory, cpu, name ascending
+    (internal/sort/nodesorting.go:74-93) -- cross-checked with the pure-Python restatement."""
+    import k8s_spark_scheduler_b200.synth as synth
+    from oracle import pyref
+    n = synth.make_nodes(400)
+    names = synth.node_names(400)
+    meta = {names[i]: (int(n["avail_cpu"][i]), int(n["avail_mem"][i]), 0) for i in range(400)}
+    want = pyref.node_names_in_priority_order(meta, {})
+    got = [names[i] for i in synth.priority_order(n["avail_cpu"], n["avail_mem"])]
+    assert got == want
+
+
+def test_integration_doc_covers_every_entry_point():
+    header = open(os.path.join(ROOT, "include", "gangpack.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(gp_[a-z_]+)\s*\(", header)))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in declared if s not in doc and s not in ("gp_abi_version",)]
+    assert not missing, missing
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    for kernel in ("gp_prep_apps", "gp_pack_independent", "gp_pack_fifo_cta", "gp_potential_nodes", "gp_build_availability"):
+        assert kernel in design, kernel
