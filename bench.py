@@ -289,28 +289,50 @@ def main():
 
     launches_per_step = 3 + 2   # build_groups, build_exec_slots, build_driver_slots, prep_apps, pack
     with torch.cuda.stream(stream):
+        # Eager warm-up steps: they also provide the per-kernel times (the library brackets its pack kernel with
+        # CUDA events) and the scan statistics that the roofline object needs.
+        pack_ns, prep_ns = [], []
         for _ in range(max(args.warmup, 3)):
             flush.fill_(1)
             device_step()
+            st = packer.stats()                # synchronises the stream; reads the pack kernel's own event time
+            pack_ns.append(st["pack_kernel_ns"]); prep_ns.append(st["prep_kernel_ns"])
+        stats = packer.stats()
+        # The step is a chain of ~10 small launches; issued from Python its duration depends on how fast the host
+        # thread can enqueue them (visibly so with 8 ranks per box).  It is therefore captured ONCE into a CUDA
+        # graph and replayed: same kernels, same work, one launch.  BENCH_GRAPH=0 keeps eager launches.
+        graph = None
+        if os.environ.get("BENCH_GRAPH", "1") != "0":
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    device_step()
+                for _ in range(2):
+                    graph.replay()
+                torch.cuda.synchronize()
+            except Exception as e:   # capture not possible: run eagerly
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                graph = None
+                torch.cuda.synchronize()
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        pack_ns, prep_ns = [], []
         barrier()
         wall0 = time.perf_counter()
         for s in range(args.steps):
             flush.fill_(s & 0xff)              # L2 flush, outside the event pair
             evs[s][0].record(stream)
-            device_step()
+            if graph is not None:
+                graph.replay()
+            else:
+                device_step()
             evs[s][1].record(stream)
-            st = packer.stats()                # synchronises the stream; reads the pack kernel's own event time
-            pack_ns.append(st["pack_kernel_ns"]); prep_ns.append(st["prep_kernel_ns"])
         barrier()
         wall1 = time.perf_counter()
         step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    stats = packer.stats()
     ms = float(np.mean(step_ms))
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
@@ -478,7 +500,8 @@ def main():
                        "executors_total_per_gpu": total_exec,
                        "l2": "256 MiB write between steps, outside the per-step CUDA-event pair",
                        "step": "snapshot layout + prep + pack, device-resident inputs, no collective in the data path "
-                               "(every rank packs its own block of the queue against its copy of the snapshot)",
+                               "(every rank packs its own block of the queue against its copy of the snapshot); "
+                               + ("the launch chain is replayed from one CUDA graph" if graph is not None else "eager launches"),
                        "e2e_step": e2e_step_desc,
                        "fits": None},
             "clocks": clocks,
