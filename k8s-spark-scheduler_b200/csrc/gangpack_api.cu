@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kPackThreads, GP_PACK_MIN_BLOCKS) gp_pack_inde
         if (lane == 0 && n1 < (unsigned int)n_apps) asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + n1));
         const PrepApp* pa = prep + i;
         int32_t d = -1;
-        if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO, 0>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+        if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
         if (lane == 0) driver_node[i] = d;
         i = n1;
         n1 = __shfl_sync(kFull, n2, 0);

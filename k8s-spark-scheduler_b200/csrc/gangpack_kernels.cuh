@@ -256,15 +256,6 @@ __device__ __forceinline__ bool driver_fits(const Snapshot& s, int32_t slot, con
     return ok;
 }
 
-// SubtractUsageIfExists for one slot (resources.go:129-135): avail -= mult * (cpu, mem, gpu)
-__device__ __forceinline__ void charge(const Snapshot& s, int32_t slot, long long mult, int64_t cpu, int64_t mem, int64_t gpu) {
-    longlong2* pp = s.pair + slot;
-    longlong2 v = *pp;
-    v.x -= mult * cpu; v.y -= mult * mem;
-    *pp = v;
-    if (gpu != 0) s.gpu[slot] -= mult * gpu;
-}
-
 // distribute-evenly, general rounds (distribute_evenly.go:49-70) over the complete candidate list
 // (m <= k entries (position, cap) in priority order), executed by ONE warp:
 // R* = min r with sum min(c, r) >= k; round r hands one executor to every node with c >= r until k are
@@ -316,17 +307,16 @@ struct WarpStats { unsigned long long nodes; unsigned long long drivers; };
 constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 capacities (uint16)
 
 // ---------------------------------------------------------------------------------------------
-// One application, one warp.  Returns the driver's node index (>= 0) or -1.
-// ALGO: 0 tightly-pack, 1 distribute-evenly.  FIFO_MODE: 0 none, 1 reference usage, 2 exact usage
-// (then the snapshot is read with plain loads and the placement is subtracted from it).
-// wcache: this warp's kCapCache x uint16 scratch in shared memory.
+// One application, one warp, against an immutable snapshot (GP_MODE_INDEPENDENT; the FIFO modes live in
+// gangpack_fifo.cuh).  Returns the driver's node index (>= 0) or -1.
+// ALGO: 0 tightly-pack, 1 distribute-evenly.  wcache: this warp's kCapCache x uint16 scratch in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, int FIFO_MODE, bool FAST, bool NOGPU>
+template <int ALGO, bool FAST, bool NOGPU>
 __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane,
                                                  int snap_flags, const GroupDesc& g0) {
-    constexpr bool MUT = FIFO_MODE != 0;
+    constexpr bool MUT = false;   // read-only path (ld.global.nc)
     Caps<FAST> a;
     a.init(pa, (pa->flags & kAppUsesGpu) || (snap_flags & kSnapGpuNegative));
     const bool ug = NOGPU ? false : a.use_gpu;      // compile-time false on the hot instantiation
@@ -406,7 +396,6 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     const uint32_t cd = (dslot < ne && k != 0) ? a.template cap<MUT>(s, g.sbase + dslot, a.d_cpu, a.d_mem, a.d_gpu, ug) : 0u;
 
     // ---- phase 3: emit ExecutorNodes -------------------------------------------------------------
-    bool driver_hosts_executor = false;
     if (k != 0) {
         if (ALGO == 0) {
             // node-major: node n receives min(cap_d(n), remaining)  (pack_tightly.go:45-61)
@@ -437,10 +426,6 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
                         int32_t nd = __shfl_sync(kFull, node, lo & 31);
                         if (j < T) out[placed + j] = nd;
                     }
-                    if (FIFO_MODE != 0 && take != 0) {
-                        if (i == dslot) driver_hosts_executor = true;
-                        charge(s, g.sbase + i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
-                    }
                 }
                 placed += T;
             }
@@ -456,51 +441,37 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
                 if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 unsigned has = __ballot_sync(kFull, c != 0);
                 uint32_t r = placed + __popc(has & ((1u << lane) - 1u));
-                if (c != 0 && r < k) {
-                    out[r] = s.slot_node[g.sbase + i];
-                    if (FIFO_MODE != 0) {
-                        if (i == dslot) driver_hosts_executor = true;
-                        charge(s, g.sbase + i, 1, a.e_cpu, a.e_mem, a.e_gpu);
-                    }
-                }
+                if (c != 0 && r < k) out[r] = s.slot_node[g.sbase + i];
                 placed += __popc(has);
             }
         } else {
             __syncwarp();
-            driver_hosts_executor = evenly_rounds<FIFO_MODE>(list, m1, k, dslot, cd, out, s.slot_node + g.sbase, lane,
-                [&](int32_t local) { charge(s, g.sbase + local, 1, a.e_cpu, a.e_mem, a.e_gpu); });
+            evenly_rounds<0>(list, m1, k, dslot, cd, out, s.slot_node + g.sbase, lane, [](int32_t) {});
         }
     }
 
-    // ---- FIFO: charge the driver (sparkpods.go:139-146 / exact) -----------------------------------
-    if (FIFO_MODE != 0) {
-        bool hosted = __any_sync(kFull, driver_hosts_executor);
-        __syncwarp();   // executor charges (other lanes) are ordered before the driver charge
-        if (lane == 0 && (FIFO_MODE == 2 || !hosted)) charge(s, g.sbase + dslot, 1, a.d_cpu, a.d_mem, a.d_gpu);
-        __syncwarp();   // the next application of this queue sees the charged snapshot
-    }
     return driver_node;
 }
 
 // everything that is not (fast class, gpu dimension idle): any int64 request / binding gpu dimension
-template <int ALGO, int FIFO_MODE>
+template <int ALGO>
 __device__ __noinline__ int32_t pack_app_general(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane, int snap_flags) {
     const GroupDesc g0 = s.groups[0];
-    return pack_app_impl<ALGO, FIFO_MODE, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+    return pack_app_impl<ALGO, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
 }
 
 // class dispatch (warp-uniform): hot path = fast class with the gpu dimension idle
-template <int ALGO, int FIFO_MODE>
+template <int ALGO>
 __device__ __forceinline__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, int32_t* __restrict__ executor_nodes,
                                             int2* __restrict__ scratch, uint16_t* __restrict__ wcache, WarpStats& st, int lane,
                                             int snap_flags, const GroupDesc& g0) {
     const uint32_t fl = pa->flags;
     const bool gpu_idle = !(fl & kAppUsesGpu) && !(snap_flags & kSnapGpuNegative);
     if ((fl & kAppFast) && gpu_idle)
-        return pack_app_impl<ALGO, FIFO_MODE, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
-    return pack_app_general<ALGO, FIFO_MODE>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
+        return pack_app_impl<ALGO, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+    return pack_app_general<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
 }
 
 }  // namespace gp
