@@ -89,8 +89,12 @@ __global__ void gp_prep_apps(int32_t n_apps,
     p.count = k;
     p.group = g;
     p.lmax = (int32_t)(lmax < (uint64_t)k ? lmax : (uint64_t)k);
+    // compact 32-bit view usable: the request shifts are at least the view's shifts
+    const bool fast32 = fast && p.div[0].kind == kDivMagic && p.div[1].kind == kDivMagic &&
+                        (int)p.div[0].sh >= meta->shift32[0] && (int)p.div[1].sh >= meta->shift32[1] &&
+                        (int)p.div[0].sh - meta->shift32[0] < 32 && (int)p.div[1].sh - meta->shift32[1] < 32;   // 32-bit shift amounts
     p.flags = ((d[2] != 0 || e[2] != 0) ? kAppUsesGpu : 0u) | ((skip && skip[i]) ? kAppSkipIfNoFit : 0u) |
-              (bad ? kAppInvalid : 0u) | (fast ? kAppFast : 0u);
+              (bad ? kAppInvalid : 0u) | (fast ? kAppFast : 0u) | (fast32 ? kAppFast32 : 0u);
     prep[i] = p;
 }
 
@@ -229,6 +233,27 @@ __global__ void gp_multi_copy(CopyJobs jobs) {
     }
 }
 
+// After the slots are laid out: the shifts of the compact view (smallest S with max_avail >> S < 2^32) ...
+__global__ void gp_snapshot_shifts(SnapMeta* __restrict__ meta) {
+    if (threadIdx.x < 2) {
+        const long long mx = meta->max_avail[threadIdx.x];
+        int sft = 0;
+        if (mx > 0) { const int bits = 64 - __clzll(mx); sft = bits > 32 ? bits - 32 : 0; }
+        meta->shift32[threadIdx.x] = sft;
+    }
+}
+// ... and the view itself: 8 bytes per slot instead of 16 (negative availability -> 0: capacity 0 either way)
+__global__ void gp_fill_pair32(int32_t n_slots, const longlong2* __restrict__ pair, const SnapMeta* __restrict__ meta,
+                               uint2* __restrict__ pair32) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const longlong2 v = pair[i];
+    uint2 o;
+    o.x = v.x < 0 ? 0u : (uint32_t)((unsigned long long)v.x >> meta->shift32[0]);
+    o.y = v.y < 0 ? 0u : (uint32_t)((unsigned long long)v.y >> meta->shift32[1]);
+    pair32[i] = o;
+}
+
 // slots -> node-table order (gp_get_snapshot)
 __global__ void gp_scatter_slots(int32_t n_slots, const longlong2* __restrict__ pair, const int64_t* __restrict__ sgpu,
                                  const int32_t* __restrict__ slot_node,
@@ -283,7 +308,7 @@ struct gp_ctx {
     int32_t n_nodes = 0, n_groups = 0, n_exec = 0, n_drv = 0, n_slots = 0;
     DevBuf node_cpu, node_mem, node_gpu;        // node-table order (as given)
     DevBuf exec_off, drv_off, exec_order, drv_order;
-    DevBuf pair, sgpu, slot_node, node_slot, drv_slot, groups, snap_flags;
+    DevBuf pair, pair32, sgpu, slot_node, node_slot, drv_slot, groups, snap_flags;
 
     // batch staging
     DevBuf a_dcpu, a_dmem, a_dgpu, a_ecpu, a_emem, a_egpu, a_count, a_group, a_skip, a_off;
@@ -349,6 +374,7 @@ static gp_status fail(gp_ctx* ctx, gp_status st, const std::string& msg) {
 static Snapshot make_snapshot(const gp_ctx* c) {
     Snapshot s;
     s.pair = c->pair.as<longlong2>();
+    s.pair32 = c->pair32.as<uint2>();
     s.gpu = c->sgpu.as<int64_t>();
     s.slot_node = c->slot_node.as<int32_t>();
     s.drv_slot = c->drv_slot.as<int32_t>();
@@ -417,7 +443,7 @@ void gp_destroy(gp_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->node_cpu, &c->node_mem, &c->node_gpu, &c->exec_off, &c->drv_off, &c->exec_order, &c->drv_order,
-                      &c->pair, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
+                      &c->pair, &c->pair32, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
                       &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf};
     for (DevBuf* b : bufs) b->release();
@@ -465,6 +491,7 @@ gp_status gp_synchronize(gp_ctx* ctx) {
 static gp_status build_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_exec, int32_t n_drv, cudaStream_t st) {
     const int32_t n_slots = n_exec + n_drv;
     GP_CUDA(c, c->pair.reserve(sizeof(longlong2) * (size_t)(n_slots + 1)));
+    GP_CUDA(c, c->pair32.reserve(sizeof(uint2) * (size_t)(n_slots + 1)));
     GP_CUDA(c, c->sgpu.reserve(sizeof(int64_t) * (size_t)(n_slots + 1)));
     GP_CUDA(c, c->slot_node.reserve(sizeof(int32_t) * (size_t)(n_slots + 1)));
     GP_CUDA(c, c->node_slot.reserve(sizeof(int32_t) * (size_t)(dn->n_nodes + 1)));
@@ -485,6 +512,11 @@ static gp_status build_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_
             n_drv, dn->n_groups, dn->exec_off, dn->drv_off, dn->drv_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
             dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
             c->node_slot.as<int32_t>(), c->drv_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
+    // spare slots that stay unused must read as "nothing available" in both views
+    GP_CUDA(c, cudaMemsetAsync(c->pair32.p, 0, sizeof(uint2) * (size_t)(n_slots + 1), st));
+    gp_snapshot_shifts<<<1, 32, 0, st>>>(c->snap_flags.as<SnapMeta>());
+    if (n_slots > 0)
+        gp_fill_pair32<<<(n_slots + T - 1) / T, T, 0, st>>>(n_slots, c->pair.as<longlong2>(), c->snap_flags.as<SnapMeta>(), c->pair32.as<uint2>());
     GP_CUDA(c, cudaGetLastError());
     c->n_nodes = dn->n_nodes; c->n_groups = dn->n_groups; c->n_exec = n_exec; c->n_drv = n_drv; c->n_slots = n_slots;
     c->have_snapshot = true;

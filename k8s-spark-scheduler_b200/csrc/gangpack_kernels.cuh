@@ -51,6 +51,8 @@ struct SnapMeta {
     int flags;
     int pad;
     long long max_avail[3];   // cpu milli, mem bytes, gpu
+    int shift32[2];           // compact view: pair32 = (max(cpu,0) >> shift32[0], max(mem,0) >> shift32[1]), both < 2^32
+    int pad2[2];
 };
 
 // How to divide by one executor-request dimension.
@@ -71,9 +73,9 @@ struct __align__(16) PrepApp {
     int32_t count;       // MinExecutorCount
     int32_t group;
     int32_t lmax;        // max executors the driver can displace on its own node (<= count)
-    uint32_t flags;      // bit0: uses gpu dim, bit1: skip_if_no_fit, bit2: invalid, bit3: fast class
+    uint32_t flags;      // bit0: uses gpu dim, bit1: skip_if_no_fit, bit2: invalid, bit3: fast class, bit4: compact 32-bit view usable
 };
-enum : uint32_t { kAppUsesGpu = 1u, kAppSkipIfNoFit = 2u, kAppInvalid = 4u, kAppFast = 8u };
+enum : uint32_t { kAppUsesGpu = 1u, kAppSkipIfNoFit = 2u, kAppInvalid = 4u, kAppFast = 8u, kAppFast32 = 16u };
 static_assert(sizeof(PrepApp) == 128, "PrepApp layout");
 
 // Smallest requests over the batch's applications of one instance group (gp_prep_apps, atomicMin).
@@ -95,6 +97,7 @@ struct GroupDesc {
 // candidate (used only when that candidate is not an executor candidate).
 struct Snapshot {
     longlong2* pair;       // [n_slots] (avail cpu milli, avail mem bytes)
+    const uint2* pair32;   // [n_slots] compact read-only view of `pair` (see SnapMeta::shift32); independent mode only
     int64_t* gpu;          // [n_slots]
     int32_t* slot_node;    // [n_slots] caller's node index, -1 = unused spare
     const int32_t* drv_slot; // [n_drv] group-local slot of each driver candidate
@@ -210,6 +213,19 @@ template <> struct Caps<true> {
         e_cpu = pa->div[0].e; e_mem = pa->div[1].e; e_gpu = pa->div[2].e;
         k = (uint32_t)pa->count; use_gpu = ug;
     }
+    // Compact view: both availabilities pre-shifted to 32 bits (negative -> 0, which also yields capacity 0 because
+    // the requests of this class are > 0).  a >> sh == (a >> S) >> (sh - S) for sh >= S, so the quotient is the same.
+    uint32_t sh32_cpu, sh32_mem;    // sh - S per dimension (kAppFast32 only)
+    __device__ __forceinline__ void init32(const SnapMeta* meta) {
+        sh32_cpu = cpu.sh - (uint32_t)meta->shift32[0];
+        sh32_mem = mem.sh - (uint32_t)meta->shift32[1];
+    }
+    __device__ __forceinline__ uint32_t cap32(uint2 v) const {
+        const uint32_t xc = v.x >> sh32_cpu, xm = v.y >> sh32_mem;
+        const uint32_t qc = (uint32_t)(((uint64_t)cpu.m_hi * xc + __umulhi(cpu.m_lo, xc)) >> 32);
+        const uint32_t qm = (uint32_t)(((uint64_t)mem.m_hi * xm + __umulhi(mem.m_lo, xm)) >> 32);
+        return umin3(qc, qm, k);
+    }
     // capacity from already-loaded availability, reservation r, clamped to k
     __device__ __forceinline__ uint32_t cap_pair(longlong2 v, int64_t r_cpu, int64_t r_mem) const {
         return umin3(fast_q_magic(v.x - r_cpu, cpu), fast_q_magic(v.y - r_mem, mem), k);
@@ -245,6 +261,8 @@ template <> struct Caps<false> {
     }
     template <bool MUT>
     __device__ __forceinline__ uint32_t cap0(const Snapshot& s, int32_t slot, bool ug) const { return cap<MUT>(s, slot, 0, 0, 0, ug); }
+    __device__ __forceinline__ void init32(const SnapMeta*) {}
+    __device__ __forceinline__ uint32_t cap32(uint2) const { return 0; }   // never instantiated with C32
 };
 
 // driverResources.GreaterThan(available) == false  (binpack.go:69)
@@ -311,7 +329,7 @@ constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 cap
 // gangpack_fifo.cuh).  Returns the driver's node index (>= 0) or -1.
 // ALGO: 0 tightly-pack, 1 distribute-evenly.  wcache: this warp's kCapCache x uint16 scratch in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, bool FAST, bool NOGPU>
+template <int ALGO, bool FAST, bool NOGPU, bool C32>
 __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane,
@@ -320,6 +338,7 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     Caps<FAST> a;
     a.init(pa, (pa->flags & kAppUsesGpu) || (snap_flags & kSnapGpuNegative));
     const bool ug = NOGPU ? false : a.use_gpu;      // compile-time false on the hot instantiation
+    if (C32) a.init32(s.meta);
     const int32_t grp = pa->group;
     const GroupDesc g = grp == 0 ? g0 : s.groups[grp];   // group 0's descriptor is kept in registers by the caller
     const uint32_t k = a.k;
@@ -345,8 +364,14 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     const unsigned long long need = (unsigned long long)k + lmax;
     while (!early && pos < ne) {
         const int32_t i0 = pos + lane, i1 = i0 + kWarp;
-        const uint32_t c0 = (i0 < ne) ? a.template cap0<MUT>(s, g.sbase + i0, ug) : 0u;
-        const uint32_t c1 = (i1 < ne) ? a.template cap0<MUT>(s, g.sbase + i1, ug) : 0u;
+        uint32_t c0 = 0u, c1 = 0u;
+        if (C32) {                                    // 8-byte records, two shifts + two multiply-highs per node
+            if (i0 < ne) c0 = a.cap32(__ldg(s.pair32 + g.sbase + i0));
+            if (i1 < ne) c1 = a.cap32(__ldg(s.pair32 + g.sbase + i1));
+        } else {
+            if (i0 < ne) c0 = a.template cap0<MUT>(s, g.sbase + i0, ug);
+            if (i1 < ne) c1 = a.template cap0<MUT>(s, g.sbase + i1, ug);
+        }
         if (cache_ok && i1 < kCapCache) { wcache[i0] = (uint16_t)c0; wcache[i1] = (uint16_t)c1; }
         const unsigned has0 = __ballot_sync(kFull, c0 != 0), has1 = __ballot_sync(kFull, c1 != 0);
         if (ALGO == 1) {
@@ -405,7 +430,7 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
                 uint32_t c = 0;
                 if (i == dslot) c = cd;
                 else if (i < cached_end) c = wcache[i];
-                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i, ug);
+                else if (i < ne) c = C32 ? a.cap32(__ldg(s.pair32 + g.sbase + i)) : a.template cap0<MUT>(s, g.sbase + i, ug);
                 if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 uint32_t incl = warp_incl_scan(c, lane);
                 uint32_t total = __shfl_sync(kFull, incl, kWarp - 1);
@@ -437,7 +462,7 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
                 uint32_t c = 0;
                 if (i == dslot) c = cd;
                 else if (i < cached_end) c = wcache[i];
-                else if (i < ne) c = a.template cap0<MUT>(s, g.sbase + i, ug);
+                else if (i < ne) c = C32 ? a.cap32(__ldg(s.pair32 + g.sbase + i)) : a.template cap0<MUT>(s, g.sbase + i, ug);
                 if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 unsigned has = __ballot_sync(kFull, c != 0);
                 uint32_t r = placed + __popc(has & ((1u << lane) - 1u));
@@ -459,7 +484,16 @@ __device__ __noinline__ int32_t pack_app_general(const Snapshot& s, const PrepAp
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane, int snap_flags) {
     const GroupDesc g0 = s.groups[0];
-    return pack_app_impl<ALGO, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+    return pack_app_impl<ALGO, false, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+}
+
+// fast class whose request shifts are below the compact view's shift (e.g. byte-granular memory requests)
+template <int ALGO>
+__device__ __noinline__ int32_t pack_app_fast64(const Snapshot& s, const PrepApp* __restrict__ pa,
+                                                int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
+                                                uint16_t* __restrict__ wcache, WarpStats& st, int lane, int snap_flags) {
+    const GroupDesc g0 = s.groups[0];
+    return pack_app_impl<ALGO, true, true, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
 }
 
 // class dispatch (warp-uniform): hot path = fast class with the gpu dimension idle
@@ -469,8 +503,10 @@ __device__ __forceinline__ int32_t pack_app(const Snapshot& s, const PrepApp* __
                                             int snap_flags, const GroupDesc& g0) {
     const uint32_t fl = pa->flags;
     const bool gpu_idle = !(fl & kAppUsesGpu) && !(snap_flags & kSnapGpuNegative);
+    if ((fl & kAppFast32) && gpu_idle)     // hottest path: compact 32-bit snapshot view
+        return pack_app_impl<ALGO, true, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
     if ((fl & kAppFast) && gpu_idle)
-        return pack_app_impl<ALGO, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+        return pack_app_fast64<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
     return pack_app_general<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
 }
 
