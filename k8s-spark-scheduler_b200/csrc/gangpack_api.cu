@@ -20,6 +20,7 @@ using namespace gp;
 // kernels
 // =============================================================================================
 
+constexpr int kPrepThreads = 256;
 // Thread per application: validate, derive the division magics and the driver-displacement bound.
 // Source tuple: types.SparkApplicationResources (internal/types/types.go:22-27).
 __global__ void gp_prep_apps(int32_t n_apps,
@@ -30,8 +31,13 @@ __global__ void gp_prep_apps(int32_t n_apps,
                              int32_t n_groups, int64_t out_cap, const SnapMeta* __restrict__ meta,
                              GroupMin* __restrict__ gmins, PrepApp* __restrict__ prep, int* __restrict__ err,
                              volatile int* __restrict__ err_host) {
-    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_apps) return;
+    // records are staged in shared memory and written out with fully coalesced 16-byte stores (a thread writing
+    // its own 128-byte record would touch 32 different lines per warp-wide store)
+    __shared__ uint4 stage[kPrepThreads * (sizeof(PrepApp) / sizeof(uint4))];
+    const int32_t block0 = blockIdx.x * blockDim.x;
+    int32_t i = block0 + threadIdx.x;
+    const bool live = i < n_apps;
+    if (!live) i = n_apps - 1;                      // keep the thread for the cooperative copy-out; its record is not stored
     int64_t d[3] = {d_cpu[i], d_mem[i], d_gpu ? d_gpu[i] : 0};
     int64_t e[3] = {e_cpu[i], e_mem[i], e_gpu ? e_gpu[i] : 0};
     int32_t k = count[i];
@@ -75,8 +81,9 @@ __global__ void gp_prep_apps(int32_t n_apps,
             if (mx > 0 && (((unsigned long long)mx >> dv.sh) >> 32) != 0) fast = false;
         }
     }
-    if (bad) { atomicOr(err, bad); *err_host = bad; k = 0; g = 0; }   // err_host: mapped pinned word, no D2H copy needed
-    else if (gmins) {
+    if (bad && live) { atomicOr(err, bad); *err_host = bad; }   // err_host: mapped pinned word, no D2H copy needed
+    if (bad) { k = 0; g = 0; }
+    else if (gmins && live) {
         // batch-wide minima per instance group (FIFO dead-node skipping)
         GroupMin* gm = gmins + g;
 #pragma unroll
@@ -95,7 +102,14 @@ __global__ void gp_prep_apps(int32_t n_apps,
                         (int)p.div[0].sh - meta->shift32[0] < 32 && (int)p.div[1].sh - meta->shift32[1] < 32;   // 32-bit shift amounts
     p.flags = ((d[2] != 0 || e[2] != 0) ? kAppUsesGpu : 0u) | ((skip && skip[i]) ? kAppSkipIfNoFit : 0u) |
               (bad ? kAppInvalid : 0u) | (fast ? kAppFast : 0u) | (fast32 ? kAppFast32 : 0u);
-    prep[i] = p;
+    constexpr int kQ = sizeof(PrepApp) / sizeof(uint4);      // 8 x 16 bytes per record
+    const uint4* src = reinterpret_cast<const uint4*>(&p);
+#pragma unroll
+    for (int w = 0; w < kQ; ++w) stage[threadIdx.x * kQ + w] = src[w];
+    __syncthreads();
+    const int32_t n_block = min((int32_t)blockDim.x, n_apps - block0);
+    uint4* dst = reinterpret_cast<uint4*>(prep + block0);
+    for (int32_t t = threadIdx.x; t < n_block * kQ; t += blockDim.x) dst[t] = stage[t];
 }
 
 // Independent mode (GP_MODE_INDEPENDENT): one warp per application; warps claim applications from a
@@ -163,11 +177,27 @@ __global__ void gp_build_groups(int32_t n_groups, const int32_t* __restrict__ ex
 }
 
 // snapshot-wide facts: negative gpu availability, per-dimension maxima (bounds for the fast class)
+// Called by the threads of a warp that own a node (`active` = their mask): the warp combines its values with
+// shuffles and issues at most one atomic per dimension.
+__device__ __forceinline__ long long warp_max_ll(unsigned active, long long v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        long long o = __shfl_xor_sync(active, v, d);     // lanes outside `active` return their own value: harmless for max
+        v = o > v ? o : v;
+    }
+    return v;
+}
 __device__ __forceinline__ void note_node(SnapMeta* meta, int64_t cv, int64_t mv, int64_t gv) {
-    if (gv < 0) atomicOr(&meta->flags, kSnapGpuNegative);
-    if (cv > 0 && cv > meta->max_avail[0]) atomicMax(&meta->max_avail[0], (long long)cv);
-    if (mv > 0 && mv > meta->max_avail[1]) atomicMax(&meta->max_avail[1], (long long)mv);
-    if (gv > 0 && gv > meta->max_avail[2]) atomicMax(&meta->max_avail[2], (long long)gv);
+    const unsigned active = __activemask();
+    const bool full = active == 0xffffffffu;
+    if (__any_sync(active, gv < 0) && (threadIdx.x & 31) == (__ffs(active) - 1)) atomicOr(&meta->flags, kSnapGpuNegative);
+    long long c = cv, m = mv, g = gv;
+    if (full) { c = warp_max_ll(active, c); m = warp_max_ll(active, m); g = warp_max_ll(active, g); }
+    if (!full || (threadIdx.x & 31) == 0) {
+        if (c > 0 && c > meta->max_avail[0]) atomicMax(&meta->max_avail[0], c);
+        if (m > 0 && m > meta->max_avail[1]) atomicMax(&meta->max_avail[1], m);
+        if (g > 0 && g > meta->max_avail[2]) atomicMax(&meta->max_avail[2], g);
+    }
 }
 
 // executor-order entries -> slots [sbase, sbase+ne)
@@ -233,24 +263,24 @@ __global__ void gp_multi_copy(CopyJobs jobs) {
     }
 }
 
-// After the slots are laid out: the shifts of the compact view (smallest S with max_avail >> S < 2^32) ...
-__global__ void gp_snapshot_shifts(SnapMeta* __restrict__ meta) {
-    if (threadIdx.x < 2) {
-        const long long mx = meta->max_avail[threadIdx.x];
-        int sft = 0;
-        if (mx > 0) { const int bits = 64 - __clzll(mx); sft = bits > 32 ? bits - 32 : 0; }
-        meta->shift32[threadIdx.x] = sft;
-    }
+// After the slots are laid out: the compact view, 8 bytes per slot instead of 16 (negative availability -> 0:
+// capacity 0 either way).  Its shifts are the smallest S with max_avail >> S < 2^32; every thread derives them
+// from SnapMeta::max_avail, thread 0 publishes them for gp_prep_apps.
+__device__ __forceinline__ int shift_for(long long mx) {
+    if (mx <= 0) return 0;
+    const int bits = 64 - __clzll(mx);
+    return bits > 32 ? bits - 32 : 0;
 }
-// ... and the view itself: 8 bytes per slot instead of 16 (negative availability -> 0: capacity 0 either way)
-__global__ void gp_fill_pair32(int32_t n_slots, const longlong2* __restrict__ pair, const SnapMeta* __restrict__ meta,
+__global__ void gp_fill_pair32(int32_t n_slots, const longlong2* __restrict__ pair, SnapMeta* __restrict__ meta,
                                uint2* __restrict__ pair32) {
+    const int s0 = shift_for(meta->max_avail[0]), s1 = shift_for(meta->max_avail[1]);
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { meta->shift32[0] = s0; meta->shift32[1] = s1; }
     if (i >= n_slots) return;
     const longlong2 v = pair[i];
     uint2 o;
-    o.x = v.x < 0 ? 0u : (uint32_t)((unsigned long long)v.x >> meta->shift32[0]);
-    o.y = v.y < 0 ? 0u : (uint32_t)((unsigned long long)v.y >> meta->shift32[1]);
+    o.x = v.x < 0 ? 0u : (uint32_t)((unsigned long long)v.x >> s0);
+    o.y = v.y < 0 ? 0u : (uint32_t)((unsigned long long)v.y >> s1);
     pair32[i] = o;
 }
 
@@ -512,11 +542,7 @@ static gp_status build_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_
             n_drv, dn->n_groups, dn->exec_off, dn->drv_off, dn->drv_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
             dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
             c->node_slot.as<int32_t>(), c->drv_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
-    // spare slots that stay unused must read as "nothing available" in both views
-    GP_CUDA(c, cudaMemsetAsync(c->pair32.p, 0, sizeof(uint2) * (size_t)(n_slots + 1), st));
-    gp_snapshot_shifts<<<1, 32, 0, st>>>(c->snap_flags.as<SnapMeta>());
-    if (n_slots > 0)
-        gp_fill_pair32<<<(n_slots + T - 1) / T, T, 0, st>>>(n_slots, c->pair.as<longlong2>(), c->snap_flags.as<SnapMeta>(), c->pair32.as<uint2>());
+    gp_fill_pair32<<<(n_slots + T) / T, T, 0, st>>>(n_slots, c->pair.as<longlong2>(), c->snap_flags.as<SnapMeta>(), c->pair32.as<uint2>());
     GP_CUDA(c, cudaGetLastError());
     c->n_nodes = dn->n_nodes; c->n_groups = dn->n_groups; c->n_exec = n_exec; c->n_drv = n_drv; c->n_slots = n_slots;
     c->have_snapshot = true;
@@ -709,7 +735,7 @@ static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(c->dev_misc.as<char>() + 8);
     PrepApp* prep = c->prep.as<PrepApp>() + lo;
     unsigned int* next_app = reinterpret_cast<unsigned int*>(c->dev_misc.as<char>() + kMiscCounters) + chunk;
-    const int T = 256;
+    const int T = kPrepThreads;
     if (mode != GP_MODE_INDEPENDENT) {
         GP_CUDA(c, c->gmin.reserve(sizeof(GroupMin) * (size_t)c->n_groups));
         GP_CUDA(c, cudaMemsetAsync(c->gmin.p, 0x7f, sizeof(GroupMin) * (size_t)c->n_groups, st));   // +inf-ish
