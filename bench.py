@@ -43,6 +43,9 @@ WORKLOADS = {
                         desc="10k nodes x 10k pending apps, tightly-pack, independent (BASELINE configs[1])"),
     "evenly-100k": dict(nodes=10000, apps=100000, algo=1, mode=0, groups=1,
                         desc="10k nodes x 100k pending apps, distribute-evenly, independent (BASELINE configs[2])"),
+    "minfrag-100k": dict(nodes=10000, apps=100000, algo=2, mode=0, groups=1,
+                         desc="10k nodes x 100k pending apps, minimal-fragmentation (the per-zone packer of "
+                              "single-az-minimal-fragmentation), independent; every decision is several full passes over the nodes"),
     "fifo-10k": dict(nodes=10000, apps=10000, algo=0, mode=1, groups=1,
                      desc="10k nodes x 10k pending apps, tightly-pack, FIFO (reference usage accounting), 1 instance group"),
     "fifo-da-50k": dict(nodes=10000, apps=50000, algo=0, mode=1, groups=16, da=True,
@@ -50,7 +53,8 @@ WORKLOADS = {
     "tightly-50k-1m": dict(nodes=50000, apps=125000, algo=0, mode=0, groups=1,
                            desc="50k nodes x 1M pending apps over 8 GPUs (125k per GPU), tightly-pack (BASELINE configs[4])"),
 }
-ALGO_NAME = {0: "tightly-pack", 1: "distribute-evenly"}
+ALGO_NAME = {0: "tightly-pack", 1: "distribute-evenly", 2: "minimal-fragmentation"}
+ORC_ALGO = {0: 0, 1: 1, 2: 4}      # gp_algo -> oracle algo id (oracle/gangpack_oracle.h)
 MODE_NAME = {0: "independent", 1: "fifo-reference", 2: "fifo-exact"}
 APP_KEYS = ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count", "group", "young")
 
@@ -133,13 +137,13 @@ def cpu_reference_run(w: dict, sample_apps: int, threads: int, repeats: int = 1)
         for _ in range(repeats):
             if w["mode"] == 0:
                 t0 = time.perf_counter()
-                cl.binpack_batch(w["algo"], drv, exe, count, onames, onames, with_efficiencies=True, n_threads=threads)
+                cl.binpack_batch(ORC_ALGO[w["algo"]], drv, exe, count, onames, onames, with_efficiencies=True, n_threads=threads)
                 times.append(time.perf_counter() - t0)
             else:
                 cl = orc.Cluster(names, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"],
                                  sched=(nodes["alloc_cpu"], nodes["alloc_mem"], nodes["alloc_gpu"]))
                 t0 = time.perf_counter()
-                cl.fifo(w["algo"], w["mode"], drv, exe, count, a["young"][:q], onames, onames, with_efficiencies=True)
+                cl.fifo(ORC_ALGO[w["algo"]], w["mode"], drv, exe, count, a["young"][:q], onames, onames, with_efficiencies=True)
                 times.append(time.perf_counter() - t0)
         used_threads = threads if w["mode"] == 0 else 1
     else:
@@ -152,9 +156,9 @@ def cpu_reference_run(w: dict, sample_apps: int, threads: int, repeats: int = 1)
             cl = orc.Cluster(sub_names, nodes["avail_cpu"][order], nodes["avail_mem"][order], nodes["avail_gpu"][order],
                              sched=(nodes["alloc_cpu"][order], nodes["alloc_mem"][order], nodes["alloc_gpu"][order]))
             if w["mode"] == 0:
-                cl.binpack_batch(w["algo"], drv[sel], exe[sel], count[sel], sub_names, sub_names, True, 1)
+                cl.binpack_batch(ORC_ALGO[w["algo"]], drv[sel], exe[sel], count[sel], sub_names, sub_names, True, 1)
             else:
-                cl.fifo(w["algo"], w["mode"], drv[sel], exe[sel], count[sel], a["young"][:q][sel], sub_names, sub_names, True)
+                cl.fifo(ORC_ALGO[w["algo"]], w["mode"], drv[sel], exe[sel], count[sel], a["young"][:q][sel], sub_names, sub_names, True)
         used_threads = min(threads, w["groups"])
         for _ in range(repeats):
             t0 = time.perf_counter()

@@ -9,8 +9,8 @@ Layout:
   go/            the cgo shim a reference maintainer would add (source only; no Go toolchain here)
 """
 from . import native, synth  # noqa: F401
-from .native import (DISTRIBUTE_EVENLY, MODE_FIFO_EXACT, MODE_FIFO_REFERENCE, MODE_INDEPENDENT,  # noqa: F401
+from .native import (DISTRIBUTE_EVENLY, MINIMAL_FRAGMENTATION, MODE_FIFO_EXACT, MODE_FIFO_REFERENCE, MODE_INDEPENDENT,  # noqa: F401
                      TIGHTLY_PACK, GangPacker, GangpackError)
 
-__all__ = ["native", "synth", "GangPacker", "GangpackError", "TIGHTLY_PACK", "DISTRIBUTE_EVENLY",
+__all__ = ["native", "synth", "GangPacker", "GangpackError", "TIGHTLY_PACK", "DISTRIBUTE_EVENLY", "MINIMAL_FRAGMENTATION",
            "MODE_INDEPENDENT", "MODE_FIFO_REFERENCE", "MODE_FIFO_EXACT"]

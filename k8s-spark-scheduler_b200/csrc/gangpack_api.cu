@@ -3,6 +3,7 @@
 #include "gangpack.h"
 #include "gangpack_kernels.cuh"
 #include "gangpack_fifo.cuh"
+#include "gangpack_minfrag.cuh"
 #include "gangpack_sort.cuh"
 
 #include <algorithm>
@@ -119,7 +120,7 @@ template <int ALGO>
 #ifndef GP_PACK_MIN_BLOCKS
 #define GP_PACK_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(kPackThreads, GP_PACK_MIN_BLOCKS) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+__global__ void __launch_bounds__(kPackThreads, ALGO == 2 ? 2 : GP_PACK_MIN_BLOCKS) gp_pack_independent(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
                                                                     int32_t* __restrict__ driver_node,
                                                                     int32_t* __restrict__ executor_nodes,
                                                                     int2* __restrict__ scratch,
@@ -143,7 +144,15 @@ __global__ void __launch_bounds__(kPackThreads, GP_PACK_MIN_BLOCKS) gp_pack_inde
         if (lane == 0 && n1 < (unsigned int)n_apps) asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + n1));
         const PrepApp* pa = prep + i;
         int32_t d = -1;
-        if (!(pa->flags & kAppInvalid)) d = pack_app<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+        if (!(pa->flags & kAppInvalid)) {
+            if constexpr (ALGO == 2) {       // minimal-fragmentation: multi-pass, see gangpack_minfrag.cuh
+                const bool gpu_idle = !(pa->flags & kAppUsesGpu) && !(snap_flags & kSnapGpuNegative);
+                d = ((pa->flags & kAppFast32) && gpu_idle) ? pack_app_minfrag<true>(s, pa, executor_nodes, scratch, st, lane, snap_flags)
+                                                           : pack_app_minfrag<false>(s, pa, executor_nodes, scratch, st, lane, snap_flags);
+            } else {
+                d = pack_app<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+            }
+        }
         if (lane == 0) driver_node[i] = d;
         i = n1;
         n1 = __shfl_sync(kFull, n2, 0);
@@ -357,7 +366,7 @@ struct gp_ctx {
                                                   // 15-33 GB/s depending on the host -> in-place reads are the steadier default
     int chunk_apps = kChunkApps;                  // GANGPACK_CHUNK_APPS
     int trace = 0;                                // GANGPACK_TRACE=1: host-side phase timing on stderr
-    int pack_ctas_per_sm[2] = {0, 0};             // occupancy of gp_pack_independent<ALGO> on this device
+    int pack_ctas_per_sm[3] = {0, 0, 0};            // occupancy of gp_pack_independent<ALGO> on this device
     bool fifo_attr_set[2] = {false, false};       // dynamic shared-memory opt-in of gp_pack_fifo_cta<ALGO,*> done on this device
 
     gp_stats last{};
@@ -708,7 +717,7 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
         if (blocks < 1) blocks = 1;
         gp_pack_independent<ALGO><<<(int)blocks, kPackThreads, 0, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch,
                                                                        stats, next_app);
-    } else {
+    } else if constexpr (ALGO != 2) {     // (check_args rejects the FIFO modes for minimal-fragmentation)
         // FIFO: one persistent 1024-thread CTA per instance group, its slots staged in shared memory
         bool& attr_set = c->fifo_attr_set[ALGO];     // per device: function attributes live in the device's context
         if (!attr_set) {
@@ -752,6 +761,8 @@ static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
     if (algo == GP_TIGHTLY_PACK)
         launch_pack<0>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
+    else if (algo == GP_MINIMAL_FRAGMENTATION)
+        launch_pack<2>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
     else
         launch_pack<1>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
     GP_CUDA(c, cudaGetLastError());
@@ -769,7 +780,7 @@ static gp_status pack_begin(gp_ctx* c, int32_t q, gp_algo algo, const gp_results
     *scratch = nullptr;
     if (q == 0) return GP_OK;
     GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));
-    if (algo == GP_DISTRIBUTE_EVENLY) {
+    if (algo != GP_TIGHTLY_PACK) {        // candidate list (distribute-evenly) / consumed-node list (minimal-fragmentation)
         GP_CUDA(c, c->scratch.reserve(sizeof(int2) * (size_t)(dout->executor_nodes_cap + 1)));
         *scratch = c->scratch.as<int2>();
     }
@@ -789,7 +800,11 @@ static gp_status pack_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode
 static gp_status check_args(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, const gp_results* out, const char* who) {
     if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, std::string(who) + ": gp_set_snapshot first");
     if (!a || !out || a->n_apps < 0) return fail(c, GP_ERR_INVALID, std::string(who) + ": NULL apps/results");
-    if (algo != GP_TIGHTLY_PACK && algo != GP_DISTRIBUTE_EVENLY) return fail(c, GP_ERR_INVALID, std::string(who) + ": unknown algo");
+    if (algo != GP_TIGHTLY_PACK && algo != GP_DISTRIBUTE_EVENLY && algo != GP_MINIMAL_FRAGMENTATION)
+        return fail(c, GP_ERR_INVALID, std::string(who) + ": unknown algo");
+    if (algo == GP_MINIMAL_FRAGMENTATION && mode != GP_MODE_INDEPENDENT)
+        return fail(c, GP_ERR_INVALID, std::string(who) + ": minimal-fragmentation is offered in GP_MODE_INDEPENDENT only "
+                                                          "(its one registered caller, single-az-minimal-fragmentation, chooses a zone per application on the host)");
     if (mode != GP_MODE_INDEPENDENT && mode != GP_MODE_FIFO_REFERENCE && mode != GP_MODE_FIFO_EXACT)
         return fail(c, GP_ERR_INVALID, std::string(who) + ": unknown mode");
     if (a->n_apps > 0 && (!a->drv_cpu_milli || !a->drv_mem_bytes || !a->exe_cpu_milli || !a->exe_mem_bytes || !a->exe_count ||

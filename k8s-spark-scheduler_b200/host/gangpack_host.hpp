@@ -242,6 +242,12 @@ inline const SparkBinPackFunction DistributeEvenly = [](const resources::Resourc
                                                         const resources::NodeGroupSchedulingMetadata& md) {
     return gangpack::PackOne(GP_DISTRIBUTE_EVENLY, d, e, c, dord, eord, md);
 };
+// binpack.MinimalFragmentation (minimal_fragmentation.go:27-35)
+inline const SparkBinPackFunction MinimalFragmentation = [](const resources::Resources& d, const resources::Resources& e, int c,
+                                                            const std::vector<std::string>& dord, const std::vector<std::string>& eord,
+                                                            const resources::NodeGroupSchedulingMetadata& md) {
+    return gangpack::PackOne(GP_MINIMAL_FRAGMENTATION, d, e, c, dord, eord, md);
+};
 }  // namespace binpack
 
 // ------------------------------------------------------------------------------------------------
@@ -326,12 +332,14 @@ inline void groupNodesByZone(const std::vector<std::string>& nodeNames, const re
     }
 }
 
-// getSingleAZSparkBinFunction(tightlyPackExecutors) + chooseBestResult, single_az.go:23-55,75-97:
-// every candidate zone is packed in ONE device batch (zone = instance group), the best result is chosen on
-// the host by average packing efficiency over [driver] + ExecutorNodes.
-inline PackingResult SingleAZTightlyPackImpl(const resources::Resources& drv, const resources::Resources& exe, int count,
-                                             const std::vector<std::string>& driverOrder, const std::vector<std::string>& executorOrder,
-                                             const resources::NodeGroupSchedulingMetadata& md) {
+// getSingleAZSparkBinFunction(fn) + chooseBestResult, single_az.go:23-55,75-97, fn = tightlyPackExecutors or
+// minimalFragmentation: every candidate zone is packed in ONE device batch (zone = instance group), the best result
+// is chosen on the host by average packing efficiency over [driver] + ExecutorNodes.  The efficiencies come from
+// SparkBinPack's `reserved` map (binpack.go:72-77): tightlyPackExecutors adds every executor to it,
+// minimalFragmentation never touches it -> for that packer the map holds the driver only (kept as is).
+inline PackingResult SingleAZPackImpl(gp_algo algo, const resources::Resources& drv, const resources::Resources& exe, int count,
+                                      const std::vector<std::string>& driverOrder, const std::vector<std::string>& executorOrder,
+                                      const resources::NodeGroupSchedulingMetadata& md) {
     std::vector<std::string> dzOrder, ezOrder;
     std::unordered_map<std::string, std::vector<std::string>> dz, ez;
     groupNodesByZone(driverOrder, md, &dzOrder, &dz);
@@ -355,7 +363,7 @@ inline PackingResult SingleAZTightlyPackImpl(const resources::Resources& drv, co
     a.exe_count = cnt.data(); a.group = grp.data(); a.exec_out_off = off.data();
     gp_results r{};
     r.driver_node = driver.data(); r.executor_nodes = exec.data(); r.executor_nodes_cap = (int64_t)exec.size();
-    d.check(gp_pack_batch(d.ctx(), &a, GP_TIGHTLY_PACK, GP_MODE_INDEPENDENT, &r), "gp_pack_batch");
+    d.check(gp_pack_batch(d.ctx(), &a, algo, GP_MODE_INDEPENDENT, &r), "gp_pack_batch");
     PackingResult best = EmptyPackingResult();                                      // :79
     AvgPackingEfficiency bestAvg = WorstAvgPackingEfficiency();                     // :80
     for (size_t z = 0; z < Z; ++z) {
@@ -364,7 +372,9 @@ inline PackingResult SingleAZTightlyPackImpl(const resources::Resources& drv, co
         res.HasCapacity = true;
         res.DriverNode = d.name(driver[z]);
         for (int64_t t = off[z]; t < off[z + 1]; ++t) res.ExecutorNodes.push_back(d.name(exec[(size_t)t]));
-        auto reserved = ReservedOf(drv, exe, res);
+        resources::NodeGroupResources reserved;
+        if (algo == GP_MINIMAL_FRAGMENTATION) reserved[res.DriverNode] = drv;
+        else reserved = ReservedOf(drv, exe, res);
         std::vector<PackingEfficiency> effs;                                        // :83-89: [driver] + executors, duplicates kept
         effs.push_back(computePackingEfficiency(res.DriverNode, md.at(res.DriverNode), reserved));
         for (const auto& n : res.ExecutorNodes) effs.push_back(computePackingEfficiency(n, md.at(n), reserved));
@@ -376,10 +386,10 @@ inline PackingResult SingleAZTightlyPackImpl(const resources::Resources& drv, co
 
 inline PackingResult GuardedSingleAZ(bool azAware, const resources::Resources& d, const resources::Resources& e, int c,
                                      const std::vector<std::string>& dord, const std::vector<std::string>& eord,
-                                     const resources::NodeGroupSchedulingMetadata& md) {
-    const int key = azAware ? 101 : 100;
+                                     const resources::NodeGroupSchedulingMetadata& md, gp_algo algo = GP_TIGHTLY_PACK) {
+    const int key = algo == GP_MINIMAL_FRAGMENTATION ? 102 : (azAware ? 101 : 100);
     try {
-        PackingResult r = SingleAZTightlyPackImpl(d, e, c, dord, eord, md);
+        PackingResult r = SingleAZPackImpl(algo, d, e, c, dord, eord, md);
         if (r.HasCapacity || !azAware) return r;
         return gangpack::PackOne(GP_TIGHTLY_PACK, d, e, c, dord, eord, md);          // az_aware_pack_tightly.go:33-37
     } catch (const gangpack::Error&) {
@@ -400,6 +410,12 @@ inline const SparkBinPackFunction AzAwareTightlyPack = [](const resources::Resou
                                                           const resources::NodeGroupSchedulingMetadata& md) {
     return GuardedSingleAZ(true, d, e, c, dord, eord, md);
 };
+// binpack.SingleAZMinimalFragmentation (single_az_minimal_fragmentation.go:20)
+inline const SparkBinPackFunction SingleAZMinimalFragmentation = [](const resources::Resources& d, const resources::Resources& e, int c,
+                                                                    const std::vector<std::string>& dord, const std::vector<std::string>& eord,
+                                                                    const resources::NodeGroupSchedulingMetadata& md) {
+    return GuardedSingleAZ(false, d, e, c, dord, eord, md, GP_MINIMAL_FRAGMENTATION);
+};
 
 }  // namespace binpack
 
@@ -417,27 +433,26 @@ inline const char* const tightlyPack = "tightly-pack";            // :23
 inline const char* const distributeEvenly = "distribute-evenly";  // :22
 inline const char* const azAwareTightlyPack = "az-aware-tightly-pack";      // :24
 inline const char* const SingleAzTightlyPack = "single-az-tightly-pack";    // :29
+inline const char* const SingleAzMinimalFragmentation = "single-az-minimal-fragmentation";   // :33
 
-// binpackFunctions (:43-49): the two packers of the hot path plus the zone-aware tightly-pack variants built
-// on them.  single-az-minimal-fragmentation is NOT provided: SelectBinpacker returns nullptr for it so the
-// embedding keeps the Go function.
+// binpackFunctions (:43-49): all five `binpack:` values.  `algo` is the device packer behind the function; the
+// zone-aware ones (needsHostLoop) choose a zone per application on the host, so the FIFO loop calls them per driver.
 inline const std::map<std::string, Binpacker>& binpackFunctions() {
     static const std::map<std::string, Binpacker> m = {
         {tightlyPack, {tightlyPack, binpack::TightlyPack, false, GP_TIGHTLY_PACK}},
         {distributeEvenly, {distributeEvenly, binpack::DistributeEvenly, false, GP_DISTRIBUTE_EVENLY}},
         {azAwareTightlyPack, {azAwareTightlyPack, binpack::AzAwareTightlyPack, false, GP_TIGHTLY_PACK}},
         {SingleAzTightlyPack, {SingleAzTightlyPack, binpack::SingleAZTightlyPack, true, GP_TIGHTLY_PACK}},
+        {SingleAzMinimalFragmentation, {SingleAzMinimalFragmentation, binpack::SingleAZMinimalFragmentation, true, GP_MINIMAL_FRAGMENTATION}},
     };
     return m;
 }
 
-inline bool IsReferenceOnlyPacker(const std::string& name) {
-    return name == "single-az-minimal-fragmentation";
-}
+// packers whose placement is not ONE device packer over ONE pair of orders (they pick a zone on the host)
+inline bool NeedsHostLoop(const Binpacker& b) { return b.Name != tightlyPack && b.Name != distributeEvenly; }
 
 // SelectBinpacker (:52-58): unknown names select distribute-evenly, exactly like the reference.
 inline const Binpacker* SelectBinpacker(const std::string& name) {
-    if (IsReferenceOnlyPacker(name)) return nullptr;
     auto it = binpackFunctions().find(name);
     if (it == binpackFunctions().end()) return &binpackFunctions().at(distributeEvenly);
     return &it->second;
@@ -575,6 +590,25 @@ inline bool FitEarlierDrivers(const binpacker::Binpacker& packer, const std::vec
         if (!drivers[i].ParseError) live.push_back(i);
     if (results) results->assign(drivers.size(), binpack::EmptyPackingResult());
     if (live.empty()) return true;
+    if (binpacker::NeedsHostLoop(packer)) {
+        // zone-aware packers: the reference's own loop (:230-259), every BinpackFunc call being one device batch over
+        // the zones; usage is subtracted on the host between calls (SubtractUsageIfExists, resources.go:129-135)
+        for (size_t i : live) {
+            const auto& a = drivers[i];
+            binpack::PackingResult pr = packer.BinpackFunc(a.Resources.DriverResources, a.Resources.ExecutorResources,
+                                                           a.Resources.MinExecutorCount, nodeNames, executorNodeNames, metadata);
+            if (!pr.HasCapacity) {
+                if (a.SkipIfNoFit) continue;                                   // :245-249
+                return false;                                                  // :250-252
+            }
+            for (const auto& u : SparkResourceUsage(a.Resources.DriverResources, a.Resources.ExecutorResources, pr.DriverNode, pr.ExecutorNodes)) {
+                auto m = metadata.find(u.first);
+                if (m != metadata.end()) m->second.AvailableResources.Sub(u.second);
+            }
+            if (results) (*results)[i] = pr;
+        }
+        return true;
+    }
     gangpack::Device& d = gangpack::Device::Get();
     d.SetSnapshot(metadata, nodeNames, executorNodeNames);
     const size_t q = live.size();

@@ -16,6 +16,7 @@
  *   node with cap >= r, in order, until `count` are placed.
  * driver loop (LIB/binpack/binpack.go:60-87): first d in driverOrder with !gt(drv, avail[d]) whose
  *   executor total  S0 - min(cap(d|0),k) + min(cap(d|drv),k)  reaches k.
+ * minimal-fragmentation (LIB/binpack/minimal_fragmentation.go:59-137): see minfrag_emit().
  *
  * Precondition (checked by the product API too): exec_order / driver_order hold no duplicates.
  */
@@ -52,6 +53,8 @@ static inline int64_t node_cap(const snap* s, int32_t n, const orc_res* r, const
     return c;
 }
 
+static void minfrag_emit(const snap* s, int32_t d, int64_t cd, const orc_res* exe, int32_t k, int32_t* out);
+
 /* returns driver node or -1; writes executor nodes (count entries) on success */
 static int32_t pack_one(const snap* s, int algo, const orc_res* drv, const orc_res* exe, int32_t k,
                         int32_t* executor_nodes) {
@@ -77,7 +80,9 @@ static int32_t pack_one(const snap* s, int algo, const orc_res* drv, const orc_r
     if (d < 0) return -1;
     int32_t placed = 0;
     if (k == 0) return d;
-    if (algo == ORC_TIGHTLY_PACK) {
+    if (algo == ORC_MINIMAL_FRAGMENTATION) {
+        minfrag_emit(s, s->in_exec[d] ? d : -1, cd, exe, k, executor_nodes);
+    } else if (algo == ORC_TIGHTLY_PACK) {
         for (int32_t i = 0; i < s->n_exec && placed < k; ++i) {
             int32_t n = s->exec_order[i];
             int64_t c = (n == d) ? cd : node_cap(s, n, &zero, exe);
@@ -94,6 +99,81 @@ static int32_t pack_one(const snap* s, int algo, const orc_res* drv, const orc_r
         }
     }
     return d;
+}
+
+/* minimal fragmentation (LIB/binpack/minimal_fragmentation.go:59-137) in closed form, for driver node d with
+ * cap(d|drv) = cd.  c(i) = UNCLAMPED capacity of the i-th executor candidate, nodes with c = 0 are filtered out.
+ *   M = max c.  If k < M: target = wrap64(k + M) / 2 and the subset S = {c < target} is tried first; it works iff
+ *   sum_S c >= k; otherwise (and when k >= M) the set is every node.  Within the chosen set:
+ *   - some c >= k: k executors on the node with the smallest such c (ties: earliest in the order);
+ *   - else nodes are consumed whole in (c descending, order ascending) while the remainder r >= c.  With
+ *     F(v) = sum of c over {c >= v}:  v* = max{v : F(v) > k}, every node with c > v* is consumed,
+ *     r* = k - F(v*+1); if v* < r*, the first m = floor(r* / v*) nodes with c == v* are consumed too; the rest
+ *     r' = r* - m v* (if any) goes to the node with the smallest c >= r' among the unconsumed ones (ties: earliest).
+ * The feasibility of a driver candidate is the same as for tightly-pack (sum c >= k), so the driver loop above
+ * is shared. */
+static void minfrag_emit(const snap* s, int32_t d, int64_t cd, const orc_res* exe, int32_t k, int32_t* out) {
+    static const orc_res zero = {0, 0, 0};
+    const int32_t ne = s->n_exec;
+    int64_t* c = (int64_t*)malloc(sizeof(int64_t) * (size_t)(ne > 0 ? ne : 1));
+    int64_t M = 0;
+    for (int32_t i = 0; i < ne; ++i) {
+        int32_t n = s->exec_order[i];
+        c[i] = (n == d) ? cd : node_cap(s, n, &zero, exe);
+        if (c[i] > M) M = c[i];
+    }
+    int64_t limit = CAP_INF;      /* the set is {0 < c <= limit} */
+    if ((int64_t)k < M) {
+        int64_t target = (int64_t)((uint64_t)k + (uint64_t)M) / 2;   /* Go int wraps; / truncates toward zero */
+        int64_t sum = 0;
+        for (int32_t i = 0; i < ne; ++i) if (c[i] > 0 && c[i] < target) sum += min64(c[i], k);
+        if (sum >= k) limit = target - 1;
+    }
+    /* smallest c >= k inside the set */
+    int32_t best = -1;
+    for (int32_t i = 0; i < ne; ++i)
+        if (c[i] >= k && c[i] <= limit && (best < 0 || c[i] < c[best])) best = i;
+    if (best >= 0) {
+        for (int32_t t = 0; t < k; ++t) out[t] = s->exec_order[best];
+        free(c);
+        return;
+    }
+    /* every c in the set is < k now */
+    int64_t U = 0, total = 0;
+    for (int32_t i = 0; i < ne; ++i) if (c[i] > 0 && c[i] <= limit) { total += c[i]; if (c[i] > U) U = c[i]; }
+    int64_t vstar = 0, Fhi = 0;   /* F(vstar + 1) */
+    if (total == k) { vstar = 0; Fhi = k; }
+    else {
+        int64_t lo = 1, hi = U;   /* F(lo) > k, F(hi + 1) <= k */
+        while (lo < hi) {
+            int64_t mid = lo + (hi - lo + 1) / 2, f = 0;
+            for (int32_t i = 0; i < ne; ++i) if (c[i] >= mid && c[i] <= limit) f += c[i];
+            if (f > k) lo = mid; else { hi = mid - 1; Fhi = f; }
+        }
+        vstar = lo;
+    }
+    int64_t r = k - Fhi, m = 0;
+    if (r > 0 && vstar < r) { m = r / vstar; r -= m * vstar; }
+    /* consumed nodes: offset = sum of larger capacities + c * (#equal capacities earlier in the order) */
+    int64_t seen_star = 0;
+    int32_t fin = -1;
+    for (int32_t i = 0; i < ne; ++i) {
+        if (c[i] <= 0 || c[i] > limit) continue;
+        int consumed = c[i] > vstar;
+        if (c[i] == vstar) { consumed = seen_star < m; ++seen_star; }
+        if (consumed) {
+            int64_t off = 0;
+            for (int32_t j = 0; j < ne; ++j) {
+                if (c[j] <= 0 || c[j] > limit) continue;
+                if (c[j] > c[i] || (c[j] == c[i] && j < i)) off += c[j];
+            }
+            for (int64_t t = 0; t < c[i]; ++t) out[off + t] = s->exec_order[i];
+        } else if (r > 0 && c[i] >= r && (fin < 0 || c[i] < c[fin])) {
+            fin = i;
+        }
+    }
+    for (int64_t t = 0; t < r; ++t) out[k - r + t] = s->exec_order[fin];
+    free(c);
 }
 
 typedef struct {

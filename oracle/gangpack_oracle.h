@@ -36,7 +36,10 @@ extern "C" {
 typedef struct { int64_t cpu, mem, gpu; } orc_res;
 
 /* 2, 3: LIB/binpack/single_az_pack_tightly.go + single_az.go:23-97, az_aware_pack_tightly.go:27-38 (literal oracle only) */
-enum { ORC_TIGHTLY_PACK = 0, ORC_DISTRIBUTE_EVENLY = 1, ORC_SINGLE_AZ_TIGHTLY_PACK = 2, ORC_AZ_AWARE_TIGHTLY_PACK = 3 };
+/* 4, 5: LIB/binpack/minimal_fragmentation.go:27-137 + LIB/capacity/capacity.go, single_az_minimal_fragmentation.go:20
+ *       (4 = MinimalFragmentation is also restated in closed form; 5 literal only) */
+enum { ORC_TIGHTLY_PACK = 0, ORC_DISTRIBUTE_EVENLY = 1, ORC_SINGLE_AZ_TIGHTLY_PACK = 2, ORC_AZ_AWARE_TIGHTLY_PACK = 3,
+       ORC_MINIMAL_FRAGMENTATION = 4, ORC_SINGLE_AZ_MINIMAL_FRAGMENTATION = 5 };
 /* FIFO accounting: 1 = the reference's sparkResourceUsage overwrite (EXT/sparkpods.go:139-146),
  *                  2 = exact sum (what separate Predicate calls converge to via UsageForNodes). */
 enum { ORC_FIFO_REFERENCE = 1, ORC_FIFO_EXACT = 2 };

@@ -70,7 +70,88 @@ def distribute_executors_evenly(exe, count, order, meta, reserved):
     return None, False
 
 
-DISTRIBUTORS = {"tightly-pack": tightly_pack_executors, "distribute-evenly": distribute_executors_evenly}
+MAX_INT = (1 << 63) - 1
+
+
+def _go_int(v):
+    """wrap to Go's 64-bit int"""
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _capacity_single_dimension(available, reserved, required):
+    """getCapacityAgainstSingleDimension, LIB/capacity/capacity.go:50-68."""
+    if reserved > available:
+        return 0
+    if required == 0:
+        return MAX_INT
+    return (available - reserved) // required
+
+
+def node_capacities(order, meta, reserved, exe):
+    """GetNodeCapacities, LIB/capacity/capacity.go:71-101 -> [(name, capacity)] in order."""
+    out = []
+    for n in order:
+        if n in meta:
+            r = reserved.get(n, ZERO)
+            out.append((n, min(_capacity_single_dimension(meta[n][d], r[d], exe[d]) for d in range(3))))
+    return out
+
+
+def _search(caps, pred):
+    """sort.Search: smallest index with pred true (pred monotone), len(caps) if none."""
+    lo, hi = 0, len(caps)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if pred(caps[mid]):
+            hi = mid
+        else:
+            lo = mid + 1
+    return lo
+
+
+def _internal_minimal_fragmentation(count, caps):
+    """internalMinimalFragmentation, LIB/binpack/minimal_fragmentation.go:97-137."""
+    caps = list(caps)
+    out = []
+    while caps:
+        position = _search(caps, lambda c: c[1] >= count)
+        if position != len(caps):
+            return out + [caps[position][0]] * count, True
+        max_capacity = caps[-1][1]
+        first_max = _search(caps, lambda c: c[1] >= max_capacity)
+        pos = first_max
+        while count >= max_capacity and pos < len(caps):
+            out += [caps[pos][0]] * max_capacity
+            count -= max_capacity
+            pos += 1
+        if count == 0:
+            return out, True
+        caps = caps[:first_max] + caps[pos:]
+    return None, False
+
+
+def minimal_fragmentation(exe, count, order, meta, reserved):
+    """minimalFragmentation, LIB/binpack/minimal_fragmentation.go:59-95 (does not touch `reserved`)."""
+    if count == 0:
+        return [], True
+    caps = [c for c in node_capacities(order, meta, reserved, exe) if c[1] > 0]
+    if not caps:
+        return None, False
+    caps.sort(key=lambda c: c[1])  # list.sort is stable, like sort.SliceStable
+    max_capacity = caps[-1][1]
+    if count < max_capacity:
+        wrapped = _go_int(count + max_capacity)
+        target = -((-wrapped) // 2) if wrapped < 0 else wrapped // 2  # Go integer division truncates toward zero
+        first = _search(caps, lambda c: c[1] >= target)
+        nodes, ok = _internal_minimal_fragmentation(count, caps[:first])
+        if ok:
+            return nodes, True
+    return _internal_minimal_fragmentation(count, caps)
+
+
+DISTRIBUTORS = {"tightly-pack": tightly_pack_executors, "distribute-evenly": distribute_executors_evenly,
+                "minimal-fragmentation": minimal_fragmentation}
 
 
 def spark_bin_pack(drv, exe, count, driver_order, exec_order, meta, distribute):
@@ -263,23 +344,31 @@ def group_nodes_by_zone(order, meta, zones):
     return in_order, by_zone
 
 
-def single_az_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched, zones):
-    """getSingleAZSparkBinFunction(tightlyPackExecutors) + chooseBestResult, single_az.go:23-55,75-97."""
+def single_az_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched, zones, distribute=None):
+    """getSingleAZSparkBinFunction(fn) + chooseBestResult, single_az.go:23-55,75-97 (fn: tightlyPackExecutors unless given)."""
+    distribute = distribute or tightly_pack_executors
     dz_order, dz = group_nodes_by_zone(driver_order, meta, zones)
     _, ez = group_nodes_by_zone(exec_order, meta, zones)
     best, best_max = (None, [], False), 0.0
     for z in dz_order:
         if z not in ez:
             continue
-        d, nodes, ok = spark_bin_pack(drv, exe, count, dz[z], ez[z], meta, tightly_pack_executors)
+        d, nodes, ok = spark_bin_pack(drv, exe, count, dz[z], ez[z], meta, distribute)
         if not ok:
             continue
-        reserved = _reserved_of(drv, exe, d, nodes)
+        # the efficiencies come from SparkBinPack's `reserved` map (binpack.go:72-77): tightly-pack adds every
+        # executor to it, minimalFragmentation never does -> driver only
+        reserved = {d: drv} if distribute is minimal_fragmentation else _reserved_of(drv, exe, d, nodes)
         effs = [compute_packing_efficiency(meta[n], sched[n], reserved.get(n)) + (sched[n][2],) for n in [d] + nodes]
         avg = avg_packing_efficiency(effs)
         if best_max < avg[3]:
             best, best_max = (d, nodes, True), avg[3]
     return best
+
+
+def single_az_minimal_fragmentation(drv, exe, count, driver_order, exec_order, meta, sched, zones):
+    """SingleAZMinimalFragmentation, LIB/binpack/single_az_minimal_fragmentation.go:20."""
+    return single_az_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched, zones, minimal_fragmentation)
 
 
 def az_aware_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched, zones):

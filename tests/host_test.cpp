@@ -72,7 +72,8 @@ static void TestSelectBinpacker() {   // internal/binpacker/binpack.go:52-58
     EXPECT(!binpacker::SelectBinpacker("tightly-pack")->IsSingleAz, "IsSingleAz false");
     EXPECT(binpacker::SelectBinpacker("single-az-tightly-pack")->IsSingleAz, "single-az-tightly-pack is a single-AZ packer (demands.go:169 reads this)");
     EXPECT(!binpacker::SelectBinpacker("az-aware-tightly-pack")->IsSingleAz, "az-aware-tightly-pack is not");
-    EXPECT(binpacker::SelectBinpacker("single-az-minimal-fragmentation") == nullptr, "packers not provided stay with the Go function");
+    EXPECT(binpacker::SelectBinpacker("single-az-minimal-fragmentation")->IsSingleAz, "single-az-minimal-fragmentation is a single-AZ packer (binpack.go:48)");
+    EXPECT(binpacker::binpackFunctions().size() == 5, "all five binpack: values are served (binpack.go:43-49)");
 }
 
 static void TestExecutorNodeOrder() {   // SURVEY App. A.5 V1 / V3 (tests/golden/hotpath_vectors.json)
@@ -185,7 +186,7 @@ static void TestHarnessThroughSingleAz() {
     NodeGroupSchedulingMetadata md;
     md["node1"] = NewNode("zone1"); md["node2"] = NewNode("zone1");
     Names n = {"node1", "node2"};
-    for (const char* name : {"single-az-tightly-pack", "az-aware-tightly-pack"}) {
+    for (const char* name : {"single-az-tightly-pack", "az-aware-tightly-pack", "single-az-minimal-fragmentation"}) {
         const binpacker::Binpacker* bp = binpacker::SelectBinpacker(name);
         EXPECT(bp->BinpackFunc(CreateResources(1000, 1, 1), CreateResources(1000, 1, 0), 2, n, n, md).HasCapacity,
                "TestScheduler: there should be enough capacity to schedule the full application");
@@ -226,7 +227,7 @@ static void TestZoneGoldens() {   // tests/golden/hotpath_vectors.json zone_case
     EXPECT(z3a.HasCapacity && z3a.DriverNode == "a1" && z3a.ExecutorNodes == Names({"a1", "a1"}), "Z3: az-aware falls back to tightly-pack");
 }
 
-// random multi-zone clusters: the device-backed host layer vs the literal CPU oracle, all four packers
+// random multi-zone clusters: the device-backed host layer vs the literal CPU oracle, all five packers + plain min-frag
 static void TestRandomAgainstOracle() {
     std::mt19937_64 rng(20260922);
     auto U = [&](int64_t lo, int64_t hi) { return (int64_t)(lo + (int64_t)(rng() % (uint64_t)(hi - lo + 1))); };
@@ -255,13 +256,15 @@ static void TestRandomAgainstOracle() {
                                           cz.data(), nullptr, nullptr);
         for (int rep = 0; rep < 4; ++rep) {
             orc_res drv = {U(0, 2) * 500, U(0, 2) * (Gi / 2), U(0, 1)}, exe = {U(1, 4) * 500, U(1, 8) * (Gi / 4), U(0, 1)};
-            int k = (int)U(0, 9);
-            const char* algos[4] = {"tightly-pack", "distribute-evenly", "single-az-tightly-pack", "az-aware-tightly-pack"};
-            for (int algo = 0; algo < 4; ++algo) {
+            int k = (int)U(0, rep == 3 ? 30 : 9);
+            const char* algos[6] = {"tightly-pack", "distribute-evenly", "single-az-tightly-pack", "az-aware-tightly-pack",
+                                    "minimal-fragmentation", "single-az-minimal-fragmentation"};   // index = oracle algo id
+            for (int algo = 0; algo < 6; ++algo) {
                 int32_t od = -1; std::vector<int32_t> oe((size_t)std::max(k, 1)); double eff[4];
                 int ok = orc_binpack(cl, algo, &drv, &exe, k, co.data(), n, co.data(), n, 1, &od, oe.data(), eff);
-                auto r = binpacker::SelectBinpacker(algos[algo])->BinpackFunc(CreateResources(drv.cpu, drv.mem, drv.gpu),
-                                                                             CreateResources(exe.cpu, exe.mem, exe.gpu), k, order, order, md);
+                const binpack::SparkBinPackFunction& fn = algo == ORC_MINIMAL_FRAGMENTATION ? binpack::MinimalFragmentation
+                                                                                            : binpacker::SelectBinpacker(algos[algo])->BinpackFunc;
+                auto r = fn(CreateResources(drv.cpu, drv.mem, drv.gpu), CreateResources(exe.cpu, exe.mem, exe.gpu), k, order, order, md);
                 bool same = (r.HasCapacity == (ok != 0));
                 if (same && ok) {
                     same = r.DriverNode == names[(size_t)od] && (int)r.ExecutorNodes.size() == k;
@@ -277,11 +280,78 @@ static void TestRandomAgainstOracle() {
     std::printf("compared %d placements against the oracle\n", compared);
 }
 
+// fitEarlierDrivers with the zone-aware packers (resource.go:224-262 calling single_az.go per driver): host loop over
+// device-packed zones vs orc_fifo on the string-keyed oracle, incl. the metadata the loop leaves behind
+static void TestZoneAwareFifoAgainstOracle() {
+    std::mt19937_64 rng(777);
+    auto U = [&](int64_t lo, int64_t hi) { return (int64_t)(lo + (int64_t)(rng() % (uint64_t)(hi - lo + 1))); };
+    const int ids[3] = {ORC_SINGLE_AZ_TIGHTLY_PACK, ORC_AZ_AWARE_TIGHTLY_PACK, ORC_SINGLE_AZ_MINIMAL_FRAGMENTATION};
+    const char* names_of[3] = {"single-az-tightly-pack", "az-aware-tightly-pack", "single-az-minimal-fragmentation"};
+    for (int trial = 0; trial < 12; ++trial) {
+        const int n = (int)U(3, 24), q = 10;
+        std::vector<std::string> names, zones;
+        std::vector<int64_t> cpu, mem, gpu, scpu, smem, sgpu;
+        for (int i = 0; i < n; ++i) {
+            char buf[16]; std::snprintf(buf, sizeof buf, "n%02d", i);
+            int64_t sc = U(4, 16) * 1000, sm = U(8, 32) * Gi;
+            names.push_back(buf); zones.push_back("z" + std::to_string(U(0, 2)));
+            cpu.push_back(U(0, sc / 500) * 500); mem.push_back(U(0, sm / Gi) * Gi); gpu.push_back(0);
+            scpu.push_back(sc); smem.push_back(sm); sgpu.push_back(0);
+        }
+        Names order = names;
+        std::shuffle(order.begin(), order.end(), rng);
+        std::vector<const char*> cn, cz, co;
+        for (auto& s2 : names) cn.push_back(s2.c_str());
+        for (auto& s2 : zones) cz.push_back(s2.c_str());
+        for (auto& s2 : order) co.push_back(s2.c_str());
+        std::vector<orc_res> drv((size_t)q), exe((size_t)q);
+        std::vector<int32_t> cnt((size_t)q);
+        std::vector<uint8_t> young((size_t)q);
+        std::vector<int64_t> off((size_t)q + 1, 0);
+        std::vector<extender::PendingDriver> queue((size_t)q);
+        for (int i = 0; i < q; ++i) {
+            drv[(size_t)i] = {U(0, 2) * 500, U(0, 2) * Gi, 0}; exe[(size_t)i] = {U(1, 4) * 500, U(1, 4) * Gi, 0};
+            cnt[(size_t)i] = (int32_t)U(0, 6); young[(size_t)i] = (uint8_t)(U(0, 3) != 0);
+            off[(size_t)i + 1] = off[(size_t)i] + cnt[(size_t)i];
+            auto& a = queue[(size_t)i];
+            a.Resources.DriverResources = CreateResources(drv[(size_t)i].cpu, drv[(size_t)i].mem, 0);
+            a.Resources.ExecutorResources = CreateResources(exe[(size_t)i].cpu, exe[(size_t)i].mem, 0);
+            a.Resources.MinExecutorCount = cnt[(size_t)i]; a.SkipIfNoFit = young[(size_t)i] != 0;
+        }
+        for (int p = 0; p < 3; ++p) {
+            NodeGroupSchedulingMetadata md;
+            for (int i = 0; i < n; ++i) md[names[(size_t)i]] = Node(cpu[(size_t)i], mem[(size_t)i], 0, scpu[(size_t)i], smem[(size_t)i], 0, zones[(size_t)i]);
+            orc_cluster* cl = orc_cluster_new(n, cn.data(), cpu.data(), mem.data(), gpu.data(), scpu.data(), smem.data(), sgpu.data(),
+                                              cz.data(), nullptr, nullptr);
+            std::vector<int32_t> od((size_t)q, -9), oe((size_t)std::max<int64_t>(off[(size_t)q], 1), -1);
+            int32_t blocked = orc_fifo(cl, ids[p], ORC_FIFO_REFERENCE, q, drv.data(), exe.data(), cnt.data(), young.data(),
+                                       co.data(), n, co.data(), n, 0, off.data(), od.data(), oe.data());
+            std::vector<binpack::PackingResult> res;
+            bool ok = extender::FitEarlierDrivers(*binpacker::SelectBinpacker(names_of[p]), queue, order, order, md, &res);
+            bool same = ok == (blocked < 0);
+            for (int i = 0; same && i < q; ++i) {
+                if (od[(size_t)i] < 0) { same = !res[(size_t)i].HasCapacity; continue; }
+                same = res[(size_t)i].HasCapacity && res[(size_t)i].DriverNode == names[(size_t)od[(size_t)i]];
+                for (int t = 0; same && t < cnt[(size_t)i]; ++t)
+                    same = res[(size_t)i].ExecutorNodes[(size_t)t] == names[(size_t)oe[(size_t)(off[(size_t)i] + t)]];
+            }
+            std::vector<int64_t> fc((size_t)n), fm((size_t)n), fg((size_t)n);
+            orc_cluster_get_available(cl, fc.data(), fm.data(), fg.data());
+            for (int i = 0; same && i < n; ++i)
+                same = md[names[(size_t)i]].AvailableResources.CPU == fc[(size_t)i] && md[names[(size_t)i]].AvailableResources.Memory == fm[(size_t)i];
+            if (!same) std::printf("zone-aware fifo mismatch trial %d packer %s\n", trial, names_of[p]);
+            EXPECT(same, "FitEarlierDrivers (zone-aware packer) == orc_fifo");
+            orc_cluster_free(cl);
+        }
+    }
+}
+
 int main() {
     TestScheduler();
     TestHarnessThroughSingleAz();
     TestZoneGoldens();
     TestRandomAgainstOracle();
+    TestZoneAwareFifoAgainstOracle();
     TestUnschedulablePodMarker();
     TestSchedulerFailsToScheduleWhenNotEnoughNvidiaGPUs();
     TestSelectBinpacker();

@@ -540,3 +540,137 @@ def test_prepare_cluster_chain(oracle, packer):
     drv = res_aos(a["drv_cpu"], a["drv_mem"], a["drv_gpu"]); exe = res_aos(a["exe_cpu"], a["exe_mem"], a["exe_gpu"])
     _, od, oe, ooff = cl.fifo(0, 1, drv, exe, a["count"], a["young"], wd, we)
     assert_same_results(got, (od, oe, ooff), "device pipeline vs literal oracle pipeline")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# minimal-fragmentation: device algo 2 == oracle algo 4 (LIB/binpack/minimal_fragmentation.go)
+# ---------------------------------------------------------------------------------------------------------------
+MF_DEV, MF_ORC = 2, 4
+
+
+def test_minfrag_doc_examples(packer):
+    """capacities a1 b1 c3 d5 e5 f17 (minimal_fragmentation.go:45-58); the count-19 line follows the code, not the comment"""
+    names = ["a", "b", "c", "d", "e", "f", "drv"]
+    cpu = np.array([1000, 1000, 3000, 5000, 5000, 17000, 500], np.int64)
+    mem = np.full(7, 1 << 40, np.int64)
+    packer.set_snapshot(cpu, mem, np.zeros(7, np.int64), np.arange(6, dtype=np.int32), np.array([6], np.int32))
+    for count, expected in [(11, ["d"] * 5 + ["e"] * 5 + ["a"]), (6, ["d"] * 5 + ["a"]),
+                            (15, ["d"] * 5 + ["e"] * 5 + ["c"] * 3 + ["a", "b"]), (17, ["f"] * 17),
+                            (19, ["f"] * 17 + ["c", "c"]), (32, ["f"] * 17 + ["d"] * 5 + ["e"] * 5 + ["c"] * 3 + ["a", "b"]),
+                            (0, [])]:
+        ok, d, ex = packer.pack_one(MF_DEV, (500, 1, 0), (1000, 1, 0), count)
+        assert ok and names[d] == "drv" and [names[i] for i in ex] == expected, count
+    ok, _, _ = packer.pack_one(MF_DEV, (500, 1, 0), (1000, 1, 0), 33)
+    assert not ok
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_minfrag_random(oracle, packer, seed):
+    rng = np.random.default_rng(8000 + seed)
+    for trial in range(5):
+        n = int(rng.integers(1, 300))
+        cpu, mem, gpu = random_cluster(rng, n, tight=bool(trial % 2), gpus=bool(seed % 2), negative=bool(seed % 3 == 0))
+        perm = rng.permutation(n)
+        exec_idx = perm[rng.random(n) < 0.85].astype(np.int32)
+        drv_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.3, 1.0)))].astype(np.int32)
+        apps = random_apps(rng, 300, gpus=bool(seed % 2), zero_dims=bool(seed % 4 == 1), big_counts=bool(seed % 4 >= 2))
+        packer.set_snapshot(cpu, mem, gpu, exec_idx, drv_idx)
+        _, want, _ = _oracle_batch(oracle, MF_ORC, 0, cpu, mem, gpu, drv_idx, exec_idx, apps)
+        got = packer.pack_batch(apps, MF_DEV, 0)
+        assert_same_results(got, want, f"minfrag seed {seed} trial {trial}")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_minfrag_dense_ties(oracle, packer, seed):
+    """small capacities with many equal values, counts spread over [0, total + 3], every-dimension-zero executors
+    (capacity math.MaxInt: the target computation wraps), consumed lists longer than one warp"""
+    rng = np.random.default_rng(8100 + seed)
+    for trial in range(6):
+        n = int(rng.integers(1, 400))
+        caps = rng.integers(0, (4, 9, 30)[trial % 3], size=n)
+        cpu = (caps * 1000 + rng.integers(0, 1000, size=n)).astype(np.int64)
+        mem = np.full(n, 1 << 40, np.int64)
+        gpu = np.zeros(n, np.int64)
+        if seed % 4 == 3:
+            cpu[rng.integers(0, n)] = -5
+        exec_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.5, 1.0)))].astype(np.int32)
+        drv_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.2, 1.0)))].astype(np.int32)
+        q = 200
+        count = rng.integers(0, max(2, int(caps.sum()) + 3), size=q).astype(np.int32)
+        count[::7] = rng.integers(0, 12, size=len(count[::7]))
+        exe_cpu = np.full(q, 1000, np.int64)
+        exe_mem = np.ones(q, np.int64)
+        if seed % 4 == 2:
+            exe_cpu[::3] = 0; exe_mem[::3] = 0
+        apps = {"drv_cpu": rng.integers(0, 4000, size=q).astype(np.int64), "drv_mem": np.ones(q, np.int64),
+                "drv_gpu": np.zeros(q, np.int64), "exe_cpu": exe_cpu, "exe_mem": exe_mem, "exe_gpu": np.zeros(q, np.int64),
+                "count": count}
+        packer.set_snapshot(cpu, mem, gpu, exec_idx, drv_idx)
+        _, want, _ = _oracle_batch(oracle, MF_ORC, 0, cpu, mem, gpu, drv_idx, exec_idx, apps)
+        got = packer.pack_batch(apps, MF_DEV, 0)
+        assert_same_results(got, want, f"minfrag dense seed {seed} trial {trial}")
+
+
+def test_minfrag_wide_capacities(oracle, packer):
+    """general (64-bit) class: byte-granular requests against 2^40-scale nodes -> capacities far above 2^32, every division path"""
+    rng = np.random.default_rng(8200)
+    n = 96
+    cpu = rng.integers(0, 1 << 40, n).astype(np.int64)
+    mem = rng.integers(0, 1 << 45, n).astype(np.int64)
+    gpu = np.zeros(n, np.int64)
+    idx = np.arange(n, dtype=np.int32)
+    exe_mem = np.array([1, 3, 1 << 20, (1 << 20) * 3, (1 << 33) + 1, (1 << 34) + 2, 7 << 31, 12345678901, 1 << 44, 5], np.int64)
+    q = len(exe_mem) * 6
+    apps = {"drv_cpu": np.full(q, 1000, np.int64), "drv_mem": np.full(q, 1 << 30, np.int64), "drv_gpu": np.zeros(q, np.int64),
+            "exe_cpu": np.tile(np.array([1, 1000, 7, 0, 1 << 35, 3 << 33], np.int64), len(exe_mem)),
+            "exe_mem": np.repeat(exe_mem, 6), "exe_gpu": np.zeros(q, np.int64),
+            "count": rng.integers(1, 3000, q).astype(np.int32)}
+    packer.set_snapshot(cpu, mem, gpu, idx, idx)
+    _, want, _ = _oracle_batch(oracle, MF_ORC, 0, cpu, mem, gpu, idx, idx, apps)
+    got = packer.pack_batch(apps, MF_DEV, 0)
+    assert_same_results(got, want, "minfrag wide")
+
+
+def test_minfrag_zones_as_groups_and_bench_shape(oracle, packer):
+    """zones = instance groups (how single-az-minimal-fragmentation uses the entry) and the 10k-node bench shape"""
+    import k8s_spark_scheduler_b200.synth as synth
+    G = 4
+    nodes = synth.make_nodes(900, groups=G)
+    apps = synth.make_apps(600, groups=G)
+    eoff, eorder = synth.group_orders(nodes)
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], eorder, eorder, eoff, eoff)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count", "group")}
+    dn, en, off = packer.pack_batch(a, MF_DEV, 0)
+    for g in range(G):
+        sel = np.nonzero(apps["group"] == g)[0]
+        sub = {k: np.asarray(v)[sel] for k, v in a.items()}
+        order = eorder[eoff[g]:eoff[g + 1]]
+        _, (wd, we, woff), _ = _oracle_batch(oracle, MF_ORC, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order, sub)
+        assert np.array_equal(dn[sel], wd), g
+        for j, i in enumerate(sel):
+            if wd[j] >= 0:
+                assert np.array_equal(en[off[i]:off[i + 1]], we[woff[j]:woff[j + 1]]), (g, i)
+    nodes = synth.make_nodes(10000)
+    apps = synth.make_apps(3000)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order)
+    a = {k: apps[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")}
+    _, want, _ = _oracle_batch(oracle, MF_ORC, 0, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order, a)
+    got = packer.pack_batch(a, MF_DEV, 0)
+    assert_same_results(got, want, "minfrag bench shape")
+    # same driver as tightly-pack: a driver candidate is feasible iff the capacities add up to k, for both packers
+    tp = packer.pack_batch(a, 0, 0)
+    assert np.array_equal(tp[0], got[0])
+
+
+def test_minfrag_is_independent_mode_only(packer):
+    from k8s_spark_scheduler_b200 import GangpackError
+    idx = np.arange(2, dtype=np.int32)
+    packer.set_snapshot([8000, 8000], [8 << 30, 8 << 30], [0, 0], idx, idx)
+    base = {"drv_cpu": [1000], "drv_mem": [1 << 30], "drv_gpu": [0], "exe_cpu": [1000], "exe_mem": [1 << 30], "exe_gpu": [0], "count": [1]}
+    for mode in (1, 2):
+        with pytest.raises(GangpackError) as e:
+            packer.pack_batch(base, MF_DEV, mode)
+        assert e.value.status == 1
+    dn, en, _ = packer.pack_batch(base, MF_DEV, 0)
+    assert dn[0] == 0 and en[0] == 0

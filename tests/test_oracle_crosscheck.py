@@ -8,7 +8,7 @@ import pytest
 from helpers import random_apps, random_cluster, res_aos
 from oracle import pyref
 
-ALGOS = [(0, "tightly-pack"), (1, "distribute-evenly")]
+ALGOS = [(0, "tightly-pack"), (1, "distribute-evenly"), (4, "minimal-fragmentation")]
 
 
 def _orders(rng, n, names):
@@ -111,3 +111,83 @@ def test_synthetic_workload_oracles_agree(oracle):
                                                  order, order, drv, exe, apps["count"], n_threads=4)
         assert np.array_equal(ld, cd) and np.array_equal(le, ce)
         assert (ld >= 0).mean() > 0.5
+
+
+def _doc_cluster():
+    """the example of LIB/binpack/minimal_fragmentation.go:45-46: capacities a1 b1 c3 d5 e5 f17 for a 1-cpu executor"""
+    names = ["a", "b", "c", "d", "e", "f"]
+    caps = [1, 1, 3, 5, 5, 17]
+    cpu = np.array([1000 * c for c in caps], dtype=np.int64)
+    mem = np.full(6, 1 << 40, dtype=np.int64)
+    gpu = np.zeros(6, dtype=np.int64)
+    return names, cpu, mem, gpu
+
+
+# (executorCount, expected ExecutorNodes) -- the doc comment of minimalFragmentation (minimal_fragmentation.go:47-58).
+# Its last example (count 19 -> [f x17, a, b]) contradicts the code below it: after f is consumed the remainder 2
+# goes to the first node with capacity >= 2, which is c (internalMinimalFragmentation :107-114) -> the code wins.
+MINFRAG_DOC = [
+    (11, ["d"] * 5 + ["e"] * 5 + ["a"]),
+    (6, ["d"] * 5 + ["a"]),
+    (15, ["d"] * 5 + ["e"] * 5 + ["c"] * 3 + ["a", "b"]),
+    (17, ["f"] * 17),
+    (19, ["f"] * 17 + ["c", "c"]),
+]
+
+
+@pytest.mark.parametrize("count,expected", MINFRAG_DOC)
+def test_minimal_fragmentation_doc_examples(oracle, count, expected):
+    names, cpu, mem, gpu = _doc_cluster()
+    exe = (1000, 1, 0)
+    meta = {n: (int(cpu[i]), int(mem[i]), 0) for i, n in enumerate(names)}
+    nodes, ok = pyref.minimal_fragmentation(exe, count, names, meta, {})
+    assert ok and nodes == expected
+    # through SparkBinPack with a driver that only fits on a node outside the executor order
+    names2 = names + ["drv"]
+    cl = oracle.Cluster(names2, np.append(cpu, 500), np.append(mem, 1 << 40), np.append(gpu, 0))
+    has, d, ex, _ = cl.binpack(4, (500, 1, 0), exe, count, ["drv"], names)
+    assert has and d == "drv" and ex == expected
+    drv = res_aos([500], [1], [0]); exa = res_aos([1000], [1], [0])
+    _, cd, ce, _, _ = oracle.closed_batch(4, 0, np.append(cpu, 500), np.append(mem, 1 << 40), np.append(gpu, 0),
+                                          [6], list(range(6)), drv, exa, [count])
+    assert cd[0] == 6 and [names2[i] for i in ce[:count]] == expected
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_minimal_fragmentation_three_way_dense(oracle, seed):
+    """small capacities with many ties, counts around the interesting thresholds, unlimited capacities"""
+    rng = np.random.default_rng(7000 + seed)
+    for trial in range(40):
+        n = int(rng.integers(1, 24))
+        caps = rng.integers(0, 9 if trial % 2 else 30, size=n)
+        cpu = (caps * 1000 + rng.integers(0, 1000, size=n)).astype(np.int64)
+        mem = np.full(n, 1 << 40, dtype=np.int64)
+        gpu = np.zeros(n, dtype=np.int64)
+        if seed % 5 == 4:
+            cpu[rng.integers(0, n)] = -5
+        names = ["n%02d" % i for i in range(n)]
+        exec_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.5, 1.0)))].astype(np.int32)
+        drv_idx = rng.permutation(n)[: max(1, int(n * rng.uniform(0.2, 1.0)))].astype(np.int32)
+        q = 12
+        count = rng.integers(0, max(2, int(caps.sum()) + 3), size=q).astype(np.int32)
+        exe_cpu = np.full(q, 1000, dtype=np.int64)
+        exe_mem = np.ones(q, dtype=np.int64)
+        if seed % 5 == 3:
+            exe_cpu[::3] = 0; exe_mem[::3] = 0          # every dimension zero: capacity math.MaxInt, target wraps
+        drv_cpu = rng.integers(0, 4000, size=q).astype(np.int64)
+        drv = res_aos(drv_cpu, np.ones(q, dtype=np.int64), np.zeros(q, dtype=np.int64))
+        exe = res_aos(exe_cpu, exe_mem, np.zeros(q, dtype=np.int64))
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        exec_names = [names[i] for i in exec_idx]; drv_names = [names[i] for i in drv_idx]
+        ld, le, off = cl.binpack_batch(4, drv, exe, count, drv_names, exec_names)
+        _, cd, ce, coff, _ = oracle.closed_batch(4, 0, cpu, mem, gpu, drv_idx, exec_idx, drv, exe, count)
+        assert np.array_equal(ld, cd), (seed, trial)
+        meta = {names[i]: (int(cpu[i]), int(mem[i]), 0) for i in range(n)}
+        for a in range(q):
+            d, ex, ok = pyref.spark_bin_pack(tuple(int(x) for x in drv[a]), tuple(int(x) for x in exe[a]), int(count[a]),
+                                             drv_names, exec_names, dict(meta), pyref.minimal_fragmentation)
+            assert ok == (ld[a] >= 0), (seed, trial, a)
+            if ok:
+                assert names[ld[a]] == d
+                assert [names[i] for i in le[off[a]:off[a + 1]]] == ex, (seed, trial, a)
+                assert np.array_equal(le[off[a]:off[a + 1]], ce[off[a]:off[a + 1]]), (seed, trial, a, count[a])
