@@ -131,7 +131,8 @@ def main():
         meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in node_list}
         sch = sched if sched is not None else dict(meta)
         expect = {}
-        for algo, fn in (("single-az-tightly-pack", pyref.single_az_tightly_pack), ("az-aware-tightly-pack", pyref.az_aware_tightly_pack)):
+        for algo, fn in (("single-az-tightly-pack", pyref.single_az_tightly_pack), ("az-aware-tightly-pack", pyref.az_aware_tightly_pack),
+                         ("single-az-minimal-fragmentation", pyref.single_az_minimal_fragmentation)):
             d, ex, ok = fn(tuple(app["drv"]), tuple(app["exe"]), app["count"], names, names, dict(meta), sch, zones)
             expect[algo] = {"fit": ok, "driver": d, "executors": ex}
             if pinned_fit is not None:
@@ -159,6 +160,41 @@ def main():
     zone_cases.append(zone_case("Z3", "derived: zero-resource app: every zone 'fits' with efficiency... chooseBestResult needs Max > 0",
                                 nodes(("a1", 0, 0, 0), ("b1", 0, 0, 0)), {"a1": "za", "b1": "zb"},
                                 {"drv": [0, 0, 0], "exe": [0, 0, 0], "count": 2}, sched={"a1": (0, 0, 0), "b1": (0, 0, 0)}))
+
+    # TestMinimalFragmentation / TestMinimalFragmentationEdgeCase (internal/extender/resource_test.go:73-165) schedule their
+    # drivers through single-az-minimal-fragmentation: a dynamic-allocation app (min 1 executor) on the two harness nodes fits
+    zone_cases.append(zone_case("Z-MF", "internal/extender/resource_test.go:73-124 TestMinimalFragmentation: driver of DynamicAllocationSparkPods(app, 1, 2)",
+                                harness_nodes, hz, {**static_app, "count": 1}, pinned_fit=True))
+
+    # ---- minimal fragmentation: LIB/binpack/minimal_fragmentation.go ---------------------------
+    # the doc comment of minimalFragmentation (:43-58): capacities a1 b1 c3 d5 e5 f17 for one executor shape
+    mf_nodes = nodes(("a", 1000, 64 * Gi, 0), ("b", 1000, 64 * Gi, 0), ("c", 3000, 64 * Gi, 0), ("d", 5000, 64 * Gi, 0),
+                     ("e", 5000, 64 * Gi, 0), ("f", 17000, 64 * Gi, 0), ("drv", 500, 64 * Gi, 0))
+    mf_exec_order = ["a", "b", "c", "d", "e", "f"]
+    minfrag_cases = []
+
+    def minfrag_case(cid, source, count, doc_expect=None, pinned="reference-doc-comment"):
+        app = {"drv": [500, 1, 0], "exe": [1000, 1, 0], "count": count}
+        meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in mf_nodes}
+        d, ex, ok = pyref.spark_bin_pack(tuple(app["drv"]), tuple(app["exe"]), count, ["drv"], mf_exec_order, dict(meta),
+                                         pyref.minimal_fragmentation)
+        if doc_expect is not None:
+            assert ok and d == "drv" and ex == doc_expect, (cid, ex, doc_expect)
+        return {"id": cid, "source": source, "nodes": mf_nodes, "driver_order": ["drv"], "exec_order": mf_exec_order, "app": app,
+                "expect": {"fit": ok, "driver": d, "executors": ex}, "pinned": {"executors": pinned}}
+
+    minfrag_cases.append(minfrag_case("MF-11", "minimal_fragmentation.go:45-46 executorCount = 11", 11, ["d"] * 5 + ["e"] * 5 + ["a"]))
+    minfrag_cases.append(minfrag_case("MF-6", "minimal_fragmentation.go:48-49 executorCount = 6", 6, ["d"] * 5 + ["a"]))
+    minfrag_cases.append(minfrag_case("MF-15", "minimal_fragmentation.go:51-52 executorCount = 15", 15,
+                                      ["d"] * 5 + ["e"] * 5 + ["c"] * 3 + ["a", "b"]))
+    minfrag_cases.append(minfrag_case("MF-17", "minimal_fragmentation.go:54-55 executorCount = 17", 17, ["f"] * 17))
+    minfrag_cases.append(minfrag_case(
+        "MF-19", "minimal_fragmentation.go:57-58 says [f x17, a, b] for executorCount = 19, but the code below it (:105-114) puts "
+        "the remainder 2 on the first node whose capacity is >= 2, i.e. c -- the code is the authority", 19,
+        ["f"] * 17 + ["c", "c"], pinned="derived-from-code"))
+    minfrag_cases.append(minfrag_case("MF-32", "derived: every node is consumed", 32,
+                                      ["f"] * 17 + ["d"] * 5 + ["e"] * 5 + ["c"] * 3 + ["a", "b"], pinned="derived"))
+    minfrag_cases.append(minfrag_case("MF-33", "derived: one more than the cluster holds", 33, pinned="derived"))
 
     # ---- FIFO loop (fitEarlierDrivers) ----------------------------------------------------------
     fifo_cases = []
@@ -236,7 +272,7 @@ def main():
 
     out = {"_comment": "generated by tests/gen_golden.py -- do not edit by hand",
            "units": {"cpu": "millicores", "mem": "bytes", "gpu": "units"},
-           "pack_cases": cases, "zone_cases": zone_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
+           "pack_cases": cases, "zone_cases": zone_cases, "minfrag_cases": minfrag_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
     path = os.path.join(ROOT, "tests", "golden", "hotpath_vectors.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:

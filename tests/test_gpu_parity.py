@@ -549,7 +549,7 @@ MF_DEV, MF_ORC = 2, 4
 
 
 def test_minfrag_doc_examples(packer):
-    """capacities a1 b1 c3 d5 e5 f17 (minimal_fragmentation.go:45-58); the count-19 line follows the code, not the comment"""
+    """capacities a1 b1 c3 d5 e5 f17 (minimal_fragmentation.go:43-58); the count-19 line follows the code, not the comment"""
     names = ["a", "b", "c", "d", "e", "f", "drv"]
     cpu = np.array([1000, 1000, 3000, 5000, 5000, 17000, 500], np.int64)
     mem = np.full(7, 1 << 40, np.int64)
@@ -562,6 +562,17 @@ def test_minfrag_doc_examples(packer):
         assert ok and names[d] == "drv" and [names[i] for i in ex] == expected, count
     ok, _, _ = packer.pack_one(MF_DEV, (500, 1, 0), (1000, 1, 0), 33)
     assert not ok
+
+
+def test_golden_minfrag_cases(golden, packer):
+    for case in golden["minfrag_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        packer.set_snapshot(cpu, mem, gpu, order_indices(case["exec_order"], names), order_indices(case["driver_order"], names))
+        app, exp = case["app"], case["expect"]
+        ok, d, ex = packer.pack_one(MF_DEV, app["drv"], app["exe"], app["count"])
+        assert ok == exp["fit"], case["id"]
+        if ok:
+            assert names[d] == exp["driver"] and [names[i] for i in ex] == exp["executors"], case["id"]
 
 
 @pytest.mark.parametrize("seed", range(10))

@@ -114,7 +114,7 @@ def test_synthetic_workload_oracles_agree(oracle):
 
 
 def _doc_cluster():
-    """the example of LIB/binpack/minimal_fragmentation.go:45-46: capacities a1 b1 c3 d5 e5 f17 for a 1-cpu executor"""
+    """the example of LIB/binpack/minimal_fragmentation.go:43-44: capacities a1 b1 c3 d5 e5 f17 for a 1-cpu executor"""
     names = ["a", "b", "c", "d", "e", "f"]
     caps = [1, 1, 3, 5, 5, 17]
     cpu = np.array([1000 * c for c in caps], dtype=np.int64)
@@ -123,7 +123,7 @@ def _doc_cluster():
     return names, cpu, mem, gpu
 
 
-# (executorCount, expected ExecutorNodes) -- the doc comment of minimalFragmentation (minimal_fragmentation.go:47-58).
+# (executorCount, expected ExecutorNodes) -- the doc comment of minimalFragmentation (minimal_fragmentation.go:43-58).
 # Its last example (count 19 -> [f x17, a, b]) contradicts the code below it: after f is consumed the remainder 2
 # goes to the first node with capacity >= 2, which is c (internalMinimalFragmentation :107-114) -> the code wins.
 MINFRAG_DOC = [

@@ -149,7 +149,27 @@ def test_packing_efficiency_by_product(oracle):
     assert eff[3] == pytest.approx((7 / 8 + 1 + 2 / 8 + 0) / 4, rel=0, abs=1e-15)
 
 
-ZONE_ALGO = {"single-az-tightly-pack": 2, "az-aware-tightly-pack": 3}
+ZONE_ALGO = {"single-az-tightly-pack": 2, "az-aware-tightly-pack": 3, "single-az-minimal-fragmentation": 5}
+
+
+def test_minimal_fragmentation_goldens(golden, oracle):
+    """the worked examples in the doc comment of minimalFragmentation (LIB/binpack/minimal_fragmentation.go:43-58) --
+    the one place the reference states exact ExecutorNodes for this packer -- on the literal and the closed-form oracle"""
+    from helpers import order_indices, res_aos
+    assert sum(c["pinned"]["executors"] == "reference-doc-comment" for c in golden["minfrag_cases"]) == 4
+    for case in golden["minfrag_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        app, exp = case["app"], case["expect"]
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        ok, d, ex, _ = cl.binpack(4, app["drv"], app["exe"], app["count"], case["driver_order"], case["exec_order"])
+        assert ok == exp["fit"], case["id"]
+        _, cd, ce, _, _ = oracle.closed_batch(4, 0, cpu, mem, gpu, order_indices(case["driver_order"], names),
+                                              order_indices(case["exec_order"], names), res_aos(*[[v] for v in app["drv"]]),
+                                              res_aos(*[[v] for v in app["exe"]]), [app["count"]])
+        assert (cd[0] >= 0) == exp["fit"], case["id"]
+        if ok:
+            assert d == exp["driver"] and ex == exp["executors"], case["id"]
+            assert names[cd[0]] == exp["driver"] and [names[i] for i in ce[:app["count"]]] == exp["executors"], case["id"]
 
 
 def test_literal_oracle_zone_cases(golden, oracle):
@@ -190,7 +210,7 @@ def test_zone_packers_random_three_way(oracle):
             drv = (int(rng.integers(0, 3)) * 500, int(rng.integers(0, 3)) << 29, int(rng.integers(0, 2)))
             exe = (int(rng.integers(1, 5)) * 500, int(rng.integers(1, 9)) << 28, int(rng.integers(0, 2)))
             k = int(rng.integers(0, 10))
-            for fn, aid in ((pyref.single_az_tightly_pack, 2), (pyref.az_aware_tightly_pack, 3)):
+            for fn, aid in ((pyref.single_az_tightly_pack, 2), (pyref.az_aware_tightly_pack, 3), (pyref.single_az_minimal_fragmentation, 5)):
                 d, ex, ok = fn(drv, exe, k, order, order, dict(meta), sched, zones)
                 lok, ld, lex, _ = cl.binpack(aid, drv, exe, k, order, order, with_efficiencies=True)
                 assert ok == lok, (trial, aid)
