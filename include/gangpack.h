@@ -49,7 +49,7 @@ typedef enum {
     GP_DISTRIBUTE_EVENLY = 1, /* "distribute-evenly" -> distribute_evenly.go:34-73, round-major (also the
                                  fallback for unknown names, binpack.go:52-57) */
     GP_MINIMAL_FRAGMENTATION = 2 /* binpack.MinimalFragmentation -> LIB/binpack/minimal_fragmentation.go:27-137 over
-                                 LIB/capacity/capacity.go:31-111: as few nodes as possible, fullest-fitting node first;
+                                 LIB/capacity/capacity.go:36-113: as few nodes as possible, fullest-fitting node first;
                                  ExecutorNodes in (capacity descending, priority order) then the remainder's node.
                                  GP_MODE_INDEPENDENT only: the building block of "single-az-minimal-fragmentation"
                                  (internal/binpacker/binpack.go:48), which packs one application per zone (zone =

@@ -2,20 +2,20 @@
 //
 // Reference (all under /root/reference; LIB = vendor/github.com/palantir/k8s-spark-scheduler-lib/pkg):
 //   MinimalFragmentation / minimalFragmentation / internalMinimalFragmentation   LIB/binpack/minimal_fragmentation.go:27-137
-//   GetNodeCapacities / GetNodeCapacity / FilterOutNodesWithoutCapacity          LIB/capacity/capacity.go:31-111
+//   GetNodeCapacities / GetNodeCapacity / FilterOutNodesWithoutCapacity          LIB/capacity/capacity.go:36-113
 //   SparkBinPack driver loop                                                     LIB/binpack/binpack.go:60-87
 //
 // The reference sorts the (node, capacity) list of every driver candidate and then peels runs of equal
 // capacity off its tail.  Here nothing is sorted.  With c(i) the UNCLAMPED capacity of the i-th executor
-// candidate (nodes with c = 0 dropped, capacity.go:103-111):
+// candidate (nodes with c = 0 dropped, capacity.go:105-113):
 //   * a driver candidate is feasible iff sum c >= k -- the same test as tightly-pack, so the driver loop is the
 //     closed form of gangpack_kernels.cuh;
 //   * M = max c.  If k < M the reference first tries the subset {c < target}, target = (k + M) / 2 in Go's wrapping
-//     int arithmetic (:82-91); that attempt succeeds iff the subset's capacities add up to k.  Otherwise every node is
-//     used (:94);
+//     int arithmetic (:80-89); that attempt succeeds iff the subset's capacities add up to k.  Otherwise every node is
+//     used (:93);
 //   * inside the chosen set: if some c >= k, all k executors go to the smallest such c (earliest node among equals,
-//     :107-114).  Otherwise nodes are consumed whole in (c descending, priority order ascending) while the remainder is
-//     >= c (:117-128): with F(v) = sum of c over {c >= v}, v* = max{v : F(v) > k} (binary search, one reduction pass per
+//     :106-113).  Otherwise nodes are consumed whole in (c descending, priority order ascending) while the remainder is
+//     >= c (:116-127): with F(v) = sum of c over {c >= v}, v* = max{v : F(v) > k} (binary search, one reduction pass per
 //     probe), every node with c > v* is consumed, r* = k - F(v*+1), the first m = floor(r*/v*) nodes of the run c == v*
 //     are consumed when v* < r*, and the rest r' goes to the smallest c >= r' among the unconsumed nodes;
 //   * ExecutorNodes lists the consumed nodes in (c descending, order ascending): the offset of a consumed node is the sum
@@ -28,7 +28,7 @@
 
 namespace gp {
 
-constexpr uint64_t kCapInf = 0x7fffffffffffffffull;   // math.MaxInt (capacity.go:56-59)
+constexpr uint64_t kCapInf = 0x7fffffffffffffffull;   // math.MaxInt (capacity.go:42-45)
 
 // unclamped cap_dim (see gangpack_kernels.cuh): a = avail - reserved
 __device__ __forceinline__ uint64_t cap_dim_u(int64_t a, const DimDiv& p) {
@@ -120,7 +120,7 @@ __device__ __forceinline__ void minfrag_emit(const CP& cp, int32_t ne, int32_t d
     T U = M;
     unsigned long long total = total_all;
     if (kT < M) {
-        // target = (executorCount + maxCapacity) / 2 with Go's wrapping 64-bit int (minimal_fragmentation.go:83)
+        // target = (executorCount + maxCapacity) / 2 with Go's wrapping 64-bit int (minimal_fragmentation.go:81)
         const int64_t target = (int64_t)((uint64_t)k + (uint64_t)M) / 2;
         if (target > 1) {
             const T tg = (T)target;
@@ -136,14 +136,14 @@ __device__ __forceinline__ void minfrag_emit(const CP& cp, int32_t ne, int32_t d
                 if (c >= kT) note_min_key(c, i, sb_c, sb_p);
             }
             st.nodes += (unsigned long long)ne;
-            if (sum_s >= k) {                // the subset can host everything (:89-91)
+            if (sum_s >= k) {                // the subset can host everything (:87-89)
                 limit = tg - 1; U = warp_max_t(us); total = sum_s;
                 best_c = sb_c; best_p = sb_p;
             }
         }
     }
     warp_min_key(best_c, best_p);
-    if (best_p >= 0) {                       // one node takes all k executors (:107-114)
+    if (best_p >= 0) {                       // one node takes all k executors (:106-113)
         const int32_t node = slot_node[best_p];
         for (uint32_t j = lane; j < k; j += kWarp) out[j] = node;
         return;

@@ -285,13 +285,13 @@ static int distribute_executors_evenly(const orc_cluster* c, const orc_res* exe,
 /* capacity.NodeAndExecutorCapacity, LIB/capacity/capacity.go:26-29 */
 typedef struct { const char* name; int64_t capacity; } node_cap;
 
-/* getCapacityAgainstSingleDimension, LIB/capacity/capacity.go:50-68 */
+/* getCapacityAgainstSingleDimension, LIB/capacity/capacity.go:36-55 */
 static int64_t capacity_single_dimension(int64_t available, int64_t reserved, int64_t required) {
-    if (reserved > available) return 0;                                 /* :51-54 */
-    if (required == 0) return INT64_MAX;                                /* :56-59 math.MaxInt */
-    return (available - reserved) / required;                           /* :62-67 floor; numerator >= 0, required > 0 */
+    if (reserved > available) return 0;                                 /* :37-40 */
+    if (required == 0) return INT64_MAX;                                /* :42-45 math.MaxInt */
+    return (available - reserved) / required;                           /* :47-54 floor; numerator >= 0, required > 0 */
 }
-/* GetNodeCapacity + min, capacity.go:31-48,114-121 */
+/* GetNodeCapacity + min, capacity.go:57-75,115-122 */
 static int64_t node_capacity(const orc_res* available, const orc_res* reserved, const orc_res* single) {
     int64_t a = capacity_single_dimension(available->cpu, reserved->cpu, single->cpu);
     int64_t b = capacity_single_dimension(available->mem, reserved->mem, single->mem);
@@ -300,7 +300,7 @@ static int64_t node_capacity(const orc_res* available, const orc_res* reserved, 
     if (b <= g) return b;
     return g;
 }
-/* sort.SliceStable by Capacity ascending (minimal_fragmentation.go:78-80) */
+/* sort.SliceStable by Capacity ascending (minimal_fragmentation.go:76-78) */
 static void msort_caps(node_cap* a, node_cap* tmp, int32_t n) {
     if (n < 2) return;
     int32_t h = n / 2;
@@ -317,34 +317,34 @@ static int32_t search_at_least(const node_cap* a, int32_t n, int64_t x) {
     while (lo < hi) { int32_t mid = lo + (hi - lo) / 2; if (a[mid].capacity >= x) hi = mid; else lo = mid + 1; }
     return lo;
 }
-/* internalMinimalFragmentation, minimal_fragmentation.go:97-137.  `caps` is copied like the reference does. */
+/* internalMinimalFragmentation, minimal_fragmentation.go:96-137.  `caps` is copied like the reference does. */
 static int internal_minimal_fragmentation(int64_t count, const node_cap* caps_in, int32_t n,
                                           const char** executor_nodes) {
-    node_cap* caps = (node_cap*)malloc(sizeof(node_cap) * (size_t)(n > 0 ? n : 1));      /* :100-101 */
+    node_cap* caps = (node_cap*)malloc(sizeof(node_cap) * (size_t)(n > 0 ? n : 1));      /* :99-100 */
     memcpy(caps, caps_in, sizeof(node_cap) * (size_t)n);
     int64_t placed = 0;
-    while (n > 0) {                                                                       /* :105 */
-        int32_t position = search_at_least(caps, n, count);                               /* :107-109 */
-        if (position != n) {                                                              /* :111-114 */
+    while (n > 0) {                                                                       /* :104 */
+        int32_t position = search_at_least(caps, n, count);                               /* :106-108 */
+        if (position != n) {                                                              /* :110-113 */
             for (int64_t t = 0; t < count; ++t) executor_nodes[placed++] = caps[position].name;
             free(caps);
             return 1;
         }
-        int64_t max_capacity = caps[n - 1].capacity;                                      /* :117 */
-        int32_t first_max = search_at_least(caps, n, max_capacity);                       /* :118-120 */
-        int32_t pos = first_max;                                                          /* :123 */
-        for (; count >= max_capacity && pos < n; ++pos) {                                 /* :124 */
-            for (int64_t t = 0; t < max_capacity; ++t) executor_nodes[placed++] = caps[pos].name; /* :126 */
-            count -= max_capacity;                                                        /* :127 */
+        int64_t max_capacity = caps[n - 1].capacity;                                      /* :116 */
+        int32_t first_max = search_at_least(caps, n, max_capacity);                       /* :117-119 */
+        int32_t pos = first_max;                                                          /* :122 */
+        for (; count >= max_capacity && pos < n; ++pos) {                                 /* :123 */
+            for (int64_t t = 0; t < max_capacity; ++t) executor_nodes[placed++] = caps[pos].name; /* :125 */
+            count -= max_capacity;                                                        /* :126 */
         }
-        if (count == 0) { free(caps); return 1; }                                         /* :130-132 */
-        memmove(caps + first_max, caps + pos, sizeof(node_cap) * (size_t)(n - pos));      /* :134 */
+        if (count == 0) { free(caps); return 1; }                                         /* :129-131 */
+        memmove(caps + first_max, caps + pos, sizeof(node_cap) * (size_t)(n - pos));      /* :133 */
         n -= pos - first_max;
     }
     free(caps);
     return 0;                                                                             /* :136 */
 }
-/* minimalFragmentation, LIB/binpack/minimal_fragmentation.go:59-95.  Note: it never adds the executors to
+/* minimalFragmentation, LIB/binpack/minimal_fragmentation.go:59-94.  Note: it never adds the executors to
  * `reserved` (only the driver's entry exists), so the efficiencies SparkBinPack computes afterwards
  * (binpack.go:77) see the driver only -- kept as is. */
 static int minimal_fragmentation(const orc_cluster* c, const orc_res* exe, int32_t count,
@@ -355,27 +355,27 @@ static int minimal_fragmentation(const orc_cluster* c, const orc_res* exe, int32
     node_cap* caps = (node_cap*)malloc(sizeof(node_cap) * (size_t)(n_order > 0 ? n_order : 1) * 2);
     node_cap* tmp = caps + (n_order > 0 ? n_order : 1);
     int32_t n = 0;
-    for (int32_t i = 0; i < n_order; ++i) {                                               /* GetNodeCapacities, capacity.go:79-100 */
+    for (int32_t i = 0; i < n_order; ++i) {                                               /* GetNodeCapacities, capacity.go:78-102 */
         const node_meta* m = meta_lookup(c, order[i]);
-        if (m == NULL) continue;                                                          /* :84 */
-        const orc_res* r = resmap_get(reserved, order[i]);                                /* :85-89 */
+        if (m == NULL) continue;                                                          /* :87 */
+        const orc_res* r = resmap_get(reserved, order[i]);                                /* :88-92 */
         if (r == NULL) r = &zero;
         int64_t cap = node_capacity(&m->available, r, exe);
-        if (cap > 0) { caps[n].name = order[i]; caps[n].capacity = cap; ++n; }            /* FilterOutNodesWithoutCapacity, :103-111 */
+        if (cap > 0) { caps[n].name = order[i]; caps[n].capacity = cap; ++n; }            /* FilterOutNodesWithoutCapacity, :105-113 */
     }
     if (n == 0) { free(caps); return 0; }                                                 /* :72-74 */
-    msort_caps(caps, tmp, n);                                                             /* :78-80 */
-    int64_t max_capacity = caps[n - 1].capacity;                                          /* :81 */
-    if ((int64_t)count < max_capacity) {                                                  /* :82 */
+    msort_caps(caps, tmp, n);                                                             /* :76-78 */
+    int64_t max_capacity = caps[n - 1].capacity;                                          /* :79 */
+    if ((int64_t)count < max_capacity) {                                                  /* :80 */
         /* Go int arithmetic wraps: count + MaxInt is negative, and / truncates toward zero */
-        int64_t target = (int64_t)((uint64_t)count + (uint64_t)max_capacity) / 2;         /* :83 */
-        int32_t first = search_at_least(caps, n, target);                                 /* :84-86 */
-        if (internal_minimal_fragmentation(count, caps, first, executor_nodes)) {         /* :89-91 */
+        int64_t target = (int64_t)((uint64_t)count + (uint64_t)max_capacity) / 2;         /* :81 */
+        int32_t first = search_at_least(caps, n, target);                                 /* :82-84 */
+        if (internal_minimal_fragmentation(count, caps, first, executor_nodes)) {         /* :87-89 */
             free(caps);
             return 1;
         }
     }
-    int ok = internal_minimal_fragmentation(count, caps, n, executor_nodes);              /* :94 */
+    int ok = internal_minimal_fragmentation(count, caps, n, executor_nodes);              /* :93 */
     free(caps);
     return ok;
 }

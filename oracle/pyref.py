@@ -80,7 +80,7 @@ def _go_int(v):
 
 
 def _capacity_single_dimension(available, reserved, required):
-    """getCapacityAgainstSingleDimension, LIB/capacity/capacity.go:50-68."""
+    """getCapacityAgainstSingleDimension, LIB/capacity/capacity.go:36-55."""
     if reserved > available:
         return 0
     if required == 0:
@@ -89,7 +89,7 @@ def _capacity_single_dimension(available, reserved, required):
 
 
 def node_capacities(order, meta, reserved, exe):
-    """GetNodeCapacities, LIB/capacity/capacity.go:71-101 -> [(name, capacity)] in order."""
+    """GetNodeCapacities, LIB/capacity/capacity.go:78-102 -> [(name, capacity)] in order."""
     out = []
     for n in order:
         if n in meta:
@@ -111,7 +111,7 @@ def _search(caps, pred):
 
 
 def _internal_minimal_fragmentation(count, caps):
-    """internalMinimalFragmentation, LIB/binpack/minimal_fragmentation.go:97-137."""
+    """internalMinimalFragmentation, LIB/binpack/minimal_fragmentation.go:96-137."""
     caps = list(caps)
     out = []
     while caps:
@@ -132,7 +132,7 @@ def _internal_minimal_fragmentation(count, caps):
 
 
 def minimal_fragmentation(exe, count, order, meta, reserved):
-    """minimalFragmentation, LIB/binpack/minimal_fragmentation.go:59-95 (does not touch `reserved`)."""
+    """minimalFragmentation, LIB/binpack/minimal_fragmentation.go:59-94 (does not touch `reserved`)."""
     if count == 0:
         return [], True
     caps = [c for c in node_capacities(order, meta, reserved, exe) if c[1] > 0]
