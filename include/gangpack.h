@@ -205,6 +205,34 @@ gp_status gp_potential_nodes(gp_ctx* ctx, const gp_sort_input* in,
 gp_status gp_prepare_cluster(gp_ctx* ctx, const gp_usage_input* usage, const gp_sort_input* sort,
                              int32_t* n_driver /* may be NULL */, int32_t* n_executor /* may be NULL */);
 
+/* ---- executors without a usable reservation (the step after the hot path) --- */
+/* rescheduleExecutor's node choice (internal/extender/resource.go:594-673) for a BATCH of executor pods, every
+ * decision independent against the current snapshot (its executor priority orders and availabilities):
+ *   min_frag == 0: the first node of the order the executor fits on (:657-662);
+ *   min_frag != 0: rescheduleExecutorWithMinimalFragmentation (:675-705) -- capacities from
+ *                  capacity.GetNodeCapacities (LIB/capacity/capacity.go:78-102) with `reserved_*` taken off each
+ *                  node (the reference passes its overhead map there, :682); a node already hosting executors of
+ *                  the same application wins, then the smallest capacity >= 1, then the order.
+ * The caller uploads with gp_set_snapshot the availability the reference would use for that branch
+ * (availableResources of :643 for first fit, availableNodesSchedulingMetadata of :640 for min_frag). */
+typedef struct {
+    int32_t n_execs;
+    const int64_t* exe_cpu_milli;        /* [n_execs] */
+    const int64_t* exe_mem_bytes;        /* [n_execs] */
+    const int64_t* exe_gpu;              /* [n_execs] or NULL (= 0) */
+    const int32_t* group;                /* [n_execs] instance group of the executor's application, or NULL (= 0) */
+    int32_t min_frag;
+    /* min_frag only: */
+    const int64_t* reserved_cpu_milli;   /* [n_nodes] or NULL (= 0) */
+    const int64_t* reserved_mem_bytes;   /* [n_nodes] (required when reserved_cpu_milli is given) */
+    const int64_t* reserved_gpu;         /* [n_nodes] or NULL (= 0) */
+    const int64_t* host_off;             /* [n_execs + 1] CSR offsets into host_nodes, or NULL (no application hosts anything yet) */
+    const int32_t* host_nodes;           /* node indices already hosting executors of the same application
+                                            (getNodesWithExecutorsBelongingToSameApp, :683) */
+} gp_reschedule;
+/* node_out[i] = node index, or -1 ("not enough capacity to reschedule the executor", :672) */
+gp_status gp_reschedule_executors(gp_ctx* ctx, const gp_reschedule* in, int32_t* node_out /* [n_execs] */);
+
 /* ---- packing ------------------------------------------------------------------------------- */
 /* One batch through the hot path with HOST buffers: H2D of the app SoA, kernels, D2H of the
  * results; returns when the results are in host memory.  FIFO modes mutate the device snapshot. */

@@ -4,6 +4,7 @@
 #include "gangpack_kernels.cuh"
 #include "gangpack_fifo.cuh"
 #include "gangpack_minfrag.cuh"
+#include "gangpack_resched.cuh"
 #include "gangpack_sort.cuh"
 
 #include <algorithm>
@@ -351,7 +352,7 @@ struct gp_ctx {
 
     // batch staging
     DevBuf a_dcpu, a_dmem, a_dgpu, a_ecpu, a_emem, a_egpu, a_count, a_group, a_skip, a_off;
-    DevBuf prep, r_driver, r_exec, scratch, dev_misc, gmin, sortbuf, usagebuf;
+    DevBuf prep, r_driver, r_exec, scratch, dev_misc, gmin, sortbuf, usagebuf, reschedbuf;
     std::vector<int32_t> iota;   // dev_misc: [0] err int, [2..3] stats u64 x2 (8B aligned at +8)
     void* pinned_misc = nullptr;                         // 32 B pinned mirror of dev_misc
     std::vector<int64_t> host_off;
@@ -484,7 +485,7 @@ void gp_destroy(gp_ctx* c) {
     DevBuf* bufs[] = {&c->node_cpu, &c->node_mem, &c->node_gpu, &c->exec_off, &c->drv_off, &c->exec_order, &c->drv_order,
                       &c->pair, &c->pair32, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
-                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf};
+                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf, &c->reschedbuf};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
     if (c->one_block) cudaFreeHost(c->one_block);
@@ -1258,5 +1259,98 @@ gp_status gp_prepare_cluster(gp_ctx* c, const gp_usage_input* usage, const gp_so
     if (n_executor) *n_executor = counts[1];
     return GP_OK;
 }
+
+// rescheduleExecutor's node choice for a batch of executors; see gangpack_resched.cuh
+gp_status gp_reschedule_executors(gp_ctx* c, const gp_reschedule* in, int32_t* node_out) {
+    if (!c) return GP_ERR_INVALID;
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, "gp_reschedule_executors: gp_set_snapshot first");
+    if (!in || in->n_execs < 0 || (in->n_execs > 0 && (!in->exe_cpu_milli || !in->exe_mem_bytes || !node_out)))
+        return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: missing arrays or bad sizes");
+    const int32_t q = in->n_execs;
+    if (q == 0) return GP_OK;
+    const bool mf = in->min_frag != 0;
+    const bool has_res = mf && in->reserved_cpu_milli;
+    const bool has_host = mf && in->host_off;
+    if (has_res && !in->reserved_mem_bytes) return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: reserved_mem_bytes missing");
+    // host validation (O(q + n_nodes + hosted)): the exact-int64 domain, non-negative requests, CSR shape
+    for (int32_t i = 0; i < q; ++i) {
+        const int64_t v[3] = {in->exe_cpu_milli[i], in->exe_mem_bytes[i], in->exe_gpu ? in->exe_gpu[i] : 0};
+        for (int64_t x : v) {
+            if (x < 0) return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: negative resource request");
+            if (x >= kMaxQuantity) return fail(c, GP_ERR_UNREPRESENTABLE, "gp_reschedule_executors: quantity >= 2^61");
+        }
+        if (in->group && (in->group[i] < 0 || in->group[i] >= c->n_groups))
+            return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: instance group out of range");
+    }
+    if (has_res)
+        for (int32_t n = 0; n < c->n_nodes; ++n) {
+            const int64_t v[3] = {in->reserved_cpu_milli[n], in->reserved_mem_bytes[n], in->reserved_gpu ? in->reserved_gpu[n] : 0};
+            for (int64_t x : v)
+                if (x >= kMaxQuantity || x <= -kMaxQuantity) return fail(c, GP_ERR_UNREPRESENTABLE, "gp_reschedule_executors: |reserved| >= 2^61");
+        }
+    int64_t hosted = 0;
+    if (has_host) {
+        if (in->host_off[0] != 0) return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: host_off must start at 0");
+        for (int32_t i = 0; i < q; ++i)
+            if (in->host_off[i + 1] < in->host_off[i]) return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: host_off not monotone");
+        hosted = in->host_off[q];
+        if (hosted > 0 && !in->host_nodes) return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: host_nodes missing");
+        for (int64_t t = 0; t < hosted; ++t)
+            if (in->host_nodes[t] < 0 || in->host_nodes[t] >= c->n_nodes)
+                return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: host_nodes index out of range");
+    }
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // one staging buffer: [exe 3q i64 | reserved 3N i64 | host_off (q+1) i64 | group q i32 | host_nodes H i32 | out q i32 | err i32]
+    const size_t Q = (size_t)q, N = (size_t)c->n_nodes, H = (size_t)hosted;
+    const size_t o_exe = 0, o_res = o_exe + 8 * 3 * Q, o_hoff = o_res + 8 * 3 * N, o_grp = o_hoff + 8 * (Q + 1),
+                 o_hn = o_grp + 4 * Q, o_out = o_hn + 4 * (H + 1), o_err = o_out + 4 * Q, total = o_err + 8;
+    GP_CUDA(c, c->reschedbuf.reserve(total));
+    char* base = c->reschedbuf.as<char>();
+    int64_t* d_exe = reinterpret_cast<int64_t*>(base + o_exe);
+    int64_t* d_res = reinterpret_cast<int64_t*>(base + o_res);
+    int64_t* d_hoff = reinterpret_cast<int64_t*>(base + o_hoff);
+    int32_t* d_grp = reinterpret_cast<int32_t*>(base + o_grp);
+    int32_t* d_hn = reinterpret_cast<int32_t*>(base + o_hn);
+    int32_t* d_out = reinterpret_cast<int32_t*>(base + o_out);
+    int* d_err = reinterpret_cast<int*>(base + o_err);
+    GP_CUDA(c, cudaMemsetAsync(d_err, 0, 8, st));
+    GP_CUDA(c, cudaMemcpyAsync(d_exe, in->exe_cpu_milli, 8 * Q, cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(d_exe + Q, in->exe_mem_bytes, 8 * Q, cudaMemcpyHostToDevice, st));
+    if (in->exe_gpu) GP_CUDA(c, cudaMemcpyAsync(d_exe + 2 * Q, in->exe_gpu, 8 * Q, cudaMemcpyHostToDevice, st));
+    if (in->group) GP_CUDA(c, cudaMemcpyAsync(d_grp, in->group, 4 * Q, cudaMemcpyHostToDevice, st));
+    if (has_res && N) {
+        GP_CUDA(c, cudaMemcpyAsync(d_res, in->reserved_cpu_milli, 8 * N, cudaMemcpyHostToDevice, st));
+        GP_CUDA(c, cudaMemcpyAsync(d_res + N, in->reserved_mem_bytes, 8 * N, cudaMemcpyHostToDevice, st));
+        if (in->reserved_gpu) GP_CUDA(c, cudaMemcpyAsync(d_res + 2 * N, in->reserved_gpu, 8 * N, cudaMemcpyHostToDevice, st));
+    }
+    if (has_host) {
+        GP_CUDA(c, cudaMemcpyAsync(d_hoff, in->host_off, 8 * (Q + 1), cudaMemcpyHostToDevice, st));
+        if (H) GP_CUDA(c, cudaMemcpyAsync(d_hn, in->host_nodes, 4 * H, cudaMemcpyHostToDevice, st));
+    }
+    ReschedIn ri{};
+    ri.exe_cpu = d_exe; ri.exe_mem = d_exe + Q; ri.exe_gpu = in->exe_gpu ? d_exe + 2 * Q : nullptr;
+    ri.group = in->group ? d_grp : nullptr;
+    ri.res_cpu = has_res ? d_res : nullptr; ri.res_mem = has_res ? d_res + N : nullptr;
+    ri.res_gpu = (has_res && in->reserved_gpu) ? d_res + 2 * N : nullptr;
+    ri.host_off = has_host ? d_hoff : nullptr; ri.host_nodes = d_hn;
+    ri.node_slot = c->node_slot.as<int32_t>();
+    ri.n_execs = q;
+    const Snapshot s = make_snapshot(c);
+    const int T = 256;
+    int64_t blocks = ((int64_t)q * 32 + T - 1) / T;
+    const int64_t max_blocks = (int64_t)c->sm_count * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (mf) gp_reschedule_kernel<true><<<(int)blocks, T, 0, st>>>(s, ri, d_out, d_err);
+    else gp_reschedule_kernel<false><<<(int)blocks, T, 0, st>>>(s, ri, d_out, d_err);
+    GP_CUDA(c, cudaGetLastError());
+    int err = 0;
+    GP_CUDA(c, cudaMemcpyAsync(node_out, d_out, 4 * Q, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    if (err) return fail(c, GP_ERR_INVALID, "gp_reschedule_executors: instance group out of range");
+    return GP_OK;
+}
+
 
 }  // extern "C"

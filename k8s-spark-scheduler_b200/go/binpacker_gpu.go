@@ -227,29 +227,162 @@ func gpuPacker(algo C.gp_algo, fallback binpack.SparkBinPackFunction) binpack.Sp
 		}
 		// PackingEfficiencies (metrics/debug log only for these two packers, EXT/resource.go:329-352) are
 		// computed on the host from the result when a caller asks for them:
-		res.PackingEfficiencies = efficienciesFor(nodesSchedulingMetadata, driverResources, executorResources, res)
+		res.PackingEfficiencies = efficienciesFor(nodesSchedulingMetadata, driverResources, executorResources, res,
+			algo != C.GP_MINIMAL_FRAGMENTATION)
 		return res
 	}
 }
 
 // efficienciesFor rebuilds the reserved map of SparkBinPack (binpack.go:72-77) from the placement and
-// calls the reference's own ComputePackingEfficiencies.
-func efficienciesFor(md resources.NodeGroupSchedulingMetadata, drv, exe *resources.Resources, r *binpack.PackingResult) map[string]*binpack.PackingEfficiency {
+// calls the reference's own ComputePackingEfficiencies.  tightlyPackExecutors / distributeExecutorsEvenly add every
+// executor to that map; minimalFragmentation never touches it (withExecutors=false), which is what the reference's
+// chooseBestResult then sees -- kept as is.
+func efficienciesFor(md resources.NodeGroupSchedulingMetadata, drv, exe *resources.Resources, r *binpack.PackingResult,
+	withExecutors bool) map[string]*binpack.PackingEfficiency {
 	reserved := resources.NodeGroupResources{r.DriverNode: drv.Copy()}
-	for _, n := range r.ExecutorNodes {
-		if reserved[n] == nil {
-			reserved[n] = resources.Zero()
+	if withExecutors {
+		for _, n := range r.ExecutorNodes {
+			if reserved[n] == nil {
+				reserved[n] = resources.Zero()
+			}
+			reserved[n].Add(exe)
 		}
-		reserved[n].Add(exe)
 	}
 	return binpack.ComputePackingEfficiencies(md, reserved)
 }
 
-// TightlyPack / DistributeEvenly are drop-in values for binpack.TightlyPack / binpack.DistributeEvenly.
+// TightlyPack / DistributeEvenly / MinimalFragmentation are drop-in values for binpack.TightlyPack /
+// binpack.DistributeEvenly / binpack.MinimalFragmentation.
 var (
-	TightlyPack      = gpuPacker(C.GP_TIGHTLY_PACK, binpack.TightlyPack)
-	DistributeEvenly = gpuPacker(C.GP_DISTRIBUTE_EVENLY, binpack.DistributeEvenly)
+	TightlyPack          = gpuPacker(C.GP_TIGHTLY_PACK, binpack.TightlyPack)
+	DistributeEvenly     = gpuPacker(C.GP_DISTRIBUTE_EVENLY, binpack.DistributeEvenly)
+	MinimalFragmentation = gpuPacker(C.GP_MINIMAL_FRAGMENTATION, binpack.MinimalFragmentation)
 )
+
+// singleAZ is getSingleAZSparkBinFunction + chooseBestResult (LIB/binpack/single_az.go:23-97) over a device packer
+// (both are unexported in the lib, hence restated here with its exported efficiency helpers).  The C++ mirror packs all
+// zones in ONE device batch (zone = instance group, host/gangpack_host.hpp SingleAZPackImpl); this thin version calls
+// the per-zone packer once per zone.
+func singleAZ(perZone binpack.SparkBinPackFunction) binpack.SparkBinPackFunction {
+	return func(ctx context.Context, driverResources, executorResources *resources.Resources, executorCount int,
+		driverNodePriorityOrder, executorNodePriorityOrder []string,
+		md resources.NodeGroupSchedulingMetadata) *binpack.PackingResult {
+		group := func(names []string) ([]string, map[string][]string) { // groupNodesByZone, :57-73
+			order, byZone := []string{}, map[string][]string{}
+			for _, n := range names {
+				m, ok := md[n]
+				if !ok {
+					continue
+				}
+				if _, seen := byZone[m.ZoneLabel]; !seen {
+					order = append(order, m.ZoneLabel)
+				}
+				byZone[m.ZoneLabel] = append(byZone[m.ZoneLabel], n)
+			}
+			return order, byZone
+		}
+		zones, dz := group(driverNodePriorityOrder)
+		_, ez := group(executorNodePriorityOrder)
+		best, bestAvg := binpack.EmptyPackingResult(), binpack.WorstAvgPackingEfficiency() // :79-80
+		for _, z := range zones {
+			eo, ok := ez[z]
+			if !ok {
+				continue // :38-41
+			}
+			r := perZone(ctx, driverResources, executorResources, executorCount, dz[z], eo, md)
+			if !r.HasCapacity {
+				continue // :44-46
+			}
+			effs := make([]*binpack.PackingEfficiency, 0, 1+len(r.ExecutorNodes)) // :83-89
+			for _, n := range append([]string{r.DriverNode}, r.ExecutorNodes...) {
+				effs = append(effs, r.PackingEfficiencies[n])
+			}
+			if avg := binpack.ComputeAvgPackingEfficiency(md, effs); bestAvg.LessThan(avg) { // :90-94
+				best, bestAvg = r, avg
+			}
+		}
+		return best
+	}
+}
+
+// Drop-in values for binpack.SingleAZTightlyPack / binpack.SingleAZMinimalFragmentation / binpack.AzAwareTightlyPack.
+var (
+	SingleAZTightlyPack          = singleAZ(TightlyPack)
+	SingleAZMinimalFragmentation = singleAZ(MinimalFragmentation)
+	AzAwareTightlyPack           = binpack.SparkBinPackFunction(func(ctx context.Context, d, e *resources.Resources, k int,
+		dord, eord []string, md resources.NodeGroupSchedulingMetadata) *binpack.PackingResult {
+		if r := SingleAZTightlyPack(ctx, d, e, k, dord, eord, md); r.HasCapacity { // az_aware_pack_tightly.go:33-37
+			return r
+		}
+		return TightlyPack(ctx, d, e, k, dord, eord, md)
+	})
+)
+
+// RescheduleExecutorNode is the node choice of rescheduleExecutor (EXT/resource.go:652-662, 675-705) on the device:
+// minFrag selects rescheduleExecutorWithMinimalFragmentation (`md` = availableNodesSchedulingMetadata of :640, `overhead`
+// the map it hands to GetNodeCapacities, `hosting` = getNodesWithExecutorsBelongingToSameApp); otherwise the first
+// node of the order that fits (`md` then carries availableResources of :643).  ok=false: run the Go code instead.
+func RescheduleExecutorNode(minFrag bool, executorResources *resources.Resources, executorNodeNames []string,
+	md resources.NodeGroupSchedulingMetadata, overhead resources.NodeGroupResources, hosting map[string]bool) (node string, found, ok bool) {
+	d, err := getDevice()
+	if err != nil {
+		return "", false, false
+	}
+	ec, em, eg, ok1 := toTriple(executorResources)
+	s, ok2 := marshal(md, nil, executorNodeNames)
+	if !ok1 || !ok2 || len(s.names) == 0 {
+		return "", false, ok1 && ok2
+	}
+	index := make(map[string]int32, len(s.names))
+	for i, n := range s.names {
+		index[n] = int32(i)
+	}
+	rc, rm, rg := make([]int64, len(s.names)), make([]int64, len(s.names)), make([]int64, len(s.names))
+	hostNodes, hostOff := []int32{}, []int64{0, 0}
+	in := C.gp_reschedule{n_execs: 1, exe_cpu_milli: (*C.int64_t)(unsafe.Pointer(&ec)), exe_mem_bytes: (*C.int64_t)(unsafe.Pointer(&em)),
+		exe_gpu: (*C.int64_t)(unsafe.Pointer(&eg))}
+	if minFrag {
+		for n, r := range overhead {
+			if i, known := index[n]; known {
+				var exact bool
+				if rc[i], rm[i], rg[i], exact = toTriple(r); !exact {
+					return "", false, false
+				}
+			}
+		}
+		for n, yes := range hosting {
+			if i, known := index[n]; known && yes {
+				hostNodes = append(hostNodes, i)
+			}
+		}
+		hostOff[1] = int64(len(hostNodes))
+		in.min_frag = 1
+		in.reserved_cpu_milli, in.reserved_mem_bytes, in.reserved_gpu = ptr64(rc), ptr64(rm), ptr64(rg)
+		in.host_off, in.host_nodes = ptr64(hostOff), ptr32(hostNodes)
+	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	d.mu.Lock()
+	defer d.mu.Unlock()
+	if err := d.setSnapshot(s); err != nil {
+		return "", false, false
+	}
+	var out C.int32_t = -1
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	for _, p := range []any{&ec, &em, &eg, ptrOrNil(rc), ptrOrNil(rm), ptrOrNil(rg), &hostOff[0], ptrOrNil32(hostNodes)} {
+		if p != nil {
+			pin.Pin(p)
+		}
+	}
+	if st := C.gp_reschedule_executors(d.ctx, &in, &out); st != C.GP_OK {
+		return "", false, false
+	}
+	if out < 0 {
+		return "", false, true // failureFit, :672
+	}
+	return s.names[out], true, true
+}
 
 // QueuedApp is what fitEarlierDrivers reads from one earlier driver pod (EXT/resource.go:230-243).
 type QueuedApp struct {

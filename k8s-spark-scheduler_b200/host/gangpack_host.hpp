@@ -23,6 +23,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -181,6 +182,7 @@ public:
     }
     const std::string& name(int32_t i) const { return names_.at((size_t)i); }
     size_t n_nodes() const { return names_.size(); }
+    int32_t index(const std::string& n) const { auto it = index_.find(n); return it == index_.end() ? -1 : it->second; }
     void check(int st, const char* what) {
         if (st != GP_OK) throw Error(st, std::string(what) + ": " + gp_last_error(ctx_));
     }
@@ -650,6 +652,49 @@ inline bool FitEarlierDrivers(const binpacker::Binpacker& packer, const std::vec
         }
     }
     return ok;
+}
+
+// The node choice of rescheduleExecutor (resource.go:652-662, 675-705) on the device.  `availableNodesSchedulingMetadata`
+// is the metadata of :640 (minimal-fragmentation branch), `availableResources` the map of :643 (first-fit branch),
+// `overhead` the map the reference hands to GetNodeCapacities as "reserved" (:682).  Returns (node, ok) like
+// rescheduleExecutorWithMinimalFragmentation; ok == false is failureFit (:672).
+inline std::pair<std::string, bool> RescheduleExecutorNode(const binpacker::Binpacker& packer, const resources::Resources& executorResources,
+                                                           const std::vector<std::string>& executorNodeNames,
+                                                           const resources::NodeGroupSchedulingMetadata& availableNodesSchedulingMetadata,
+                                                           const resources::NodeGroupResources& availableResources,
+                                                           const resources::NodeGroupResources& overhead,
+                                                           const std::set<std::string>& nodesWithExecutorsBelongingToThisApp) {
+    gangpack::Device& d = gangpack::Device::Get();
+    const bool minFrag = packer.Name == binpacker::SingleAzMinimalFragmentation;           // :652
+    if (minFrag) {
+        d.SetSnapshot(availableNodesSchedulingMetadata, {}, executorNodeNames);
+    } else {
+        resources::NodeGroupSchedulingMetadata md;
+        for (const auto& kv : availableResources) md[kv.first].AvailableResources = kv.second;
+        d.SetSnapshot(md, {}, executorNodeNames);
+    }
+    const size_t N = d.n_nodes();
+    int64_t ec = executorResources.CPU, em = executorResources.Memory, eg = executorResources.NvidiaGPU;
+    std::vector<int64_t> rc(N, 0), rm(N, 0), rg(N, 0);
+    std::vector<int32_t> hosting;
+    int64_t hoff[2] = {0, 0};
+    gp_reschedule in{};
+    in.n_execs = 1; in.exe_cpu_milli = &ec; in.exe_mem_bytes = &em; in.exe_gpu = &eg; in.min_frag = minFrag ? 1 : 0;
+    if (minFrag) {
+        for (const auto& kv : overhead) {
+            int32_t i = d.index(kv.first);
+            if (i >= 0) { rc[(size_t)i] = kv.second.CPU; rm[(size_t)i] = kv.second.Memory; rg[(size_t)i] = kv.second.NvidiaGPU; }
+        }
+        for (const auto& n : nodesWithExecutorsBelongingToThisApp) { int32_t i = d.index(n); if (i >= 0) hosting.push_back(i); }
+        hoff[1] = (int64_t)hosting.size();
+        in.reserved_cpu_milli = rc.data(); in.reserved_mem_bytes = rm.data(); in.reserved_gpu = rg.data();
+        in.host_off = hoff; in.host_nodes = hosting.data();
+    }
+    int32_t node = -1;
+    if (N == 0) return {std::string(), false};
+    d.check(gp_reschedule_executors(d.ctx(), &in, &node), "gp_reschedule_executors");
+    if (node < 0) return {std::string(), false};
+    return {d.name(node), true};
 }
 
 }  // namespace extender

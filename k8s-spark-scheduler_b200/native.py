@@ -35,7 +35,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
            "gp_free_pinned", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_one",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
-           "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster"]
+           "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors"]
 
 
 class GangpackError(RuntimeError):
@@ -98,6 +98,13 @@ class gp_usage_input(C.Structure):
                 ("res_mem_bytes", C.c_void_p), ("res_gpu", C.c_void_p)]
 
 
+class gp_reschedule(C.Structure):
+    _fields_ = [("n_execs", C.c_int32), ("exe_cpu_milli", C.c_void_p), ("exe_mem_bytes", C.c_void_p), ("exe_gpu", C.c_void_p),
+                ("group", C.c_void_p), ("min_frag", C.c_int32), ("reserved_cpu_milli", C.c_void_p),
+                ("reserved_mem_bytes", C.c_void_p), ("reserved_gpu", C.c_void_p), ("host_off", C.c_void_p),
+                ("host_nodes", C.c_void_p)]
+
+
 class gp_stats(C.Structure):
     _fields_ = [("nodes_scanned", C.c_int64), ("drivers_tried", C.c_int64), ("kernel_launches", C.c_int64),
                 ("pack_kernel_ns", C.c_int64), ("prep_kernel_ns", C.c_int64), ("reserved", C.c_int64 * 3)]
@@ -155,6 +162,8 @@ def load():
     L.gp_potential_nodes.restype = C.c_int
     L.gp_potential_nodes.argtypes = [C.c_void_p, C.POINTER(gp_sort_input), C.c_void_p, C.POINTER(C.c_int32),
                                      C.c_void_p, C.POINTER(C.c_int32)]
+    L.gp_reschedule_executors.restype = C.c_int
+    L.gp_reschedule_executors.argtypes = [C.c_void_p, C.POINTER(gp_reschedule), C.c_void_p]
     _lib = L
     return L
 
@@ -246,6 +255,28 @@ class GangPacker:
         cpu = np.empty(self.n_nodes, np.int64); mem = np.empty(self.n_nodes, np.int64); gpu = np.empty(self.n_nodes, np.int64)
         self._check(load().gp_get_snapshot(self._h, _p(cpu), _p(mem), _p(gpu)))
         return cpu, mem, gpu
+
+    # ---- executors without a usable reservation (rescheduleExecutor's node choice) -----------------
+    def reschedule_executors(self, exe, min_frag=False, group=None, reserved=None, hosting=None):
+        """exe: (cpu[q], mem[q], gpu[q]|None); reserved: (cpu[n], mem[n], gpu[n]|None) or None; hosting: list of
+        per-executor node-index lists (nodes already hosting executors of the same application) or None.
+        -> node index per executor (-1: no capacity)."""
+        ec, em = _np(exe[0], np.int64), _np(exe[1], np.int64)
+        eg = _np(exe[2], np.int64) if len(exe) > 2 else None
+        q = len(ec)
+        grp = _np(group, np.int32)
+        rs = [_np(x, np.int64) for x in reserved] if reserved is not None else [None] * 3
+        hoff = hn = None
+        if hosting is not None:
+            hoff = np.zeros(q + 1, np.int64)
+            np.cumsum([len(h) for h in hosting], out=hoff[1:])
+            hn = np.array([n for h in hosting for n in h] or [0], np.int32)
+        out = np.full(max(q, 1), -9, np.int32)
+        r = gp_reschedule(n_execs=q, exe_cpu_milli=_p(ec), exe_mem_bytes=_p(em), exe_gpu=_p(eg), group=_p(grp),
+                          min_frag=1 if min_frag else 0, reserved_cpu_milli=_p(rs[0]), reserved_mem_bytes=_p(rs[1]),
+                          reserved_gpu=_p(rs[2] if len(rs) > 2 else None), host_off=_p(hoff), host_nodes=_p(hn))
+        self._check(load().gp_reschedule_executors(self._h, C.byref(r), _p(out)))
+        return out[:q]
 
     # ---- availability snapshot from reservations (NodeSchedulingMetadataForNodes) ----------------
     def build_availability(self, alloc, overhead, res_node, res):

@@ -691,6 +691,49 @@ int32_t orc_fifo(orc_cluster* c, int algo, int mode, int32_t n_apps,
     return blocked;
 }
 
+/* ------------------------------------------------------------------ executor reschedule ---- */
+/* The node choice of rescheduleExecutor (EXT/resource.go:594-673) for one executor pod.
+ * first fit (:657-662): `available` of the cluster plays availableResources (:643).
+ * minimal fragmentation (rescheduleExecutorWithMinimalFragmentation, :675-705): `available` plays
+ * availableNodesSchedulingMetadata (:640), reserved_* the overhead map handed to GetNodeCapacities as "reserved"
+ * (:682), hosting_names the nodes of getNodesWithExecutorsBelongingToSameApp (:683). */
+int32_t orc_reschedule_executor(const orc_cluster* c, int min_frag, const orc_res* exe,
+                                const char* const* exec_order, int32_t n_exec,
+                                const char* const* reserved_names, const orc_res* reserved, int32_t n_reserved,
+                                const char* const* hosting_names, int32_t n_hosting) {
+    static const orc_res zero = {0, 0, 0};
+    if (!min_frag) {
+        for (int32_t i = 0; i < n_exec; ++i) {                                            /* :658 */
+            const node_meta* m = meta_lookup(c, exec_order[i]);
+            if (m == NULL) continue;       /* PotentialNodes only yields known names; a missing one cannot be chosen */
+            if (!res_greater_than(exe, &m->available)) return orc_cluster_index(c, exec_order[i]);   /* :659-661 */
+        }
+        return -1;                                                                        /* :672 */
+    }
+    resmap over; resmap_init(&over, n_reserved > 0 ? n_reserved : 4);
+    for (int32_t i = 0; i < n_reserved; ++i) resmap_put(&over, reserved_names[i], &reserved[i]);
+    strmap hosting; strmap_init(&hosting, (uint32_t)(n_hosting > 0 ? n_hosting : 4));    /* map[string]bool, :683 */
+    for (int32_t i = 0; i < n_hosting; ++i)
+        if (strmap_find(&hosting, hosting_names[i]) == NULL) strmap_insert(&hosting, hosting_names[i], 1);
+    const char* best = NULL; int64_t best_cap = 0; int best_hosts = 0;                    /* var best, :685 */
+    for (int32_t i = 0; i < n_exec; ++i) {                      /* GetNodeCapacities (capacity.go:78-102) fused with the loop :686 */
+        const node_meta* m = meta_lookup(c, exec_order[i]);
+        if (m == NULL) continue;                                                          /* capacity.go:87 */
+        const orc_res* r = resmap_get(&over, exec_order[i]);                              /* capacity.go:88-92 */
+        if (r == NULL) r = &zero;
+        int64_t cap = node_capacity(&m->available, r, exe);
+        if (cap < 1) continue;                                                            /* :687 */
+        int hosts = strmap_find(&hosting, exec_order[i]) != NULL;
+        if (best == NULL                                                                  /* :689-691 */
+            || (hosts && !best_hosts)                                                     /* :692-694 */
+            || (hosts == best_hosts && cap < best_cap)) {                                 /* :695-697 */
+            best = exec_order[i]; best_cap = cap; best_hosts = hosts;
+        }
+    }
+    resmap_free(&over); strmap_free(&hosting);
+    return best ? orc_cluster_index(c, best) : -1;                                        /* :702 */
+}
+
 /* ------------------------------------------------------------------ snapshot build ---- */
 /* UsageForNodes (LIB/resources/resources.go:31-43) over hard reservations + UsedSoftReservationResources
  * (internal/cache/softreservations.go:155-170), summed like GetReservedResources

@@ -109,6 +109,15 @@ void orc_potential_nodes(const orc_cluster*, const char* const* candidate_names,
                          int32_t* driver_out, int32_t* n_driver_out,
                          int32_t* exec_out, int32_t* n_exec_out);
 
+/* rescheduleExecutor's node choice (EXT/resource.go:594-705) for one executor: first fit over the
+ * executor order (min_frag == 0) or rescheduleExecutorWithMinimalFragmentation (min_frag != 0; reserved_* = the
+ * overhead map it passes to GetNodeCapacities, hosting_names = nodes already hosting executors of the same
+ * application).  Returns the cluster index of the chosen node or -1. */
+int32_t orc_reschedule_executor(const orc_cluster*, int min_frag, const orc_res* exe,
+                                const char* const* exec_order, int32_t n_exec,
+                                const char* const* reserved_names, const orc_res* reserved, int32_t n_reserved,
+                                const char* const* hosting_names, int32_t n_hosting);
+
 /* Snapshot build: GetReservedResources (EXT/resourcereservations.go:258-263: UsageForNodes over
  * the hard reservations, LIB/resources/resources.go:31-43, plus the soft reservations,
  * internal/cache/softreservations.go:155-170) and NodeSchedulingMetadataForNodes (resources.go:61-100).

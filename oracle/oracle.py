@@ -64,6 +64,9 @@ def lib():
         L.orc_node_scheduling_metadata.restype = None
         L.orc_node_scheduling_metadata.argtypes = [C.c_int32, C.POINTER(C.c_char_p)] + [C.c_void_p] * 6 + [
             C.c_int64, C.POINTER(C.c_char_p)] + [C.c_void_p] * 9
+        L.orc_reschedule_executor.restype = C.c_int32
+        L.orc_reschedule_executor.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_char_p), C.c_int32,
+                                              C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.c_int32]
         L.orc_closed_batch.restype = C.c_int32
         L.orc_closed_batch.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
@@ -165,6 +168,17 @@ class Cluster:
                                  _names(driver_order), len(driver_order), _names(exec_order), len(exec_order),
                                  int(with_efficiencies), _ptr(off), _ptr(driver_node), _ptr(executor_nodes))
         return blocked, driver_node, executor_nodes, off
+
+    def reschedule_executor(self, min_frag, exe, exec_order, reserved=None, hosting=()):
+        """rescheduleExecutor's node choice -> node name or None.  reserved: {name: (cpu, mem, gpu)}."""
+        e = np.array(exe, dtype=np.int64)
+        reserved = reserved or {}
+        rn = list(reserved)
+        rv = np.ascontiguousarray([reserved[k] for k in rn] or [(0, 0, 0)], dtype=np.int64)
+        hosting = list(hosting)
+        i = lib().orc_reschedule_executor(self._h, int(bool(min_frag)), _ptr(e), _names(exec_order), len(exec_order),
+                                          _names(rn), _ptr(rv), len(rn), _names(hosting), len(hosting))
+        return self.names[i] if i >= 0 else None
 
     def potential_nodes(self, candidate_names, driver_label_rank=None, exec_label_rank=None):
         d = np.empty(max(self.n, 1), np.int32); e = np.empty(max(self.n, 1), np.int32)

@@ -380,6 +380,32 @@ def az_aware_tightly_pack(drv, exe, count, driver_order, exec_order, meta, sched
 
 
 # ---------------------------------------------------------------------------------------------
+# executor reschedule
+# ---------------------------------------------------------------------------------------------
+def reschedule_first_fit(exe, exec_order, available):
+    """rescheduleExecutor, EXT/resource.go:657-662: first node of the order the executor fits on, else None."""
+    for n in exec_order:
+        if n in available and not gt(exe, available[n]):
+            return n
+    return None
+
+
+def reschedule_minimal_fragmentation(exe, exec_order, meta, overhead, hosting):
+    """rescheduleExecutorWithMinimalFragmentation, EXT/resource.go:675-705 (overhead is what it passes to
+    GetNodeCapacities as `reserved`; hosting = getNodesWithExecutorsBelongingToSameApp)."""
+    best = None
+    for n, cap in node_capacities(exec_order, meta, overhead, exe):
+        if cap >= 1:
+            if best is None:
+                best = (n, cap)
+            elif (n in hosting) and (best[0] not in hosting):
+                best = (n, cap)
+            elif ((n in hosting) == (best[0] in hosting)) and cap < best[1]:
+                best = (n, cap)
+    return best[0] if best else None
+
+
+# ---------------------------------------------------------------------------------------------
 # snapshot build (SURVEY 8f row f2)
 # ---------------------------------------------------------------------------------------------
 def node_scheduling_metadata(alloc, overhead, reservations):

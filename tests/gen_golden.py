@@ -196,6 +196,44 @@ def main():
                                       ["f"] * 17 + ["d"] * 5 + ["e"] * 5 + ["c"] * 3 + ["a", "b"], pinned="derived"))
     minfrag_cases.append(minfrag_case("MF-33", "derived: one more than the cluster holds", 33, pinned="derived"))
 
+    # ---- executor reschedule: the node choice pinned by the reference's own tests ----------------
+    resched_cases = []
+
+    def resched_case(cid, source, node_list, exe, order, min_frag, hosting=(), overhead=None, pinned=None):
+        meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in node_list}
+        if min_frag:
+            got = pyref.reschedule_minimal_fragmentation(tuple(exe), order, meta, overhead or {}, set(hosting))
+        else:
+            got = pyref.reschedule_first_fit(tuple(exe), order, meta)
+        if pinned is not None:
+            assert got == pinned, (cid, got, pinned)
+        return {"id": cid, "source": source, "nodes": node_list, "exe": list(exe), "exec_order": order, "min_frag": bool(min_frag),
+                "hosting": list(hosting), "overhead": {k: list(v) for k, v in (overhead or {}).items()},
+                "expect": got, "pinned": "reference-test" if pinned is not None else "derived"}
+
+    # TestMinimalFragmentation (resource_test.go:73-124): static-app (driver + 2 executors, 1 cpu / 1 B each) sits on node1,
+    # dyn-app's driver and exec-0 sit on node2; exec-1 is offered [node1, node2] and must go to node2 although node1 sorts first
+    resched_cases.append(resched_case(
+        "R-MF1", "internal/extender/resource_test.go:73-124 TestMinimalFragmentation: 'attracted to the node already hosting the first executor'",
+        nodes(("node1", 5000, 8 * Gi - 3, 0), ("node2", 6000, 8 * Gi - 2, 0)), (1000, 1, 0), ["node1", "node2"], True,
+        hosting=["node2"], pinned="node2"))
+    # TestMinimalFragmentationEdgeCase (resource_test.go:126-165): node1 hosts a 1-cpu / 4-B driver, node2 a 4-cpu / 1-B driver;
+    # the 3-cpu executor has capacity 2 on node1 and 1 on node2 -> node2 ("has the smallest capacity"), no node hosts the app yet
+    resched_cases.append(resched_case(
+        "R-MF2", "internal/extender/resource_test.go:126-165 TestMinimalFragmentationEdgeCase: 'scheduled on node2 as it has the smallest capacity'",
+        nodes(("node1", 7000, 8 * Gi - 4, 0), ("node2", 4000, 8 * Gi - 1, 0)), (3000, 1, 0), ["node1", "node2"], True, pinned="node2"))
+    resched_cases.append(resched_case(
+        "R-MF3", "derived: the overhead map is taken off again inside GetNodeCapacities (resource.go:682) -> node1 drops to capacity 0",
+        nodes(("node1", 3000, 8 * Gi, 0), ("node2", 9000, 8 * Gi, 0)), (3000, 1, 0), ["node1", "node2"], True,
+        overhead={"node1": (500, 0, 0)}))
+    resched_cases.append(resched_case(
+        "R-FF1", "derived: first fit over the executor order (resource.go:657-662)",
+        nodes(("node1", 500, 8 * Gi, 0), ("node2", 1000, 8 * Gi, 0), ("node3", 8000, 8 * Gi, 0)), (1000, 1, 0),
+        ["node1", "node2", "node3"], False))
+    resched_cases.append(resched_case(
+        "R-FF2", "derived: nothing fits -> 'not enough capacity to reschedule the executor' (resource.go:672)",
+        nodes(("node1", 500, 8 * Gi, 0)), (1000, 1, 0), ["node1"], False))
+
     # ---- FIFO loop (fitEarlierDrivers) ----------------------------------------------------------
     fifo_cases = []
 
@@ -272,7 +310,7 @@ def main():
 
     out = {"_comment": "generated by tests/gen_golden.py -- do not edit by hand",
            "units": {"cpu": "millicores", "mem": "bytes", "gpu": "units"},
-           "pack_cases": cases, "zone_cases": zone_cases, "minfrag_cases": minfrag_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
+           "pack_cases": cases, "zone_cases": zone_cases, "minfrag_cases": minfrag_cases, "resched_cases": resched_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
     path = os.path.join(ROOT, "tests", "golden", "hotpath_vectors.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:

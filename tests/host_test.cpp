@@ -346,12 +346,39 @@ static void TestZoneAwareFifoAgainstOracle() {
     }
 }
 
+// resource_test.go:73-165: the two reference tests that pin rescheduleExecutorWithMinimalFragmentation's node choice
+static void TestMinimalFragmentationReschedule() {
+    const binpacker::Binpacker& mf = *binpacker::SelectBinpacker("single-az-minimal-fragmentation");
+    {   // TestMinimalFragmentation: static-app (driver + 2 executors) on node1, dyn-app driver + exec-0 on node2
+        NodeGroupSchedulingMetadata md;
+        md["node1"] = Node(5000, 8 * Gi - 3, 0, 8000, 8 * Gi, 1, "zone1");
+        md["node2"] = Node(6000, 8 * Gi - 2, 0, 8000, 8 * Gi, 1, "zone1");
+        auto r = extender::RescheduleExecutorNode(mf, CreateResources(1000, 1, 0), {"node1", "node2"}, md, {}, {}, {"node2"});
+        EXPECT(r.second && r.first == "node2", "The dynamic pod should be attracted to the node already hosting the first executor");
+    }
+    {   // TestMinimalFragmentationEdgeCase
+        NodeGroupSchedulingMetadata md;
+        md["node1"] = Node(7000, 8 * Gi - 4, 0, 8000, 8 * Gi, 1, "zone1");
+        md["node2"] = Node(4000, 8 * Gi - 1, 0, 8000, 8 * Gi, 1, "zone1");
+        auto r = extender::RescheduleExecutorNode(mf, CreateResources(3000, 1, 0), {"node1", "node2"}, md, {}, {}, {});
+        EXPECT(r.second && r.first == "node2", "This pod should be scheduled on node2 as it has the smallest capacity");
+        resources::NodeGroupResources avail;
+        avail["node1"] = CreateResources(7000, 8 * Gi - 4, 0); avail["node2"] = CreateResources(4000, 8 * Gi - 1, 0);
+        auto ff = extender::RescheduleExecutorNode(*binpacker::SelectBinpacker("tightly-pack"), CreateResources(3000, 1, 0),
+                                                   {"node1", "node2"}, md, avail, {}, {});
+        EXPECT(ff.second && ff.first == "node1", "every other packer takes the first node of the order that fits (resource.go:657-662)");
+        auto none = extender::RescheduleExecutorNode(mf, CreateResources(9000, 1, 0), {"node1", "node2"}, md, {}, {}, {});
+        EXPECT(!none.second, "not enough capacity to reschedule the executor");
+    }
+}
+
 int main() {
     TestScheduler();
     TestHarnessThroughSingleAz();
     TestZoneGoldens();
     TestRandomAgainstOracle();
     TestZoneAwareFifoAgainstOracle();
+    TestMinimalFragmentationReschedule();
     TestUnschedulablePodMarker();
     TestSchedulerFailsToScheduleWhenNotEnoughNvidiaGPUs();
     TestSelectBinpacker();

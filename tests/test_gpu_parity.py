@@ -685,3 +685,94 @@ def test_minfrag_is_independent_mode_only(packer):
         assert e.value.status == 1
     dn, en, _ = packer.pack_batch(base, MF_DEV, 0)
     assert dn[0] == 0 and en[0] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# executor reschedule: gp_reschedule_executors == rescheduleExecutor's node choice
+# ---------------------------------------------------------------------------------------------------------------
+def test_reschedule_goldens(golden, packer):
+    for case in golden["resched_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        order = order_indices(case["exec_order"], names)
+        packer.set_snapshot(cpu, mem, gpu, order, order)
+        idx = {n: i for i, n in enumerate(names)}
+        reserved = None
+        if case["overhead"]:
+            reserved = [np.zeros(len(names), np.int64) for _ in range(3)]
+            for k, v in case["overhead"].items():
+                for d in range(3):
+                    reserved[d][idx[k]] = v[d]
+        exe = ([case["exe"][0]], [case["exe"][1]], [case["exe"][2]])
+        got = packer.reschedule_executors(exe, min_frag=case["min_frag"], reserved=reserved,
+                                          hosting=[[idx[h] for h in case["hosting"]]] if case["min_frag"] else None)
+        want = idx[case["expect"]] if case["expect"] is not None else -1
+        assert got[0] == want, case["id"]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_reschedule_random(oracle, packer, seed):
+    rng = np.random.default_rng(9100 + seed)
+    for trial in range(6):
+        n = int(rng.integers(1, 400))
+        names = ["n%03d" % i for i in range(n)]
+        cpu = (rng.integers(-1, 9, n) * 1000).astype(np.int64)
+        mem = (rng.integers(0, 9, n) * (1 << 30) + rng.integers(0, 5, n)).astype(np.int64)
+        gpu = rng.integers(0, 3, n).astype(np.int64)
+        order = rng.permutation(n)[: int(rng.integers(1, n + 1))].astype(np.int32)
+        packer.set_snapshot(cpu, mem, gpu, order, order)
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        onames = [names[i] for i in order]
+        q = 64
+        ec = (rng.integers(0, 4, q) * 1000).astype(np.int64)
+        em = (rng.integers(0, 3, q) * (1 << 30) + (rng.integers(0, 3, q) == 0) * 3).astype(np.int64)
+        eg = rng.integers(0, 2, q).astype(np.int64)
+        res = [(rng.integers(0, 3, n) * 500).astype(np.int64), (rng.integers(0, 2, n) * (1 << 29)).astype(np.int64), np.zeros(n, np.int64)]
+        over = {names[i]: (int(res[0][i]), int(res[1][i]), 0) for i in range(n)}
+        hosting = [[int(x) for x in rng.permutation(n)[: int(rng.integers(0, 6))]] for _ in range(q)]
+        ff = packer.reschedule_executors((ec, em, eg))
+        mf = packer.reschedule_executors((ec, em, eg), min_frag=True, reserved=res, hosting=hosting)
+        mf0 = packer.reschedule_executors((ec, em, eg), min_frag=True)
+        for i in range(q):
+            exe = (int(ec[i]), int(em[i]), int(eg[i]))
+            w = cl.reschedule_executor(False, exe, onames)
+            assert ff[i] == (names.index(w) if w else -1), (seed, trial, i, "first fit")
+            w = cl.reschedule_executor(True, exe, onames, over, [names[h] for h in hosting[i]])
+            assert mf[i] == (names.index(w) if w else -1), (seed, trial, i, "min frag")
+            w = cl.reschedule_executor(True, exe, onames)
+            assert mf0[i] == (names.index(w) if w else -1), (seed, trial, i, "min frag, no overhead / hosting")
+
+
+def test_reschedule_groups_and_errors(oracle, packer):
+    import k8s_spark_scheduler_b200.synth as synth
+    from k8s_spark_scheduler_b200 import GangpackError
+    G = 3
+    nodes = synth.make_nodes(600, groups=G)
+    eoff, eorder = synth.group_orders(nodes)
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], eorder, eorder, eoff, eoff)
+    names = synth.node_names(600)
+    rng = np.random.default_rng(5)
+    q = 90
+    grp = rng.integers(0, G, q).astype(np.int32)
+    ec = (rng.integers(1, 9, q) * 500).astype(np.int64); em = (rng.integers(1, 9, q) << 29).astype(np.int64)
+    ff = packer.reschedule_executors((ec, em, None)[:2] + (np.zeros(q, np.int64),), group=grp)
+    mf = packer.reschedule_executors((ec, em, np.zeros(q, np.int64)), min_frag=True, group=grp)
+    for g in range(G):
+        order = eorder[eoff[g]:eoff[g + 1]]
+        cl = oracle.Cluster([names[i] for i in order], nodes["avail_cpu"][order], nodes["avail_mem"][order], nodes["avail_gpu"][order])
+        onames = [names[i] for i in order]
+        for i in np.nonzero(grp == g)[0]:
+            exe = (int(ec[i]), int(em[i]), 0)
+            w = cl.reschedule_executor(False, exe, onames)
+            assert ff[i] == (names.index(w) if w else -1), (g, i)
+            w = cl.reschedule_executor(True, exe, onames)
+            assert mf[i] == (names.index(w) if w else -1), (g, i)
+    with pytest.raises(GangpackError) as e:
+        packer.reschedule_executors(([-1], [1], [0]))
+    assert e.value.status == 1
+    with pytest.raises(GangpackError) as e:
+        packer.reschedule_executors(([1], [1], [0]), group=[7])
+    assert e.value.status == 1
+    with pytest.raises(GangpackError) as e:
+        packer.reschedule_executors(([1], [1], [0]), min_frag=True, hosting=[[100000]])
+    assert e.value.status == 1
+    assert len(packer.reschedule_executors(([], [], []))) == 0

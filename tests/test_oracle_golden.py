@@ -237,3 +237,34 @@ def test_snapshot_build_oracles_agree(oracle):
         assert (av[0][i], av[1][i], av[2][i]) == pa[nm]
         assert (sc[0][i], sc[1][i], sc[2][i]) == ps[nm]
     assert (av[0] < 0).any()      # over-committed nodes exist: availability may be negative
+
+
+def test_reschedule_goldens(golden, oracle):
+    """rescheduleExecutor's node choice: two vectors pinned by the reference's own tests
+    (TestMinimalFragmentation / TestMinimalFragmentationEdgeCase) plus derived ones, on the literal C oracle"""
+    assert sum(c["pinned"] == "reference-test" for c in golden["resched_cases"]) == 2
+    for case in golden["resched_cases"]:
+        names, cpu, mem, gpu = case_arrays(case["nodes"])
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        got = cl.reschedule_executor(case["min_frag"], case["exe"], case["exec_order"],
+                                     {k: tuple(v) for k, v in case["overhead"].items()}, case["hosting"])
+        assert got == case["expect"], case["id"]
+
+
+def test_reschedule_random_two_way(oracle):
+    """literal C == pure Python on random clusters: ties in capacity, hosting sets, overhead larger than what is left"""
+    from oracle import pyref
+    rng = np.random.default_rng(4242)
+    for trial in range(300):
+        n = int(rng.integers(1, 30))
+        names = ["n%02d" % i for i in range(n)]
+        cpu = rng.integers(-1, 9, n) * 1000; mem = rng.integers(0, 9, n) * (1 << 30); gpu = rng.integers(0, 3, n)
+        cl = oracle.Cluster(names, cpu, mem, gpu)
+        meta = {names[i]: (int(cpu[i]), int(mem[i]), int(gpu[i])) for i in range(n)}
+        order = [names[i] for i in rng.permutation(n)[: int(rng.integers(1, n + 1))]] + ["ghost"]
+        exe = (int(rng.integers(0, 4)) * 1000, int(rng.integers(0, 3)) << 30, int(rng.integers(0, 2)))
+        over = {names[i]: (int(rng.integers(0, 3)) * 500, int(rng.integers(0, 2)) << 29, 0) for i in range(n) if rng.random() < 0.3}
+        hosting = [names[i] for i in range(n) if rng.random() < 0.25]
+        assert cl.reschedule_executor(False, exe, order) == pyref.reschedule_first_fit(exe, order, meta), trial
+        assert cl.reschedule_executor(True, exe, order, over, hosting) == \
+            pyref.reschedule_minimal_fragmentation(exe, order, meta, over, set(hosting)), trial
