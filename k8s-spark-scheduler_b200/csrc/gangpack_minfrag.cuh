@@ -12,7 +12,8 @@
 //     closed form of gangpack_kernels.cuh;
 //   * M = max c.  If k < M the reference first tries the subset {c < target}, target = (k + M) / 2 in Go's wrapping
 //     int arithmetic (:80-89); that attempt succeeds iff the subset's capacities add up to k.  Otherwise every node is
-//     used (:93);
+//     used (:93).  Because target >= k, the subset is either answered by the smallest c >= k or equals {c < k}: no
+//     extra pass (see minfrag_emit);
 //   * inside the chosen set: if some c >= k, all k executors go to the smallest such c (earliest node among equals,
 //     :106-113).  Otherwise nodes are consumed whole in (c descending, priority order ascending) while the remainder is
 //     >= c (:116-127): with F(v) = sum of c over {c >= v}, v* = max{v : F(v) > k} (binary search, one reduction pass per
@@ -100,54 +101,42 @@ __device__ __forceinline__ void minfrag_emit(const CP& cp, int32_t ne, int32_t d
                                              int2* __restrict__ list, WarpStats& st, int lane) {
     typedef typename CP::T T;
     const T kT = (T)k;
-    const T none_limit = ~(T)0;
     auto capd = [&](int32_t i) -> T { return i == dslot ? cd : cp.cap0(i); };
 
-    // ---- pass 1: M, sum min(c, k), and the smallest c >= k over every node ----------------------------------
-    T M = 0;
-    unsigned long long total_all = 0;
-    T best_c = 0; int32_t best_p = -1;
+    // ---- pass 1 (the only full pass most applications need): M, the smallest c >= k, and sum / max of {c < k} ----
+    T M = 0, max_lt = 0;
+    unsigned long long sum_lt = 0;           // sum of c over {c < k}
+    T best_c = 0; int32_t best_p = -1;       // smallest c >= k, earliest position among equals
     for (int32_t p0 = 0; p0 < ne; p0 += kWarp) {
         const int32_t i = p0 + lane;
         const T c = i < ne ? capd(i) : (T)0;
         M = c > M ? c : M;
-        total_all += warp_sum((uint32_t)(c < kT ? c : kT));
+        const T lt = c < kT ? c : (T)0;
+        max_lt = lt > max_lt ? lt : max_lt;
+        sum_lt += warp_sum((uint32_t)lt);
         if (c >= kT) note_min_key(c, i, best_c, best_p);
     }
     st.nodes += (unsigned long long)ne;
     M = warp_max_t(M);
-    T limit = none_limit;                    // the set is {0 < c <= limit}
-    T U = M;
-    unsigned long long total = total_all;
-    if (kT < M) {
-        // target = (executorCount + maxCapacity) / 2 with Go's wrapping 64-bit int (minimal_fragmentation.go:81)
-        const int64_t target = (int64_t)((uint64_t)k + (uint64_t)M) / 2;
-        if (target > 1) {
-            const T tg = (T)target;
-            T us = 0;
-            unsigned long long sum_s = 0;
-            T sb_c = 0; int32_t sb_p = -1;
-            for (int32_t p0 = 0; p0 < ne; p0 += kWarp) {
-                const int32_t i = p0 + lane;
-                T c = i < ne ? capd(i) : (T)0;
-                if (c >= tg) c = 0;
-                us = c > us ? c : us;
-                sum_s += warp_sum((uint32_t)(c < kT ? c : kT));
-                if (c >= kT) note_min_key(c, i, sb_c, sb_p);
-            }
-            st.nodes += (unsigned long long)ne;
-            if (sum_s >= k) {                // the subset can host everything (:87-89)
-                limit = tg - 1; U = warp_max_t(us); total = sum_s;
-                best_c = sb_c; best_p = sb_p;
-            }
-        }
-    }
     warp_min_key(best_c, best_p);
+    // The subset {c < target}, target = (executorCount + maxCapacity) / 2 in Go's wrapping 64-bit int
+    // (minimal_fragmentation.go:80-89), needs no pass of its own.  k < M makes target >= k when the sum does not wrap,
+    // so with b = the smallest c >= k (it exists, M > k):  b < target -> the subset contains b, is feasible through b
+    // alone and b is its answer as well;  b >= target -> no c of the subset reaches k and every c < k is below target,
+    // i.e. the subset is exactly {c < k}.  A wrapped or tiny target (<= 1) empties the subset; the reference then uses
+    // every node (:93), whose answer is b.
+    T limit = ~(T)0;                         // the set is {0 < c <= limit}
+    const unsigned long long total = sum_lt; // capacity of the set whenever the greedy part below runs (all its c < k)
+    if (kT < M) {
+        const int64_t target = (int64_t)((uint64_t)k + (uint64_t)M) / 2;
+        if (target > 1 && (uint64_t)best_c >= (uint64_t)target && sum_lt >= k) { limit = kT - 1; best_p = -1; }
+    }
     if (best_p >= 0) {                       // one node takes all k executors (:106-113)
         const int32_t node = slot_node[best_p];
         for (uint32_t j = lane; j < k; j += kWarp) out[j] = node;
         return;
     }
+    const T U = warp_max_t(max_lt);          // largest c of the set
 
     // ---- every c of the set is < k: find v* = max{v : F(v) > k} -----------------------------------------------
     uint32_t vstar = 0;

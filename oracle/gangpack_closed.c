@@ -122,17 +122,22 @@ static void minfrag_emit(const snap* s, int32_t d, int64_t cd, const orc_res* ex
         c[i] = (n == d) ? cd : node_cap(s, n, &zero, exe);
         if (c[i] > M) M = c[i];
     }
+    /* The subset {c < target} of minimal_fragmentation.go:80-89 needs no pass of its own.  k < M makes
+     * target = (k + M) / 2 >= k when the sum does not wrap, so with b = the smallest c >= k (it exists, M > k):
+     *   b < target  -> the subset contains b, is feasible through b alone, and b is its answer as well;
+     *   b >= target -> no c of the subset reaches k and every c < k is below target: the subset is exactly {c < k}.
+     * A wrapped or tiny target (<= 1) empties the subset; the reference then uses every node, whose answer is b. */
     int64_t limit = CAP_INF;      /* the set is {0 < c <= limit} */
+    int32_t best = -1;
+    int64_t sum_lt = 0;
+    for (int32_t i = 0; i < ne; ++i) {
+        if (c[i] >= k && (best < 0 || c[i] < c[best])) best = i;
+        if (c[i] > 0 && c[i] < k) sum_lt += c[i];
+    }
     if ((int64_t)k < M) {
         int64_t target = (int64_t)((uint64_t)k + (uint64_t)M) / 2;   /* Go int wraps; / truncates toward zero */
-        int64_t sum = 0;
-        for (int32_t i = 0; i < ne; ++i) if (c[i] > 0 && c[i] < target) sum += min64(c[i], k);
-        if (sum >= k) limit = target - 1;
+        if (target > 1 && c[best] >= target && sum_lt >= k) { limit = (int64_t)k - 1; best = -1; }
     }
-    /* smallest c >= k inside the set */
-    int32_t best = -1;
-    for (int32_t i = 0; i < ne; ++i)
-        if (c[i] >= k && c[i] <= limit && (best < 0 || c[i] < c[best])) best = i;
     if (best >= 0) {
         for (int32_t t = 0; t < k; ++t) out[t] = s->exec_order[best];
         free(c);
