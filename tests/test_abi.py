@@ -50,8 +50,11 @@ def test_struct_layout_matches_header(native):
     #include <stddef.h>
     #include "gangpack.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu\n", sizeof(gp_config), sizeof(gp_nodes), sizeof(gp_apps), sizeof(gp_results), sizeof(gp_stats));
-      printf("%zu %zu %zu\n", offsetof(gp_nodes, n_groups), offsetof(gp_apps, exec_out_off), offsetof(gp_results, executor_nodes_cap));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(gp_config), sizeof(gp_nodes), sizeof(gp_apps), sizeof(gp_results), sizeof(gp_stats),
+             sizeof(gp_sort_input), sizeof(gp_usage_input), sizeof(gp_reschedule));
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(gp_nodes, n_groups), offsetof(gp_apps, exec_out_off), offsetof(gp_results, executor_nodes_cap),
+             offsetof(gp_sort_input, executor_label_rank), offsetof(gp_usage_input, res_gpu), offsetof(gp_reschedule, min_frag),
+             offsetof(gp_reschedule, host_nodes));
       return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -62,9 +65,12 @@ def test_struct_layout_matches_header(native):
     sizes = [int(x) for x in lines[0].split()]
     offs = [int(x) for x in lines[1].split()]
     assert sizes == [ctypes.sizeof(native.gp_config), ctypes.sizeof(native.gp_nodes), ctypes.sizeof(native.gp_apps),
-                     ctypes.sizeof(native.gp_results), ctypes.sizeof(native.gp_stats)]
+                     ctypes.sizeof(native.gp_results), ctypes.sizeof(native.gp_stats), ctypes.sizeof(native.gp_sort_input),
+                     ctypes.sizeof(native.gp_usage_input), ctypes.sizeof(native.gp_reschedule)]
     assert offs == [native.gp_nodes.n_groups.offset, native.gp_apps.exec_out_off.offset,
-                    native.gp_results.executor_nodes_cap.offset]
+                    native.gp_results.executor_nodes_cap.offset, native.gp_sort_input.executor_label_rank.offset,
+                    native.gp_usage_input.res_gpu.offset, native.gp_reschedule.min_frag.offset,
+                    native.gp_reschedule.host_nodes.offset]
 
 
 def test_no_cpu_fallback(native):
