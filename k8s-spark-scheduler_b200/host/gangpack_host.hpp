@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "gangpack.h"
+#include "spark_resources.hpp"
 
 namespace gangpack {
 struct Error : std::runtime_error {
@@ -569,6 +570,26 @@ struct PendingDriver {                    // what fitEarlierDrivers reads off a 
     bool ParseError = false;              // sparkResources failed -> skipped (resource.go:232-237)
     bool SkipIfNoFit = false;             // shouldSkipDriverFifo (resource.go:264-270): younger than enforce-after-pod-age
 };
+
+// One queued driver pod -> what fitEarlierDrivers needs of it: sparkResources (sparkpods.go:73-137) over its annotations
+// (spark_resources.hpp).  A parse error marks the entry like resource.go:232-237 does (skipped); a quantity outside the
+// exact-int64 model is reported through *exact = false so that the embedding runs the original Go loop instead.
+inline PendingDriver PendingDriverFromAnnotations(const std::string& name, const std::map<std::string, std::string>& annotations,
+                                                  bool skipIfNoFit, bool* exact = nullptr) {
+    PendingDriver d;
+    d.Name = name;
+    d.SkipIfNoFit = skipIfNoFit;
+    ParsedSparkResources r;
+    d.ParseError = !SparkResources(annotations, &r).empty();
+    if (exact) *exact = r.Exact;
+    if (!d.ParseError) {
+        d.Resources.DriverResources = resources::CreateResources(r.DriverCPUMilli, r.DriverMemoryBytes, r.DriverNvidiaGPUs);
+        d.Resources.ExecutorResources = resources::CreateResources(r.ExecutorCPUMilli, r.ExecutorMemoryBytes, r.ExecutorNvidiaGPUs);
+        d.Resources.MinExecutorCount = (int)r.MinExecutorCount;
+        d.Resources.MaxExecutorCount = (int)r.MaxExecutorCount;
+    }
+    return d;
+}
 
 // sparkResourceUsage (sparkpods.go:139-146): ASSIGNMENT semantics, kept bug-for-bug.
 inline resources::NodeGroupResources SparkResourceUsage(const resources::Resources& drv, const resources::Resources& exe,

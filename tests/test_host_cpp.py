@@ -34,3 +34,11 @@ def test_host_layer_suite(host_binary):
     p = subprocess.run([host_binary], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "all passed" in p.stdout
+
+
+def test_host_input_side_on_cpu(host_binary):
+    """driver annotations -> application tuple (sparkResources + the k8s quantity grammar), the reference's own
+    sparkpods_test.go cases; no device involved"""
+    p = subprocess.run([os.path.join(HOST, "host_cpu_test")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "all passed" in p.stdout
