@@ -8,15 +8,18 @@
 //   resource.ParseQuantity grammar        vendor/k8s.io/apimachinery/pkg/api/resource/quantity.go:147-262 (parseQuantityString),
 //                                         :264-300 (ParseQuantity), suffix.go:113-132,180-198 (suffix table / exponents)
 //   Quantity.Value() (executor counts)    quantity.go:732-734 -> rounds a fractional value away from zero
+//   filterToEarliestAndSort (the FIFO queue) internal/extender/sparkpods.go:54-74, internal/podspec.go:22-26
 //
 // A quantity the int64 model cannot hold exactly (finer than a millicore / a byte, or |v| >= 2^61) is reported as
 // Unrepresentable: the embedding then lets the original Go code handle that application -- nothing
 // is rounded silently.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <string>
+#include <vector>
 
 namespace resource {
 
@@ -206,6 +209,34 @@ inline std::string SparkResources(const std::map<std::string, std::string>& anno
     if (dynamicAllocationEnabled) { out->MinExecutorCount = daMin; out->MaxExecutorCount = daMax; }           // :110-115
     else { out->MinExecutorCount = executorCount; out->MaxExecutorCount = executorCount; }                    // :116-120
     return "";
+}
+
+// What ListEarlierDrivers looks at on a driver pod (sparkpods.go:45-74).
+struct QueuedDriverPod {
+    std::string UID;
+    int64_t CreationSeconds = 0;          // CreationTimestamp
+    std::string NodeName;                 // Spec.NodeName ("" = unscheduled)
+    std::string SchedulerName;            // Spec.SchedulerName
+    bool HasInstanceGroup = false;        // FindInstanceGroupFromPodSpec succeeded (podspec.go:29-35)
+    std::string InstanceGroup;
+    bool Deleting = false;                // DeletionTimestamp != nil
+};
+
+// filterToEarliestAndSort (sparkpods.go:54-74): the drivers that must fit before `driver` may be scheduled -- unscheduled,
+// same scheduler, same instance group (MatchPodInstanceGroup, podspec.go:22-26), created strictly earlier, not being
+// deleted -- oldest first.  This is the order of one instance group's queue in a GP_MODE_FIFO_* batch.  (The reference
+// sorts with the unstable sort.Slice; equal timestamps keep their input order here.)
+inline std::vector<QueuedDriverPod> FilterToEarliestAndSort(const QueuedDriverPod& driver, const std::vector<QueuedDriverPod>& allDrivers) {
+    std::vector<QueuedDriverPod> earlier;
+    for (const auto& p : allDrivers) {
+        if (p.NodeName.empty() && p.SchedulerName == driver.SchedulerName &&
+            p.HasInstanceGroup && driver.HasInstanceGroup && p.InstanceGroup == driver.InstanceGroup &&
+            p.CreationSeconds < driver.CreationSeconds && !p.Deleting)
+            earlier.push_back(p);
+    }
+    std::stable_sort(earlier.begin(), earlier.end(),
+                     [](const QueuedDriverPod& a, const QueuedDriverPod& b) { return a.CreationSeconds < b.CreationSeconds; });
+    return earlier;
 }
 
 }  // namespace extender

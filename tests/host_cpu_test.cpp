@@ -100,7 +100,31 @@ static void TestParseQuantity() {   // grammar of quantity.go:147-300, suffix.go
     EXPECT(ParseQuantityScaled("2", 0, &v, true) == ParseStatus::Ok && v == 2, "Value() of 2 is 2");
 }
 
+static extender::QueuedDriverPod Pod(int64_t seconds, const char* uid) {   // createPod, sparkpods_test.go:125-157
+    extender::QueuedDriverPod p;
+    p.UID = uid; p.CreationSeconds = seconds; p.HasInstanceGroup = true; p.InstanceGroup = "instance-group-foobar";
+    return p;
+}
+
+static void TestIsEarliest() {   // sparkpods_test.go:174-226
+    auto uids = [](const std::vector<extender::QueuedDriverPod>& v) { std::vector<std::string> u; for (auto& p : v) u.push_back(p.UID); return u; };
+    typedef std::vector<std::string> U;
+    using extender::FilterToEarliestAndSort;
+    EXPECT(uids(FilterToEarliestAndSort(Pod(100, "1"), {Pod(101, "3"), Pod(150, "2"), Pod(100, "1")})) == U{}, "selects earliest unassigned");
+    EXPECT(uids(FilterToEarliestAndSort(Pod(100, "1"), {Pod(101, "2")})) == U{}, "selects if earliest and not in cache");
+    EXPECT(uids(FilterToEarliestAndSort(Pod(100, "1"), {Pod(101, "3"), Pod(99, "2"), Pod(100, "1")})) == U{"2"}, "does not select when not earliest");
+    EXPECT(uids(FilterToEarliestAndSort(Pod(100, "1"), {Pod(99, "3"), Pod(101, "2")})) == U{"3"}, "does not select when not earliest and not in cache");
+    // the other filters of sparkpods.go:59-64 and the ordering of :70-72
+    auto scheduled = Pod(50, "s"); scheduled.NodeName = "n1";
+    auto other = Pod(60, "o"); other.InstanceGroup = "another-group";
+    auto dying = Pod(70, "d"); dying.Deleting = true;
+    auto foreign = Pod(80, "f"); foreign.SchedulerName = "default-scheduler";
+    EXPECT(uids(FilterToEarliestAndSort(Pod(100, "1"), {Pod(90, "b"), scheduled, other, dying, foreign, Pod(10, "a")})) == (U{"a", "b"}),
+           "unscheduled, same scheduler, same instance group, not deleting; oldest first");
+}
+
 int main() {
+    TestIsEarliest();
     TestSparkResources();
     TestSparkResourcesErrors();
     TestParseQuantity();
