@@ -422,3 +422,106 @@ def node_scheduling_metadata(alloc, overhead, reservations):
         available[n] = sub(a, u)                      # :89
         schedulable[n] = sub(a, o)                    # :90
     return available, schedulable
+
+
+# ---------------------------------------------------------------------------------------------
+# inputs of the path: annotations -> application tuple, the FIFO queue
+# ---------------------------------------------------------------------------------------------
+_DEC_SUFFIX = {"n": -9, "u": -6, "m": -3, "": 0, "k": 3, "M": 6, "G": 9, "T": 12, "P": 15, "E": 18}   # suffix.go:121-132
+_BIN_SUFFIX = {"Ki": 10, "Mi": 20, "Gi": 30, "Ti": 40, "Pi": 50, "Ei": 60}                            # suffix.go:113-118
+
+
+def parse_quantity(s):
+    """resource.ParseQuantity (vendor/k8s.io/apimachinery/pkg/api/resource/quantity.go:147-300) -> (status, Fraction).
+    status: 'ok' | 'ErrFormatWrong' | 'ErrSuffix'.  The value is exact (no rounding to nano, no int64 cap: the callers
+    here decide what their integer model can hold)."""
+    from fractions import Fraction
+    import re
+    if s == "":
+        return "ErrFormatWrong", None
+    m = re.fullmatch(r"([+-]?)([0-9]*)(?:\.([0-9]*))?([eEinumkKMGTP]*[+-]?[0-9]*)", s)
+    if not m:
+        return "ErrFormatWrong", None
+    sign, num, denom, suffix = m.group(1), m.group(2), m.group(3) or "", m.group(4)
+    if suffix in _DEC_SUFFIX:
+        mult = Fraction(10) ** _DEC_SUFFIX[suffix]
+    elif suffix in _BIN_SUFFIX:
+        mult = Fraction(2) ** _BIN_SUFFIX[suffix]
+    elif len(suffix) > 1 and suffix[0] in "eE" and re.fullmatch(r"[+-]?[0-9]+", suffix[1:]):
+        mult = Fraction(10) ** int(suffix[1:])
+    else:
+        return "ErrSuffix", None
+    digits = (num or "0") + denom
+    v = Fraction(int(digits), 10 ** len(denom)) * mult
+    return "ok", (-v if sign == "-" else v)
+
+
+def quantity_scaled(s, scale, round_up_fraction=False):
+    """-> (status, int): the quantity in units of 10^-scale if that is an exact integer below 2^61 ('unrepresentable'
+    otherwise); round_up_fraction reproduces Quantity.Value() (away from zero, quantity.go:732-734)."""
+    st, v = parse_quantity(s)
+    if st != "ok":
+        return st, None
+    v = v * 10 ** scale
+    if v.denominator != 1:
+        if not round_up_fraction:
+            return "unrepresentable", None
+        v = abs(v)
+        v = (v.numerator // v.denominator + 1) * (1 if parse_quantity(s)[1] > 0 else -1)
+    v = int(v)
+    if abs(v) >= 1 << 61:
+        return "unrepresentable", None
+    return "ok", v
+
+
+def spark_resources(annotations):
+    """sparkResources, EXT/sparkpods.go:73-137 -> (error_text | None, dict).  Quantities in millicores / bytes / units;
+    'exact': False when one of them is outside the int64 model."""
+    da = False
+    if "spark-dynamic-allocation-enabled" in annotations:
+        v = annotations["spark-dynamic-allocation-enabled"]
+        if v in ("1", "t", "T", "TRUE", "true", "True"):
+            da = True
+        elif v in ("0", "f", "F", "FALSE", "false", "False"):
+            da = False
+        else:
+            return "annotation DynamicAllocationEnabled could not be parsed as a boolean", None
+    fields = [("spark-driver-cpu", 3), ("spark-driver-mem", 0), ("spark-driver-nvidia.com/gpu", 0), ("spark-executor-cpu", 3),
+              ("spark-executor-mem", 0), ("spark-executor-nvidia.com/gpu", 0), ("spark-executor-count", 0),
+              ("spark-dynamic-allocation-min-executor-count", 0), ("spark-dynamic-allocation-max-executor-count", 0)]
+    counts = {"spark-executor-count", "spark-dynamic-allocation-min-executor-count", "spark-dynamic-allocation-max-executor-count"}
+    parsed, exact = {}, True
+    for a, scale in fields:
+        if a not in annotations:
+            if a in ("spark-driver-nvidia.com/gpu", "spark-executor-nvidia.com/gpu"):
+                continue
+            if not da and a == "spark-executor-count":
+                return "annotation ExecutorCount is required when DynamicAllocationEnabled is false", None
+            if da and a in ("spark-dynamic-allocation-min-executor-count", "spark-dynamic-allocation-max-executor-count"):
+                return "annotation %s is required when DynamicAllocationEnabled is true" % a, None
+            if a in counts:
+                continue
+            return "annotation %s is missing from driver" % a, None
+        st, v = quantity_scaled(annotations[a], scale, round_up_fraction=a in counts)
+        if st == "unrepresentable":
+            exact = False
+            continue
+        if st != "ok":
+            return "annotation %s does not have a parseable value %s" % (a, annotations[a]), None
+        parsed[a] = v
+    g = lambda k: parsed.get(k, 0)
+    lo, hi = ((g("spark-dynamic-allocation-min-executor-count"), g("spark-dynamic-allocation-max-executor-count")) if da
+              else (g("spark-executor-count"), g("spark-executor-count")))
+    return None, {"drv": [g("spark-driver-cpu"), g("spark-driver-mem"), g("spark-driver-nvidia.com/gpu")],
+                  "exe": [g("spark-executor-cpu"), g("spark-executor-mem"), g("spark-executor-nvidia.com/gpu")],
+                  "min": lo, "max": hi, "exact": exact}
+
+
+def filter_to_earliest_and_sort(driver, all_drivers):
+    """filterToEarliestAndSort, EXT/sparkpods.go:54-74.  Pods are dicts {uid, created, node, scheduler, group, deleting}
+    (group None = no instance group found, internal/podspec.go:22-35).  Equal timestamps keep their input order."""
+    earlier = [p for p in all_drivers
+               if not p.get("node") and p.get("scheduler", "") == driver.get("scheduler", "")
+               and p.get("group") is not None and p.get("group") == driver.get("group")
+               and p["created"] < driver["created"] and not p.get("deleting")]
+    return sorted(earlier, key=lambda p: p["created"])

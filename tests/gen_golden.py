@@ -234,6 +234,59 @@ def main():
         "R-FF2", "derived: nothing fits -> 'not enough capacity to reschedule the executor' (resource.go:672)",
         nodes(("node1", 500, 8 * Gi, 0)), (1000, 1, 0), ["node1"], False))
 
+    # ---- inputs of the path: annotations -> tuple, queue membership/order -----------------------
+    Mi = 1 << 20
+    static_ann = {"spark-driver-cpu": "1", "spark-driver-mem": "2432Mi", "spark-driver-nvidia.com/gpu": "1", "spark-executor-cpu": "2",
+                  "spark-executor-mem": "6758Mi", "spark-executor-nvidia.com/gpu": "1", "spark-executor-count": "2"}
+    dyn_ann = {k: v for k, v in static_ann.items() if k != "spark-executor-count"}
+    dyn_ann.update({"spark-dynamic-allocation-enabled": "true", "spark-dynamic-allocation-min-executor-count": "2",
+                    "spark-dynamic-allocation-max-executor-count": "5"})
+    nogpu_ann = {k: v for k, v in static_ann.items() if "gpu" not in k}
+    annotation_cases = []
+
+    def annotation_case(cid, source, ann, pinned=None):
+        err, got = pyref.spark_resources(ann)
+        if pinned is not None:
+            assert err is None and got == pinned, (cid, err, got)
+        return {"id": cid, "source": source, "annotations": ann, "error": err, "expect": got,
+                "pinned": "reference-test" if pinned is not None else "derived"}
+
+    annotation_cases.append(annotation_case("A-static", "internal/extender/sparkpods_test.go:46-66 static allocation", static_ann,
+                                            {"drv": [1000, 2432 * Mi, 1], "exe": [2000, 6758 * Mi, 1], "min": 2, "max": 2, "exact": True}))
+    annotation_cases.append(annotation_case("A-dynamic", "internal/extender/sparkpods_test.go:67-89 dynamic allocation", dyn_ann,
+                                            {"drv": [1000, 2432 * Mi, 1], "exe": [2000, 6758 * Mi, 1], "min": 2, "max": 5, "exact": True}))
+    annotation_cases.append(annotation_case("A-nogpu", "internal/extender/sparkpods_test.go:90-108 no gpu annotations", nogpu_ann,
+                                            {"drv": [1000, 2432 * Mi, 0], "exe": [2000, 6758 * Mi, 0], "min": 2, "max": 2, "exact": True}))
+    annotation_cases.append(annotation_case("A-err-count", "sparkpods.go:90-91", {k: v for k, v in nogpu_ann.items() if k != "spark-executor-count"}))
+    annotation_cases.append(annotation_case("A-err-missing", "sparkpods.go:98", {k: v for k, v in nogpu_ann.items() if k != "spark-executor-mem"}))
+    annotation_cases.append(annotation_case("A-err-parse", "sparkpods.go:101-104", {**nogpu_ann, "spark-executor-mem": "4 GiB"}))
+    annotation_cases.append(annotation_case("A-submilli", "derived: a valid Quantity finer than a millicore is flagged, not rounded",
+                                            {**nogpu_ann, "spark-executor-cpu": "0.0005"}))
+
+    def pod(created, uid, **kw):
+        return {"uid": uid, "created": created, "node": "", "scheduler": "", "group": "instance-group-foobar", "deleting": False, **kw}
+
+    queue_cases = []
+
+    def queue_case(cid, source, driver, pods, pinned=None):
+        got = [p["uid"] for p in pyref.filter_to_earliest_and_sort(driver, pods)]
+        if pinned is not None:
+            assert got == pinned, (cid, got, pinned)
+        return {"id": cid, "source": source, "driver": driver, "pods": pods, "expect": got,
+                "pinned": "reference-test" if pinned is not None else "derived"}
+
+    me = pod(100, "1")
+    queue_cases.append(queue_case("Q1", "internal/extender/sparkpods_test.go:182-189 selects earliest unassigned", me,
+                                  [pod(101, "3"), pod(150, "2"), pod(100, "1")], []))
+    queue_cases.append(queue_case("Q2", "sparkpods_test.go:190-194 selects if earliest and not in cache", me, [pod(101, "2")], []))
+    queue_cases.append(queue_case("Q3", "sparkpods_test.go:195-202 does not select when not earliest", me,
+                                  [pod(101, "3"), pod(99, "2"), pod(100, "1")], ["2"]))
+    queue_cases.append(queue_case("Q4", "sparkpods_test.go:203-209 does not select when not earliest and not in cache", me,
+                                  [pod(99, "3"), pod(101, "2")], ["3"]))
+    queue_cases.append(queue_case("Q5", "derived: the other filters of sparkpods.go:59-64 and the ordering of :70-72", me,
+                                  [pod(90, "b"), pod(50, "s", node="n1"), pod(60, "o", group="another-group"), pod(70, "d", deleting=True),
+                                   pod(80, "f", scheduler="default-scheduler"), pod(10, "a")]))
+
     # ---- FIFO loop (fitEarlierDrivers) ----------------------------------------------------------
     fifo_cases = []
 
@@ -310,7 +363,7 @@ def main():
 
     out = {"_comment": "generated by tests/gen_golden.py -- do not edit by hand",
            "units": {"cpu": "millicores", "mem": "bytes", "gpu": "units"},
-           "pack_cases": cases, "zone_cases": zone_cases, "minfrag_cases": minfrag_cases, "resched_cases": resched_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
+           "pack_cases": cases, "zone_cases": zone_cases, "minfrag_cases": minfrag_cases, "resched_cases": resched_cases, "annotation_cases": annotation_cases, "queue_cases": queue_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
     path = os.path.join(ROOT, "tests", "golden", "hotpath_vectors.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:

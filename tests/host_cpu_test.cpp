@@ -2,6 +2,7 @@
 // annotations -> application tuple step of the reference (internal/extender/sparkpods.go:73-137), written like its own
 // sparkpods_test.go:38-117.  No device, no libgangpack.
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 
@@ -123,7 +124,43 @@ static void TestIsEarliest() {   // sparkpods_test.go:174-226
            "unscheduled, same scheduler, same instance group, not deleting; oldest first");
 }
 
-int main() {
+// CLI used by tests/test_host_cpp.py to cross-check this C++ restatement with the Python one (oracle/pyref.py):
+//   host_cpu_test quantity <scale> <roundUp 0|1> <string>...   -> one "<status> <value>" line per string
+//   host_cpu_test annotations k=v k=v ...                      -> error text, or "ok drv exe min max exact" numbers
+static int Cli(int argc, char** argv) {
+    const std::string mode = argv[1];
+    if (mode == "quantity" && argc >= 4) {
+        const int scale = std::atoi(argv[2]);
+        const bool up = std::atoi(argv[3]) != 0;
+        static const char* const names[] = {"ok", "ErrFormatWrong", "ErrSuffix", "ErrNumeric", "unrepresentable"};
+        for (int i = 4; i < argc; ++i) {
+            int64_t v = 0;
+            resource::ParseStatus st = resource::ParseQuantityScaled(argv[i], scale, &v, up);
+            std::printf("%s %lld\n", names[(int)st], (long long)v);
+        }
+        return 0;
+    }
+    if (mode == "annotations") {
+        Annotations a;
+        for (int i = 2; i < argc; ++i) {
+            std::string kv = argv[i];
+            size_t eq = kv.find('=');
+            a[kv.substr(0, eq)] = eq == std::string::npos ? "" : kv.substr(eq + 1);
+        }
+        ParsedSparkResources r;
+        std::string err = SparkResources(a, &r);
+        if (!err.empty()) { std::printf("%s\n", err.c_str()); return 0; }
+        std::printf("ok %lld %lld %lld %lld %lld %lld %lld %lld %d\n", (long long)r.DriverCPUMilli, (long long)r.DriverMemoryBytes,
+                    (long long)r.DriverNvidiaGPUs, (long long)r.ExecutorCPUMilli, (long long)r.ExecutorMemoryBytes,
+                    (long long)r.ExecutorNvidiaGPUs, (long long)r.MinExecutorCount, (long long)r.MaxExecutorCount, r.Exact ? 1 : 0);
+        return 0;
+    }
+    std::printf("usage: host_cpu_test [quantity <scale> <roundUp> <str>... | annotations k=v ...]\n");
+    return 2;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1) return Cli(argc, argv);
     TestIsEarliest();
     TestSparkResources();
     TestSparkResourcesErrors();

@@ -268,3 +268,16 @@ def test_reschedule_random_two_way(oracle):
         assert cl.reschedule_executor(False, exe, order) == pyref.reschedule_first_fit(exe, order, meta), trial
         assert cl.reschedule_executor(True, exe, order, over, hosting) == \
             pyref.reschedule_minimal_fragmentation(exe, order, meta, over, set(hosting)), trial
+
+
+def test_input_side_goldens(golden):
+    """the reference's sparkpods_test.go pins the annotation -> tuple parsing (3 cases) and the FIFO
+    queue membership/order (4 cases); the Python restatement reproduces the committed vectors"""
+    from oracle import pyref
+    assert sum(c["pinned"] == "reference-test" for c in golden["annotation_cases"]) == 3
+    assert sum(c["pinned"] == "reference-test" for c in golden["queue_cases"]) == 4
+    for case in golden["annotation_cases"]:
+        err, got = pyref.spark_resources(case["annotations"])
+        assert err == case["error"] and got == case["expect"], case["id"]
+    for case in golden["queue_cases"]:
+        assert [p["uid"] for p in pyref.filter_to_earliest_and_sort(case["driver"], case["pods"])] == case["expect"], case["id"]
