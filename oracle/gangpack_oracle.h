@@ -5,13 +5,17 @@
  * include, link or execute this code; only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs do.
  *
- * PARITY STATUS: partially pinned.  The reference's own tests pin this path only coarsely
- * (fit / no-fit for three app shapes, min-executor semantics, node-priority orders); the exact
- * contents/order of ExecutorNodes for tightly-pack / distribute-evenly and the FIFO subtraction
- * are NOT pinned by any test or golden vector in /root/reference (the lib's *_test.go files are
- * not vendored) and Go cannot run here -> for those outputs: "parity unpinned", authority is the
- * cited source lines.  tests/golden/ holds the vectors the reference does pin plus hand-derived
- * ones, re-derived by an independent pure-Python literal restatement.
+ * PARITY STATUS: partially pinned.  Pinned by the reference's own tests / worked examples (tests/golden/, asserted in
+ * tests/test_oracle_golden.py): fit / no-fit for the harness app shapes and min-executor semantics
+ * (EXT/resource_test.go, unschedulablepods_test.go), node-priority orders and label priorities
+ * (internal/sort/nodesorting_test.go), the node chosen by rescheduleExecutorWithMinimalFragmentation
+ * (resource_test.go:73-165), ExecutorNodes of minimalFragmentation for the four doc-comment examples that agree with its
+ * code (LIB/binpack/minimal_fragmentation.go:43-55), annotation -> tuple parsing and FIFO queue membership/order
+ * (EXT/sparkpods_test.go).  NOT pinned by any test or golden vector in /root/reference (the lib's *_test.go files are
+ * not vendored) and Go cannot run here: the exact contents/order of ExecutorNodes for tightly-pack / distribute-evenly
+ * and the FIFO subtraction -> for those outputs: "parity unpinned", authority is the cited source lines; three
+ * independent restatements (literal C, closed-form C, pure Python) must agree on them.  tests/golden/ also holds
+ * hand-derived vectors, re-derived by the pure-Python restatement.
  *
  * Two restatements live here:
  *   literal  (gangpack_oracle.c) -- loop-for-loop, string-keyed maps like the Go code.
