@@ -191,3 +191,47 @@ def test_minimal_fragmentation_three_way_dense(oracle, seed):
                 assert names[ld[a]] == d
                 assert [names[i] for i in le[off[a]:off[a + 1]]] == ex, (seed, trial, a)
                 assert np.array_equal(le[off[a]:off[a + 1]], ce[off[a]:off[a + 1]]), (seed, trial, a, count[a])
+
+
+@pytest.mark.parametrize("algo_id", [0, 1, 4])
+def test_placements_respect_capacity_and_shape(oracle, algo_id):
+    """size-independent properties of every packer on mid-size clusters (closed-form oracle, the GPU suite checks the same on
+    the device): count executors, every node's load fits its availability with the driver on it, tightly-pack is node-major
+    in priority order, distribute-evenly is round-major without repeats inside a round, minimal-fragmentation fills
+    every node but the last one it uses to capacity"""
+    rng = np.random.default_rng(31337 + algo_id)
+    for trial in range(12):
+        n = int(rng.integers(50, 400))
+        cpu, mem, gpu = random_cluster(rng, n, tight=bool(trial % 2))
+        order = rng.permutation(n).astype(np.int32)
+        apps = random_apps(rng, 64, big_counts=True)
+        drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"])
+        exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+        _, dn, en, off, _ = oracle.closed_batch(algo_id, 0, cpu, mem, gpu, order, order, drv, exe, apps["count"])
+        pos = np.empty(n, np.int64); pos[order] = np.arange(n)
+        for a in range(len(dn)):
+            if dn[a] < 0:
+                continue
+            ex = en[off[a]:off[a + 1]]
+            assert len(ex) == apps["count"][a]
+            load = np.bincount(ex, minlength=n)
+            for d, (node_av, e_req, d_req) in enumerate(((cpu, exe[a][0], drv[a][0]), (mem, exe[a][1], drv[a][1]))):
+                used = load * e_req
+                used[dn[a]] += d_req
+                assert (used[load > 0] <= node_av[load > 0]).all() and used[dn[a]] <= node_av[dn[a]], (trial, a, d)
+            if len(ex) == 0:
+                continue
+            if algo_id == 0:
+                assert (np.diff(pos[ex]) >= 0).all(), (trial, a)
+            elif algo_id == 1:
+                # round-major: inside a round the priority positions increase and no node appears twice
+                rounds = np.split(ex, np.nonzero(np.diff(pos[ex]) < 0)[0] + 1)
+                assert all(len(set(r)) == len(r) for r in rounds), (trial, a)
+            else:
+                # consumed nodes appear as runs; every run but the last is a full node (no room for one more executor)
+                runs = [(ex[i], int(load[ex[i]])) for i in range(len(ex)) if i == 0 or ex[i] != ex[i - 1]]
+                assert len({r[0] for r in runs}) == len(runs), (trial, a)
+                for node, cnt in runs[:-1]:
+                    extra_cpu = (cnt + 1) * exe[a][0] + (drv[a][0] if node == dn[a] else 0)
+                    extra_mem = (cnt + 1) * exe[a][1] + (drv[a][1] if node == dn[a] else 0)
+                    assert extra_cpu > cpu[node] or extra_mem > mem[node], (trial, a, node)
