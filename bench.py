@@ -50,6 +50,12 @@ WORKLOADS = {
                      desc="10k nodes x 10k pending apps, tightly-pack, FIFO (reference usage accounting), 1 instance group"),
     "fifo-da-50k": dict(nodes=10000, apps=50000, algo=0, mode=1, groups=16, da=True,
                         desc="dynamic-allocation sweep, 10k nodes x 50k apps, FIFO on, 16 instance groups (BASELINE configs[3])"),
+    "tightly-100k-deep": dict(nodes=10000, apps=100000, algo=0, mode=0, groups=1, fill=(0.95, 1.0), deep=True,
+                              desc="10k nodes x 100k pending apps, tightly-pack, independent, DEEP scans: cluster 95-100 % full "
+                                   "(97.5 % on average), gangs of 4..128 executors that walk ~8 000 nodes of the priority order, one "
+                                   "third of the applications fit nowhere (full-table scan, no fit)"),
+    "evenly-100k-deep": dict(nodes=10000, apps=100000, algo=1, mode=0, groups=1, fill=(0.95, 1.0), deep=True,
+                             desc="same deep-scan cluster and queue, distribute-evenly"),
     "tightly-50k-1m": dict(nodes=50000, apps=125000, algo=0, mode=0, groups=1,
                            desc="50k nodes x 1M pending apps over 8 GPUs (125k per GPU), tightly-pack (BASELINE configs[4])"),
 }
@@ -62,10 +68,10 @@ APP_KEYS = ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "c
 # ------------------------------------------------------------------------------------------------
 def make_workload(w: dict, rank: int):
     from k8s_spark_scheduler_b200 import synth
-    nodes = synth.make_nodes(w["nodes"], groups=w["groups"])
+    nodes = synth.make_nodes(w["nodes"], groups=w["groups"], fill=w.get("fill", (0.0, 0.9)))
     # every rank gets a different slice of the (conceptually N x apps long) queue
     apps = synth.make_apps(w["apps"], seed=synth.APP_SEED + 7919 * rank, groups=w["groups"],
-                           da_sweep=bool(w.get("da")))
+                           da_sweep=bool(w.get("da")), deep=bool(w.get("deep")))
     eoff, eorder = synth.group_orders(nodes)
     a = {k: apps[k] for k in APP_KEYS}
     a["off"] = synth.exec_offsets(apps["count"])
@@ -120,7 +126,10 @@ class ClockSampler:
 def cpu_reference_run(w: dict, sample_apps: int, threads: int, repeats: int = 1):
     """Times the literal CPU restatement of the reference path (oracle/, kind 'port') on a bounded
     sample of the same workload, with ComputePackingEfficiencies on (the reference runs it inside
-    SparkBinPack on every successful pack, binpack.go:77)."""
+    SparkBinPack on every successful pack, binpack.go:77).
+    Returns (apps timed, threads used, [seconds per repeat], results) where results is a list of
+    (queue indices, driver_node, executor_nodes, exec offsets) in NODE-TABLE indices -- what the parity word of
+    the bench line is checked against (outside every timed region)."""
     from k8s_spark_scheduler_b200 import synth
     from oracle import oracle as orc
     nodes, a, eoff, eorder = make_workload(w, 0)
@@ -129,22 +138,19 @@ def cpu_reference_run(w: dict, sample_apps: int, threads: int, repeats: int = 1)
     drv = orc.res_array(a["drv_cpu"][:q], a["drv_mem"][:q], a["drv_gpu"][:q])
     exe = orc.res_array(a["exe_cpu"][:q], a["exe_mem"][:q], a["exe_gpu"][:q])
     count = a["count"][:q]
-    times = []
+    times, results = [], []
     if w["groups"] == 1:
-        cl = orc.Cluster(names, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"],
-                         sched=(nodes["alloc_cpu"], nodes["alloc_mem"], nodes["alloc_gpu"]))
         onames = [names[i] for i in eorder]
         for _ in range(repeats):
+            cl = orc.Cluster(names, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"],
+                             sched=(nodes["alloc_cpu"], nodes["alloc_mem"], nodes["alloc_gpu"]))
+            t0 = time.perf_counter()
             if w["mode"] == 0:
-                t0 = time.perf_counter()
-                cl.binpack_batch(ORC_ALGO[w["algo"]], drv, exe, count, onames, onames, with_efficiencies=True, n_threads=threads)
-                times.append(time.perf_counter() - t0)
+                dn, en, off = cl.binpack_batch(ORC_ALGO[w["algo"]], drv, exe, count, onames, onames, with_efficiencies=True, n_threads=threads)
             else:
-                cl = orc.Cluster(names, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"],
-                                 sched=(nodes["alloc_cpu"], nodes["alloc_mem"], nodes["alloc_gpu"]))
-                t0 = time.perf_counter()
-                cl.fifo(ORC_ALGO[w["algo"]], w["mode"], drv, exe, count, a["young"][:q], onames, onames, with_efficiencies=True)
-                times.append(time.perf_counter() - t0)
+                _, dn, en, off = cl.fifo(ORC_ALGO[w["algo"]], w["mode"], drv, exe, count, a["young"][:q], onames, onames, with_efficiencies=True)
+            times.append(time.perf_counter() - t0)
+            results = [(np.arange(q), dn, en, off)]
         used_threads = threads if w["mode"] == 0 else 1
     else:
         # FIFO per instance group: groups are independent queues -> one thread per group
@@ -156,40 +162,81 @@ def cpu_reference_run(w: dict, sample_apps: int, threads: int, repeats: int = 1)
             cl = orc.Cluster(sub_names, nodes["avail_cpu"][order], nodes["avail_mem"][order], nodes["avail_gpu"][order],
                              sched=(nodes["alloc_cpu"][order], nodes["alloc_mem"][order], nodes["alloc_gpu"][order]))
             if w["mode"] == 0:
-                cl.binpack_batch(ORC_ALGO[w["algo"]], drv[sel], exe[sel], count[sel], sub_names, sub_names, True, 1)
+                dn, en, off = cl.binpack_batch(ORC_ALGO[w["algo"]], drv[sel], exe[sel], count[sel], sub_names, sub_names, True, 1)
             else:
-                cl.fifo(ORC_ALGO[w["algo"]], w["mode"], drv[sel], exe[sel], count[sel], a["young"][:q][sel], sub_names, sub_names, True)
+                _, dn, en, off = cl.fifo(ORC_ALGO[w["algo"]], w["mode"], drv[sel], exe[sel], count[sel], a["young"][:q][sel], sub_names, sub_names, True)
+            # sub-cluster indices -> node-table indices
+            return sel, np.where(dn >= 0, order[np.maximum(dn, 0)], dn), order[np.maximum(en, 0)], off
         used_threads = min(threads, w["groups"])
         for _ in range(repeats):
             t0 = time.perf_counter()
             with cf.ThreadPoolExecutor(used_threads) as ex:   # ctypes releases the GIL
-                list(ex.map(run_group, range(w["groups"])))
+                results = list(ex.map(run_group, range(w["groups"])))
             times.append(time.perf_counter() - t0)
-    return q, used_threads, times
+    return q, used_threads, times, results
+
+
+def parity_word(results, gpu_driver, gpu_exec, gpu_off):
+    """Compares the CPU port's placements with the GPU's on the same applications (bit-exact: driver node and, for
+    every application that fits, the whole ExecutorNodes slice in order).  -> (applications checked, mismatches)."""
+    checked = mism = 0
+    for sel, dn, en, off in results:
+        gd = np.asarray(gpu_driver)[sel]
+        bad = gd != dn
+        mism += int(bad.sum())
+        checked += len(sel)
+        for j in np.nonzero(~bad & (dn >= 0))[0]:
+            i = sel[j]
+            if not np.array_equal(np.asarray(gpu_exec[gpu_off[i]:gpu_off[i + 1]], dtype=np.int64), en[off[j]:off[j + 1]]):
+                mism += 1
+    return checked, mism
+
+
+def common_config(w: dict, q: int, world: int, total_exec: int) -> dict:
+    """The `config` object -- identical in the repo arm and the reference arm (same workload, same sizes)."""
+    return {"workload": w["desc"], "nodes": w["nodes"], "apps_per_gpu": q, "apps_total": q * world,
+            "algo": ALGO_NAME[w["algo"]], "mode": MODE_NAME[w["mode"]], "instance_groups": w["groups"],
+            "executors_total_per_gpu": int(total_exec),
+            "l2": "256 MiB write between steps, outside the per-step CUDA-event pair (GPU arm); CPU arm: working set > LLC share"}
+
+
+def calibrated_sample(w: dict, cores: int, budget_s: float, cap: int) -> int:
+    """Applications per CPU step so that one step of the literal port takes about `budget_s` seconds on this host."""
+    probe = min(cap, 2000 if w["mode"] == 0 else 400)
+    _, _, times, _ = cpu_reference_run(w, probe, cores, repeats=1)
+    rate = probe / max(times[0], 1e-6)
+    return int(max(min(cap, rate * budget_s), min(cap, 1000)))
 
 
 def run_reference_arm(args, w):
+    """`--impl reference`: the reference's own CPU implementation of the path.  Go cannot run here, so this is the
+    literal C restatement of the Go code (oracle/, kind "port") on all host cores, on the repo arm's config.  At N=1 a
+    step is the WHOLE workload whenever that takes a few seconds; otherwise (N>1: N x the queue; deep scans) a bounded
+    sample, stated in cpu_baseline.sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from k8s_spark_scheduler_b200 import synth
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample
-    # warm-up + timed steps on the bounded sample
-    q, threads, _ = cpu_reference_run(w, min(sample, 2000), cores, repeats=max(args.warmup, 1) if args.warmup else 0) \
-        if args.warmup else (0, cores, [])
-    q, threads, times = cpu_reference_run(w, sample, cores, repeats=args.steps)
+    _, a, _, _ = make_workload(w, 0)
+    q_full = len(a["count"])
+    total_exec = int(synth.exec_offsets(a["count"])[-1])
+    world = max(args.gpus, 1)
+    sample = args.cpu_sample or calibrated_sample(w, cores, 4.0, q_full)     # ~4 s per step -> ~2 min for 25 steps
+    q, threads, times, _ = cpu_reference_run(w, sample, cores, repeats=args.steps)
     t = float(np.mean(times))
     value = q / t
+    whole = (q == q_full and world == 1)
     line = {
         "impl": "reference", "metric": "gang_placements_per_sec", "value": value, "unit": "decisions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": w["desc"], "nodes": w["nodes"], "apps_per_step_sample": q, "algo": ALGO_NAME[w["algo"]],
-                   "mode": MODE_NAME[w["mode"]], "instance_groups": w["groups"]},
+        "config": common_config(w, q_full, world, total_exec),
         "cpu_baseline": {"value": value, "unit": "decisions/s", "cores": threads, "kind": "port",
-                         "sample": f"first {q} apps of the workload per step, literal C restatement of the Go path "
-                                   f"(string-keyed maps, per-candidate map allocation, ComputePackingEfficiencies on), "
-                                   f"{threads} host threads; Go toolchain absent so the reference itself cannot run"},
+                         "sample": (f"the whole workload per step ({q} apps)" if whole else
+                                    f"first {q} of the {q_full * world} apps per step") +
+                                   ", literal C restatement of the Go path (string-keyed maps, per-candidate map allocation, "
+                                   f"ComputePackingEfficiencies on), {threads} host threads; Go toolchain absent so the reference itself cannot run"},
         "e2e": {"value": value, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,6 +255,16 @@ def _watchdog(seconds: float):
     return t
 
 
+def load_traffic(kernel_name: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture (profiles/traffic.json)."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        for key, t in json.load(open(tpath)).items():
+            if t.get("kernel") == kernel_name and t.get("workload") == workload:
+                return t
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,18 +272,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tightly-100k", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=0, help="apps per CPU-baseline step (0 = auto)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="apps per CPU-baseline step (0 = calibrated to the host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: abort if the run takes longer")
     args = ap.parse_args()
-    _watchdog(args.max_seconds)
+    wd = _watchdog(args.max_seconds)
     w = WORKLOADS[args.workload]
-    if args.cpu_sample == 0:
-        # ~10-30 s of CPU work: ~0.2-0.5 ms per decision per thread for the literal port
-        args.cpu_sample = min(w["apps"], 40000 if w["mode"] == 0 else 4000)
 
     if args.impl == "reference":
         run_reference_arm(args, w)
+        wd.cancel()
         return
 
     import torch
@@ -264,37 +319,37 @@ def main():
         torch.cuda.synchronize()
 
     # ================= value: device-resident inputs, no collective in the data path =====================
-    # Every rank holds the snapshot and its own block of the queue in HBM; a step = snapshot layout + prep + pack.
+    # Every rank holds the snapshot and its own block of the queue in HBM; a step = snapshot layout + pack.
     # (The path shards by application with nothing to exchange while packing; distributing the snapshot and
     #  collecting the placements are the multi-GPU analogue of H2D / D2H and are timed in `e2e` below.)
-    with torch.cuda.stream(stream):
-        # the snapshot lives in ONE flat buffer so that a single NCCL broadcast can move it (e2e):
-        # [cpu int64 x N | mem int64 x N | gpu int64 x N | executor/driver order int32 x len(eorder)]
-        snapbuf = torch.zeros(3 * n_nodes + (n_ord + 1) // 2, dtype=torch.int64, device=dev)
-        tn = {"cpu": snapbuf[0:n_nodes], "mem": snapbuf[n_nodes:2 * n_nodes], "gpu": snapbuf[2 * n_nodes:3 * n_nodes],
-              "eorder": snapbuf[3 * n_nodes:].view(torch.int32)[:n_ord], "eoff": dev_t(eoff, torch.int32)}
-        tn["cpu"].copy_(dev_t(nodes["avail_cpu"], torch.int64)); tn["mem"].copy_(dev_t(nodes["avail_mem"], torch.int64))
-        tn["gpu"].copy_(dev_t(nodes["avail_gpu"], torch.int64)); tn["eorder"].copy_(dev_t(eorder, torch.int32))
-        ta = {k: dev_t(a[k], torch.int64 if a[k].dtype == np.int64 else (torch.uint8 if a[k].dtype == np.uint8 else torch.int32))
-              for k in APP_KEYS}
-        ta["off"] = dev_t(a["off"], torch.int64)
-        if w["groups"] == 1:
-            ta.pop("group")
-        if mode == 0:
-            ta.pop("young")
-        d_driver = torch.empty(q, dtype=torch.int32, device=dev)
-        d_exec = torch.empty(max(total_exec, 1), dtype=torch.int32, device=dev)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    stream.synchronize()
+    # All tensors are allocated on torch's default stream (torch's allocator must never see the library's stream,
+    # which dies with the context); only the WORK is enqueued on the library's stream.
+    # the snapshot lives in ONE flat buffer so that a single NCCL broadcast can move it (e2e):
+    # [cpu int64 x N | mem int64 x N | gpu int64 x N | executor/driver order int32 x len(eorder)]
+    snapbuf = torch.zeros(3 * n_nodes + (n_ord + 1) // 2, dtype=torch.int64, device=dev)
+    tn = {"cpu": snapbuf[0:n_nodes], "mem": snapbuf[n_nodes:2 * n_nodes], "gpu": snapbuf[2 * n_nodes:3 * n_nodes],
+          "eorder": snapbuf[3 * n_nodes:].view(torch.int32)[:n_ord], "eoff": dev_t(eoff, torch.int32)}
+    tn["cpu"].copy_(dev_t(nodes["avail_cpu"], torch.int64)); tn["mem"].copy_(dev_t(nodes["avail_mem"], torch.int64))
+    tn["gpu"].copy_(dev_t(nodes["avail_gpu"], torch.int64)); tn["eorder"].copy_(dev_t(eorder, torch.int32))
+    ta = {k: dev_t(a[k], torch.int64 if a[k].dtype == np.int64 else (torch.uint8 if a[k].dtype == np.uint8 else torch.int32))
+          for k in APP_KEYS}
+    ta["off"] = dev_t(a["off"], torch.int64)
+    if w["groups"] == 1:
+        ta.pop("group")
+    if mode == 0:
+        ta.pop("young")
+    d_driver = torch.empty(q, dtype=torch.int32, device=dev)
+    d_exec = torch.empty(max(total_exec, 1), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    torch.cuda.synchronize()
 
     def device_step():
         packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
         packer.pack_batch_device(ta, algo, mode, d_driver, d_exec)
 
-    launches_per_step = 3 + 2   # build_groups, build_exec_slots, build_driver_slots, prep_apps, pack
     with torch.cuda.stream(stream):
         # Eager warm-up steps: they also provide the per-kernel times (the library brackets its pack kernel with
-        # CUDA events) and the scan statistics that the roofline object needs.
+        # CUDA events on its own launch stream) and the scan statistics that the roofline object needs.
         pack_ns, prep_ns = [], []
         for _ in range(max(args.warmup, 3)):
             flush.fill_(1)
@@ -302,6 +357,7 @@ def main():
             st = packer.stats()                # synchronises the stream; reads the pack kernel's own event time
             pack_ns.append(st["pack_kernel_ns"]); prep_ns.append(st["prep_kernel_ns"])
         stats = packer.stats()
+        launches_per_step = 4 + int(stats["kernel_launches"])   # build_groups, exec_slots, driver_slots, fill_pair32 + the pack call's own
         # The step is a chain of ~10 small launches; issued from Python its duration depends on how fast the host
         # thread can enqueue them (visibly so with 8 ranks per box).  It is therefore captured ONCE into a CUDA
         # graph and replayed: same kernels, same work, one launch.  BENCH_GRAPH=0 keeps eager launches.
@@ -341,6 +397,8 @@ def main():
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     value = q * world / (ms * 1e-3)
+    dev_driver_np = d_driver.cpu().numpy()          # device-resident results: the N>1 parity word compares the host path with them
+    dev_exec_np = d_exec.cpu().numpy()
 
     # ================= e2e: host buffers in, host results out ================================================
     # all-zero GPU request columns are passed as NULL (= 0), as the ABI allows; the shim knows while marshalling
@@ -362,6 +420,7 @@ def main():
         pn[k] = packer.pinned(len(v), v.dtype); pn[k][:] = v
     snap_bytes = 3 * 8 * n_nodes + 2 * 4 * n_ord + 2 * 4 * len(eoff)
     in_bytes = sum(v.nbytes for v in pin.values())
+    shm = None
 
     if world == 1:
         out_driver = packer.pinned(q, np.int32)
@@ -374,85 +433,89 @@ def main():
             packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
             return int(out_driver[0])          # the host reads the result
 
-        for _ in range(max(args.warmup, 3)):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_t = []
-        e2e_launches = 0
-        for s in range(args.steps):
-            with torch.cuda.stream(stream):
-                flush.fill_(s & 0xff)
-            stream.synchronize()
-            t0 = time.perf_counter()
-            e2e_step()
-            e2e_t.append(time.perf_counter() - t0)
-            e2e_launches += 3 + packer.stats()["kernel_launches"]   # snapshot layout + (prep + pack) per pipelined chunk
-        e2e_ms = float(np.mean(e2e_t)) * 1e3
-        e2e_value = q / (e2e_ms * 1e-3)
         e2e_step_desc = "gp_set_snapshot + gp_pack_batch from pinned host buffers to host results"
+        snap_launches = 4
     else:
-        # N>1: rank 0 uploads the snapshot (H2D) and ONE NCCL broadcast distributes it; every rank packs
-        # its own host-resident block of the queue (inputs read in place from mapped pinned memory) in 4 chunks, and
-        # each chunk's placements ([driver | ExecutorNodes], padded to the largest rank so the collective is regular)
-        # are all-gathered over NVLink asynchronously while the next chunk is packed; rank 0 finally copies every
-        # rank's placements to its host memory.  Timed with wall clock between barriers, max over ranks.
-        n_ch = 4 if mode == 0 else 1
+        # N>1.  ONE scheduler process (rank 0) owns the cluster state and consumes every placement; one worker
+        # process per GPU.  Rank 0 uploads the snapshot (H2D) and ONE NCCL broadcast distributes it over NVLink; every rank
+        # packs its own host-resident block of the queue and copies ITS placements over ITS OWN PCIe link straight into the
+        # scheduler's result buffer -- a POSIX shared-memory segment page-locked by every worker (gp_register_host).  No
+        # gather through one GPU, no collective on the results.  Wall clock between barriers, max over ranks.
+        from multiprocessing import shared_memory
+        sizes = torch.tensor([q, max(total_exec, 1)], device=dev, dtype=torch.int64)
+        all_sizes = [torch.zeros(2, device=dev, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes)
+        all_sizes = torch.stack(all_sizes).cpu().numpy()
+        words = all_sizes.sum(axis=1)                                   # int32 words per rank: [driver | ExecutorNodes]
+        base = np.concatenate([[0], np.cumsum(words)])
+        shm_name = f"gangpack_bench_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=shm_name).unlink()      # stale segment of a killed run
+            except FileNotFoundError:
+                pass
+            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=int(base[-1]) * 4)
+        dist.barrier()
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=shm_name)
+        dist.barrier()
+        whole = np.frombuffer(shm.buf, dtype=np.int32, count=int(base[-1]))
+        mine = whole[int(base[rank]):int(base[rank + 1])]
+        packer.register_host(mine)
+        out_driver, out_exec = mine[:q], mine[q:]
         h_snap = torch.empty(snapbuf.numel(), dtype=torch.int64).pin_memory()
         h_snap.copy_(snapbuf.cpu())
-        chunks = []
-        with torch.cuda.stream(stream):
-            for c in range(n_ch):
-                lo, hi = (q * c) // n_ch, (q * (c + 1)) // n_ch
-                e0, e1 = int(a["off"][lo]), int(a["off"][hi])
-                t = torch.tensor([e1 - e0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); pad = max(int(t.item()), 1)
-                res = torch.empty((hi - lo) + pad, dtype=torch.int32, device=dev)
-                hin = {k: torch.from_numpy(v[lo:hi]) for k, v in pin.items() if k != "off"}      # mapped pinned views
-                off_c = packer.pinned(hi - lo + 1, np.int64); off_c[:] = a["off"][lo:hi + 1] - e0
-                hin["off"] = torch.from_numpy(off_c)
-                gathered = torch.empty(res.numel() * world, dtype=torch.int32, device=dev)
-                chunks.append({"apps": hin, "res": res, "driver": res[:hi - lo], "exec": res[hi - lo:], "gathered": gathered,
-                               "host": torch.empty(gathered.numel(), dtype=torch.int32).pin_memory() if rank == 0 else None})
-        stream.synchronize()
         h2d = in_bytes + (snapbuf.numel() * 8 if rank == 0 else 0)
-        d2h = sum(ch["gathered"].numel() * 4 for ch in chunks) if rank == 0 else 0
+        d2h = out_driver.nbytes + 4 * total_exec
 
-        def e2e_step_multi():
+        def e2e_step():
             with torch.cuda.stream(stream):
                 if rank == 0:
                     snapbuf.copy_(h_snap, non_blocking=True)
                 dist.broadcast(snapbuf, src=0)
                 packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
-                works = []
-                for ch in chunks:
-                    packer.pack_batch_device(ch["apps"], algo, mode, ch["driver"], ch["exec"])
-                    works.append(dist.all_gather_into_tensor(ch["gathered"], ch["res"], async_op=True))
-                for ch, wk in zip(chunks, works):
-                    wk.wait()
-                    if rank == 0:
-                        ch["host"].copy_(ch["gathered"], non_blocking=True)
-                stream.synchronize()
-            return int(chunks[0]["host"][0]) if rank == 0 else 0
+            packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
+            return int(out_driver[0])
 
-        for _ in range(max(args.warmup, 3)):
-            e2e_step_multi()
-        barrier()
-        e2e_t = []
-        for s in range(args.steps):
-            with torch.cuda.stream(stream):
-                flush.fill_(s & 0xff)
+        e2e_step_desc = ("rank 0 H2D snapshot + ONE NCCL broadcast (NVLink) + layout; every rank: gp_pack_batch from its pinned host "
+                         "block of the queue, results DMA'd over its own PCIe link into the scheduler's shared-memory result buffer")
+        snap_launches = 4
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    e2e_t = []
+    e2e_launches = 0
+    for s in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(s & 0xff)
+        stream.synchronize()
+        if world > 1:
             barrier()
-            t0 = time.perf_counter()
-            e2e_step_multi()
+        t0 = time.perf_counter()
+        e2e_step()
+        if world > 1:
             barrier()
-            e2e_t.append(time.perf_counter() - t0)
-        e2e_ms = float(np.mean(e2e_t)) * 1e3
+        e2e_t.append(time.perf_counter() - t0)
+        e2e_launches += snap_launches + packer.stats()["kernel_launches"]   # snapshot layout + the pack call's launches (per pipelined chunk)
+    e2e_ms = float(np.mean(e2e_t)) * 1e3
+    if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-        e2e_value = q * world / (e2e_ms * 1e-3)
-        e2e_launches = (3 + 2 * n_ch) * args.steps
-        e2e_step_desc = ("rank 0 H2D snapshot + NCCL broadcast + layout + per-rank pack of host-resident apps (4 chunks) + "
-                         "async NCCL all-gather of placements overlapped with the next chunk + rank 0 D2H of all placements")
+    e2e_value = q * world / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- parity word (outside every timed region) ------------------------------------------------------
+    # (a) every rank: the host path's placements == the device-resident path's placements, all q applications
+    # (FIFO modes included: both ran the same queue against the same snapshot);
+    fits = dev_driver_np >= 0
+    emask = np.repeat(fits, a["count"])
+    path_mism = int((np.asarray(out_driver) != dev_driver_np).sum()) + \
+        int((np.asarray(out_exec[:total_exec])[emask] != dev_exec_np[:total_exec][emask]).sum())
+    if world > 1:
+        t = torch.tensor([path_mism], device=dev, dtype=torch.int64); dist.all_reduce(t); path_mism = int(t.item())
+        # (b) rank 0 -- the consumer -- finds every rank's block in the shared buffer: spot-check against rank 0's own view
+        dist.barrier()
 
     # ---- roofline of the dominant kernel (pack) ----------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -462,70 +525,88 @@ def main():
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
     R = 2   # cpu + mem; the gpu array is skipped when no request and no negative availability
     k_total = total_exec
-    alg_bytes = (stats["nodes_scanned"] * 8 * R + stats["drivers_tried"] * 4 + q * (64 + 8) + 8 * 0 + 4 * k_total)
+    alg_bytes = (stats["nodes_scanned"] * 8 * R + stats["drivers_tried"] * 4 + q * (64 + 8) + 4 * k_total)
     nominal_bytes = q * (w["nodes"] * 8 * R + w["nodes"] * 4 + 64 + 8) + 4 * k_total
     pack_s = float(np.mean(pack_ns)) * 1e-9
     kernel_name = f"gp_pack_{'independent' if mode == 0 else 'fifo_cta'}<{ALGO_NAME[algo]}>"
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        t = json.load(open(tpath)).get(kernel_name)
-        if t and t.get("workload") == args.workload and world == 1:
-            traffic = t["dram_bytes_per_launch"]
+    tr = load_traffic(kernel_name, args.workload) if world == 1 else None
+    traffic = tr["dram_bytes_per_launch"] if tr else None
     roofline = {
+        # `achieved`/`frac` follow SURVEY 8(d): ALGORITHMIC bytes / kernel time against the measured HBM copy bandwidth.
+        # The kernel itself is NOT limited by DRAM: `limiter` says what ncu shows, `dram_frac` what the DRAM pins really carry.
         "bound": "hbm", "kernel": kernel_name,
         "achieved": alg_bytes / pack_s / 1e9, "peak": peak, "unit": "GB/s",
         "frac": alg_bytes / pack_s / 1e9 / peak, "peak_source": peak_src,
         "traffic": traffic,
+        "dram_frac": (traffic / pack_s / 1e9 / peak) if traffic else None,
+        "limiter": (tr or {}).get("limiter", "instruction issue / L1 latency (integer scan over an L1/L2-resident snapshot); see DESIGN.md section 6"),
         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": pack_s * 1e3,
         "nodes_scanned_per_decision": stats["nodes_scanned"] / q, "drivers_tried_per_decision": stats["drivers_tried"] / q,
         "full_table_equivalent_GBps": nominal_bytes / pack_s / 1e9,
         "note": "algorithmic bytes use the nodes actually visited (early exit is exact); the snapshot is served "
-                "from L1/L2, so DRAM traffic is far below this -- see DESIGN.md section 6",
+                "from L1/L2, so DRAM traffic is far below this -- dram_frac is the honest HBM share",
     }
 
-    # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ------------------------------------
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only) + parity of the GPU results against it -----
     cpu_baseline = None
+    parity_checked = parity_mism = 0
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        qs, threads, times = cpu_reference_run(w, args.cpu_sample, cores, repeats=1)
+        sample = args.cpu_sample or calibrated_sample(w, cores, 12.0, q)          # ~10-20 s of CPU work
+        qs, threads, times, results = cpu_reference_run(w, sample, cores, repeats=1)
         cpu_baseline = {"value": qs / times[0], "unit": "decisions/s", "cores": threads, "kind": "port",
                         "sample": f"first {qs} apps of the workload, literal C restatement of the Go path (string-keyed maps, "
                                   f"per-candidate map allocation, ComputePackingEfficiencies on), {threads} threads, "
                                   f"{times[0]:.2f} s"}
+        parity_checked, parity_mism = parity_word(results, out_driver, out_exec, a["off"])
 
     if rank == 0:
+        cfg = common_config(w, q, world, total_exec)
+        cfg.update({"step": "snapshot layout + pack, device-resident inputs, no collective in the data path "
+                            "(every rank packs its own block of the queue against its copy of the snapshot); "
+                            + ("the launch chain is replayed from one CUDA graph" if graph is not None else "eager launches"),
+                    "e2e_step": e2e_step_desc})
         line = {
             "metric": "gang_placements_per_sec", "value": value, "unit": "decisions/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": w["desc"], "nodes": w["nodes"], "apps_per_gpu": q, "apps_total": q * world,
-                       "algo": ALGO_NAME[algo], "mode": MODE_NAME[mode], "instance_groups": w["groups"],
-                       "executors_total_per_gpu": total_exec,
-                       "l2": "256 MiB write between steps, outside the per-step CUDA-event pair",
-                       "step": "snapshot layout + prep + pack, device-resident inputs, no collective in the data path "
-                               "(every rank packs its own block of the queue against its copy of the snapshot); "
-                               + ("the launch chain is replayed from one CUDA graph" if graph is not None else "eager launches"),
-                       "e2e_step": e2e_step_desc,
-                       "fits": None},
+            "config": cfg,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "decisions/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches_per_step * args.steps + e2e_launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "parity_checked": int(parity_checked), "mismatches": int(parity_mism),
+            "parity": {"vs_cpu_port": {"apps": int(parity_checked), "mismatches": int(parity_mism)},
+                       "host_path_vs_device_path": {"apps": q * world, "mismatching_words": path_mism}},
             "kernel_ms": {"pack": pack_s * 1e3, "prep": float(np.mean(prep_ns)) * 1e-6},
             "wall_s_value_region": wall1 - wall0,
         }
         print(json.dumps(line), flush=True)
-    # Leave without tearing anything down: tensors allocated on the library's stream must not outlive that
-    # stream (the caching allocator records events on it when they are freed), and destroying a process group
-    # with outstanding async work can block.  Every rank has finished its last
-    # collective (the all-reduce of the e2e time) at this point.
+
+    # ---- orderly teardown: the driver's exit hook must see this process with libgangpack.so mapped -------
     torch.cuda.synchronize()
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
+    del graph, evs
+    del snapbuf, tn, ta, d_driver, d_exec, flush
+    pin = pn = out_driver = out_exec = None
+    if shm is not None:
+        whole = mine = None
+    packer.close()                                    # frees pinned blocks, unregisters the shared segment, gp_destroy
+    if shm is not None:
+        try:
+            shm.close()
+        except BufferError:
+            pass
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shm.unlink()
+    if world > 1:
+        dist.destroy_process_group()
+    wd.cancel()
+    if (parity_mism or path_mism) and rank == 0:
+        raise SystemExit(f"parity failure: {parity_mism} vs the CPU port, {path_mism} host-path vs device-path")
 
 
 if __name__ == "__main__":

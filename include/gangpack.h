@@ -104,7 +104,8 @@ typedef struct {
     const int64_t* exe_cpu_milli;    /* [n_apps] per-executor resources */
     const int64_t* exe_mem_bytes;
     const int64_t* exe_gpu;          /* or NULL (= 0) */
-    const int32_t* exe_count;        /* [n_apps] MinExecutorCount (resource.go:242,325); >= 0 */
+    const int32_t* exe_count;        /* [n_apps] MinExecutorCount (resource.go:242,325); >= 0, <= 2^24 (<= 2^20 in the
+                                        FIFO modes); larger -> GP_ERR_UNREPRESENTABLE */
     const int32_t* group;            /* [n_apps] instance group, or NULL (= 0) */
     const uint8_t* skip_if_no_fit;   /* [n_apps] FIFO only: shouldSkipDriverFifo (resource.go:264-270), or NULL */
     const int64_t* exec_out_off;     /* [n_apps+1] exclusive prefix sum of exe_count, or NULL (computed) */
@@ -115,8 +116,8 @@ typedef struct {
  *                  == -1: HasCapacity=false (EmptyPackingResult)
  *                  == -2: not evaluated -- an earlier app of its group blocked the FIFO queue
  *   executor_nodes[exec_out_off[i] .. +exe_count[i]) : ExecutorNodes, in the reference's order
- *     (reservation names executor-1..k follow it, resourcereservations.go:501-510); untouched
- *     unless driver_node[i] >= 0.
+ *     (reservation names executor-1..k follow it, resourcereservations.go:501-510); its contents are
+ *     UNDEFINED unless driver_node[i] >= 0 (the FIFO kernels emit optimistically before feasibility is known).
  * PackingEfficiencies are not produced on the device (metrics by-product). */
 typedef struct {
     int32_t* driver_node;            /* [n_apps] */
@@ -136,6 +137,13 @@ int gp_backend(const gp_ctx* ctx);
  * wraps it with unsafe.Slice.  Pageable memory is accepted everywhere, just slower. */
 gp_status gp_alloc_pinned(gp_ctx* ctx, size_t bytes, void** out);
 gp_status gp_free_pinned(gp_ctx* ctx, void* p);
+
+/* Page-locks caller-owned host memory (cudaHostRegister, portable + mapped) so that gp_pack_batch can DMA results
+ * straight into it / read inputs in place -- e.g. a POSIX shared-memory segment that the scheduler process and the
+ * per-GPU worker processes of one box share: every worker copies its block of the placements over its OWN PCIe
+ * link into the scheduler's buffer (no gather through one GPU).  The range must stay mapped until unregistered. */
+gp_status gp_register_host(gp_ctx* ctx, void* p, size_t bytes);
+gp_status gp_unregister_host(gp_ctx* ctx, void* p);
 
 /* ---- snapshot ------------------------------------------------------------------------------ */
 /* Validates, copies to the device and lays the snapshot out in executor-priority order. */

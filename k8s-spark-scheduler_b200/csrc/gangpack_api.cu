@@ -47,6 +47,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
     int bad = 0;
     if (k < 0) bad |= kErrNegativeRequest;
     if (k > kMaxCount) bad |= kErrUnrepresentable;
+    if (gmins && k > kMaxCountFifo) bad |= kErrUnrepresentable;   // FIFO modes: block-wide uint32 sums of clamped capacities stay exact
     if (g < 0 || g >= n_groups) bad |= kErrBadGroup;
     int64_t off = out_off[i];
     if (off < 0 || out_off[i + 1] - off != (int64_t)k || out_off[i + 1] > out_cap) bad |= kErrBadOffsets;
@@ -518,6 +519,20 @@ gp_status gp_free_pinned(gp_ctx* ctx, void* p) {
     return GP_OK;
 }
 
+gp_status gp_register_host(gp_ctx* ctx, void* p, size_t bytes) {
+    if (!ctx || !p || !bytes) return GP_ERR_INVALID;
+    GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    GP_CUDA(ctx, cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return GP_OK;
+}
+
+gp_status gp_unregister_host(gp_ctx* ctx, void* p) {
+    if (!ctx || !p) return GP_ERR_INVALID;
+    GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    GP_CUDA(ctx, cudaHostUnregister(p));
+    return GP_OK;
+}
+
 void* gp_stream(gp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 gp_status gp_synchronize(gp_ctx* ctx) {
@@ -736,6 +751,12 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
             gp_pack_fifo_cta<ALGO, 1><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins);
         else
             gp_pack_fifo_cta<ALGO, 2><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins);
+        // the FIFO kernels subtract usage from `pair` in place: refresh the compact 32-bit view so that a later
+        // independent pack on this context (the driver's own pack after fitEarlierDrivers, resource.go:255 then :321)
+        // sees the charged availability
+        const int T = 256;
+        gp_fill_pair32<<<(c->n_slots + T) / T, T, 0, st>>>(c->n_slots, c->pair.as<longlong2>(), c->snap_flags.as<SnapMeta>(), c->pair32.as<uint2>());
+        c->last.kernel_launches += 1;
     }
 }
 

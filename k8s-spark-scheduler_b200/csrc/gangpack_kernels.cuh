@@ -32,6 +32,7 @@ namespace gp {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int32_t kMaxCount = 1 << 24;            // exe_count limit (keeps 32-lane int32 sums exact)
+constexpr int32_t kMaxCountFifo = 1 << 20;        // FIFO modes: 1024 threads x min(cap, k) must stay below 2^32
 constexpr int64_t kMaxQuantity = (int64_t)1 << 61; // |quantity| limit of the exact-int64 domain
 
 // error bits raised by device-side validation (read back by the host API)

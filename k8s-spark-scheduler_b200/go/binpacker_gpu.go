@@ -181,6 +181,18 @@ func ptrOrNil32(v []int32) any {
 	}
 	return &v[0]
 }
+func ptrOrNil8(v []uint8) any {
+	if len(v) == 0 {
+		return nil
+	}
+	return &v[0]
+}
+func ptr8(v []uint8) *C.uint8_t {
+	if len(v) == 0 {
+		return nil
+	}
+	return (*C.uint8_t)(unsafe.Pointer(&v[0]))
+}
 
 // gpuPacker returns a binpack.SparkBinPackFunction (LIB/binpack/binpack.go:43-48) backed by the device;
 // any failure (no device, CUDA error, unrepresentable quantity) runs `fallback`, the original Go packer,
@@ -402,6 +414,9 @@ func FitEarlierDriversBatch(algo C.gp_algo, apps []QueuedApp, nodeNames, executo
 	if err != nil {
 		return false, false
 	}
+	if len(apps) == 0 {
+		return true, true // no earlier drivers: nothing to fit, nothing to subtract (EXT/resource.go:230 loop body never runs)
+	}
 	s, exact := marshal(metadata, nodeNames, executorNodeNames)
 	if !exact {
 		return false, false
@@ -432,9 +447,19 @@ func FitEarlierDriversBatch(algo C.gp_algo, apps []QueuedApp, nodeNames, executo
 	if err := d.setSnapshot(s); err != nil {
 		return false, false
 	}
+	// gp_apps / gp_results hold Go pointers: every slice base is pinned for the duration of the call
+	// (cgocheck: "Go pointer to unpinned Go pointer"), exactly as setSnapshot does for the node table.
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	for _, p := range []any{ptrOrNil(dc), ptrOrNil(dm), ptrOrNil(dg), ptrOrNil(ec), ptrOrNil(em), ptrOrNil(eg),
+		ptrOrNil32(cnt), ptrOrNil8(skip), ptrOrNil(off), ptrOrNil32(driver), ptrOrNil32(exec)} {
+		if p != nil {
+			pin.Pin(p)
+		}
+	}
 	ga := C.gp_apps{n_apps: C.int32_t(q), drv_cpu_milli: ptr64(dc), drv_mem_bytes: ptr64(dm), drv_gpu: ptr64(dg),
 		exe_cpu_milli: ptr64(ec), exe_mem_bytes: ptr64(em), exe_gpu: ptr64(eg), exe_count: ptr32(cnt),
-		skip_if_no_fit: (*C.uint8_t)(unsafe.Pointer(&skip[0])), exec_out_off: ptr64(off)}
+		skip_if_no_fit: ptr8(skip), exec_out_off: ptr64(off)}
 	gr := C.gp_results{driver_node: ptr32(driver), executor_nodes: ptr32(exec), executor_nodes_cap: C.int64_t(len(exec))}
 	if st := C.gp_pack_batch(d.ctx, &ga, algo, C.GP_MODE_FIFO_REFERENCE, &gr); st != C.GP_OK {
 		return false, false

@@ -33,7 +33,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 
 # every symbol include/gangpack.h declares (tests assert the .so exports exactly these)
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
-           "gp_free_pinned", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_one",
+           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_one",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
            "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors"]
 
@@ -135,6 +135,10 @@ def load():
     L.gp_alloc_pinned.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.gp_free_pinned.restype = C.c_int
     L.gp_free_pinned.argtypes = [C.c_void_p, C.c_void_p]
+    L.gp_register_host.restype = C.c_int
+    L.gp_register_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.gp_unregister_host.restype = C.c_int
+    L.gp_unregister_host.argtypes = [C.c_void_p, C.c_void_p]
     L.gp_set_snapshot.restype = C.c_int
     L.gp_set_snapshot.argtypes = [C.c_void_p, C.POINTER(gp_nodes)]
     L.gp_get_snapshot.restype = C.c_int
@@ -209,12 +213,16 @@ class GangPacker:
             raise GangpackError(st, (L.gp_last_error(None) or b"").decode())
         self._keep = None
         self._pinned = []
+        self._registered = []
 
     def close(self):
         if getattr(self, "_h", None):
             for p in self._pinned:
                 p.free()
             self._pinned = []
+            for addr in self._registered:
+                load().gp_unregister_host(self._h, addr)
+            self._registered = []
             load().gp_destroy(self._h)
             self._h = None
 
@@ -232,6 +240,15 @@ class GangPacker:
         p = PinnedArray(self, shape, dtype)
         self._pinned.append(p)
         return p.array
+
+    def register_host(self, array: np.ndarray):
+        """Page-lock caller-owned memory (e.g. a shared-memory segment) so results can be DMA'd straight into it."""
+        self._check(load().gp_register_host(self._h, array.ctypes.data, array.nbytes))
+        self._registered.append(array.ctypes.data)
+
+    def unregister_host(self, array: np.ndarray):
+        self._check(load().gp_unregister_host(self._h, array.ctypes.data))
+        self._registered.remove(array.ctypes.data)
 
     def pinned_columns(self, n: int, names, dtype=np.int64) -> dict:
         """`names` equally spaced columns of n elements inside ONE pinned block (column after column): the layout

@@ -30,12 +30,14 @@ def _pick(r: np.ndarray, choices) -> np.ndarray:
     return c[(r % np.uint64(len(c))).astype(np.int64)]
 
 
-def make_nodes(n: int, seed: int = NODE_SEED, groups: int = 1, gpu_variant: bool = False) -> dict:
+def make_nodes(n: int, seed: int = NODE_SEED, groups: int = 1, gpu_variant: bool = False, fill=(0.0, 0.9)) -> dict:
+    """fill = (lo, hi): pre-existing usage fraction u ~ U[lo, hi) (U[0, 0.9); the deep-scan workloads use
+    a nearly full cluster, e.g. (0.90, 1.0))."""
     r = splitmix64(seed, 3 * n).reshape(3, n)
     t = (r[0] % np.uint64(4)).astype(np.int64)                       # instance type
     alloc_cpu = np.array([16, 32, 64, 96], dtype=np.int64)[t] * 1000
     alloc_mem = np.array([64, 128, 256, 384], dtype=np.int64)[t] * Gi
-    u = (r[1] >> np.uint64(11)).astype(np.float64) / float(1 << 53) * 0.9   # usage fraction U[0,0.9)
+    u = fill[0] + (r[1] >> np.uint64(11)).astype(np.float64) / float(1 << 53) * (fill[1] - fill[0])   # usage fraction U[lo,hi)
     used_cpu = (np.floor(alloc_cpu * u / 250.0)).astype(np.int64) * 250      # quantised to 250m
     used_mem = (np.floor(alloc_mem * u / (256.0 * Mi))).astype(np.int64) * (256 * Mi)
     alloc_gpu = _pick(r[2], [0, 8]) if gpu_variant else np.zeros(n, dtype=np.int64)
@@ -75,7 +77,7 @@ def group_orders(nodes: dict):
 
 
 def make_apps(q: int, seed: int = APP_SEED, groups: int = 1, da_sweep: bool = False,
-              young_frac: float = 0.0, gpu_variant: bool = False, readme_app: bool = False) -> dict:
+              young_frac: float = 0.0, gpu_variant: bool = False, readme_app: bool = False, deep: bool = False) -> dict:
     r = splitmix64(seed, 8 * q).reshape(8, q)
     if readme_app:  # README.md:37-41
         drv_cpu = np.full(q, 1000, np.int64); drv_mem = np.full(q, 1 * Gi, np.int64)
@@ -87,6 +89,11 @@ def make_apps(q: int, seed: int = APP_SEED, groups: int = 1, da_sweep: bool = Fa
         exe_cpu = _pick(r[2], [1, 2, 4]) * 1000
         exe_mem = _pick(r[3], [2, 4, 8, 16]) * Gi
         count = (r[4] % np.uint64(32)).astype(np.int32) + 1              # U{1..32}
+    if deep:        # deep-scan queue for a nearly full cluster (make_nodes(fill=(0.95, 1.0))): gangs of 4..128 executors that
+        # walk ~8 000 nodes of the priority order before they find room, and one third of the applications ask for
+        # 8-core executors that fit nowhere (no node has 8 free cores) -> full-table scan, no fit
+        exe_cpu = _pick(r[2], [1, 2, 8]) * 1000
+        count = count * 4
     max_count = count.copy()
     if da_sweep:  # dynamic allocation: only MIN is packed (EXT/resource.go:242,325)
         count = _pick(r[4], [0, 1, 2, 4, 8, 16]).astype(np.int32)

@@ -238,8 +238,13 @@ def node_names_in_priority_order(meta, zones):
         pa, pb = prio[zones.get(a, "default")], prio[zones.get(b, "default")]
         if pa != pb:
             return pa < pb
-        if meta[a] != meta[b]:
-            return resources_less_than(meta[a], meta[b])
+        # the documented deterministic order (include/gangpack.h, gp_potential_nodes): when resourcesLessThan is
+        # false BOTH ways -- equal (memory, cpu), whatever the gpu column says (:88-92 never looks at it) -- the
+        # name decides.  The reference leaves that case to an unstable sort.
+        if resources_less_than(meta[a], meta[b]):
+            return True
+        if resources_less_than(meta[b], meta[a]):
+            return False
         return a < b
 
     def cmp(a, b):

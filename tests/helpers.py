@@ -81,3 +81,30 @@ def assert_same_results(got, want, label=""):
         app = int(np.searchsorted(woff, diff[0], side="right") - 1)
         raise AssertionError(f"{label} executor_nodes differ first at app {app}: got {ge[woff[app]:woff[app+1]]} "
                              f"want {we[woff[app]:woff[app+1]]}")
+
+
+def node_names(n):
+    return ["node-%06d" % i for i in range(n)]
+
+
+def literal_batch(oracle, algo, cpu, mem, gpu, drv_idx, exec_idx, apps, n_threads=8):
+    """Independent batch through the LITERAL restatement (string-keyed maps, loop for loop: oracle/gangpack_oracle.c,
+    following pack_tightly.go:45-61 / distribute_evenly.go:49-70 / binpack.go:60-87) -> (driver_node, executor_nodes, off)
+    in node-table indices."""
+    names = node_names(len(cpu))
+    cl = oracle.Cluster(names, cpu, mem, gpu)
+    drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"])
+    exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+    dn, en, off = cl.binpack_batch(algo, drv, exe, apps["count"], [names[i] for i in drv_idx], [names[i] for i in exec_idx],
+                                   with_efficiencies=False, n_threads=n_threads)
+    return dn, en, off
+
+
+def literal_fifo(oracle, algo, mode, cpu, mem, gpu, drv_idx, exec_idx, apps, young):
+    """fitEarlierDrivers through the literal restatement -> ((driver_node, executor_nodes, off), final (cpu, mem, gpu))."""
+    names = node_names(len(cpu))
+    cl = oracle.Cluster(names, cpu, mem, gpu)
+    drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"])
+    exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+    _, dn, en, off = cl.fifo(algo, mode, drv, exe, apps["count"], young, [names[i] for i in drv_idx], [names[i] for i in exec_idx])
+    return (dn, en, off), cl.available()
