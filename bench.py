@@ -274,6 +274,8 @@ def main():
     ap.add_argument("--workload", default="tightly-100k", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="apps per CPU-baseline step (0 = calibrated to the host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wire", default="compact", choices=["compact", "int64"],
+                    help="host path layout: compact = what gp_pack_batch_wire allows for this batch; int64 = gp_pack_batch")
     ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: abort if the run takes longer")
     args = ap.parse_args()
     wd = _watchdog(args.max_seconds)
@@ -402,13 +404,27 @@ def main():
 
     # ================= e2e: host buffers in, host results out ================================================
     # all-zero GPU request columns are passed as NULL (= 0), as the ABI allows; the shim knows while marshalling
-    host_keys = [k for k in a if not (k in ("drv_gpu", "exe_gpu") and not a[k].any())]
-    i64_cols = [k for k in ("drv_cpu", "drv_mem", "exe_cpu", "exe_mem", "drv_gpu", "exe_gpu") if k in host_keys]
-    pin = packer.pinned_columns(q, i64_cols)          # one pinned block, column after column (as the shim allocates it)
+    # Wire format, chosen per batch like the shim would (include/gangpack.h, gp_pack_batch_wire): int32 millicores / MiB
+    # when every quantity is exactly representable, offsets derived on the device and uint16 node indices for the
+    # independent tightly-pack / distribute-evenly path on <= 65 535 nodes; --wire int64 keeps the plain gp_pack_batch layout.
+    fused = (mode == 0 and algo != 2)
+    wire = None
+    src = a
+    if args.wire == "compact":
+        c32 = g.native.compact_apps({k: a[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}, mem_shift=20)
+        wire = dict(quantity_bits=32 if c32 is not None else 64, mem_shift=20,
+                    node_bits=16 if (fused and n_nodes <= 65535) else 32, offsets=not fused)
+        if c32 is not None:
+            src = dict(a); src.update(c32)
+    host_keys = [k for k in src if not (k in ("drv_gpu", "exe_gpu") and not a[k].any())]
+    if wire is not None and not wire["offsets"]:
+        host_keys.remove("off")
+    q_cols = [k for k in ("drv_cpu", "drv_mem", "exe_cpu", "exe_mem", "drv_gpu", "exe_gpu") if k in host_keys]
+    pin = packer.pinned_columns(q, q_cols, dtype=src["drv_cpu"].dtype)   # one pinned block, column after column (as the shim allocates it)
     for k in host_keys:
         if k not in pin:
-            pin[k] = packer.pinned(len(a[k]), a[k].dtype)
-        pin[k][:] = a[k]
+            pin[k] = packer.pinned(len(src[k]), src[k].dtype)
+        pin[k][:] = src[k]
     if w["groups"] == 1:
         pin.pop("group", None)
     if mode == 0:
@@ -423,17 +439,18 @@ def main():
     shm = None
 
     if world == 1:
+        node_dt = np.uint16 if (wire and wire["node_bits"] == 16) else np.int32
         out_driver = packer.pinned(q, np.int32)
-        out_exec = packer.pinned(max(total_exec, 1), np.int32)
+        out_exec = packer.pinned(max(total_exec, 1), node_dt)
         h2d = in_bytes + snap_bytes
-        d2h = out_driver.nbytes + 4 * total_exec
+        d2h = out_driver.nbytes + out_exec.itemsize * total_exec
 
         def e2e_step():
             packer.set_snapshot(pn["cpu"], pn["mem"], pn["gpu"], pn["eorder"], pn["eorder"], pn["eoff"], pn["eoff"])
-            packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
+            packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec), wire=wire)
             return int(out_driver[0])          # the host reads the result
 
-        e2e_step_desc = "gp_set_snapshot + gp_pack_batch from pinned host buffers to host results"
+        e2e_step_desc = "gp_set_snapshot + gp_pack_batch_wire from pinned host buffers to host results"
         snap_launches = 4
     else:
         # N>1.  ONE scheduler process (rank 0) owns the cluster state and consumes every placement; one worker
@@ -442,31 +459,32 @@ def main():
         # scheduler's result buffer -- a POSIX shared-memory segment page-locked by every worker (gp_register_host).  No
         # gather through one GPU, no collective on the results.  Wall clock between barriers, max over ranks.
         from multiprocessing import shared_memory
-        sizes = torch.tensor([q, max(total_exec, 1)], device=dev, dtype=torch.int64)
-        all_sizes = [torch.zeros(2, device=dev, dtype=torch.int64) for _ in range(world)]
+        node_dt = np.uint16 if (wire and wire["node_bits"] == 16) else np.int32
+        my_bytes = ((4 * q + node_dt().itemsize * max(total_exec, 1)) + 255) & ~255          # [driver int32 | ExecutorNodes]
+        sizes = torch.tensor([my_bytes], device=dev, dtype=torch.int64)
+        all_sizes = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(all_sizes, sizes)
-        all_sizes = torch.stack(all_sizes).cpu().numpy()
-        words = all_sizes.sum(axis=1)                                   # int32 words per rank: [driver | ExecutorNodes]
-        base = np.concatenate([[0], np.cumsum(words)])
+        base = np.concatenate([[0], np.cumsum([int(x.item()) for x in all_sizes])])
         shm_name = f"gangpack_bench_{os.environ.get('MASTER_PORT', '0')}"
         if rank == 0:
             try:
                 shared_memory.SharedMemory(name=shm_name).unlink()      # stale segment of a killed run
             except FileNotFoundError:
                 pass
-            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=int(base[-1]) * 4)
+            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=int(base[-1]))
         dist.barrier()
         if rank != 0:
             shm = shared_memory.SharedMemory(name=shm_name)
         dist.barrier()
-        whole = np.frombuffer(shm.buf, dtype=np.int32, count=int(base[-1]))
+        whole = np.frombuffer(shm.buf, dtype=np.uint8, count=int(base[-1]))
         mine = whole[int(base[rank]):int(base[rank + 1])]
         packer.register_host(mine)
-        out_driver, out_exec = mine[:q], mine[q:]
+        out_driver = mine[:4 * q].view(np.int32)
+        out_exec = mine[4 * q:4 * q + node_dt().itemsize * max(total_exec, 1)].view(node_dt)
         h_snap = torch.empty(snapbuf.numel(), dtype=torch.int64).pin_memory()
         h_snap.copy_(snapbuf.cpu())
         h2d = in_bytes + (snapbuf.numel() * 8 if rank == 0 else 0)
-        d2h = out_driver.nbytes + 4 * total_exec
+        d2h = out_driver.nbytes + out_exec.itemsize * total_exec
 
         def e2e_step():
             with torch.cuda.stream(stream):
@@ -474,7 +492,7 @@ def main():
                     snapbuf.copy_(h_snap, non_blocking=True)
                 dist.broadcast(snapbuf, src=0)
                 packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
-            packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec))
+            packer.pack_batch(pin, algo, mode, out=(out_driver, out_exec), wire=wire)
             return int(out_driver[0])
 
         e2e_step_desc = ("rank 0 H2D snapshot + ONE NCCL broadcast (NVLink) + layout; every rank: gp_pack_batch from its pinned host "
@@ -525,10 +543,15 @@ def main():
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
     R = 2   # cpu + mem; the gpu array is skipped when no request and no negative availability
     k_total = total_exec
-    alg_bytes = (stats["nodes_scanned"] * 8 * R + stats["drivers_tried"] * 4 + q * (64 + 8) + 4 * k_total)
+    # scan path: 8R bytes per node evaluated; table path: one 4-byte prefix word per probe; per driver candidate its slot
+    # index + its (cpu, mem) record; per application the tuple (64 B) + the result header (8 B); 4 B per emitted executor
+    scan_nodes = stats["scan_path_nodes"] if fused else stats["nodes_scanned"]
+    table_probes = stats["nodes_scanned"] - scan_nodes
+    alg_bytes = (scan_nodes * 8 * R + table_probes * 4 + stats["drivers_tried"] * (4 + 16 if fused else 4)
+                 + q * (64 + 8) + 4 * k_total)
     nominal_bytes = q * (w["nodes"] * 8 * R + w["nodes"] * 4 + 64 + 8) + 4 * k_total
     pack_s = float(np.mean(pack_ns)) * 1e-9
-    kernel_name = f"gp_pack_{'independent' if mode == 0 else 'fifo_cta'}<{ALGO_NAME[algo]}>"
+    kernel_name = f"gp_pack_{('tables' if fused else 'independent') if mode == 0 else 'fifo_cta'}<{ALGO_NAME[algo]}>"
     tr = load_traffic(kernel_name, args.workload) if world == 1 else None
     traffic = tr["dram_bytes_per_launch"] if tr else None
     roofline = {
@@ -541,7 +564,8 @@ def main():
         "dram_frac": (traffic / pack_s / 1e9 / peak) if traffic else None,
         "limiter": (tr or {}).get("limiter", "instruction issue / L1 latency (integer scan over an L1/L2-resident snapshot); see DESIGN.md section 6"),
         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": pack_s * 1e3,
-        "nodes_scanned_per_decision": stats["nodes_scanned"] / q, "drivers_tried_per_decision": stats["drivers_tried"] / q,
+        "nodes_scanned_per_decision": scan_nodes / q, "table_words_per_decision": table_probes / q,
+        "drivers_tried_per_decision": stats["drivers_tried"] / q, "scan_path_apps": int(stats["scan_path_apps"]),
         "full_table_equivalent_GBps": nominal_bytes / pack_s / 1e9,
         "note": "algorithmic bytes use the nodes actually visited (early exit is exact); the snapshot is served "
                 "from L1/L2, so DRAM traffic is far below this -- dram_frac is the honest HBM share",
@@ -565,7 +589,9 @@ def main():
         cfg.update({"step": "snapshot layout + pack, device-resident inputs, no collective in the data path "
                             "(every rank packs its own block of the queue against its copy of the snapshot); "
                             + ("the launch chain is replayed from one CUDA graph" if graph is not None else "eager launches"),
-                    "e2e_step": e2e_step_desc})
+                    "e2e_step": e2e_step_desc, "e2e_wire": wire or "int64 quantities, int64 offsets, int32 node indices",
+                    "decision_path": ("per-shape capacity tables" if (fused and os.environ.get("GANGPACK_TABLES", "1") != "0") else "node-order scan")
+                                     + f"; {stats['scan_path_apps']} of {q} applications decided by the scan"})
         line = {
             "metric": "gang_placements_per_sec", "value": value, "unit": "decisions/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,

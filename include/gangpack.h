@@ -246,6 +246,43 @@ gp_status gp_reschedule_executors(gp_ctx* ctx, const gp_reschedule* in, int32_t*
  * results; returns when the results are in host memory.  FIFO modes mutate the device snapshot. */
 gp_status gp_pack_batch(gp_ctx* ctx, const gp_apps* apps, gp_algo algo, gp_mode mode, gp_results* out);
 
+/* ---- compact wire formats for the PCIe-bound host path ------------------------------------------------------------
+ * The reference hands a packer six resource.Quantity values and a count per application (types.SparkApplicationResources,
+ * internal/types/types.go:22-27) and reads ExecutorNodes back as strings (binpack.go:25-30); what crosses PCIe here is
+ * chosen per batch by the shim:
+ *   inputs   quantity_bits 64: int64 columns exactly as in gp_apps (60 B per application with offsets);
+ *            quantity_bits 32: int32 columns -- millicores, (bytes >> mem_shift), gpu units -- 28 B per application.  Only
+ *            when every value is exactly representable (memory a whole multiple of 2^mem_shift bytes, everything < 2^31);
+ *            the library rebuilds the exact int64 quantities, so results are bit-identical to the 64-bit layout.
+ *   offsets  exec_out_off NULL: the exclusive prefix sum of exe_count is derived on the device (the caller recomputes
+ *            it with a running sum while it walks the results).
+ *   results  node_bits 16: ExecutorNodes as uint16 node indices -- allowed when the node table has <= 65 535 entries;
+ *            GP_MODE_INDEPENDENT with tightly-pack / distribute-evenly only (GP_ERR_INVALID otherwise). */
+typedef struct {
+    int32_t n_apps;
+    int32_t quantity_bits;           /* 64 or 32 */
+    int32_t mem_shift;               /* 32-bit layout only: 0..40 */
+    int32_t reserved;
+    const void* drv_cpu;             /* [n_apps] int64 or int32, as quantity_bits says */
+    const void* drv_mem;
+    const void* drv_gpu;             /* or NULL (= 0) */
+    const void* exe_cpu;
+    const void* exe_mem;
+    const void* exe_gpu;             /* or NULL (= 0) */
+    const int32_t* exe_count;        /* as in gp_apps */
+    const int32_t* group;            /* or NULL */
+    const uint8_t* skip_if_no_fit;   /* or NULL */
+    const int64_t* exec_out_off;     /* [n_apps+1] or NULL (derived on the device) */
+} gp_apps_wire;
+typedef struct {
+    int32_t* driver_node;            /* [n_apps] as in gp_results */
+    void* executor_nodes;            /* int32[executor_nodes_cap] (node_bits 32) or uint16[executor_nodes_cap] (node_bits 16) */
+    int64_t executor_nodes_cap;
+    int32_t node_bits;               /* 32 or 16 */
+    int32_t reserved;
+} gp_results_wire;
+gp_status gp_pack_batch_wire(gp_ctx* ctx, const gp_apps_wire* apps, gp_algo algo, gp_mode mode, gp_results_wire* out);
+
 /* binpack.SparkBinPackFunction for one application (group 0 of the snapshot).
  * Returns GP_OK and *has_capacity; executor_nodes must hold exe_count entries. */
 gp_status gp_pack_one(gp_ctx* ctx, gp_algo algo,
@@ -255,8 +292,8 @@ gp_status gp_pack_one(gp_ctx* ctx, gp_algo algo,
 
 /* ---- device-resident entry points (multi-GPU plumbing, kernel-only timing) ----------------- */
 /* Same as gp_set_snapshot / gp_pack_batch but every array pointer inside gp_nodes / gp_apps /
- * gp_results is a DEVICE pointer on ctx's device (exec_out_off is then mandatory; group and
- * skip_if_no_fit may still be NULL) and nothing is copied or validated on the host.  Work is
+ * gp_results is a DEVICE pointer on ctx's device (group, skip_if_no_fit and -- for independent tightly-pack /
+ * distribute-evenly -- exec_out_off may be NULL) and nothing is copied or validated on the host.  Work is
  * enqueued on `stream` (a cudaStream_t; NULL = the context's stream) and NOT synchronised (the two
  * order lengths are passed by value so that no device->host read is needed).
  * gp_set_snapshot_device keeps no reference to the caller's arrays after it returns. */
@@ -277,8 +314,11 @@ typedef struct {
     int64_t drivers_tried;
     int64_t kernel_launches;   /* launches of this library's kernels in that call */
     int64_t pack_kernel_ns;    /* device time of the pack kernel (CUDA events on the launch stream) */
-    int64_t prep_kernel_ns;    /* device time of the app-preparation kernel */
-    int64_t reserved[3];
+    int64_t prep_kernel_ns;    /* device time of the kernels before it (preparation / shape classification + capacity tables) */
+    int64_t scan_path_apps;    /* independent tightly/evenly: applications decided by the node-order scan instead of the
+                                  per-shape capacity tables (all of them with GANGPACK_TABLES=0) */
+    int64_t scan_path_nodes;   /* executor-order entries those scans visited (nodes_scanned also counts table probes) */
+    int64_t reserved[1];
 } gp_stats;
 gp_status gp_last_stats(gp_ctx* ctx, gp_stats* out);
 

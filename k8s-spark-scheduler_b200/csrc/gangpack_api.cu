@@ -4,6 +4,7 @@
 #include "gangpack_kernels.cuh"
 #include "gangpack_fifo.cuh"
 #include "gangpack_minfrag.cuh"
+#include "gangpack_tables.cuh"
 #include "gangpack_resched.cuh"
 #include "gangpack_sort.cuh"
 
@@ -23,13 +24,10 @@ using namespace gp;
 // =============================================================================================
 
 constexpr int kPrepThreads = 256;
-// Thread per application: validate, derive the division magics and the driver-displacement bound.
+// Thread per application: validate, derive the division magics and the driver-displacement bound (FIFO modes and
+// minimal-fragmentation; independent tightly-pack / distribute-evenly prepare inside gp_pack_tables).
 // Source tuple: types.SparkApplicationResources (internal/types/types.go:22-27).
-__global__ void gp_prep_apps(int32_t n_apps,
-                             const int64_t* __restrict__ d_cpu, const int64_t* __restrict__ d_mem, const int64_t* __restrict__ d_gpu,
-                             const int64_t* __restrict__ e_cpu, const int64_t* __restrict__ e_mem, const int64_t* __restrict__ e_gpu,
-                             const int32_t* __restrict__ count, const int32_t* __restrict__ group,
-                             const uint8_t* __restrict__ skip, const int64_t* __restrict__ out_off,
+__global__ void gp_prep_apps(int32_t n_apps, AppColumns cols, const uint8_t* __restrict__ skip,
                              int32_t n_groups, int64_t out_cap, const SnapMeta* __restrict__ meta,
                              GroupMin* __restrict__ gmins, PrepApp* __restrict__ prep, int* __restrict__ err,
                              volatile int* __restrict__ err_host) {
@@ -40,49 +38,26 @@ __global__ void gp_prep_apps(int32_t n_apps,
     int32_t i = block0 + threadIdx.x;
     const bool live = i < n_apps;
     if (!live) i = n_apps - 1;                      // keep the thread for the cooperative copy-out; its record is not stored
-    int64_t d[3] = {d_cpu[i], d_mem[i], d_gpu ? d_gpu[i] : 0};
-    int64_t e[3] = {e_cpu[i], e_mem[i], e_gpu ? e_gpu[i] : 0};
-    int32_t k = count[i];
-    int32_t g = group ? group[i] : 0;
+    int64_t d[3] = {cols.load(0, i), cols.load(1, i), cols.load(2, i)};
+    int64_t e[3] = {cols.load(3, i), cols.load(4, i), cols.load(5, i)};
+    int32_t k = cols.count[i];
+    int32_t g = cols.group ? cols.group[i] : 0;
     int bad = 0;
     if (k < 0) bad |= kErrNegativeRequest;
     if (k > kMaxCount) bad |= kErrUnrepresentable;
     if (gmins && k > kMaxCountFifo) bad |= kErrUnrepresentable;   // FIFO modes: block-wide uint32 sums of clamped capacities stay exact
     if (g < 0 || g >= n_groups) bad |= kErrBadGroup;
-    int64_t off = out_off[i];
-    if (off < 0 || out_off[i + 1] - off != (int64_t)k || out_off[i + 1] > out_cap) bad |= kErrBadOffsets;
+    int64_t off = cols.off[i];
+    if (off < 0 || cols.off[i + 1] - off != (int64_t)k || cols.off[i + 1] > out_cap) bad |= kErrBadOffsets;
     PrepApp p;
     uint64_t lmax = 0;
     bool fast = true;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-        if (d[t] < 0 || e[t] < 0) bad |= kErrNegativeRequest;
-        if (d[t] >= kMaxQuantity || e[t] >= kMaxQuantity) bad |= kErrUnrepresentable;
+        uint64_t l;
         p.drv[t] = d[t];
-        DimDiv dv;
-        dv.e = e[t]; dv.magic = 0; dv.sh = 0; dv.kind = kDivInf;
-        if (e[t] > 0) {
-            uint32_t sh = (uint32_t)(__ffsll((long long)e[t]) - 1);
-            uint64_t odd = (uint64_t)e[t] >> sh;
-            dv.sh = sh;
-            if (odd == 1 && sh >= 1) { dv.kind = kDivMagic; dv.magic = 1ull << 63; dv.sh = sh - 1; }   // a / 2^sh = (a >> (sh-1)) / 2
-            else if (odd == 1) dv.kind = kDivShift;                                                     // e == 1
-            else if ((odd >> 32) == 0) { dv.kind = kDivMagic; dv.magic = 0xFFFFFFFFFFFFFFFFull / odd + 1; }
-            else { dv.kind = kDivSlow; dv.sh = 0; }
-            // a driver of d displaces at most ceil(d/e) executors in this dimension
-            if (d[t] > 0) {
-                uint64_t l = ((uint64_t)d[t] + (uint64_t)e[t] - 1) / (uint64_t)e[t];
-                if (l > lmax) lmax = l;
-            }
-        }
-        p.div[t] = dv;
-        // fast class: the shifted numerator of every node fits 32 bits (SnapMeta::max_avail bounds it)
-        if (dv.kind == kDivSlow) fast = false;
-        else if (t < 2 && dv.kind != kDivMagic) fast = false;       // cpu / mem of the fast class are magic divisions only
-        else if (dv.kind != kDivInf) {
-            long long mx = meta->max_avail[t];
-            if (mx > 0 && (((unsigned long long)mx >> dv.sh) >> 32) != 0) fast = false;
-        }
+        p.div[t] = prep_dim(d[t], e[t], t, meta->max_avail[t], bad, l, fast);
+        if (l > lmax) lmax = l;
     }
     if (bad && live) { atomicOr(err, bad); *err_host = bad; }   // err_host: mapped pinned word, no D2H copy needed
     if (bad) { k = 0; g = 0; }
@@ -99,10 +74,7 @@ __global__ void gp_prep_apps(int32_t n_apps,
     p.count = k;
     p.group = g;
     p.lmax = (int32_t)(lmax < (uint64_t)k ? lmax : (uint64_t)k);
-    // compact 32-bit view usable: the request shifts are at least the view's shifts
-    const bool fast32 = fast && p.div[0].kind == kDivMagic && p.div[1].kind == kDivMagic &&
-                        (int)p.div[0].sh >= meta->shift32[0] && (int)p.div[1].sh >= meta->shift32[1] &&
-                        (int)p.div[0].sh - meta->shift32[0] < 32 && (int)p.div[1].sh - meta->shift32[1] < 32;   // 32-bit shift amounts
+    const bool fast32 = prep_fast32(fast, p.div[0], p.div[1], meta);
     p.flags = ((d[2] != 0 || e[2] != 0) ? kAppUsesGpu : 0u) | ((skip && skip[i]) ? kAppSkipIfNoFit : 0u) |
               (bad ? kAppInvalid : 0u) | (fast ? kAppFast : 0u) | (fast32 ? kAppFast32 : 0u);
     constexpr int kQ = sizeof(PrepApp) / sizeof(uint4);      // 8 x 16 bytes per record
@@ -155,7 +127,7 @@ __global__ void __launch_bounds__(kPackThreads, ALGO == 2 ? GP_MF_MIN_BLOCKS : G
                 d = ((pa->flags & kAppFast32) && gpu_idle) ? pack_app_minfrag<true>(s, pa, executor_nodes, scratch, st, lane, snap_flags)
                                                            : pack_app_minfrag<false>(s, pa, executor_nodes, scratch, st, lane, snap_flags);
             } else {
-                d = pack_app<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+                d = pack_app<ALGO, int32_t>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
             }
         }
         if (lane == 0) driver_node[i] = d;
@@ -331,7 +303,7 @@ struct DevBuf {
 };
 
 // dev_misc layout: [0] error bits (int), [8..24) stats (2 x u64), [32..32+4*kMaxChunks) per-chunk work counters
-static constexpr size_t kMiscCounters = 32, kMiscBytes = 32 + 4 * 16;
+static constexpr size_t kMiscCounters = 64, kMiscBytes = 64 + 4 * 16;   // [0] err, [8..40) 4 x u64 statistics, [64..) counters
 static constexpr int32_t kChunkApps = 32768;
 static constexpr int32_t kZeroCopyOutApps = 8192;  // batches up to this size write results straight into mapped host memory   // apps per pipelined chunk of gp_pack_batch (~1.5 MB H2D, ~70 us of kernel)
 
@@ -366,12 +338,15 @@ struct gp_ctx {
     void* one_block = nullptr;                    // gp_pack_one staging (mapped pinned)
     size_t one_bytes = 0;
     int zero_copy = 1;                            // GANGPACK_ZERO_COPY=0 disables reading/writing mapped host buffers in kernels
-    int zero_copy_in_max = 1 << 30;               // batches up to this size read their inputs in place (GANGPACK_ZC_IN_MAX).
-                                                  // Measured on this pool: SM reads of mapped memory sustain ~21 GB/s, H2D DMA
-                                                  // 15-33 GB/s depending on the host -> in-place reads are the steadier default
+    int use_tables = 1;                           // GANGPACK_TABLES=0: every independent decision takes the node-order scan
     int chunk_apps = kChunkApps;                  // GANGPACK_CHUNK_APPS
     int trace = 0;                                // GANGPACK_TRACE=1: host-side phase timing on stderr
     int pack_ctas_per_sm[3] = {0, 0, 0};            // occupancy of gp_pack_independent<ALGO> on this device
+    int tab_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};   // occupancy of gp_pack_tables<ALGO, OUT>
+    bool tab_attr_set[2] = {false, false};
+    // per pipeline lane: shape hash + header, capacity tables, group totals, per-application shape slot
+    struct TableSet { DevBuf hdr, table, total, app_slot; } tabs[kLanes];
+    DevBuf off_dev;                               // ExecutorNodes offsets derived on the device
     bool fifo_attr_set[2] = {false, false};       // dynamic shared-memory opt-in of gp_pack_fifo_cta<ALGO,*> done on this device
 
     gp_stats last{};
@@ -466,7 +441,7 @@ gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
     if (const char* z = std::getenv("GANGPACK_ZERO_COPY")) c->zero_copy = std::atoi(z);
-    if (const char* z = std::getenv("GANGPACK_ZC_IN_MAX")) c->zero_copy_in_max = std::atoi(z);
+    if (const char* z = std::getenv("GANGPACK_TABLES")) c->use_tables = std::atoi(z);
     if (const char* z = std::getenv("GANGPACK_CHUNK_APPS")) c->chunk_apps = std::max(1024, std::atoi(z));
     if (const char* z = std::getenv("GANGPACK_TRACE")) c->trace = std::atoi(z);
     if ((e = cudaSetDevice(dev)) != cudaSuccess ||
@@ -489,8 +464,10 @@ void gp_destroy(gp_ctx* c) {
     DevBuf* bufs[] = {&c->node_cpu, &c->node_mem, &c->node_gpu, &c->exec_off, &c->drv_off, &c->exec_order, &c->drv_order,
                       &c->pair, &c->pair32, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
-                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf, &c->reschedbuf};
+                      &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf, &c->reschedbuf,
+                      &c->off_dev};
     for (DevBuf* b : bufs) b->release();
+    for (auto& t : c->tabs) { t.hdr.release(); t.table.release(); t.total.release(); t.app_slot.release(); }
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
     if (c->one_block) cudaFreeHost(c->one_block);
     for (auto& row : c->ev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
@@ -719,6 +696,29 @@ gp_status gp_get_snapshot(gp_ctx* c, int64_t* cpu, int64_t* mem, int64_t* gpu) {
 
 // ---- packing ------------------------------------------------------------------------------------
 
+// device views of one batch
+struct DevApps {
+    AppColumns cols;                 // device pointers; cols.off may be NULL (derived on the device)
+    const uint8_t* skip;
+    int32_t n;
+};
+struct DevResults {
+    int32_t* driver;
+    void* exec;                      // int32 or uint16
+    int64_t cap;
+    int node_bits;
+};
+
+static AppColumns cols_at(const AppColumns& c, int32_t lo) {
+    AppColumns r = c;
+    const size_t es = c.bits == 64 ? 8 : 4;
+    for (int k = 0; k < 6; ++k) if (c.q[k]) r.q[k] = static_cast<const char*>(c.q[k]) + es * (size_t)lo;
+    r.count = c.count + lo;
+    if (c.group) r.group = c.group + lo;
+    if (c.off) r.off = c.off + lo;
+    return r;
+}
+
 template <int ALGO>
 static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepApp* prep, int32_t n_apps,
                         int32_t* driver_node, int32_t* executor_nodes, int2* scratch, unsigned long long* stats,
@@ -760,15 +760,91 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
     }
 }
 
-// Device-resident apps [lo, hi): enqueue prep + pack on `st`; chunk index selects the timing events.
-static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int32_t hi, gp_algo algo, gp_mode mode,
-                                   gp_results* dout, int2* scratch, cudaStream_t st, int chunk) {
+// independent tightly-pack / distribute-evenly: classify -> capacity tables -> fused pack (gangpack_tables.cuh)
+template <int ALGO, class OUT>
+static gp_status launch_tables(gp_ctx* c, const Snapshot& s, const AppColumns& cols, const ShapeTables& tabs, const int32_t* app_slot,
+                               int32_t q, const DevResults& dr, int32_t lo, int2* scratch, unsigned long long* stats,
+                               unsigned int* next_app, int* d_err, volatile int* err_host, bool use_tables, cudaStream_t st, int chunk) {
+    if (use_tables) {
+        bool& attr = c->tab_attr_set[ALGO];
+        if (!attr) {
+            GP_CUDA(c, cudaFuncSetAttribute(gp_build_shape_tables<ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes));
+            attr = true;
+        }
+        gp_build_shape_tables<ALGO><<<dim3(kMaxShapes, (unsigned)c->n_groups), kTabThreads, kTabSmemBytes, st>>>(s, tabs);
+        c->last.kernel_launches += 1;
+    }
+    int& per_sm = c->tab_ctas_per_sm[ALGO][sizeof(OUT) == 2 ? 1 : 0];
+    if (per_sm == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gp_pack_tables<ALGO, OUT>, kPackTabThreads, 0);
+        if (per_sm < 1) per_sm = 1;
+    }
+    int64_t blocks = ((int64_t)q * 32 + kPackTabThreads - 1) / kPackTabThreads;
+    const int64_t max_blocks = (int64_t)c->sm_count * per_sm;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
+    gp_pack_tables<ALGO, OUT><<<(int)blocks, kPackTabThreads, 0, st>>>(s, cols, tabs, app_slot, q, dr.cap, dr.driver + lo,
+                                                                      static_cast<OUT*>(dr.exec), scratch, stats, next_app, d_err, err_host);
+    c->last.kernel_launches += 1;
+    return GP_OK;
+}
+
+// Device-resident apps [lo, hi): enqueue the kernels on `st`; chunk index selects the timing events and the table lane.
+// off_base: ExecutorNodes offset of application `lo` (only used when the offsets are derived on the device).
+static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int32_t hi, int64_t off_base, gp_algo algo, gp_mode mode,
+                                   const DevResults& dr, int2* scratch, cudaStream_t st, int chunk) {
     const int32_t q = hi - lo;
     if (q <= 0) return GP_OK;
     int* d_err = c->dev_misc.as<int>();
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(c->dev_misc.as<char>() + 8);
-    PrepApp* prep = c->prep.as<PrepApp>() + lo;
     unsigned int* next_app = reinterpret_cast<unsigned int*>(c->dev_misc.as<char>() + kMiscCounters) + chunk;
+    volatile int* err_host = reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48);
+    Snapshot s = make_snapshot(c);
+    AppColumns cols = cols_at(da.cols, lo);
+
+    if (mode == GP_MODE_INDEPENDENT && algo != GP_MINIMAL_FRAGMENTATION) {
+        gp_ctx::TableSet& T = c->tabs[chunk % gp_ctx::kLanes];
+        const size_t hdr_bytes = 512 + sizeof(ShapeEntry) * (size_t)kShapeSlots;
+        static_assert(sizeof(ShapeHeader) <= 512, "ShapeHeader");
+        const bool use_tables = c->use_tables && q >= 32;
+        GP_CUDA(c, T.hdr.reserve(hdr_bytes));
+        GP_CUDA(c, T.app_slot.reserve(sizeof(int32_t) * (size_t)q));
+        if (use_tables) {
+            GP_CUDA(c, T.table.reserve(sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)((c->n_slots + 4) & ~3)));
+            GP_CUDA(c, T.total.reserve(sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)c->n_groups));
+            GP_CUDA(c, cudaMemsetAsync(T.hdr.p, 0, hdr_bytes, st));
+        }
+        ShapeTables tabs;
+        tabs.hdr = T.hdr.as<ShapeHeader>();
+        tabs.entries = reinterpret_cast<ShapeEntry*>(T.hdr.as<char>() + 512);
+        tabs.table = T.table.as<uint32_t>(); tabs.total = T.total.as<uint32_t>();
+        tabs.pitch = (c->n_slots + 4) & ~3; tabs.n_groups = c->n_groups;      // rows start 16-byte aligned
+        int64_t* off_out = nullptr;
+        if (!da.cols.off) {                       // derive the offsets on the device
+            off_out = c->off_dev.as<int64_t>() + lo;
+            cols.off = off_out;
+        }
+        GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
+        gp_classify_apps<<<(q + kClassifyThreads - 1) / kClassifyThreads, kClassifyThreads, 0, st>>>(
+            q, cols, tabs, c->snap_flags.as<SnapMeta>(), off_base, off_out, T.app_slot.as<int32_t>(), use_tables ? 1 : 0);
+        c->last.kernel_launches += 1;
+        gp_status r;
+        const bool o16 = dr.node_bits == 16;
+        if (algo == GP_TIGHTLY_PACK)
+            r = o16 ? launch_tables<0, uint16_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
+                    : launch_tables<0, int32_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
+        else
+            r = o16 ? launch_tables<1, uint16_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
+                    : launch_tables<1, int32_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
+        if (r != GP_OK) return r;
+        GP_CUDA(c, cudaGetLastError());
+        GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
+        return GP_OK;
+    }
+
+    // ---- FIFO modes and minimal-fragmentation: prepared records + the pack kernel ------------------------------------
+    PrepApp* prep = c->prep.as<PrepApp>() + lo;
     const int T = kPrepThreads;
     if (mode != GP_MODE_INDEPENDENT) {
         GP_CUDA(c, c->gmin.reserve(sizeof(GroupMin) * (size_t)c->n_groups));
@@ -776,53 +852,43 @@ static gp_status pack_device_range(gp_ctx* c, const gp_apps* da, int32_t lo, int
     }
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
     gp_prep_apps<<<(q + T - 1) / T, T, 0, st>>>(
-        q, da->drv_cpu_milli + lo, da->drv_mem_bytes + lo, da->drv_gpu ? da->drv_gpu + lo : nullptr, da->exe_cpu_milli + lo,
-        da->exe_mem_bytes + lo, da->exe_gpu ? da->exe_gpu + lo : nullptr, da->exe_count + lo, da->group ? da->group + lo : nullptr,
-        da->skip_if_no_fit ? da->skip_if_no_fit + lo : nullptr, da->exec_out_off + lo, c->n_groups, dout->executor_nodes_cap,
-        c->snap_flags.as<SnapMeta>(), mode == GP_MODE_INDEPENDENT ? nullptr : c->gmin.as<GroupMin>(), prep, d_err,
-        reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48));
-    Snapshot s = make_snapshot(c);
+        q, cols, da.skip ? da.skip + lo : nullptr, c->n_groups, dr.cap,
+        c->snap_flags.as<SnapMeta>(), mode == GP_MODE_INDEPENDENT ? nullptr : c->gmin.as<GroupMin>(), prep, d_err, err_host);
     s.gmins = c->gmin.as<GroupMin>();
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
+    int32_t* exec32 = static_cast<int32_t*>(dr.exec);
     if (algo == GP_TIGHTLY_PACK)
-        launch_pack<0>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
+        launch_pack<0>(c, mode, s, prep, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
     else if (algo == GP_MINIMAL_FRAGMENTATION)
-        launch_pack<2>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
+        launch_pack<2>(c, mode, s, prep, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
     else
-        launch_pack<1>(c, mode, s, prep, q, dout->driver_node + lo, dout->executor_nodes, scratch, d_stats, next_app, st);
+        launch_pack<1>(c, mode, s, prep, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
     GP_CUDA(c, cudaGetLastError());
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
     c->last.kernel_launches += 2;
     return GP_OK;
 }
 
+static bool fused_path(gp_algo algo, gp_mode mode) { return mode == GP_MODE_INDEPENDENT && algo != GP_MINIMAL_FRAGMENTATION; }
+
 // common prologue: buffers, counters
-static gp_status pack_begin(gp_ctx* c, int32_t q, gp_algo algo, const gp_results* dout, int2** scratch, cudaStream_t st) {
+static gp_status pack_begin(gp_ctx* c, int32_t q, gp_algo algo, gp_mode mode, int64_t exec_cap, bool derive_off, int2** scratch, cudaStream_t st) {
     GP_CUDA(c, cudaMemsetAsync(c->dev_misc.p, 0, kMiscBytes, st));
     *reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48) = 0;   // host-visible error word
     c->last = gp_stats{};
     c->ev_chunks = 0;
     *scratch = nullptr;
     if (q == 0) return GP_OK;
-    GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));
+    if (!fused_path(algo, mode)) GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));
+    if (derive_off) GP_CUDA(c, c->off_dev.reserve(sizeof(int64_t) * (size_t)(q + 1)));
     if (algo != GP_TIGHTLY_PACK) {        // candidate list (distribute-evenly) / consumed-node list (minimal-fragmentation)
-        GP_CUDA(c, c->scratch.reserve(sizeof(int2) * (size_t)(dout->executor_nodes_cap + 1)));
+        GP_CUDA(c, c->scratch.reserve(sizeof(int2) * (size_t)(exec_cap + 1)));
         *scratch = c->scratch.as<int2>();
     }
     return GP_OK;
 }
 
-// everything device-resident; enqueues prep + pack on `st`
-static gp_status pack_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode mode, gp_results* dout, cudaStream_t st) {
-    int2* scratch = nullptr;
-    gp_status s = pack_begin(c, da->n_apps, algo, dout, &scratch, st);
-    if (s != GP_OK || da->n_apps == 0) return s;
-    s = pack_device_range(c, da, 0, da->n_apps, algo, mode, dout, scratch, st, 0);
-    if (s == GP_OK) c->ev_chunks = 1;
-    return s;
-}
-
-static gp_status check_args(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, const gp_results* out, const char* who) {
+static gp_status check_args(gp_ctx* c, const gp_apps_wire* a, gp_algo algo, gp_mode mode, const gp_results_wire* out, const char* who) {
     if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, std::string(who) + ": gp_set_snapshot first");
     if (!a || !out || a->n_apps < 0) return fail(c, GP_ERR_INVALID, std::string(who) + ": NULL apps/results");
     if (algo != GP_TIGHTLY_PACK && algo != GP_DISTRIBUTE_EVENLY && algo != GP_MINIMAL_FRAGMENTATION)
@@ -832,9 +898,15 @@ static gp_status check_args(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode m
                                                           "(its one registered caller, single-az-minimal-fragmentation, chooses a zone per application on the host)");
     if (mode != GP_MODE_INDEPENDENT && mode != GP_MODE_FIFO_REFERENCE && mode != GP_MODE_FIFO_EXACT)
         return fail(c, GP_ERR_INVALID, std::string(who) + ": unknown mode");
-    if (a->n_apps > 0 && (!a->drv_cpu_milli || !a->drv_mem_bytes || !a->exe_cpu_milli || !a->exe_mem_bytes || !a->exe_count ||
-                          !out->driver_node))
+    if (a->quantity_bits != 64 && a->quantity_bits != 32) return fail(c, GP_ERR_INVALID, std::string(who) + ": quantity_bits must be 64 or 32");
+    if (a->quantity_bits == 32 && (a->mem_shift < 0 || a->mem_shift > 40)) return fail(c, GP_ERR_INVALID, std::string(who) + ": mem_shift out of range");
+    if (out->node_bits != 32 && out->node_bits != 16) return fail(c, GP_ERR_INVALID, std::string(who) + ": node_bits must be 32 or 16");
+    if (out->node_bits == 16 && (!fused_path(algo, mode) || c->n_nodes > 65535))
+        return fail(c, GP_ERR_INVALID, std::string(who) + ": 16-bit node indices need <= 65535 nodes and GP_MODE_INDEPENDENT tightly-pack / distribute-evenly");
+    if (a->n_apps > 0 && (!a->drv_cpu || !a->drv_mem || !a->exe_cpu || !a->exe_mem || !a->exe_count || !out->driver_node))
         return fail(c, GP_ERR_INVALID, std::string(who) + ": missing app/result arrays");
+    if (a->n_apps > 0 && !a->exec_out_off && !fused_path(algo, mode))
+        return fail(c, GP_ERR_INVALID, std::string(who) + ": exec_out_off may only be NULL for GP_MODE_INDEPENDENT tightly-pack / distribute-evenly");
     return GP_OK;
 }
 
@@ -850,40 +922,65 @@ static void fill_kernel_times(gp_ctx* c) {
 
 static gp_status decode_device_error(gp_ctx* c, int err) {
     if (err == 0) return GP_OK;
-    if (err & kErrUnrepresentable) return fail(c, GP_ERR_UNREPRESENTABLE, "pack: quantity >= 2^61 or exe_count > 2^24");
+    if (err & kErrUnrepresentable) return fail(c, GP_ERR_UNREPRESENTABLE, "pack: quantity >= 2^61 or exe_count > 2^24 (2^20 in the FIFO modes)");
     if (err & kErrNegativeRequest) return fail(c, GP_ERR_INVALID, "pack: negative resource request or executor count");
     if (err & kErrBadGroup) return fail(c, GP_ERR_INVALID, "pack: app group out of range");
     return fail(c, GP_ERR_CAPACITY, "pack: exec_out_off inconsistent with exe_count or executor_nodes_cap too small");
+}
+
+static gp_apps_wire widen(const gp_apps* a) {
+    gp_apps_wire w{};
+    w.n_apps = a->n_apps; w.quantity_bits = 64; w.mem_shift = 0;
+    w.drv_cpu = a->drv_cpu_milli; w.drv_mem = a->drv_mem_bytes; w.drv_gpu = a->drv_gpu;
+    w.exe_cpu = a->exe_cpu_milli; w.exe_mem = a->exe_mem_bytes; w.exe_gpu = a->exe_gpu;
+    w.exe_count = a->exe_count; w.group = a->group; w.skip_if_no_fit = a->skip_if_no_fit; w.exec_out_off = a->exec_out_off;
+    return w;
 }
 
 extern "C" {
 
 gp_status gp_pack_batch_device(gp_ctx* c, const gp_apps* da, gp_algo algo, gp_mode mode, gp_results* dout, void* stream) {
     if (!c) return GP_ERR_INVALID;
-    gp_status s = check_args(c, da, algo, mode, dout, "gp_pack_batch_device");
+    if (!da || !dout) return fail(c, GP_ERR_INVALID, "gp_pack_batch_device: NULL apps/results");
+    const gp_apps_wire w = widen(da);
+    gp_results_wire ow{dout->driver_node, dout->executor_nodes, dout->executor_nodes_cap, 32, 0};
+    gp_status s = check_args(c, &w, algo, mode, &ow, "gp_pack_batch_device");
     if (s != GP_OK) return s;
-    if (da->n_apps > 0 && !da->exec_out_off) return fail(c, GP_ERR_INVALID, "gp_pack_batch_device: exec_out_off is mandatory");
     GP_CUDA(c, cudaSetDevice(c->device));
-    return pack_device(c, da, algo, mode, dout, stream ? (cudaStream_t)stream : c->stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int2* scratch = nullptr;
+    s = pack_begin(c, w.n_apps, algo, mode, ow.executor_nodes_cap, !w.exec_out_off, &scratch, st);
+    if (s != GP_OK || w.n_apps == 0) return s;
+    DevApps dv{};
+    dv.cols.q[0] = w.drv_cpu; dv.cols.q[1] = w.drv_mem; dv.cols.q[2] = w.drv_gpu;
+    dv.cols.q[3] = w.exe_cpu; dv.cols.q[4] = w.exe_mem; dv.cols.q[5] = w.exe_gpu;
+    dv.cols.count = w.exe_count; dv.cols.group = w.group; dv.cols.off = w.exec_out_off; dv.cols.bits = 64; dv.cols.mem_shift = 0;
+    dv.skip = w.skip_if_no_fit; dv.n = w.n_apps;
+    DevResults dr{ow.driver_node, ow.executor_nodes, ow.executor_nodes_cap, 32};
+    s = pack_device_range(c, dv, 0, w.n_apps, 0, algo, mode, dr, scratch, st, 0);
+    if (s == GP_OK) c->ev_chunks = 1;
+    return s;
 }
 
 gp_status gp_last_stats(gp_ctx* c, gp_stats* out) {
     if (!c || !out) return GP_ERR_INVALID;
     GP_CUDA(c, cudaSetDevice(c->device));
-    GP_CUDA(c, cudaMemcpyAsync(c->pinned_misc, c->dev_misc.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(c->pinned_misc, c->dev_misc.p, 40, cudaMemcpyDeviceToHost, c->stream));
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
     const unsigned long long* s = reinterpret_cast<const unsigned long long*>((const char*)c->pinned_misc + 8);
     c->last.nodes_scanned = (int64_t)s[0];
     c->last.drivers_tried = (int64_t)s[1];
+    c->last.scan_path_apps = (int64_t)s[2];
+    c->last.scan_path_nodes = (int64_t)s[3];
     fill_kernel_times(c);
     *out = c->last;
     int err = *reinterpret_cast<const int*>(c->pinned_misc);
     return decode_device_error(c, err);
 }
 
-static gp_status pack_batch_impl(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out);
+static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo, gp_mode mode, gp_results_wire* out);
 
-gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out) {
+gp_status gp_pack_batch_wire(gp_ctx* c, const gp_apps_wire* a, gp_algo algo, gp_mode mode, gp_results_wire* out) {
     if (!c) return GP_ERR_INVALID;
     gp_status s = pack_batch_impl(c, a, algo, mode, out);
     if (s != GP_OK) {
@@ -899,7 +996,15 @@ gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode,
     return s;
 }
 
-static gp_status pack_batch_impl(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out) {
+gp_status gp_pack_batch(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_results* out) {
+    if (!c) return GP_ERR_INVALID;
+    if (!a || !out) return fail(c, GP_ERR_INVALID, "gp_pack_batch: NULL apps/results");
+    const gp_apps_wire w = widen(a);
+    gp_results_wire ow{out->driver_node, out->executor_nodes, out->executor_nodes_cap, 32, 0};
+    return gp_pack_batch_wire(c, &w, algo, mode, &ow);
+}
+
+static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo, gp_mode mode, gp_results_wire* out) {
     gp_status s = check_args(c, a, algo, mode, out, "gp_pack_batch");
     if (s != GP_OK) return s;
     const int32_t q = a->n_apps;
@@ -907,66 +1012,49 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_m
     const auto t_begin = std::chrono::steady_clock::now();
     GP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    // ExecutorNodes offsets: the caller's CSR offsets, or computed here
-    const int64_t* off = a->exec_out_off;
-    if (!off) {
-        c->host_off.resize((size_t)q + 1);
-        int64_t acc = 0;
-        for (int32_t i = 0; i < q; ++i) { c->host_off[i] = acc; acc += a->exe_count[i] > 0 ? a->exe_count[i] : 0; }
-        c->host_off[q] = acc;
-        off = c->host_off.data();
+    const size_t es = a->quantity_bits == 64 ? 8 : 4;       // bytes per quantity
+    const size_t os = out->node_bits == 16 ? 2 : 4;         // bytes per ExecutorNodes entry
+    const int64_t* off = a->exec_out_off;                   // may be NULL: derived on the device, chunk bases summed here
+    if (off) {
+        const int64_t total = off[q];
+        if (total < 0 || total > out->executor_nodes_cap) return fail(c, GP_ERR_CAPACITY, "gp_pack_batch: executor_nodes_cap too small");
+        if (total > 0 && !out->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_batch: executor_nodes is NULL");
     }
-    const int64_t total = off[q];
-    if (total < 0 || total > out->executor_nodes_cap) return fail(c, GP_ERR_CAPACITY, "gp_pack_batch: executor_nodes_cap too small");
-    if (total > 0 && !out->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_batch: executor_nodes is NULL");
-
-    const size_t b64 = sizeof(int64_t) * (size_t)q, b32 = sizeof(int32_t) * (size_t)q;
-    // the int64 columns are staged in ONE pitched device block (rows: drv cpu, drv mem, exe cpu, exe mem, drv gpu,
+    const size_t bq = es * (size_t)q, b32 = sizeof(int32_t) * (size_t)q;
+    // the quantity columns are staged in ONE pitched device block (rows: drv cpu, drv mem, exe cpu, exe mem, drv gpu,
     // exe gpu) so that equally spaced host columns can be moved by a single 2-D DMA per chunk
-    const size_t dpitch = (b64 + 255) & ~(size_t)255;
+    const size_t dpitch = (bq + 255) & ~(size_t)255;
     GP_CUDA(c, c->a_dcpu.reserve(dpitch * 6));
     GP_CUDA(c, c->a_count.reserve(b32));
-    GP_CUDA(c, c->a_off.reserve(sizeof(int64_t) * (size_t)(q + 1)));
+    if (off) GP_CUDA(c, c->a_off.reserve(sizeof(int64_t) * (size_t)(q + 1)));
     GP_CUDA(c, c->r_driver.reserve(b32));
-    GP_CUDA(c, c->r_exec.reserve(sizeof(int32_t) * (size_t)(total + 1)));
+    GP_CUDA(c, c->r_exec.reserve(os * (size_t)(out->executor_nodes_cap + 1)));
     if (a->group) GP_CUDA(c, c->a_group.reserve(b32));
     if (a->skip_if_no_fit) GP_CUDA(c, c->a_skip.reserve((size_t)q));
-    // Mapped pinned inputs are read by gp_prep_apps straight from host memory (each value is read exactly
-    // once, so staging them in HBM first would only add a copy); otherwise they are staged by DMA.
-    const void* mi[10] = {mapped_ptr(c, a->drv_cpu_milli, b64), mapped_ptr(c, a->drv_mem_bytes, b64),
-                          mapped_ptr(c, a->exe_cpu_milli, b64), mapped_ptr(c, a->exe_mem_bytes, b64),
-                          mapped_ptr(c, a->exe_count, b32), mapped_ptr(c, off, sizeof(int64_t) * (size_t)(q + 1)),
-                          a->drv_gpu ? mapped_ptr(c, a->drv_gpu, b64) : nullptr, a->exe_gpu ? mapped_ptr(c, a->exe_gpu, b64) : nullptr,
-                          a->group ? mapped_ptr(c, a->group, b32) : nullptr,
-                          a->skip_if_no_fit ? mapped_ptr(c, a->skip_if_no_fit, (size_t)q) : nullptr};
-    const bool in_mapped = q <= c->zero_copy_in_max && mi[0] && mi[1] && mi[2] && mi[3] && mi[4] && mi[5] && (!a->drv_gpu || mi[6]) && (!a->exe_gpu || mi[7]) &&
-                           (!a->group || mi[8]) && (!a->skip_if_no_fit || mi[9]);
-    // Small batches are latency-bound: results are written straight into mapped host buffers.
-    // Large ones are bandwidth-bound: one big DMA per chunk uses PCIe better than 64-byte stores.
-    void* mo_driver = const_cast<void*>(mapped_ptr(c, out->driver_node, b32));
-    void* mo_exec = total > 0 ? const_cast<void*>(mapped_ptr(c, out->executor_nodes, sizeof(int32_t) * (size_t)total)) : nullptr;
-    const bool out_mapped = q <= kZeroCopyOutApps && mo_driver && (total == 0 || mo_exec);
-    gp_apps da = *a;
-    if (in_mapped) {
-        da.drv_cpu_milli = (const int64_t*)mi[0]; da.drv_mem_bytes = (const int64_t*)mi[1];
-        da.exe_cpu_milli = (const int64_t*)mi[2]; da.exe_mem_bytes = (const int64_t*)mi[3];
-        da.exe_count = (const int32_t*)mi[4]; da.exec_out_off = (const int64_t*)mi[5];
-        da.drv_gpu = (const int64_t*)mi[6]; da.exe_gpu = (const int64_t*)mi[7];
-        da.group = (const int32_t*)mi[8]; da.skip_if_no_fit = (const uint8_t*)mi[9];
-    } else {
-        char* blk = c->a_dcpu.as<char>();
-        da.drv_cpu_milli = (const int64_t*)(blk + 0 * dpitch); da.drv_mem_bytes = (const int64_t*)(blk + 1 * dpitch);
-        da.exe_cpu_milli = (const int64_t*)(blk + 2 * dpitch); da.exe_mem_bytes = (const int64_t*)(blk + 3 * dpitch);
-        da.exe_count = c->a_count.as<int32_t>(); da.exec_out_off = c->a_off.as<int64_t>();
-        da.drv_gpu = a->drv_gpu ? (const int64_t*)(blk + 4 * dpitch) : nullptr;
-        da.exe_gpu = a->exe_gpu ? (const int64_t*)(blk + 5 * dpitch) : nullptr;
-        da.group = a->group ? c->a_group.as<int32_t>() : nullptr;
-        da.skip_if_no_fit = a->skip_if_no_fit ? c->a_skip.as<uint8_t>() : nullptr;
-    }
-    gp_results dr;
-    dr.driver_node = out_mapped ? (int32_t*)mo_driver : c->r_driver.as<int32_t>();
-    dr.executor_nodes = out_mapped ? (int32_t*)mo_exec : c->r_exec.as<int32_t>();
-    dr.executor_nodes_cap = total;
+    // Small batches are latency-bound: inputs are gathered by ONE kernel reading the mapped host buffers (a chain of
+    // tiny DMA copies costs ~8-10 us each in stream order) and results are written straight into mapped host buffers.
+    // Large ones are bandwidth-bound: DMA per pipelined chunk in both directions.
+    const bool small = q <= kZeroCopyOutApps;
+    void* mo_driver = small ? const_cast<void*>(mapped_ptr(c, out->driver_node, b32)) : nullptr;
+    void* mo_exec = (small && out->executor_nodes) ? const_cast<void*>(mapped_ptr(c, out->executor_nodes, os * (size_t)out->executor_nodes_cap)) : nullptr;
+    const bool out_mapped = small && mo_driver && (out->executor_nodes_cap == 0 || !out->executor_nodes || mo_exec);
+    char* blk = c->a_dcpu.as<char>();
+    DevApps dv{};
+    const void* hq[6] = {a->drv_cpu, a->drv_mem, a->exe_cpu, a->exe_mem, a->drv_gpu, a->exe_gpu};    // staging row order
+    dv.cols.q[0] = blk + 0 * dpitch; dv.cols.q[1] = blk + 1 * dpitch; dv.cols.q[3] = blk + 2 * dpitch; dv.cols.q[4] = blk + 3 * dpitch;
+    dv.cols.q[2] = a->drv_gpu ? blk + 4 * dpitch : nullptr;
+    dv.cols.q[5] = a->exe_gpu ? blk + 5 * dpitch : nullptr;
+    dv.cols.count = c->a_count.as<int32_t>();
+    dv.cols.group = a->group ? c->a_group.as<int32_t>() : nullptr;
+    dv.cols.off = off ? c->a_off.as<int64_t>() : nullptr;
+    dv.cols.bits = a->quantity_bits; dv.cols.mem_shift = a->mem_shift;
+    dv.skip = a->skip_if_no_fit ? c->a_skip.as<uint8_t>() : nullptr;
+    dv.n = q;
+    DevResults dr;
+    dr.driver = out_mapped ? (int32_t*)mo_driver : c->r_driver.as<int32_t>();
+    dr.exec = out_mapped ? mo_exec : c->r_exec.p;
+    dr.cap = out->executor_nodes_cap;
+    dr.node_bits = out->node_bits;
 
     // Independent decisions are chunked and the chunks rotate over kLanes streams, so the H2D of
     // chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap (PCIe is full duplex).
@@ -977,50 +1065,85 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_m
         if (n_chunks > gp_ctx::kMaxChunks) n_chunks = gp_ctx::kMaxChunks;
     }
     int2* scratch = nullptr;
-    s = pack_begin(c, q, algo, &dr, &scratch, st);
+    s = pack_begin(c, q, algo, mode, out->executor_nodes_cap, !off, &scratch, st);
     if (s != GP_OK) return s;
     GP_CUDA(c, cudaEventRecord(c->ev_ready, st));      // snapshot + zeroed counters are ready
+    int64_t e_run = 0;                                 // ExecutorNodes entries before the current chunk
     for (int ch = 0; ch < n_chunks; ++ch) {
         const int32_t lo = (int32_t)((int64_t)q * ch / n_chunks), hi = (int32_t)((int64_t)q * (ch + 1) / n_chunks);
         const size_t n = (size_t)(hi - lo);
         cudaStream_t ls = n_chunks == 1 ? st : c->lane[ch % gp_ctx::kLanes];
         if (n_chunks > 1) GP_CUDA(c, cudaStreamWaitEvent(ls, c->ev_ready, 0));
-        if (!in_mapped) {
-            // int64 columns: one 2-D DMA when the host columns are equally spaced (one pinned block laid out
+        // ---- inputs -> HBM ----------------------------------------------------------------------------------
+        bool gathered = false;
+        if (small && !a->skip_if_no_fit) {
+            CopyJobs jobs{};
+            bool ok = true;
+            auto add = [&](const void* src, void* dst, size_t bytes) {
+                if (!src || !bytes) return;
+                const void* m = mapped_ptr(c, src, bytes);
+                if (!m || jobs.n >= 8) { ok = false; return; }
+                jobs.j[jobs.n++] = CopyJob{m, dst, bytes};
+            };
+            // all six quantity rows when they are one equally spaced block, else row by row (<= 8 jobs in total)
+            add(a->drv_cpu, blk + 0 * dpitch, bq); add(a->drv_mem, blk + 1 * dpitch, bq);
+            add(a->exe_cpu, blk + 2 * dpitch, bq); add(a->exe_mem, blk + 3 * dpitch, bq);
+            if (a->drv_gpu) add(a->drv_gpu, blk + 4 * dpitch, bq);
+            if (a->exe_gpu) add(a->exe_gpu, blk + 5 * dpitch, bq);
+            add(a->exe_count, c->a_count.p, b32);
+            if (a->group) add(a->group, c->a_group.p, b32);
+            if (off && ok) { if (jobs.n < 8) add(off, c->a_off.p, sizeof(int64_t) * (size_t)(q + 1)); else ok = false; }
+            if (ok) {
+                gp_multi_copy<<<q <= 64 ? 1 : 32, 256, 0, ls>>>(jobs);
+                GP_CUDA(c, cudaGetLastError());
+                c->last.kernel_launches += 1;
+                gathered = true;
+            }
+        }
+        if (!gathered) {
+            // quantity columns: one 2-D DMA when the host columns are equally spaced (one pinned block laid out
             // column after column, as the shim allocates it), else one DMA per column
-            const int64_t* cols[6] = {a->drv_cpu_milli, a->drv_mem_bytes, a->exe_cpu_milli, a->exe_mem_bytes, a->drv_gpu, a->exe_gpu};
             int ncols = 4;
             if (a->drv_gpu && a->exe_gpu) ncols = 6;
-            const ptrdiff_t spitch = (const char*)cols[1] - (const char*)cols[0];
-            bool spaced = spitch >= (ptrdiff_t)b64 && spitch <= ((ptrdiff_t)1 << 30);   // cudaMemcpy2D pitch limit (maxPitch ~2 GiB)
-            for (int k = 2; spaced && k < ncols; ++k) spaced = ((const char*)cols[k] - (const char*)cols[k - 1]) == spitch;
-            char* blk = c->a_dcpu.as<char>();
-            if (spaced && cudaMemcpy2DAsync(blk + sizeof(int64_t) * (size_t)lo, dpitch, cols[0] + lo, (size_t)spitch,
-                                            sizeof(int64_t) * n, (size_t)ncols, cudaMemcpyHostToDevice, ls) != cudaSuccess) {
+            const ptrdiff_t spitch = (const char*)hq[1] - (const char*)hq[0];
+            bool spaced = spitch >= (ptrdiff_t)bq && spitch <= ((ptrdiff_t)1 << 30);   // cudaMemcpy2D pitch limit (maxPitch ~2 GiB)
+            for (int k = 2; spaced && k < ncols; ++k) spaced = ((const char*)hq[k] - (const char*)hq[k - 1]) == spitch;
+            if (spaced && cudaMemcpy2DAsync(blk + es * (size_t)lo, dpitch, (const char*)hq[0] + es * (size_t)lo, (size_t)spitch,
+                                            es * n, (size_t)ncols, cudaMemcpyHostToDevice, ls) != cudaSuccess) {
                 cudaGetLastError();      // not accepted as a 2-D copy after all: column by column
                 spaced = false;
             }
             if (!spaced) {
                 for (int k = 0; k < ncols; ++k)
-                    GP_CUDA(c, cudaMemcpyAsync(blk + k * dpitch + sizeof(int64_t) * (size_t)lo, cols[k] + lo, sizeof(int64_t) * n,
+                    GP_CUDA(c, cudaMemcpyAsync(blk + k * dpitch + es * (size_t)lo, (const char*)hq[k] + es * (size_t)lo, es * n,
                                                cudaMemcpyHostToDevice, ls));
             }
             if (ncols == 4) {   // gpu columns given one at a time
-                if (a->drv_gpu) GP_CUDA(c, cudaMemcpyAsync(blk + 4 * dpitch + sizeof(int64_t) * (size_t)lo, a->drv_gpu + lo, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ls));
-                if (a->exe_gpu) GP_CUDA(c, cudaMemcpyAsync(blk + 5 * dpitch + sizeof(int64_t) * (size_t)lo, a->exe_gpu + lo, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ls));
+                if (a->drv_gpu) GP_CUDA(c, cudaMemcpyAsync(blk + 4 * dpitch + es * (size_t)lo, (const char*)a->drv_gpu + es * (size_t)lo, es * n, cudaMemcpyHostToDevice, ls));
+                if (a->exe_gpu) GP_CUDA(c, cudaMemcpyAsync(blk + 5 * dpitch + es * (size_t)lo, (const char*)a->exe_gpu + es * (size_t)lo, es * n, cudaMemcpyHostToDevice, ls));
             }
             GP_CUDA(c, cudaMemcpyAsync(c->a_count.as<int32_t>() + lo, a->exe_count + lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ls));
-            GP_CUDA(c, cudaMemcpyAsync(c->a_off.as<int64_t>() + lo, off + lo, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ls));
+            if (off) GP_CUDA(c, cudaMemcpyAsync(c->a_off.as<int64_t>() + lo, off + lo, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ls));
             if (a->group) GP_CUDA(c, cudaMemcpyAsync(c->a_group.as<int32_t>() + lo, a->group + lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ls));
             if (a->skip_if_no_fit) GP_CUDA(c, cudaMemcpyAsync(c->a_skip.as<uint8_t>() + lo, a->skip_if_no_fit + lo, n, cudaMemcpyHostToDevice, ls));
         }
-        s = pack_device_range(c, &da, lo, hi, algo, mode, &dr, scratch, ls, ch);
+        // ---- this chunk's ExecutorNodes range ------------------------------------------------------------------
+        int64_t e0, e1;
+        if (off) { e0 = off[lo]; e1 = off[hi]; }
+        else {
+            int64_t acc = 0;
+            const int32_t* cnt = a->exe_count;
+            for (int32_t i = lo; i < hi; ++i) acc += cnt[i] > 0 ? cnt[i] : 0;
+            e0 = e_run; e1 = e_run + acc; e_run = e1;
+            if (e1 > out->executor_nodes_cap) return fail(c, GP_ERR_CAPACITY, "gp_pack_batch: executor_nodes_cap too small");
+            if (e1 > 0 && !out->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_batch: executor_nodes is NULL");
+        }
+        s = pack_device_range(c, dv, lo, hi, e0, algo, mode, dr, scratch, ls, ch);
         if (s != GP_OK) return s;
         if (out_mapped) continue;
-        GP_CUDA(c, cudaMemcpyAsync(out->driver_node + lo, dr.driver_node + lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ls));
-        const int64_t e0 = off[lo], e1 = off[hi];
+        GP_CUDA(c, cudaMemcpyAsync(out->driver_node + lo, dr.driver + lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ls));
         if (e1 > e0)
-            GP_CUDA(c, cudaMemcpyAsync(out->executor_nodes + e0, dr.executor_nodes + e0, sizeof(int32_t) * (size_t)(e1 - e0),
+            GP_CUDA(c, cudaMemcpyAsync((char*)out->executor_nodes + os * (size_t)e0, (char*)dr.exec + os * (size_t)e0, os * (size_t)(e1 - e0),
                                        cudaMemcpyDeviceToHost, ls));
     }
     c->ev_chunks = n_chunks;
@@ -1034,8 +1157,8 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_m
     GP_CUDA(c, cudaStreamSynchronize(st));
     if (c->trace) {
         const auto t_done = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[gangpack] pack_batch q=%d chunks=%d in_mapped=%d out_mapped=%d issue=%.1fus wait=%.1fus\n", q, n_chunks,
-                     (int)in_mapped, (int)out_mapped, std::chrono::duration<double, std::micro>(t_issued - t_begin).count(),
+        std::fprintf(stderr, "[gangpack] pack_batch q=%d chunks=%d bits=%d/%d out_mapped=%d issue=%.1fus wait=%.1fus\n", q, n_chunks,
+                     a->quantity_bits, out->node_bits, (int)out_mapped, std::chrono::duration<double, std::micro>(t_issued - t_begin).count(),
                      std::chrono::duration<double, std::micro>(t_done - t_issued).count());
     }
     // validation errors arrive through the mapped error word; scan statistics stay on the device until
@@ -1072,7 +1195,7 @@ gp_status gp_pack_one(gp_ctx* c, gp_algo algo, int64_t drv_cpu, int64_t drv_mem,
     a.drv_cpu_milli = q + 0; a.drv_mem_bytes = q + 1; a.drv_gpu = q + 2;
     a.exe_cpu_milli = q + 3; a.exe_mem_bytes = q + 4; a.exe_gpu = q + 5;
     a.exe_count = i32;
-    a.exec_out_off = q + 6;
+    a.exec_out_off = algo == GP_MINIMAL_FRAGMENTATION ? q + 6 : nullptr;   // derived on the device where the kernel can
     gp_results r{};
     r.driver_node = i32 + 1;
     r.executor_nodes = exec_out;

@@ -280,9 +280,9 @@ __device__ __forceinline__ bool driver_fits(const Snapshot& s, int32_t slot, con
 // R* = min r with sum min(c, r) >= k; round r hands one executor to every node with c >= r until k are
 // placed; ExecutorNodes is round-major.  charge1(local_slot) subtracts one executor (FIFO modes).
 // Returns whether the driver's node received an executor.
-template <int FIFO_MODE, class ChargeFn>
+template <int FIFO_MODE, class OUT, class ChargeFn>
 __device__ __forceinline__ bool evenly_rounds(int2* __restrict__ list, uint32_t m, uint32_t k, int32_t dslot, uint32_t cd,
-                                              int32_t* __restrict__ out, const int32_t* __restrict__ slot_node, int lane,
+                                              OUT* __restrict__ out, const int32_t* __restrict__ slot_node, int lane,
                                               ChargeFn charge1) {
     bool driver_hosts_executor = false;
     for (uint32_t t = lane; t < m; t += kWarp) {   // patch the driver's own entry with cap(d|drv)
@@ -311,7 +311,7 @@ __device__ __forceinline__ bool evenly_rounds(int2* __restrict__ list, uint32_t 
             unsigned has = __ballot_sync(kFull, in);
             uint32_t idx = base + __popc(has & ((1u << lane) - 1u));
             if (in && idx < k) {
-                out[idx] = slot_node[e.x];
+                out[idx] = (OUT)slot_node[e.x];
                 if (FIFO_MODE == 2 || (FIFO_MODE == 1 && r == 1)) charge1(e.x);
                 if (FIFO_MODE != 0 && e.x == dslot) driver_hosts_executor = true;
             }
@@ -330,9 +330,9 @@ constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 cap
 // gangpack_fifo.cuh).  Returns the driver's node index (>= 0) or -1.
 // ALGO: 0 tightly-pack, 1 distribute-evenly.  wcache: this warp's kCapCache x uint16 scratch in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, bool FAST, bool NOGPU, bool C32>
+template <int ALGO, bool FAST, bool NOGPU, bool C32, class OUT>
 __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepApp* __restrict__ pa,
-                                                 int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
+                                                 OUT* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane,
                                                  int snap_flags, const GroupDesc& g0) {
     constexpr bool MUT = false;   // read-only path (ld.global.nc)
@@ -346,7 +346,7 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
     const uint32_t lmax = (uint32_t)pa->lmax;
     const int32_t ne = g.ne;
     const int64_t out_off = pa->out_off;
-    int32_t* out = executor_nodes + out_off;
+    OUT* out = executor_nodes + out_off;
     int2* list = scratch ? scratch + out_off : nullptr;   // distribute-evenly candidate list
     const bool cache_ok = k <= 0xFFFFu;
 
@@ -450,7 +450,7 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
                             if (v <= j) lo += step;
                         }
                         int32_t nd = __shfl_sync(kFull, node, lo & 31);
-                        if (j < T) out[placed + j] = nd;
+                        if (j < T) out[placed + j] = (OUT)nd;
                     }
                 }
                 placed += T;
@@ -467,12 +467,12 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
                 if (p0 >= cached_end) st.nodes += (unsigned long long)((ne - p0) < kWarp ? (ne - p0) : kWarp);
                 unsigned has = __ballot_sync(kFull, c != 0);
                 uint32_t r = placed + __popc(has & ((1u << lane) - 1u));
-                if (c != 0 && r < k) out[r] = s.slot_node[g.sbase + i];
+                if (c != 0 && r < k) out[r] = (OUT)s.slot_node[g.sbase + i];
                 placed += __popc(has);
             }
         } else {
             __syncwarp();
-            evenly_rounds<0>(list, m1, k, dslot, cd, out, s.slot_node + g.sbase, lane, [](int32_t) {});
+            evenly_rounds<0, OUT>(list, m1, k, dslot, cd, out, s.slot_node + g.sbase, lane, [](int32_t) {});
         }
     }
 
@@ -480,35 +480,71 @@ __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepAp
 }
 
 // everything that is not (fast class, gpu dimension idle): any int64 request / binding gpu dimension
-template <int ALGO>
+template <int ALGO, class OUT>
 __device__ __noinline__ int32_t pack_app_general(const Snapshot& s, const PrepApp* __restrict__ pa,
-                                                 int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
+                                                 OUT* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane, int snap_flags) {
     const GroupDesc g0 = s.groups[0];
-    return pack_app_impl<ALGO, false, false, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+    return pack_app_impl<ALGO, false, false, false, OUT>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
 }
 
 // fast class whose request shifts are below the compact view's shift (e.g. byte-granular memory requests)
-template <int ALGO>
+template <int ALGO, class OUT>
 __device__ __noinline__ int32_t pack_app_fast64(const Snapshot& s, const PrepApp* __restrict__ pa,
-                                                int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
+                                                OUT* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                 uint16_t* __restrict__ wcache, WarpStats& st, int lane, int snap_flags) {
     const GroupDesc g0 = s.groups[0];
-    return pack_app_impl<ALGO, true, true, false>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+    return pack_app_impl<ALGO, true, true, false, OUT>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
 }
 
 // class dispatch (warp-uniform): hot path = fast class with the gpu dimension idle
-template <int ALGO>
-__device__ __forceinline__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, int32_t* __restrict__ executor_nodes,
+template <int ALGO, class OUT>
+__device__ __forceinline__ int32_t pack_app(const Snapshot& s, const PrepApp* __restrict__ pa, OUT* __restrict__ executor_nodes,
                                             int2* __restrict__ scratch, uint16_t* __restrict__ wcache, WarpStats& st, int lane,
                                             int snap_flags, const GroupDesc& g0) {
     const uint32_t fl = pa->flags;
     const bool gpu_idle = !(fl & kAppUsesGpu) && !(snap_flags & kSnapGpuNegative);
     if ((fl & kAppFast32) && gpu_idle)     // hottest path: compact 32-bit snapshot view
-        return pack_app_impl<ALGO, true, true, true>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+        return pack_app_impl<ALGO, true, true, true, OUT>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
     if ((fl & kAppFast) && gpu_idle)
-        return pack_app_fast64<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
-    return pack_app_general<ALGO>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
+        return pack_app_fast64<ALGO, OUT>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
+    return pack_app_general<ALGO, OUT>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+// application preparation (validation bits, division recipes, driver-displacement bound, arithmetic class)
+// shared by gp_prep_apps (thread per application) and the fused pack kernels (lanes 0..2 of a warp, one dimension each)
+// ---------------------------------------------------------------------------------------------
+// One dimension: `bad` gets the validation bits, `l` the bound ceil(d/e) on the executors the driver displaces in this
+// dimension, `fast` is cleared when the dimension does not qualify for the 32-bit class.
+__device__ __forceinline__ DimDiv prep_dim(int64_t d, int64_t e, int t, long long max_avail, int& bad, uint64_t& l, bool& fast) {
+    if (d < 0 || e < 0) bad |= kErrNegativeRequest;
+    if (d >= kMaxQuantity || e >= kMaxQuantity) bad |= kErrUnrepresentable;
+    DimDiv dv;
+    dv.e = e; dv.magic = 0; dv.sh = 0; dv.kind = kDivInf;
+    l = 0;
+    if (e > 0) {
+        const uint32_t sh = (uint32_t)(__ffsll((long long)e) - 1);
+        const uint64_t odd = (uint64_t)e >> sh;
+        dv.sh = sh;
+        if (odd == 1 && sh >= 1) { dv.kind = kDivMagic; dv.magic = 1ull << 63; dv.sh = sh - 1; }   // a / 2^sh = (a >> (sh-1)) / 2
+        else if (odd == 1) dv.kind = kDivShift;                                                     // e == 1
+        else if ((odd >> 32) == 0) { dv.kind = kDivMagic; dv.magic = 0xFFFFFFFFFFFFFFFFull / odd + 1; }
+        else { dv.kind = kDivSlow; dv.sh = 0; }
+        if (d > 0) l = ((uint64_t)d + (uint64_t)e - 1) / (uint64_t)e;   // a driver of d displaces at most ceil(d/e) executors here
+    }
+    // fast class: the shifted numerator of every node fits 32 bits (SnapMeta::max_avail bounds it)
+    if (dv.kind == kDivSlow) fast = false;
+    else if (t < 2 && dv.kind != kDivMagic) fast = false;       // cpu / mem of the fast class are magic divisions only
+    else if (dv.kind != kDivInf) {
+        if (max_avail > 0 && (((unsigned long long)max_avail >> dv.sh) >> 32) != 0) fast = false;
+    }
+    return dv;
+}
+// compact 32-bit view usable: the request shifts are at least the view's shifts
+__device__ __forceinline__ bool prep_fast32(bool fast, const DimDiv& c, const DimDiv& m, const SnapMeta* meta) {
+    return fast && c.kind == kDivMagic && m.kind == kDivMagic && (int)c.sh >= meta->shift32[0] && (int)m.sh >= meta->shift32[1] &&
+           (int)c.sh - meta->shift32[0] < 32 && (int)m.sh - meta->shift32[1] < 32;   // 32-bit shift amounts
 }
 
 }  // namespace gp

@@ -15,7 +15,8 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("GANGPACK_LIB") or os.path.join(_PKG, "libgangpack.so")   # GANGPACK_LIB: experimental builds
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("gangpack_api.cu", "gangpack_kernels.cuh", "gangpack_fifo.cuh", "gangpack_minfrag.cuh", "gangpack_sort.cuh")] + [
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("gangpack_api.cu", "gangpack_kernels.cuh", "gangpack_fifo.cuh", "gangpack_minfrag.cuh",
+                                                    "gangpack_sort.cuh", "gangpack_tables.cuh", "gangpack_resched.cuh")] + [
     os.path.join(_ROOT, "include", "gangpack.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -33,7 +34,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 
 # every symbol include/gangpack.h declares (tests assert the .so exports exactly these)
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
-           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_one",
+           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
            "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors"]
 
@@ -80,6 +81,18 @@ class gp_apps(C.Structure):
                 ("skip_if_no_fit", C.c_void_p), ("exec_out_off", C.c_void_p)]
 
 
+class gp_apps_wire(C.Structure):
+    _fields_ = [("n_apps", C.c_int32), ("quantity_bits", C.c_int32), ("mem_shift", C.c_int32), ("reserved", C.c_int32),
+                ("drv_cpu", C.c_void_p), ("drv_mem", C.c_void_p), ("drv_gpu", C.c_void_p),
+                ("exe_cpu", C.c_void_p), ("exe_mem", C.c_void_p), ("exe_gpu", C.c_void_p),
+                ("exe_count", C.c_void_p), ("group", C.c_void_p), ("skip_if_no_fit", C.c_void_p), ("exec_out_off", C.c_void_p)]
+
+
+class gp_results_wire(C.Structure):
+    _fields_ = [("driver_node", C.c_void_p), ("executor_nodes", C.c_void_p), ("executor_nodes_cap", C.c_int64),
+                ("node_bits", C.c_int32), ("reserved", C.c_int32)]
+
+
 class gp_results(C.Structure):
     _fields_ = [("driver_node", C.c_void_p), ("executor_nodes", C.c_void_p), ("executor_nodes_cap", C.c_int64)]
 
@@ -107,7 +120,8 @@ class gp_reschedule(C.Structure):
 
 class gp_stats(C.Structure):
     _fields_ = [("nodes_scanned", C.c_int64), ("drivers_tried", C.c_int64), ("kernel_launches", C.c_int64),
-                ("pack_kernel_ns", C.c_int64), ("prep_kernel_ns", C.c_int64), ("reserved", C.c_int64 * 3)]
+                ("pack_kernel_ns", C.c_int64), ("prep_kernel_ns", C.c_int64), ("scan_path_apps", C.c_int64),
+                ("scan_path_nodes", C.c_int64), ("reserved", C.c_int64 * 1)]
 
 
 _lib = None
@@ -145,6 +159,8 @@ def load():
     L.gp_get_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_pack_batch.restype = C.c_int
     L.gp_pack_batch.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.c_int, C.POINTER(gp_results)]
+    L.gp_pack_batch_wire.restype = C.c_int
+    L.gp_pack_batch_wire.argtypes = [C.c_void_p, C.POINTER(gp_apps_wire), C.c_int, C.c_int, C.POINTER(gp_results_wire)]
     L.gp_pack_one.restype = C.c_int
     L.gp_pack_one.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 6 + [C.c_int32, C.POINTER(C.c_int32),
                                                                           C.POINTER(C.c_int32), C.c_void_p]
@@ -178,6 +194,25 @@ def _np(a, dtype):
 
 def _p(a):
     return None if a is None else a.ctypes.data
+
+
+def compact_apps(apps: dict, mem_shift: int = 20):
+    """What the shim does while marshalling: the 32-bit wire layout when every quantity is exactly representable
+    (memory a whole multiple of 2^mem_shift bytes, everything < 2^31), else None (use the int64 layout)."""
+    out = dict(apps)
+    for k in ("drv_cpu", "drv_gpu", "exe_cpu", "exe_gpu", "drv_mem", "exe_mem"):
+        v = apps.get(k)
+        if v is None:
+            continue
+        v = np.asarray(v, np.int64)
+        if k.endswith("mem"):
+            if (v & ((1 << mem_shift) - 1)).any():
+                return None
+            v = v >> mem_shift
+        if (v < 0).any() or (v >= (1 << 31)).any():
+            return None
+        out[k] = v.astype(np.int32)
+    return out
 
 
 class PinnedArray:
@@ -348,34 +383,52 @@ class GangPacker:
         return d[:nd.value].copy(), e[:ne.value].copy()
 
     # ---- packing -----------------------------------------------------------------------------
-    def pack_batch(self, apps: dict, algo: int, mode: int = MODE_INDEPENDENT, out=None):
+    def pack_batch(self, apps: dict, algo: int, mode: int = MODE_INDEPENDENT, out=None, wire=None):
         """apps: dict with drv_cpu, drv_mem, [drv_gpu], exe_cpu, exe_mem, [exe_gpu], count, [group], [young],
-        [off].  Returns (driver_node[q], executor_nodes[sum count], off[q+1])."""
+        [off].  Returns (driver_node[q], executor_nodes[sum count], off[q+1]).
+
+        wire=None: the int64 layout through gp_pack_batch.  wire=dict(quantity_bits=32|64, mem_shift=.., node_bits=16|32,
+        offsets=True|False) goes through gp_pack_batch_wire: with quantity_bits 32 the six quantity arrays of `apps` must
+        ALREADY be int32 in wire units (millicores, bytes >> mem_shift, gpu units -- see compact_apps()); offsets=False
+        passes exec_out_off = NULL (derived on the device)."""
         q = len(apps["count"])
         count = _np(apps["count"], np.int32)
         off = _np(apps.get("off"), np.int64)
         if off is None:
             off = np.zeros(q + 1, np.int64)
             np.cumsum(np.maximum(count, 0), out=off[1:])
+        bits = 64 if wire is None else int(wire.get("quantity_bits", 64))
+        qdt = np.int64 if bits == 64 else np.int32
         arrs = dict(
-            drv_cpu=_np(apps["drv_cpu"], np.int64), drv_mem=_np(apps["drv_mem"], np.int64),
-            drv_gpu=_np(apps.get("drv_gpu"), np.int64),
-            exe_cpu=_np(apps["exe_cpu"], np.int64), exe_mem=_np(apps["exe_mem"], np.int64),
-            exe_gpu=_np(apps.get("exe_gpu"), np.int64),
+            drv_cpu=_np(apps["drv_cpu"], qdt), drv_mem=_np(apps["drv_mem"], qdt),
+            drv_gpu=_np(apps.get("drv_gpu"), qdt),
+            exe_cpu=_np(apps["exe_cpu"], qdt), exe_mem=_np(apps["exe_mem"], qdt),
+            exe_gpu=_np(apps.get("exe_gpu"), qdt),
             group=_np(apps.get("group"), np.int32), young=_np(apps.get("young"), np.uint8))
         total = int(off[-1]) if q else 0
+        node_bits = 32 if wire is None else int(wire.get("node_bits", 32))
         if out is None:
             driver_node = np.full(q, -9, np.int32)
-            executor_nodes = np.full(max(total, 1), -9, np.int32)
+            executor_nodes = np.full(max(total, 1), -9 if node_bits == 32 else 65535, np.int32 if node_bits == 32 else np.uint16)
         else:
             driver_node, executor_nodes = out
-        a = gp_apps(n_apps=q, drv_cpu_milli=_p(arrs["drv_cpu"]), drv_mem_bytes=_p(arrs["drv_mem"]),
-                    drv_gpu=_p(arrs["drv_gpu"]), exe_cpu_milli=_p(arrs["exe_cpu"]), exe_mem_bytes=_p(arrs["exe_mem"]),
-                    exe_gpu=_p(arrs["exe_gpu"]), exe_count=_p(count), group=_p(arrs["group"]),
-                    skip_if_no_fit=_p(arrs["young"]), exec_out_off=_p(off))
-        r = gp_results(driver_node=_p(driver_node), executor_nodes=_p(executor_nodes),
-                       executor_nodes_cap=len(executor_nodes))
-        self._check(load().gp_pack_batch(self._h, C.byref(a), algo, mode, C.byref(r)))
+        if wire is None:
+            a = gp_apps(n_apps=q, drv_cpu_milli=_p(arrs["drv_cpu"]), drv_mem_bytes=_p(arrs["drv_mem"]),
+                        drv_gpu=_p(arrs["drv_gpu"]), exe_cpu_milli=_p(arrs["exe_cpu"]), exe_mem_bytes=_p(arrs["exe_mem"]),
+                        exe_gpu=_p(arrs["exe_gpu"]), exe_count=_p(count), group=_p(arrs["group"]),
+                        skip_if_no_fit=_p(arrs["young"]), exec_out_off=_p(off))
+            r = gp_results(driver_node=_p(driver_node), executor_nodes=_p(executor_nodes),
+                           executor_nodes_cap=len(executor_nodes))
+            self._check(load().gp_pack_batch(self._h, C.byref(a), algo, mode, C.byref(r)))
+        else:
+            a = gp_apps_wire(n_apps=q, quantity_bits=bits, mem_shift=int(wire.get("mem_shift", 0)),
+                             drv_cpu=_p(arrs["drv_cpu"]), drv_mem=_p(arrs["drv_mem"]), drv_gpu=_p(arrs["drv_gpu"]),
+                             exe_cpu=_p(arrs["exe_cpu"]), exe_mem=_p(arrs["exe_mem"]), exe_gpu=_p(arrs["exe_gpu"]),
+                             exe_count=_p(count), group=_p(arrs["group"]), skip_if_no_fit=_p(arrs["young"]),
+                             exec_out_off=_p(off) if wire.get("offsets", True) else None)
+            r = gp_results_wire(driver_node=_p(driver_node), executor_nodes=_p(executor_nodes),
+                                executor_nodes_cap=len(executor_nodes), node_bits=node_bits)
+            self._check(load().gp_pack_batch_wire(self._h, C.byref(a), algo, mode, C.byref(r)))
         return driver_node, executor_nodes[:total], off
 
     def pack_one(self, algo, drv, exe, count):
@@ -390,7 +443,8 @@ class GangPacker:
         s = gp_stats()
         self._check(load().gp_last_stats(self._h, C.byref(s)))
         return {"nodes_scanned": s.nodes_scanned, "drivers_tried": s.drivers_tried, "kernel_launches": s.kernel_launches,
-                "pack_kernel_ns": s.pack_kernel_ns, "prep_kernel_ns": s.prep_kernel_ns}
+                "pack_kernel_ns": s.pack_kernel_ns, "prep_kernel_ns": s.prep_kernel_ns,
+                "scan_path_apps": s.scan_path_apps, "scan_path_nodes": s.scan_path_nodes}
 
     # ---- device-resident (torch tensors on this context's device) ----------------------------
     def stream_handle(self) -> int:

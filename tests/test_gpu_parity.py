@@ -277,9 +277,9 @@ def test_pinned_host_paths(oracle, packer):
 
 
 def test_pinned_host_paths_dma_route():
-    """Same test with in-place reads disabled, so the pinned buffers take the (2-D) DMA staging route."""
+    """Same test with mapped-memory access disabled: every buffer takes the (2-D) DMA staging route."""
     import os, subprocess, sys
-    env = dict(os.environ, GANGPACK_ZC_IN_MAX="0")
+    env = dict(os.environ, GANGPACK_ZERO_COPY="0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                         "-k", "test_pinned_host_paths and not dma_route"], env=env, capture_output=True, text=True, timeout=300)

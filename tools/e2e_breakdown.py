@@ -48,6 +48,23 @@ print("build_availability (10k nodes, 200k reservations) %8.1f us" % t(lambda: p
 print("prepare_cluster (availability + sort + layout, chained) %8.1f us" % t(lambda: p.prepare_cluster(_alloc, None, _rnode, _res)))
 print("set_snapshot        %8.1f us" % t(snap))
 print("pack_batch (pinned) %8.1f us" % t(pack), p.stats())
+# compact wire format: int32 millicores / MiB, no offsets, uint16 node indices
+if w["mode"] == 0 and w["algo"] != 2:
+    c32 = g.native.compact_apps({k: a[k] for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}, 20)
+    cols = [k for k in ("drv_cpu", "drv_mem", "exe_cpu", "exe_mem", "drv_gpu", "exe_gpu") if a[k].any()]
+    pc = p.pinned_columns(q, cols, dtype=np.int32)
+    for k in cols: pc[k][:] = c32[k]
+    pc["count"] = pin["count"]
+    oe16 = p.pinned(max(total, 1), np.uint16)
+    wire = dict(quantity_bits=32, mem_shift=20, node_bits=16, offsets=False)
+    print("pack_batch_wire (int32 in, no offsets, uint16 out) %8.1f us" % t(lambda: p.pack_batch(pc, w["algo"], w["mode"], out=(od, oe16), wire=wire)), p.stats())
+    for chunk in (8192, 16384, 65536):
+        os.environ["GANGPACK_CHUNK_APPS"] = str(chunk)
+        p2 = g.GangPacker(0)
+        p2.set_snapshot(pn["cpu"], pn["mem"], pn["gpu"], pn["eorder"], pn["eorder"], pn["eoff"], pn["eoff"])
+        print("   chunk_apps %6d: %8.1f us" % (chunk, t(lambda: p2.pack_batch(pc, w["algo"], w["mode"], out=(od, oe16), wire=wire))))
+        p2.close()
+    os.environ.pop("GANGPACK_CHUNK_APPS", None)
 pageable = {k: np.array(v) for k, v in pin.items()}
 print("pack_batch (pageable in, pinned out) %8.1f us" % t(lambda: p.pack_batch(pageable, w["algo"], w["mode"], out=(od, oe))))
 # raw PCIe
