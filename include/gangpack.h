@@ -306,6 +306,30 @@ gp_status gp_pack_batch_device(gp_ctx* ctx, const gp_apps* dev_apps, gp_algo alg
 void* gp_stream(gp_ctx* ctx);
 gp_status gp_synchronize(gp_ctx* ctx);
 
+/* ---- several GPUs of one box behind ONE host process -----------------------------------------------
+ * The reference is a single process with a serial Predicate (internal/extender/resource.go:194-205); this handle lets
+ * that process use every GPU: one gp_ctx + one worker thread per entry of `devices` (an ordinal may repeat).
+ *   gp_multi_set_snapshot   every device receives the full snapshot by a direct H2D copy over its own PCIe link.
+ *   gp_multi_pack_batch     GP_MODE_INDEPENDENT: the queue is cut into one contiguous block per device and every device
+ *                           copies ITS placements straight into the caller's result buffers (no gather through one GPU,
+ *                           no collective: the path has no exchange step).  FIFO modes: whole instance groups per device
+ *                           (queues of different groups are independent: internal/extender/sparkpods.go:61,
+ *                           resource.go:292-295; longest-processing-time first on applications x nodes), results are
+ *                           scattered back into queue order; exec_out_off is mandatory and node_bits must be 32 there.
+ *                           Results are bit-identical to gp_pack_batch_wire on one context.
+ *   gp_multi_get_snapshot   after a FIFO batch: every node from the device that owned its instance group.
+ *   gp_multi_group_owner    which device ran each instance group's queue in the last FIFO batch. */
+typedef struct gp_multi gp_multi;
+gp_status gp_multi_create(gp_multi** out, const int32_t* devices /* NULL = 0..n-1 */, int32_t n_devices);
+void gp_multi_destroy(gp_multi* m);
+const char* gp_multi_last_error(const gp_multi* m);
+int32_t gp_multi_size(const gp_multi* m);
+gp_ctx* gp_multi_ctx(gp_multi* m, int32_t i);      /* the i-th context, e.g. for gp_alloc_pinned / gp_last_stats */
+gp_status gp_multi_set_snapshot(gp_multi* m, const gp_nodes* nodes);
+gp_status gp_multi_pack_batch(gp_multi* m, const gp_apps_wire* apps, gp_algo algo, gp_mode mode, gp_results_wire* out);
+gp_status gp_multi_get_snapshot(gp_multi* m, int64_t* avail_cpu_milli, int64_t* avail_mem_bytes, int64_t* avail_gpu);
+gp_status gp_multi_group_owner(gp_multi* m, int32_t* owner /* [n_groups] */);
+
 /* Statistics of the last gp_pack_batch* on this context (host call, synchronises the stream):
  * nodes_scanned = executor-order entries visited, drivers_tried = driver-order entries visited,
  * summed over apps -- the N_e / N_d of the algorithmic-bytes formula. */

@@ -10,7 +10,7 @@ Layout:
 """
 from . import native, synth  # noqa: F401
 from .native import (DISTRIBUTE_EVENLY, MINIMAL_FRAGMENTATION, MODE_FIFO_EXACT, MODE_FIFO_REFERENCE, MODE_INDEPENDENT,  # noqa: F401
-                     TIGHTLY_PACK, GangPacker, GangpackError)
+                     TIGHTLY_PACK, GangPacker, GangpackError, MultiGangPacker)
 
-__all__ = ["native", "synth", "GangPacker", "GangpackError", "TIGHTLY_PACK", "DISTRIBUTE_EVENLY", "MINIMAL_FRAGMENTATION",
+__all__ = ["native", "synth", "GangPacker", "MultiGangPacker", "GangpackError", "TIGHTLY_PACK", "DISTRIBUTE_EVENLY", "MINIMAL_FRAGMENTATION",
            "MODE_INDEPENDENT", "MODE_FIFO_REFERENCE", "MODE_FIFO_EXACT"]

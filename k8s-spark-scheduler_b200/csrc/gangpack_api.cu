@@ -481,7 +481,7 @@ void gp_destroy(gp_ctx* c) {
 gp_status gp_alloc_pinned(gp_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return GP_ERR_INVALID;
     GP_CUDA(ctx, cudaSetDevice(ctx->device));
-    GP_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    GP_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));   // pinned for every device of the process (gp_multi)
     ctx->pinned_blocks.emplace_back(static_cast<const char*>(*out), bytes ? bytes : 1);
     return GP_OK;
 }

@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("GANGPACK_LIB") or os.path.join(_PKG, "libgangpack.so")   # GANGPACK_LIB: experimental builds
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("gangpack_api.cu", "gangpack_kernels.cuh", "gangpack_fifo.cuh", "gangpack_minfrag.cuh",
-                                                    "gangpack_sort.cuh", "gangpack_tables.cuh", "gangpack_resched.cuh")] + [
+                                                    "gangpack_sort.cuh", "gangpack_tables.cuh", "gangpack_resched.cuh", "gangpack_multi.cu")] + [
     os.path.join(_ROOT, "include", "gangpack.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -36,7 +36,9 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
            "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
-           "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors"]
+           "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors",
+           "gp_multi_create", "gp_multi_destroy", "gp_multi_last_error", "gp_multi_size", "gp_multi_ctx",
+           "gp_multi_set_snapshot", "gp_multi_pack_batch", "gp_multi_get_snapshot", "gp_multi_group_owner"]
 
 
 class GangpackError(RuntimeError):
@@ -57,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in _SOURCES)
     if stale:
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, _SOURCES[0]]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, _SOURCES[0],
+                                        os.path.join(_PKG, "csrc", "gangpack_multi.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)
@@ -184,6 +187,24 @@ def load():
                                      C.c_void_p, C.POINTER(C.c_int32)]
     L.gp_reschedule_executors.restype = C.c_int
     L.gp_reschedule_executors.argtypes = [C.c_void_p, C.POINTER(gp_reschedule), C.c_void_p]
+    L.gp_multi_create.restype = C.c_int
+    L.gp_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32]
+    L.gp_multi_destroy.restype = None
+    L.gp_multi_destroy.argtypes = [C.c_void_p]
+    L.gp_multi_last_error.restype = C.c_char_p
+    L.gp_multi_last_error.argtypes = [C.c_void_p]
+    L.gp_multi_size.restype = C.c_int32
+    L.gp_multi_size.argtypes = [C.c_void_p]
+    L.gp_multi_ctx.restype = C.c_void_p
+    L.gp_multi_ctx.argtypes = [C.c_void_p, C.c_int32]
+    L.gp_multi_set_snapshot.restype = C.c_int
+    L.gp_multi_set_snapshot.argtypes = [C.c_void_p, C.POINTER(gp_nodes)]
+    L.gp_multi_pack_batch.restype = C.c_int
+    L.gp_multi_pack_batch.argtypes = [C.c_void_p, C.POINTER(gp_apps_wire), C.c_int, C.c_int, C.POINTER(gp_results_wire)]
+    L.gp_multi_get_snapshot.restype = C.c_int
+    L.gp_multi_get_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gp_multi_group_owner.restype = C.c_int
+    L.gp_multi_group_owner.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -476,3 +497,99 @@ class GangPacker:
         r = gp_results(driver_node=driver_node.data_ptr(), executor_nodes=executor_nodes.data_ptr(),
                        executor_nodes_cap=executor_nodes.numel())
         self._check(load().gp_pack_batch_device(self._h, C.byref(a), algo, mode, C.byref(r), stream or None))
+
+
+class MultiGangPacker:
+    """gp_multi: one host process, several GPUs (or several contexts on one GPU).  Same call shapes as GangPacker."""
+
+    def __init__(self, devices):
+        L = load()
+        self._h = C.c_void_p()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        st = L.gp_multi_create(C.byref(self._h), dev.ctypes.data, len(dev))
+        if st != 0:
+            raise GangpackError(st, (L.gp_last_error(None) or b"").decode())
+        self.n_devices = len(dev)
+        self._pinned = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for ctx, ptr in self._pinned:
+                load().gp_free_pinned(ctx, ptr)
+            self._pinned = []
+            load().gp_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != 0:
+            raise GangpackError(st, (load().gp_multi_last_error(self._h) or b"").decode())
+
+    def pinned(self, shape, dtype) -> np.ndarray:
+        """Pinned host memory (portable: usable by every device of the handle)."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        nbytes = max(n * dt.itemsize, 1)
+        ptr = C.c_void_p()
+        ctx = load().gp_multi_ctx(self._h, 0)
+        st = load().gp_alloc_pinned(ctx, nbytes, C.byref(ptr))
+        if st != 0:
+            raise GangpackError(st, (load().gp_last_error(ctx) or b"").decode())
+        self._pinned.append((ctx, ptr))
+        buf = (C.c_char * nbytes).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+    def set_snapshot(self, avail_cpu, avail_mem, avail_gpu, exec_order, drv_order, exec_off=None, drv_off=None):
+        cpu, mem, gpu = _np(avail_cpu, np.int64), _np(avail_mem, np.int64), _np(avail_gpu, np.int64)
+        eo, do = _np(exec_order, np.int32), _np(drv_order, np.int32)
+        eoff = _np(exec_off if exec_off is not None else [0, len(eo)], np.int32)
+        doff = _np(drv_off if drv_off is not None else [0, len(do)], np.int32)
+        n = gp_nodes(n_nodes=len(cpu), avail_cpu_milli=_p(cpu), avail_mem_bytes=_p(mem), avail_gpu=_p(gpu),
+                     n_groups=len(eoff) - 1, exec_off=_p(eoff), exec_order=_p(eo), drv_off=_p(doff), drv_order=_p(do))
+        self._check(load().gp_multi_set_snapshot(self._h, C.byref(n)))
+        self.n_nodes, self.n_groups = len(cpu), len(eoff) - 1
+
+    def get_snapshot(self):
+        cpu = np.empty(self.n_nodes, np.int64); mem = np.empty(self.n_nodes, np.int64); gpu = np.empty(self.n_nodes, np.int64)
+        self._check(load().gp_multi_get_snapshot(self._h, _p(cpu), _p(mem), _p(gpu)))
+        return cpu, mem, gpu
+
+    def group_owner(self):
+        o = np.empty(self.n_groups, np.int32)
+        self._check(load().gp_multi_group_owner(self._h, _p(o)))
+        return o
+
+    def pack_batch(self, apps: dict, algo: int, mode: int = MODE_INDEPENDENT, out=None, wire=None):
+        """Same contract as GangPacker.pack_batch (wire=None -> int64 quantities, offsets given, int32 node indices)."""
+        wire = dict(wire or dict(quantity_bits=64, node_bits=32, offsets=True))
+        q = len(apps["count"])
+        count = _np(apps["count"], np.int32)
+        off = _np(apps.get("off"), np.int64)
+        if off is None:
+            off = np.zeros(q + 1, np.int64)
+            np.cumsum(np.maximum(count, 0), out=off[1:])
+        bits = int(wire.get("quantity_bits", 64))
+        qdt = np.int64 if bits == 64 else np.int32
+        arrs = {k: _np(apps.get(k), qdt) for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}
+        grp, young = _np(apps.get("group"), np.int32), _np(apps.get("young"), np.uint8)
+        total = int(off[-1]) if q else 0
+        node_bits = int(wire.get("node_bits", 32))
+        if out is None:
+            driver_node = np.full(q, -9, np.int32)
+            executor_nodes = np.full(max(total, 1), -9 if node_bits == 32 else 65535, np.int32 if node_bits == 32 else np.uint16)
+        else:
+            driver_node, executor_nodes = out
+        a = gp_apps_wire(n_apps=q, quantity_bits=bits, mem_shift=int(wire.get("mem_shift", 0)),
+                         drv_cpu=_p(arrs["drv_cpu"]), drv_mem=_p(arrs["drv_mem"]), drv_gpu=_p(arrs["drv_gpu"]),
+                         exe_cpu=_p(arrs["exe_cpu"]), exe_mem=_p(arrs["exe_mem"]), exe_gpu=_p(arrs["exe_gpu"]),
+                         exe_count=_p(count), group=_p(grp), skip_if_no_fit=_p(young),
+                         exec_out_off=_p(off) if wire.get("offsets", True) else None)
+        r = gp_results_wire(driver_node=_p(driver_node), executor_nodes=_p(executor_nodes),
+                            executor_nodes_cap=len(executor_nodes), node_bits=node_bits)
+        self._check(load().gp_multi_pack_batch(self._h, C.byref(a), algo, mode, C.byref(r)))
+        return driver_node, executor_nodes[:total], off
