@@ -199,6 +199,13 @@ typedef struct {
     const uint8_t* ready;                /* [n_nodes] NodeReady == True, or NULL (= all) */
     const int32_t* driver_label_rank;    /* [n_nodes] rank of the node's value of driver-prioritized-node-label, -1 unknown; NULL = not configured */
     const int32_t* executor_label_rank;  /* same for executor-prioritized-node-label */
+    const int64_t* avail_gpu;            /* [n_nodes] or NULL: only used to DETECT the ties below (gp_prepare_cluster: taken from the
+                                            availability it computes) */
+    int32_t* undefined_ties;             /* out, or NULL: number of adjacent pairs of the node order whose relative order the
+                                            reference's comparator leaves undefined -- same zone priority, memory and cpu but
+                                            different gpu (scheduleContextLessThan, nodesorting.go:83-93, is then "not less" both
+                                            ways and sort.Slice is unstable).  Non-zero: this library ordered them
+                                            by name; a shim that wants the reference's own (unspecified) choice falls back to Go */
 } gp_sort_input;
 gp_status gp_potential_nodes(gp_ctx* ctx, const gp_sort_input* in,
                              int32_t* driver_order /* [n_nodes] */, int32_t* n_driver,

@@ -347,6 +347,8 @@ struct gp_ctx {
     // per pipeline lane: shape hash + header, capacity tables, group totals, per-application shape slot
     struct TableSet { DevBuf hdr, table, total, app_slot; } tabs[kLanes];
     DevBuf off_dev;                               // ExecutorNodes offsets derived on the device
+    DevBuf fifo_list;                             // FIFO modes: per-instance-group application lists (queue order)
+    bool sort_attr_set = false;
     bool fifo_attr_set[2] = {false, false};       // dynamic shared-memory opt-in of gp_pack_fifo_cta<ALGO,*> done on this device
 
     gp_stats last{};
@@ -465,7 +467,7 @@ void gp_destroy(gp_ctx* c) {
                       &c->pair, &c->pair32, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
                       &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf, &c->reschedbuf,
-                      &c->off_dev};
+                      &c->off_dev, &c->fifo_list};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : c->tabs) { t.hdr.release(); t.table.release(); t.total.release(); t.app_slot.release(); }
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
@@ -720,7 +722,7 @@ static AppColumns cols_at(const AppColumns& c, int32_t lo) {
 }
 
 template <int ALGO>
-static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepApp* prep, int32_t n_apps,
+static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepApp* prep, const int32_t* app_group, int32_t n_apps,
                         int32_t* driver_node, int32_t* executor_nodes, int2* scratch, unsigned long long* stats,
                         unsigned int* next_app, cudaStream_t st) {
     if (mode == GP_MODE_INDEPENDENT) {
@@ -747,10 +749,12 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
         // small groups: fewer threads per CTA (the per-application fixed cost scales with the CTA size)
         const int avg_ne = c->n_groups > 0 ? c->n_exec / c->n_groups : 0;
         const int kFifoThreadsRt = avg_ne <= 1536 ? 256 : (avg_ne <= 4096 ? 512 : kFifoThreads);
+        int32_t* app_list = c->fifo_list.as<int32_t>();
+        unsigned int* cursor = reinterpret_cast<unsigned int*>(c->dev_misc.as<char>() + 56);     // zeroed by pack_begin
         if (mode == GP_MODE_FIFO_REFERENCE)
-            gp_pack_fifo_cta<ALGO, 1><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins);
+            gp_pack_fifo_cta<ALGO, 1><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, app_group, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins, app_list, cursor);
         else
-            gp_pack_fifo_cta<ALGO, 2><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins);
+            gp_pack_fifo_cta<ALGO, 2><<<s.n_groups, kFifoThreadsRt, kFifoSmemBytes, st>>>(s, prep, app_group, n_apps, driver_node, executor_nodes, scratch, stats, s.gmins, app_list, cursor);
         // the FIFO kernels subtract usage from `pair` in place: refresh the compact 32-bit view so that a later
         // independent pack on this context (the driver's own pack after fitEarlierDrivers, resource.go:255 then :321)
         // sees the charged availability
@@ -847,6 +851,7 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
     PrepApp* prep = c->prep.as<PrepApp>() + lo;
     const int T = kPrepThreads;
     if (mode != GP_MODE_INDEPENDENT) {
+        GP_CUDA(c, c->fifo_list.reserve(sizeof(int32_t) * (size_t)(q + 1)));
         GP_CUDA(c, c->gmin.reserve(sizeof(GroupMin) * (size_t)c->n_groups));
         GP_CUDA(c, cudaMemsetAsync(c->gmin.p, 0x7f, sizeof(GroupMin) * (size_t)c->n_groups, st));   // +inf-ish
     }
@@ -858,11 +863,11 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
     int32_t* exec32 = static_cast<int32_t*>(dr.exec);
     if (algo == GP_TIGHTLY_PACK)
-        launch_pack<0>(c, mode, s, prep, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
+        launch_pack<0>(c, mode, s, prep, cols.group, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
     else if (algo == GP_MINIMAL_FRAGMENTATION)
-        launch_pack<2>(c, mode, s, prep, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
+        launch_pack<2>(c, mode, s, prep, cols.group, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
     else
-        launch_pack<1>(c, mode, s, prep, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
+        launch_pack<1>(c, mode, s, prep, cols.group, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
     GP_CUDA(c, cudaGetLastError());
     GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
     c->last.kernel_launches += 2;
@@ -1253,28 +1258,31 @@ static gp_status stage_availability(gp_ctx* c, const gp_usage_input* in, cudaStr
 
 struct SortStage { const int32_t* drv; const int32_t* exe; const int32_t* counts; };
 
-// f1 stage: d_cpu / d_mem are device arrays (NULL: uploaded from `in`); leaves the two orders and their lengths on the device.
-static gp_status stage_sort(gp_ctx* c, const gp_sort_input* in, const long long* d_cpu, const long long* d_mem, cudaStream_t st,
-                            SortStage* out) {
+// f1 stage: d_cpu / d_mem / d_gpu are device arrays (NULL: uploaded from `in`; gpu optional); leaves the two orders and
+// counts[3] = {#driver candidates, #executor candidates, #undefined ties} on the device.
+static gp_status stage_sort(gp_ctx* c, const gp_sort_input* in, const long long* d_cpu, const long long* d_mem, const long long* d_gpu,
+                            cudaStream_t st, SortStage* out) {
     const int32_t n = in->n_nodes;
     // cheap host validation of the two id arrays the kernels index with
     if (in->zone_id) for (int32_t i = 0; i < n; ++i)
         if (in->zone_id[i] < 0 || in->zone_id[i] >= in->n_zones) return fail(c, GP_ERR_INVALID, "gp_potential_nodes: zone_id out of range");
     if (in->name_rank) for (int32_t i = 0; i < n; ++i)
         if (in->name_rank[i] < 0 || in->name_rank[i] >= n) return fail(c, GP_ERR_INVALID, "gp_potential_nodes: name_rank out of range");
-    // one scratch block: [cpu i64][mem i64][keys][tot u64 x 2Z][zone][nrank][prio Z][pos][order][drv][exe][drv2][exe2][lr_d][lr_e][counts 2][flags 3n]
+    // one scratch block
     const size_t N = (size_t)n, Z = (size_t)in->n_zones;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_cpu = take(8 * N), o_mem = take(8 * N), o_keys = take(sizeof(SortKey) * N), o_tot = take(16 * Z),
-                 o_zone = take(4 * N), o_nr = take(4 * N), o_prio = take(4 * Z), o_pos = take(4 * N), o_order = take(4 * N),
+    const size_t o_cpu = take(8 * N), o_mem = take(8 * N), o_gpu = take(8 * N), o_keys = take(sizeof(SortKey) * N), o_sorted = take(sizeof(SortKey) * N),
+                 o_tot = take(16 * Z), o_zone = take(4 * N), o_nr = take(4 * N), o_prio = take(4 * Z), o_pos = take(4 * N), o_order = take(4 * N),
                  o_drv = take(4 * N), o_exe = take(4 * N), o_drv2 = take(4 * N), o_exe2 = take(4 * N), o_lrd = take(4 * N),
-                 o_lre = take(4 * N), o_cnt = take(8), o_fc = take(N), o_fu = take(N), o_fr = take(N);
+                 o_lre = take(4 * N), o_lk = take(sizeof(LabelKey) * N), o_lks = take(sizeof(LabelKey) * N), o_cnt = take(16),
+                 o_fc = take(N), o_fu = take(N), o_fr = take(N);
     GP_CUDA(c, c->sortbuf.reserve(off));
     char* b = c->sortbuf.as<char>();
     auto up = [&](size_t o, const void* src, size_t bytes) { return cudaMemcpyAsync(b + o, src, bytes, cudaMemcpyHostToDevice, st); };
     if (!d_cpu) { GP_CUDA(c, up(o_cpu, in->avail_cpu_milli, 8 * N)); d_cpu = (const long long*)(b + o_cpu); }
     if (!d_mem) { GP_CUDA(c, up(o_mem, in->avail_mem_bytes, 8 * N)); d_mem = (const long long*)(b + o_mem); }
+    if (!d_gpu && in->avail_gpu) { GP_CUDA(c, up(o_gpu, in->avail_gpu, 8 * N)); d_gpu = (const long long*)(b + o_gpu); }
     if (in->zone_id) GP_CUDA(c, up(o_zone, in->zone_id, 4 * N)); else GP_CUDA(c, cudaMemsetAsync(b + o_zone, 0, 4 * N, st));
     if (in->name_rank) GP_CUDA(c, up(o_nr, in->name_rank, 4 * N));
     else { c->iota.resize(N); for (int32_t i = 0; i < n; ++i) c->iota[(size_t)i] = i; GP_CUDA(c, up(o_nr, c->iota.data(), 4 * N)); }
@@ -1284,28 +1292,39 @@ static gp_status stage_sort(gp_ctx* c, const gp_sort_input* in, const long long*
     if (in->driver_label_rank) GP_CUDA(c, up(o_lrd, in->driver_label_rank, 4 * N));
     if (in->executor_label_rank) GP_CUDA(c, up(o_lre, in->executor_label_rank, 4 * N));
     GP_CUDA(c, cudaMemsetAsync(b + o_tot, 0, 16 * Z, st));
+    if (!c->sort_attr_set) {
+        GP_CUDA(c, cudaFuncSetAttribute(gp_sort_tiles<SortKey>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortTile * sizeof(SortKey))));
+        c->sort_attr_set = true;
+    }
     const int T = 256;
     const int nb = (n + T - 1) / T;
+    const int ntile = (n + kSortTile - 1) / kSortTile;
+    SortKey* keys = (SortKey*)(b + o_keys);
+    SortKey* sorted = (SortKey*)(b + o_sorted);
+    int32_t* pos = (int32_t*)(b + o_pos);
     gp_zone_totals<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (unsigned long long*)(b + o_tot));
     gp_zone_priority<<<(in->n_zones + T - 1) / T, T, 0, st>>>(in->n_zones, (const unsigned long long*)(b + o_tot), (int32_t*)(b + o_prio));
-    gp_make_keys<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (const int32_t*)(b + o_prio), (const int32_t*)(b + o_nr),
-                                   (SortKey*)(b + o_keys), (int32_t*)(b + o_pos));
-    gp_rank_nodes<<<dim3((unsigned)nb, (unsigned)((n + kTileJ - 1) / kTileJ)), T, 0, st>>>(n, (const SortKey*)(b + o_keys), (int32_t*)(b + o_pos));
-    gp_scatter_order<<<nb, T, 0, st>>>(n, (const int32_t*)(b + o_pos), (int32_t*)(b + o_order));
+    gp_make_keys<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (const int32_t*)(b + o_prio), (const int32_t*)(b + o_nr), keys);
+    gp_sort_tiles<SortKey><<<ntile, kSortThreads, kSortTile * sizeof(SortKey), st>>>(n, nullptr, keys, sorted);
+    gp_rank_by_search<SortKey><<<nb, T, 0, st>>>(n, nullptr, keys, sorted, pos);
+    gp_scatter_order<<<nb, T, 0, st>>>(n, pos, (int32_t*)(b + o_order));
     gp_split_candidates<<<1, 1024, 0, st>>>(n, (const int32_t*)(b + o_order), in->is_driver_candidate ? (const uint8_t*)(b + o_fc) : nullptr,
                                            in->unschedulable ? (const uint8_t*)(b + o_fu) : nullptr, in->ready ? (const uint8_t*)(b + o_fr) : nullptr,
-                                           (int32_t*)(b + o_drv), (int32_t*)(b + o_exe), (int32_t*)(b + o_cnt));
+                                           keys, d_gpu, (int32_t*)(b + o_drv), (int32_t*)(b + o_exe), (int32_t*)(b + o_cnt));
     out->drv = (const int32_t*)(b + o_drv);
     out->exe = (const int32_t*)(b + o_exe);
     out->counts = (const int32_t*)(b + o_cnt);
-    if (in->driver_label_rank) {
-        gp_label_sort<<<nb, T, 0, st>>>(out->counts, out->drv, (const int32_t*)(b + o_lrd), (int32_t*)(b + o_drv2));
-        out->drv = (const int32_t*)(b + o_drv2);
-    }
-    if (in->executor_label_rank) {
-        gp_label_sort<<<nb, T, 0, st>>>(out->counts + 1, out->exe, (const int32_t*)(b + o_lre), (int32_t*)(b + o_exe2));
-        out->exe = (const int32_t*)(b + o_exe2);
-    }
+    auto label_sort = [&](const int32_t* cnt, const int32_t* list, size_t o_rank, size_t o_out) {
+        LabelKey* lk = (LabelKey*)(b + o_lk);
+        LabelKey* lks = (LabelKey*)(b + o_lks);
+        gp_label_keys<<<nb, T, 0, st>>>(cnt, list, (const int32_t*)(b + o_rank), lk);
+        gp_sort_tiles<LabelKey><<<ntile, kSortThreads, kSortTile * sizeof(LabelKey), st>>>(n, cnt, lk, lks);
+        gp_rank_by_search<LabelKey><<<nb, T, 0, st>>>(n, cnt, lk, lks, pos);
+        gp_label_scatter<<<nb, T, 0, st>>>(cnt, list, pos, (int32_t*)(b + o_out));
+        return (const int32_t*)(b + o_out);
+    };
+    if (in->driver_label_rank) out->drv = label_sort(out->counts, out->drv, o_lrd, o_drv2);
+    if (in->executor_label_rank) out->exe = label_sort(out->counts + 1, out->exe, o_lre, o_exe2);
     GP_CUDA(c, cudaGetLastError());
     return GP_OK;
 }
@@ -1329,15 +1348,16 @@ gp_status gp_potential_nodes(gp_ctx* c, const gp_sort_input* in, int32_t* driver
     GP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     SortStage so{};
-    gp_status s = stage_sort(c, in, nullptr, nullptr, st, &so);
+    gp_status s = stage_sort(c, in, nullptr, nullptr, nullptr, st, &so);
     if (s != GP_OK) return s;
-    int32_t counts[2] = {0, 0};
-    GP_CUDA(c, cudaMemcpyAsync(counts, so.counts, 8, cudaMemcpyDeviceToHost, st));
+    int32_t counts[3] = {0, 0, 0};
+    GP_CUDA(c, cudaMemcpyAsync(counts, so.counts, 12, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaMemcpyAsync(driver_order, so.drv, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaMemcpyAsync(executor_order, so.exe, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaStreamSynchronize(st));
     *n_driver = counts[0];
     *n_executor = counts[1];
+    if (in->undefined_ties) *in->undefined_ties = counts[2];
     return GP_OK;
 }
 
@@ -1380,7 +1400,7 @@ gp_status gp_prepare_cluster(gp_ctx* c, const gp_usage_input* usage, const gp_so
     if (s != GP_OK) return s;
     const size_t N = (size_t)n;
     SortStage so{};
-    s = stage_sort(c, sort, d_avail, d_avail + N, st, &so);
+    s = stage_sort(c, sort, d_avail, d_avail + N, d_avail + 2 * N, st, &so);
     if (s != GP_OK) return s;
     // node-table copy (gp_get_snapshot) and the one-group offsets, then the usual slot layout with N as the upper bound
     const size_t nb = sizeof(int64_t) * (N + 1);
@@ -1398,10 +1418,11 @@ gp_status gp_prepare_cluster(gp_ctx* c, const gp_usage_input* usage, const gp_so
     dn.drv_off = c->drv_off.as<int32_t>(); dn.drv_order = so.drv;
     s = build_snapshot_device(c, &dn, n, n, st);      // n is the upper bound of both order lengths
     if (s != GP_OK) return s;
-    int32_t counts[2] = {0, 0};
-    GP_CUDA(c, cudaMemcpyAsync(counts, so.counts, 8, cudaMemcpyDeviceToHost, st));
+    int32_t counts[3] = {0, 0, 0};
+    GP_CUDA(c, cudaMemcpyAsync(counts, so.counts, 12, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaStreamSynchronize(st));
     c->n_drv = counts[0]; c->n_exec = counts[1];
+    if (sort->undefined_ties) *sort->undefined_ties = counts[2];
     if (n_driver) *n_driver = counts[0];
     if (n_executor) *n_executor = counts[1];
     return GP_OK;

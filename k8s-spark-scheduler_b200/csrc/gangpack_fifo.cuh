@@ -2,7 +2,12 @@
 //
 // The loop is a true sequential dependency inside one instance group (application i+1 sees the
 // usage application i subtracted), so parallelism comes from WITHIN an application and ACROSS
-// instance groups: one persistent CTA (1024 threads) owns one group's queue.
+// instance groups: one persistent CTA owns one group's queue.
+//   * WARP FIRST: the typical application resolves inside the first few hundred live nodes, so warp 0 walks the queue
+//     alone -- first fitting driver, 32 nodes per step from the live prefix, warp scan, emit, charge -- without a single
+//     block-wide barrier.  The other warps sleep on a named hardware barrier (bar.sync 1) and are woken only when an
+//     application outgrows the warp's window budget or needs the exact three-phase decision: then the whole CTA runs
+//     fifo_app() below (1024 nodes per step).
 //   * the group's executor-order slots (16 B (cpu,mem) records) are staged into shared memory with
 //     TMA bulk copies (cp.async.bulk + mbarrier) and written back with a bulk store at the end, so the
 //     block-serial commit of reservations never leaves the SM;
@@ -16,7 +21,7 @@
 
 namespace gp {
 
-constexpr int kFifoThreads = 1024;
+constexpr int kFifoThreads = 512;
 constexpr int kFifoWarps = kFifoThreads / 32;
 constexpr int kFifoSmemSlots = 11776;          // 184 KB of (cpu,mem) records
 constexpr int kFifoCache = 12288;              // uint16 capacity cache entries (24 KB)
@@ -29,6 +34,10 @@ struct FifoScratch {
     unsigned mask[kFifoWarps];
     int32_t first_live_e;                      // executor-order positions before this are dead for the whole batch
     int32_t first_live_d;                      // same for driver-order entries
+    int32_t cmd_app;                           // warp 0 -> helpers: application to run block-wide, -1 = exit
+    uint32_t cmd_seq;
+    int32_t list_base;                         // this group's slice of the per-group application lists
+    int32_t result;                            // block path -> warp 0
 };
 
 // dead for every application of the batch (see GroupMin)
@@ -359,18 +368,129 @@ __device__ __forceinline__ int32_t fifo_app(const Snapshot& s, const GroupDesc& 
     return driver_node;
 }
 
+// ---- one application, warp 0 alone ------------------------------------------------------------------------------
+constexpr int kWarpWinE = 16;          // executor windows of 32 nodes the warp tries before it calls the CTA (512 nodes)
+constexpr int kWarpWinD = 8;           // driver windows (256 candidates)
+constexpr int32_t kEscalate = -3;      // "the whole CTA must decide this application" (never stored as a result)
+
+__device__ __forceinline__ void bar_sync_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// Optimistic single pass, exactly like the first part of fifo_app(): the first driver candidate that FITS is the
+// reference's answer whenever the executors fit with it (binpack.go:67-85).  tightly-pack: node n takes min(cap, rest);
+// distribute-evenly: one round, every hosting node takes one (distribute_evenly.go:49-70 when k hosting nodes exist).
+// Anything else -- no room inside the window budget, executors that do not fit with that driver, several rounds --
+// returns kEscalate with NOTHING charged.  start_e / start_d: the dead prefixes (registers of warp 0).
+template <int ALGO, int FIFO_MODE, bool FAST>
+__device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupDesc& g, const FifoView& view, const PrepApp* __restrict__ pa,
+                                                 int32_t* __restrict__ executor_nodes, uint16_t* __restrict__ cache,
+                                                 int32_t& start_e, int32_t& start_d, WarpStats& st, const GroupMin& gm,
+                                                 bool drv_identity, int lane) {
+    FifoCaps<FAST> a;
+    a.init(pa, (pa->flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
+    const uint32_t k = a.k;
+    if (k > 0xFFFFu) return kEscalate;                       // takes are cached as uint16
+    const int32_t ne = g.ne, nd = g.nd;
+    int32_t* out = executor_nodes + pa->out_off;
+    const int32_t* slot_node = s.slot_node + g.sbase;
+    const bool ug = a.use_gpu;
+
+    // ---- advance the dead prefixes: nodes that can host nothing for ANY application of the batch (GroupMin) ----
+    for (int t = 0; t < 4 && start_e < ne; ++t) {
+        const int32_t i = start_e + lane;
+        const bool alive = i < ne && !dead_for(gm.exe, view.pair(i), ug ? view.gpu(i) : 0, ug);
+        const unsigned vote = __ballot_sync(kFull, alive);
+        if (vote) { start_e += __ffs(vote) - 1; break; }
+        start_e = min(ne, start_e + kWarp);
+    }
+    for (int t = 0; t < 4 && start_d < nd; ++t) {
+        const int32_t j = start_d + lane;
+        bool alive = false;
+        if (j < nd) {
+            const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
+            alive = !dead_for(gm.drv, view.pair(ls), ug ? view.gpu(ls) : 0, ug);
+        }
+        const unsigned vote = __ballot_sync(kFull, alive);
+        if (vote) { start_d += __ffs(vote) - 1; break; }
+        start_d = min(nd, start_d + kWarp);
+    }
+
+    // ---- first driver candidate that fits -----------------------------------------------------------------------
+    int32_t j1 = -1, j0 = start_d;
+    for (int w = 0; j0 < nd && j1 < 0 && w < kWarpWinD; ++w, j0 += kWarp) {
+        const int32_t j = j0 + lane;
+        bool fits = false;
+        if (j < nd) {
+            const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
+            const longlong2 v = view.pair(ls);
+            fits = !(a.d_cpu > v.x) && !(a.d_mem > v.y) && !(ug && a.d_gpu > view.gpu(ls));
+        }
+        const unsigned vote = __ballot_sync(kFull, fits);
+        st.drivers += (unsigned long long)((nd - j0) < kWarp ? (nd - j0) : kWarp);
+        if (vote) j1 = j0 + __ffs(vote) - 1;
+    }
+    if (j1 < 0) return j0 >= nd ? -1 : kEscalate;            // no candidate fits at all -> EmptyPackingResult
+    const int32_t d1 = drv_identity ? j1 : s.drv_slot[g.dbase + j1];
+    if (k == 0) {                                            // no executors: the driver alone (pack_tightly.go:42-44)
+        if (lane == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+        __syncwarp();
+        return slot_node[d1];
+    }
+    const uint32_t cd1 = d1 < ne ? a.capr(view, d1, a.d_cpu, a.d_mem, a.d_gpu) : 0u;
+
+    // ---- executors: 32 nodes per step from the live prefix ----------------------------------------------------------
+    uint32_t placed = 0;
+    int32_t pos = start_e;
+    for (int w = 0; placed < k && pos < ne && w < kWarpWinE; ++w, pos += kWarp) {
+        const int32_t i = pos + lane;
+        uint32_t c = 0;
+        if (i < ne) c = (i == d1) ? cd1 : a.capr(view, i, 0, 0, 0);
+        const uint32_t unit = (ALGO == 0) ? c : (c != 0 ? 1u : 0u);
+        const uint32_t incl = warp_incl_scan(unit, lane);
+        const uint32_t total = __shfl_sync(kFull, incl, kWarp - 1);
+        const uint32_t room = k - placed;
+        const uint32_t T = total < room ? total : room;
+        const uint32_t excl = incl - unit;
+        const uint32_t take = excl >= T ? 0u : ((unit < T - excl) ? unit : (T - excl));
+        cache[pos - start_e + lane] = (uint16_t)take;
+        if (take != 0) {
+            const int32_t node = slot_node[i];
+            for (uint32_t t = 0; t < take; ++t) out[placed + excl + t] = node;
+        }
+        placed += T;
+    }
+    st.nodes += (unsigned long long)((pos < ne ? pos : ne) - start_e);
+    if (placed != k) return kEscalate;                       // nothing has been charged
+
+    // ---- commit (sparkpods.go:139-146 / exact accounting) -----------------------------------------------------------
+    __syncwarp();
+    for (int32_t p0 = start_e; p0 < pos; p0 += kWarp) {
+        const int32_t i = p0 + lane;
+        if (i >= ne) continue;
+        const uint32_t take = cache[i - start_e];
+        if (take != 0) view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
+        if (i == d1 && (FIFO_MODE == 2 || take == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+    }
+    const bool driver_done = (d1 >= start_e && d1 < pos && d1 < ne);      // its owner lane handled it above
+    if (!driver_done && lane == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+    __syncwarp();                                            // the next application sees the charged snapshot
+    return slot_node[d1];
+}
+
 template <int ALGO, int FIFO_MODE>
-__global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, const PrepApp* __restrict__ prep, int32_t n_apps,
+__global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, const PrepApp* __restrict__ prep,
+                                                                    const int32_t* __restrict__ app_group, int32_t n_apps,
                                                                     int32_t* __restrict__ driver_node,
                                                                     int32_t* __restrict__ executor_nodes,
                                                                     int2* __restrict__ scratch,
                                                                     unsigned long long* __restrict__ stats,
-                                                                    const GroupMin* __restrict__ gmins) {
+                                                                    const GroupMin* __restrict__ gmins,
+                                                                    int32_t* __restrict__ app_list, unsigned int* __restrict__ list_cursor) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FifoScratch& sh = *reinterpret_cast<FifoScratch*>(smem_raw);
     uint16_t* cache = reinterpret_cast<uint16_t*>(smem_raw + 2048);
     longlong2* spair = reinterpret_cast<longlong2*>(smem_raw + 2048 + kFifoCache * sizeof(uint16_t));
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int32_t nt = (int32_t)blockDim.x;
     const int32_t grp = blockIdx.x;
     const GroupDesc g = s.groups[grp];
 
@@ -381,7 +501,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
     view.gg = s.gpu + g.sbase;
     view.n_smem = g.ne < kFifoSmemSlots ? g.ne : kFifoSmemSlots;
     const uint32_t stage_bytes = (uint32_t)view.n_smem * (uint32_t)sizeof(longlong2);
-    if (tid == 0) { mbar_init(&sh.bar, 1); sh.first_live_e = 0; sh.first_live_d = 0; }
+    if (tid == 0) { mbar_init(&sh.bar, 1); sh.first_live_e = 0; sh.first_live_d = 0; sh.cmd_app = -1; sh.cmd_seq = 0; }
     const GroupMin gm = gmins[grp];
     __syncthreads();
     if (tid == 0 && stage_bytes != 0) {
@@ -391,41 +511,89 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
             tma_load_1d(reinterpret_cast<unsigned char*>(spair) + off, reinterpret_cast<const unsigned char*>(view.gp) + off, n, &sh.bar);
         }
     }
-    if (stage_bytes != 0) mbar_wait(&sh.bar, 0);
-    __syncthreads();
 
     WarpStats st{0, 0};
     int buf = 0;
-    bool blocked = false;
-    uint32_t app_seq = 0;
-    const int32_t nt = (int32_t)blockDim.x, nw = nt >> 5;
-    for (int32_t i0 = 0; i0 < n_apps; i0 += nt) {
-        int32_t i = i0 + tid;
-        bool mine = (i < n_apps) && (prep[i].group == grp);
-        unsigned m = __ballot_sync(kFull, mine);
-        __syncthreads();                 // previous round's masks fully consumed
-        if (lane == 0) sh.mask[w] = m;
+    // ---- this group's applications in queue order (fitEarlierDrivers walks ONE instance group's queue,
+    // sparkpods.go:61): with one group that is every application; otherwise a stable compaction into app_list
+    const bool all_mine = (s.n_groups == 1) || app_group == nullptr;     // no group column: every application is in group 0
+    int32_t my_cnt = (app_group == nullptr && grp != 0) ? 0 : n_apps;
+    const int32_t* mine = nullptr;
+    if (!all_mine) {
+        int32_t cnt = 0;
+        for (int32_t i0 = 0; i0 < n_apps; i0 += nt) {
+            const int32_t i = i0 + tid;
+            cnt += __syncthreads_count(i < n_apps && app_group[i] == grp);
+        }
+        if (tid == 0) sh.list_base = (int32_t)atomicAdd(list_cursor, (unsigned int)cnt);
         __syncthreads();
-        for (int ww = 0; ww < nw; ++ww) {
-            unsigned mm = sh.mask[ww];
-            while (mm) {
-                int src = __ffs(mm) - 1;
-                mm &= mm - 1;
-                int32_t app = i0 + ww * 32 + src;
+        int32_t* dst = app_list + sh.list_base;
+        uint32_t running = 0;
+        for (int32_t i0 = 0; i0 < n_apps; i0 += nt) {
+            const int32_t i = i0 + tid;
+            const bool m = i < n_apps && app_group[i] == grp;
+            uint32_t excl, total;
+            block_excl_scan(sh, buf, m ? 1u : 0u, excl, total);
+            if (m) dst[running + excl] = i;
+            running += total;
+        }
+        my_cnt = cnt;
+        mine = dst;
+    }
+    // driver order == executor order position by position? (the usual case: both come from one sorted list)
+    bool ident = true;
+    for (int32_t j = tid; j < g.nd; j += nt) ident = ident && (s.drv_slot[g.dbase + j] == j);
+    const bool drv_identity = __syncthreads_and(ident) != 0;
+
+    if (stage_bytes != 0) mbar_wait(&sh.bar, 0);
+    __syncthreads();
+
+    auto run_block = [&](int32_t app, uint32_t seq) -> int32_t {       // every thread of the CTA
+        const PrepApp* pa = prep + app;
+        return (pa->flags & kAppFast) ? fifo_app<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, seq)
+                                      : fifo_app<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, seq);
+    };
+
+    if (w == 0) {
+        int32_t start_e = 0, start_d = 0;
+        bool blocked = false;
+        uint32_t seq = 0;
+        for (int32_t t = 0; t < my_cnt; ++t) {
+            const int32_t app = mine ? mine[t] : t;
+            if (lane == 0 && t + 1 < my_cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + (mine ? mine[t + 1] : t + 1)));
+            int32_t d;
+            if (blocked) d = -2;                                   // never evaluated (resource.go:252)
+            else {
                 const PrepApp* pa = prep + app;
-                int32_t d;
-                if (blocked) d = -2;                                   // never evaluated (resource.go:252)
-                else {
-                    d = -1;
-                    const uint32_t fl = pa->flags;
-                    if (!(fl & kAppInvalid)) {
-                        if (fl & kAppFast) d = fifo_app<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, app_seq++);
-                        else d = fifo_app<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, app_seq++);
+                const uint32_t fl = pa->flags;
+                d = -1;
+                if (!(fl & kAppInvalid)) {
+                    int32_t r = (fl & kAppFast) ? fifo_app_warp<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, lane)
+                                                : fifo_app_warp<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, lane);
+                    if (r == kEscalate) {
+                        if (lane == 0) { sh.first_live_e = start_e; sh.first_live_d = start_d; sh.cmd_app = app; sh.cmd_seq = seq; }
+                        __syncwarp();
+                        bar_sync_named(1, nt);                     // wake the helper warps
+                        r = run_block(app, seq);
+                        __syncwarp();
+                        start_e = sh.first_live_e; start_d = sh.first_live_d;
                     }
-                    if (d < 0 && !(fl & kAppSkipIfNoFit)) blocked = true;   // resource.go:244-253
+                    d = r;
+                    ++seq;
                 }
-                if (tid == 0) driver_node[app] = d;
+                if (d < 0 && !(fl & kAppSkipIfNoFit)) blocked = true;   // resource.go:244-253
             }
+            if (lane == 0) driver_node[app] = d;
+        }
+        if (lane == 0) sh.cmd_app = -1;
+        __syncwarp();
+        bar_sync_named(1, nt);                                     // release the helpers
+    } else {
+        for (;;) {
+            bar_sync_named(1, nt);
+            const int32_t app = sh.cmd_app;
+            if (app < 0) break;
+            run_block(app, sh.cmd_seq);
         }
     }
 

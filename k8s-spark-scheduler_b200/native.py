@@ -104,7 +104,8 @@ class gp_sort_input(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("avail_cpu_milli", C.c_void_p), ("avail_mem_bytes", C.c_void_p),
                 ("n_zones", C.c_int32), ("zone_id", C.c_void_p), ("name_rank", C.c_void_p),
                 ("is_driver_candidate", C.c_void_p), ("unschedulable", C.c_void_p), ("ready", C.c_void_p),
-                ("driver_label_rank", C.c_void_p), ("executor_label_rank", C.c_void_p)]
+                ("driver_label_rank", C.c_void_p), ("executor_label_rank", C.c_void_p),
+                ("avail_gpu", C.c_void_p), ("undefined_ties", C.c_void_p)]
 
 
 class gp_usage_input(C.Structure):
@@ -389,18 +390,23 @@ class GangPacker:
 
     # ---- node priority order (NodeSorter.PotentialNodes) ---------------------------------------
     def potential_nodes(self, avail_cpu, avail_mem, zone_id=None, n_zones=1, name_rank=None, is_driver_candidate=None,
-                        unschedulable=None, ready=None, driver_label_rank=None, executor_label_rank=None):
-        """-> (driver_order, executor_order) as int32 node-index arrays."""
+                        unschedulable=None, ready=None, driver_label_rank=None, executor_label_rank=None, avail_gpu=None):
+        """-> (driver_order, executor_order) as int32 node-index arrays.  With avail_gpu given, self.undefined_ties is the
+        number of adjacent pairs the reference's comparator leaves undefined."""
         cpu, mem = _np(avail_cpu, np.int64), _np(avail_mem, np.int64)
+        gpu = _np(avail_gpu, np.int64)
         n = len(cpu)
         arrs = [_np(zone_id, np.int32), _np(name_rank, np.int32), _np(is_driver_candidate, np.uint8), _np(unschedulable, np.uint8),
                 _np(ready, np.uint8), _np(driver_label_rank, np.int32), _np(executor_label_rank, np.int32)]
+        ties = C.c_int32(0)
         si = gp_sort_input(n_nodes=n, avail_cpu_milli=_p(cpu), avail_mem_bytes=_p(mem), n_zones=n_zones, zone_id=_p(arrs[0]),
                            name_rank=_p(arrs[1]), is_driver_candidate=_p(arrs[2]), unschedulable=_p(arrs[3]), ready=_p(arrs[4]),
-                           driver_label_rank=_p(arrs[5]), executor_label_rank=_p(arrs[6]))
+                           driver_label_rank=_p(arrs[5]), executor_label_rank=_p(arrs[6]), avail_gpu=_p(gpu),
+                           undefined_ties=C.addressof(ties))
         d = np.empty(max(n, 1), np.int32); e = np.empty(max(n, 1), np.int32)
         nd, ne = C.c_int32(0), C.c_int32(0)
         self._check(load().gp_potential_nodes(self._h, C.byref(si), _p(d), C.byref(nd), _p(e), C.byref(ne)))
+        self.undefined_ties = ties.value
         return d[:nd.value].copy(), e[:ne.value].copy()
 
     # ---- packing -----------------------------------------------------------------------------

@@ -168,3 +168,45 @@ def test_scan_path_forced():
     p = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x"] + tests, env=env, cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [4095, 4097, 50000, 500000])
+def test_node_order_large(packer, n):
+    """PotentialNodes (internal/sort/nodesorting.go:83-122) at sizes that span one tile, a tile boundary, BASELINE
+    configs[4] and 10x that: the device order (tile sort in shared memory + binary-search ranks) must equal a host
+    lexicographic sort on (zone priority, memory, cpu, name) with heavy ties; label-rank re-sort on the candidate lists."""
+    rng = np.random.default_rng(n)
+    Z = 3
+    zone = rng.integers(0, Z, n).astype(np.int32)
+    cpu = (rng.integers(0, 40, n) * 500).astype(np.int64) - (rng.integers(0, 50, n) == 0) * 3000
+    mem = (rng.integers(0, 64, n) << 30).astype(np.int64)
+    rank = rng.permutation(n).astype(np.int32)                      # rank of the node name
+    cand = (rng.random(n) < 0.7).astype(np.uint8)
+    unsched = (rng.random(n) < 0.05).astype(np.uint8)
+    ready = (rng.random(n) < 0.97).astype(np.uint8)
+    lrd = rng.integers(-1, 4, n).astype(np.int32)
+    d, e = packer.potential_nodes(cpu, mem, zone, Z, rank, cand, unsched, ready, lrd, None)
+    # host truth
+    tot_m = np.array([mem[zone == z].sum() for z in range(Z)]); tot_c = np.array([cpu[zone == z].sum() for z in range(Z)])
+    zorder = sorted(range(Z), key=lambda z: (tot_m[z], tot_c[z], z))
+    zprio = np.empty(Z, np.int64); zprio[zorder] = np.arange(Z)
+    order = np.lexsort((rank, cpu, mem, zprio[zone]))
+    drv = order[cand[order] != 0]
+    key = np.where(lrd[drv] < 0, 1 << 30, lrd[drv])
+    drv = drv[np.argsort(key, kind="stable")]
+    exe = order[(unsched[order] == 0) & (ready[order] != 0)]
+    assert np.array_equal(d, drv.astype(np.int32))
+    assert np.array_equal(e, exe.astype(np.int32))
+
+
+def test_undefined_ties_are_reported(packer):
+    """equal (zone priority, memory, cpu) with different gpu is 'not less' both ways in the reference's
+    comparator (nodesorting.go:83-93) -> sort.Slice may order the pair either way.  The device orders by name and says so."""
+    cpu = np.array([4000, 4000, 4000, 8000], np.int64); mem = np.array([1 << 33] * 3 + [1 << 34], np.int64)
+    gpu = np.array([0, 1, 0, 0], np.int64)
+    d, e = packer.potential_nodes(cpu, mem, avail_gpu=gpu)
+    assert list(d) == [0, 1, 2, 3] and packer.undefined_ties == 2          # (n0,n1) and (n1,n2) differ in gpu only
+    d, e = packer.potential_nodes(cpu, mem, avail_gpu=np.zeros(4, np.int64))
+    assert packer.undefined_ties == 0
+    d, e = packer.potential_nodes(cpu, mem)
+    assert packer.undefined_ties == 0                                        # no gpu column: nothing to detect
