@@ -313,6 +313,28 @@ gp_status gp_pack_batch_device(gp_ctx* ctx, const gp_apps* dev_apps, gp_algo alg
 void* gp_stream(gp_ctx* ctx);
 gp_status gp_synchronize(gp_ctx* ctx);
 
+/* ---- single-AZ packers on the device -----------------------------------------------------------
+ * getSingleAZSparkBinFunction + chooseBestResult (LIB/binpack/single_az.go:23-97) for a BATCH of applications.  The
+ * snapshot's instance groups are the candidate zones in driverZonesInOrder order (groupNodesByZone, :57-73; zones without
+ * executor candidates are left out by the caller like :38-41).  Every application is packed in every zone
+ * (algo GP_TIGHTLY_PACK = "single-az-tightly-pack", GP_MINIMAL_FRAGMENTATION = "single-az-minimal-fragmentation"), the
+ * float64 packing efficiencies (LIB/binpack/efficiency.go:66-156) are evaluated in the reference's operation order --
+ * [driver] + ExecutorNodes, duplicates kept, sequential sums, cpu through Quantity.Value() -- and the zone with the highest
+ * AvgPackingEfficiency.Max wins: the first among equals, and none when every average is 0 (:80, :91).  For
+ * minimal-fragmentation the efficiencies see the driver only (minimalFragmentation never adds its executors to
+ * SparkBinPack's reserved map) -- kept.  "az-aware-tightly-pack" (az_aware_pack_tightly.go:27-38) = this call, then plain
+ * gp_pack_batch(GP_TIGHTLY_PACK) over the undivided orders for the applications that got zone -1.
+ * gp_set_schedulable: NodeSchedulingMetadata.SchedulableResources of the current snapshot's nodes (resources.go:61-100). */
+gp_status gp_set_schedulable(gp_ctx* ctx, const int64_t* sched_cpu_milli, const int64_t* sched_mem_bytes, const int64_t* sched_gpu /* or NULL */);
+typedef struct {
+    int32_t* zone;                   /* [n_apps] chosen instance group (zone), -1 = EmptyPackingResult */
+    int32_t* driver_node;            /* [n_apps] */
+    int32_t* executor_nodes;         /* CSR by exec_out_off (or the prefix sum of exe_count); defined when zone >= 0 */
+    int64_t executor_nodes_cap;
+    double* avg_efficiency;          /* [n_apps][4] = AvgPackingEfficiency{CPU, Memory, GPU, Max} of the winner, or NULL */
+} gp_zone_results;
+gp_status gp_pack_batch_zones(gp_ctx* ctx, const gp_apps* apps /* group, skip_if_no_fit ignored */, gp_algo algo, gp_zone_results* out);
+
 /* ---- several GPUs of one box behind ONE host process -----------------------------------------------
  * The reference is a single process with a serial Predicate (internal/extender/resource.go:194-205); this handle lets
  * that process use every GPU: one gp_ctx + one worker thread per entry of `devices` (an ordinal may repeat).

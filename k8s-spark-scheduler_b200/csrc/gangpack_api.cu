@@ -5,6 +5,7 @@
 #include "gangpack_fifo.cuh"
 #include "gangpack_minfrag.cuh"
 #include "gangpack_tables.cuh"
+#include "gangpack_zones.cuh"
 #include "gangpack_resched.cuh"
 #include "gangpack_sort.cuh"
 
@@ -348,6 +349,8 @@ struct gp_ctx {
     struct TableSet { DevBuf hdr, table, total, app_slot; } tabs[kLanes];
     DevBuf off_dev;                               // ExecutorNodes offsets derived on the device
     DevBuf fifo_list;                             // FIFO modes: per-instance-group application lists (queue order)
+    DevBuf sched, zonebuf;                        // SchedulableResources [3][n_nodes]; staging of gp_pack_batch_zones
+    bool have_sched = false;
     bool sort_attr_set = false;
     bool fifo_attr_set[2] = {false, false};       // dynamic shared-memory opt-in of gp_pack_fifo_cta<ALGO,*> done on this device
 
@@ -467,7 +470,7 @@ void gp_destroy(gp_ctx* c) {
                       &c->pair, &c->pair32, &c->sgpu, &c->slot_node, &c->node_slot, &c->drv_slot, &c->groups, &c->snap_flags,
                       &c->a_dcpu, &c->a_dmem, &c->a_dgpu, &c->a_ecpu, &c->a_emem, &c->a_egpu, &c->a_count, &c->a_group,
                       &c->a_skip, &c->a_off, &c->prep, &c->r_driver, &c->r_exec, &c->scratch, &c->dev_misc, &c->gmin, &c->sortbuf, &c->usagebuf, &c->reschedbuf,
-                      &c->off_dev, &c->fifo_list};
+                      &c->off_dev, &c->fifo_list, &c->sched, &c->zonebuf};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : c->tabs) { t.hdr.release(); t.table.release(); t.total.release(); t.app_slot.release(); }
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
@@ -553,6 +556,7 @@ static gp_status build_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_
     GP_CUDA(c, cudaGetLastError());
     c->n_nodes = dn->n_nodes; c->n_groups = dn->n_groups; c->n_exec = n_exec; c->n_drv = n_drv; c->n_slots = n_slots;
     c->have_snapshot = true;
+    c->have_sched = false;               // SchedulableResources belong to a node table
     return GP_OK;
 }
 
@@ -1212,6 +1216,111 @@ gp_status gp_pack_one(gp_ctx* c, gp_algo algo, int64_t drv_cpu, int64_t drv_mem,
     *driver_node = d >= 0 ? d : -1;
     if (d >= 0 && n_exec) std::memcpy(executor_nodes, exec_out, sizeof(int32_t) * n_exec);
     return GP_OK;
+}
+
+// ---- single-AZ packers: pack every zone, choose by packing efficiency on the device (gangpack_zones.cuh) ----------
+gp_status gp_set_schedulable(gp_ctx* c, const int64_t* cpu, const int64_t* mem, const int64_t* gpu) {
+    if (!c) return GP_ERR_INVALID;
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, "gp_set_schedulable: gp_set_snapshot first");
+    if (c->n_nodes > 0 && (!cpu || !mem)) return fail(c, GP_ERR_INVALID, "gp_set_schedulable: missing arrays");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)c->n_nodes;
+    for (size_t i = 0; i < N; ++i) {
+        const int64_t v[3] = {cpu[i], mem[i], gpu ? gpu[i] : 0};
+        for (int64_t x : v) if (x >= kMaxQuantity || x <= -kMaxQuantity) return fail(c, GP_ERR_UNREPRESENTABLE, "gp_set_schedulable: |quantity| >= 2^61");
+    }
+    GP_CUDA(c, c->sched.reserve(24 * (N + 1)));
+    char* b = c->sched.as<char>();
+    if (N) {
+        GP_CUDA(c, cudaMemcpyAsync(b, cpu, 8 * N, cudaMemcpyHostToDevice, c->stream));
+        GP_CUDA(c, cudaMemcpyAsync(b + 8 * N, mem, 8 * N, cudaMemcpyHostToDevice, c->stream));
+        if (gpu) GP_CUDA(c, cudaMemcpyAsync(b + 16 * N, gpu, 8 * N, cudaMemcpyHostToDevice, c->stream));
+        else GP_CUDA(c, cudaMemsetAsync(b + 16 * N, 0, 8 * N, c->stream));
+    }
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_sched = true;
+    return GP_OK;
+}
+
+gp_status gp_pack_batch_zones(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_zone_results* out) {
+    if (!c) return GP_ERR_INVALID;
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, "gp_pack_batch_zones: gp_set_snapshot first");
+    if (!c->have_sched) return fail(c, GP_ERR_INVALID, "gp_pack_batch_zones: gp_set_schedulable first (the efficiencies need SchedulableResources)");
+    if (!a || !out || a->n_apps < 0) return fail(c, GP_ERR_INVALID, "gp_pack_batch_zones: NULL apps/results");
+    if (algo != GP_TIGHTLY_PACK && algo != GP_MINIMAL_FRAGMENTATION)
+        return fail(c, GP_ERR_INVALID, "gp_pack_batch_zones: the single-AZ packers are tightly-pack and minimal-fragmentation (single_az_pack_tightly.go, single_az_minimal_fragmentation.go)");
+    const int32_t Q = a->n_apps, Z = c->n_groups;
+    if (Q == 0) return GP_OK;
+    if (!a->drv_cpu_milli || !a->drv_mem_bytes || !a->exe_cpu_milli || !a->exe_mem_bytes || !a->exe_count || !out->zone || !out->driver_node)
+        return fail(c, GP_ERR_INVALID, "gp_pack_batch_zones: missing app/result arrays");
+    if ((int64_t)Q * Z > 0x7fffffffLL) return fail(c, GP_ERR_INVALID, "gp_pack_batch_zones: n_apps x zones too large");
+    const int64_t* off = a->exec_out_off;
+    if (!off) {
+        c->host_off.resize((size_t)Q + 1);
+        int64_t acc = 0;
+        for (int32_t i = 0; i < Q; ++i) { c->host_off[(size_t)i] = acc; acc += a->exe_count[i] > 0 ? a->exe_count[i] : 0; }
+        c->host_off[(size_t)Q] = acc;
+        off = c->host_off.data();
+    }
+    const int64_t total = off[Q];
+    if (total < 0 || total > out->executor_nodes_cap) return fail(c, GP_ERR_CAPACITY, "gp_pack_batch_zones: executor_nodes_cap too small");
+    if (total > 0 && !out->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_batch_zones: executor_nodes is NULL");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t q = (size_t)Q, R = q * (size_t)Z, T = (size_t)total;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t o_in = take(48 * q), o_cnt = take(4 * q), o_off = take(8 * (q + 1)), o_rows = take(48 * R), o_rcnt = take(4 * R), o_rgrp = take(4 * R),
+                 o_roff = take(8 * (R + 1)), o_rdrv = take(4 * R), o_rexe = take(4 * ((size_t)Z * T + 1)), o_zone = take(4 * q), o_drv = take(4 * q),
+                 o_exe = take(4 * (T + 1)), o_avg = take(32 * q);
+    GP_CUDA(c, c->zonebuf.reserve(o));
+    char* b = c->zonebuf.as<char>();
+    const int64_t* hc[6] = {a->drv_cpu_milli, a->drv_mem_bytes, a->drv_gpu, a->exe_cpu_milli, a->exe_mem_bytes, a->exe_gpu};
+    SixCols six{};
+    for (int k = 0; k < 6; ++k) {
+        if (!hc[k]) continue;
+        GP_CUDA(c, cudaMemcpyAsync(b + o_in + 8 * q * (size_t)k, hc[k], 8 * q, cudaMemcpyHostToDevice, st));
+        six.p[k] = reinterpret_cast<const int64_t*>(b + o_in + 8 * q * (size_t)k);
+    }
+    GP_CUDA(c, cudaMemcpyAsync(b + o_cnt, a->exe_count, 4 * q, cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(b + o_off, off, 8 * (q + 1), cudaMemcpyHostToDevice, st));
+    const int TH = 256;
+    // the efficiencies read the availability in node-table order: refresh that copy from the slots (a FIFO batch may
+    // have charged them since gp_set_snapshot)
+    if (c->n_slots > 0)
+        gp_scatter_slots<<<(c->n_slots + TH - 1) / TH, TH, 0, st>>>(c->n_slots, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
+                                                                   c->node_cpu.as<int64_t>(), c->node_mem.as<int64_t>(), c->node_gpu.as<int64_t>());
+    gp_zone_expand<<<(unsigned)((R + 1 + TH - 1) / TH), TH, 0, st>>>(Q, Z, six, (const int32_t*)(b + o_cnt), (const int64_t*)(b + o_off),
+                                                                      (int64_t*)(b + o_rows), (int32_t*)(b + o_rcnt), (int32_t*)(b + o_rgrp), (int64_t*)(b + o_roff));
+    int2* scratch = nullptr;
+    gp_status s = pack_begin(c, (int32_t)R, algo, GP_MODE_INDEPENDENT, (int64_t)Z * total, false, &scratch, st);
+    if (s != GP_OK) return s;
+    DevApps dv{};
+    for (int k = 0; k < 6; ++k) dv.cols.q[k] = b + o_rows + 8 * R * (size_t)k;
+    dv.cols.count = (const int32_t*)(b + o_rcnt); dv.cols.group = (const int32_t*)(b + o_rgrp); dv.cols.off = (const int64_t*)(b + o_roff);
+    dv.cols.bits = 64; dv.cols.mem_shift = 0; dv.skip = nullptr; dv.n = (int32_t)R;
+    DevResults dr{(int32_t*)(b + o_rdrv), b + o_rexe, (int64_t)Z * total, 32};
+    s = pack_device_range(c, dv, 0, (int32_t)R, 0, algo, GP_MODE_INDEPENDENT, dr, scratch, st, 0);
+    if (s != GP_OK) return s;
+    c->ev_chunks = 1;
+    ZoneChooseIn zi{};
+    const size_t N = (size_t)c->n_nodes;
+    zi.avail[0] = c->node_cpu.as<long long>(); zi.avail[1] = c->node_mem.as<long long>(); zi.avail[2] = c->node_gpu.as<long long>();
+    zi.sched[0] = c->sched.as<long long>(); zi.sched[1] = c->sched.as<long long>() + N; zi.sched[2] = c->sched.as<long long>() + 2 * N;
+    for (int k = 0; k < 3; ++k) { zi.drv[k] = six.p[k]; zi.exe[k] = six.p[3 + k]; }
+    zi.count = (const int32_t*)(b + o_cnt); zi.out_off = (const int64_t*)(b + o_off);
+    zi.row_driver = (const int32_t*)(b + o_rdrv); zi.row_exec = (const int32_t*)(b + o_rexe);
+    zi.n_apps = Q; zi.n_zones = Z; zi.executors_reserved = algo == GP_TIGHTLY_PACK ? 1 : 0;
+    gp_zone_choose<<<(unsigned)((q * 32 + TH - 1) / TH), TH, 0, st>>>(zi, (int32_t*)(b + o_zone), (int32_t*)(b + o_drv), (int32_t*)(b + o_exe),
+                                                                       out->avg_efficiency ? (double*)(b + o_avg) : nullptr);
+    GP_CUDA(c, cudaGetLastError());
+    c->last.kernel_launches += 2;
+    GP_CUDA(c, cudaMemcpyAsync(out->zone, b + o_zone, 4 * q, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(out->driver_node, b + o_drv, 4 * q, cudaMemcpyDeviceToHost, st));
+    if (T) GP_CUDA(c, cudaMemcpyAsync(out->executor_nodes, b + o_exe, 4 * T, cudaMemcpyDeviceToHost, st));
+    if (out->avg_efficiency) GP_CUDA(c, cudaMemcpyAsync(out->avg_efficiency, b + o_avg, 32 * q, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    return decode_device_error(c, *reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48));
 }
 
 // ---- node priority order (f1) and availability snapshot (f2): device stages + the entries built on them ----

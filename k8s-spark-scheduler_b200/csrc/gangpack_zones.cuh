@@ -1,0 +1,144 @@
+// gangpack_zones.cuh -- SURVEY §8f row f3 on the device: the float64 packing efficiencies and chooseBestResult of the
+// single-AZ packers.
+//
+// Reference (LIB = /root/reference/vendor/github.com/palantir/k8s-spark-scheduler-lib/pkg):
+//   computePackingEfficiency / ComputeAvgPackingEfficiency      LIB/binpack/efficiency.go:79-156
+//   getSingleAZSparkBinFunction / chooseBestResult              LIB/binpack/single_az.go:23-55, 75-97
+//   SparkBinPack's `reserved` map (what the efficiencies see)   LIB/binpack/binpack.go:72-77
+//   Quantity.Value() of a milli quantity (ceil away from zero)  vendor/k8s.io/apimachinery/pkg/api/resource/quantity.go:732-734
+//
+// Every application has been packed once per candidate zone (zone = instance group; row = app * Z + z of an independent
+// batch).  One warp per application: lane z walks row (app, z) SEQUENTIALLY in the reference's order -- [driver] +
+// ExecutorNodes, duplicates kept -- so the float64 sums round exactly like the Go loop; the warp then takes the arg-max of
+// AvgPackingEfficiency.Max with the reference's tie rule (strict LessThan against a running best that starts at 0.0:
+// the first zone with the highest average wins, and nothing wins when every average is 0) and copies the winning row.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gp {
+
+struct ZoneChooseIn {
+    const long long* avail[3];        // node-table order
+    const long long* sched[3];        // SchedulableResources, node-table order (gpu may be NULL = 0)
+    const int64_t* drv[3];            // per application (device columns, int64)
+    const int64_t* exe[3];
+    const int32_t* count;
+    const int64_t* out_off;           // [n_apps + 1] CSR of the chosen placements
+    const int32_t* row_driver;        // [n_apps * Z]
+    const int32_t* row_exec;          // row (app, z) at Z * out_off[app] + z * count[app]
+    int32_t n_apps, n_zones;
+    int32_t executors_reserved;       // 1: tightly-pack (every executor is in `reserved`), 0: minimal-fragmentation (driver only)
+};
+
+__device__ __forceinline__ long long cpu_value(long long milli) {       // Quantity.Value(): whole cores, inexact -> away from zero
+    const long long q = milli / 1000, rem = milli % 1000;
+    return rem > 0 ? q + 1 : (rem < 0 ? q - 1 : q);
+}
+__device__ __forceinline__ long long normalize_resource(long long v) { return v == 0 ? 1 : v; }       // efficiency.go:104-109
+
+// computePackingEfficiency (efficiency.go:79-102) for node n with `r*` reserved on it; returns max(GPU, max(CPU, Memory))
+// and the three components
+__device__ __forceinline__ double node_efficiency(const ZoneChooseIn& in, int32_t n, long long rc, long long rm, long long rg,
+                                                  double& cpu, double& mem, double& gpu, bool& has_gpu) {
+    const long long sc = in.sched[0][n], sm = in.sched[1][n], sg = in.sched[2] ? in.sched[2][n] : 0;
+    const long long uc = sc - in.avail[0][n] + rc, um = sm - in.avail[1][n] + rm, ug = sg - in.avail[2][n] + rg;
+    has_gpu = sg != 0;
+    gpu = has_gpu ? (double)ug / (double)normalize_resource(sg) : 0.0;
+    cpu = (double)cpu_value(uc) / (double)normalize_resource(cpu_value(sc));
+    mem = (double)um / (double)normalize_resource(sm);
+    return fmax(gpu, fmax(cpu, mem));
+}
+
+__global__ void __launch_bounds__(256) gp_zone_choose(ZoneChooseIn in, int32_t* __restrict__ zone_out, int32_t* __restrict__ driver_out,
+                                                      int32_t* __restrict__ exec_out, double* __restrict__ avg_out /* [n_apps][4] or NULL */) {
+    const int lane = threadIdx.x & 31;
+    const int32_t app = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (app >= in.n_apps) return;
+    const int32_t Z = in.n_zones;
+    const int32_t k = in.count[app] > 0 ? in.count[app] : 0;
+    const int64_t base = (int64_t)Z * in.out_off[app];
+    const long long dc = in.drv[0][app], dm = in.drv[1][app], dg = in.drv[2] ? in.drv[2][app] : 0;
+    const long long ec = in.exe[0][app], em = in.exe[1][app], eg = in.exe[2] ? in.exe[2][app] : 0;
+    double best = 0.0;                 // WorstAvgPackingEfficiency().Max
+    int32_t best_z = -1;
+    double best4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int32_t z0 = 0; z0 < Z; z0 += 32) {
+        const int32_t z = z0 + lane;
+        double avg_max = 0.0, a4[4] = {0.0, 0.0, 0.0, 0.0};
+        bool fits = false;
+        if (z < Z) {
+            const int32_t d = in.row_driver[(int64_t)app * Z + z];
+            if (d >= 0) {
+                fits = true;
+                const int32_t* ex = in.row_exec + base + (int64_t)z * k;
+                // executors on the driver's node (reserved[driver] = driver + its executors, binpack.go:72-75 + pack_tightly.go:50)
+                long long on_driver = 0;
+                if (in.executors_reserved) for (int32_t t = 0; t < k; ++t) on_driver += ex[t] == d ? 1 : 0;
+                double cpuSum = 0.0, memSum = 0.0, gpuSum = 0.0, maxSum = 0.0, c, m, g;
+                int nodesWithGPU = 0;
+                bool hg;
+                double mx = node_efficiency(in, d, dc + on_driver * ec, dm + on_driver * em, dg + on_driver * eg, c, m, g, hg);
+                cpuSum += c; memSum += m; if (hg) { gpuSum += g; nodesWithGPU++; } maxSum += mx;
+                int32_t t = 0;
+                while (t < k) {
+                    const int32_t n = ex[t];
+                    // executors of this placement on node n (ExecutorNodes may list a node in several runs: count them all)
+                    long long cnt = 0;
+                    if (in.executors_reserved) for (int32_t u = 0; u < k; ++u) cnt += ex[u] == n ? 1 : 0;
+                    const long long isd = n == d ? 1 : 0;
+                    mx = node_efficiency(in, n, isd * dc + cnt * ec, isd * dm + cnt * em, isd * dg + cnt * eg, c, m, g, hg);
+                    // every entry of the run adds the same efficiency again (ComputeAvgPackingEfficiency loops over entries)
+                    int32_t run = 1;
+                    while (t + run < k && ex[t + run] == n) ++run;
+                    for (int32_t u = 0; u < run; ++u) { cpuSum += c; memSum += m; if (hg) { gpuSum += g; nodesWithGPU++; } maxSum += mx; }
+                    t += run;
+                }
+                const double length = fmax((double)(k + 1), 1.0);
+                a4[0] = cpuSum / length; a4[1] = memSum / length;
+                a4[2] = nodesWithGPU == 0 ? 1.0 : gpuSum / (double)nodesWithGPU;
+                a4[3] = maxSum / length;
+                avg_max = a4[3];
+            }
+        }
+        // arg-max in zone order with strict '<' against the running best (single_az.go:91-94)
+        for (int32_t t = 0; t < 32 && z0 + t < Z; ++t) {
+            const bool f = __shfl_sync(0xffffffffu, fits ? 1 : 0, t) != 0;
+            const double v = __shfl_sync(0xffffffffu, avg_max, t);
+            const double v0 = __shfl_sync(0xffffffffu, a4[0], t), v1 = __shfl_sync(0xffffffffu, a4[1], t), v2 = __shfl_sync(0xffffffffu, a4[2], t);
+            if (f && best < v) { best = v; best_z = z0 + t; best4[0] = v0; best4[1] = v1; best4[2] = v2; best4[3] = v; }
+        }
+    }
+    if (lane == 0) {
+        zone_out[app] = best_z;
+        driver_out[app] = best_z >= 0 ? in.row_driver[(int64_t)app * Z + best_z] : -1;
+        if (avg_out) { avg_out[4 * (int64_t)app + 0] = best4[0]; avg_out[4 * (int64_t)app + 1] = best4[1]; avg_out[4 * (int64_t)app + 2] = best4[2]; avg_out[4 * (int64_t)app + 3] = best4[3]; }
+    }
+    if (best_z >= 0) {
+        const int32_t* ex = in.row_exec + base + (int64_t)best_z * k;
+        int32_t* out = exec_out + in.out_off[app];
+        for (int32_t t = lane; t < k; t += 32) out[t] = ex[t];
+    }
+}
+
+// rows (app, z): the application's tuple with group = z, executor slice at Z * off[app] + z * count[app]
+struct SixCols { const int64_t* p[6]; };      // drv cpu, drv mem, drv gpu, exe cpu, exe mem, exe gpu (NULL = 0)
+__global__ void gp_zone_expand(int32_t n_apps, int32_t Z, SixCols src,
+                               const int32_t* __restrict__ count, const int64_t* __restrict__ off,
+                               int64_t* __restrict__ dst /* [6][n_apps * Z] */, int32_t* __restrict__ rcount, int32_t* __restrict__ rgroup,
+                               int64_t* __restrict__ roff /* [n_apps * Z + 1] */) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t R = (int64_t)n_apps * Z;
+    if (r > R) return;
+    if (r == R) { roff[R] = (int64_t)Z * off[n_apps]; return; }
+    const int32_t app = (int32_t)(r / Z), z = (int32_t)(r % Z);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dst[(int64_t)c * R + r] = src.p[c] ? src.p[c][app] : 0;
+    const int32_t k = count[app];
+    rcount[r] = k;
+    rgroup[r] = z;
+    roff[r] = (int64_t)Z * off[app] + (int64_t)z * (k > 0 ? k : 0);
+}
+
+}  // namespace gp

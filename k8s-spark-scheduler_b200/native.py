@@ -16,7 +16,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("GANGPACK_LIB") or os.path.join(_PKG, "libgangpack.so")   # GANGPACK_LIB: experimental builds
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("gangpack_api.cu", "gangpack_kernels.cuh", "gangpack_fifo.cuh", "gangpack_minfrag.cuh",
-                                                    "gangpack_sort.cuh", "gangpack_tables.cuh", "gangpack_resched.cuh", "gangpack_multi.cu")] + [
+                                                    "gangpack_sort.cuh", "gangpack_tables.cuh", "gangpack_resched.cuh", "gangpack_multi.cu",
+                                                    "gangpack_zones.cuh")] + [
     os.path.join(_ROOT, "include", "gangpack.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,7 +35,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 
 # every symbol include/gangpack.h declares (tests assert the .so exports exactly these)
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
-           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one",
+           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one", "gp_set_schedulable", "gp_pack_batch_zones",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
            "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors",
            "gp_multi_create", "gp_multi_destroy", "gp_multi_last_error", "gp_multi_size", "gp_multi_ctx",
@@ -94,6 +95,11 @@ class gp_apps_wire(C.Structure):
 class gp_results_wire(C.Structure):
     _fields_ = [("driver_node", C.c_void_p), ("executor_nodes", C.c_void_p), ("executor_nodes_cap", C.c_int64),
                 ("node_bits", C.c_int32), ("reserved", C.c_int32)]
+
+
+class gp_zone_results(C.Structure):
+    _fields_ = [("zone", C.c_void_p), ("driver_node", C.c_void_p), ("executor_nodes", C.c_void_p), ("executor_nodes_cap", C.c_int64),
+                ("avg_efficiency", C.c_void_p)]
 
 
 class gp_results(C.Structure):
@@ -165,6 +171,10 @@ def load():
     L.gp_pack_batch.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.c_int, C.POINTER(gp_results)]
     L.gp_pack_batch_wire.restype = C.c_int
     L.gp_pack_batch_wire.argtypes = [C.c_void_p, C.POINTER(gp_apps_wire), C.c_int, C.c_int, C.POINTER(gp_results_wire)]
+    L.gp_set_schedulable.restype = C.c_int
+    L.gp_set_schedulable.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gp_pack_batch_zones.restype = C.c_int
+    L.gp_pack_batch_zones.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.POINTER(gp_zone_results)]
     L.gp_pack_one.restype = C.c_int
     L.gp_pack_one.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 6 + [C.c_int32, C.POINTER(C.c_int32),
                                                                           C.POINTER(C.c_int32), C.c_void_p]
@@ -457,6 +467,29 @@ class GangPacker:
                                 executor_nodes_cap=len(executor_nodes), node_bits=node_bits)
             self._check(load().gp_pack_batch_wire(self._h, C.byref(a), algo, mode, C.byref(r)))
         return driver_node, executor_nodes[:total], off
+
+    def set_schedulable(self, sched_cpu, sched_mem, sched_gpu=None):
+        """NodeSchedulingMetadata.SchedulableResources of the current snapshot's nodes (needed by pack_batch_zones)."""
+        c, m, g = _np(sched_cpu, np.int64), _np(sched_mem, np.int64), _np(sched_gpu, np.int64)
+        self._check(load().gp_set_schedulable(self._h, _p(c), _p(m), _p(g)))
+
+    def pack_batch_zones(self, apps: dict, algo: int):
+        """single-az-tightly-pack / single-az-minimal-fragmentation for a batch: the snapshot's instance groups are the
+        candidate zones.  -> (zone[q], driver_node[q], executor_nodes, off[q+1], avg_efficiency[q,4])."""
+        q = len(apps["count"])
+        count = _np(apps["count"], np.int32)
+        off = np.zeros(q + 1, np.int64)
+        np.cumsum(np.maximum(count, 0), out=off[1:])
+        arrs = {k: _np(apps.get(k), np.int64) for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}
+        total = int(off[-1]) if q else 0
+        zone = np.full(q, -9, np.int32); drv = np.full(q, -9, np.int32)
+        exe = np.full(max(total, 1), -9, np.int32); avg = np.zeros((max(q, 1), 4), np.float64)
+        a = gp_apps(n_apps=q, drv_cpu_milli=_p(arrs["drv_cpu"]), drv_mem_bytes=_p(arrs["drv_mem"]), drv_gpu=_p(arrs["drv_gpu"]),
+                    exe_cpu_milli=_p(arrs["exe_cpu"]), exe_mem_bytes=_p(arrs["exe_mem"]), exe_gpu=_p(arrs["exe_gpu"]),
+                    exe_count=_p(count), group=None, skip_if_no_fit=None, exec_out_off=_p(off))
+        r = gp_zone_results(zone=_p(zone), driver_node=_p(drv), executor_nodes=_p(exe), executor_nodes_cap=len(exe), avg_efficiency=_p(avg))
+        self._check(load().gp_pack_batch_zones(self._h, C.byref(a), algo, C.byref(r)))
+        return zone, drv, exe[:total], off, avg[:q]
 
     def pack_one(self, algo, drv, exe, count):
         """binpack.SparkBinPackFunction for one app -> (has_capacity, driver_node, executor_nodes)."""

@@ -1,0 +1,100 @@
+"""SURVEY 8f row f3 on the device: single-az-tightly-pack / single-az-minimal-fragmentation for a batch
+(gp_pack_batch_zones: pack every zone, float64 packing efficiencies and chooseBestResult in a kernel) against the LITERAL
+restatement of getSingleAZSparkBinFunction + chooseBestResult + ComputePackingEfficiencies (LIB/binpack/single_az.go:23-97,
+efficiency.go:66-156) -- the choice must be bit-identical: same zone, same driver node, same ExecutorNodes."""
+import numpy as np
+import pytest
+
+from helpers import node_names, random_apps, random_cluster, res_aos
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def packer(gangpack):
+    p = gangpack.GangPacker()
+    yield p
+    p.close()
+
+
+def _zone_groups(order_d, order_e, zone_of):
+    """groupNodesByZone (single_az.go:57-73) for both orders; zones without executor candidates are skipped (:38-41)."""
+    zones, dz, ez = [], {}, {}
+    for n in order_d:
+        z = zone_of[n]
+        if z not in dz:
+            zones.append(z); dz[z] = []
+        dz[z].append(n)
+    for n in order_e:
+        ez.setdefault(zone_of[n], []).append(n)
+    zones = [z for z in zones if z in ez]
+    eoff, doff, eo, do = [0], [0], [], []
+    for z in zones:
+        eo += ez[z]; do += dz[z]
+        eoff.append(len(eo)); doff.append(len(do))
+    return zones, np.array(eo, np.int32), np.array(do, np.int32), np.array(eoff, np.int32), np.array(doff, np.int32)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_single_az_packers_vs_literal(oracle, packer, seed):
+    rng = np.random.default_rng(700 + seed)
+    n = int(rng.integers(30, 160))
+    Z = int(rng.integers(1, 5))
+    cpu, mem, gpu = random_cluster(rng, n, tight=bool(seed % 2), gpus=bool(seed % 3 == 0))
+    # schedulable = available + what is already used (whole cores and odd millicores both occur: Value() rounds up)
+    sc = cpu + rng.integers(0, 9, n) * 250 + (rng.integers(0, 3, n) == 0) * 1
+    sm = mem + rng.integers(0, 17, n) * (1 << 28)
+    sg = np.maximum(gpu, 0) + (rng.integers(0, 2, n) if seed % 3 == 0 else 0)
+    zone_of = rng.integers(0, Z, n)
+    names = node_names(n)
+    labels = ["zone-%d" % z for z in zone_of]
+    order = rng.permutation(n)
+    order_e = [int(i) for i in order if rng.random() < 0.85]
+    order_d = [int(i) for i in rng.permutation(n)[: max(1, int(n * 0.7))]]
+    zones, eo, do, eoff, doff = _zone_groups(order_d, order_e, zone_of)
+    q = 250
+    apps = random_apps(rng, q, gpus=bool(seed % 3 == 0), zero_dims=bool(seed == 5))
+    cl = oracle.Cluster(names, cpu, mem, gpu, sched=(sc, sm, sg), zone=labels)
+    drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"]); exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+    if not zones:
+        return
+    packer.set_snapshot(cpu, mem, gpu, eo, do, eoff, doff)
+    packer.set_schedulable(sc, sm, sg)
+    for algo, oalgo in ((0, 2), (2, 5)):                       # single-az-tightly-pack, single-az-minimal-fragmentation
+        wd, we, woff = cl.binpack_batch(oalgo, drv, exe, apps["count"], [names[i] for i in order_d], [names[i] for i in order_e],
+                                        with_efficiencies=True, n_threads=4)
+        zone, gd, ge, goff, avg = packer.pack_batch_zones(apps, algo)
+        assert np.array_equal(goff, woff)
+        bad = np.nonzero(gd != wd)[0]
+        assert bad.size == 0, (seed, algo, bad[:5], gd[bad[:5]], wd[bad[:5]])
+        for i in np.nonzero(wd >= 0)[0]:
+            assert np.array_equal(ge[goff[i]:goff[i + 1]], we[woff[i]:woff[i + 1]]), (seed, algo, i)
+            assert zone[i] == zones.index(zone_of[wd[i]])
+            assert avg[i, 3] > 0.0
+        assert (zone[wd < 0] == -1).all()
+
+
+def test_zones_after_fifo_sees_charged_availability(oracle, packer):
+    """The efficiencies read the availability the FIFO batch left behind (node-table copy refreshed from the slots)."""
+    rng = np.random.default_rng(9)
+    n = 60
+    cpu = (rng.integers(8, 32, n) * 1000).astype(np.int64); mem = (rng.integers(16, 64, n) << 30).astype(np.int64); gpu = np.zeros(n, np.int64)
+    sc, sm, sg = cpu + 4000, mem + (8 << 30), gpu
+    zone_of = np.arange(n) % 3
+    names = node_names(n)
+    order = [int(i) for i in np.lexsort((np.arange(n), cpu, mem))]
+    zones, eo, do, eoff, doff = _zone_groups(order, order, zone_of)
+    queue = random_apps(rng, 40); queue["group"] = (np.arange(40) % len(zones)).astype(np.int32); queue["young"] = np.ones(40, np.uint8)
+    packer.set_snapshot(cpu, mem, gpu, eo, do, eoff, doff)
+    packer.pack_batch(queue, 0, 2)
+    fc, fm, fg = packer.get_snapshot()
+    assert not np.array_equal(fc, cpu)
+    packer.set_schedulable(sc, sm, sg)
+    mine = random_apps(rng, 60)
+    zone, gd, ge, goff, _ = packer.pack_batch_zones(mine, 0)
+    cl = oracle.Cluster(names, fc, fm, fg, sched=(sc, sm, sg), zone=["zone-%d" % z for z in zone_of])
+    drv = res_aos(mine["drv_cpu"], mine["drv_mem"], mine["drv_gpu"]); exe = res_aos(mine["exe_cpu"], mine["exe_mem"], mine["exe_gpu"])
+    wd, we, woff = cl.binpack_batch(2, drv, exe, mine["count"], [names[i] for i in order], [names[i] for i in order], with_efficiencies=True)
+    assert np.array_equal(gd, wd)
+    for i in np.nonzero(wd >= 0)[0]:
+        assert np.array_equal(ge[goff[i]:goff[i + 1]], we[woff[i]:woff[i + 1]])
