@@ -335,6 +335,31 @@ typedef struct {
 } gp_zone_results;
 gp_status gp_pack_batch_zones(gp_ctx* ctx, const gp_apps* apps /* group, skip_if_no_fit ignored */, gp_algo algo, gp_zone_results* out);
 
+/* ---- reservation table of a batch + a snapshot that stays on the device ---------------
+ * gp_reserve_placements: newResourceReservation (internal/extender/resourcereservations.go:491-528) for every application
+ * of a packed batch whose driver_node >= 0, as a flat SoA table the shim turns into ResourceReservation objects: one row
+ * per reservation slot -- slot 0 = "driver", slot i = "executor-i" (executorReservationName, :530-533) -> node index and
+ * the slot's resources; rows of one application are contiguous, applications in queue order.  With subtract_from_snapshot
+ * != 0 the same kernel takes every reserved pod off the availability the device holds (exact accounting, what
+ * UsageForNodes, LIB/resources/resources.go:31-43, adds up from these reservations on the next Predicate), so the next
+ * gp_pack_* call needs no gp_set_snapshot.
+ * gp_apply_usage_delta: reservations that appeared (sign = +1: availability goes down) or went away (sign = -1) since
+ * the snapshot was laid out -- the incremental form of GetReservedResources (resourcereservations.go:258-263). */
+typedef struct {
+    int64_t rows_cap;                /* rows the arrays below can hold; sum over placed apps of 1 + exe_count */
+    int32_t* app;                    /* [rows_cap] index of the application in the batch */
+    int32_t* slot;                   /* 0 = "driver", i = "executor-i" */
+    int32_t* node;                   /* Reservation.Node as node index */
+    int64_t* cpu_milli;              /* Reservation.Resources */
+    int64_t* mem_bytes;
+    int64_t* gpu;                    /* or NULL (not returned) */
+    int64_t n_rows;                  /* out */
+} gp_reservation_table;
+gp_status gp_reserve_placements(gp_ctx* ctx, const gp_apps* apps, const gp_results* placed /* host arrays of a previous gp_pack_batch */,
+                                int32_t subtract_from_snapshot, gp_reservation_table* out /* may be NULL with subtract */);
+gp_status gp_apply_usage_delta(gp_ctx* ctx, int64_t n_rows, const int32_t* node, const int64_t* cpu_milli, const int64_t* mem_bytes,
+                               const int64_t* gpu /* or NULL */, int32_t sign /* +1 reserve, -1 release */);
+
 /* ---- several GPUs of one box behind ONE host process -----------------------------------------------
  * The reference is a single process with a serial Predicate (internal/extender/resource.go:194-205); this handle lets
  * that process use every GPU: one gp_ctx + one worker thread per entry of `devices` (an ordinal may repeat).

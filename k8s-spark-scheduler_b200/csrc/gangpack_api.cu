@@ -213,7 +213,7 @@ __global__ void gp_build_driver_slots(int32_t n_drv, int32_t n_groups,
                                       const int32_t* __restrict__ drv_order,
                                       const int64_t* __restrict__ cpu, const int64_t* __restrict__ mem, const int64_t* __restrict__ gpu,
                                       longlong2* __restrict__ pair, int64_t* __restrict__ sgpu, int32_t* __restrict__ slot_node,
-                                      const int32_t* __restrict__ node_slot, int32_t* __restrict__ drv_slot, SnapMeta* __restrict__ meta) {
+                                      int32_t* __restrict__ node_slot, int32_t* __restrict__ drv_slot, SnapMeta* __restrict__ meta) {
     int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_drv || j >= drv_off[n_groups]) return;       // n_drv may be an upper bound
     int32_t g = find_group(drv_off, n_groups, j);
@@ -231,6 +231,7 @@ __global__ void gp_build_driver_slots(int32_t n_drv, int32_t n_groups,
         sgpu[slot] = gv;
         note_node(meta, cv, mv, gv);
         slot_node[slot] = node;
+        node_slot[node] = slot;          // the node's availability lives in its spare slot (gp_reserve_placements / gp_apply_usage_delta)
         drv_slot[j] = local;
     }
 }
@@ -1321,6 +1322,132 @@ gp_status gp_pack_batch_zones(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_zone
     if (out->avg_efficiency) GP_CUDA(c, cudaMemcpyAsync(out->avg_efficiency, b + o_avg, 32 * q, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaStreamSynchronize(st));
     return decode_device_error(c, *reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48));
+}
+
+// ---- reservation table + device-resident snapshot upkeep (gangpack_zones.cuh) -------------------------------------------
+static gp_status refresh_views(gp_ctx* c, bool raised, cudaStream_t st) {
+    const int T = 256;
+    if (c->n_slots <= 0) return GP_OK;
+    SnapMeta* meta = c->snap_flags.as<SnapMeta>();
+    if (raised)
+        gp_refresh_meta<<<(c->n_slots + T - 1) / T, T, 0, st>>>(c->n_slots, c->pair.as<longlong2>(), c->sgpu.as<long long>(), c->slot_node.as<int32_t>(),
+                                                               &meta->flags, meta->max_avail);
+    else   // availabilities only went down: a negative gpu value may have appeared
+        gp_refresh_meta<<<(c->n_slots + T - 1) / T, T, 0, st>>>(c->n_slots, c->pair.as<longlong2>(), c->sgpu.as<long long>(), c->slot_node.as<int32_t>(),
+                                                               &meta->flags, meta->max_avail);
+    gp_fill_pair32<<<(c->n_slots + T) / T, T, 0, st>>>(c->n_slots, c->pair.as<longlong2>(), meta, c->pair32.as<uint2>());
+    GP_CUDA(c, cudaGetLastError());
+    return GP_OK;
+}
+
+gp_status gp_reserve_placements(gp_ctx* c, const gp_apps* a, const gp_results* placed, int32_t subtract, gp_reservation_table* out) {
+    if (!c) return GP_ERR_INVALID;
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, "gp_reserve_placements: gp_set_snapshot first");
+    if (!a || !placed || a->n_apps < 0 || (!out && !subtract)) return fail(c, GP_ERR_INVALID, "gp_reserve_placements: NULL arguments");
+    const int32_t Q = a->n_apps;
+    if (out) out->n_rows = 0;
+    if (Q == 0) return GP_OK;
+    if (!a->drv_cpu_milli || !a->drv_mem_bytes || !a->exe_cpu_milli || !a->exe_mem_bytes || !a->exe_count || !placed->driver_node)
+        return fail(c, GP_ERR_INVALID, "gp_reserve_placements: missing app/result arrays");
+    // host pass: offsets, rows per placed application, index validation
+    std::vector<int64_t>& off = c->host_off;
+    off.resize(2 * ((size_t)Q + 1));
+    int64_t* roff = off.data() + Q + 1;
+    int64_t acc = 0, rows = 0;
+    for (int32_t i = 0; i < Q; ++i) {
+        const int64_t k = a->exe_count[i] > 0 ? a->exe_count[i] : 0;
+        off[(size_t)i] = a->exec_out_off ? a->exec_out_off[i] : acc;
+        acc += k;
+        roff[i] = rows;
+        const int32_t d = placed->driver_node[i];
+        if (d >= c->n_nodes) return fail(c, GP_ERR_INVALID, "gp_reserve_placements: driver_node out of range");
+        if (d >= 0) {
+            if (k > 0 && !placed->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_reserve_placements: executor_nodes is NULL");
+            if (off[(size_t)i] < 0 || off[(size_t)i] + k > placed->executor_nodes_cap) return fail(c, GP_ERR_CAPACITY, "gp_reserve_placements: offsets exceed executor_nodes_cap");
+            for (int64_t t = 0; t < k; ++t) {
+                const int32_t n = placed->executor_nodes[off[(size_t)i] + t];
+                if (n < 0 || n >= c->n_nodes) return fail(c, GP_ERR_INVALID, "gp_reserve_placements: executor node out of range");
+            }
+            rows += 1 + k;
+        }
+    }
+    off[(size_t)Q] = a->exec_out_off ? a->exec_out_off[Q] : acc;
+    roff[Q] = rows;
+    const int64_t total = placed->executor_nodes_cap < off[(size_t)Q] ? placed->executor_nodes_cap : off[(size_t)Q];
+    if (out && rows > out->rows_cap) return fail(c, GP_ERR_CAPACITY, "gp_reserve_placements: rows_cap too small");
+    if (out && rows > 0 && (!out->app || !out->slot || !out->node || !out->cpu_milli || !out->mem_bytes))
+        return fail(c, GP_ERR_INVALID, "gp_reserve_placements: missing table arrays");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t q = (size_t)Q, T = (size_t)(total > 0 ? total : 0), R = (size_t)rows;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t o_in = take(48 * q), o_cnt = take(4 * q), o_off = take(8 * (q + 1)), o_roff = take(8 * (q + 1)), o_drv = take(4 * q), o_exe = take(4 * (T + 1)),
+                 o_ra = take(4 * (R + 1)), o_rs = take(4 * (R + 1)), o_rn = take(4 * (R + 1)), o_rc = take(8 * (R + 1)), o_rm = take(8 * (R + 1)), o_rg = take(8 * (R + 1));
+    GP_CUDA(c, c->zonebuf.reserve(o));
+    char* b = c->zonebuf.as<char>();
+    const int64_t* hc[6] = {a->drv_cpu_milli, a->drv_mem_bytes, a->drv_gpu, a->exe_cpu_milli, a->exe_mem_bytes, a->exe_gpu};
+    ReserveIn ri{};
+    for (int k = 0; k < 6; ++k) {
+        if (!hc[k]) continue;
+        GP_CUDA(c, cudaMemcpyAsync(b + o_in + 8 * q * (size_t)k, hc[k], 8 * q, cudaMemcpyHostToDevice, st));
+        ri.cols.p[k] = reinterpret_cast<const int64_t*>(b + o_in + 8 * q * (size_t)k);
+    }
+    GP_CUDA(c, cudaMemcpyAsync(b + o_cnt, a->exe_count, 4 * q, cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(b + o_off, off.data(), 8 * (q + 1), cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(b + o_roff, roff, 8 * (q + 1), cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(b + o_drv, placed->driver_node, 4 * q, cudaMemcpyHostToDevice, st));
+    if (T) GP_CUDA(c, cudaMemcpyAsync(b + o_exe, placed->executor_nodes, 4 * T, cudaMemcpyHostToDevice, st));
+    ri.count = (const int32_t*)(b + o_cnt); ri.off = (const int64_t*)(b + o_off); ri.row_off = (const int64_t*)(b + o_roff);
+    ri.driver = (const int32_t*)(b + o_drv); ri.exec = (const int32_t*)(b + o_exe); ri.n_apps = Q; ri.subtract = subtract ? 1 : 0;
+    ReserveOut ro{(int32_t*)(b + o_ra), (int32_t*)(b + o_rs), (int32_t*)(b + o_rn), (long long*)(b + o_rc), (long long*)(b + o_rm), (long long*)(b + o_rg)};
+    const int TH = 256;
+    gp_reserve_rows<<<(unsigned)((q * 32 + TH - 1) / TH), TH, 0, st>>>(ri, ro, c->node_slot.as<int32_t>(), c->pair.as<longlong2>(), c->sgpu.as<long long>(),
+                                                                        c->node_cpu.as<long long>(), c->node_mem.as<long long>(), c->node_gpu.as<long long>());
+    GP_CUDA(c, cudaGetLastError());
+    if (subtract) { gp_status s = refresh_views(c, false, st); if (s != GP_OK) return s; }
+    if (out && R) {
+        GP_CUDA(c, cudaMemcpyAsync(out->app, ro.app, 4 * R, cudaMemcpyDeviceToHost, st));
+        GP_CUDA(c, cudaMemcpyAsync(out->slot, ro.slot, 4 * R, cudaMemcpyDeviceToHost, st));
+        GP_CUDA(c, cudaMemcpyAsync(out->node, ro.node, 4 * R, cudaMemcpyDeviceToHost, st));
+        GP_CUDA(c, cudaMemcpyAsync(out->cpu_milli, ro.cpu, 8 * R, cudaMemcpyDeviceToHost, st));
+        GP_CUDA(c, cudaMemcpyAsync(out->mem_bytes, ro.mem, 8 * R, cudaMemcpyDeviceToHost, st));
+        if (out->gpu) GP_CUDA(c, cudaMemcpyAsync(out->gpu, ro.gpu, 8 * R, cudaMemcpyDeviceToHost, st));
+    }
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    if (out) out->n_rows = rows;
+    return GP_OK;
+}
+
+gp_status gp_apply_usage_delta(gp_ctx* c, int64_t n_rows, const int32_t* node, const int64_t* cpu, const int64_t* mem, const int64_t* gpu, int32_t sign) {
+    if (!c) return GP_ERR_INVALID;
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, "gp_apply_usage_delta: gp_set_snapshot first");
+    if (n_rows < 0 || (sign != 1 && sign != -1) || (n_rows > 0 && (!node || !cpu || !mem))) return fail(c, GP_ERR_INVALID, "gp_apply_usage_delta: bad arguments");
+    if (n_rows == 0) return GP_OK;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t v[3] = {cpu[r], mem[r], gpu ? gpu[r] : 0};
+        for (int64_t x : v) if (x >= kMaxQuantity || x <= -kMaxQuantity) return fail(c, GP_ERR_UNREPRESENTABLE, "gp_apply_usage_delta: |quantity| >= 2^61");
+    }
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t R = (size_t)n_rows;
+    GP_CUDA(c, c->zonebuf.reserve(28 * R + 1024));
+    char* b = c->zonebuf.as<char>();
+    const size_t o_c = 0, o_m = 8 * R, o_g = 16 * R, o_n = 24 * R;
+    GP_CUDA(c, cudaMemcpyAsync(b + o_c, cpu, 8 * R, cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(b + o_m, mem, 8 * R, cudaMemcpyHostToDevice, st));
+    if (gpu) GP_CUDA(c, cudaMemcpyAsync(b + o_g, gpu, 8 * R, cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(b + o_n, node, 4 * R, cudaMemcpyHostToDevice, st));
+    const int TH = 256;
+    gp_usage_delta<<<(unsigned)((R + TH - 1) / TH), TH, 0, st>>>(n_rows, (const int32_t*)(b + o_n), (const long long*)(b + o_c), (const long long*)(b + o_m),
+                                                                  gpu ? (const long long*)(b + o_g) : nullptr, sign, c->n_nodes, c->node_slot.as<int32_t>(),
+                                                                  c->pair.as<longlong2>(), c->sgpu.as<long long>(), c->node_cpu.as<long long>(),
+                                                                  c->node_mem.as<long long>(), c->node_gpu.as<long long>());
+    GP_CUDA(c, cudaGetLastError());
+    gp_status s = refresh_views(c, sign < 0, st);
+    if (s != GP_OK) return s;
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    return GP_OK;
 }
 
 // ---- node priority order (f1) and availability snapshot (f2): device stages + the entries built on them ----

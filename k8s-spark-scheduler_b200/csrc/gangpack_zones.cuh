@@ -141,4 +141,84 @@ __global__ void gp_zone_expand(int32_t n_apps, int32_t Z, SixCols src,
     roff[r] = (int64_t)Z * off[app] + (int64_t)z * (k > 0 ? k : 0);
 }
 
+// ---- reservation table of a batch of placements + the device-resident snapshot kept current ----
+// newResourceReservation (internal/extender/resourcereservations.go:491-528): reservations["driver"] = {driver node, driver
+// resources}, reservations["executor-<i>"] = {ExecutorNodes[i-1], executor resources} (executorReservationName, :530-533).
+// One warp per placed application writes its 1 + k rows (slot 0 = "driver", slot i = "executor-i") and, when asked to,
+// subtracts every pod from the availability the device keeps -- what UsageForNodes (LIB/resources/resources.go:31-43) will
+// add up from these very reservations on the next Predicate.  Integer adds commute: atomics are exact.
+struct ReserveIn {
+    SixCols cols;                     // int64 device columns of the applications
+    const int32_t* count;
+    const int64_t* off;               // ExecutorNodes offsets
+    const int64_t* row_off;           // first row of each application (placed ones only advance it)
+    const int32_t* driver;
+    const int32_t* exec;
+    int32_t n_apps;
+    int32_t subtract;
+};
+struct ReserveOut { int32_t* app; int32_t* slot; int32_t* node; long long* cpu; long long* mem; long long* gpu; };
+
+__device__ __forceinline__ void charge_node(int32_t node, long long c, long long m, long long g, const int32_t* __restrict__ node_slot,
+                                            longlong2* pair, long long* sgpu, long long* ncpu, long long* nmem, long long* ngpu) {
+    const int32_t sl = node_slot[node];
+    if (sl >= 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&pair[sl].x), (unsigned long long)(-c));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&pair[sl].y), (unsigned long long)(-m));
+        if (g != 0) atomicAdd(reinterpret_cast<unsigned long long*>(sgpu + sl), (unsigned long long)(-g));
+    } else {                          // a node outside every order lives in the node-table copy only
+        atomicAdd(reinterpret_cast<unsigned long long*>(ncpu + node), (unsigned long long)(-c));
+        atomicAdd(reinterpret_cast<unsigned long long*>(nmem + node), (unsigned long long)(-m));
+        if (g != 0) atomicAdd(reinterpret_cast<unsigned long long*>(ngpu + node), (unsigned long long)(-g));
+    }
+}
+
+__global__ void __launch_bounds__(256) gp_reserve_rows(ReserveIn in, ReserveOut out, const int32_t* __restrict__ node_slot, longlong2* pair,
+                                                       long long* sgpu, long long* ncpu, long long* nmem, long long* ngpu) {
+    const int lane = threadIdx.x & 31;
+    const int32_t i = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (i >= in.n_apps) return;
+    const int32_t d = in.driver[i];
+    if (d < 0) return;
+    const int32_t k = in.count[i] > 0 ? in.count[i] : 0;
+    const int64_t r0 = in.row_off[i];
+    const long long dc = in.cols.p[0][i], dm = in.cols.p[1][i], dg = in.cols.p[2] ? in.cols.p[2][i] : 0;
+    const long long ec = in.cols.p[3][i], em = in.cols.p[4][i], eg = in.cols.p[5] ? in.cols.p[5][i] : 0;
+    if (lane == 0) {
+        out.app[r0] = i; out.slot[r0] = 0; out.node[r0] = d; out.cpu[r0] = dc; out.mem[r0] = dm; out.gpu[r0] = dg;
+        if (in.subtract) charge_node(d, dc, dm, dg, node_slot, pair, sgpu, ncpu, nmem, ngpu);
+    }
+    const int32_t* ex = in.exec + in.off[i];
+    for (int32_t t = lane; t < k; t += 32) {
+        const int64_t r = r0 + 1 + t;
+        const int32_t n = ex[t];
+        out.app[r] = i; out.slot[r] = t + 1; out.node[r] = n; out.cpu[r] = ec; out.mem[r] = em; out.gpu[r] = eg;
+        if (in.subtract) charge_node(n, ec, em, eg, node_slot, pair, sgpu, ncpu, nmem, ngpu);
+    }
+}
+
+// availability[node] -= sign * (cpu, mem, gpu) for a list of (node, resources) rows: reservations that appeared (sign +1)
+// or went away (sign -1) since the snapshot was laid out.  Keeps SnapMeta::max_avail an upper bound.
+__global__ void gp_usage_delta(int64_t n_rows, const int32_t* __restrict__ node, const long long* __restrict__ cpu, const long long* __restrict__ mem,
+                               const long long* __restrict__ gpu, int sign, int32_t n_nodes, const int32_t* __restrict__ node_slot, longlong2* pair,
+                               long long* sgpu, long long* ncpu, long long* nmem, long long* ngpu) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int32_t n = node[r];
+    if (n < 0 || n >= n_nodes) return;           // a reservation on a node that left: ignored (resources.go:67-75)
+    charge_node(n, sign * cpu[r], sign * mem[r], gpu ? sign * gpu[r] : 0, node_slot, pair, sgpu, ncpu, nmem, ngpu);
+}
+// after a delta that may have RAISED availabilities: refresh the per-dimension maxima and the negative-gpu flag
+__global__ void gp_refresh_meta(int32_t n_slots, const longlong2* __restrict__ pair, const long long* __restrict__ sgpu, const int32_t* __restrict__ slot_node,
+                                int* flags, long long* max_avail) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots || slot_node[s] < 0) return;
+    const longlong2 v = pair[s];
+    const long long g = sgpu[s];
+    if (v.x > max_avail[0]) atomicMax(max_avail + 0, v.x);
+    if (v.y > max_avail[1]) atomicMax(max_avail + 1, v.y);
+    if (g > max_avail[2]) atomicMax(max_avail + 2, g);
+    if (g < 0) atomicOr(flags, 1);
+}
+
 }  // namespace gp

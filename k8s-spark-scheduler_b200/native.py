@@ -35,7 +35,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 
 # every symbol include/gangpack.h declares (tests assert the .so exports exactly these)
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
-           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one", "gp_set_schedulable", "gp_pack_batch_zones",
+           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one", "gp_set_schedulable", "gp_pack_batch_zones", "gp_reserve_placements", "gp_apply_usage_delta",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
            "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors",
            "gp_multi_create", "gp_multi_destroy", "gp_multi_last_error", "gp_multi_size", "gp_multi_ctx",
@@ -100,6 +100,11 @@ class gp_results_wire(C.Structure):
 class gp_zone_results(C.Structure):
     _fields_ = [("zone", C.c_void_p), ("driver_node", C.c_void_p), ("executor_nodes", C.c_void_p), ("executor_nodes_cap", C.c_int64),
                 ("avg_efficiency", C.c_void_p)]
+
+
+class gp_reservation_table(C.Structure):
+    _fields_ = [("rows_cap", C.c_int64), ("app", C.c_void_p), ("slot", C.c_void_p), ("node", C.c_void_p), ("cpu_milli", C.c_void_p),
+                ("mem_bytes", C.c_void_p), ("gpu", C.c_void_p), ("n_rows", C.c_int64)]
 
 
 class gp_results(C.Structure):
@@ -175,6 +180,10 @@ def load():
     L.gp_set_schedulable.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_pack_batch_zones.restype = C.c_int
     L.gp_pack_batch_zones.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.POINTER(gp_zone_results)]
+    L.gp_reserve_placements.restype = C.c_int
+    L.gp_reserve_placements.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.POINTER(gp_results), C.c_int32, C.POINTER(gp_reservation_table)]
+    L.gp_apply_usage_delta.restype = C.c_int
+    L.gp_apply_usage_delta.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.gp_pack_one.restype = C.c_int
     L.gp_pack_one.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 6 + [C.c_int32, C.POINTER(C.c_int32),
                                                                           C.POINTER(C.c_int32), C.c_void_p]
@@ -490,6 +499,30 @@ class GangPacker:
         r = gp_zone_results(zone=_p(zone), driver_node=_p(drv), executor_nodes=_p(exe), executor_nodes_cap=len(exe), avg_efficiency=_p(avg))
         self._check(load().gp_pack_batch_zones(self._h, C.byref(a), algo, C.byref(r)))
         return zone, drv, exe[:total], off, avg[:q]
+
+    def reserve_placements(self, apps: dict, placed, subtract=True):
+        """newResourceReservation for a packed batch -> dict of row arrays (app, slot, node, cpu, mem, gpu); with subtract the
+        device-resident snapshot is charged with every reserved pod.  placed = (driver_node, executor_nodes, off)."""
+        q = len(apps["count"])
+        count = _np(apps["count"], np.int32)
+        driver, execn, off = placed
+        driver = _np(driver, np.int32); execn = _np(execn, np.int32); off = _np(off, np.int64)
+        arrs = {k: _np(apps.get(k), np.int64) for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}
+        rows = int(((driver >= 0) * (1 + np.maximum(count, 0).astype(np.int64))).sum()) if q else 0
+        t = {k: np.zeros(max(rows, 1), np.int32) for k in ("app", "slot", "node")}
+        t.update({k: np.zeros(max(rows, 1), np.int64) for k in ("cpu", "mem", "gpu")})
+        a = gp_apps(n_apps=q, drv_cpu_milli=_p(arrs["drv_cpu"]), drv_mem_bytes=_p(arrs["drv_mem"]), drv_gpu=_p(arrs["drv_gpu"]),
+                    exe_cpu_milli=_p(arrs["exe_cpu"]), exe_mem_bytes=_p(arrs["exe_mem"]), exe_gpu=_p(arrs["exe_gpu"]),
+                    exe_count=_p(count), group=None, skip_if_no_fit=None, exec_out_off=_p(off))
+        r = gp_results(driver_node=_p(driver), executor_nodes=_p(execn), executor_nodes_cap=len(execn))
+        tab = gp_reservation_table(rows_cap=len(t["app"]), app=_p(t["app"]), slot=_p(t["slot"]), node=_p(t["node"]),
+                                   cpu_milli=_p(t["cpu"]), mem_bytes=_p(t["mem"]), gpu=_p(t["gpu"]), n_rows=0)
+        self._check(load().gp_reserve_placements(self._h, C.byref(a), C.byref(r), 1 if subtract else 0, C.byref(tab)))
+        return {k: v[:tab.n_rows] for k, v in t.items()}
+
+    def apply_usage_delta(self, node, cpu, mem, gpu=None, sign=1):
+        n, c, m, g = _np(node, np.int32), _np(cpu, np.int64), _np(mem, np.int64), _np(gpu, np.int64)
+        self._check(load().gp_apply_usage_delta(self._h, len(n), _p(n), _p(c), _p(m), _p(g), sign))
 
     def pack_one(self, algo, drv, exe, count):
         """binpack.SparkBinPackFunction for one app -> (has_capacity, driver_node, executor_nodes)."""

@@ -98,3 +98,53 @@ def test_zones_after_fifo_sees_charged_availability(oracle, packer):
     assert np.array_equal(gd, wd)
     for i in np.nonzero(wd >= 0)[0]:
         assert np.array_equal(ge[goff[i]:goff[i + 1]], we[woff[i]:woff[i + 1]])
+
+
+def test_reservation_table_and_resident_snapshot(oracle, packer):
+    """gp_reserve_placements = newResourceReservation (resourcereservations.go:491-528) for a batch + exact charging of the
+    device-resident snapshot; gp_apply_usage_delta releases / adds reservations.  Rows: slot 0 = "driver" on DriverNode with
+    the driver's resources, slot i = "executor-i" on ExecutorNodes[i-1] with the executor's resources.  The availability
+    the device then holds equals allocatable - UsageForNodes(reservations) (resources.go:31-43), and a following batch packs
+    against it like the oracle does on the recomputed availability."""
+    import k8s_spark_scheduler_b200.synth as synth
+    nodes = synth.make_nodes(800)
+    order = synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"])
+    drv_order = order[: 500]                                   # some executor candidates are no driver candidates ...
+    exe_order = order[100:]                                    # ... and vice versa (spare driver slots)
+    apps = synth.make_apps(300, seed=3)
+    KEYS = ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu", "count")
+    a = {k: apps[k] for k in KEYS}
+    packer.set_snapshot(nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], exe_order, drv_order)
+    placed = packer.pack_batch(a, 0, 0)
+    # independent decisions may overcommit a node between them: reserving all of them is still well defined (negative availability)
+    rows = packer.reserve_placements(a, placed, subtract=True)
+    dn, en, off = placed
+    exp = []
+    for i in range(300):
+        if dn[i] < 0:
+            continue
+        exp.append((i, 0, dn[i], a["drv_cpu"][i], a["drv_mem"][i], a["drv_gpu"][i]))
+        for t in range(a["count"][i]):
+            exp.append((i, t + 1, en[off[i] + t], a["exe_cpu"][i], a["exe_mem"][i], a["exe_gpu"][i]))
+    exp = np.array(exp, np.int64)
+    got = np.stack([rows[k].astype(np.int64) for k in ("app", "slot", "node", "cpu", "mem", "gpu")], axis=1)
+    assert np.array_equal(got, exp)
+    use_c = np.zeros(800, np.int64); use_m = np.zeros(800, np.int64)
+    np.add.at(use_c, exp[:, 2], exp[:, 3]); np.add.at(use_m, exp[:, 2], exp[:, 4])
+    fc, fm, fg = packer.get_snapshot()
+    assert np.array_equal(fc, nodes["avail_cpu"] - use_c) and np.array_equal(fm, nodes["avail_mem"] - use_m)
+    # the next batch packs against the charged snapshot without gp_set_snapshot
+    nxt = synth.make_apps(200, seed=4)
+    b = {k: nxt[k] for k in KEYS}
+    from helpers import res_aos, assert_same_results
+    for algo in (0, 1):
+        got2 = packer.pack_batch(b, algo, 0)
+        _, wd, we, woff, _ = oracle.closed_batch(algo, 0, fc, fm, fg, drv_order, exe_order, res_aos(b["drv_cpu"], b["drv_mem"], b["drv_gpu"]),
+                                                 res_aos(b["exe_cpu"], b["exe_mem"], b["exe_gpu"]), b["count"], None, n_threads=4)
+        assert_same_results(got2, (wd, we, woff), f"after reserve algo {algo}")
+    # releasing every reservation restores the original availability, bit for bit
+    packer.apply_usage_delta(exp[:, 2], exp[:, 3], exp[:, 4], exp[:, 5], sign=-1)
+    rc, rm, rg = packer.get_snapshot()
+    assert np.array_equal(rc, nodes["avail_cpu"]) and np.array_equal(rm, nodes["avail_mem"])
+    got3 = packer.pack_batch(a, 0, 0)
+    assert_same_results(got3, placed, "after release")
