@@ -179,6 +179,15 @@ gp_status gp_build_availability(gp_ctx* ctx, const gp_usage_input* in,
                                 int64_t* avail_cpu_milli, int64_t* avail_mem_bytes, int64_t* avail_gpu,
                                 int64_t* sched_cpu_milli, int64_t* sched_mem_bytes, int64_t* sched_gpu);
 
+/* availableResources of rescheduleExecutor's FIRST-FIT branch (internal/extender/resource.go:638-643), bug for bug: the
+ * reference calls NodeSchedulingMetadataForNodes(availableNodes, usage, overhead) -- which adds the overhead into the usage
+ * map's EXISTING entries in place (resources.go:72-76) -- and then usage.Add(overhead) once more, so
+ *   available[n] = allocatable[n] - (sum of reservations on n + overhead[n] * (n carries a reservation ? 2 : 1))
+ * (SURVEY App. B7).  This is the availability to upload with gp_set_snapshot before gp_reschedule_executors(min_frag = 0);
+ * the minimal-fragmentation branch uses the plain gp_build_availability output (:640, :682). */
+gp_status gp_build_reschedule_availability(gp_ctx* ctx, const gp_usage_input* in,
+                                           int64_t* avail_cpu_milli, int64_t* avail_mem_bytes, int64_t* avail_gpu);
+
 /* ---- node priority order (the step before the hot path) ------------------- */
 /* NodeSorter.PotentialNodes (internal/sort/nodesorting.go:41-64) on the device: nodes in ascending
  * (AZ priority, available memory, available CPU, name) order (:83-122), split into the driver candidates

@@ -1454,13 +1454,15 @@ gp_status gp_apply_usage_delta(gp_ctx* c, int64_t n_rows, const int32_t* node, c
 }  // extern "C"
 
 // f2 stage: uploads the inputs, leaves avail[3][N] / sched[3][N] on the device (usagebuf).
-static gp_status stage_availability(gp_ctx* c, const gp_usage_input* in, cudaStream_t st, long long** d_avail, long long** d_sched) {
+static gp_status stage_availability(gp_ctx* c, const gp_usage_input* in, cudaStream_t st, long long** d_avail, long long** d_sched,
+                                    long long** d_resched = nullptr) {
     const int32_t n = in->n_nodes;
     const size_t N = (size_t)n, R = (size_t)in->n_reservations;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_alloc = take(24 * N), o_over = take(24 * N), o_usage = take(24 * N), o_avail = take(24 * N), o_sched = take(24 * N),
-                 o_rn = take(4 * R), o_rc = take(8 * R), o_rm = take(8 * R), o_rg = take(8 * R);
+    const size_t o_alloc = take(24 * N), o_over = take(24 * N), o_usage = take(24 * N + 4 * N), o_avail = take(24 * N), o_sched = take(24 * N),
+                 o_resched = take(24 * N), o_rn = take(4 * R), o_rc = take(8 * R), o_rm = take(8 * R), o_rg = take(8 * R);
+    const size_t o_has = o_usage + 24 * N;      // zeroed together with the usage sums
     GP_CUDA(c, c->usagebuf.reserve(off));
     char* b = c->usagebuf.as<char>();
     auto up = [&](size_t o, const void* src, size_t bytes) { return cudaMemcpyAsync(b + o, src, bytes, cudaMemcpyHostToDevice, st); };
@@ -1470,7 +1472,7 @@ static gp_status stage_availability(gp_ctx* c, const gp_usage_input* in, cudaStr
     if (in->overhead_cpu_milli) GP_CUDA(c, up(o_over, in->overhead_cpu_milli, 8 * N));
     if (in->overhead_mem_bytes) GP_CUDA(c, up(o_over + 8 * N, in->overhead_mem_bytes, 8 * N));
     if (in->overhead_gpu) GP_CUDA(c, up(o_over + 16 * N, in->overhead_gpu, 8 * N));
-    GP_CUDA(c, cudaMemsetAsync(b + o_usage, 0, 24 * N, st));
+    GP_CUDA(c, cudaMemsetAsync(b + o_usage, 0, 28 * N, st));
     const int T = 256;
     if (R) {
         GP_CUDA(c, up(o_rn, in->res_node, 4 * R));
@@ -1479,13 +1481,15 @@ static gp_status stage_availability(gp_ctx* c, const gp_usage_input* in, cudaStr
         if (in->res_gpu) GP_CUDA(c, up(o_rg, in->res_gpu, 8 * R));
         gp_usage_scatter<<<(unsigned)((R + T - 1) / T), T, 0, st>>>((long long)R, (const int32_t*)(b + o_rn), (const long long*)(b + o_rc),
                                                                    (const long long*)(b + o_rm), in->res_gpu ? (const long long*)(b + o_rg) : nullptr,
-                                                                   n, (unsigned long long*)(b + o_usage));
+                                                                   n, (unsigned long long*)(b + o_usage), d_resched ? (unsigned int*)(b + o_has) : nullptr);
     }
     const long long* al = (const long long*)(b + o_alloc);
     const long long* ov = (const long long*)(b + o_over);
     gp_availability<<<(n + T - 1) / T, T, 0, st>>>(n, al, al + N, in->alloc_gpu ? al + 2 * N : nullptr, in->overhead_cpu_milli ? ov : nullptr,
                                                    in->overhead_mem_bytes ? ov + N : nullptr, in->overhead_gpu ? ov + 2 * N : nullptr,
-                                                   (const unsigned long long*)(b + o_usage), (long long*)(b + o_avail), (long long*)(b + o_sched));
+                                                   (const unsigned long long*)(b + o_usage), (long long*)(b + o_avail), (long long*)(b + o_sched),
+                                                   (const unsigned int*)(b + o_has), d_resched ? (long long*)(b + o_resched) : nullptr);
+    if (d_resched) *d_resched = (long long*)(b + o_resched);
     GP_CUDA(c, cudaGetLastError());
     *d_avail = (long long*)(b + o_avail);
     *d_sched = (long long*)(b + o_sched);
@@ -1614,6 +1618,27 @@ gp_status gp_build_availability(gp_ctx* c, const gp_usage_input* in, int64_t* av
     int64_t* outs[6] = {avail_cpu, avail_mem, avail_gpu, sched_cpu, sched_mem, sched_gpu};
     for (int k = 0; k < 6; ++k)
         if (outs[k]) GP_CUDA(c, cudaMemcpyAsync(outs[k], (k < 3 ? d_avail : d_sched) + N * (size_t)(k % 3), 8 * N, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    return GP_OK;
+}
+
+// availableResources of rescheduleExecutor's first-fit branch: the availability to upload before gp_reschedule_executors(min_frag = 0)
+gp_status gp_build_reschedule_availability(gp_ctx* c, const gp_usage_input* in, int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu) {
+    if (!c) return GP_ERR_INVALID;
+    if (!in || in->n_nodes < 0 || in->n_reservations < 0 || (in->n_nodes > 0 && (!in->alloc_cpu_milli || !in->alloc_mem_bytes)) ||
+        (in->n_reservations > 0 && (!in->res_node || !in->res_cpu_milli || !in->res_mem_bytes)))
+        return fail(c, GP_ERR_INVALID, "gp_build_reschedule_availability: missing arrays or bad sizes");
+    const int32_t n = in->n_nodes;
+    if (n == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    long long *d_avail = nullptr, *d_sched = nullptr, *d_re = nullptr;
+    gp_status s = stage_availability(c, in, st, &d_avail, &d_sched, &d_re);
+    if (s != GP_OK) return s;
+    const size_t N = (size_t)n;
+    int64_t* outs[3] = {avail_cpu, avail_mem, avail_gpu};
+    for (int k = 0; k < 3; ++k)
+        if (outs[k]) GP_CUDA(c, cudaMemcpyAsync(outs[k], d_re + N * (size_t)k, 8 * N, cudaMemcpyDeviceToHost, st));
     GP_CUDA(c, cudaStreamSynchronize(st));
     return GP_OK;
 }

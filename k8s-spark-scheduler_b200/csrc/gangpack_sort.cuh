@@ -228,11 +228,12 @@ __global__ void gp_label_scatter(const int32_t* __restrict__ count_ptr, const in
 // (reservation -> node) pairs: thread per reservation, 64-bit atomics (integer adds commute: exact).
 __global__ void gp_usage_scatter(long long n_res, const int32_t* __restrict__ res_node, const long long* __restrict__ res_cpu,
                                  const long long* __restrict__ res_mem, const long long* __restrict__ res_gpu, int32_t n_nodes,
-                                 unsigned long long* __restrict__ usage /* [3][n_nodes] */) {
+                                 unsigned long long* __restrict__ usage /* [3][n_nodes] */, unsigned int* __restrict__ has_entry /* [n_nodes] or NULL */) {
     const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (r >= n_res) return;
     const int32_t node = res_node[r];
     if (node < 0 || node >= n_nodes) return;            // reservation on a node that is not in the list: ignored (:67-75)
+    if (has_entry) has_entry[node] = 1u;                // the usage map has an entry for this node (whatever its value)
     atomicAdd(usage + node, (unsigned long long)res_cpu[r]);
     atomicAdd(usage + n_nodes + node, (unsigned long long)res_mem[r]);
     if (res_gpu) atomicAdd(usage + 2 * (size_t)n_nodes + node, (unsigned long long)res_gpu[r]);
@@ -244,7 +245,8 @@ __global__ void gp_availability(int32_t n, const long long* __restrict__ alloc_c
                                 const long long* __restrict__ alloc_gpu, const long long* __restrict__ over_cpu,
                                 const long long* __restrict__ over_mem, const long long* __restrict__ over_gpu,
                                 const unsigned long long* __restrict__ usage, long long* __restrict__ avail /* [3][n] */,
-                                long long* __restrict__ sched /* [3][n] */) {
+                                long long* __restrict__ sched /* [3][n] */, const unsigned int* __restrict__ has_entry = nullptr,
+                                long long* __restrict__ resched /* [3][n] or NULL */ = nullptr) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long a[3] = {alloc_cpu[i], alloc_mem[i], alloc_gpu ? alloc_gpu[i] : 0};
@@ -254,6 +256,9 @@ __global__ void gp_availability(int32_t n, const long long* __restrict__ alloc_c
         const long long u = (long long)usage[(size_t)d * n + i];
         avail[(size_t)d * n + i] = a[d] - (u + o[d]);
         sched[(size_t)d * n + i] = a[d] - o[d];
+        // availableResources of rescheduleExecutor (EXT/resource.go:638-643): NodeSchedulingMetadataForNodes has already added
+        // the overhead into the usage map's EXISTING entries in place when usage.Add(overhead) adds it again
+        if (resched) resched[(size_t)d * n + i] = a[d] - (u + o[d] * (has_entry[i] ? 2 : 1));
     }
 }
 

@@ -37,7 +37,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
            "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one", "gp_set_schedulable", "gp_pack_batch_zones", "gp_reserve_placements", "gp_apply_usage_delta",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
-           "gp_potential_nodes", "gp_build_availability", "gp_prepare_cluster", "gp_reschedule_executors",
+           "gp_potential_nodes", "gp_build_availability", "gp_build_reschedule_availability", "gp_prepare_cluster", "gp_reschedule_executors",
            "gp_multi_create", "gp_multi_destroy", "gp_multi_last_error", "gp_multi_size", "gp_multi_ctx",
            "gp_multi_set_snapshot", "gp_multi_pack_batch", "gp_multi_get_snapshot", "gp_multi_group_owner"]
 
@@ -199,6 +199,8 @@ def load():
     L.gp_last_stats.argtypes = [C.c_void_p, C.POINTER(gp_stats)]
     L.gp_build_availability.restype = C.c_int
     L.gp_build_availability.argtypes = [C.c_void_p, C.POINTER(gp_usage_input)] + [C.c_void_p] * 6
+    L.gp_build_reschedule_availability.restype = C.c_int
+    L.gp_build_reschedule_availability.argtypes = [C.c_void_p, C.POINTER(gp_usage_input)] + [C.c_void_p] * 3
     L.gp_prepare_cluster.restype = C.c_int
     L.gp_prepare_cluster.argtypes = [C.c_void_p, C.POINTER(gp_usage_input), C.POINTER(gp_sort_input), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32)]
@@ -385,6 +387,20 @@ class GangPacker:
         outs = [np.empty(max(n, 1), np.int64) for _ in range(6)]
         self._check(load().gp_build_availability(self._h, C.byref(ui), *[_p(o) for o in outs]))
         return [o[:n] for o in outs[:3]], [o[:n] for o in outs[3:]]
+
+    def build_reschedule_availability(self, alloc, overhead, res_node, res):
+        """availableResources of rescheduleExecutor's first-fit branch (overhead counted twice on nodes with reservations)."""
+        al = [_np(x, np.int64) for x in alloc]
+        ov = [_np(x, np.int64) for x in overhead] if overhead is not None else [None] * 3
+        rn = _np(res_node, np.int32)
+        rs = [_np(x, np.int64) for x in res]
+        n = len(al[0])
+        ui = gp_usage_input(n_nodes=n, alloc_cpu_milli=_p(al[0]), alloc_mem_bytes=_p(al[1]), alloc_gpu=_p(al[2]),
+                            overhead_cpu_milli=_p(ov[0]), overhead_mem_bytes=_p(ov[1]), overhead_gpu=_p(ov[2]),
+                            n_reservations=len(rn), res_node=_p(rn), res_cpu_milli=_p(rs[0]), res_mem_bytes=_p(rs[1]), res_gpu=_p(rs[2]))
+        outs = [np.empty(max(n, 1), np.int64) for _ in range(3)]
+        self._check(load().gp_build_reschedule_availability(self._h, C.byref(ui), *[_p(o) for o in outs]))
+        return [o[:n] for o in outs]
 
     def prepare_cluster(self, alloc, overhead, res_node, res, zone_id=None, n_zones=1, name_rank=None, is_driver_candidate=None,
                         unschedulable=None, ready=None, driver_label_rank=None, executor_label_rank=None):

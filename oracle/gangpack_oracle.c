@@ -770,6 +770,49 @@ void orc_node_scheduling_metadata(int32_t n_nodes, const char* const* names,
     resmap_free(&usage);
 }
 
+/* availableResources of rescheduleExecutor's first-fit branch (EXT/resource.go:638-643), statement by statement:
+ *   usage := GetReservedResources()                                             :638
+ *   availableNodesSchedulingMetadata := NodeSchedulingMetadataForNodes(availableNodes, usage, overhead)   :640
+ *        -- which ADDS the overhead into usage's existing entries in place (resources.go:72-76: currentUsageForNode is the
+ *           map's own *Resources when the node has an entry, a fresh Zero() otherwise)
+ *   usage.Add(overhead)                                                         :642  (creates missing entries)
+ *   availableResources := AvailableForNodes(availableNodes, usage)              :643
+ * => nodes that carry at least one reservation lose their overhead TWICE. */
+void orc_reschedule_available(int32_t n_nodes, const char* const* names,
+                              const int64_t* alloc_cpu, const int64_t* alloc_mem, const int64_t* alloc_gpu,
+                              const int64_t* over_cpu, const int64_t* over_mem, const int64_t* over_gpu,
+                              int64_t n_res, const char* const* res_node_name,
+                              const int64_t* res_cpu, const int64_t* res_mem, const int64_t* res_gpu,
+                              int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu) {
+    static const orc_res zero = {0, 0, 0};
+    resmap usage;
+    resmap_init(&usage, n_nodes);
+    for (int64_t r = 0; r < n_res; ++r) {                      /* GetReservedResources: UsageForNodes + soft reservations */
+        orc_res* u = resmap_get(&usage, res_node_name[r]);
+        if (u == NULL) u = resmap_put(&usage, res_node_name[r], &zero);
+        orc_res add = {res_cpu[r], res_mem[r], res_gpu ? res_gpu[r] : 0};
+        res_add(u, &add);
+    }
+    for (int32_t i = 0; i < n_nodes; ++i) {                    /* NodeSchedulingMetadataForNodes, resources.go:67-76 */
+        orc_res overhead = {over_cpu ? over_cpu[i] : 0, over_mem ? over_mem[i] : 0, over_gpu ? over_gpu[i] : 0};
+        orc_res* u = resmap_get(&usage, names[i]);
+        if (u != NULL) res_add(u, &overhead);                  /* :76 mutates the map's entry; a missing entry is a temporary */
+    }
+    for (int32_t i = 0; i < n_nodes; ++i) {                    /* usage.Add(overhead), resources.go:109-116 */
+        orc_res overhead = {over_cpu ? over_cpu[i] : 0, over_mem ? over_mem[i] : 0, over_gpu ? over_gpu[i] : 0};
+        orc_res* u = resmap_get(&usage, names[i]);
+        if (u == NULL) u = resmap_put(&usage, names[i], &zero);
+        res_add(u, &overhead);
+    }
+    for (int32_t i = 0; i < n_nodes; ++i) {                    /* AvailableForNodes, resources.go:46-56 */
+        const orc_res* u = resmap_get(&usage, names[i]);
+        orc_res a = {alloc_cpu[i], alloc_mem[i], alloc_gpu ? alloc_gpu[i] : 0};
+        if (u) res_sub(&a, u);
+        avail_cpu[i] = a.cpu; avail_mem[i] = a.mem; avail_gpu[i] = a.gpu;
+    }
+    resmap_free(&usage);
+}
+
 /* ------------------------------------------------------------------ node sorting ---- */
 /* resourcesLessThan, internal/sort/nodesorting.go:74-80 */
 static int resources_less_than(const orc_res* l, const orc_res* r) {

@@ -134,6 +134,15 @@ void orc_node_scheduling_metadata(int32_t n_nodes, const char* const* names,
                                   int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu,
                                   int64_t* sched_cpu, int64_t* sched_mem, int64_t* sched_gpu);
 
+/* availableResources of rescheduleExecutor's first-fit branch (EXT/resource.go:638-643) with the overhead double count of
+ * SURVEY App. B7 (nodes that carry a reservation lose their overhead twice). */
+void orc_reschedule_available(int32_t n_nodes, const char* const* names,
+                              const int64_t* alloc_cpu, const int64_t* alloc_mem, const int64_t* alloc_gpu,
+                              const int64_t* over_cpu, const int64_t* over_mem, const int64_t* over_gpu,
+                              int64_t n_res, const char* const* res_node_name,
+                              const int64_t* res_cpu, const int64_t* res_mem, const int64_t* res_gpu,
+                              int64_t* avail_cpu, int64_t* avail_mem, int64_t* avail_gpu);
+
 /* ------------------------------------------------------------------ closed form ---- */
 
 /* Same semantics on index arrays: node table [n_nodes] (int64 SoA), exec_order / driver_order are

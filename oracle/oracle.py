@@ -64,6 +64,9 @@ def lib():
         L.orc_node_scheduling_metadata.restype = None
         L.orc_node_scheduling_metadata.argtypes = [C.c_int32, C.POINTER(C.c_char_p)] + [C.c_void_p] * 6 + [
             C.c_int64, C.POINTER(C.c_char_p)] + [C.c_void_p] * 9
+        L.orc_reschedule_available.restype = None
+        L.orc_reschedule_available.argtypes = [C.c_int32, C.POINTER(C.c_char_p)] + [C.c_void_p] * 6 + [
+            C.c_int64, C.POINTER(C.c_char_p)] + [C.c_void_p] * 6
         L.orc_reschedule_executor.restype = C.c_int32
         L.orc_reschedule_executor.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_char_p), C.c_int32,
                                               C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.c_int32]
@@ -202,6 +205,19 @@ def node_scheduling_metadata(names, alloc, overhead, res_node_names, res):
                                        len(res_node_names), _names(res_node_names), _ptr(rs[0]), _ptr(rs[1]), _ptr(rs[2]),
                                        _ptr(av[0]), _ptr(av[1]), _ptr(av[2]), _ptr(sc[0]), _ptr(sc[1]), _ptr(sc[2]))
     return av, sc
+
+
+def reschedule_available(names, alloc, overhead, res_node_names, res):
+    """availableResources of rescheduleExecutor's first-fit branch (overhead counted twice on nodes with reservations)."""
+    n = len(names)
+    al = [_i64(x) for x in alloc]
+    ov = [_i64(x) for x in overhead] if overhead is not None else [None] * 3
+    rs = [_i64(x) for x in res]
+    av = [np.empty(n, np.int64) for _ in range(3)]
+    lib().orc_reschedule_available(n, _names(names), _ptr(al[0]), _ptr(al[1]), _ptr(al[2]), _ptr(ov[0]), _ptr(ov[1]), _ptr(ov[2]),
+                                   len(res_node_names), _names(res_node_names), _ptr(rs[0]), _ptr(rs[1]), _ptr(rs[2]),
+                                   _ptr(av[0]), _ptr(av[1]), _ptr(av[2]))
+    return av
 
 
 def closed_batch(algo, mode, avail_cpu, avail_mem, avail_gpu, driver_order, exec_order,

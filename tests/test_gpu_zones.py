@@ -148,3 +148,23 @@ def test_reservation_table_and_resident_snapshot(oracle, packer):
     assert np.array_equal(rc, nodes["avail_cpu"]) and np.array_equal(rm, nodes["avail_mem"])
     got3 = packer.pack_batch(a, 0, 0)
     assert_same_results(got3, placed, "after release")
+
+
+def test_reschedule_availability_double_counts_overhead(oracle, packer):
+    """EXT/resource.go:638-643 bug for bug: nodes that carry a reservation lose their overhead twice in the
+    availability the first-fit reschedule sees.  Device == the statement-by-statement restatement; and the node choice of
+    a first-fit reschedule on that availability == the literal oracle's."""
+    rng = np.random.default_rng(21)
+    n, R = 500, 900
+    names = node_names(n)
+    alloc = [(rng.integers(8, 64, n) * 1000).astype(np.int64), (rng.integers(16, 256, n) << 30).astype(np.int64), rng.integers(0, 3, n).astype(np.int64)]
+    over = [(rng.integers(0, 4, n) * 250).astype(np.int64), (rng.integers(0, 8, n) << 28).astype(np.int64), np.zeros(n, np.int64)]
+    rnode = rng.integers(-1, n // 2, R).astype(np.int32)            # half of the nodes carry reservations; -1 = a node that left
+    res = [(rng.integers(0, 5, R) * 500).astype(np.int64), (rng.integers(0, 9, R) << 29).astype(np.int64), (rng.integers(0, 4, R) == 0).astype(np.int64)]
+    got = packer.build_reschedule_availability(alloc, over, rnode, res)
+    want = oracle.reschedule_available(names, alloc, over, [names[i] if i >= 0 else "gone-%d" % t for t, i in enumerate(rnode)], res)
+    for g_, w_ in zip(got, want):
+        assert np.array_equal(g_, w_)
+    plain, _ = packer.build_availability(alloc, over, rnode, res)
+    has = np.zeros(n, bool); has[rnode[rnode >= 0]] = True
+    assert np.array_equal(plain[0] - got[0], over[0] * has)         # exactly one extra overhead where a reservation exists
