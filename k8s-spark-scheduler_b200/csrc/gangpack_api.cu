@@ -348,6 +348,7 @@ struct gp_ctx {
     bool tab_attr_set[2] = {false, false};
     // per pipeline lane: shape hash + header, capacity tables, group totals, per-application shape slot
     struct TableSet { DevBuf hdr, table, total, app_slot; } tabs[kLanes];
+    bool record_events = true;                    // CUDA events around the kernels (gp_last_stats); the pipelined host path skips them
     DevBuf off_dev;                               // ExecutorNodes offsets derived on the device
     DevBuf fifo_list;                             // FIFO modes: per-instance-group application lists (queue order)
     DevBuf sched, zonebuf;                        // SchedulableResources [3][n_nodes]; staging of gp_pack_batch_zones
@@ -769,11 +770,13 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
     }
 }
 
-// independent tightly-pack / distribute-evenly: classify -> capacity tables -> fused pack (gangpack_tables.cuh)
+// independent tightly-pack / distribute-evenly: classify -> capacity tables -> thread-per-application decisions ->
+// warp-per-application scan of whatever the tables could not decide (gangpack_tables.cuh)
 template <int ALGO, class OUT>
 static gp_status launch_tables(gp_ctx* c, const Snapshot& s, const AppColumns& cols, const ShapeTables& tabs, const int32_t* app_slot,
-                               int32_t q, const DevResults& dr, int32_t lo, int2* scratch, unsigned long long* stats,
-                               unsigned int* next_app, int* d_err, volatile int* err_host, bool use_tables, cudaStream_t st, int chunk) {
+                               PrepApp* prep, int32_t* listed, int32_t q, const DevResults& dr, int32_t lo, int2* scratch,
+                               unsigned long long* stats, unsigned int* next_app, int* d_err, volatile int* err_host, bool use_tables,
+                               cudaStream_t st, int chunk) {
     if (use_tables) {
         bool& attr = c->tab_attr_set[ALGO];
         if (!attr) {
@@ -781,21 +784,25 @@ static gp_status launch_tables(gp_ctx* c, const Snapshot& s, const AppColumns& c
             attr = true;
         }
         gp_build_shape_tables<ALGO><<<dim3(kMaxShapes, (unsigned)c->n_groups), kTabThreads, kTabSmemBytes, st>>>(s, tabs);
-        c->last.kernel_launches += 1;
+        gp_build_driver_firstfit<<<dim3(kMaxShapes, (unsigned)c->n_groups), 256, 0, st>>>(s, tabs);
+        c->last.kernel_launches += 2;
     }
+    if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
+    gp_decide_tables<ALGO, OUT><<<(q + kDecideThreads - 1) / kDecideThreads, kDecideThreads, 0, st>>>(
+        s, cols, tabs, app_slot, q, dr.cap, dr.driver + lo, static_cast<OUT*>(dr.exec), prep, listed, stats, d_err, err_host, use_tables ? 0 : 1);
     int& per_sm = c->tab_ctas_per_sm[ALGO][sizeof(OUT) == 2 ? 1 : 0];
     if (per_sm == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gp_pack_tables<ALGO, OUT>, kPackTabThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gp_pack_listed<ALGO, OUT>, kPackTabThreads, 0);
         if (per_sm < 1) per_sm = 1;
     }
+    // persistent grid; with the tables on the list is normally short (or empty: the CTAs leave at once)
     int64_t blocks = ((int64_t)q * 32 + kPackTabThreads - 1) / kPackTabThreads;
-    const int64_t max_blocks = (int64_t)c->sm_count * per_sm;
+    const int64_t max_blocks = (int64_t)c->sm_count * (use_tables ? 2 : per_sm);
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
-    GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
-    gp_pack_tables<ALGO, OUT><<<(int)blocks, kPackTabThreads, 0, st>>>(s, cols, tabs, app_slot, q, dr.cap, dr.driver + lo,
-                                                                      static_cast<OUT*>(dr.exec), scratch, stats, next_app, d_err, err_host);
-    c->last.kernel_launches += 1;
+    gp_pack_listed<ALGO, OUT><<<(int)blocks, kPackTabThreads, 0, st>>>(s, tabs.hdr, prep, listed, dr.driver + lo, static_cast<OUT*>(dr.exec), scratch,
+                                                                      stats, next_app);
+    c->last.kernel_launches += 2;
     return GP_OK;
 }
 
@@ -814,41 +821,48 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
 
     if (mode == GP_MODE_INDEPENDENT && algo != GP_MINIMAL_FRAGMENTATION) {
         gp_ctx::TableSet& T = c->tabs[chunk % gp_ctx::kLanes];
-        const size_t hdr_bytes = 512 + sizeof(ShapeEntry) * (size_t)kShapeSlots;
-        static_assert(sizeof(ShapeHeader) <= 512, "ShapeHeader");
+        const size_t hdr_bytes = 1024 + (sizeof(ShapeEntry) + sizeof(DriverEntry)) * (size_t)kShapeSlots;
         const bool use_tables = c->use_tables && q >= 32;
         GP_CUDA(c, T.hdr.reserve(hdr_bytes));
-        GP_CUDA(c, T.app_slot.reserve(sizeof(int32_t) * (size_t)q));
+        GP_CUDA(c, T.app_slot.reserve(sizeof(int32_t) * 3 * (size_t)q));          // [executor slot | driver slot | listed]
         if (use_tables) {
             GP_CUDA(c, T.table.reserve(sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)((c->n_slots + 4) & ~3)));
-            GP_CUDA(c, T.total.reserve(sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)c->n_groups));
-            GP_CUDA(c, cudaMemsetAsync(T.hdr.p, 0, hdr_bytes, st));
+            GP_CUDA(c, T.total.reserve(2 * sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)c->n_groups));
         }
+        // the hash tables and the header (listed counter) start from zero: the whole block when the tables are used
+        GP_CUDA(c, cudaMemsetAsync(T.hdr.p, 0, use_tables ? hdr_bytes : 1024, st));
         ShapeTables tabs;
         tabs.hdr = T.hdr.as<ShapeHeader>();
-        tabs.entries = reinterpret_cast<ShapeEntry*>(T.hdr.as<char>() + 512);
+        tabs.entries = reinterpret_cast<ShapeEntry*>(T.hdr.as<char>() + 1024);
+        tabs.dentries = reinterpret_cast<DriverEntry*>(T.hdr.as<char>() + 1024 + sizeof(ShapeEntry) * (size_t)kShapeSlots);
         tabs.table = T.table.as<uint32_t>(); tabs.total = T.total.as<uint32_t>();
+        tabs.firstfit = reinterpret_cast<int32_t*>(T.total.as<uint32_t>() + (size_t)kMaxShapes * (size_t)c->n_groups);
         tabs.pitch = (c->n_slots + 4) & ~3; tabs.n_groups = c->n_groups;      // rows start 16-byte aligned
         int64_t* off_out = nullptr;
         if (!da.cols.off) {                       // derive the offsets on the device
             off_out = c->off_dev.as<int64_t>() + lo;
             cols.off = off_out;
         }
-        GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
-        gp_classify_apps<<<(q + kClassifyThreads - 1) / kClassifyThreads, kClassifyThreads, 0, st>>>(
-            q, cols, tabs, c->snap_flags.as<SnapMeta>(), off_base, off_out, T.app_slot.as<int32_t>(), use_tables ? 1 : 0);
-        c->last.kernel_launches += 1;
+        int32_t* app_slot = T.app_slot.as<int32_t>();
+        int32_t* listed = app_slot + 2 * (size_t)q;
+        PrepApp* prep = c->prep.as<PrepApp>() + lo;
+        if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
+        if (use_tables || off_out) {
+            gp_classify_apps<<<(q + kClassifyThreads - 1) / kClassifyThreads, kClassifyThreads, 0, st>>>(
+                q, cols, tabs, c->snap_flags.as<SnapMeta>(), off_base, off_out, app_slot, use_tables ? 1 : 0);
+            c->last.kernel_launches += 1;
+        }
         gp_status r;
         const bool o16 = dr.node_bits == 16;
         if (algo == GP_TIGHTLY_PACK)
-            r = o16 ? launch_tables<0, uint16_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
-                    : launch_tables<0, int32_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
+            r = o16 ? launch_tables<0, uint16_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
+                    : launch_tables<0, int32_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
         else
-            r = o16 ? launch_tables<1, uint16_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
-                    : launch_tables<1, int32_t>(c, s, cols, tabs, T.app_slot.as<int32_t>(), q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
+            r = o16 ? launch_tables<1, uint16_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
+                    : launch_tables<1, int32_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
         if (r != GP_OK) return r;
         GP_CUDA(c, cudaGetLastError());
-        GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
+        if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
         return GP_OK;
     }
 
@@ -860,12 +874,12 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
         GP_CUDA(c, c->gmin.reserve(sizeof(GroupMin) * (size_t)c->n_groups));
         GP_CUDA(c, cudaMemsetAsync(c->gmin.p, 0x7f, sizeof(GroupMin) * (size_t)c->n_groups, st));   // +inf-ish
     }
-    GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
+    if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
     gp_prep_apps<<<(q + T - 1) / T, T, 0, st>>>(
         q, cols, da.skip ? da.skip + lo : nullptr, c->n_groups, dr.cap,
         c->snap_flags.as<SnapMeta>(), mode == GP_MODE_INDEPENDENT ? nullptr : c->gmin.as<GroupMin>(), prep, d_err, err_host);
     s.gmins = c->gmin.as<GroupMin>();
-    GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
+    if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
     int32_t* exec32 = static_cast<int32_t*>(dr.exec);
     if (algo == GP_TIGHTLY_PACK)
         launch_pack<0>(c, mode, s, prep, cols.group, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
@@ -874,7 +888,7 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
     else
         launch_pack<1>(c, mode, s, prep, cols.group, q, dr.driver + lo, exec32, scratch, d_stats, next_app, st);
     GP_CUDA(c, cudaGetLastError());
-    GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
+    if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
     c->last.kernel_launches += 2;
     return GP_OK;
 }
@@ -889,7 +903,7 @@ static gp_status pack_begin(gp_ctx* c, int32_t q, gp_algo algo, gp_mode mode, in
     c->ev_chunks = 0;
     *scratch = nullptr;
     if (q == 0) return GP_OK;
-    if (!fused_path(algo, mode)) GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));
+    GP_CUDA(c, c->prep.reserve(sizeof(PrepApp) * (size_t)q));      // FIFO / minimal-fragmentation: every application; tables: the listed ones
     if (derive_off) GP_CUDA(c, c->off_dev.reserve(sizeof(int64_t) * (size_t)(q + 1)));
     if (algo != GP_TIGHTLY_PACK) {        // candidate list (distribute-evenly) / consumed-node list (minimal-fragmentation)
         GP_CUDA(c, c->scratch.reserve(sizeof(int2) * (size_t)(exec_cap + 1)));
@@ -1077,6 +1091,10 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
     int2* scratch = nullptr;
     s = pack_begin(c, q, algo, mode, out->executor_nodes_cap, !off, &scratch, st);
     if (s != GP_OK) return s;
+    // per-kernel CUDA events are for gp_last_stats; the pipelined path is bound by how fast the host thread can issue
+    // its ~10 calls per chunk, so it leaves them out (pack_kernel_ns / prep_kernel_ns then read 0)
+    struct EvGuard { gp_ctx* c; ~EvGuard() { c->record_events = true; } } ev_guard{c};
+    c->record_events = n_chunks == 1;
     GP_CUDA(c, cudaEventRecord(c->ev_ready, st));      // snapshot + zeroed counters are ready
     int64_t e_run = 0;                                 // ExecutorNodes entries before the current chunk
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -1156,7 +1174,7 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
             GP_CUDA(c, cudaMemcpyAsync((char*)out->executor_nodes + os * (size_t)e0, (char*)dr.exec + os * (size_t)e0, os * (size_t)(e1 - e0),
                                        cudaMemcpyDeviceToHost, ls));
     }
-    c->ev_chunks = n_chunks;
+    c->ev_chunks = c->record_events ? n_chunks : 0;
     const auto t_issued = std::chrono::steady_clock::now();
     if (n_chunks > 1) {
         for (int l = 0; l < gp_ctx::kLanes && l < n_chunks; ++l) {

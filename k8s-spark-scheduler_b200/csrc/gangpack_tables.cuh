@@ -19,14 +19,17 @@
 //                         thread evaluates 4 consecutive nodes, a block-wide exclusive scan turns capacities into the
 //                         prefix table  S[i] = sum_{n<i} min(cap(n|0), CLAMP)   (tightly-pack) or
 //                                       M[i] = #{n<i : cap(n|0) >= 1}            (distribute-evenly);
-//   K3 gp_pack_tables     one warp per application, inputs read raw (no prepared record round-trips HBM): feasibility
-//                         is  S[ne] - delta(d) >= k  per driver candidate d (delta = what the driver displaces on its
-//                         own node: O(1) per candidate, the reference's loop binpack.go:67-85 verbatim), the first
-//                         hosting node is found by a 32-ary search of the table, and ExecutorNodes is expanded from the
-//                         prefix values of 32 nodes at a time (shuffle binary search -> coalesced stores).
-// What the tables cannot answer exactly is handed to the scan path of gangpack_kernels.cuh INSIDE the same kernel
-// (warp-uniform branch): more than kMaxShapes distinct shapes in a batch, executor counts above the table clamp,
-// distribute-evenly placements that need more than one round.  GANGPACK_TABLES=0 forces that path for everything.
+//   K2d gp_build_driver_firstfit  one CTA per (driver shape, instance group): the first driver candidate the shape fits on;
+//   K3 gp_decide_tables   ONE THREAD per application (with the tables a decision is O(log N + k) scalar work -- a warp per
+//                         application, right for an O(N) scan, would idle 31 lanes): feasibility is
+//                         S[ne] - delta(d) >= k  per driver candidate d starting at the shape's first fit (delta = what the
+//                         driver displaces on its own node: O(1) per candidate, the reference's loop binpack.go:67-85
+//                         verbatim), the first hosting node is found by binary search of the prefix table, ExecutorNodes
+//                         is emitted by walking the table from there (zero-capacity runs are jumped by binary search).
+// What the tables cannot answer exactly -- more than kMaxShapes distinct shapes in a batch, executor counts above the table
+// clamp, distribute-evenly placements that need more than one round -- is appended, already prepared (PrepApp), to a list
+// that the warp-per-application scan kernel gp_pack_listed (the node-order scan of gangpack_kernels.cuh) works off.
+// GANGPACK_TABLES=0 sends every application down that path.
 #pragma once
 
 #include "gangpack_kernels.cuh"
@@ -49,18 +52,33 @@ struct __align__(16) ShapeEntry {     // 96 bytes
 };
 static_assert(sizeof(ShapeEntry) == 96, "ShapeEntry layout");
 
+struct __align__(16) DriverEntry {    // 48 bytes: interned driver request
+    unsigned long long key;
+    int32_t id;
+    uint32_t pad;
+    int64_t d[3];
+    int64_t pad2;
+};
+static_assert(sizeof(DriverEntry) == 48, "DriverEntry layout");
+
 // device-side header of one table set
 struct ShapeHeader {
-    int32_t n_shapes;                 // shapes claimed so far (may exceed kMaxShapes)
-    int32_t fallback_apps;            // statistics: applications that took the scan path
-    int32_t id_slot[kMaxShapes];      // dense id -> hash slot
+    int32_t n_shapes;                 // executor shapes claimed so far (may exceed kMaxShapes)
+    int32_t n_dshapes;                // driver shapes claimed so far
+    int32_t n_listed;                 // applications handed to the scan kernel
+    int32_t pad;
+    int32_t id_slot[kMaxShapes];      // dense executor-shape id -> hash slot
+    int32_t did_slot[kMaxShapes];     // dense driver-shape id -> hash slot
 };
+static_assert(sizeof(ShapeHeader) <= 1024, "ShapeHeader");
 
 struct ShapeTables {
     ShapeEntry* entries;              // [kShapeSlots]
+    DriverEntry* dentries;            // [kShapeSlots]
     ShapeHeader* hdr;
     uint32_t* table;                  // [kMaxShapes][pitch] exclusive prefix per instance group, indexed by slot
     uint32_t* total;                  // [kMaxShapes][n_groups]
+    int32_t* firstfit;                // [kMaxShapes][n_groups] first driver-order position the driver shape fits on (nd: none)
     int32_t pitch;                    // row length (>= n_slots, multiple of 4)
     int32_t n_groups;
 };
@@ -164,6 +182,32 @@ __global__ void __launch_bounds__(kClassifyThreads) gp_classify_apps(int32_t n_a
         }
     }
     app_slot[i] = found;
+
+    // ---- the driver request, interned the same way: its first fitting candidate is searched once per shape (K2d) ----
+    const int64_t d0 = cols.load(0, i), d1 = cols.load(1, i), d2 = cols.load(2, i);
+    int32_t dfound = -1;
+    if (d0 >= 0 && d1 >= 0 && d2 >= 0 && d0 < kMaxQuantity && d1 < kMaxQuantity && d2 < kMaxQuantity) {
+        const unsigned long long fp = shape_fingerprint(d0 ^ 0x5bd1e995, d1, d2);
+        int32_t slot = (int32_t)(fp & (kShapeSlots - 1));
+        for (int p = 0; p < kShapeProbes && dfound < 0; ++p) {
+            DriverEntry* en = tabs.dentries + slot;
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&en->key);
+            if (cur == 0) {
+                cur = atomicCAS(&en->key, 0ull, fp);
+                if (cur == 0) {
+                    int32_t id = atomicAdd(&tabs.hdr->n_dshapes, 1);
+                    if (id >= kMaxShapes) id = -1;
+                    en->d[0] = d0; en->d[1] = d1; en->d[2] = d2;
+                    en->id = id;
+                    if (id >= 0) tabs.hdr->did_slot[id] = slot;
+                    cur = fp;
+                }
+            }
+            if (cur == fp) dfound = slot;
+            slot = (slot + 1) & (kShapeSlots - 1);
+        }
+    }
+    app_slot[n_apps + i] = dfound;         // second half of the array: driver-shape slots
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -252,179 +296,231 @@ __global__ void __launch_bounds__(kTabThreads, 1) gp_build_shape_tables(Snapshot
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3: one warp per application
+// K2d: first fitting driver candidate per (driver shape, instance group)
 // ---------------------------------------------------------------------------------------------------------------
-struct TabStats { unsigned long long probes, drivers, fallback; };
+__global__ void __launch_bounds__(256) gp_build_driver_firstfit(Snapshot s, ShapeTables tabs) {
+    __shared__ int32_t s_first;
+    const int id = blockIdx.x, grp = blockIdx.y;
+    const int n = min(tabs.hdr->n_dshapes, kMaxShapes);
+    if (id >= n) return;
+    const DriverEntry& en = tabs.dentries[tabs.hdr->did_slot[id]];
+    const int64_t d0 = en.d[0], d1 = en.d[1], d2 = en.d[2];
+    const GroupDesc g = s.groups[grp];
+    const bool ug = d2 != 0 || (s.meta->flags & kSnapGpuNegative);
+    const longlong2* gpair = s.pair + g.sbase;
+    const int64_t* ggpu = s.gpu + g.sbase;
+    if (threadIdx.x == 0) s_first = g.nd;
+    __syncthreads();
+    for (int32_t j0 = 0; j0 < g.nd; j0 += blockDim.x) {
+        const int32_t j = j0 + threadIdx.x;
+        bool fits = false;
+        if (j < g.nd) {
+            const int32_t ls = s.drv_slot[g.dbase + j];
+            const longlong2 v = __ldg(gpair + ls);
+            fits = !(d0 > v.x) && !(d1 > v.y) && !(ug && d2 > __ldg(ggpu + ls));     // driverResources.GreaterThan(available) == false
+        }
+        if (fits) atomicMin(&s_first, j);
+        __syncthreads();
+        if (s_first < g.nd) break;               // block-uniform
+    }
+    if (threadIdx.x == 0) tabs.firstfit[(size_t)id * tabs.n_groups + grp] = s_first;
+}
 
+// ---------------------------------------------------------------------------------------------------------------
+// K3: one thread per application
+// ---------------------------------------------------------------------------------------------------------------
 // prefix value S(i), i in [0, ne]
 __device__ __forceinline__ uint32_t tab_at(const uint32_t* __restrict__ tab, int32_t i, int32_t ne, uint32_t total) {
     return i < ne ? __ldg(tab + i) : total;
 }
-
-// Largest i in [0, ne] with S(i) <= 0, narrowed to a window of <= 32 entries: returns lo such that the first node with
-// a non-zero table increment lies in [lo, lo + 32).  Requires total > 0.
-__device__ __forceinline__ int32_t tab_first_window(const uint32_t* __restrict__ tab, int32_t ne, uint32_t total, int lane, TabStats& st) {
-    int32_t lo = 0, hi = ne;       // S(lo) == 0, S(hi) > 0
-    while (hi - lo > 32) {
-        const int32_t step = (hi - lo + 31) / 32;
-        const int32_t p = lo + (lane + 1) * step;
-        const bool zero = p < hi && tab_at(tab, p, ne, total) == 0;
-        const unsigned z = __ballot_sync(kFull, zero);
-        const int c = __ffs(~z) - 1;           // leading lanes whose probe is still 0 (S is non-decreasing)
-        lo += c * step;
-        hi = min(hi, lo + step);
-        st.probes += 32;
+// smallest p in (lo, ne] with S(p) > val; requires S(ne) = total > val
+__device__ __forceinline__ int32_t tab_next_above(const uint32_t* __restrict__ tab, int32_t lo, int32_t ne, uint32_t total, uint32_t val,
+                                                  unsigned long long& probes) {
+    int32_t a = lo + 1, b = ne;                     // answer in [a, b]
+    while (a < b) {
+        const int32_t mid = (a + b) >> 1;
+        if (tab_at(tab, mid, ne, total) > val) b = mid; else a = mid + 1;
+        ++probes;
     }
-    return lo;
+    return a;
 }
 
+constexpr int kDecideThreads = 128;
+// cols: raw application columns; app_slot: [2][n_apps] executor / driver shape slots from K1.  Applications the tables
+// cannot decide are prepared (PrepApp) and appended to `listed`; force_scan appends every application.
 template <int ALGO, class OUT>
-__device__ __forceinline__ int32_t pack_app_tables(const Snapshot& s, const GroupDesc& g, const uint32_t* __restrict__ tab, uint32_t total,
-                                                   const ShapeEntry& en, int64_t d_cpu, int64_t d_mem, int64_t d_gpu, uint32_t k,
-                                                   OUT* __restrict__ out, TabStats& st, int lane, int snap_flags, bool& need_scan) {
-    const int32_t ne = g.ne;
-    const uint32_t clamp = table_clamp(ne);
-    need_scan = false;
-    if (k > clamp) { need_scan = true; return -1; }
-    if (ALGO == 0) { if (k != 0 && total < k) return -1; }                        // not even without a driver (pack_tightly.go:62)
-    else if (k != 0 && total < k + 1) { need_scan = true; return -1; }            // fewer than k+1 hosting nodes: rounds / exact test
-
-    const bool drv_gpu = d_gpu != 0 || (snap_flags & kSnapGpuNegative);
-    const bool cap_gpu = drv_gpu || (en.flags & 1u);
-    const longlong2* gpair = s.pair + g.sbase;
-    const int64_t* ggpu = s.gpu + g.sbase;
-
-    // ---- driver loop (binpack.go:67-85): first candidate that fits and leaves room for k executors ----------------
-    int32_t dslot = -1;
-    uint32_t cd = 0, c0d = 0, Sp = 0;
-    for (int32_t j0 = 0; j0 < g.nd && dslot < 0; j0 += kWarp) {
-        const int32_t j = j0 + lane;
-        bool feasible = false;
-        int32_t ls = -1;
-        uint32_t my_cd = 0, my_c0 = 0, my_sp = 0;
-        if (j < g.nd) {
-            ls = s.drv_slot[g.dbase + j];
-            const longlong2 v = __ldg(gpair + ls);
-            const int64_t gv = drv_gpu || cap_gpu ? __ldg(ggpu + ls) : 0;
-            feasible = !(d_cpu > v.x) && !(d_mem > v.y) && !(drv_gpu && d_gpu > gv);
-            if (feasible && ls < ne && k != 0) {
-                my_sp = __ldg(tab + ls);
-                my_c0 = tab_at(tab, ls + 1, ne, total) - my_sp;
-                if (my_c0 != 0) {        // what the node can still take once the driver sits on it
-                    uint32_t c = min(cap_dim(v.x - d_cpu, en.div[0], clamp), cap_dim(v.y - d_mem, en.div[1], clamp));
-                    if (cap_gpu) c = min(c, cap_dim(gv - d_gpu, en.div[2], clamp));
-                    if (ALGO == 1) c = c != 0 ? 1u : 0u;
-                    my_cd = c;
+__global__ void __launch_bounds__(kDecideThreads) gp_decide_tables(Snapshot s, AppColumns cols, ShapeTables tabs,
+                                                                   const int32_t* __restrict__ app_slot, int32_t n_apps, int64_t out_cap,
+                                                                   int32_t* __restrict__ driver_node, OUT* __restrict__ executor_nodes,
+                                                                   PrepApp* __restrict__ prep, int32_t* __restrict__ listed,
+                                                                   unsigned long long* __restrict__ stats, int* __restrict__ err,
+                                                                   volatile int* __restrict__ err_host, int force_scan) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long probes = 0, drivers = 0;
+    if (i < n_apps) {
+        const int64_t d_cpu = cols.load(0, i), d_mem = cols.load(1, i), d_gpu = cols.load(2, i);
+        const int64_t e_cpu = cols.load(3, i), e_mem = cols.load(4, i), e_gpu = cols.load(5, i);
+        const int32_t kk = cols.count[i];
+        const int32_t grp = cols.group ? cols.group[i] : 0;
+        const int64_t off = cols.off[i], off1 = cols.off[i + 1];
+        // ---- validation (types.SparkApplicationResources must be non-negative and inside the exact-int64 domain) ----
+        int bad = 0;
+        if (d_cpu < 0 || d_mem < 0 || d_gpu < 0 || e_cpu < 0 || e_mem < 0 || e_gpu < 0 || kk < 0) bad |= kErrNegativeRequest;
+        if (d_cpu >= kMaxQuantity || d_mem >= kMaxQuantity || d_gpu >= kMaxQuantity || e_cpu >= kMaxQuantity || e_mem >= kMaxQuantity ||
+            e_gpu >= kMaxQuantity || kk > kMaxCount) bad |= kErrUnrepresentable;
+        if (grp < 0 || grp >= s.n_groups) bad |= kErrBadGroup;
+        if (off < 0 || off1 - off != (int64_t)(kk > 0 ? kk : 0) || off1 > out_cap) bad |= kErrBadOffsets;
+        if (bad) {
+            atomicOr(err, bad); *err_host = bad;
+            driver_node[i] = -1;
+        } else {
+            const GroupDesc g = s.groups[grp];
+            const int32_t ne = g.ne, nd = g.nd;
+            const uint32_t k = (uint32_t)kk;
+            const int snap_flags = s.meta->flags;
+            bool need_scan = force_scan != 0;
+            int32_t result = -1;
+            const ShapeEntry* en = nullptr;
+            const uint32_t* tab = nullptr;
+            uint32_t total = 0;
+            const uint32_t clamp = table_clamp(ne);
+            if (!need_scan) {
+                const int32_t slot = app_slot[i];
+                if (slot < 0) need_scan = true;
+                else {
+                    en = tabs.entries + slot;       // the full tuple decides, not the fingerprint
+                    if (en->id < 0 || en->div[0].e != e_cpu || en->div[1].e != e_mem || en->div[2].e != e_gpu || k > clamp) need_scan = true;
+                    else {
+                        tab = tabs.table + (size_t)en->id * tabs.pitch + g.sbase;
+                        total = tabs.total[(size_t)en->id * tabs.n_groups + grp];
+                        if (ALGO == 1 && k != 0 && total < k + 1) need_scan = true;      // fewer than k+1 hosting nodes: rounds / exact test
+                    }
                 }
-                if (ALGO == 0) feasible = (total - (my_c0 - my_cd) >= k);
-                // distribute-evenly: total >= k+1 hosting nodes, the driver removes at most its own -> always feasible
             }
-        }
-        const unsigned vote = __ballot_sync(kFull, feasible);
-        st.drivers += (unsigned long long)((g.nd - j0) < kWarp ? (g.nd - j0) : kWarp);
-        if (vote) {
-            const int src = __ffs(vote) - 1;
-            dslot = __shfl_sync(kFull, ls, src);
-            cd = __shfl_sync(kFull, my_cd, src);
-            c0d = __shfl_sync(kFull, my_c0, src);
-            Sp = __shfl_sync(kFull, my_sp, src);
-        }
-    }
-    if (dslot < 0) return -1;
-    const int32_t driver_node = s.slot_node[g.sbase + dslot];
-    if (k == 0) return driver_node;
-
-    // ---- emission: output j belongs to the node whose adjusted prefix range holds j ------------------------------
-    // adjusted inclusive prefix of node i:  S'(i+1) = S(i+1) - (i >= dslot ? delta : 0),  delta = c0(d) - cd(d)
-    const uint32_t delta = (dslot < ne) ? c0d - cd : 0u;
-    const int32_t dpos = (dslot < ne) ? dslot : 0x7fffffff;
-    (void)Sp;
-    int32_t pos = tab_first_window(tab, ne, total, lane, st);
-    uint32_t placed = 0;
-    const int32_t* slot_node = s.slot_node + g.sbase;
-    while (placed < k && pos < ne) {
-        const int32_t i = pos + lane;
-        uint32_t Sv = 0xFFFFFFFFu;                        // lanes beyond the order: never selected
-        int32_t node = -1;
-        if (i < ne) {
-            Sv = tab_at(tab, i + 1, ne, total);
-            if (i >= dpos) Sv -= delta;
-            node = __ldg(slot_node + i);
-        }
-        st.probes += 32;
-        // last valid lane's value bounds what this window can place
-        const int lastl = min(kWarp - 1, ne - 1 - pos);
-        const uint32_t wend = __shfl_sync(kFull, Sv, lastl);
-        const uint32_t endv = wend < k ? wend : k;
-        for (uint32_t j0 = placed; j0 < endv; j0 += kWarp) {
-            const uint32_t j = j0 + lane;
-            int lo = 0;                                   // first lane whose adjusted inclusive prefix exceeds j
+            if (!need_scan && !(ALGO == 0 && k != 0 && total < k)) {                  // total < k: not even without a driver (pack_tightly.go:62)
+                const bool drv_gpu = d_gpu != 0 || (snap_flags & kSnapGpuNegative);
+                const bool cap_gpu = drv_gpu || (en->flags & 1u);
+                const longlong2* gpair = s.pair + g.sbase;
+                const int64_t* ggpu = s.gpu + g.sbase;
+                // ---- driver loop (binpack.go:67-85) from the shape's first fitting candidate ---------------------------
+                int32_t j = 0;
+                {
+                    const int32_t ds = app_slot[n_apps + i];
+                    if (ds >= 0) {
+                        const DriverEntry& de = tabs.dentries[ds];
+                        if (de.id >= 0 && de.d[0] == d_cpu && de.d[1] == d_mem && de.d[2] == d_gpu) j = tabs.firstfit[(size_t)de.id * tabs.n_groups + grp];
+                    }
+                }
+                int32_t dslot = -1;
+                uint32_t cd = 0, c0d = 0;
+                for (; j < nd; ++j) {
+                    ++drivers;
+                    const int32_t ls = s.drv_slot[g.dbase + j];
+                    const longlong2 v = __ldg(gpair + ls);
+                    const int64_t gv = (drv_gpu || cap_gpu) ? __ldg(ggpu + ls) : 0;
+                    if ((d_cpu > v.x) || (d_mem > v.y) || (drv_gpu && d_gpu > gv)) continue;
+                    uint32_t my_c0 = 0, my_cd = 0;
+                    if (ls < ne && k != 0) {
+                        const uint32_t sp = __ldg(tab + ls);
+                        my_c0 = tab_at(tab, ls + 1, ne, total) - sp;
+                        probes += 2;
+                        if (my_c0 != 0) {        // what the node can still take once the driver sits on it
+                            uint32_t c = min(cap_dim(v.x - d_cpu, en->div[0], clamp), cap_dim(v.y - d_mem, en->div[1], clamp));
+                            if (cap_gpu) c = min(c, cap_dim(gv - d_gpu, en->div[2], clamp));
+                            if (ALGO == 1) c = c != 0 ? 1u : 0u;
+                            my_cd = c;
+                        }
+                        if (ALGO == 0 && total - (my_c0 - my_cd) < k) continue;       // the executors do not fit with this driver
+                        // distribute-evenly: >= k+1 hosting nodes, the driver removes at most its own
+                    }
+                    dslot = ls; cd = my_cd; c0d = my_c0;
+                    break;
+                }
+                if (dslot >= 0) {
+                    result = s.slot_node[g.sbase + dslot];
+                    if (k != 0) {
+                        // ---- emission: walk the prefix table from the first hosting node ---------------------------------
+                        OUT* out = executor_nodes + off;
+                        const int32_t* slot_node = s.slot_node + g.sbase;
+                        const int32_t dpos = (dslot < ne) ? dslot : 0x7fffffff;
+                        (void)c0d;
+                        int32_t pos = tab_next_above(tab, 0, ne, total, 0u, probes) - 1;
+                        uint32_t prev = 0, placed = 0;
+                        while (placed < k && pos < ne) {
+                            const uint32_t nxt = tab_at(tab, pos + 1, ne, total);
+                            ++probes;
+                            uint32_t c = nxt - prev;
+                            if (pos == dpos) c = cd;
+                            if (c == 0) {                               // zero-capacity run (or the driver ate its node): jump
+                                if (nxt >= total) break;                // cannot happen for a feasible placement
+                                pos = tab_next_above(tab, pos + 1, ne, total, nxt, probes) - 1;
+                                prev = nxt;
+                                continue;
+                            }
+                            const uint32_t take = c < k - placed ? c : k - placed;
+                            const OUT node = (OUT)__ldg(slot_node + pos);
+                            for (uint32_t t = 0; t < take; ++t) out[placed + t] = node;
+                            placed += take;
+                            prev = nxt;
+                            ++pos;
+                        }
+                    }
+                }
+            }
+            if (need_scan) {
+                // ---- prepared record for the scan kernel ------------------------------------------------------------------
+                const int32_t at = atomicAdd(&tabs.hdr->n_listed, 1);
+                PrepApp p;
+                int b2 = 0; uint64_t lmax = 0; bool fast = true;
+                const int64_t dd[3] = {d_cpu, d_mem, d_gpu}, ee[3] = {e_cpu, e_mem, e_gpu};
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const uint32_t v = __shfl_sync(kFull, Sv, lo + step - 1);
-                if (v <= j) lo += step;
+                for (int t = 0; t < 3; ++t) {
+                    uint64_t l;
+                    p.drv[t] = dd[t];
+                    p.div[t] = prep_dim(dd[t], ee[t], t, s.meta->max_avail[t], b2, l, fast);
+                    if (l > lmax) lmax = l;
+                }
+                p.out_off = off; p.count = kk; p.group = grp;
+                p.lmax = (int32_t)(lmax < (uint64_t)k ? lmax : (uint64_t)k);
+                const bool f32 = prep_fast32(fast, p.div[0], p.div[1], s.meta);
+                p.flags = ((d_gpu != 0 || e_gpu != 0) ? kAppUsesGpu : 0u) | (fast ? kAppFast : 0u) | (f32 ? kAppFast32 : 0u);
+                const uint4* src = reinterpret_cast<const uint4*>(&p);
+                uint4* dst = reinterpret_cast<uint4*>(prep + at);
+#pragma unroll
+                for (int t = 0; t < (int)(sizeof(PrepApp) / sizeof(uint4)); ++t) dst[t] = src[t];
+                listed[at] = i;
+            } else {
+                driver_node[i] = result;
             }
-            const int32_t nd = __shfl_sync(kFull, node, lo & 31);
-            if (j < endv) out[j] = (OUT)nd;
         }
-        placed = endv > placed ? endv : placed;
-        pos += kWarp;
     }
-    return driver_node;
+    // statistics: one atomic per warp
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { probes += __shfl_xor_sync(kFull, probes, d); drivers += __shfl_xor_sync(kFull, drivers, d); }
+    if ((threadIdx.x & 31) == 0 && (probes | drivers)) { atomicAdd(stats + 0, probes); atomicAdd(stats + 1, drivers); }
 }
 
-// The node-order scan of gangpack_kernels.cuh for ONE application inside the fused kernel (out of line: its register
-// needs must not weigh on the table path).  The prepared record is built in shared memory, lanes 0..2 one dimension each.
-template <int ALGO, class OUT>
-__device__ __noinline__ int32_t scan_path_app(const Snapshot& s, PrepApp* pa, int64_t d_cpu, int64_t d_mem, int64_t d_gpu,
-                                              int64_t e_cpu, int64_t e_mem, int64_t e_gpu, int32_t kk, int32_t grp,
-                                              OUT* __restrict__ out, int2* __restrict__ list, uint16_t* __restrict__ wcache,
-                                              WarpStats& st, int lane, int snap_flags) {
-    int b2 = 0; uint64_t l = 0; bool fast = true;
-    if (lane < 3) {
-        const int64_t dd = lane == 0 ? d_cpu : (lane == 1 ? d_mem : d_gpu);
-        const int64_t ee = lane == 0 ? e_cpu : (lane == 1 ? e_mem : e_gpu);
-        pa->div[lane] = prep_dim(dd, ee, lane, s.meta->max_avail[lane], b2, l, fast);
-        pa->drv[lane] = dd;
-    }
-    unsigned long long lm = l;
-    lm = max(lm, __shfl_xor_sync(kFull, lm, 1)); lm = max(lm, __shfl_xor_sync(kFull, lm, 2));   // lanes 0..3 (lane 3 holds 0)
-    const bool all_fast = __all_sync(kFull, fast);
-    __syncwarp();
-    if (lane == 0) {
-        pa->out_off = 0;                    // `out` / `list` already point at this application's slice
-        pa->count = kk; pa->group = grp;
-        pa->lmax = (int32_t)(lm < (unsigned long long)(uint32_t)kk ? lm : (unsigned long long)(uint32_t)kk);
-        const bool f32 = prep_fast32(all_fast, pa->div[0], pa->div[1], s.meta);
-        pa->flags = ((d_gpu != 0 || e_gpu != 0) ? kAppUsesGpu : 0u) | (all_fast ? kAppFast : 0u) | (f32 ? kAppFast32 : 0u);
-    }
-    __syncwarp();
-    const GroupDesc g0 = s.groups[0];
-    const int32_t d = pack_app<ALGO, OUT>(s, pa, out, list, wcache, st, lane, snap_flags, g0);
-    __syncwarp();
-    return d;
-}
-
+// ---------------------------------------------------------------------------------------------------------------
+// the node-order scan for the listed applications: one warp per application (gangpack_kernels.cuh)
+// ---------------------------------------------------------------------------------------------------------------
 constexpr int kPackTabThreads = 256;
 #ifndef GP_TAB_MIN_BLOCKS
 #define GP_TAB_MIN_BLOCKS 4
 #endif
-// cols: raw application columns; app_slot from K1; `force_scan` routes every application to the scan path.
 template <int ALGO, class OUT>
-__global__ void __launch_bounds__(kPackTabThreads, GP_TAB_MIN_BLOCKS) gp_pack_tables(Snapshot s, AppColumns cols, ShapeTables tabs,
-                                                                                     const int32_t* __restrict__ app_slot, int32_t n_apps,
-                                                                                     int64_t out_cap, int32_t* __restrict__ driver_node,
+__global__ void __launch_bounds__(kPackTabThreads, GP_TAB_MIN_BLOCKS) gp_pack_listed(Snapshot s, const ShapeHeader* __restrict__ hdr,
+                                                                                     const PrepApp* __restrict__ prep,
+                                                                                     const int32_t* __restrict__ listed,
+                                                                                     int32_t* __restrict__ driver_node,
                                                                                      OUT* __restrict__ executor_nodes,
                                                                                      int2* __restrict__ scratch,
                                                                                      unsigned long long* __restrict__ stats,
-                                                                                     unsigned int* __restrict__ next_app,
-                                                                                     int* __restrict__ err, volatile int* __restrict__ err_host) {
+                                                                                     unsigned int* __restrict__ next_app) {
     __shared__ uint16_t cap_cache[kPackTabThreads / 32][kCapCache];
-    __shared__ PrepApp prep_sm[kPackTabThreads / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint16_t* wcache = cap_cache[w];
-    PrepApp* pa = &prep_sm[w];
-    TabStats ts{0, 0, 0};
+    const int n = hdr->n_listed;
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31;
+    uint16_t* wcache = cap_cache[threadIdx.x >> 5];
     WarpStats st{0, 0};
     const int snap_flags = s.meta->flags;
     const GroupDesc g0 = s.groups[0];
@@ -432,62 +528,22 @@ __global__ void __launch_bounds__(kPackTabThreads, GP_TAB_MIN_BLOCKS) gp_pack_ta
     if (lane == 0) { i = atomicAdd(next_app, 1u); n1 = atomicAdd(next_app, 1u); }
     i = __shfl_sync(kFull, i, 0);
     n1 = __shfl_sync(kFull, n1, 0);
-    while (i < (unsigned int)n_apps) {
+    unsigned long long apps_done = 0;
+    while (i < (unsigned int)n) {
         unsigned int n2 = 0;
         if (lane == 0) n2 = atomicAdd(next_app, 1u);
-        // ---- the raw tuple: one field per lane, then broadcast ------------------------------------------------
-        int64_t f = 0;
-        if (lane < 6) f = cols.load(lane, (int32_t)i);
-        else if (lane == 6) f = cols.count[i];
-        else if (lane == 7) f = cols.group ? cols.group[i] : 0;
-        else if (lane == 8) f = cols.off[i];
-        else if (lane == 9) f = cols.off[i + 1];
-        else if (lane == 10) f = app_slot[i];
-        const int64_t d_cpu = __shfl_sync(kFull, f, 0), d_mem = __shfl_sync(kFull, f, 1), d_gpu = __shfl_sync(kFull, f, 2);
-        const int64_t e_cpu = __shfl_sync(kFull, f, 3), e_mem = __shfl_sync(kFull, f, 4), e_gpu = __shfl_sync(kFull, f, 5);
-        const int32_t kk = (int32_t)__shfl_sync(kFull, f, 6);
-        const int32_t grp = (int32_t)__shfl_sync(kFull, f, 7);
-        const int64_t off = __shfl_sync(kFull, f, 8), off1 = __shfl_sync(kFull, f, 9);
-        const int32_t slot = (int32_t)__shfl_sync(kFull, f, 10);
-        // ---- validation (types.SparkApplicationResources must be non-negative and inside the exact-int64 domain) ----
-        int bad = 0;
-        if (lane < 6) { if (f < 0) bad |= kErrNegativeRequest; if (f >= kMaxQuantity) bad |= kErrUnrepresentable; }
-        if (kk < 0) bad |= kErrNegativeRequest;
-        if (kk > kMaxCount) bad |= kErrUnrepresentable;
-        if (grp < 0 || grp >= s.n_groups) bad |= kErrBadGroup;
-        if (off < 0 || off1 - off != (int64_t)(kk > 0 ? kk : 0) || off1 > out_cap) bad |= kErrBadOffsets;
-        bad = __reduce_or_sync(kFull, bad);
-        int32_t d = -1;
-        if (bad) {
-            if (lane == 0) { atomicOr(err, bad); *err_host = bad; }
-        } else {
-            const GroupDesc g = grp == 0 ? g0 : s.groups[grp];
-            const uint32_t k = (uint32_t)kk;
-            bool need_scan = true;
-            if (slot >= 0) {
-                const ShapeEntry& en = tabs.entries[slot];
-                // the full tuple decides, not the fingerprint
-                if (en.id >= 0 && en.div[0].e == e_cpu && en.div[1].e == e_mem && en.div[2].e == e_gpu) {
-                    const uint32_t* tab = tabs.table + (size_t)en.id * tabs.pitch + g.sbase;
-                    const uint32_t total = tabs.total[(size_t)en.id * tabs.n_groups + grp];
-                    d = pack_app_tables<ALGO, OUT>(s, g, tab, total, en, d_cpu, d_mem, d_gpu, k, executor_nodes + off, ts, lane,
-                                                   snap_flags, need_scan);
-                }
-            }
-            if (need_scan) {
-                ts.fallback += 1;
-                d = scan_path_app<ALGO, OUT>(s, pa, d_cpu, d_mem, d_gpu, e_cpu, e_mem, e_gpu, kk, grp, executor_nodes + off,
-                                             scratch ? scratch + off : nullptr, wcache, st, lane, snap_flags);
-            }
-        }
-        if (lane == 0) driver_node[i] = d;
+        if (lane == 0 && n1 < (unsigned int)n) asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + n1));
+        const PrepApp* pa = prep + i;
+        const int32_t d = pack_app<ALGO, OUT>(s, pa, executor_nodes, scratch, wcache, st, lane, snap_flags, g0);
+        if (lane == 0) driver_node[listed[i]] = d;
+        ++apps_done;
         i = n1;
         n1 = __shfl_sync(kFull, n2, 0);
     }
     if (lane == 0) {
-        atomicAdd(stats + 0, st.nodes + ts.probes);
-        atomicAdd(stats + 1, st.drivers + ts.drivers);
-        atomicAdd(stats + 2, ts.fallback);
+        atomicAdd(stats + 0, st.nodes);
+        atomicAdd(stats + 1, st.drivers);
+        atomicAdd(stats + 2, apps_done);
         atomicAdd(stats + 3, st.nodes);
     }
 }
