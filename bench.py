@@ -201,11 +201,16 @@ def common_config(w: dict, q: int, world: int, total_exec: int) -> dict:
 
 
 def calibrated_sample(w: dict, cores: int, budget_s: float, cap: int) -> int:
-    """Applications per CPU step so that one step of the literal port takes about `budget_s` seconds on this host."""
-    probe = min(cap, 2000 if w["mode"] == 0 else 400)
-    _, _, times, _ = cpu_reference_run(w, probe, cores, repeats=1)
-    rate = probe / max(times[0], 1e-6)
-    return int(max(min(cap, rate * budget_s), min(cap, 1000)))
+    """Applications per CPU step so that one step of the literal port takes about `budget_s` seconds on this host
+    (the deep-scan workloads run at tens of decisions per second, the headline one at ~10^5)."""
+    probe, rate = min(cap, 4 * cores if w["mode"] == 0 else 64), 1.0
+    for _ in range(3):
+        _, _, times, _ = cpu_reference_run(w, probe, cores, repeats=1)
+        rate = probe / max(times[0], 1e-6)
+        if times[0] > 0.4 or probe >= cap:
+            break
+        probe = int(min(cap, max(probe * 8, rate * 0.8)))
+    return int(max(min(cap, rate * budget_s), min(cap, 2 * cores)))
 
 
 def run_reference_arm(args, w):
@@ -551,7 +556,9 @@ def main():
                  + q * (64 + 8) + 4 * k_total)
     nominal_bytes = q * (w["nodes"] * 8 * R + w["nodes"] * 4 + 64 + 8) + 4 * k_total
     pack_s = float(np.mean(pack_ns)) * 1e-9
-    kernel_name = f"gp_pack_{('tables' if fused else 'independent') if mode == 0 else 'fifo_cta'}<{ALGO_NAME[algo]}>"
+    tables_on = fused and os.environ.get("GANGPACK_TABLES", "1") != "0"
+    kernel_name = (("gp_decide_tables" if tables_on else "gp_pack_listed") if fused else
+                   ("gp_pack_independent" if mode == 0 else "gp_pack_fifo_cta")) + f"<{ALGO_NAME[algo]}>"
     tr = load_traffic(kernel_name, args.workload) if world == 1 else None
     traffic = tr["dram_bytes_per_launch"] if tr else None
     roofline = {
