@@ -480,6 +480,11 @@ def main():
         dist.barrier()
         if rank != 0:
             shm = shared_memory.SharedMemory(name=shm_name)
+            try:        # Python < 3.13 registers attached segments with its resource tracker, which would unlink rank 0's segment
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         dist.barrier()
         whole = np.frombuffer(shm.buf, dtype=np.uint8, count=int(base[-1]))
         mine = whole[int(base[rank]):int(base[rank + 1])]
@@ -632,7 +637,10 @@ def main():
         if world > 1:
             dist.barrier()
         if rank == 0:
-            shm.unlink()
+            try:
+                shm.unlink()
+            except FileNotFoundError:
+                pass
     if world > 1:
         dist.destroy_process_group()
     wd.cancel()
