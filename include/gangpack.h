@@ -69,9 +69,15 @@ typedef enum {
     GP_MODE_FIFO_EXACT = 2
 } gp_mode;
 
+/* gp_config.flags */
+#define GP_CFG_ASYNC_SNAPSHOT 1  /* gp_set_snapshot with page-locked (gp_alloc_pinned / gp_register_host) inputs returns while the
+                                    device is still reading them: the buffers must stay unchanged until the next gp_pack_* /
+                                    gp_get_snapshot / gp_synchronize call on the context has returned.  The upload then overlaps the
+                                    input copies of that call (one Predicate = snapshot + pack, back to back) */
 typedef struct {
     int32_t device;          /* CUDA device ordinal; -1 = current device */
-    int32_t reserved[7];
+    int32_t flags;           /* GP_CFG_* */
+    int32_t reserved[6];
 } gp_config;
 
 /* The node snapshot (NodeGroupSchedulingMetadata.AvailableResources, resources.go:61-100) plus the

@@ -306,7 +306,7 @@ struct DevBuf {
 
 // dev_misc layout: [0] error bits (int), [8..24) stats (2 x u64), [32..32+4*kMaxChunks) per-chunk work counters
 static constexpr size_t kMiscCounters = 64, kMiscBytes = 64 + 4 * 16;   // [0] err, [8..40) 4 x u64 statistics, [64..) counters
-static constexpr int32_t kChunkApps = 32768;
+static constexpr int32_t kChunkApps = 50000;
 static constexpr int32_t kZeroCopyOutApps = 8192;  // batches up to this size write results straight into mapped host memory   // apps per pipelined chunk of gp_pack_batch (~1.5 MB H2D, ~70 us of kernel)
 
 struct gp_ctx {
@@ -341,6 +341,7 @@ struct gp_ctx {
     size_t one_bytes = 0;
     int zero_copy = 1;                            // GANGPACK_ZERO_COPY=0 disables reading/writing mapped host buffers in kernels
     int use_tables = 1;                           // GANGPACK_TABLES=0: every independent decision takes the node-order scan
+    bool async_snapshot = false;                  // gp_config.flags & GP_CFG_ASYNC_SNAPSHOT
     int chunk_apps = kChunkApps;                  // GANGPACK_CHUNK_APPS
     int trace = 0;                                // GANGPACK_TRACE=1: host-side phase timing on stderr
     int pack_ctas_per_sm[3] = {0, 0, 0};            // occupancy of gp_pack_independent<ALGO> on this device
@@ -447,6 +448,7 @@ gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
     if (!c) { g_create_error = "gp_create: out of memory"; return GP_ERR_INVALID; }
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
+    c->async_snapshot = cfg && (cfg->flags & GP_CFG_ASYNC_SNAPSHOT);
     if (const char* z = std::getenv("GANGPACK_ZERO_COPY")) c->zero_copy = std::atoi(z);
     if (const char* z = std::getenv("GANGPACK_TABLES")) c->use_tables = std::atoi(z);
     if (const char* z = std::getenv("GANGPACK_CHUNK_APPS")) c->chunk_apps = std::max(1024, std::atoi(z));
@@ -579,33 +581,37 @@ gp_status gp_set_snapshot(gp_ctx* c, const gp_nodes* n) {
     if ((n_exec > 0 && !n->exec_order) || (n_drv > 0 && !n->drv_order))
         return fail(c, GP_ERR_INVALID, "gp_set_snapshot: order arrays missing");
     {
+        // owner[v] = 4 * group + (bit0: listed as executor candidate, bit1: listed as driver candidate); -1 = unseen
         std::vector<int32_t>& owner = c->v_owner;
-        std::vector<uint8_t>&seen_e = c->v_seen_e, &seen_d = c->v_seen_d;
         owner.assign((size_t)n->n_nodes, -1);
-        seen_e.assign((size_t)n->n_nodes, 0);
-        seen_d.assign((size_t)n->n_nodes, 0);
+        const uint32_t N = (uint32_t)n->n_nodes;
         for (int32_t g = 0; g < G; ++g) {
             for (int32_t e = n->exec_off[g]; e < n->exec_off[g + 1]; ++e) {
-                int32_t v = n->exec_order[e];
-                if (v < 0 || v >= n->n_nodes) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: exec_order index out of range");
-                if (seen_e[v]) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node listed twice in executor orders");
-                seen_e[v] = 1; owner[v] = g;
+                const uint32_t v = (uint32_t)n->exec_order[e];
+                if (v >= N) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: exec_order index out of range");
+                if (owner[v] >= 0) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node listed twice in executor orders");
+                owner[v] = 4 * g + 1;
             }
+        }
+        for (int32_t g = 0; g < G; ++g) {
             for (int32_t d = n->drv_off[g]; d < n->drv_off[g + 1]; ++d) {
-                int32_t v = n->drv_order[d];
-                if (v < 0 || v >= n->n_nodes) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: drv_order index out of range");
-                if (seen_d[v]) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node listed twice in driver orders");
-                if (owner[v] >= 0 && owner[v] != g)
-                    return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node belongs to two instance groups");
-                seen_d[v] = 1; owner[v] = g;
+                const uint32_t v = (uint32_t)n->drv_order[d];
+                if (v >= N) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: drv_order index out of range");
+                const int32_t o = owner[v];
+                if (o >= 0 && (o & 2)) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node listed twice in driver orders");
+                if (o >= 0 && (o >> 2) != g) return fail(c, GP_ERR_INVALID, "gp_set_snapshot: node belongs to two instance groups");
+                owner[v] = 4 * g + (o >= 0 ? (o & 3) : 0) + 2;
             }
         }
-        for (int32_t i = 0; i < n->n_nodes; ++i) {
-            int64_t a = n->avail_cpu_milli[i], b = n->avail_mem_bytes[i], g = n->avail_gpu ? n->avail_gpu[i] : 0;
-            if (a >= kMaxQuantity || a <= -kMaxQuantity || b >= kMaxQuantity || b <= -kMaxQuantity ||
-                g >= kMaxQuantity || g <= -kMaxQuantity)
-                return fail(c, GP_ERR_UNREPRESENTABLE, "gp_set_snapshot: |quantity| >= 2^61");
+        // exact-int64 domain: branch-free so that the loop vectorises
+        const int64_t* cols[3] = {n->avail_cpu_milli, n->avail_mem_bytes, n->avail_gpu};
+        uint64_t out_of_domain = 0;
+        for (int k = 0; k < 3; ++k) {
+            const int64_t* p = cols[k];
+            if (!p) continue;
+            for (uint32_t i = 0; i < N; ++i) out_of_domain |= (uint64_t)(p[i] >= kMaxQuantity) | (uint64_t)(p[i] <= -kMaxQuantity);
         }
+        if (out_of_domain) return fail(c, GP_ERR_UNREPRESENTABLE, "gp_set_snapshot: |quantity| >= 2^61");
     }
     GP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -656,7 +662,9 @@ gp_status gp_set_snapshot(gp_ctx* c, const gp_nodes* n) {
     dn.exec_order = c->exec_order.as<int32_t>(); dn.drv_order = c->drv_order.as<int32_t>();
     gp_status s = build_snapshot_device(c, &dn, n_exec, n_drv, st);
     if (s != GP_OK) return s;
-    GP_CUDA(c, cudaStreamSynchronize(st));   // the caller may reuse its host buffers
+    // GP_CFG_ASYNC_SNAPSHOT with page-locked inputs: return while the device is still reading them -- the upload and the
+    // slot layout then overlap the H2D copies of the gp_pack_* call that follows
+    if (!(c->async_snapshot && all_mapped)) GP_CUDA(c, cudaStreamSynchronize(st));   // the caller may reuse its host buffers
     return GP_OK;
 }
 
@@ -1101,8 +1109,7 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
         const int32_t lo = (int32_t)((int64_t)q * ch / n_chunks), hi = (int32_t)((int64_t)q * (ch + 1) / n_chunks);
         const size_t n = (size_t)(hi - lo);
         cudaStream_t ls = n_chunks == 1 ? st : c->lane[ch % gp_ctx::kLanes];
-        if (n_chunks > 1) GP_CUDA(c, cudaStreamWaitEvent(ls, c->ev_ready, 0));
-        // ---- inputs -> HBM ----------------------------------------------------------------------------------
+        // ---- inputs -> HBM (the copies need not wait for the snapshot layout; the kernels below do) ----------------------------------------------------------------------------------
         bool gathered = false;
         if (small && !a->skip_if_no_fit) {
             CopyJobs jobs{};
@@ -1155,6 +1162,7 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
             if (a->group) GP_CUDA(c, cudaMemcpyAsync(c->a_group.as<int32_t>() + lo, a->group + lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ls));
             if (a->skip_if_no_fit) GP_CUDA(c, cudaMemcpyAsync(c->a_skip.as<uint8_t>() + lo, a->skip_if_no_fit + lo, n, cudaMemcpyHostToDevice, ls));
         }
+        if (n_chunks > 1) GP_CUDA(c, cudaStreamWaitEvent(ls, c->ev_ready, 0));
         // ---- this chunk's ExecutorNodes range ------------------------------------------------------------------
         int64_t e0, e1;
         if (off) { e0 = off[lo]; e1 = off[hi]; }

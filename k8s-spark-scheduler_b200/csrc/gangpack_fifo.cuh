@@ -369,8 +369,8 @@ __device__ __forceinline__ int32_t fifo_app(const Snapshot& s, const GroupDesc& 
 }
 
 // ---- one application, warp 0 alone ------------------------------------------------------------------------------
-constexpr int kWarpWinE = 16;          // executor windows of 32 nodes the warp tries before it calls the CTA (512 nodes)
-constexpr int kWarpWinD = 8;           // driver windows (256 candidates)
+constexpr int kWarpWinE = 32;          // executor windows of 32 nodes the warp tries before it calls the CTA (1 024 nodes)
+constexpr int kWarpWinD = 32;          // driver windows (1 024 candidates)
 constexpr int32_t kEscalate = -3;      // "the whole CTA must decide this application" (never stored as a result)
 
 __device__ __forceinline__ void bar_sync_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
         int32_t start_e = 0, start_d = 0;
         bool blocked = false;
         uint32_t seq = 0;
+        unsigned long long escalated = 0;
         for (int32_t t = 0; t < my_cnt; ++t) {
             const int32_t app = mine ? mine[t] : t;
             if (lane == 0 && t + 1 < my_cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + (mine ? mine[t + 1] : t + 1)));
@@ -571,6 +572,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
                     int32_t r = (fl & kAppFast) ? fifo_app_warp<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, lane)
                                                 : fifo_app_warp<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, lane);
                     if (r == kEscalate) {
+                        ++escalated;
                         if (lane == 0) { sh.first_live_e = start_e; sh.first_live_d = start_d; sh.cmd_app = app; sh.cmd_seq = seq; }
                         __syncwarp();
                         bar_sync_named(1, nt);                     // wake the helper warps
@@ -585,7 +587,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
             }
             if (lane == 0) driver_node[app] = d;
         }
-        if (lane == 0) sh.cmd_app = -1;
+        if (lane == 0) { sh.cmd_app = -1; if (escalated) atomicAdd(stats + 2, escalated); }   // stats[2]: applications decided by the whole CTA
         __syncwarp();
         bar_sync_named(1, nt);                                     // release the helpers
     } else {

@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(kClassifyThreads) gp_classify_apps(int32_t n_a
         int32_t slot = (int32_t)(fp & (kShapeSlots - 1));
         for (int p = 0; p < kShapeProbes && found < 0; ++p) {
             ShapeEntry* en = tabs.entries + slot;
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&en->key);
+            // plain (L1-cacheable) load: a key never changes once set, and a stale 0 is resolved by the CAS below --
+            // 100 000 threads polling a dozen L2 lines with volatile loads serialise on those lines
+            unsigned long long cur = en->key;
             if (cur == 0) {
                 cur = atomicCAS(&en->key, 0ull, fp);
                 if (cur == 0) {
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kClassifyThreads) gp_classify_apps(int32_t n_a
         int32_t slot = (int32_t)(fp & (kShapeSlots - 1));
         for (int p = 0; p < kShapeProbes && dfound < 0; ++p) {
             DriverEntry* en = tabs.dentries + slot;
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&en->key);
+            unsigned long long cur = en->key;
             if (cur == 0) {
                 cur = atomicCAS(&en->key, 0ull, fp);
                 if (cur == 0) {

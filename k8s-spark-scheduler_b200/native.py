@@ -69,7 +69,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 class gp_config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("reserved", C.c_int32 * 7)]
+    _fields_ = [("device", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+CFG_ASYNC_SNAPSHOT = 1
 
 
 class gp_nodes(C.Structure):
@@ -282,10 +285,10 @@ class PinnedArray:
 class GangPacker:
     """One gp_ctx.  Not thread-safe (like the C ABI)."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, async_snapshot: bool = False):
         L = load()
         self._h = C.c_void_p()
-        cfg = gp_config(device=device)
+        cfg = gp_config(device=device, flags=CFG_ASYNC_SNAPSHOT if async_snapshot else 0)
         st = L.gp_create(C.byref(self._h), C.byref(cfg))
         if st != 0:
             raise GangpackError(st, (L.gp_last_error(None) or b"").decode())
@@ -540,6 +543,51 @@ class GangPacker:
     def apply_usage_delta(self, node, cpu, mem, gpu=None, sign=1):
         n, c, m, g = _np(node, np.int32), _np(cpu, np.int64), _np(mem, np.int64), _np(gpu, np.int64)
         self._check(load().gp_apply_usage_delta(self._h, len(n), _p(n), _p(c), _p(m), _p(g), sign))
+
+    # ---- bound calls: what a shim does -- marshal the argument structs ONCE over its long-lived buffers, then one FFI call
+    # per Predicate (the numpy / ctypes marshalling of set_snapshot() / pack_batch() costs more than a small batch's kernels)
+    def bind_snapshot(self, avail_cpu, avail_mem, avail_gpu, exec_order, drv_order, exec_off, drv_off):
+        """-> zero-argument callable running gp_set_snapshot on these (caller-owned, stable) arrays."""
+        keep = [_np(avail_cpu, np.int64), _np(avail_mem, np.int64), _np(avail_gpu, np.int64), _np(exec_order, np.int32),
+                _np(drv_order, np.int32), _np(exec_off, np.int32), _np(drv_off, np.int32)]
+        n = gp_nodes(n_nodes=len(keep[0]), avail_cpu_milli=_p(keep[0]), avail_mem_bytes=_p(keep[1]), avail_gpu=_p(keep[2]),
+                     n_groups=len(keep[5]) - 1, exec_off=_p(keep[5]), exec_order=_p(keep[3]), drv_off=_p(keep[6]), drv_order=_p(keep[4]))
+        fn, h, ref = load().gp_set_snapshot, self._h, C.byref(n)
+        self.n_nodes = len(keep[0])
+
+        def call(_keep=(keep, n)):
+            st = fn(h, ref)
+            if st != 0:
+                self._check(st)
+        return call
+
+    def bind_batch(self, apps: dict, algo: int, mode: int, out, wire: dict):
+        """-> zero-argument callable running gp_pack_batch_wire on these (caller-owned, stable) arrays; results land in `out`."""
+        bits = int(wire.get("quantity_bits", 64))
+        qdt = np.int64 if bits == 64 else np.int32
+        q = len(apps["count"])
+        keep = {k: _np(apps.get(k), qdt) for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}
+        keep["count"] = _np(apps["count"], np.int32)
+        keep["group"] = _np(apps.get("group"), np.int32)
+        keep["young"] = _np(apps.get("young"), np.uint8)
+        keep["off"] = _np(apps.get("off"), np.int64) if wire.get("offsets", True) else None
+        if wire.get("offsets", True) and keep["off"] is None:
+            raise ValueError("bind_batch: wire.offsets is set but apps has no 'off'")
+        driver_node, executor_nodes = out
+        a = gp_apps_wire(n_apps=q, quantity_bits=bits, mem_shift=int(wire.get("mem_shift", 0)),
+                         drv_cpu=_p(keep["drv_cpu"]), drv_mem=_p(keep["drv_mem"]), drv_gpu=_p(keep["drv_gpu"]),
+                         exe_cpu=_p(keep["exe_cpu"]), exe_mem=_p(keep["exe_mem"]), exe_gpu=_p(keep["exe_gpu"]),
+                         exe_count=_p(keep["count"]), group=_p(keep["group"]), skip_if_no_fit=_p(keep["young"]),
+                         exec_out_off=_p(keep["off"]))
+        r = gp_results_wire(driver_node=_p(driver_node), executor_nodes=_p(executor_nodes),
+                            executor_nodes_cap=len(executor_nodes), node_bits=int(wire.get("node_bits", 32)))
+        fn, h, ra, rr = load().gp_pack_batch_wire, self._h, C.byref(a), C.byref(r)
+
+        def call(_keep=(keep, a, r, out)):
+            st = fn(h, ra, algo, mode, rr)
+            if st != 0:
+                self._check(st)
+        return call
 
     def pack_one(self, algo, drv, exe, count):
         """binpack.SparkBinPackFunction for one app -> (has_capacity, driver_node, executor_nodes)."""

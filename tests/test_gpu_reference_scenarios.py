@@ -115,8 +115,12 @@ def test_dynamic_allocation_scenarios(packer):
     # "soft reservations are created on full nodes first" (:209-224): driver restricted to node2
     x = MiniExtender(packer, nodes, 0)
     d, e = x.schedule_driver("app", DRV, POD, 1, ["node2"])
-    assert (d, e) == ("node2", ["node2"])
-    assert x.bind_to_reservation("app", "exec-0", nodes) == "node2"
+    # the driver may only go to node2; the executor order still holds both (equally free) nodes, node1 first by name, so
+    # tightly-pack reserves the executor slot on node1 ...
+    assert (d, e) == ("node2", ["node1"])
+    # ... but kube-scheduler offers exec-0 only [node2] (`nodeNames[1:]`): its reservation moves with it
+    assert x.bind_to_reservation("app", "exec-0", ["node2"]) == "node2"
+    # now node2 is the fuller node: it sorts first and takes the extra executor (expectedPodToNodeSoftReservationsMap: node2)
     assert x.schedule_extra_executor("app", "exec-1", POD, nodes) == "node2"
     # "schedules an executor only in the same AZ as the original application" (:263-292): static app on node1, the dynamic
     # app (min 0) on node2; its executors are restricted to the application's zone = {node2} by the control plane
