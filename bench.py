@@ -468,34 +468,11 @@ def main():
         # packs its own host-resident block of the queue and copies ITS placements over ITS OWN PCIe link straight into the
         # scheduler's result buffer -- a POSIX shared-memory segment page-locked by every worker (gp_register_host).  No
         # gather through one GPU, no collective on the results.  Wall clock between barriers, max over ranks.
-        from multiprocessing import shared_memory
+        from k8s_spark_scheduler_b200 import multigpu
         node_dt = np.uint16 if (wire and wire["node_bits"] == 16) else np.int32
-        my_bytes = ((4 * q + node_dt().itemsize * max(total_exec, 1)) + 255) & ~255          # [driver int32 | ExecutorNodes]
-        sizes = torch.tensor([my_bytes], device=dev, dtype=torch.int64)
-        all_sizes = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(all_sizes, sizes)
-        base = np.concatenate([[0], np.cumsum([int(x.item()) for x in all_sizes])])
-        shm_name = f"gangpack_bench_{os.environ.get('MASTER_PORT', '0')}"
-        if rank == 0:
-            try:
-                shared_memory.SharedMemory(name=shm_name).unlink()      # stale segment of a killed run
-            except FileNotFoundError:
-                pass
-            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=int(base[-1]))
-        dist.barrier()
-        if rank != 0:
-            shm = shared_memory.SharedMemory(name=shm_name)
-            try:        # Python < 3.13 registers attached segments with its resource tracker, which would unlink rank 0's segment
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(shm._name, "shared_memory")
-            except Exception:
-                pass
-        dist.barrier()
-        whole = np.frombuffer(shm.buf, dtype=np.uint8, count=int(base[-1]))
-        mine = whole[int(base[rank]):int(base[rank + 1])]
-        packer.register_host(mine)
-        out_driver = mine[:4 * q].view(np.int32)
-        out_exec = mine[4 * q:4 * q + node_dt().itemsize * max(total_exec, 1)].view(node_dt)
+        shm = multigpu.SharedResults(f"gangpack_bench_{os.environ.get('MASTER_PORT', '0')}", q, total_exec, node_dt, device=dev)
+        packer.register_host(shm.mine)
+        out_driver, out_exec = shm.driver, shm.executors
         h_snap = torch.empty(snapbuf.numel(), dtype=torch.int64).pin_memory()
         h_snap.copy_(snapbuf.cpu())
         h2d = in_bytes + (snapbuf.numel() * 8 if rank == 0 else 0)
@@ -507,7 +484,7 @@ def main():
             with torch.cuda.stream(stream):
                 if rank == 0:
                     snapbuf.copy_(h_snap, non_blocking=True)
-                dist.broadcast(snapbuf, src=0)
+                multigpu.broadcast_snapshot(snapbuf, src=0)
                 packer.set_snapshot_device(tn["cpu"], tn["mem"], tn["gpu"], tn["eoff"], tn["eorder"], tn["eoff"], tn["eorder"])
             call_pack()
             return int(out_driver[0])
@@ -547,8 +524,18 @@ def main():
         int((np.asarray(out_exec[:total_exec])[emask] != dev_exec_np[:total_exec][emask]).sum())
     if world > 1:
         t = torch.tensor([path_mism], device=dev, dtype=torch.int64); dist.all_reduce(t); path_mism = int(t.item())
-        # (b) rank 0 -- the consumer -- finds every rank's block in the shared buffer: spot-check against rank 0's own view
+        # (b) rank 0 -- the consumer -- finds every rank's block in the shared buffer: each rank publishes a checksum of the
+        # placements it computed on the device, rank 0 recomputes them from the shared segment
         dist.barrier()
+        mine_sum = torch.tensor([int(dev_driver_np.astype(np.int64).sum()), int(dev_exec_np[:total_exec][emask].astype(np.int64).sum())],
+                                device=dev, dtype=torch.int64)
+        sums = [torch.zeros(2, device=dev, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sums, mine_sum)
+        if rank == 0:
+            for r in range(1, world):
+                rd, _ = shm.block(r)
+                if int(rd.astype(np.int64).sum()) != int(sums[r][0].item()):
+                    path_mism += 1
 
     # ---- roofline of the dominant kernel (pack) ----------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -633,21 +620,10 @@ def main():
     del graph, evs
     del snapbuf, tn, ta, d_driver, d_exec, flush
     pin = pn = out_driver = out_exec = None
-    if shm is not None:
-        whole = mine = None
+    call_pack = call_snapshot = None
     packer.close()                                    # frees pinned blocks, unregisters the shared segment, gp_destroy
     if shm is not None:
-        try:
-            shm.close()
-        except BufferError:
-            pass
-        if world > 1:
-            dist.barrier()
-        if rank == 0:
-            try:
-                shm.unlink()
-            except FileNotFoundError:
-                pass
+        shm.close()
     if world > 1:
         dist.destroy_process_group()
     wd.cancel()

@@ -1,22 +1,21 @@
-"""App-sharded gang placement over the GPUs of one box (independent mode).
+"""One process per GPU on one box: what `bench.py --gpus N` runs between the ranks.
 
-One process per GPU (torch.distributed, NCCL over NVLink).  The path shards naturally: pending
-applications are independent units against one snapshot, so
+The placement path has NO exchange step -- pending applications are independent units against one snapshot (independent
+mode) and the FIFO queues of different instance groups are independent -- so the only things that move between the
+processes are the multi-GPU analogues of H2D and D2H:
 
-  1. rank 0 owns the node snapshot -> ONE broadcast of (avail cpu, mem, gpu, executor order, driver order);
-  2. every rank packs its contiguous block of the queue on its own GPU (no collective in the data path);
-  3. the emitted placements (driver node per app, ExecutorNodes) are all-gathered, padded to the largest
-     shard so the collective is regular, and re-assembled in queue order.
+  * the node snapshot: ONE broadcast of a flat buffer from the rank that owns the cluster state (`broadcast_snapshot`);
+  * the placements: every rank copies ITS block straight into the scheduler's result buffer, a POSIX shared-memory segment
+    that all worker processes of the box map and page-lock (`SharedResults`); on the GPU box the copy is a DMA over the
+    rank's own PCIe link (gp_register_host + gp_pack_batch_wire), no gather through one GPU and no collective.
 
-FIFO mode shards by instance group instead (whole groups -> ranks; a group's queue is strictly
-sequential): `assign_groups`.
-
-The collectives work on whatever backend the process group has: NCCL on the GPU box, gloo in the CPU
-tests (tests/test_multigpu_gloo.py), where the per-shard pack function is supplied by the test.
+The same code runs over gloo on CPU in tests/test_multigpu_gloo.py (world size 2, the per-rank packer being the oracle).
+A single host process that drives several GPUs uses gp_multi_* (csrc/gangpack_multi.cu) instead.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Tuple
+from multiprocessing import shared_memory
+from typing import Tuple
 
 import numpy as np
 import torch
@@ -28,67 +27,66 @@ def shard_bounds(q: int, rank: int, world: int) -> Tuple[int, int]:
     return (q * rank) // world, (q * (rank + 1)) // world
 
 
-def assign_groups(cost: List[int], world: int) -> List[int]:
-    """Greedy longest-processing-time assignment of instance groups to ranks (FIFO mode):
-    cost[g] ~ apps_g * nodes_g.  Returns owner rank per group."""
-    owner = [0] * len(cost)
-    load = [0] * world
-    for g in sorted(range(len(cost)), key=lambda i: -cost[i]):
-        r = min(range(world), key=lambda i: load[i])
-        owner[g] = r
-        load[r] += cost[g]
-    return owner
+def broadcast_snapshot(flat: torch.Tensor, src: int = 0, group=None) -> None:
+    """One broadcast of the flat snapshot buffer [cpu | mem | gpu | orders] from the rank that owns the cluster state."""
+    dist.broadcast(flat, src=src, group=group)
 
 
-def broadcast_snapshot(t: Dict[str, torch.Tensor], src: int = 0, group=None) -> None:
-    """One broadcast per snapshot array from the rank that owns the cluster state."""
-    for k in ("cpu", "mem", "gpu", "eorder", "dorder"):
-        if k in t and t[k] is not None:
-            dist.broadcast(t[k], src=src, group=group)
+class SharedResults:
+    """The scheduler's result buffer, shared by the worker processes of one box.
 
+    Rank r owns bytes [base[r], base[r+1]): `driver` (int32 x q_r) followed by `executors` (node_dtype x total_r).
+    Rank 0 -- the consumer -- sees every rank's block through `block(r, q_r, total_r)`."""
 
-def gather_placements(driver_local: torch.Tensor, exec_local: torch.Tensor, n_exec_local: int, group=None):
-    """All-gather (driver_node, executor_nodes) of every shard and re-assemble them in queue order.
+    def __init__(self, name: str, q: int, total_exec: int, node_dtype, device=None, group=None):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.node_dtype = np.dtype(node_dtype)
+        self.q, self.total = int(q), int(total_exec)
+        my_bytes = ((4 * self.q + self.node_dtype.itemsize * max(self.total, 1)) + 255) & ~255
+        dev = device if device is not None else torch.device("cpu")
+        sizes = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(self.world)]
+        dist.all_gather(sizes, torch.tensor([my_bytes, self.q, self.total], dtype=torch.int64, device=dev), group=group)
+        self.sizes = np.stack([s.cpu().numpy() for s in sizes])
+        self.base = np.concatenate([[0], np.cumsum(self.sizes[:, 0])]).astype(np.int64)
+        if self.rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()      # stale segment of a killed run
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=int(self.base[-1]))
+        dist.barrier(group=group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+            try:        # Python < 3.13 registers attached segments with its resource tracker, which would unlink rank 0's segment
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        dist.barrier(group=group)
+        self.whole = np.frombuffer(self.shm.buf, dtype=np.uint8, count=int(self.base[-1]))
+        self.mine = self.whole[int(self.base[self.rank]):int(self.base[self.rank + 1])]
+        self.driver, self.executors = self._split(self.mine, self.q, self.total)
+        self._group = group
 
-    driver_local: int32 [q_local]; exec_local: int32 [>= n_exec_local].
-    Returns (driver_all int32 [sum q], exec_all int32 [sum n_exec], exec_base int64 [world+1]) where
-    shard r's executor offsets must be shifted by exec_base[r]."""
-    world = dist.get_world_size(group)
-    dev = driver_local.device
-    sizes = torch.tensor([driver_local.numel(), int(n_exec_local)], dtype=torch.int64, device=dev)
-    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes, group=group)
-    all_sizes = torch.stack(all_sizes).cpu().numpy()
-    max_q, max_e = int(all_sizes[:, 0].max()), max(int(all_sizes[:, 1].max()), 1)
-    dpad = torch.full((max_q,), -9, dtype=torch.int32, device=dev)
-    dpad[: driver_local.numel()] = driver_local
-    epad = torch.full((max_e,), -9, dtype=torch.int32, device=dev)
-    epad[: int(n_exec_local)] = exec_local[: int(n_exec_local)]
-    dg = torch.empty(max_q * world, dtype=torch.int32, device=dev)
-    eg = torch.empty(max_e * world, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(dg, dpad, group=group)
-    dist.all_gather_into_tensor(eg, epad, group=group)
-    dparts = [dg[r * max_q: r * max_q + int(all_sizes[r, 0])] for r in range(world)]
-    eparts = [eg[r * max_e: r * max_e + int(all_sizes[r, 1])] for r in range(world)]
-    exec_base = np.zeros(world + 1, dtype=np.int64)
-    np.cumsum(all_sizes[:, 1], out=exec_base[1:])
-    return torch.cat(dparts), torch.cat(eparts), exec_base
+    def _split(self, block, q, total):
+        d = block[:4 * q].view(np.int32)
+        e = block[4 * q:4 * q + self.node_dtype.itemsize * max(total, 1)].view(self.node_dtype)
+        return d, e
 
+    def block(self, r: int):
+        """(driver_node, executor_nodes) of rank r as the consumer sees them."""
+        b = self.whole[int(self.base[r]):int(self.base[r + 1])]
+        return self._split(b, int(self.sizes[r, 1]), int(self.sizes[r, 2]))
 
-def sharded_pack(apps: Dict[str, np.ndarray], snapshot: Dict[str, torch.Tensor],
-                 pack_shard: Callable[[Dict[str, np.ndarray], Dict[str, torch.Tensor]], Tuple[torch.Tensor, torch.Tensor, int]],
-                 group=None):
-    """Full multi-GPU round for an independent batch.
-
-    apps: the WHOLE queue as host arrays (every rank sees the same queue, e.g. decoded from the same
-    request); snapshot: device tensors, valid on rank 0 (others receive them).  pack_shard(local_apps,
-    snapshot) -> (driver_local, exec_local, n_exec_local) runs the single-GPU hot path.
-    Returns (driver_node [q], executor_nodes [sum count]) in queue order on every rank."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    q = len(apps["count"])
-    lo, hi = shard_bounds(q, rank, world)
-    broadcast_snapshot(snapshot, 0, group)
-    local = {k: (np.ascontiguousarray(v[lo:hi]) if v is not None else None) for k, v in apps.items() if k != "off"}
-    d_local, e_local, n_e = pack_shard(local, snapshot)
-    d_all, e_all, _ = gather_placements(d_local, e_local, n_e, group)
-    return d_all, e_all
+    def close(self):
+        self.whole = self.mine = self.driver = self.executors = None
+        try:
+            self.shm.close()
+        except BufferError:
+            pass
+        dist.barrier(group=self._group)
+        if self.rank == 0:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
