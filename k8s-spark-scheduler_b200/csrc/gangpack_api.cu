@@ -791,9 +791,8 @@ static gp_status launch_tables(gp_ctx* c, const Snapshot& s, const AppColumns& c
             GP_CUDA(c, cudaFuncSetAttribute(gp_build_shape_tables<ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes));
             attr = true;
         }
-        gp_build_shape_tables<ALGO><<<dim3(kMaxShapes, (unsigned)c->n_groups), kTabThreads, kTabSmemBytes, st>>>(s, tabs);
-        gp_build_driver_firstfit<<<dim3(kMaxShapes, (unsigned)c->n_groups), 256, 0, st>>>(s, tabs);
-        c->last.kernel_launches += 2;
+        gp_build_shape_tables<ALGO><<<dim3(2 * kMaxShapes, (unsigned)c->n_groups), kTabThreads, kTabSmemBytes, st>>>(s, tabs);
+        c->last.kernel_launches += 1;
     }
     if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][1], st));
     gp_decide_tables<ALGO, OUT><<<(q + kDecideThreads - 1) / kDecideThreads, kDecideThreads, 0, st>>>(
@@ -1549,15 +1548,15 @@ static gp_status stage_sort(gp_ctx* c, const gp_sort_input* in, const long long*
     if (!d_cpu) { GP_CUDA(c, up(o_cpu, in->avail_cpu_milli, 8 * N)); d_cpu = (const long long*)(b + o_cpu); }
     if (!d_mem) { GP_CUDA(c, up(o_mem, in->avail_mem_bytes, 8 * N)); d_mem = (const long long*)(b + o_mem); }
     if (!d_gpu && in->avail_gpu) { GP_CUDA(c, up(o_gpu, in->avail_gpu, 8 * N)); d_gpu = (const long long*)(b + o_gpu); }
-    if (in->zone_id) GP_CUDA(c, up(o_zone, in->zone_id, 4 * N)); else GP_CUDA(c, cudaMemsetAsync(b + o_zone, 0, 4 * N, st));
+    const bool zoned = in->zone_id != nullptr && in->n_zones > 1;       // one zone: priority 0 for every node, nothing to total
+    if (zoned) GP_CUDA(c, up(o_zone, in->zone_id, 4 * N));
     if (in->name_rank) GP_CUDA(c, up(o_nr, in->name_rank, 4 * N));
-    else { c->iota.resize(N); for (int32_t i = 0; i < n; ++i) c->iota[(size_t)i] = i; GP_CUDA(c, up(o_nr, c->iota.data(), 4 * N)); }
     if (in->is_driver_candidate) GP_CUDA(c, up(o_fc, in->is_driver_candidate, N));
     if (in->unschedulable) GP_CUDA(c, up(o_fu, in->unschedulable, N));
     if (in->ready) GP_CUDA(c, up(o_fr, in->ready, N));
     if (in->driver_label_rank) GP_CUDA(c, up(o_lrd, in->driver_label_rank, 4 * N));
     if (in->executor_label_rank) GP_CUDA(c, up(o_lre, in->executor_label_rank, 4 * N));
-    GP_CUDA(c, cudaMemsetAsync(b + o_tot, 0, 16 * Z, st));
+    if (zoned) GP_CUDA(c, cudaMemsetAsync(b + o_tot, 0, 16 * Z, st));
     if (!c->sort_attr_set) {
         GP_CUDA(c, cudaFuncSetAttribute(gp_sort_tiles<SortKey>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortTile * sizeof(SortKey))));
         c->sort_attr_set = true;
@@ -1568,9 +1567,12 @@ static gp_status stage_sort(gp_ctx* c, const gp_sort_input* in, const long long*
     SortKey* keys = (SortKey*)(b + o_keys);
     SortKey* sorted = (SortKey*)(b + o_sorted);
     int32_t* pos = (int32_t*)(b + o_pos);
-    gp_zone_totals<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (unsigned long long*)(b + o_tot));
-    gp_zone_priority<<<(in->n_zones + T - 1) / T, T, 0, st>>>(in->n_zones, (const unsigned long long*)(b + o_tot), (int32_t*)(b + o_prio));
-    gp_make_keys<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (const int32_t*)(b + o_prio), (const int32_t*)(b + o_nr), keys);
+    if (zoned) {
+        gp_zone_totals<<<nb, T, 0, st>>>(n, d_cpu, d_mem, (const int32_t*)(b + o_zone), (unsigned long long*)(b + o_tot));
+        gp_zone_priority<<<(in->n_zones + T - 1) / T, T, 0, st>>>(in->n_zones, (const unsigned long long*)(b + o_tot), (int32_t*)(b + o_prio));
+    }
+    gp_make_keys<<<nb, T, 0, st>>>(n, d_cpu, d_mem, zoned ? (const int32_t*)(b + o_zone) : nullptr, (const int32_t*)(b + o_prio),
+                                   in->name_rank ? (const int32_t*)(b + o_nr) : nullptr, keys);
     gp_sort_tiles<SortKey><<<ntile, kSortThreads, kSortTile * sizeof(SortKey), st>>>(n, nullptr, keys, sorted);
     gp_rank_by_search<SortKey><<<nb, T, 0, st>>>(n, nullptr, keys, sorted, pos);
     gp_scatter_order<<<nb, T, 0, st>>>(n, pos, (int32_t*)(b + o_order));

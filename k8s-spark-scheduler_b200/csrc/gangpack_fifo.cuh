@@ -369,8 +369,12 @@ __device__ __forceinline__ int32_t fifo_app(const Snapshot& s, const GroupDesc& 
 }
 
 // ---- one application, warp 0 alone ------------------------------------------------------------------------------
-constexpr int kWarpWinE = 32;          // executor windows of 32 nodes the warp tries before it calls the CTA (1 024 nodes)
-constexpr int kWarpWinD = 32;          // driver windows (1 024 candidates)
+// A single warp is bound by the LATENCY of its dependent instruction chain (measured: ~450 instructions and 2 us per
+// application with one node per lane per step), so every step is made wide: 4 driver candidates and 2 executor nodes per
+// lane (128 / 64 per step) -- the usual application then needs ONE driver step and ONE executor step, and the independent
+// per-element work inside a step overlaps.
+constexpr int kWarpWinE = 16;          // executor steps of 64 nodes the warp tries before it calls the CTA (1 024 nodes)
+constexpr int kWarpWinD = 8;           // driver steps of 128 candidates (1 024 candidates)
 constexpr int32_t kEscalate = -3;      // "the whole CTA must decide this application" (never stored as a result)
 
 __device__ __forceinline__ void bar_sync_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -384,7 +388,7 @@ template <int ALGO, int FIFO_MODE, bool FAST>
 __device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupDesc& g, const FifoView& view, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, uint16_t* __restrict__ cache,
                                                  int32_t& start_e, int32_t& start_d, WarpStats& st, const GroupMin& gm,
-                                                 bool drv_identity, int lane) {
+                                                 bool drv_identity, bool refresh, int lane) {
     FifoCaps<FAST> a;
     a.init(pa, (pa->flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
     const uint32_t k = a.k;
@@ -394,39 +398,47 @@ __device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupD
     const int32_t* slot_node = s.slot_node + g.sbase;
     const bool ug = a.use_gpu;
 
-    // ---- advance the dead prefixes: nodes that can host nothing for ANY application of the batch (GroupMin) ----
-    for (int t = 0; t < 4 && start_e < ne; ++t) {
-        const int32_t i = start_e + lane;
-        const bool alive = i < ne && !dead_for(gm.exe, view.pair(i), ug ? view.gpu(i) : 0, ug);
-        const unsigned vote = __ballot_sync(kFull, alive);
-        if (vote) { start_e += __ffs(vote) - 1; break; }
-        start_e = min(ne, start_e + kWarp);
-    }
-    for (int t = 0; t < 4 && start_d < nd; ++t) {
-        const int32_t j = start_d + lane;
-        bool alive = false;
-        if (j < nd) {
-            const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
-            alive = !dead_for(gm.drv, view.pair(ls), ug ? view.gpu(ls) : 0, ug);
+    // ---- every 4th application: advance the dead prefixes -- nodes that can host nothing for ANY application of the
+    // batch (GroupMin); availability only decreases, so such nodes stay dead
+    if (refresh) {
+        for (int t = 0; t < 4 && start_e < ne; ++t) {
+            const int32_t i = start_e + lane;
+            const bool alive = i < ne && !dead_for(gm.exe, view.pair(i), ug ? view.gpu(i) : 0, ug);
+            const unsigned vote = __ballot_sync(kFull, alive);
+            if (vote) { start_e += __ffs(vote) - 1; break; }
+            start_e = min(ne, start_e + kWarp);
         }
-        const unsigned vote = __ballot_sync(kFull, alive);
-        if (vote) { start_d += __ffs(vote) - 1; break; }
-        start_d = min(nd, start_d + kWarp);
+        for (int t = 0; t < 4 && start_d < nd; ++t) {
+            const int32_t j = start_d + lane;
+            bool alive = false;
+            if (j < nd) {
+                const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
+                alive = !dead_for(gm.drv, view.pair(ls), ug ? view.gpu(ls) : 0, ug);
+            }
+            const unsigned vote = __ballot_sync(kFull, alive);
+            if (vote) { start_d += __ffs(vote) - 1; break; }
+            start_d = min(nd, start_d + kWarp);
+        }
     }
 
-    // ---- first driver candidate that fits -----------------------------------------------------------------------
+    // ---- first driver candidate that fits: lane l owns the 4 CONSECUTIVE candidates j0 + 4l .. j0 + 4l + 3, so the first
+    // fitting candidate of the step is a plain minimum over the lanes (one REDUX) ----------------------------------------
     int32_t j1 = -1, j0 = start_d;
-    for (int w = 0; j0 < nd && j1 < 0 && w < kWarpWinD; ++w, j0 += kWarp) {
-        const int32_t j = j0 + lane;
-        bool fits = false;
-        if (j < nd) {
-            const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
-            const longlong2 v = view.pair(ls);
-            fits = !(a.d_cpu > v.x) && !(a.d_mem > v.y) && !(ug && a.d_gpu > view.gpu(ls));
+    for (int w = 0; j0 < nd && j1 < 0 && w < kWarpWinD; ++w, j0 += 4 * kWarp) {
+        int32_t mine = 0x7fffffff;
+#pragma unroll
+        for (int u = 3; u >= 0; --u) {
+            const int32_t j = j0 + 4 * lane + u;
+            if (j < nd) {
+                const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
+                const longlong2 v = view.pair(ls);
+                const bool fits = !(a.d_cpu > v.x) && !(a.d_mem > v.y) && !(ug && a.d_gpu > view.gpu(ls));
+                if (fits) mine = j;
+            }
         }
-        const unsigned vote = __ballot_sync(kFull, fits);
-        st.drivers += (unsigned long long)((nd - j0) < kWarp ? (nd - j0) : kWarp);
-        if (vote) j1 = j0 + __ffs(vote) - 1;
+        const int32_t first = (int32_t)__reduce_min_sync(kFull, (unsigned)mine);
+        st.drivers += (unsigned long long)((nd - j0) < 4 * kWarp ? (nd - j0) : 4 * kWarp);
+        if (first != 0x7fffffff) j1 = first;
     }
     if (j1 < 0) return j0 >= nd ? -1 : kEscalate;            // no candidate fits at all -> EmptyPackingResult
     const int32_t d1 = drv_identity ? j1 : s.drv_slot[g.dbase + j1];
@@ -437,38 +449,64 @@ __device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupD
     }
     const uint32_t cd1 = d1 < ne ? a.capr(view, d1, a.d_cpu, a.d_mem, a.d_gpu) : 0u;
 
-    // ---- executors: 32 nodes per step from the live prefix ----------------------------------------------------------
+    // ---- executors: lane l owns nodes pos + 2l, pos + 2l + 1 (64 consecutive nodes per step) ----------------------------
     uint32_t placed = 0;
     int32_t pos = start_e;
-    for (int w = 0; placed < k && pos < ne && w < kWarpWinE; ++w, pos += kWarp) {
-        const int32_t i = pos + lane;
-        uint32_t c = 0;
-        if (i < ne) c = (i == d1) ? cd1 : a.capr(view, i, 0, 0, 0);
-        const uint32_t unit = (ALGO == 0) ? c : (c != 0 ? 1u : 0u);
-        const uint32_t incl = warp_incl_scan(unit, lane);
+    for (int w = 0; placed < k && pos < ne && w < kWarpWinE; ++w, pos += 2 * kWarp) {
+        const int32_t i0 = pos + 2 * lane, i1 = i0 + 1;
+        uint32_t c0 = 0, c1 = 0;
+        if (i0 < ne) c0 = (i0 == d1) ? cd1 : a.capr(view, i0, 0, 0, 0);
+        if (i1 < ne) c1 = (i1 == d1) ? cd1 : a.capr(view, i1, 0, 0, 0);
+        const uint32_t u0 = (ALGO == 0) ? c0 : (c0 != 0 ? 1u : 0u), u1 = (ALGO == 0) ? c1 : (c1 != 0 ? 1u : 0u);
+        const uint32_t sum = u0 + u1;
+        const uint32_t incl = warp_incl_scan(sum, lane);
         const uint32_t total = __shfl_sync(kFull, incl, kWarp - 1);
         const uint32_t room = k - placed;
         const uint32_t T = total < room ? total : room;
-        const uint32_t excl = incl - unit;
-        const uint32_t take = excl >= T ? 0u : ((unit < T - excl) ? unit : (T - excl));
-        cache[pos - start_e + lane] = (uint16_t)take;
-        if (take != 0) {
-            const int32_t node = slot_node[i];
-            for (uint32_t t = 0; t < take; ++t) out[placed + excl + t] = node;
+        const uint32_t excl = incl - sum;
+        const uint32_t rem = excl >= T ? 0u : T - excl;
+        const uint32_t t0 = u0 < rem ? u0 : rem;
+        const uint32_t t1 = u1 < rem - t0 ? u1 : rem - t0;
+        *reinterpret_cast<ushort2*>(cache + (pos - start_e) + 2 * lane) = make_ushort2((unsigned short)t0, (unsigned short)t1);
+        if (t0 | t1) {
+            int32_t* o = out + placed + excl;
+            if (t0) { const int32_t node = slot_node[i0]; for (uint32_t t = 0; t < t0; ++t) o[t] = node; }
+            if (t1) { const int32_t node = slot_node[i1]; for (uint32_t t = 0; t < t1; ++t) o[t0 + t] = node; }
         }
         placed += T;
+        if (placed == k && w == 0) {
+            // the usual case: everything fits inside the first step -> commit straight from registers
+            // (sparkpods.go:139-146 / exact accounting), no second pass over the cached takes
+            st.nodes += (unsigned long long)((pos + 2 * kWarp < ne ? pos + 2 * kWarp : ne) - start_e);
+            if (i0 < ne) {
+                if (t0 != 0) view.charge(i0, (FIFO_MODE == 1) ? 1 : (long long)t0, a.e_cpu, a.e_mem, a.e_gpu);
+                if (i0 == d1 && (FIFO_MODE == 2 || t0 == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+            }
+            if (i1 < ne) {
+                if (t1 != 0) view.charge(i1, (FIFO_MODE == 1) ? 1 : (long long)t1, a.e_cpu, a.e_mem, a.e_gpu);
+                if (i1 == d1 && (FIFO_MODE == 2 || t1 == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+            }
+            const bool in_step = (d1 >= pos && d1 < pos + 2 * kWarp && d1 < ne);
+            if (!in_step && lane == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+            __syncwarp();
+            return slot_node[d1];
+        }
     }
     st.nodes += (unsigned long long)((pos < ne ? pos : ne) - start_e);
     if (placed != k) return kEscalate;                       // nothing has been charged
 
-    // ---- commit (sparkpods.go:139-146 / exact accounting) -----------------------------------------------------------
+    // ---- commit after several steps (sparkpods.go:139-146 / exact accounting) ------------------------------------------
     __syncwarp();
-    for (int32_t p0 = start_e; p0 < pos; p0 += kWarp) {
-        const int32_t i = p0 + lane;
-        if (i >= ne) continue;
-        const uint32_t take = cache[i - start_e];
-        if (take != 0) view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
-        if (i == d1 && (FIFO_MODE == 2 || take == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+    for (int32_t p0 = start_e; p0 < pos; p0 += 2 * kWarp) {
+        const ushort2 tk = *reinterpret_cast<const ushort2*>(cache + (p0 - start_e) + 2 * lane);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int32_t i = p0 + 2 * lane + u;
+            const uint32_t take = u == 0 ? tk.x : tk.y;
+            if (i >= ne) continue;
+            if (take != 0) view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
+            if (i == d1 && (FIFO_MODE == 2 || take == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+        }
     }
     const bool driver_done = (d1 >= start_e && d1 < pos && d1 < ne);      // its owner lane handled it above
     if (!driver_done && lane == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
@@ -569,8 +607,9 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
                 const uint32_t fl = pa->flags;
                 d = -1;
                 if (!(fl & kAppInvalid)) {
-                    int32_t r = (fl & kAppFast) ? fifo_app_warp<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, lane)
-                                                : fifo_app_warp<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, lane);
+                    const bool refresh = (seq & 3u) == 0;
+                    int32_t r = (fl & kAppFast) ? fifo_app_warp<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, refresh, lane)
+                                                : fifo_app_warp<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, refresh, lane);
                     if (r == kEscalate) {
                         ++escalated;
                         if (lane == 0) { sh.first_live_e = start_e; sh.first_live_d = start_d; sh.cmd_app = app; sh.cmd_seq = seq; }

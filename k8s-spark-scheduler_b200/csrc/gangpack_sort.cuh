@@ -63,13 +63,14 @@ __global__ void gp_zone_priority(int32_t n_zones, const unsigned long long* __re
     prio[z] = p;
 }
 
+// zone == NULL: one zone (priority 0); name_rank == NULL: index order
 __global__ void gp_make_keys(int32_t n, const long long* __restrict__ cpu, const long long* __restrict__ mem,
                              const int32_t* __restrict__ zone, const int32_t* __restrict__ zone_prio,
                              const int32_t* __restrict__ name_rank, SortKey* __restrict__ keys) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     SortKey k;
-    k.mem = mem[i]; k.cpu = cpu[i]; k.az = zone_prio[zone[i]]; k.name_rank = name_rank[i];
+    k.mem = mem[i]; k.cpu = cpu[i]; k.az = zone ? zone_prio[zone[i]] : 0; k.name_rank = name_rank ? name_rank[i] : i;
     keys[i] = k;
 }
 

@@ -19,7 +19,8 @@
 //                         thread evaluates 4 consecutive nodes, a block-wide exclusive scan turns capacities into the
 //                         prefix table  S[i] = sum_{n<i} min(cap(n|0), CLAMP)   (tightly-pack) or
 //                                       M[i] = #{n<i : cap(n|0) >= 1}            (distribute-evenly);
-//   K2d gp_build_driver_firstfit  one CTA per (driver shape, instance group): the first driver candidate the shape fits on;
+//       (same launch, second half of the grid: one CTA per (driver shape, instance group) finds the first driver candidate
+//       the shape fits on);
 //   K3 gp_decide_tables   ONE THREAD per application (with the tables a decision is O(log N + k) scalar work -- a warp per
 //                         application, right for an O(N) scan, would idle 31 lanes): feasibility is
 //                         S[ne] - delta(d) >= k  per driver candidate d starting at the shape's first fit (delta = what the
@@ -221,9 +222,14 @@ struct TabScratch {
 };
 constexpr size_t kTabSmemBytes = 1024 + 2 * (size_t)kTabTile * sizeof(longlong2);      // 1 KB scratch + 2 x 64 KB tiles
 
+__device__ __forceinline__ void driver_firstfit_block(const Snapshot& s, const ShapeTables& tabs, int id, int grp);
+
+// grid (2 * kMaxShapes, n_groups): blocks [0, kMaxShapes) build the capacity table of executor shape blockIdx.x, blocks
+// [kMaxShapes, 2 kMaxShapes) find the first fitting candidate of driver shape blockIdx.x - kMaxShapes (one launch for both)
 template <int ALGO>
 __global__ void __launch_bounds__(kTabThreads, 1) gp_build_shape_tables(Snapshot s, ShapeTables tabs) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (blockIdx.x >= kMaxShapes) { driver_firstfit_block(s, tabs, (int)blockIdx.x - kMaxShapes, (int)blockIdx.y); return; }
     TabScratch& sh = *reinterpret_cast<TabScratch*>(smem_raw);
     longlong2* tile[2] = {reinterpret_cast<longlong2*>(smem_raw + 1024), reinterpret_cast<longlong2*>(smem_raw + 1024) + kTabTile};
     const int id = blockIdx.x, grp = blockIdx.y;
@@ -300,9 +306,8 @@ __global__ void __launch_bounds__(kTabThreads, 1) gp_build_shape_tables(Snapshot
 // ---------------------------------------------------------------------------------------------------------------
 // K2d: first fitting driver candidate per (driver shape, instance group)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gp_build_driver_firstfit(Snapshot s, ShapeTables tabs) {
+__device__ __forceinline__ void driver_firstfit_block(const Snapshot& s, const ShapeTables& tabs, int id, int grp) {
     __shared__ int32_t s_first;
-    const int id = blockIdx.x, grp = blockIdx.y;
     const int n = min(tabs.hdr->n_dshapes, kMaxShapes);
     if (id >= n) return;
     const DriverEntry& en = tabs.dentries[tabs.hdr->did_slot[id]];
@@ -395,11 +400,13 @@ __global__ void __launch_bounds__(kDecideThreads) gp_decide_tables(Snapshot s, A
                     else {
                         tab = tabs.table + (size_t)en->id * tabs.pitch + g.sbase;
                         total = tabs.total[(size_t)en->id * tabs.n_groups + grp];
-                        if (ALGO == 1 && k != 0 && total < k + 1) need_scan = true;      // fewer than k+1 hosting nodes: rounds / exact test
+                        // distribute-evenly: no hosting node at all -> no executor can be placed (distribute_evenly.go:72);
+                        // 1..k hosting nodes: several rounds or an exact per-candidate test -> the scan decides
+                        if (ALGO == 1 && k != 0 && total != 0 && total < k + 1) need_scan = true;
                     }
                 }
             }
-            if (!need_scan && !(ALGO == 0 && k != 0 && total < k)) {                  // total < k: not even without a driver (pack_tightly.go:62)
+            if (!need_scan && !(k != 0 && (ALGO == 0 ? total < k : total == 0))) {   // not even without a driver (pack_tightly.go:62, distribute_evenly.go:72)
                 const bool drv_gpu = d_gpu != 0 || (snap_flags & kSnapGpuNegative);
                 const bool cap_gpu = drv_gpu || (en->flags & 1u);
                 const longlong2* gpair = s.pair + g.sbase;
