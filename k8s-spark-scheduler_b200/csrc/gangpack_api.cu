@@ -304,6 +304,17 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// A fixed sequence of kernel launches / memsets that repeats with identical arguments (one Predicate after the other:
+// same buffers, same batch shape) is captured ONCE into a CUDA graph and replayed with a single launch call -- the
+// pipelined host path is bound by how fast the host thread can issue its calls, not by the GPU.  The key is the byte image
+// of every argument of the sequence; it is captured when the same key is seen twice in a row.
+struct GraphCache {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<char> key, last_key;
+    int launches = 0;
+    void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key.clear(); last_key.clear(); }
+};
+
 // dev_misc layout: [0] error bits (int), [8..24) stats (2 x u64), [32..32+4*kMaxChunks) per-chunk work counters
 static constexpr size_t kMiscCounters = 64, kMiscBytes = 64 + 4 * 16;   // [0] err, [8..40) 4 x u64 statistics, [64..) counters
 static constexpr int32_t kChunkApps = 50000;
@@ -350,6 +361,9 @@ struct gp_ctx {
     // per pipeline lane: shape hash + header, capacity tables, group totals, per-application shape slot
     struct TableSet { DevBuf hdr, table, total, app_slot; } tabs[kLanes];
     bool record_events = true;                    // CUDA events around the kernels (gp_last_stats); the pipelined host path skips them
+    int use_graphs = 1;                           // GANGPACK_GRAPHS=0: always issue the launches one by one
+    GraphCache g_chunk[kMaxChunks + 1];           // per pipelined chunk (+1: an unchunked batch on the context's own stream): classify .. scan
+    GraphCache g_snapshot;                        // slot layout of gp_set_snapshot
     DevBuf off_dev;                               // ExecutorNodes offsets derived on the device
     DevBuf fifo_list;                             // FIFO modes: per-instance-group application lists (queue order)
     DevBuf sched, zonebuf;                        // SchedulableResources [3][n_nodes]; staging of gp_pack_batch_zones
@@ -379,6 +393,53 @@ static cudaError_t create_aux(gp_ctx* c) {
             return GP_ERR_CUDA;                                                                \
         }                                                                                      \
     } while (0)
+
+// issue(): enqueues the sequence on `st` and returns (status, launches).  See GraphCache.
+template <class F>
+static gp_status run_cached(gp_ctx* c, GraphCache& gc, const void* key, size_t kn, cudaStream_t st, F&& issue) {
+    const char* kb = static_cast<const char*>(key);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (!c->use_graphs || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        int n = 0;
+        gp_status s = issue(n);
+        c->last.kernel_launches += n;
+        return s;
+    }
+    if (gc.exec && gc.key.size() == kn && std::memcmp(gc.key.data(), kb, kn) == 0) {
+        GP_CUDA(c, cudaGraphLaunch(gc.exec, st));
+        c->last.kernel_launches += gc.launches;
+        return GP_OK;
+    }
+    if (gc.last_key.size() == kn && std::memcmp(gc.last_key.data(), kb, kn) == 0 &&
+        cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        int n = 0;
+        const gp_status s = issue(n);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (s == GP_OK && e == cudaSuccess && g) {
+            cudaGraphExec_t ex = nullptr;
+            if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
+                if (gc.exec) cudaGraphExecDestroy(gc.exec);
+                gc.exec = ex; gc.key.assign(kb, kb + kn); gc.launches = n;
+                cudaGraphDestroy(g);
+                GP_CUDA(c, cudaGraphLaunch(gc.exec, st));
+                c->last.kernel_launches += n;
+                return GP_OK;
+            }
+        }
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();                 // capture did not work out: issue directly below
+        if (s != GP_OK) return s;
+    } else {
+        cudaGetLastError();
+    }
+    gc.last_key.assign(kb, kb + kn);
+    int n = 0;
+    gp_status s = issue(n);
+    c->last.kernel_launches += n;
+    return s;
+}
 
 // Device-visible alias of a host buffer, or nullptr.  Buffers from gp_alloc_pinned are known; anything
 // else is asked of the driver (cudaHostRegister / cudaHostAlloc memory of the caller qualifies).
@@ -451,6 +512,7 @@ gp_status gp_create(gp_ctx** out, const gp_config* cfg) {
     c->async_snapshot = cfg && (cfg->flags & GP_CFG_ASYNC_SNAPSHOT);
     if (const char* z = std::getenv("GANGPACK_ZERO_COPY")) c->zero_copy = std::atoi(z);
     if (const char* z = std::getenv("GANGPACK_TABLES")) c->use_tables = std::atoi(z);
+    if (const char* z = std::getenv("GANGPACK_GRAPHS")) c->use_graphs = std::atoi(z);
     if (const char* z = std::getenv("GANGPACK_CHUNK_APPS")) c->chunk_apps = std::max(1024, std::atoi(z));
     if (const char* z = std::getenv("GANGPACK_TRACE")) c->trace = std::atoi(z);
     if ((e = cudaSetDevice(dev)) != cudaSuccess ||
@@ -477,6 +539,8 @@ void gp_destroy(gp_ctx* c) {
                       &c->off_dev, &c->fifo_list, &c->sched, &c->zonebuf};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : c->tabs) { t.hdr.release(); t.table.release(); t.total.release(); t.app_slot.release(); }
+    for (auto& g : c->g_chunk) g.reset();
+    c->g_snapshot.reset();
     if (c->pinned_misc) cudaFreeHost(c->pinned_misc);
     if (c->one_block) cudaFreeHost(c->one_block);
     for (auto& row : c->ev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
@@ -541,23 +605,32 @@ static gp_status build_snapshot_device(gp_ctx* c, const gp_nodes* dn, int32_t n_
     GP_CUDA(c, c->node_slot.reserve(sizeof(int32_t) * (size_t)(dn->n_nodes + 1)));
     GP_CUDA(c, c->drv_slot.reserve(sizeof(int32_t) * (size_t)(n_drv + 1)));
     GP_CUDA(c, c->groups.reserve(sizeof(GroupDesc) * (size_t)dn->n_groups));
-    GP_CUDA(c, cudaMemsetAsync(c->slot_node.p, 0xFF, sizeof(int32_t) * (size_t)(n_slots + 1), st));
-    GP_CUDA(c, cudaMemsetAsync(c->node_slot.p, 0xFF, sizeof(int32_t) * (size_t)(dn->n_nodes + 1), st));
-    GP_CUDA(c, cudaMemsetAsync(c->snap_flags.p, 0, sizeof(SnapMeta), st));
-    const int T = 256;
-    gp_build_groups<<<(dn->n_groups + T - 1) / T, T, 0, st>>>(dn->n_groups, dn->exec_off, dn->drv_off, c->groups.as<GroupDesc>());
-    if (n_exec > 0)
-        gp_build_exec_slots<<<(n_exec + T - 1) / T, T, 0, st>>>(
-            n_exec, dn->n_groups, dn->exec_off, dn->drv_off, dn->exec_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
-            dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
-            c->node_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
-    if (n_drv > 0)
-        gp_build_driver_slots<<<(n_drv + T - 1) / T, T, 0, st>>>(
-            n_drv, dn->n_groups, dn->exec_off, dn->drv_off, dn->drv_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
-            dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
-            c->node_slot.as<int32_t>(), c->drv_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
-    gp_fill_pair32<<<(n_slots + T) / T, T, 0, st>>>(n_slots, c->pair.as<longlong2>(), c->snap_flags.as<SnapMeta>(), c->pair32.as<uint2>());
-    GP_CUDA(c, cudaGetLastError());
+    struct { gp_nodes dn; int32_t n_exec, n_drv; void* buf[8]; } key{};
+    key.dn = *dn; key.n_exec = n_exec; key.n_drv = n_drv;
+    void* bufs[8] = {c->pair.p, c->pair32.p, c->sgpu.p, c->slot_node.p, c->node_slot.p, c->drv_slot.p, c->groups.p, c->snap_flags.p};
+    std::memcpy(key.buf, bufs, sizeof(bufs));
+    gp_status rs = run_cached(c, c->g_snapshot, &key, sizeof(key), st, [&](int& launches) -> gp_status {
+        GP_CUDA(c, cudaMemsetAsync(c->slot_node.p, 0xFF, sizeof(int32_t) * (size_t)(n_slots + 1), st));
+        GP_CUDA(c, cudaMemsetAsync(c->node_slot.p, 0xFF, sizeof(int32_t) * (size_t)(dn->n_nodes + 1), st));
+        GP_CUDA(c, cudaMemsetAsync(c->snap_flags.p, 0, sizeof(SnapMeta), st));
+        const int T = 256;
+        gp_build_groups<<<(dn->n_groups + T - 1) / T, T, 0, st>>>(dn->n_groups, dn->exec_off, dn->drv_off, c->groups.as<GroupDesc>());
+        if (n_exec > 0)
+            gp_build_exec_slots<<<(n_exec + T - 1) / T, T, 0, st>>>(
+                n_exec, dn->n_groups, dn->exec_off, dn->drv_off, dn->exec_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
+                dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
+                c->node_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
+        if (n_drv > 0)
+            gp_build_driver_slots<<<(n_drv + T - 1) / T, T, 0, st>>>(
+                n_drv, dn->n_groups, dn->exec_off, dn->drv_off, dn->drv_order, dn->avail_cpu_milli, dn->avail_mem_bytes,
+                dn->avail_gpu, c->pair.as<longlong2>(), c->sgpu.as<int64_t>(), c->slot_node.as<int32_t>(),
+                c->node_slot.as<int32_t>(), c->drv_slot.as<int32_t>(), c->snap_flags.as<SnapMeta>());
+        gp_fill_pair32<<<(n_slots + T) / T, T, 0, st>>>(n_slots, c->pair.as<longlong2>(), c->snap_flags.as<SnapMeta>(), c->pair32.as<uint2>());
+        GP_CUDA(c, cudaGetLastError());
+        launches = 0;       // (the snapshot layout is not part of a pack call's launch count)
+        return GP_OK;
+    });
+    if (rs != GP_OK) return rs;
     c->n_nodes = dn->n_nodes; c->n_groups = dn->n_groups; c->n_exec = n_exec; c->n_drv = n_drv; c->n_slots = n_slots;
     c->have_snapshot = true;
     c->have_sched = false;               // SchedulableResources belong to a node table
@@ -762,7 +835,8 @@ static void launch_pack(gp_ctx* c, gp_mode mode, const Snapshot& s, const PrepAp
         }
         // small groups: fewer threads per CTA (the per-application fixed cost scales with the CTA size)
         const int avg_ne = c->n_groups > 0 ? c->n_exec / c->n_groups : 0;
-        const int kFifoThreadsRt = avg_ne <= 1536 ? 256 : (avg_ne <= 4096 ? 512 : kFifoThreads);
+        const int kFifoThreadsRt = kFifoThreads;
+        (void)avg_ne;
         int32_t* app_list = c->fifo_list.as<int32_t>();
         unsigned int* cursor = reinterpret_cast<unsigned int*>(c->dev_misc.as<char>() + 56);     // zeroed by pack_begin
         if (mode == GP_MODE_FIFO_REFERENCE)
@@ -836,8 +910,6 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
             GP_CUDA(c, T.table.reserve(sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)((c->n_slots + 4) & ~3)));
             GP_CUDA(c, T.total.reserve(2 * sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)c->n_groups));
         }
-        // the hash tables and the header (listed counter) start from zero: the whole block when the tables are used
-        GP_CUDA(c, cudaMemsetAsync(T.hdr.p, 0, use_tables ? hdr_bytes : 1024, st));
         ShapeTables tabs;
         tabs.hdr = T.hdr.as<ShapeHeader>();
         tabs.entries = reinterpret_cast<ShapeEntry*>(T.hdr.as<char>() + 1024);
@@ -853,24 +925,44 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
         int32_t* app_slot = T.app_slot.as<int32_t>();
         int32_t* listed = app_slot + 2 * (size_t)q;
         PrepApp* prep = c->prep.as<PrepApp>() + lo;
-        if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
-        if (use_tables || off_out) {
-            gp_classify_apps<<<(q + kClassifyThreads - 1) / kClassifyThreads, kClassifyThreads, 0, st>>>(
-                q, cols, tabs, c->snap_flags.as<SnapMeta>(), off_base, off_out, app_slot, use_tables ? 1 : 0);
-            c->last.kernel_launches += 1;
-        }
-        gp_status r;
         const bool o16 = dr.node_bits == 16;
-        if (algo == GP_TIGHTLY_PACK)
-            r = o16 ? launch_tables<0, uint16_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
-                    : launch_tables<0, int32_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
-        else
-            r = o16 ? launch_tables<1, uint16_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
-                    : launch_tables<1, int32_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
-        if (r != GP_OK) return r;
-        GP_CUDA(c, cudaGetLastError());
-        if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
-        return GP_OK;
+        auto issue = [&](int& launches) -> gp_status {
+            const int before = (int)c->last.kernel_launches;
+            // the hash tables and the header (listed counter) start from zero: the whole block when the tables are used
+            GP_CUDA(c, cudaMemsetAsync(T.hdr.p, 0, use_tables ? hdr_bytes : 1024, st));
+            if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
+            if (use_tables || off_out) {
+                gp_classify_apps<<<(q + kClassifyThreads - 1) / kClassifyThreads, kClassifyThreads, 0, st>>>(
+                    q, cols, tabs, c->snap_flags.as<SnapMeta>(), off_base, off_out, app_slot, use_tables ? 1 : 0);
+                c->last.kernel_launches += 1;
+            }
+            gp_status r;
+            if (algo == GP_TIGHTLY_PACK)
+                r = o16 ? launch_tables<0, uint16_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
+                        : launch_tables<0, int32_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
+            else
+                r = o16 ? launch_tables<1, uint16_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk)
+                        : launch_tables<1, int32_t>(c, s, cols, tabs, app_slot, prep, listed, q, dr, lo, scratch, d_stats, next_app, d_err, err_host, use_tables, st, chunk);
+            if (r != GP_OK) return r;
+            GP_CUDA(c, cudaGetLastError());
+            if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][2], st));
+            launches = (int)c->last.kernel_launches - before;
+            c->last.kernel_launches = before;          // run_cached adds `launches` (also when the graph is replayed)
+            return GP_OK;
+        };
+        if (c->record_events) {                        // timing events inside: always issued directly
+            int n = 0;
+            gp_status r = issue(n);
+            c->last.kernel_launches += n;
+            return r;
+        }
+        struct { int32_t algo, o16, use_tables, q, lo, chunk; int64_t off_base; AppColumns cols; ShapeTables tabs; Snapshot snap;
+                 const void* p[10]; int64_t cap; } key{};
+        key.algo = (int32_t)algo; key.o16 = o16; key.use_tables = use_tables; key.q = q; key.lo = lo; key.chunk = chunk; key.off_base = off_base;
+        key.cols = cols; key.tabs = tabs; key.snap = s; key.cap = dr.cap;
+        const void* ptrs[10] = {app_slot, prep, listed, dr.driver, dr.exec, scratch, d_stats, next_app, d_err, off_out};
+        std::memcpy(key.p, ptrs, sizeof(ptrs));
+        return run_cached(c, c->g_chunk[st == c->stream ? gp_ctx::kMaxChunks : chunk], &key, sizeof(key), st, issue);
     }
 
     // ---- FIFO modes and minimal-fragmentation: prepared records + the pack kernel ------------------------------------

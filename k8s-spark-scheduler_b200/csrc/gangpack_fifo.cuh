@@ -21,7 +21,7 @@
 
 namespace gp {
 
-constexpr int kFifoThreads = 512;
+constexpr int kFifoThreads = 256;     // warp 0 does the common case alone and wants registers; the CTA path is the exception
 constexpr int kFifoWarps = kFifoThreads / 32;
 constexpr int kFifoSmemSlots = 11776;          // 184 KB of (cpu,mem) records
 constexpr int kFifoCache = 12288;              // uint16 capacity cache entries (24 KB)
@@ -369,78 +369,101 @@ __device__ __forceinline__ int32_t fifo_app(const Snapshot& s, const GroupDesc& 
 }
 
 // ---- one application, warp 0 alone ------------------------------------------------------------------------------
-// A single warp is bound by the LATENCY of its dependent instruction chain (measured: ~450 instructions and 2 us per
-// application with one node per lane per step), so every step is made wide: 4 driver candidates and 2 executor nodes per
-// lane (128 / 64 per step) -- the usual application then needs ONE driver step and ONE executor step, and the independent
-// per-element work inside a step overlaps.
-constexpr int kWarpWinE = 16;          // executor steps of 64 nodes the warp tries before it calls the CTA (1 024 nodes)
-constexpr int kWarpWinD = 8;           // driver steps of 128 candidates (1 024 candidates)
+// A single warp is bound by the LATENCY of its dependent instruction chain (measured: ~650 instructions and 2 us per
+// application when it scans from the batch-wide dead prefix), so the chain is cut where it can be:
+//   * the prepared record of the NEXT application is fetched one application ahead -- one coalesced 128-byte load, lane w
+//     keeps word w -- and decoded with shuffles: no global-memory latency on the critical path;
+//   * availability only ever decreases inside the loop, so "the first driver candidate a driver shape fits on" and "the
+//     first node with room for an executor shape" only move forward: warp 0 keeps one cursor per distinct driver /
+//     executor request (up to 32 each, one per lane, full tuple compared) and starts both scans there -- typically ONE
+//     32-wide step each instead of a walk from the dead prefix;
+//   * when everything fits inside the first step the charges are applied straight from registers.
+constexpr int kWarpWinE = 32;          // executor steps of 32 nodes the warp tries before it calls the CTA (1 024 nodes)
+constexpr int kWarpWinD = 32;          // driver steps of 32 candidates (1 024 candidates)
 constexpr int32_t kEscalate = -3;      // "the whole CTA must decide this application" (never stored as a result)
 
 __device__ __forceinline__ void bar_sync_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// one cursor per distinct request tuple, entry l lives in lane l
+struct ShapeCursors {
+    int64_t k0, k1, k2;
+    int32_t pos;
+    int32_t n;             // entries in use (warp-uniform)
+    __device__ __forceinline__ void init() { k0 = k1 = k2 = -1; pos = 0; n = 0; }
+    // returns the lane that holds the tuple's cursor (-1: table full) and its value (dflt for a new entry)
+    __device__ __forceinline__ int find(int64_t a, int64_t b, int64_t c, int32_t dflt, int32_t& cur, int lane) {
+        const unsigned vote = __ballot_sync(kFull, lane < n && k0 == a && k1 == b && k2 == c);
+        int src;
+        if (vote) src = __ffs(vote) - 1;
+        else if (n < kWarp) { src = n; if (lane == src) { k0 = a; k1 = b; k2 = c; pos = dflt; } ++n; }
+        else { cur = dflt; return -1; }
+        cur = __shfl_sync(kFull, pos, src);
+        if (cur < dflt) cur = dflt;      // the batch-wide dead prefix is a lower bound as well
+        return src;
+    }
+};
+
+// the prepared record from the word every lane holds (PrepApp is 32 words)
+__device__ __forceinline__ PrepApp decode_prep(uint32_t rec) {
+    auto W = [&](int w) { return __shfl_sync(kFull, rec, w); };
+    auto W64 = [&](int w) { return (int64_t)(((uint64_t)W(w + 1) << 32) | (uint64_t)W(w)); };
+    PrepApp p;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        p.drv[t] = W64(2 * t);
+        p.div[t].magic = (uint64_t)W64(6 + 6 * t);
+        p.div[t].e = W64(8 + 6 * t);
+        p.div[t].sh = W(10 + 6 * t);
+        p.div[t].kind = W(11 + 6 * t);
+    }
+    p.out_off = W64(24);
+    p.count = (int32_t)W(26); p.group = (int32_t)W(27); p.lmax = (int32_t)W(28); p.flags = W(29);
+    return p;
+}
+static_assert(offsetof(PrepApp, div) == 24 && offsetof(PrepApp, out_off) == 96 && offsetof(PrepApp, count) == 104 && offsetof(PrepApp, flags) == 116 &&
+              offsetof(DimDiv, e) == 8 && offsetof(DimDiv, sh) == 16 && offsetof(DimDiv, kind) == 20, "decode_prep layout");
 
 // Optimistic single pass, exactly like the first part of fifo_app(): the first driver candidate that FITS is the
 // reference's answer whenever the executors fit with it (binpack.go:67-85).  tightly-pack: node n takes min(cap, rest);
 // distribute-evenly: one round, every hosting node takes one (distribute_evenly.go:49-70 when k hosting nodes exist).
 // Anything else -- no room inside the window budget, executors that do not fit with that driver, several rounds --
-// returns kEscalate with NOTHING charged.  start_e / start_d: the dead prefixes (registers of warp 0).
-template <int ALGO, int FIFO_MODE, bool FAST>
-__device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupDesc& g, const FifoView& view, const PrepApp* __restrict__ pa,
+// returns kEscalate with NOTHING charged.  Fast arithmetic class only (the general class goes to the CTA).
+template <int ALGO, int FIFO_MODE>
+__device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupDesc& g, const FifoView& view, const PrepApp& pa,
                                                  int32_t* __restrict__ executor_nodes, uint16_t* __restrict__ cache,
-                                                 int32_t& start_e, int32_t& start_d, WarpStats& st, const GroupMin& gm,
-                                                 bool drv_identity, bool refresh, int lane) {
-    FifoCaps<FAST> a;
-    a.init(pa, (pa->flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
+                                                 int32_t start_e, int32_t start_d, ShapeCursors& dcur, ShapeCursors& ecur,
+                                                 WarpStats& st, bool drv_identity, int lane) {
+    FifoCaps<true> a;
+    a.init(&pa, (pa.flags & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative));
     const uint32_t k = a.k;
     if (k > 0xFFFFu) return kEscalate;                       // takes are cached as uint16
     const int32_t ne = g.ne, nd = g.nd;
-    int32_t* out = executor_nodes + pa->out_off;
+    int32_t* out = executor_nodes + pa.out_off;
     const int32_t* slot_node = s.slot_node + g.sbase;
     const bool ug = a.use_gpu;
 
-    // ---- every 4th application: advance the dead prefixes -- nodes that can host nothing for ANY application of the
-    // batch (GroupMin); availability only decreases, so such nodes stay dead
-    if (refresh) {
-        for (int t = 0; t < 4 && start_e < ne; ++t) {
-            const int32_t i = start_e + lane;
-            const bool alive = i < ne && !dead_for(gm.exe, view.pair(i), ug ? view.gpu(i) : 0, ug);
-            const unsigned vote = __ballot_sync(kFull, alive);
-            if (vote) { start_e += __ffs(vote) - 1; break; }
-            start_e = min(ne, start_e + kWarp);
+    // ---- first driver candidate that fits, from this driver shape's cursor -------------------------------------------
+    int32_t from_d;
+    const int dsrc = dcur.find(a.d_cpu, a.d_mem, a.d_gpu, start_d, from_d, lane);
+    int32_t j1 = -1, j0 = from_d;
+    for (int w = 0; j0 < nd && j1 < 0 && w < kWarpWinD; ++w, j0 += kWarp) {
+        const int32_t j = j0 + lane;
+        bool fits = false;
+        if (j < nd) {
+            const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
+            const longlong2 v = view.pair(ls);
+            fits = !(a.d_cpu > v.x) && !(a.d_mem > v.y) && !(ug && a.d_gpu > view.gpu(ls));
         }
-        for (int t = 0; t < 4 && start_d < nd; ++t) {
-            const int32_t j = start_d + lane;
-            bool alive = false;
-            if (j < nd) {
-                const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
-                alive = !dead_for(gm.drv, view.pair(ls), ug ? view.gpu(ls) : 0, ug);
-            }
-            const unsigned vote = __ballot_sync(kFull, alive);
-            if (vote) { start_d += __ffs(vote) - 1; break; }
-            start_d = min(nd, start_d + kWarp);
-        }
+        const unsigned vote = __ballot_sync(kFull, fits);
+        st.drivers += (unsigned long long)((nd - j0) < kWarp ? (nd - j0) : kWarp);
+        if (vote) j1 = j0 + __ffs(vote) - 1;
     }
-
-    // ---- first driver candidate that fits: lane l owns the 4 CONSECUTIVE candidates j0 + 4l .. j0 + 4l + 3, so the first
-    // fitting candidate of the step is a plain minimum over the lanes (one REDUX) ----------------------------------------
-    int32_t j1 = -1, j0 = start_d;
-    for (int w = 0; j0 < nd && j1 < 0 && w < kWarpWinD; ++w, j0 += 4 * kWarp) {
-        int32_t mine = 0x7fffffff;
-#pragma unroll
-        for (int u = 3; u >= 0; --u) {
-            const int32_t j = j0 + 4 * lane + u;
-            if (j < nd) {
-                const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
-                const longlong2 v = view.pair(ls);
-                const bool fits = !(a.d_cpu > v.x) && !(a.d_mem > v.y) && !(ug && a.d_gpu > view.gpu(ls));
-                if (fits) mine = j;
-            }
-        }
-        const int32_t first = (int32_t)__reduce_min_sync(kFull, (unsigned)mine);
-        st.drivers += (unsigned long long)((nd - j0) < 4 * kWarp ? (nd - j0) : 4 * kWarp);
-        if (first != 0x7fffffff) j1 = first;
+    if (j1 < 0) {
+        if (j0 < nd) return kEscalate;                       // window budget exhausted
+        if (lane == dsrc) dcur.pos = nd;                     // this shape fits nowhere any more
+        return -1;                                           // no candidate fits at all -> EmptyPackingResult
     }
-    if (j1 < 0) return j0 >= nd ? -1 : kEscalate;            // no candidate fits at all -> EmptyPackingResult
+    if (lane == dsrc) dcur.pos = j1;                         // candidates before j1 can never fit this shape again
     const int32_t d1 = drv_identity ? j1 : s.drv_slot[g.dbase + j1];
     if (k == 0) {                                            // no executors: the driver alone (pack_tightly.go:42-44)
         if (lane == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
@@ -449,66 +472,62 @@ __device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupD
     }
     const uint32_t cd1 = d1 < ne ? a.capr(view, d1, a.d_cpu, a.d_mem, a.d_gpu) : 0u;
 
-    // ---- executors: lane l owns nodes pos + 2l, pos + 2l + 1 (64 consecutive nodes per step) ----------------------------
+    // ---- executors: 32 nodes per step from this executor shape's cursor -------------------------------------------------
+    int32_t from_e;
+    const int esrc = ecur.find(a.e_cpu, a.e_mem, a.e_gpu, start_e, from_e, lane);
     uint32_t placed = 0;
-    int32_t pos = start_e;
-    for (int w = 0; placed < k && pos < ne && w < kWarpWinE; ++w, pos += 2 * kWarp) {
-        const int32_t i0 = pos + 2 * lane, i1 = i0 + 1;
-        uint32_t c0 = 0, c1 = 0;
-        if (i0 < ne) c0 = (i0 == d1) ? cd1 : a.capr(view, i0, 0, 0, 0);
-        if (i1 < ne) c1 = (i1 == d1) ? cd1 : a.capr(view, i1, 0, 0, 0);
-        const uint32_t u0 = (ALGO == 0) ? c0 : (c0 != 0 ? 1u : 0u), u1 = (ALGO == 0) ? c1 : (c1 != 0 ? 1u : 0u);
-        const uint32_t sum = u0 + u1;
-        const uint32_t incl = warp_incl_scan(sum, lane);
+    int32_t pos = from_e, first_room = -1;
+    for (int w = 0; placed < k && pos < ne && w < kWarpWinE; ++w, pos += kWarp) {
+        const int32_t i = pos + lane;
+        uint32_t c0 = 0;                                     // capacity without a driver: what the cursor is about
+        if (i < ne) c0 = a.capr(view, i, 0, 0, 0);
+        const uint32_t c = (i == d1) ? cd1 : c0;
+        if (first_room < 0) {
+            const unsigned room_vote = __ballot_sync(kFull, c0 != 0);
+            if (room_vote) first_room = pos + __ffs(room_vote) - 1;
+        }
+        const uint32_t unit = (ALGO == 0) ? c : (c != 0 ? 1u : 0u);
+        const uint32_t incl = warp_incl_scan(unit, lane);
         const uint32_t total = __shfl_sync(kFull, incl, kWarp - 1);
         const uint32_t room = k - placed;
         const uint32_t T = total < room ? total : room;
-        const uint32_t excl = incl - sum;
-        const uint32_t rem = excl >= T ? 0u : T - excl;
-        const uint32_t t0 = u0 < rem ? u0 : rem;
-        const uint32_t t1 = u1 < rem - t0 ? u1 : rem - t0;
-        *reinterpret_cast<ushort2*>(cache + (pos - start_e) + 2 * lane) = make_ushort2((unsigned short)t0, (unsigned short)t1);
-        if (t0 | t1) {
-            int32_t* o = out + placed + excl;
-            if (t0) { const int32_t node = slot_node[i0]; for (uint32_t t = 0; t < t0; ++t) o[t] = node; }
-            if (t1) { const int32_t node = slot_node[i1]; for (uint32_t t = 0; t < t1; ++t) o[t0 + t] = node; }
+        const uint32_t excl = incl - unit;
+        const uint32_t take = excl >= T ? 0u : ((unit < T - excl) ? unit : (T - excl));
+        if (take != 0) {
+            const int32_t node = slot_node[i];
+            for (uint32_t t = 0; t < take; ++t) out[placed + excl + t] = node;
         }
         placed += T;
         if (placed == k && w == 0) {
             // the usual case: everything fits inside the first step -> commit straight from registers
-            // (sparkpods.go:139-146 / exact accounting), no second pass over the cached takes
-            st.nodes += (unsigned long long)((pos + 2 * kWarp < ne ? pos + 2 * kWarp : ne) - start_e);
-            if (i0 < ne) {
-                if (t0 != 0) view.charge(i0, (FIFO_MODE == 1) ? 1 : (long long)t0, a.e_cpu, a.e_mem, a.e_gpu);
-                if (i0 == d1 && (FIFO_MODE == 2 || t0 == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+            // (sparkpods.go:139-146 / exact accounting)
+            st.nodes += (unsigned long long)((pos + kWarp < ne ? pos + kWarp : ne) - from_e);
+            if (i < ne) {
+                if (take != 0) view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
+                if (i == d1 && (FIFO_MODE == 2 || take == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
             }
-            if (i1 < ne) {
-                if (t1 != 0) view.charge(i1, (FIFO_MODE == 1) ? 1 : (long long)t1, a.e_cpu, a.e_mem, a.e_gpu);
-                if (i1 == d1 && (FIFO_MODE == 2 || t1 == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
-            }
-            const bool in_step = (d1 >= pos && d1 < pos + 2 * kWarp && d1 < ne);
+            const bool in_step = (d1 >= pos && d1 < pos + kWarp && d1 < ne);
             if (!in_step && lane == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
+            if (lane == esrc && first_room >= 0) ecur.pos = first_room;      // nodes before it have no room for this shape, for good
             __syncwarp();
             return slot_node[d1];
         }
+        cache[pos - from_e + lane] = (uint16_t)take;
     }
-    st.nodes += (unsigned long long)((pos < ne ? pos : ne) - start_e);
+    st.nodes += (unsigned long long)((pos < ne ? pos : ne) - from_e);
+    if (lane == esrc) ecur.pos = first_room >= 0 ? first_room : (pos < ne ? pos : ne);   // valid whether or not the placement succeeds
     if (placed != k) return kEscalate;                       // nothing has been charged
 
     // ---- commit after several steps (sparkpods.go:139-146 / exact accounting) ------------------------------------------
     __syncwarp();
-    for (int32_t p0 = start_e; p0 < pos; p0 += 2 * kWarp) {
-        const ushort2 tk = *reinterpret_cast<const ushort2*>(cache + (p0 - start_e) + 2 * lane);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int32_t i = p0 + 2 * lane + u;
-            const uint32_t take = u == 0 ? tk.x : tk.y;
-            if (i >= ne) continue;
-            if (take != 0) view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
-            if (i == d1 && (FIFO_MODE == 2 || take == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
-        }
+    for (int32_t p0 = from_e; p0 < pos; p0 += kWarp) {
+        const int32_t i = p0 + lane;
+        if (i >= ne) continue;
+        const uint32_t take = cache[i - from_e];
+        if (take != 0) view.charge(i, (FIFO_MODE == 1) ? 1 : (long long)take, a.e_cpu, a.e_mem, a.e_gpu);
+        if (i == d1 && (FIFO_MODE == 2 || take == 0)) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
     }
-    const bool driver_done = (d1 >= start_e && d1 < pos && d1 < ne);      // its owner lane handled it above
+    const bool driver_done = (d1 >= from_e && d1 < pos && d1 < ne);       // its owner lane handled it above
     if (!driver_done && lane == 0) view.charge(d1, 1, a.d_cpu, a.d_mem, a.d_gpu);
     __syncwarp();                                            // the next application sees the charged snapshot
     return slot_node[d1];
@@ -597,19 +616,48 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
         bool blocked = false;
         uint32_t seq = 0;
         unsigned long long escalated = 0;
+        ShapeCursors dcur, ecur;
+        dcur.init(); ecur.init();
+        // software pipeline: the record of application t+1 (one coalesced 128-byte load, lane w keeps word w) and the index of
+        // application t+2 are in flight while application t is decided
+        int32_t app = my_cnt > 0 ? (mine ? mine[0] : 0) : 0;
+        int32_t app_next = my_cnt > 1 ? (mine ? mine[1] : 1) : 0;
+        uint32_t rec = my_cnt > 0 ? reinterpret_cast<const uint32_t*>(prep + app)[lane] : 0u;
         for (int32_t t = 0; t < my_cnt; ++t) {
-            const int32_t app = mine ? mine[t] : t;
-            if (lane == 0 && t + 1 < my_cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + (mine ? mine[t + 1] : t + 1)));
+            const uint32_t rec_next = (t + 1 < my_cnt) ? __ldg(reinterpret_cast<const uint32_t*>(prep + app_next) + lane) : 0u;
+            const int32_t app_next2 = (t + 2 < my_cnt) ? (mine ? mine[t + 2] : t + 2) : 0;
             int32_t d;
             if (blocked) d = -2;                                   // never evaluated (resource.go:252)
             else {
-                const PrepApp* pa = prep + app;
-                const uint32_t fl = pa->flags;
+                const PrepApp pa = decode_prep(rec);
+                const uint32_t fl = pa.flags;
                 d = -1;
                 if (!(fl & kAppInvalid)) {
-                    const bool refresh = (seq & 3u) == 0;
-                    int32_t r = (fl & kAppFast) ? fifo_app_warp<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, refresh, lane)
-                                                : fifo_app_warp<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, cache, start_e, start_d, st, gm, drv_identity, refresh, lane);
+                    if ((seq & 15u) == 0) {
+                        // every 16th application: advance the dead prefixes -- nodes that can host nothing for ANY application
+                        // of the batch (GroupMin); they bound every cursor from below and are where the CTA path starts
+                        const bool ug = (fl & kAppUsesGpu) || (s.meta->flags & kSnapGpuNegative);
+                        for (int u = 0; u < 8 && start_e < g.ne; ++u) {
+                            const int32_t i = start_e + lane;
+                            const bool alive = i < g.ne && !dead_for(gm.exe, view.pair(i), ug ? view.gpu(i) : 0, ug);
+                            const unsigned vote = __ballot_sync(kFull, alive);
+                            if (vote) { start_e += __ffs(vote) - 1; break; }
+                            start_e = min(g.ne, start_e + kWarp);
+                        }
+                        for (int u = 0; u < 8 && start_d < g.nd; ++u) {
+                            const int32_t j = start_d + lane;
+                            bool alive = false;
+                            if (j < g.nd) {
+                                const int32_t ls = drv_identity ? j : s.drv_slot[g.dbase + j];
+                                alive = !dead_for(gm.drv, view.pair(ls), ug ? view.gpu(ls) : 0, ug);
+                            }
+                            const unsigned vote = __ballot_sync(kFull, alive);
+                            if (vote) { start_d += __ffs(vote) - 1; break; }
+                            start_d = min(g.nd, start_d + kWarp);
+                        }
+                    }
+                    int32_t r = (fl & kAppFast) ? fifo_app_warp<ALGO, FIFO_MODE>(s, g, view, pa, executor_nodes, cache, start_e, start_d, dcur, ecur, st, drv_identity, lane)
+                                                : kEscalate;
                     if (r == kEscalate) {
                         ++escalated;
                         if (lane == 0) { sh.first_live_e = start_e; sh.first_live_d = start_d; sh.cmd_app = app; sh.cmd_seq = seq; }
@@ -625,6 +673,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
                 if (d < 0 && !(fl & kAppSkipIfNoFit)) blocked = true;   // resource.go:244-253
             }
             if (lane == 0) driver_node[app] = d;
+            app = app_next; app_next = app_next2; rec = rec_next;
         }
         if (lane == 0) { sh.cmd_app = -1; if (escalated) atomicAdd(stats + 2, escalated); }   // stats[2]: applications decided by the whole CTA
         __syncwarp();
