@@ -36,8 +36,12 @@ print("pack_one            %8.1f us" % t(lambda: p.pack_one(0, (1000, 1 << 30, 0
 pack = lambda: p.pack_batch(pin, w["algo"], w["mode"], out=(od, oe))
 print("potential_nodes (device sort, 10k nodes) %8.1f us" % t(lambda: p.potential_nodes(pn["cpu"], pn["mem"])))
 import k8s_spark_scheduler_b200.synth as _synth
-_n50 = _synth.make_nodes(50000)
-print("potential_nodes (device sort, 50k nodes) %8.1f us" % t(lambda: p.potential_nodes(_n50["avail_cpu"], _n50["avail_mem"]), 5))
+for _nn in (50000, 500000):
+    _n50 = _synth.make_nodes(_nn)
+    _pc = p.pinned(_nn, np.int64); _pc[:] = _n50["avail_cpu"]
+    _pm = p.pinned(_nn, np.int64); _pm[:] = _n50["avail_mem"]
+    print("potential_nodes (device sort, %d nodes, pinned inputs) %8.1f us" % (_nn, t(lambda: p.potential_nodes(_pc, _pm), 5)))
+    print("potential_nodes (device sort, %d nodes, pageable inputs) %8.1f us" % (_nn, t(lambda: p.potential_nodes(_n50["avail_cpu"], _n50["avail_mem"]), 5)))
 _t0 = time.perf_counter(); _synth.priority_order(nodes["avail_cpu"], nodes["avail_mem"]); print("numpy lexsort 10k nodes %8.1f us" % ((time.perf_counter() - _t0) * 1e6))
 _R = 200000
 _rng = np.random.default_rng(1)
