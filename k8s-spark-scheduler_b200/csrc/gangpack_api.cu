@@ -329,6 +329,7 @@ struct gp_ctx {
     cudaStream_t lane[kLanes] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[kMaxChunks][3] = {};    // per chunk: prep start, pack start, pack end
     cudaEvent_t ev_ready = nullptr, ev_done[kLanes] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr;           // GANGPACK_TRACE=2: start of the pipelined batch (timeline of the chunks on stderr)
     int ev_chunks = 0;
     std::string err;
 
@@ -381,6 +382,7 @@ static cudaError_t create_aux(gp_ctx* c) {
     for (auto& l : c->lane) if ((e = cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking)) != cudaSuccess) return e;
     for (auto& row : c->ev) for (auto& ev : row) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&c->ev_t0)) != cudaSuccess) return e;
     for (auto& ev : c->ev_done) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     return cudaSuccess;
 }
@@ -545,6 +547,7 @@ void gp_destroy(gp_ctx* c) {
     if (c->one_block) cudaFreeHost(c->one_block);
     for (auto& row : c->ev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     for (cudaEvent_t e : c->ev_done) if (e) cudaEventDestroy(e);
     for (cudaStream_t l : c->lane) if (l) cudaStreamDestroy(l);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1195,6 +1198,8 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
     struct EvGuard { gp_ctx* c; ~EvGuard() { c->record_events = true; } } ev_guard{c};
     c->record_events = n_chunks == 1;
     GP_CUDA(c, cudaEventRecord(c->ev_ready, st));      // snapshot + zeroed counters are ready
+    const bool timeline = c->trace >= 2 && !c->record_events;
+    if (timeline) GP_CUDA(c, cudaEventRecord(c->ev_t0, st));
     int64_t e_run = 0;                                 // ExecutorNodes entries before the current chunk
     for (int ch = 0; ch < n_chunks; ++ch) {
         const int32_t lo = (int32_t)((int64_t)q * ch / n_chunks), hi = (int32_t)((int64_t)q * (ch + 1) / n_chunks);
@@ -1253,6 +1258,7 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
             if (a->group) GP_CUDA(c, cudaMemcpyAsync(c->a_group.as<int32_t>() + lo, a->group + lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ls));
             if (a->skip_if_no_fit) GP_CUDA(c, cudaMemcpyAsync(c->a_skip.as<uint8_t>() + lo, a->skip_if_no_fit + lo, n, cudaMemcpyHostToDevice, ls));
         }
+        if (timeline) GP_CUDA(c, cudaEventRecord(c->ev[ch][0], ls));       // inputs of this chunk are in HBM
         if (n_chunks > 1) GP_CUDA(c, cudaStreamWaitEvent(ls, c->ev_ready, 0));
         // ---- this chunk's ExecutorNodes range ------------------------------------------------------------------
         int64_t e0, e1;
@@ -1267,12 +1273,14 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
         }
         s = pack_device_range(c, dv, lo, hi, e0, algo, mode, dr, scratch, ls, ch);
         if (s != GP_OK) return s;
+        if (timeline) GP_CUDA(c, cudaEventRecord(c->ev[ch][1], ls));       // kernels of this chunk done
         if (out_mapped) continue;
         GP_CUDA(c, cudaMemcpyAsync(out->driver_node + lo, dr.driver + lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ls));
         if (e1 > e0)
             GP_CUDA(c, cudaMemcpyAsync((char*)out->executor_nodes + os * (size_t)e0, (char*)dr.exec + os * (size_t)e0, os * (size_t)(e1 - e0),
                                        cudaMemcpyDeviceToHost, ls));
     }
+    if (timeline) for (int ch = 0; ch < n_chunks; ++ch) GP_CUDA(c, cudaEventRecord(c->ev[ch][2], n_chunks == 1 ? st : c->lane[ch % gp_ctx::kLanes]));
     c->ev_chunks = c->record_events ? n_chunks : 0;
     const auto t_issued = std::chrono::steady_clock::now();
     if (n_chunks > 1) {
@@ -1282,6 +1290,13 @@ static gp_status pack_batch_impl(gp_ctx* c, const gp_apps_wire* a, gp_algo algo,
         }
     }
     GP_CUDA(c, cudaStreamSynchronize(st));
+    if (timeline) {
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, c->ev_t0, c->ev[ch][0]); cudaEventElapsedTime(&b, c->ev_t0, c->ev[ch][1]); cudaEventElapsedTime(&d, c->ev_t0, c->ev[ch][2]);
+            std::fprintf(stderr, "[gangpack]   chunk %d: inputs in HBM at %.1f us, kernels done at %.1f us, results on the host at %.1f us\n", ch, a * 1e3, b * 1e3, d * 1e3);
+        }
+    }
     if (c->trace) {
         const auto t_done = std::chrono::steady_clock::now();
         std::fprintf(stderr, "[gangpack] pack_batch q=%d chunks=%d bits=%d/%d out_mapped=%d issue=%.1fus wait=%.1fus\n", q, n_chunks,

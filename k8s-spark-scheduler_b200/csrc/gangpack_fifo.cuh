@@ -85,6 +85,7 @@ struct FifoView {
     longlong2* gp;          // global slots of this group (s.pair + sbase)
     int64_t* gg;            // global gpu values of this group
     int32_t n_smem;
+    bool all_smem;          // every slot this kernel touches is staged (warp 0's fast accessors rely on it)
     __device__ __forceinline__ longlong2* pair_ptr(int32_t local) const { return local < n_smem ? sp + local : gp + local; }
     __device__ __forceinline__ longlong2 pair(int32_t local) const {
         if (local < n_smem) return sp[local];
@@ -106,10 +107,30 @@ struct FifoView {
     }
 };
 
+// the same view when EVERY slot the kernel touches is staged in shared memory (identical driver / executor orders, group
+// within the staging area): no shared-or-global branch on warp 0's critical path
+struct FifoViewS {
+    longlong2* sp;
+    int64_t* gg;
+    __device__ __forceinline__ longlong2 pair(int32_t local) const { return sp[local]; }
+    __device__ __forceinline__ int64_t gpu(int32_t local) const {
+        int64_t v;
+        asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(gg + local) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void charge(int32_t local, long long mult, int64_t cpu, int64_t mem, int64_t gpu_req) const {
+        longlong2 v = sp[local];
+        v.x -= mult * cpu; v.y -= mult * mem;
+        sp[local] = v;
+        if (gpu_req != 0) gg[local] -= mult * gpu_req;
+    }
+};
+
 // capacity of one slot for one application (fast or general class), clamped to k
 template <bool FAST> struct FifoCaps;
 template <> struct FifoCaps<true> : Caps<true> {
-    __device__ __forceinline__ uint32_t capr(const FifoView& v, int32_t local, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
+    template <class V>
+    __device__ __forceinline__ uint32_t capr(const V& v, int32_t local, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
         longlong2 p = v.pair(local);
         uint32_t c = cap_pair(p, r_cpu, r_mem);
         if (use_gpu) c = min(c, fast_q(v.gpu(local) - r_gpu, gpu));
@@ -117,7 +138,8 @@ template <> struct FifoCaps<true> : Caps<true> {
     }
 };
 template <> struct FifoCaps<false> : Caps<false> {
-    __device__ __forceinline__ uint32_t capr(const FifoView& v, int32_t local, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
+    template <class V>
+    __device__ __forceinline__ uint32_t capr(const V& v, int32_t local, int64_t r_cpu, int64_t r_mem, int64_t r_gpu) const {
         longlong2 p = v.pair(local);
         uint32_t c = min(cap_dim(p.x - r_cpu, cpu, k), cap_dim(p.y - r_mem, mem, k));
         if (use_gpu) c = min(c, cap_dim(v.gpu(local) - r_gpu, gpu, k));
@@ -428,8 +450,8 @@ static_assert(offsetof(PrepApp, div) == 24 && offsetof(PrepApp, out_off) == 96 &
 // distribute-evenly: one round, every hosting node takes one (distribute_evenly.go:49-70 when k hosting nodes exist).
 // Anything else -- no room inside the window budget, executors that do not fit with that driver, several rounds --
 // returns kEscalate with NOTHING charged.  Fast arithmetic class only (the general class goes to the CTA).
-template <int ALGO, int FIFO_MODE>
-__device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupDesc& g, const FifoView& view, const PrepApp& pa,
+template <int ALGO, int FIFO_MODE, class V>
+__device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupDesc& g, const V& view, const PrepApp& pa,
                                                  int32_t* __restrict__ executor_nodes, uint16_t* __restrict__ cache,
                                                  int32_t start_e, int32_t start_d, ShapeCursors& dcur, ShapeCursors& ecur,
                                                  WarpStats& st, bool drv_identity, int lane) {
@@ -493,9 +515,21 @@ __device__ __forceinline__ int32_t fifo_app_warp(const Snapshot& s, const GroupD
         const uint32_t T = total < room ? total : room;
         const uint32_t excl = incl - unit;
         const uint32_t take = excl >= T ? 0u : ((unit < T - excl) ? unit : (T - excl));
-        if (take != 0) {
-            const int32_t node = slot_node[i];
-            for (uint32_t t = 0; t < take; ++t) out[placed + excl + t] = node;
+        if (T != 0) {
+            // output j of this step belongs to the first lane whose inclusive prefix exceeds j: shuffle binary search, one
+            // coalesced store per 32 outputs (a per-lane loop over `take` serialises up to k stores in one lane)
+            const int32_t node = take != 0 ? slot_node[i] : -1;
+            for (uint32_t jb = 0; jb < T; jb += kWarp) {
+                const uint32_t j = jb + lane;
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const uint32_t v = __shfl_sync(kFull, incl, lo + step - 1);
+                    if (v <= j) lo += step;
+                }
+                const int32_t nd_ = __shfl_sync(kFull, node, lo & 31);
+                if (j < T) out[placed + j] = nd_;
+            }
         }
         placed += T;
         if (placed == k && w == 0) {
@@ -557,6 +591,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
     view.gp = s.pair + g.sbase;
     view.gg = s.gpu + g.sbase;
     view.n_smem = g.ne < kFifoSmemSlots ? g.ne : kFifoSmemSlots;
+    view.all_smem = false;
     const uint32_t stage_bytes = (uint32_t)view.n_smem * (uint32_t)sizeof(longlong2);
     if (tid == 0) { mbar_init(&sh.bar, 1); sh.first_live_e = 0; sh.first_live_d = 0; sh.cmd_app = -1; sh.cmd_seq = 0; }
     const GroupMin gm = gmins[grp];
@@ -601,6 +636,8 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
     bool ident = true;
     for (int32_t j = tid; j < g.nd; j += nt) ident = ident && (s.drv_slot[g.dbase + j] == j);
     const bool drv_identity = __syncthreads_and(ident) != 0;
+    // identical orders and a group that fits the staging area: no slot outside shared memory is ever touched
+    view.all_smem = drv_identity && g.ne <= kFifoSmemSlots;
 
     if (stage_bytes != 0) mbar_wait(&sh.bar, 0);
     __syncthreads();
@@ -618,6 +655,8 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
         unsigned long long escalated = 0;
         ShapeCursors dcur, ecur;
         dcur.init(); ecur.init();
+        FifoViewS view_s;
+        view_s.sp = view.sp; view_s.gg = view.gg;
         // software pipeline: the record of application t+1 (one coalesced 128-byte load, lane w keeps word w) and the index of
         // application t+2 are in flight while application t is decided
         int32_t app = my_cnt > 0 ? (mine ? mine[0] : 0) : 0;
@@ -656,8 +695,10 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
                             start_d = min(g.nd, start_d + kWarp);
                         }
                     }
-                    int32_t r = (fl & kAppFast) ? fifo_app_warp<ALGO, FIFO_MODE>(s, g, view, pa, executor_nodes, cache, start_e, start_d, dcur, ecur, st, drv_identity, lane)
-                                                : kEscalate;
+                    int32_t r = kEscalate;                         // general arithmetic class: the CTA decides
+                    if (fl & kAppFast)
+                        r = view.all_smem ? fifo_app_warp<ALGO, FIFO_MODE>(s, g, view_s, pa, executor_nodes, cache, start_e, start_d, dcur, ecur, st, true, lane)
+                                          : fifo_app_warp<ALGO, FIFO_MODE>(s, g, view, pa, executor_nodes, cache, start_e, start_d, dcur, ecur, st, drv_identity, lane);
                     if (r == kEscalate) {
                         ++escalated;
                         if (lane == 0) { sh.first_live_e = start_e; sh.first_live_d = start_d; sh.cmd_app = app; sh.cmd_seq = seq; }

@@ -707,14 +707,15 @@ class MultiGangPacker:
         q = len(apps["count"])
         count = _np(apps["count"], np.int32)
         off = _np(apps.get("off"), np.int64)
-        if off is None:
+        derive = not wire.get("offsets", True)
+        if off is None and not (derive and out is not None):      # hot path (caller's buffers, device-derived offsets): no host cumsum
             off = np.zeros(q + 1, np.int64)
             np.cumsum(np.maximum(count, 0), out=off[1:])
         bits = int(wire.get("quantity_bits", 64))
         qdt = np.int64 if bits == 64 else np.int32
         arrs = {k: _np(apps.get(k), qdt) for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}
         grp, young = _np(apps.get("group"), np.int32), _np(apps.get("young"), np.uint8)
-        total = int(off[-1]) if q else 0
+        total = (int(off[-1]) if q else 0) if off is not None else len(out[1])
         node_bits = int(wire.get("node_bits", 32))
         if out is None:
             driver_node = np.full(q, -9, np.int32)
@@ -725,7 +726,7 @@ class MultiGangPacker:
                          drv_cpu=_p(arrs["drv_cpu"]), drv_mem=_p(arrs["drv_mem"]), drv_gpu=_p(arrs["drv_gpu"]),
                          exe_cpu=_p(arrs["exe_cpu"]), exe_mem=_p(arrs["exe_mem"]), exe_gpu=_p(arrs["exe_gpu"]),
                          exe_count=_p(count), group=_p(grp), skip_if_no_fit=_p(young),
-                         exec_out_off=_p(off) if wire.get("offsets", True) else None)
+                         exec_out_off=None if derive else _p(off))
         r = gp_results_wire(driver_node=_p(driver_node), executor_nodes=_p(executor_nodes),
                             executor_nodes_cap=len(executor_nodes), node_bits=node_bits)
         self._check(load().gp_multi_pack_batch(self._h, C.byref(a), algo, mode, C.byref(r)))
