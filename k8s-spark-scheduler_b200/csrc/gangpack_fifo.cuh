@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
     for (int32_t j = tid; j < g.nd; j += nt) ident = ident && (s.drv_slot[g.dbase + j] == j);
     const bool drv_identity = __syncthreads_and(ident) != 0;
     // identical orders and a group that fits the staging area: no slot outside shared memory is ever touched
-    view.all_smem = drv_identity && g.ne <= kFifoSmemSlots;
+    view.all_smem = drv_identity && g.nd <= g.ne && g.ne <= kFifoSmemSlots;     // (nd > ne: spare driver-only slots live in global memory)
 
     if (stage_bytes != 0) mbar_wait(&sh.bar, 0);
     __syncthreads();
@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
                         r = run_block(app, seq);
                         __syncwarp();
                         start_e = sh.first_live_e; start_d = sh.first_live_d;
+                        __syncwarp();                              // every lane has read them before lane 0 writes them again
                     }
                     d = r;
                     ++seq;
