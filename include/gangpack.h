@@ -349,6 +349,16 @@ typedef struct {
     double* avg_efficiency;          /* [n_apps][4] = AvgPackingEfficiency{CPU, Memory, GPU, Max} of the winner, or NULL */
 } gp_zone_results;
 gp_status gp_pack_batch_zones(gp_ctx* ctx, const gp_apps* apps /* group, skip_if_no_fit ignored */, gp_algo algo, gp_zone_results* out);
+/* The FIFO loop with a single-AZ packer in ONE launch: fitEarlierDrivers (internal/extender/resource.go:224-262) when
+ * binpacker.BinpackFunc is SingleAZTightlyPack / SingleAZMinimalFragmentation.  The applications are the queue in order;
+ * each one is packed in every zone against the availability its predecessors left, the zone is chosen like above, the
+ * winner's usage is subtracted (mode GP_MODE_FIFO_REFERENCE: sparkResourceUsage's map assignment, sparkpods.go:139-146;
+ * GP_MODE_FIFO_EXACT: every pod) and the next application sees it.  An application that fits in no zone gets zone -1,
+ * driver_node -1 and -- unless skip_if_no_fit[i] -- blocks the queue: everything behind it reports driver_node -2
+ * (never evaluated, resource.go:244-253).  The availability the device holds afterwards is what the loop left (read it
+ * with gp_get_snapshot).  At most 64 zones; exec_out_off must be NULL or the prefix sum of exe_count.
+ * ("az-aware-tightly-pack" needs the undivided orders for its fallback and stays a per-driver call sequence.) */
+gp_status gp_pack_fifo_zones(gp_ctx* ctx, const gp_apps* apps /* group ignored */, gp_algo algo, gp_mode mode, gp_zone_results* out);
 
 /* ---- reservation table of a batch + a snapshot that stays on the device ---------------
  * gp_reserve_placements: newResourceReservation (internal/extender/resourcereservations.go:491-528) for every application

@@ -6,6 +6,7 @@
 #include "gangpack_minfrag.cuh"
 #include "gangpack_tables.cuh"
 #include "gangpack_zones.cuh"
+#include "gangpack_zonefifo.cuh"
 #include "gangpack_resched.cuh"
 #include "gangpack_sort.cuh"
 
@@ -1470,6 +1471,96 @@ static gp_status refresh_views(gp_ctx* c, bool raised, cudaStream_t st) {
     gp_fill_pair32<<<(c->n_slots + T) / T, T, 0, st>>>(c->n_slots, c->pair.as<longlong2>(), meta, c->pair32.as<uint2>());
     GP_CUDA(c, cudaGetLastError());
     return GP_OK;
+}
+
+// the FIFO loop with a single-AZ packer in one launch (gangpack_zonefifo.cuh)
+gp_status gp_pack_fifo_zones(gp_ctx* c, const gp_apps* a, gp_algo algo, gp_mode mode, gp_zone_results* out) {
+    if (!c) return GP_ERR_INVALID;
+    if (!c->have_snapshot) return fail(c, GP_ERR_NO_SNAPSHOT, "gp_pack_fifo_zones: gp_set_snapshot first");
+    if (!c->have_sched) return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: gp_set_schedulable first (the efficiencies need SchedulableResources)");
+    if (!a || !out || a->n_apps < 0) return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: NULL apps/results");
+    if (algo != GP_TIGHTLY_PACK && algo != GP_MINIMAL_FRAGMENTATION)
+        return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: the single-AZ packers are tightly-pack and minimal-fragmentation");
+    if (mode != GP_MODE_FIFO_REFERENCE && mode != GP_MODE_FIFO_EXACT)
+        return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: mode must be one of the FIFO modes (independent decisions: gp_pack_batch_zones)");
+    const int32_t Q = a->n_apps, Z = c->n_groups;
+    if (Z > kZoneFifoMaxZones) return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: more than 64 zones");
+    if (Q == 0) return GP_OK;
+    if (!a->drv_cpu_milli || !a->drv_mem_bytes || !a->exe_cpu_milli || !a->exe_mem_bytes || !a->exe_count || !out->zone || !out->driver_node)
+        return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: missing app/result arrays");
+    std::vector<int64_t>& hoff = c->host_off;
+    hoff.resize((size_t)Q + 1);
+    int64_t acc = 0, pitch = 1;
+    for (int32_t i = 0; i < Q; ++i) {
+        const int64_t k = a->exe_count[i] > 0 ? a->exe_count[i] : 0;
+        hoff[(size_t)i] = acc; acc += k;
+        if (k > pitch) pitch = k;
+    }
+    hoff[(size_t)Q] = acc;
+    if (a->exec_out_off)
+        for (int32_t i = 0; i <= Q; ++i)
+            if (a->exec_out_off[i] != hoff[(size_t)i]) return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: exec_out_off must be the prefix sum of exe_count (or NULL)");
+    const int64_t total = acc;
+    if (total > out->executor_nodes_cap) return fail(c, GP_ERR_CAPACITY, "gp_pack_fifo_zones: executor_nodes_cap too small");
+    if (total > 0 && !out->executor_nodes) return fail(c, GP_ERR_INVALID, "gp_pack_fifo_zones: executor_nodes is NULL");
+    pitch = (pitch + 3) & ~(int64_t)3;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t q = (size_t)Q, T = (size_t)total, RP = (size_t)Z * (size_t)pitch;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t o_in = take(48 * q), o_cnt = take(4 * q), o_off = take(8 * (q + 1)), o_skip = take(q), o_rexe = take(4 * RP),
+                 o_rlist = take(algo == GP_MINIMAL_FRAGMENTATION ? 8 * RP : 0), o_zone = take(4 * q), o_drv = take(4 * q),
+                 o_exe = take(4 * (T + 1)), o_avg = take(32 * q);
+    GP_CUDA(c, c->zonebuf.reserve(o));
+    char* b = c->zonebuf.as<char>();
+    int2* unused = nullptr;
+    gp_status s = pack_begin(c, Q, GP_TIGHTLY_PACK, mode, total, false, &unused, st);
+    if (s != GP_OK) return s;
+    const int64_t* hc[6] = {a->drv_cpu_milli, a->drv_mem_bytes, a->drv_gpu, a->exe_cpu_milli, a->exe_mem_bytes, a->exe_gpu};
+    AppColumns cols{};
+    for (int k = 0; k < 6; ++k) {
+        if (!hc[k]) continue;
+        GP_CUDA(c, cudaMemcpyAsync(b + o_in + 8 * q * (size_t)k, hc[k], 8 * q, cudaMemcpyHostToDevice, st));
+        cols.q[k] = b + o_in + 8 * q * (size_t)k;
+    }
+    GP_CUDA(c, cudaMemcpyAsync(b + o_cnt, a->exe_count, 4 * q, cudaMemcpyHostToDevice, st));
+    GP_CUDA(c, cudaMemcpyAsync(b + o_off, hoff.data(), 8 * (q + 1), cudaMemcpyHostToDevice, st));
+    if (a->skip_if_no_fit) GP_CUDA(c, cudaMemcpyAsync(b + o_skip, a->skip_if_no_fit, q, cudaMemcpyHostToDevice, st));
+    cols.count = (const int32_t*)(b + o_cnt); cols.group = nullptr; cols.off = (const int64_t*)(b + o_off); cols.bits = 64; cols.mem_shift = 0;
+    int* d_err = c->dev_misc.as<int>();
+    volatile int* err_host = reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48);
+    unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(c->dev_misc.as<char>() + 8);
+    PrepApp* prep = c->prep.as<PrepApp>();
+    gp_prep_apps<<<(Q + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(
+        Q, cols, a->skip_if_no_fit ? (const uint8_t*)(b + o_skip) : nullptr, c->n_groups, total, c->snap_flags.as<SnapMeta>(), nullptr, prep, d_err, err_host);
+    Snapshot snap = make_snapshot(c);
+    ZoneFifoIn zi{};
+    const size_t N = (size_t)c->n_nodes;
+    zi.sched[0] = c->sched.as<long long>(); zi.sched[1] = c->sched.as<long long>() + N; zi.sched[2] = c->sched.as<long long>() + 2 * N;
+    zi.node_slot = c->node_slot.as<int32_t>();
+    zi.row_exec = (int32_t*)(b + o_rexe);
+    zi.row_list = algo == GP_MINIMAL_FRAGMENTATION ? (int2*)(b + o_rlist) : nullptr;
+    zi.row_pitch = pitch; zi.n_apps = Q; zi.n_zones = Z;
+    double* avg = out->avg_efficiency ? (double*)(b + o_avg) : nullptr;
+    int32_t* zo = (int32_t*)(b + o_zone); int32_t* dq = (int32_t*)(b + o_drv); int32_t* eo = (int32_t*)(b + o_exe);
+    if (algo == GP_TIGHTLY_PACK) {
+        if (mode == GP_MODE_FIFO_REFERENCE) gp_pack_fifo_zones_cta<0, 1><<<1, kZoneFifoThreads, 0, st>>>(snap, prep, zi, zo, dq, eo, avg, d_stats);
+        else gp_pack_fifo_zones_cta<0, 2><<<1, kZoneFifoThreads, 0, st>>>(snap, prep, zi, zo, dq, eo, avg, d_stats);
+    } else {
+        if (mode == GP_MODE_FIFO_REFERENCE) gp_pack_fifo_zones_cta<2, 1><<<1, kZoneFifoThreads, 0, st>>>(snap, prep, zi, zo, dq, eo, avg, d_stats);
+        else gp_pack_fifo_zones_cta<2, 2><<<1, kZoneFifoThreads, 0, st>>>(snap, prep, zi, zo, dq, eo, avg, d_stats);
+    }
+    GP_CUDA(c, cudaGetLastError());
+    c->last.kernel_launches += 2;
+    s = refresh_views(c, false, st);                   // the compact view follows the charged slots
+    if (s != GP_OK) return s;
+    GP_CUDA(c, cudaMemcpyAsync(out->zone, zo, 4 * q, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaMemcpyAsync(out->driver_node, dq, 4 * q, cudaMemcpyDeviceToHost, st));
+    if (T) GP_CUDA(c, cudaMemcpyAsync(out->executor_nodes, eo, 4 * T, cudaMemcpyDeviceToHost, st));
+    if (avg) GP_CUDA(c, cudaMemcpyAsync(out->avg_efficiency, avg, 32 * q, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(c, cudaStreamSynchronize(st));
+    return decode_device_error(c, *reinterpret_cast<volatile int*>(static_cast<char*>(c->pinned_misc) + 48));
 }
 
 gp_status gp_reserve_placements(gp_ctx* c, const gp_apps* a, const gp_results* placed, int32_t subtract, gp_reservation_table* out) {

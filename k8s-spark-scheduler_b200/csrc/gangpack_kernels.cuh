@@ -330,22 +330,26 @@ constexpr int kCapCache = 1024;   // per-warp shared-memory cache of phase-1 cap
 // gangpack_fifo.cuh).  Returns the driver's node index (>= 0) or -1.
 // ALGO: 0 tightly-pack, 1 distribute-evenly.  wcache: this warp's kCapCache x uint16 scratch in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, bool FAST, bool NOGPU, bool C32, class OUT>
+// MUT: the snapshot changes inside the launch (zone-aware FIFO, gangpack_zones.cuh): coherent loads, never with C32 (the
+// compact view is not kept current).  grp_override / out_override: pack against another instance group than pa->group and
+// write ExecutorNodes (and the candidate list) at another offset than pa->out_off.
+template <int ALGO, bool FAST, bool NOGPU, bool C32, class OUT, bool MUT = false>
 __device__ __forceinline__ int32_t pack_app_impl(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  OUT* __restrict__ executor_nodes, int2* __restrict__ scratch,
                                                  uint16_t* __restrict__ wcache, WarpStats& st, int lane,
-                                                 int snap_flags, const GroupDesc& g0) {
-    constexpr bool MUT = false;   // read-only path (ld.global.nc)
+                                                 int snap_flags, const GroupDesc& g0,
+                                                 int32_t grp_override = -1, int64_t out_override = -1) {
+    static_assert(!(MUT && C32), "the compact view is read-only");
     Caps<FAST> a;
     a.init(pa, (pa->flags & kAppUsesGpu) || (snap_flags & kSnapGpuNegative));
     const bool ug = NOGPU ? false : a.use_gpu;      // compile-time false on the hot instantiation
     if (C32) a.init32(s.meta);
-    const int32_t grp = pa->group;
+    const int32_t grp = grp_override >= 0 ? grp_override : pa->group;
     const GroupDesc g = grp == 0 ? g0 : s.groups[grp];   // group 0's descriptor is kept in registers by the caller
     const uint32_t k = a.k;
     const uint32_t lmax = (uint32_t)pa->lmax;
     const int32_t ne = g.ne;
-    const int64_t out_off = pa->out_off;
+    const int64_t out_off = out_override >= 0 ? out_override : pa->out_off;
     OUT* out = executor_nodes + out_off;
     int2* list = scratch ? scratch + out_off : nullptr;   // distribute-evenly candidate list
     const bool cache_ok = k <= 0xFFFFu;

@@ -42,20 +42,22 @@ __device__ __forceinline__ uint64_t cap_dim_u(int64_t a, const DimDiv& p) {
 }
 
 // ---- capacity providers: cap0(i) = unclamped capacity of executor candidate i with nothing reserved -------------
-struct MfCapGeneral {            // any int64 request, gpu dimension on demand
+template <bool MUT>
+struct MfCapGeneralT {           // any int64 request, gpu dimension on demand; MUT: the snapshot changes inside the launch
     typedef uint64_t T;
     DimDiv cpu, mem, gpu;
     const longlong2* pair;       // group base applied
     const int64_t* gpuv;
     bool ug;
     __device__ __forceinline__ T cap(int32_t i, int64_t rc, int64_t rm, int64_t rg) const {
-        const longlong2 v = __ldg(pair + i);
+        const longlong2 v = load_pair<MUT>(pair + i);
         T c = min(cap_dim_u(v.x - rc, cpu), cap_dim_u(v.y - rm, mem));
-        if (ug) c = min(c, cap_dim_u(__ldg(gpuv + i) - rg, gpu));
+        if (ug) c = min(c, cap_dim_u(load_gpu<MUT>(gpuv + i) - rg, gpu));
         return c;
     }
     __device__ __forceinline__ T cap0(int32_t i) const { return cap(i, 0, 0, 0); }
 };
+typedef MfCapGeneralT<false> MfCapGeneral;
 struct MfCapFast32 {             // fast class, gpu idle, compact 32-bit view: capacities < 2^32
     typedef uint32_t T;
     uint32_t mc_lo, mc_hi, mm_lo, mm_hi, shc, shm;
@@ -211,21 +213,23 @@ __device__ __forceinline__ void minfrag_emit(const CP& cp, int32_t ne, int32_t d
 }
 
 // One application (GP_MODE_INDEPENDENT).  Returns the driver's node index or -1.
-template <bool FAST32>
+// MUT / grp_override / out_override: see pack_app_impl (gangpack_kernels.cuh)
+template <bool FAST32, bool MUT = false>
 __device__ __noinline__ int32_t pack_app_minfrag(const Snapshot& s, const PrepApp* __restrict__ pa,
                                                  int32_t* __restrict__ executor_nodes, int2* __restrict__ scratch,
-                                                 WarpStats& st, int lane, int snap_flags) {
-    constexpr bool MUT = false;
+                                                 WarpStats& st, int lane, int snap_flags,
+                                                 int32_t grp_override = -1, int64_t out_override = -1) {
+    static_assert(!(MUT && FAST32), "the compact view is read-only");
     Caps<false> a;
     a.init(pa, (pa->flags & kAppUsesGpu) || (snap_flags & kSnapGpuNegative));
     const bool ug = a.use_gpu;
-    const GroupDesc g = s.groups[pa->group];
+    const GroupDesc g = s.groups[grp_override >= 0 ? grp_override : pa->group];
     const uint32_t k = a.k;
     const uint32_t lmax = (uint32_t)pa->lmax;
     const int32_t ne = g.ne;
-    const int64_t out_off = pa->out_off;
+    const int64_t out_off = out_override >= 0 ? out_override : pa->out_off;
 
-    MfCapGeneral cg;
+    MfCapGeneralT<MUT> cg;
     cg.cpu = a.cpu; cg.mem = a.mem; cg.gpu = a.gpu; cg.ug = ug;
     cg.pair = s.pair + g.sbase; cg.gpuv = s.gpu + g.sbase;
     MfCapFast32 cf;

@@ -38,17 +38,63 @@ __device__ __forceinline__ long long cpu_value(long long milli) {       // Quant
 }
 __device__ __forceinline__ long long normalize_resource(long long v) { return v == 0 ? 1 : v; }       // efficiency.go:104-109
 
-// computePackingEfficiency (efficiency.go:79-102) for node n with `r*` reserved on it; returns max(GPU, max(CPU, Memory))
-// and the three components
-__device__ __forceinline__ double node_efficiency(const ZoneChooseIn& in, int32_t n, long long rc, long long rm, long long rg,
-                                                  double& cpu, double& mem, double& gpu, bool& has_gpu) {
-    const long long sc = in.sched[0][n], sm = in.sched[1][n], sg = in.sched[2] ? in.sched[2][n] : 0;
-    const long long uc = sc - in.avail[0][n] + rc, um = sm - in.avail[1][n] + rm, ug = sg - in.avail[2][n] + rg;
+// computePackingEfficiency (efficiency.go:79-102) for a node with SchedulableResources (sc, sm, sg), AvailableResources
+// (ac, am, ag) and `r*` reserved on it; returns max(GPU, max(CPU, Memory)) and the three components
+__device__ __forceinline__ double node_efficiency_values(long long sc, long long sm, long long sg, long long ac, long long am, long long ag,
+                                                         long long rc, long long rm, long long rg,
+                                                         double& cpu, double& mem, double& gpu, bool& has_gpu) {
+    const long long uc = sc - ac + rc, um = sm - am + rm, ug = sg - ag + rg;
     has_gpu = sg != 0;
     gpu = has_gpu ? (double)ug / (double)normalize_resource(sg) : 0.0;
     cpu = (double)cpu_value(uc) / (double)normalize_resource(cpu_value(sc));
     mem = (double)um / (double)normalize_resource(sm);
     return fmax(gpu, fmax(cpu, mem));
+}
+
+// availability in node-table order (an immutable copy: independent batches)
+struct NodeTableAvail {
+    const long long* a[3];
+    __device__ __forceinline__ void load(int32_t n, long long& c, long long& m, long long& g) const { c = a[0][n]; m = a[1][n]; g = a[2][n]; }
+};
+
+// ComputeAvgPackingEfficiency (efficiency.go:111-156) over [driver] + ExecutorNodes of ONE packing result, walked
+// sequentially by the calling thread in the reference's order (duplicates kept) so the float64 sums round like the Go loop.
+// AV: where the current AvailableResources of a node come from.
+template <class AV>
+__device__ __forceinline__ void zone_row_average(const AV& av, const long long* const* sched, int32_t d, const int32_t* ex, int32_t k,
+                                                 long long dc, long long dm, long long dg, long long ec, long long em, long long eg,
+                                                 bool executors_reserved, double* a4) {
+    auto eff = [&](int32_t n, long long rc, long long rm, long long rg, double& c, double& m, double& g, bool& hg) {
+        long long ac, am, ag;
+        av.load(n, ac, am, ag);
+        return node_efficiency_values(sched[0][n], sched[1][n], sched[2] ? sched[2][n] : 0, ac, am, ag, rc, rm, rg, c, m, g, hg);
+    };
+    // executors on the driver's node (reserved[driver] = driver + its executors, binpack.go:72-75 + pack_tightly.go:50)
+    long long on_driver = 0;
+    if (executors_reserved) for (int32_t t = 0; t < k; ++t) on_driver += ex[t] == d ? 1 : 0;
+    double cpuSum = 0.0, memSum = 0.0, gpuSum = 0.0, maxSum = 0.0, c, m, g;
+    int nodesWithGPU = 0;
+    bool hg;
+    double mx = eff(d, dc + on_driver * ec, dm + on_driver * em, dg + on_driver * eg, c, m, g, hg);
+    cpuSum += c; memSum += m; if (hg) { gpuSum += g; nodesWithGPU++; } maxSum += mx;
+    int32_t t = 0;
+    while (t < k) {
+        const int32_t n = ex[t];
+        // executors of this placement on node n (ExecutorNodes may list a node in several runs: count them all)
+        long long cnt = 0;
+        if (executors_reserved) for (int32_t u = 0; u < k; ++u) cnt += ex[u] == n ? 1 : 0;
+        const long long isd = n == d ? 1 : 0;
+        mx = eff(n, isd * dc + cnt * ec, isd * dm + cnt * em, isd * dg + cnt * eg, c, m, g, hg);
+        // every entry of the run adds the same efficiency again (ComputeAvgPackingEfficiency loops over entries)
+        int32_t run = 1;
+        while (t + run < k && ex[t + run] == n) ++run;
+        for (int32_t u = 0; u < run; ++u) { cpuSum += c; memSum += m; if (hg) { gpuSum += g; nodesWithGPU++; } maxSum += mx; }
+        t += run;
+    }
+    const double length = fmax((double)(k + 1), 1.0);
+    a4[0] = cpuSum / length; a4[1] = memSum / length;
+    a4[2] = nodesWithGPU == 0 ? 1.0 : gpuSum / (double)nodesWithGPU;
+    a4[3] = maxSum / length;
 }
 
 __global__ void __launch_bounds__(256) gp_zone_choose(ZoneChooseIn in, int32_t* __restrict__ zone_out, int32_t* __restrict__ driver_out,
@@ -61,6 +107,8 @@ __global__ void __launch_bounds__(256) gp_zone_choose(ZoneChooseIn in, int32_t* 
     const int64_t base = (int64_t)Z * in.out_off[app];
     const long long dc = in.drv[0][app], dm = in.drv[1][app], dg = in.drv[2] ? in.drv[2][app] : 0;
     const long long ec = in.exe[0][app], em = in.exe[1][app], eg = in.exe[2] ? in.exe[2][app] : 0;
+    NodeTableAvail av;
+    av.a[0] = in.avail[0]; av.a[1] = in.avail[1]; av.a[2] = in.avail[2];
     double best = 0.0;                 // WorstAvgPackingEfficiency().Max
     int32_t best_z = -1;
     double best4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -72,33 +120,7 @@ __global__ void __launch_bounds__(256) gp_zone_choose(ZoneChooseIn in, int32_t* 
             const int32_t d = in.row_driver[(int64_t)app * Z + z];
             if (d >= 0) {
                 fits = true;
-                const int32_t* ex = in.row_exec + base + (int64_t)z * k;
-                // executors on the driver's node (reserved[driver] = driver + its executors, binpack.go:72-75 + pack_tightly.go:50)
-                long long on_driver = 0;
-                if (in.executors_reserved) for (int32_t t = 0; t < k; ++t) on_driver += ex[t] == d ? 1 : 0;
-                double cpuSum = 0.0, memSum = 0.0, gpuSum = 0.0, maxSum = 0.0, c, m, g;
-                int nodesWithGPU = 0;
-                bool hg;
-                double mx = node_efficiency(in, d, dc + on_driver * ec, dm + on_driver * em, dg + on_driver * eg, c, m, g, hg);
-                cpuSum += c; memSum += m; if (hg) { gpuSum += g; nodesWithGPU++; } maxSum += mx;
-                int32_t t = 0;
-                while (t < k) {
-                    const int32_t n = ex[t];
-                    // executors of this placement on node n (ExecutorNodes may list a node in several runs: count them all)
-                    long long cnt = 0;
-                    if (in.executors_reserved) for (int32_t u = 0; u < k; ++u) cnt += ex[u] == n ? 1 : 0;
-                    const long long isd = n == d ? 1 : 0;
-                    mx = node_efficiency(in, n, isd * dc + cnt * ec, isd * dm + cnt * em, isd * dg + cnt * eg, c, m, g, hg);
-                    // every entry of the run adds the same efficiency again (ComputeAvgPackingEfficiency loops over entries)
-                    int32_t run = 1;
-                    while (t + run < k && ex[t + run] == n) ++run;
-                    for (int32_t u = 0; u < run; ++u) { cpuSum += c; memSum += m; if (hg) { gpuSum += g; nodesWithGPU++; } maxSum += mx; }
-                    t += run;
-                }
-                const double length = fmax((double)(k + 1), 1.0);
-                a4[0] = cpuSum / length; a4[1] = memSum / length;
-                a4[2] = nodesWithGPU == 0 ? 1.0 : gpuSum / (double)nodesWithGPU;
-                a4[3] = maxSum / length;
+                zone_row_average(av, in.sched, d, in.row_exec + base + (int64_t)z * k, k, dc, dm, dg, ec, em, eg, in.executors_reserved != 0, a4);
                 avg_max = a4[3];
             }
         }

@@ -181,6 +181,15 @@ public:
         n.drv_off = doff.data(); n.drv_order = drv_.data();
         check(gp_set_snapshot(ctx_, &n), "gp_set_snapshot");
     }
+    // NodeSchedulingMetadata.SchedulableResources of the interned nodes (the packing efficiencies read them)
+    void SetSchedulable(const resources::NodeGroupSchedulingMetadata& md) {
+        std::vector<int64_t> c(names_.size()), m(names_.size()), g(names_.size());
+        for (size_t i = 0; i < names_.size(); ++i) {
+            const auto& s = md.at(names_[i]).SchedulableResources;
+            c[i] = s.CPU; m[i] = s.Memory; g[i] = s.NvidiaGPU;
+        }
+        check(gp_set_schedulable(ctx_, c.data(), m.data(), g.data()), "gp_set_schedulable");
+    }
     const std::string& name(int32_t i) const { return names_.at((size_t)i); }
     size_t n_nodes() const { return names_.size(); }
     int32_t index(const std::string& n) const { auto it = index_.find(n); return it == index_.end() ? -1 : it->second; }
@@ -613,9 +622,69 @@ inline bool FitEarlierDrivers(const binpacker::Binpacker& packer, const std::vec
         if (!drivers[i].ParseError) live.push_back(i);
     if (results) results->assign(drivers.size(), binpack::EmptyPackingResult());
     if (live.empty()) return true;
+    if (packer.IsSingleAz) {
+        // single-AZ packers: the whole queue in ONE launch (gp_pack_fifo_zones) -- zone = instance group, the zone choice of
+        // driver i feeds driver i+1 on the device
+        std::vector<std::string> dzOrder, ezOrder;
+        std::unordered_map<std::string, std::vector<std::string>> dz, ez;
+        binpack::groupNodesByZone(nodeNames, metadata, &dzOrder, &dz);
+        binpack::groupNodesByZone(executorNodeNames, metadata, &ezOrder, &ez);
+        std::vector<std::pair<std::vector<std::string>, std::vector<std::string>>> groups;
+        for (const auto& z : dzOrder)
+            if (ez.count(z)) groups.emplace_back(dz[z], ez[z]);                 // single_az.go:36-41
+        const size_t q = live.size();
+        if (groups.empty()) {                                                   // EmptyPackingResult for every driver
+            for (size_t j = 0; j < q; ++j) if (!drivers[live[j]].SkipIfNoFit) return false;
+            return true;
+        }
+        gangpack::Device& d = gangpack::Device::Get();
+        d.SetSnapshotGroups(metadata, groups);
+        d.SetSchedulable(metadata);
+        std::vector<int64_t> dc(q), dm(q), dg(q), ec(q), em(q), eg(q);
+        std::vector<int32_t> cnt(q), zone(q, -1), driver(q, -1);
+        std::vector<uint8_t> skip(q);
+        int64_t total = 0;
+        for (size_t j = 0; j < q; ++j) {
+            const auto& a = drivers[live[j]];
+            dc[j] = a.Resources.DriverResources.CPU; dm[j] = a.Resources.DriverResources.Memory; dg[j] = a.Resources.DriverResources.NvidiaGPU;
+            ec[j] = a.Resources.ExecutorResources.CPU; em[j] = a.Resources.ExecutorResources.Memory; eg[j] = a.Resources.ExecutorResources.NvidiaGPU;
+            cnt[j] = a.Resources.MinExecutorCount;
+            skip[j] = a.SkipIfNoFit ? 1 : 0;
+            total += std::max(cnt[j], 0);
+        }
+        std::vector<int32_t> exec((size_t)std::max<int64_t>(total, 1));
+        gp_apps a{};
+        a.n_apps = (int32_t)q;
+        a.drv_cpu_milli = dc.data(); a.drv_mem_bytes = dm.data(); a.drv_gpu = dg.data();
+        a.exe_cpu_milli = ec.data(); a.exe_mem_bytes = em.data(); a.exe_gpu = eg.data();
+        a.exe_count = cnt.data(); a.skip_if_no_fit = skip.data();
+        gp_zone_results r{};
+        r.zone = zone.data(); r.driver_node = driver.data(); r.executor_nodes = exec.data(); r.executor_nodes_cap = (int64_t)exec.size();
+        d.check(gp_pack_fifo_zones(d.ctx(), &a, (gp_algo)packer.algo, GP_MODE_FIFO_REFERENCE, &r), "gp_pack_fifo_zones");
+        std::vector<int64_t> cpu(d.n_nodes()), mem(d.n_nodes()), gpu(d.n_nodes());
+        d.check(gp_get_snapshot(d.ctx(), cpu.data(), mem.data(), gpu.data()), "gp_get_snapshot");
+        for (size_t i = 0; i < d.n_nodes(); ++i) {
+            auto& m = metadata.at(d.name((int32_t)i)).AvailableResources;
+            m.CPU = cpu[i]; m.Memory = mem[i]; m.NvidiaGPU = gpu[i];
+        }
+        bool ok = true;
+        int64_t at = 0;
+        for (size_t j = 0; j < q; ++j) {
+            if (driver[j] == -2 || (driver[j] == -1 && !skip[j])) ok = false;   // :250-252
+            if (results && driver[j] >= 0) {
+                auto& pr = (*results)[live[j]];
+                pr.HasCapacity = true;
+                pr.DriverNode = d.name(driver[j]);
+                for (int64_t t = 0; t < std::max(cnt[j], 0); ++t) pr.ExecutorNodes.push_back(d.name(exec[(size_t)(at + t)]));
+            }
+            at += std::max(cnt[j], 0);
+        }
+        return ok;
+    }
     if (binpacker::NeedsHostLoop(packer)) {
-        // zone-aware packers: the reference's own loop (:230-259), every BinpackFunc call being one device batch over
-        // the zones; usage is subtracted on the host between calls (SubtractUsageIfExists, resources.go:129-135)
+        // az-aware-tightly-pack: the reference's own loop (:230-259), every BinpackFunc call being one device batch over
+        // the zones (+ the undivided fallback); usage is subtracted on the host between calls (SubtractUsageIfExists,
+        // resources.go:129-135)
         for (size_t i : live) {
             const auto& a = drivers[i];
             binpack::PackingResult pr = packer.BinpackFunc(a.Resources.DriverResources, a.Resources.ExecutorResources,

@@ -35,7 +35,7 @@ STATUS_NAMES = {0: "GP_OK", 1: "GP_ERR_INVALID", 2: "GP_ERR_CUDA", 3: "GP_ERR_NO
 
 # every symbol include/gangpack.h declares (tests assert the .so exports exactly these)
 EXPORTS = ["gp_abi_version", "gp_create", "gp_destroy", "gp_last_error", "gp_backend", "gp_alloc_pinned",
-           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one", "gp_set_schedulable", "gp_pack_batch_zones", "gp_reserve_placements", "gp_apply_usage_delta",
+           "gp_free_pinned", "gp_register_host", "gp_unregister_host", "gp_set_snapshot", "gp_get_snapshot", "gp_pack_batch", "gp_pack_batch_wire", "gp_pack_one", "gp_set_schedulable", "gp_pack_batch_zones", "gp_pack_fifo_zones", "gp_reserve_placements", "gp_apply_usage_delta",
            "gp_set_snapshot_device", "gp_pack_batch_device", "gp_stream", "gp_synchronize", "gp_last_stats",
            "gp_potential_nodes", "gp_build_availability", "gp_build_reschedule_availability", "gp_prepare_cluster", "gp_reschedule_executors",
            "gp_multi_create", "gp_multi_destroy", "gp_multi_last_error", "gp_multi_size", "gp_multi_ctx",
@@ -183,6 +183,8 @@ def load():
     L.gp_set_schedulable.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gp_pack_batch_zones.restype = C.c_int
     L.gp_pack_batch_zones.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.POINTER(gp_zone_results)]
+    L.gp_pack_fifo_zones.restype = C.c_int
+    L.gp_pack_fifo_zones.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.c_int, C.c_int, C.POINTER(gp_zone_results)]
     L.gp_reserve_placements.restype = C.c_int
     L.gp_reserve_placements.argtypes = [C.c_void_p, C.POINTER(gp_apps), C.POINTER(gp_results), C.c_int32, C.POINTER(gp_reservation_table)]
     L.gp_apply_usage_delta.restype = C.c_int
@@ -518,6 +520,25 @@ class GangPacker:
                     exe_count=_p(count), group=None, skip_if_no_fit=None, exec_out_off=_p(off))
         r = gp_zone_results(zone=_p(zone), driver_node=_p(drv), executor_nodes=_p(exe), executor_nodes_cap=len(exe), avg_efficiency=_p(avg))
         self._check(load().gp_pack_batch_zones(self._h, C.byref(a), algo, C.byref(r)))
+        return zone, drv, exe[:total], off, avg[:q]
+
+    def pack_fifo_zones(self, apps: dict, algo: int, mode: int = 1):
+        """fitEarlierDrivers with a single-AZ packer in one launch: `apps` is the queue in order (optional "young" = skip the
+        driver instead of blocking the queue when it fits nowhere).  -> like pack_batch_zones; driver_node -2 = never evaluated."""
+        q = len(apps["count"])
+        count = _np(apps["count"], np.int32)
+        off = np.zeros(q + 1, np.int64)
+        np.cumsum(np.maximum(count, 0), out=off[1:])
+        arrs = {k: _np(apps.get(k), np.int64) for k in ("drv_cpu", "drv_mem", "drv_gpu", "exe_cpu", "exe_mem", "exe_gpu")}
+        young = _np(apps.get("young"), np.uint8)
+        total = int(off[-1]) if q else 0
+        zone = np.full(q, -9, np.int32); drv = np.full(q, -9, np.int32)
+        exe = np.full(max(total, 1), -9, np.int32); avg = np.zeros((max(q, 1), 4), np.float64)
+        a = gp_apps(n_apps=q, drv_cpu_milli=_p(arrs["drv_cpu"]), drv_mem_bytes=_p(arrs["drv_mem"]), drv_gpu=_p(arrs["drv_gpu"]),
+                    exe_cpu_milli=_p(arrs["exe_cpu"]), exe_mem_bytes=_p(arrs["exe_mem"]), exe_gpu=_p(arrs["exe_gpu"]),
+                    exe_count=_p(count), group=None, skip_if_no_fit=_p(young), exec_out_off=_p(off))
+        r = gp_zone_results(zone=_p(zone), driver_node=_p(drv), executor_nodes=_p(exe), executor_nodes_cap=len(exe), avg_efficiency=_p(avg))
+        self._check(load().gp_pack_fifo_zones(self._h, C.byref(a), algo, mode, C.byref(r)))
         return zone, drv, exe[:total], off, avg[:q]
 
     def reserve_placements(self, apps: dict, placed, subtract=True):

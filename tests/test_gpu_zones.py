@@ -74,6 +74,84 @@ def test_single_az_packers_vs_literal(oracle, packer, seed):
         assert (zone[wd < 0] == -1).all()
 
 
+def _fifo_zone_case(rng, seed, n, Z, q, tight):
+    cpu, mem, gpu = random_cluster(rng, n, tight=tight, gpus=bool(seed % 3 == 0))
+    sc = cpu + rng.integers(0, 9, n) * 250 + (rng.integers(0, 3, n) == 0) * 1
+    sm = mem + rng.integers(0, 17, n) * (1 << 28)
+    sg = np.maximum(gpu, 0) + (rng.integers(0, 2, n) if seed % 3 == 0 else 0)
+    zone_of = rng.integers(0, Z, n)
+    order_e = [int(i) for i in rng.permutation(n) if rng.random() < 0.9]
+    order_d = [int(i) for i in rng.permutation(n)[: max(1, int(n * 0.7))]]
+    apps = random_apps(rng, q, gpus=bool(seed % 3 == 0), zero_dims=bool(seed == 5))
+    apps["young"] = (rng.random(q) < (0.97 if seed % 2 else 1.0)).astype(np.uint8)      # odd seeds: the queue may block
+    return cpu, mem, gpu, sc, sm, sg, zone_of, order_d, order_e, apps
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fifo_with_single_az_packers_vs_literal(oracle, packer, seed):
+    """gp_pack_fifo_zones = fitEarlierDrivers (resource.go:224-262) with SingleAZTightlyPack / SingleAZMinimalFragmentation as
+    BinpackFunc, one launch for the whole queue: zone choice, placements, blocking and the availability left behind must equal
+    the literal restatement's loop (which packs every zone, compares the float64 averages and subtracts the winner's usage
+    per driver), in both accounting modes."""
+    rng = np.random.default_rng(4100 + seed)
+    n = int(rng.integers(40, 200)); Z = int(rng.integers(1, 6)); q = 220
+    cpu, mem, gpu, sc, sm, sg, zone_of, order_d, order_e, apps = _fifo_zone_case(rng, seed, n, Z, q, tight=bool(seed % 2))
+    names = node_names(n)
+    labels = ["zone-%d" % z for z in zone_of]
+    zones, eo, do, eoff, doff = _zone_groups(order_d, order_e, zone_of)
+    if not zones:
+        return
+    drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"]); exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+    for algo, oalgo in ((0, 2), (2, 5)):
+        for mode in (1, 2):
+            cl = oracle.Cluster(names, cpu, mem, gpu, sched=(sc, sm, sg), zone=labels)
+            blocked, wd, we, woff = cl.fifo(oalgo, mode, drv, exe, apps["count"], apps["young"], [names[i] for i in order_d],
+                                            [names[i] for i in order_e], with_efficiencies=True)
+            packer.set_snapshot(cpu, mem, gpu, eo, do, eoff, doff)
+            packer.set_schedulable(sc, sm, sg)
+            zone, gd, ge, goff, avg = packer.pack_fifo_zones(apps, algo, mode)
+            assert np.array_equal(goff, woff)
+            bad = np.nonzero(gd != wd)[0]
+            assert bad.size == 0, (seed, algo, mode, bad[:5], gd[bad[:5]], wd[bad[:5]], blocked)
+            for i in np.nonzero(wd >= 0)[0]:
+                assert np.array_equal(ge[goff[i]:goff[i + 1]], we[woff[i]:woff[i + 1]]), (seed, algo, mode, i)
+                assert zone[i] == zones.index(zone_of[wd[i]])
+            assert (zone[wd < 0] == -1).all()
+            fc, fm, fg = packer.get_snapshot()
+            wc, wm, wg = cl.available()
+            assert np.array_equal(fc, wc) and np.array_equal(fm, wm) and np.array_equal(fg, wg), (seed, algo, mode)
+    # the device keeps the availability the loop left: an independent zone batch right after sees it
+    zone2, gd2, ge2, goff2, _ = packer.pack_batch_zones(apps, 0)
+    wd2, we2, woff2 = cl.binpack_batch(2, drv, exe, apps["count"], [names[i] for i in order_d], [names[i] for i in order_e], with_efficiencies=True)
+    # (cl holds the state of the last loop: minimal-fragmentation, exact accounting -- the same the device just ran)
+    assert np.array_equal(gd2, wd2)
+
+
+def test_fifo_zones_blocks_and_rejects(oracle, packer, gangpack):
+    """A driver that fits in no zone and is not young stops the queue (-2 behind it, resource.go:244-253); wrong modes /
+    packers are refused."""
+    n = 12
+    cpu = np.full(n, 8000, np.int64); mem = np.full(n, 32 << 30, np.int64); gpu = np.zeros(n, np.int64)
+    zone_of = np.arange(n) % 3
+    order = list(range(n))
+    zones, eo, do, eoff, doff = _zone_groups(order, order, zone_of)
+    packer.set_snapshot(cpu, mem, gpu, eo, do, eoff, doff)
+    packer.set_schedulable(cpu, mem, gpu)
+    apps = {"drv_cpu": np.array([1000, 1000, 1000, 1000], np.int64), "drv_mem": np.full(4, 1 << 30, np.int64), "drv_gpu": np.zeros(4, np.int64),
+            "exe_cpu": np.array([2000, 4000, 2000, 2000], np.int64), "exe_mem": np.full(4, 2 << 30, np.int64), "exe_gpu": np.zeros(4, np.int64),
+            "count": np.array([3, 40, 2, 2], np.int32), "young": np.array([0, 1, 0, 0], np.uint8)}
+    zone, gd, ge, goff, _ = packer.pack_fifo_zones(apps, 0, 1)
+    assert gd[0] >= 0 and gd[1] == -1 and gd[2] >= 0 and gd[3] >= 0          # the young driver is skipped
+    apps["young"][1] = 0
+    packer.set_snapshot(cpu, mem, gpu, eo, do, eoff, doff)
+    zone, gd, ge, goff, _ = packer.pack_fifo_zones(apps, 0, 1)
+    assert gd[0] >= 0 and list(gd[1:]) == [-1, -2, -2] and list(zone[1:]) == [-1, -1, -1]
+    with pytest.raises(gangpack.native.GangpackError):
+        packer.pack_fifo_zones(apps, 1, 1)                                      # distribute-evenly has no single-AZ form
+    with pytest.raises(gangpack.native.GangpackError):
+        packer.pack_fifo_zones(apps, 0, 0)                                      # independent decisions: gp_pack_batch_zones
+
+
 def test_zones_after_fifo_sees_charged_availability(oracle, packer):
     """The efficiencies read the availability the FIFO batch left behind (node-table copy refreshed from the slots)."""
     rng = np.random.default_rng(9)

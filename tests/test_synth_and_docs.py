@@ -56,6 +56,6 @@ def test_integration_doc_covers_every_entry_point():
     missing = [s for s in declared if s not in doc and s not in ("gp_abi_version",)]
     assert not missing, missing
     design = open(os.path.join(ROOT, "DESIGN.md")).read()
-    for kernel in ("gp_prep_apps", "gp_pack_independent", "gp_pack_fifo_cta", "gp_potential_nodes", "gp_build_availability",
+    for kernel in ("gp_prep_apps", "gp_pack_independent", "gp_pack_fifo_cta", "gp_pack_fifo_zones_cta", "gp_potential_nodes", "gp_build_availability",
                    "gp_classify_apps", "gp_build_shape_tables", "gp_decide_tables", "gp_pack_listed", "gp_zone_choose", "gp_sort_tiles"):
         assert kernel in design, kernel
