@@ -616,11 +616,17 @@ def main():
         print(json.dumps(line), flush=True)
 
     # ---- orderly teardown: the driver's exit hook must see this process with libgangpack.so mapped -------
+    # Everything torch used on the library's stream (device tensors, the pinned snapshot copy -- torch's host allocator
+    # records an event on that stream when the block is freed) and every view into the shared segment goes BEFORE gp_destroy.
     torch.cuda.synchronize()
     del graph, evs
     del snapbuf, tn, ta, d_driver, d_exec, flush
+    h_snap = e2e_step = rd = sums = mine_sum = t = None
     pin = pn = out_driver = out_exec = None
     call_pack = call_snapshot = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     packer.close()                                    # frees pinned blocks, unregisters the shared segment, gp_destroy
     if shm is not None:
         shm.close()
