@@ -643,6 +643,9 @@ __global__ void __launch_bounds__(kFifoThreads, 1) gp_pack_fifo_cta(Snapshot s, 
     __syncthreads();
 
     auto run_block = [&](int32_t app, uint32_t seq) -> int32_t {       // every thread of the CTA
+        // every helper has read the command word before warp 0 can post the next one, also when fifo_app() leaves
+        // without a block-wide barrier of its own (racecheck: cmd_app written while a late helper still read it)
+        __syncthreads();
         const PrepApp* pa = prep + app;
         return (pa->flags & kAppFast) ? fifo_app<ALGO, FIFO_MODE, true>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, seq)
                                       : fifo_app<ALGO, FIFO_MODE, false>(s, g, view, pa, executor_nodes, scratch, cache, sh, buf, st, gm, seq);

@@ -144,6 +144,7 @@ def test_fifo_zones_blocks_and_rejects(oracle, packer, gangpack):
     assert gd[0] >= 0 and gd[1] == -1 and gd[2] >= 0 and gd[3] >= 0          # the young driver is skipped
     apps["young"][1] = 0
     packer.set_snapshot(cpu, mem, gpu, eo, do, eoff, doff)
+    packer.set_schedulable(cpu, mem, gpu)                                      # a new snapshot drops the schedulable resources
     zone, gd, ge, goff, _ = packer.pack_fifo_zones(apps, 0, 1)
     assert gd[0] >= 0 and list(gd[1:]) == [-1, -2, -2] and list(zone[1:]) == [-1, -1, -1]
     with pytest.raises(gangpack.native.GangpackError):
