@@ -77,10 +77,14 @@ def test_deep_workload_all_apps(oracle, packer, algo):
     assert_same_results(got, want, f"deep closed algo {algo}")
     nofit = float((want[0] < 0).mean())
     assert 0.05 < nofit < 0.95, nofit          # the workload really mixes fitting and non-fitting gangs
-    sl = {k: v[:1500] for k, v in a.items()}
-    lit = literal_batch(oracle, algo, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order, sl, n_threads=16)
+    # the literal restatement pays the reference's O(driver candidates x executor nodes) for every gang that fits nowhere
+    # (~0.1 s per application and core here): a 240-application slice keeps the suite inside a few minutes
+    L = 240
+    sl = {k: v[:L] for k, v in a.items()}
+    lit = literal_batch(oracle, algo, nodes["avail_cpu"], nodes["avail_mem"], nodes["avail_gpu"], order, order, sl, n_threads=32)
     off = got[2]
-    assert_same_results((got[0][:1500], got[1][:off[1500]], off[:1501]), lit, f"deep literal slice algo {algo}")
+    assert (lit[0] < 0).any() and (lit[0] >= 0).any()
+    assert_same_results((got[0][:L], got[1][:off[L]], off[:L + 1]), lit, f"deep literal slice algo {algo}")
 
 
 def test_fifo_then_independent_pack_sees_charged_snapshot(oracle, packer):
