@@ -8,6 +8,8 @@ import sys
 def row(path):
     d = json.loads(open(path).read().strip().splitlines()[-1])
     name = os.path.basename(path)[6:-5]
+    if d.get("impl") == "reference":
+        return "| %s (CPU arm) | %.3g (%.1f ms per step) | - | - | - | - | %s | - |" % (name, d["value"], d["ms_per_step"], d["cpu_baseline"]["kind"])
     r = d.get("roofline") or {}
     cpu = d.get("cpu_baseline") or {}
     e = d["e2e"]
