@@ -909,10 +909,13 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
         const size_t hdr_bytes = 1024 + (sizeof(ShapeEntry) + sizeof(DriverEntry)) * (size_t)kShapeSlots;
         const bool use_tables = c->use_tables && q >= 32;
         GP_CUDA(c, T.hdr.reserve(hdr_bytes));
-        GP_CUDA(c, T.app_slot.reserve(sizeof(int32_t) * 3 * (size_t)q));          // [executor slot | driver slot | listed]
+        // [executor slot | driver slot | listed | block sums of the executor counts (K0)]
+        const size_t slot_words = (3 * (size_t)q + 1) & ~(size_t)1;             // keeps the block sums 8-byte aligned
+        const size_t n_blocks = ((size_t)q + kClassifyThreads - 1) / kClassifyThreads;
+        GP_CUDA(c, T.app_slot.reserve(sizeof(int32_t) * slot_words + sizeof(unsigned long long) * (n_blocks + 1)));
         if (use_tables) {
             GP_CUDA(c, T.table.reserve(sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)((c->n_slots + 4) & ~3)));
-            GP_CUDA(c, T.total.reserve(2 * sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)c->n_groups));
+            GP_CUDA(c, T.total.reserve(3 * sizeof(uint32_t) * (size_t)kMaxShapes * (size_t)c->n_groups));   // total | firstfit | first_host
         }
         ShapeTables tabs;
         tabs.hdr = T.hdr.as<ShapeHeader>();
@@ -920,6 +923,7 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
         tabs.dentries = reinterpret_cast<DriverEntry*>(T.hdr.as<char>() + 1024 + sizeof(ShapeEntry) * (size_t)kShapeSlots);
         tabs.table = T.table.as<uint32_t>(); tabs.total = T.total.as<uint32_t>();
         tabs.firstfit = reinterpret_cast<int32_t*>(T.total.as<uint32_t>() + (size_t)kMaxShapes * (size_t)c->n_groups);
+        tabs.first_host = tabs.firstfit + (size_t)kMaxShapes * (size_t)c->n_groups;
         tabs.pitch = (c->n_slots + 4) & ~3; tabs.n_groups = c->n_groups;      // rows start 16-byte aligned
         int64_t* off_out = nullptr;
         if (!da.cols.off) {                       // derive the offsets on the device
@@ -936,8 +940,13 @@ static gp_status pack_device_range(gp_ctx* c, const DevApps& da, int32_t lo, int
             GP_CUDA(c, cudaMemsetAsync(T.hdr.p, 0, use_tables ? hdr_bytes : 1024, st));
             if (c->record_events) GP_CUDA(c, cudaEventRecord(c->ev[chunk][0], st));
             if (use_tables || off_out) {
-                gp_classify_apps<<<(q + kClassifyThreads - 1) / kClassifyThreads, kClassifyThreads, 0, st>>>(
-                    q, cols, tabs, c->snap_flags.as<SnapMeta>(), off_base, off_out, app_slot, use_tables ? 1 : 0);
+                unsigned long long* block_sums = reinterpret_cast<unsigned long long*>(app_slot + slot_words);
+                if (off_out) {
+                    gp_count_blocks<<<(unsigned)n_blocks, kClassifyThreads, 0, st>>>(q, cols.count, block_sums);
+                    c->last.kernel_launches += 1;
+                }
+                gp_classify_apps<<<(unsigned)n_blocks, kClassifyThreads, 0, st>>>(
+                    q, cols, tabs, c->snap_flags.as<SnapMeta>(), off_base, off_out, block_sums, app_slot, use_tables ? 1 : 0);
                 c->last.kernel_launches += 1;
             }
             gp_status r;

@@ -25,8 +25,9 @@
 //                         application, right for an O(N) scan, would idle 31 lanes): feasibility is
 //                         S[ne] - delta(d) >= k  per driver candidate d starting at the shape's first fit (delta = what the
 //                         driver displaces on its own node: O(1) per candidate, the reference's loop binpack.go:67-85
-//                         verbatim), the first hosting node is found by binary search of the prefix table, ExecutorNodes
-//                         is emitted by walking the table from there (zero-capacity runs are jumped by binary search).
+//                         verbatim), the walk starts at the shape's first hosting node (one word per (shape, group), written
+//                         by K2), ExecutorNodes is emitted by walking the table from there with the next word always in
+//                         flight (zero-capacity runs are jumped by a galloping search).
 // What the tables cannot answer exactly -- more than kMaxShapes distinct shapes in a batch, executor counts above the table
 // clamp, distribute-evenly placements that need more than one round -- is appended, already prepared (PrepApp), to a list
 // that the warp-per-application scan kernel gp_pack_listed (the node-order scan of gangpack_kernels.cuh) works off.
@@ -80,6 +81,7 @@ struct ShapeTables {
     uint32_t* table;                  // [kMaxShapes][pitch] exclusive prefix per instance group, indexed by slot
     uint32_t* total;                  // [kMaxShapes][n_groups]
     int32_t* firstfit;                // [kMaxShapes][n_groups] first driver-order position the driver shape fits on (nd: none)
+    int32_t* first_host;              // [kMaxShapes][n_groups] first executor-order position with capacity > 0 for the shape (ne: none)
     int32_t pitch;                    // row length (>= n_slots, multiple of 4)
     int32_t n_groups;
 };
@@ -121,22 +123,63 @@ struct AppColumns {
 // K1: intern executor shapes, derive offsets
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kClassifyThreads = 256;
+
+// K0: executor counts per block of kClassifyThreads applications (the offsets K1 derives are an exclusive prefix sum: every
+// CTA of K1 adds up the <= n/256 block sums before its own block instead of re-reading every count before it -- the
+// redundant form moved q^2/512 words through L2)
+__global__ void __launch_bounds__(kClassifyThreads) gp_count_blocks(int32_t n_apps, const int32_t* __restrict__ count,
+                                                                    unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long s_part[kClassifyThreads / 32];
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int32_t c = i < n_apps ? count[i] : 0;
+    unsigned long long v = c > 0 ? (unsigned long long)c : 0ull;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+    if (lane == 0) s_part[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < kClassifyThreads / 32; ++k) t += s_part[k];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// intern one request tuple (fingerprint fp) into the open-addressing table of ENTRY records; returns the slot or -1.
+// `init(entry, slot)` fills a freshly claimed entry.  Called by ONE lane per distinct fingerprint of a warp.
+template <class ENTRY, class INIT>
+__device__ __forceinline__ int32_t intern_shape(ENTRY* table, unsigned long long fp, INIT init) {
+    int32_t slot = (int32_t)(fp & (kShapeSlots - 1));
+    for (int p = 0; p < kShapeProbes; ++p) {
+        ENTRY* en = table + slot;
+        // plain (L1-cacheable) load: a key never changes once set, and a stale 0 is resolved by the CAS below
+        unsigned long long cur = en->key;
+        if (cur == 0) {
+            cur = atomicCAS(&en->key, 0ull, fp);
+            if (cur == 0) { init(en, slot); cur = fp; }
+        }
+        if (cur == fp) return slot;
+        slot = (slot + 1) & (kShapeSlots - 1);
+    }
+    return -1;
+}
+
 __global__ void __launch_bounds__(kClassifyThreads) gp_classify_apps(int32_t n_apps, AppColumns cols, ShapeTables tabs,
                                                                      const SnapMeta* __restrict__ meta,
                                                                      int64_t off_base, int64_t* __restrict__ off_out /* or NULL */,
+                                                                     const unsigned long long* __restrict__ block_sums /* with off_out */,
                                                                      int32_t* __restrict__ app_slot, int use_tables) {
     __shared__ unsigned long long s_part[kClassifyThreads / 32];
     const int32_t block0 = blockIdx.x * blockDim.x;
     const int32_t i = block0 + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
-    // ---- ExecutorNodes offsets = exclusive prefix sum of max(count, 0), when the caller passed none.  Each CTA sums
-    // the counts before its own block itself (L2-resident, <= n_apps loads per CTA): no inter-CTA dependency.
+    // ---- ExecutorNodes offsets = exclusive prefix sum of max(count, 0), when the caller passed none: the block sums of
+    // K0 before this block + a block-wide scan of this block's counts (no inter-CTA dependency inside this launch)
     if (off_out) {
         unsigned long long before = 0;
-        for (int32_t t = threadIdx.x; t < block0; t += blockDim.x) { const int32_t c = cols.count[t]; before += c > 0 ? (unsigned)c : 0u; }
+        for (int32_t t = threadIdx.x; t < (int32_t)blockIdx.x; t += blockDim.x) before += block_sums[t];
         const int32_t mine = (i < n_apps) ? max(cols.count[i], 0) : 0;
-        // block reduce of `before`, block exclusive scan of `mine`
         unsigned long long wb = before;
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) wb += __shfl_xor_sync(kFull, wb, d);
@@ -151,66 +194,54 @@ __global__ void __launch_bounds__(kClassifyThreads) gp_classify_apps(int32_t n_a
         if (i == n_apps - 1) off_out[n_apps] = (int64_t)(base + prev + incl);
         __syncthreads();
     }
+    const unsigned act = __ballot_sync(kFull, i < n_apps);     // the lanes that intern (the whole warp except in the last block)
     if (i >= n_apps) return;
     if (!use_tables) { app_slot[i] = -1; return; }
 
+    // A queue has few distinct requests: the lanes of a warp that carry the same fingerprint elect ONE of them to probe /
+    // claim the entry (100 000 threads doing their own CAS on a dozen lines serialise on those lines); the consumer
+    // verifies the full tuple, so a fingerprint collision inside a warp only sends an application to the scan.
     const int64_t e0 = cols.load(3, i), e1 = cols.load(4, i), e2 = cols.load(5, i);
-    int32_t found = -1;
-    if (e0 >= 0 && e1 >= 0 && e2 >= 0 && e0 < kMaxQuantity && e1 < kMaxQuantity && e2 < kMaxQuantity) {
-        const unsigned long long fp = shape_fingerprint(e0, e1, e2);
-        int32_t slot = (int32_t)(fp & (kShapeSlots - 1));
-        for (int p = 0; p < kShapeProbes && found < 0; ++p) {
-            ShapeEntry* en = tabs.entries + slot;
-            // plain (L1-cacheable) load: a key never changes once set, and a stale 0 is resolved by the CAS below --
-            // 100 000 threads polling a dozen L2 lines with volatile loads serialise on those lines
-            unsigned long long cur = en->key;
-            if (cur == 0) {
-                cur = atomicCAS(&en->key, 0ull, fp);
-                if (cur == 0) {
-                    // this thread owns the entry: dense id, division recipes (verified by every consumer against its own tuple)
-                    int32_t id = atomicAdd(&tabs.hdr->n_shapes, 1);
-                    if (id >= kMaxShapes) id = -1;
-                    int bad = 0; uint64_t l; bool fast = true;
-                    en->div[0] = prep_dim(0, e0, 0, meta->max_avail[0], bad, l, fast);
-                    en->div[1] = prep_dim(0, e1, 1, meta->max_avail[1], bad, l, fast);
-                    en->div[2] = prep_dim(0, e2, 2, meta->max_avail[2], bad, l, fast);
-                    en->flags = e2 != 0 ? 1u : 0u;
-                    en->id = id;
-                    if (id >= 0) tabs.hdr->id_slot[id] = slot;
-                    cur = fp;
-                }
-            }
-            if (cur == fp) found = slot;
-            slot = (slot + 1) & (kShapeSlots - 1);
-        }
+    const bool e_ok = e0 >= 0 && e1 >= 0 && e2 >= 0 && e0 < kMaxQuantity && e1 < kMaxQuantity && e2 < kMaxQuantity;
+    const unsigned long long efp = e_ok ? shape_fingerprint(e0, e1, e2) : 0ull;
+    {
+        const unsigned same = __match_any_sync(act, efp);
+        const int leader = __ffs(same) - 1;
+        int32_t found = -1;
+        if (lane == leader && e_ok)
+            found = intern_shape(tabs.entries, efp, [&](ShapeEntry* en, int32_t slot) {
+                // this lane owns the entry: dense id, division recipes (verified by every consumer against its own tuple)
+                int32_t id = atomicAdd(&tabs.hdr->n_shapes, 1);
+                if (id >= kMaxShapes) id = -1;
+                int bad = 0; uint64_t l; bool fast = true;
+                en->div[0] = prep_dim(0, e0, 0, meta->max_avail[0], bad, l, fast);
+                en->div[1] = prep_dim(0, e1, 1, meta->max_avail[1], bad, l, fast);
+                en->div[2] = prep_dim(0, e2, 2, meta->max_avail[2], bad, l, fast);
+                en->flags = e2 != 0 ? 1u : 0u;
+                en->id = id;
+                if (id >= 0) tabs.hdr->id_slot[id] = slot;
+            });
+        app_slot[i] = __shfl_sync(act, found, leader);
     }
-    app_slot[i] = found;
 
     // ---- the driver request, interned the same way: its first fitting candidate is searched once per shape (K2d) ----
     const int64_t d0 = cols.load(0, i), d1 = cols.load(1, i), d2 = cols.load(2, i);
-    int32_t dfound = -1;
-    if (d0 >= 0 && d1 >= 0 && d2 >= 0 && d0 < kMaxQuantity && d1 < kMaxQuantity && d2 < kMaxQuantity) {
-        const unsigned long long fp = shape_fingerprint(d0 ^ 0x5bd1e995, d1, d2);
-        int32_t slot = (int32_t)(fp & (kShapeSlots - 1));
-        for (int p = 0; p < kShapeProbes && dfound < 0; ++p) {
-            DriverEntry* en = tabs.dentries + slot;
-            unsigned long long cur = en->key;
-            if (cur == 0) {
-                cur = atomicCAS(&en->key, 0ull, fp);
-                if (cur == 0) {
-                    int32_t id = atomicAdd(&tabs.hdr->n_dshapes, 1);
-                    if (id >= kMaxShapes) id = -1;
-                    en->d[0] = d0; en->d[1] = d1; en->d[2] = d2;
-                    en->id = id;
-                    if (id >= 0) tabs.hdr->did_slot[id] = slot;
-                    cur = fp;
-                }
-            }
-            if (cur == fp) dfound = slot;
-            slot = (slot + 1) & (kShapeSlots - 1);
-        }
+    const bool d_ok = d0 >= 0 && d1 >= 0 && d2 >= 0 && d0 < kMaxQuantity && d1 < kMaxQuantity && d2 < kMaxQuantity;
+    const unsigned long long dfp = d_ok ? shape_fingerprint(d0 ^ 0x5bd1e995, d1, d2) : 0ull;
+    {
+        const unsigned same = __match_any_sync(act, dfp);
+        const int leader = __ffs(same) - 1;
+        int32_t dfound = -1;
+        if (lane == leader && d_ok)
+            dfound = intern_shape(tabs.dentries, dfp, [&](DriverEntry* en, int32_t slot) {
+                int32_t id = atomicAdd(&tabs.hdr->n_dshapes, 1);
+                if (id >= kMaxShapes) id = -1;
+                en->d[0] = d0; en->d[1] = d1; en->d[2] = d2;
+                en->id = id;
+                if (id >= 0) tabs.hdr->did_slot[id] = slot;
+            });
+        app_slot[n_apps + i] = __shfl_sync(act, dfound, leader);         // second half of the array: driver-shape slots
     }
-    app_slot[n_apps + i] = dfound;         // second half of the array: driver-shape slots
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -219,6 +250,7 @@ __global__ void __launch_bounds__(kClassifyThreads) gp_classify_apps(int32_t n_a
 struct TabScratch {
     unsigned long long bar[2];
     uint32_t part[2][kTabThreads / 32];
+    int32_t first_host;
 };
 constexpr size_t kTabSmemBytes = 1024 + 2 * (size_t)kTabTile * sizeof(longlong2);      // 1 KB scratch + 2 x 64 KB tiles
 
@@ -246,7 +278,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) gp_build_shape_tables(Snapshot
     const int64_t* ggpu = s.gpu + g.sbase;
     uint32_t* out = tabs.table + (size_t)id * tabs.pitch + g.sbase;
 
-    if (tid == 0) { mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1); }
+    if (tid == 0) { mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1); sh.first_host = ne; }
     __syncthreads();
     const int n_tiles = (ne + kTabTile - 1) / kTabTile;
     auto issue = [&](int t) {          // thread 0: TMA bulk copies of tile t into buffer t & 1 (<= 32 KB per copy)
@@ -269,6 +301,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) gp_build_shape_tables(Snapshot
         const int32_t i0 = lo + tid * kTabPerThread;
         uint32_t v[kTabPerThread];
         uint32_t sum = 0;
+        int32_t my_first = 0x7fffffff;
 #pragma unroll
         for (int j = 0; j < kTabPerThread; ++j) {
             const int32_t i = i0 + j;
@@ -279,8 +312,14 @@ __global__ void __launch_bounds__(kTabThreads, 1) gp_build_shape_tables(Snapshot
                 if (ug) c = min(c, cap_dim(__ldg(ggpu + i), dg, clamp));
                 if (ALGO == 1) c = c != 0 ? 1u : 0u;
             }
+            if (c != 0 && i < my_first) my_first = i;
             v[j] = sum;             // exclusive within the thread
             sum += c;
+        }
+        // the first hosting node of the shape: every decision of the shape starts its walk there (no search per application)
+        {
+            const uint32_t wmin = __reduce_min_sync(kFull, (uint32_t)my_first);
+            if (lane == 0 && wmin != 0x7fffffffu) atomicMin(&sh.first_host, (int32_t)wmin);
         }
         // block-wide exclusive scan of the per-thread sums
         const uint32_t incl = warp_incl_scan(sum, lane);
@@ -300,7 +339,10 @@ __global__ void __launch_bounds__(kTabThreads, 1) gp_build_shape_tables(Snapshot
         carry += tile_total;
         __syncthreads();            // tile[t & 1] and part[t & 1] may be overwritten from here on
     }
-    if (tid == 0) tabs.total[(size_t)id * tabs.n_groups + grp] = carry;
+    if (tid == 0) {
+        tabs.total[(size_t)id * tabs.n_groups + grp] = carry;
+        tabs.first_host[(size_t)id * tabs.n_groups + grp] = sh.first_host;     // ordered by the barrier that ended the last tile
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -343,7 +385,16 @@ __device__ __forceinline__ uint32_t tab_at(const uint32_t* __restrict__ tab, int
 // smallest p in (lo, ne] with S(p) > val; requires S(ne) = total > val
 __device__ __forceinline__ int32_t tab_next_above(const uint32_t* __restrict__ tab, int32_t lo, int32_t ne, uint32_t total, uint32_t val,
                                                   unsigned long long& probes) {
-    int32_t a = lo + 1, b = ne;                     // answer in [a, b]
+    int32_t a = lo + 1, b = ne;                     // answer in [a, b], S(b) > val
+    // gallop first: the zero-capacity runs inside a walk are short (1-2 probes instead of log2(ne))
+    int32_t step = 1;
+    while (a < b) {
+        const int32_t t = a + step - 1 < b - 1 ? a + step - 1 : b - 1;      // t in [a, b-1]
+        ++probes;
+        if (tab_at(tab, t, ne, total) > val) { b = t; break; }             // answer in [a, t]
+        a = t + 1;                                                          // answer in [t+1, b]
+        step <<= 1;
+    }
     while (a < b) {
         const int32_t mid = (a + b) >> 1;
         if (tab_at(tab, mid, ne, total) > val) b = mid; else a = mid + 1;
@@ -453,10 +504,15 @@ __global__ void __launch_bounds__(kDecideThreads) gp_decide_tables(Snapshot s, A
                         const int32_t* slot_node = s.slot_node + g.sbase;
                         const int32_t dpos = (dslot < ne) ? dslot : 0x7fffffff;
                         (void)c0d;
-                        int32_t pos = tab_next_above(tab, 0, ne, total, 0u, probes) - 1;
+                        int32_t pos = __ldg(tabs.first_host + (size_t)en->id * tabs.n_groups + grp);    // first node with room for the shape
+                        ++probes;
                         uint32_t prev = 0, placed = 0;
+                        uint32_t nxt = tab_at(tab, pos + 1, ne, total);
+                        ++probes;
                         while (placed < k && pos < ne) {
-                            const uint32_t nxt = tab_at(tab, pos + 1, ne, total);
+                            // S(pos + 2) is requested before S(pos + 1) is consumed: the walk's dependent-load chain is
+                            // what bounds this kernel (one thread per application), so the next word is always in flight
+                            const uint32_t nxt2 = tab_at(tab, pos + 2, ne, total);
                             ++probes;
                             uint32_t c = nxt - prev;
                             if (pos == dpos) c = cd;
@@ -464,6 +520,8 @@ __global__ void __launch_bounds__(kDecideThreads) gp_decide_tables(Snapshot s, A
                                 if (nxt >= total) break;                // cannot happen for a feasible placement
                                 pos = tab_next_above(tab, pos + 1, ne, total, nxt, probes) - 1;
                                 prev = nxt;
+                                nxt = tab_at(tab, pos + 1, ne, total);
+                                ++probes;
                                 continue;
                             }
                             const uint32_t take = c < k - placed ? c : k - placed;
@@ -471,6 +529,7 @@ __global__ void __launch_bounds__(kDecideThreads) gp_decide_tables(Snapshot s, A
                             for (uint32_t t = 0; t < take; ++t) out[placed + t] = node;
                             placed += take;
                             prev = nxt;
+                            nxt = nxt2;
                             ++pos;
                         }
                     }
