@@ -94,6 +94,62 @@ def test_fifo_three_way(oracle, seed, mode):
                 assert meta[names[i]] == (lfinal[0][i], lfinal[1][i], lfinal[2][i])
 
 
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("mode", ["reference", "exact"])
+def test_fifo_with_zone_aware_packers_two_way(oracle, seed, mode):
+    """fitEarlierDrivers (resource.go:224-262) with the zone-aware packers as BinpackFunc: the literal C loop (orc_fifo over
+    single_az.go / az_aware_pack_tightly.go / single_az_minimal_fragmentation.go) against the pure-Python statement of the
+    same loop -- placements, blocking and the availability left behind.  This is the checker of gp_pack_fifo_zones."""
+    rng = np.random.default_rng(2600 + seed)
+    mode_id = {"reference": 1, "exact": 2}[mode]
+    fns = ((2, pyref.single_az_tightly_pack), (3, pyref.az_aware_tightly_pack), (5, pyref.single_az_minimal_fragmentation))
+    for trial in range(3):
+        n = int(rng.integers(6, 30))
+        names = ["node-%03d" % i for i in range(n)]
+        sched_cpu = rng.integers(2, 17, n) * 1000; sched_mem = rng.integers(2, 33, n) * (1 << 30); sched_gpu = rng.integers(0, 3, n) * (seed % 2)
+        cpu = (sched_cpu * rng.uniform(0.3, 1, n)).astype(np.int64) // 250 * 250
+        mem = (sched_mem * rng.uniform(0.3, 1, n)).astype(np.int64) // (1 << 28) * (1 << 28)
+        gpu = np.minimum(sched_gpu, rng.integers(0, 3, n))
+        zones = {nm: "z%d" % rng.integers(0, 3) for nm in names}
+        exec_idx, drv_idx = _orders(rng, n, names)
+        exec_names = [names[i] for i in exec_idx]; drv_names = [names[i] for i in drv_idx]
+        q = 24
+        apps = random_apps(rng, q, gpus=bool(seed % 2))
+        apps["count"] = np.minimum(apps["count"], 6).astype(np.int32)
+        young = (rng.random(q) < 0.8).astype(np.uint8)
+        drv = res_aos(apps["drv_cpu"], apps["drv_mem"], apps["drv_gpu"]); exe = res_aos(apps["exe_cpu"], apps["exe_mem"], apps["exe_gpu"])
+        sched = {names[i]: (int(sched_cpu[i]), int(sched_mem[i]), int(sched_gpu[i])) for i in range(n)}
+        for algo_id, fn in fns:
+            cl = oracle.Cluster(names, cpu, mem, gpu, sched=(sched_cpu, sched_mem, sched_gpu), zone=[zones[nm] for nm in names])
+            lb, ld, le, off = cl.fifo(algo_id, mode_id, drv, exe, apps["count"], young, drv_names, exec_names, with_efficiencies=True)
+            meta = {names[i]: (int(cpu[i]), int(mem[i]), int(gpu[i])) for i in range(n)}
+            blocked = -1
+            for i in range(q):
+                if blocked >= 0:
+                    assert ld[i] == -2, (seed, trial, algo_id, i)
+                    continue
+                d_req = tuple(int(x) for x in drv[i]); e_req = tuple(int(x) for x in exe[i])
+                d, ex, ok = fn(d_req, e_req, int(apps["count"][i]), drv_names, exec_names, meta, sched, zones)
+                if not ok:
+                    assert ld[i] == -1, (seed, trial, algo_id, i)
+                    if not young[i]:
+                        blocked = i
+                    continue
+                assert names[ld[i]] == d and [names[j] for j in le[off[i]:off[i + 1]]] == ex, (seed, trial, algo_id, i)
+                if mode == "reference":
+                    for nm, u in pyref.spark_resource_usage(d_req, e_req, d, ex).items():
+                        if nm in meta:
+                            meta[nm] = pyref.sub(meta[nm], u)
+                else:
+                    meta[d] = pyref.sub(meta[d], d_req)
+                    for nm in ex:
+                        meta[nm] = pyref.sub(meta[nm], e_req)
+            assert lb == blocked, (seed, trial, algo_id)
+            final = cl.available()
+            for i in range(n):
+                assert meta[names[i]] == (final[0][i], final[1][i], final[2][i]), (seed, trial, algo_id, names[i])
+
+
 def test_synthetic_workload_oracles_agree(oracle):
     """The bench workload shape at reduced size: literal (threaded) == closed form."""
     import k8s_spark_scheduler_b200.synth as synth
