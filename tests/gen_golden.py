@@ -328,6 +328,51 @@ def main():
     fifo_cases.append(fifo_case("F3-evenly-exact", "FIFO with distribute-evenly, exact accounting",
                                 v1_nodes, three, "distribute-evenly", "exact"))
 
+    # ---- FIFO loop with the zone-aware packers (fitEarlierDrivers calling single_az.go per queued driver) -------------
+    zone_fifo_cases = []
+    ZONE_FN = {"single-az-tightly-pack": pyref.single_az_tightly_pack, "az-aware-tightly-pack": pyref.az_aware_tightly_pack,
+               "single-az-minimal-fragmentation": pyref.single_az_minimal_fragmentation}
+
+    def zone_fifo_case(cid, source, node_list, zones, sched, apps, packer, mode):
+        names = [n["name"] for n in node_list]
+        meta = {n["name"]: (n["cpu"], n["mem"], n["gpu"]) for n in node_list}
+        fn = ZONE_FN[packer]
+        out, blocked = [], -1
+        for i, a in enumerate(apps):
+            if blocked >= 0:
+                out.append({"driver": "unevaluated", "executors": []})
+                continue
+            d, ex, ok = fn(tuple(a["drv"]), tuple(a["exe"]), a["count"], names, names, meta, sched, zones)
+            if not ok:
+                out.append({"driver": None, "executors": []})
+                if not a.get("young", False):
+                    blocked = i
+                continue
+            out.append({"driver": d, "executors": ex})
+            if mode == "reference":
+                for n, u in pyref.spark_resource_usage(tuple(a["drv"]), tuple(a["exe"]), d, ex).items():
+                    if n in meta:
+                        meta[n] = pyref.sub(meta[n], u)
+            else:
+                meta[d] = pyref.sub(meta[d], tuple(a["drv"]))
+                for n in ex:
+                    meta[n] = pyref.sub(meta[n], tuple(a["exe"]))
+        final = [{"name": n, "cpu": meta[n][0], "mem": meta[n][1], "gpu": meta[n][2]} for n in names]
+        return {"id": cid, "source": source, "nodes": node_list, "zones": zones,
+                "schedulable": [{"name": n, "cpu": sched[n][0], "mem": sched[n][1], "gpu": sched[n][2]} for n in names],
+                "apps": apps, "packer": packer, "mode": mode,
+                "expect": {"blocked": blocked, "results": out, "final_available": final}, "pinned": "derived"}
+
+    zqueue = [{**app_readme, "count": 3}, {**app_readme, "count": 2}, {**app_readme, "count": 12, "young": True},
+              {**app_readme, "count": 3}, {**app_readme, "count": 12}, {**app_readme, "count": 1}]
+    for packer in ZONE_FN:
+        for mode in ("reference", "exact"):
+            zone_fifo_cases.append(zone_fifo_case(
+                "ZF-%s-%s" % (packer, mode),
+                "derived: EXT/resource.go:224-262 with %s as BinpackFunc (LIB/binpack/single_az.go:23-97): the zone chosen for one "
+                "driver changes what the next one sees; a young driver that fits nowhere is skipped, an old one blocks the queue" % packer,
+                three_zone, tz, tsched, zqueue, packer, mode))
+
     # ---- node priority order (internal/sort) ------------------------------------------------------
     sort_cases = []
 
@@ -363,7 +408,7 @@ def main():
 
     out = {"_comment": "generated by tests/gen_golden.py -- do not edit by hand",
            "units": {"cpu": "millicores", "mem": "bytes", "gpu": "units"},
-           "pack_cases": cases, "zone_cases": zone_cases, "minfrag_cases": minfrag_cases, "resched_cases": resched_cases, "annotation_cases": annotation_cases, "queue_cases": queue_cases, "fifo_cases": fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
+           "pack_cases": cases, "zone_cases": zone_cases, "minfrag_cases": minfrag_cases, "resched_cases": resched_cases, "annotation_cases": annotation_cases, "queue_cases": queue_cases, "fifo_cases": fifo_cases, "zone_fifo_cases": zone_fifo_cases, "sort_cases": sort_cases, "label_cases": label_cases}
     path = os.path.join(ROOT, "tests", "golden", "hotpath_vectors.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:

@@ -98,6 +98,21 @@ def test_closed_oracle_fifo_cases(golden, oracle):
         _check_fifo(case, names, blocked, dn, en, off, final)
 
 
+def test_literal_oracle_zone_fifo_cases(golden, oracle):
+    """fitEarlierDrivers with the zone-aware packers (the checker of gp_pack_fifo_zones): the literal C loop reproduces the
+    committed fixture (generated by the pure-Python statement, tests/gen_golden.py)."""
+    packer_id = {"single-az-tightly-pack": 2, "az-aware-tightly-pack": 3, "single-az-minimal-fragmentation": 5}
+    assert len(golden["zone_fifo_cases"]) == 6
+    for case in golden["zone_fifo_cases"]:
+        names, cpu, mem, gpu, drv, exe, count, young = _fifo_inputs(case)
+        sched = {s["name"]: (s["cpu"], s["mem"], s["gpu"]) for s in case["schedulable"]}
+        sc = tuple(np.array([sched[n][k] for n in names], np.int64) for k in range(3))
+        cl = oracle.Cluster(names, cpu, mem, gpu, sched=sc, zone=[case["zones"].get(n, "default") for n in names])
+        blocked, dn, en, off = cl.fifo(packer_id[case["packer"]], MODE_ID[case["mode"]], drv, exe, count, young, names, names,
+                                       with_efficiencies=True)
+        _check_fifo(case, names, blocked, dn, en, off, cl.available())
+
+
 def test_node_priority_order_goldens(golden, oracle):
     """internal/sort/nodesorting_test.go:98-182 through PotentialNodes (all nodes are candidates)."""
     for case in golden["sort_cases"]:
